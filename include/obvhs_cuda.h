@@ -1,0 +1,179 @@
+/*
+ * obvhs_cuda.h -- C ABI of libobvhs_cuda (sm_100a), the B200-native drop-in for the data-parallel hot path of
+ * obvhs 0.3.1: PLOC BVH2 build -> parallel reinsertion -> BVH2->CWBVH collapse -> CWBVH ray traversal.
+ *
+ * The reference (pure Rust) has no FFI layer; each entry point below names the Rust interface it replaces
+ * (paths relative to the reference checkout). INTEGRATION.md shows the `extern "C"` block + safe wrappers a
+ * maintainer adds to obvhs to route these calls here.
+ *
+ * Conventions
+ *   - every call returns int: 0 = OBVHS_OK, <0 = ObvhsStatus error. Nothing throws across the boundary;
+ *     obvhs_cuda_last_error() returns a description of the last failure on that context.
+ *   - POD structs are byte-identical to the reference's #[repr(C)] Pod types (sizes static-asserted in the library).
+ *   - data pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes). Host buffers are staged
+ *     through the context's stream; device buffers are used in place.
+ *   - a context owns one CUDA stream (its own, or the caller's) and the reusable scratch of the builder
+ *     (the reference's PlocBuilder keeps current_nodes/next_nodes/mortons for reuse, ploc/mod.rs:35-45).
+ *     One context is thread-compatible; distinct contexts are independent.
+ *   - there is NO CPU fallback: without a CUDA device obvhs_cuda_create fails with OBVHS_ERR_CUDA.
+ */
+#ifndef OBVHS_CUDA_H
+#define OBVHS_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    OBVHS_OK = 0,
+    OBVHS_ERR_INVALID_ARG = -1,
+    OBVHS_ERR_CUDA = -2,
+    OBVHS_ERR_UNSUPPORTED = -3, /* pre_split presets, depth beyond the fixed stacks */
+    OBVHS_ERR_NAN_INPUT = -4,   /* the reference panics / goes out of bounds on NaN AABBs (ploc/mod.rs:451) */
+    OBVHS_ERR_STACK_OVERFLOW = -5
+} ObvhsStatus;
+
+/* src/aabb.rs:11-16 -- two Vec3A lanes; the 4th float of each lane is padding (never read, never compared). */
+typedef struct { float min[3]; float _pad0; float max[3]; float _pad1; } ObvhsAabb;
+/* src/triangle.rs:8-13 */
+typedef struct { float v0[3]; float _pad0; float v1[3]; float _pad1; float v2[3]; float _pad2; } ObvhsTriangle;
+/* src/bvh2/node.rs:40-66 (default 48-byte layout). prim_count == 0 => inner node, children at first_index, +1. */
+typedef struct { ObvhsAabb aabb; uint32_t prim_count; uint32_t first_index; uint32_t meta1; uint32_t meta2; } ObvhsBvh2Node;
+/* src/cwbvh/node.rs:12-54 -- 80 bytes, no padding */
+typedef struct {
+    float p[3];
+    uint8_t e[3];
+    uint8_t imask;
+    uint32_t child_base_idx;
+    uint32_t primitive_base_idx;
+    uint8_t child_meta[8];
+    uint8_t child_min_x[8], child_max_x[8], child_min_y[8], child_max_y[8], child_min_z[8], child_max_z[8];
+} ObvhsCwBvhNode;
+/* src/ray.rs:15-30 */
+typedef struct {
+    float origin[3]; float _pad0; float direction[3]; float _pad1; float inv_direction[3]; float _pad2;
+    float tmin, tmax; float _pad3[2];
+} ObvhsRay;
+/* src/ray.rs:63-70; RayHit::none() = ids 0xffffffff, t = +inf */
+typedef struct { uint32_t primitive_id, geometry_id, instance_id; float t; } ObvhsRayHit;
+
+/* src/lib.rs:208-231 BvhBuildParams, field for field. ploc_search_distance is the u32 form of PlocSearchDistance
+ * (ploc/mod.rs:534-562: 1,2,6,14,24,32); sort_precision is 64 or 128 (ploc/mod.rs:658-661). */
+typedef struct {
+    uint32_t pre_split; /* must be 0: spatial pre-splits (src/splits.rs) are outside this library's path */
+    uint32_t ploc_search_distance;
+    uint64_t search_depth_threshold;
+    float reinsertion_batch_ratio;
+    float post_collapse_reinsertion_batch_ratio_multiplier; /* Bvh2-only in the reference; ignored for CwBvh */
+    uint32_t sort_precision;
+    uint32_t max_prims_per_leaf; /* CwBvh builders clamp to 1..3 (cwbvh/builder.rs:74) */
+    float collapse_traversal_cost; /* Bvh2-only; ignored */
+} ObvhsBuildParams;
+
+typedef struct ObvhsContext ObvhsContext;
+typedef struct ObvhsBvh2 ObvhsBvh2;   /* device-resident Bvh2 (src/bvh2/mod.rs:31-85) */
+typedef struct ObvhsCwBvh ObvhsCwBvh; /* device-resident CwBvh (src/cwbvh/mod.rs:43-55) + optional permuted triangles */
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+/* stream: a cudaStream_t the caller owns, or NULL to let the context create one. */
+int obvhs_cuda_create(int device, void* stream, ObvhsContext** out);
+void obvhs_cuda_destroy(ObvhsContext* ctx);
+const char* obvhs_cuda_last_error(const ObvhsContext* ctx);
+int obvhs_cuda_synchronize(ObvhsContext* ctx);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx);
+/* 6 built-in presets of src/lib.rs:233-305 by name: fastest_build, very_fast_build, fast_build, medium_build,
+ * slow_build, very_slow_build. */
+int obvhs_cuda_build_params_preset(const char* name, ObvhsBuildParams* out);
+
+/* ---- PLOC (src/ploc/mod.rs) ----------------------------------------------------------------------------- */
+/* Stage probe for parity tests: leaf init + scene AABB (ploc/mod.rs:187-243), Morton codes (:287-288,782-785;
+ * morton.rs:35-89) in ORIGINAL order and the sorted order (:811-827, ties by ascending index). Any output may be
+ * NULL. precision 64: codes_hi is zero filled. */
+int obvhs_cuda_morton_sort(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, uint32_t sort_precision,
+                           uint64_t* codes_lo, uint64_t* codes_hi, uint32_t* order, ObvhsAabb* total_aabb);
+/* PlocBuilder::build(search_distance, aabbs, indices, sort_precision, search_depth_threshold) -> Bvh2
+ * (ploc/mod.rs:95-102). indices == NULL means 0..n. */
+int obvhs_cuda_ploc_build(ObvhsContext* ctx, const ObvhsAabb* aabbs, const uint32_t* indices, size_t n,
+                          uint32_t search_distance, uint32_t sort_precision, size_t search_depth_threshold,
+                          ObvhsBvh2** out);
+/* Same over &[Triangle] (Boundable for Triangle, triangle.rs:28-30): the AABB is computed inside leaf init. */
+int obvhs_cuda_ploc_build_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, uint32_t search_distance,
+                               uint32_t sort_precision, size_t search_depth_threshold, ObvhsBvh2** out);
+
+/* ---- Bvh2 (src/bvh2/mod.rs) ------------------------------------------------------------------------------ */
+void obvhs_cuda_bvh2_free(ObvhsBvh2* bvh);
+size_t obvhs_cuda_bvh2_node_count(const ObvhsBvh2* bvh);
+size_t obvhs_cuda_bvh2_prim_count(const ObvhsBvh2* bvh);
+size_t obvhs_cuda_bvh2_max_depth(const ObvhsBvh2* bvh);       /* Bvh2::max_depth, ploc/mod.rs:501 */
+size_t obvhs_cuda_bvh2_ploc_iterations(const ObvhsBvh2* bvh); /* `depth` at loop exit, ploc/mod.rs:327-493 */
+int obvhs_cuda_bvh2_children_ordered_after_parents(const ObvhsBvh2* bvh);
+/* nodes: node_count x 48 B; primitive_indices: prim_count x u32; parents: node_count x u32 (needs parents computed).
+ * Any may be NULL. */
+int obvhs_cuda_bvh2_download(ObvhsContext* ctx, const ObvhsBvh2* bvh, ObvhsBvh2Node* nodes, uint32_t* primitive_indices,
+                             uint32_t* parents);
+int obvhs_cuda_bvh2_upload(ObvhsContext* ctx, const ObvhsBvh2Node* nodes, size_t node_count,
+                           const uint32_t* primitive_indices, size_t prim_count, size_t max_depth,
+                           int children_ordered_after_parents, ObvhsBvh2** out);
+int obvhs_cuda_bvh2_compute_parents(ObvhsContext* ctx, ObvhsBvh2* bvh);                 /* bvh2/mod.rs:586-619 */
+int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh);                       /* bvh2/mod.rs:527-569 */
+/* rewrite every leaf's AABB from per-primitive AABBs (dynamic scenes, examples/physics.rs:500-539), then refit_all */
+int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* prim_aabbs, size_t n);
+
+/* ReinsertionOptimizer::run(&mut bvh, batch_size_ratio, ratio_sequence) (bvh2/reinsertion.rs:40-57,92-111).
+ * ratio_sequence == NULL selects the default 1/1, 1/3, ... 1/31. applied_out (optional) receives the number of
+ * reinsertions applied. */
+int obvhs_cuda_reinsertion_run(ObvhsContext* ctx, ObvhsBvh2* bvh, float batch_size_ratio, const float* ratio_sequence,
+                               size_t n_sequence, uint64_t* applied_out);
+
+/* ---- CwBvh (src/cwbvh) ------------------------------------------------------------------------------------ */
+/* bvh2_to_cwbvh(&bvh2, max_prims_per_leaf, order_children, include_exact_node_aabbs) (bvh2_to_cwbvh.rs:490-510).
+ * include_exact_node_aabbs must be 0. */
+int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t max_prims_per_leaf, int order_children,
+                             int include_exact_node_aabbs, ObvhsCwBvh** out);
+/* build_cwbvh_from_tris(triangles, config, core_build_time) (cwbvh/builder.rs:20-85). core_build_seconds (optional)
+ * is INCREMENTED by the device time of PLOC -> reinsertion -> collapse, as the reference's `+=` does. The permuted
+ * triangle array (examples/obj_cwbvh.rs:63-67) is attached to the result so it can be traversed directly. */
+int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
+                                     double* core_build_seconds, ObvhsCwBvh** out);
+void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh);
+size_t obvhs_cuda_cwbvh_node_count(const ObvhsCwBvh* bvh);
+size_t obvhs_cuda_cwbvh_prim_count(const ObvhsCwBvh* bvh);
+int obvhs_cuda_cwbvh_download(ObvhsContext* ctx, const ObvhsCwBvh* bvh, ObvhsCwBvhNode* nodes, uint32_t* primitive_indices,
+                              ObvhsAabb* total_aabb);
+int obvhs_cuda_cwbvh_upload(ObvhsContext* ctx, const ObvhsCwBvhNode* nodes, size_t node_count,
+                            const uint32_t* primitive_indices, size_t prim_count, const ObvhsAabb* total_aabb,
+                            ObvhsCwBvh** out);
+/* bvh_tris[i] = tris[primitive_indices[i]] (examples/obj_cwbvh.rs:63-67), kept on the device inside the handle. */
+int obvhs_cuda_cwbvh_set_triangles(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* tris, size_t n);
+/* device addresses of the buffers (for NCCL broadcast of a finished tree); bvh_tris is NULL until set. */
+int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** primitive_indices, void** bvh_tris);
+/* empty device-resident CwBvh with the given sizes, to receive a broadcast */
+int obvhs_cuda_cwbvh_alloc(ObvhsContext* ctx, size_t node_count, size_t prim_count, int with_triangles,
+                           const ObvhsAabb* total_aabb, ObvhsCwBvh** out);
+
+/* Batched CwBvh::ray_traverse(ray, &mut hit, |ray, id| bvh_tris[id].intersect(ray)) (cwbvh/mod.rs:169-198,
+ * traverse_macro.rs:59-126, triangle.rs:35-76): hits[i] starts as RayHit::none(); hit.primitive_id indexes
+ * primitive_indices order (NOT the original triangle id), exactly like the reference. */
+int obvhs_cuda_cwbvh_ray_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
+                                        ObvhsRayHit* hits);
+/* Batched CwBvh::ray_traverse_miss (cwbvh/mod.rs:201-225): miss[i] = 1 when nothing is hit before ray.tmax. */
+int obvhs_cuda_cwbvh_ray_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
+                                             uint8_t* miss);
+/* Batched CwBvh::ray_traverse_anyhit (cwbvh/mod.rs:233-245) with a counting closure: counts[i] = number of
+ * triangles the ray intersects (t < +inf) among those the node tests let through. */
+int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays,
+                                                     size_t n, uint32_t* counts);
+/* Same closest-hit traversal, also accumulating the per-launch totals the roofline model needs:
+ * counters[0] += nodes visited, counters[1] += triangles tested (host or device pointer to 2 x u64). */
+int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
+                                                ObvhsRayHit* hits, uint64_t* counters);
+/* Ray::new for n rays (src/ray.rs:34-52): origin_dir is n x 6 floats (ox,oy,oz,dx,dy,dz). */
+int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBVHS_CUDA_H */

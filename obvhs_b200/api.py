@@ -1,0 +1,458 @@
+"""Host-side mirror of the reference's API for the hot path, over the C ABI of libobvhs_cuda (include/obvhs_cuda.h).
+
+Names, argument meaning and error behaviour follow obvhs 0.3.1:
+
+* ``PlocBuilder.build(search_distance, aabbs, indices, sort_precision, search_depth_threshold) -> Bvh2``
+  (src/ploc/mod.rs:95-102), ``PlocSearchDistance`` (:534-562), ``SortPrecision`` (:658-661)
+* ``ReinsertionOptimizer().run(bvh, batch_size_ratio, ratio_sequence)`` (src/bvh2/reinsertion.rs:40-57)
+* ``bvh2_to_cwbvh(bvh2, max_prims_per_leaf, order_children, include_exact_node_aabbs) -> CwBvh``
+  (src/cwbvh/bvh2_to_cwbvh.rs:490-510)
+* ``build_cwbvh_from_tris(triangles, config, core_build_time) -> CwBvh`` (src/cwbvh/builder.rs:20-85),
+  ``BvhBuildParams`` + presets (src/lib.rs:208-305)
+* ``CwBvh.ray_traverse / ray_traverse_miss`` batched over an array of rays (src/cwbvh/mod.rs:169-225)
+
+Arrays may be numpy arrays (host) or torch CUDA tensors (device, used in place); results come back as the same
+kind as the `out=` argument, numpy by default. There is NO CPU fallback: importing works anywhere, but any call
+needs the compiled library and a CUDA device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .types import BVH2_NODE, CWBVH_NODE, RAY_HIT
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libobvhs_cuda.so")
+
+
+class ObvhsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libobvhs_cuda error {code}: {msg}")
+        self.code = code
+
+
+class BuildParamsC(C.Structure):
+    _fields_ = [
+        ("pre_split", C.c_uint32),
+        ("ploc_search_distance", C.c_uint32),
+        ("search_depth_threshold", C.c_uint64),
+        ("reinsertion_batch_ratio", C.c_float),
+        ("post_collapse_reinsertion_batch_ratio_multiplier", C.c_float),
+        ("sort_precision", C.c_uint32),
+        ("max_prims_per_leaf", C.c_uint32),
+        ("collapse_traversal_cost", C.c_float),
+    ]
+
+
+_lib = None
+
+# every symbol include/obvhs_cuda.h declares: name -> (restype, argtypes)
+_vp, _sz, _u32, _i32, _f32, _u64 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_float, C.c_uint64
+_PP = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "obvhs_cuda_create": (_i32, [_i32, _vp, _PP]),
+    "obvhs_cuda_destroy": (None, [_vp]),
+    "obvhs_cuda_last_error": (C.c_char_p, [_vp]),
+    "obvhs_cuda_synchronize": (_i32, [_vp]),
+    "obvhs_cuda_launch_count": (_u64, [_vp]),
+    "obvhs_cuda_build_params_preset": (_i32, [C.c_char_p, C.POINTER(BuildParamsC)]),
+    "obvhs_cuda_morton_sort": (_i32, [_vp, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
+    "obvhs_cuda_ploc_build": (_i32, [_vp, _vp, _vp, _sz, _u32, _u32, _sz, _PP]),
+    "obvhs_cuda_ploc_build_tris": (_i32, [_vp, _vp, _sz, _u32, _u32, _sz, _PP]),
+    "obvhs_cuda_bvh2_free": (None, [_vp]),
+    "obvhs_cuda_bvh2_node_count": (_sz, [_vp]),
+    "obvhs_cuda_bvh2_prim_count": (_sz, [_vp]),
+    "obvhs_cuda_bvh2_max_depth": (_sz, [_vp]),
+    "obvhs_cuda_bvh2_ploc_iterations": (_sz, [_vp]),
+    "obvhs_cuda_bvh2_children_ordered_after_parents": (_i32, [_vp]),
+    "obvhs_cuda_bvh2_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "obvhs_cuda_bvh2_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _sz, _i32, _PP]),
+    "obvhs_cuda_bvh2_compute_parents": (_i32, [_vp, _vp]),
+    "obvhs_cuda_bvh2_refit_all": (_i32, [_vp, _vp]),
+    "obvhs_cuda_bvh2_set_leaf_aabbs": (_i32, [_vp, _vp, _vp, _sz]),
+    "obvhs_cuda_reinsertion_run": (_i32, [_vp, _vp, _f32, _vp, _sz, C.POINTER(_u64)]),
+    "obvhs_cuda_bvh2_to_cwbvh": (_i32, [_vp, _vp, _u32, _i32, _i32, _PP]),
+    "obvhs_cuda_build_cwbvh_from_tris": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
+    "obvhs_cuda_cwbvh_free": (None, [_vp]),
+    "obvhs_cuda_cwbvh_node_count": (_sz, [_vp]),
+    "obvhs_cuda_cwbvh_prim_count": (_sz, [_vp]),
+    "obvhs_cuda_cwbvh_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "obvhs_cuda_cwbvh_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _PP]),
+    "obvhs_cuda_cwbvh_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
+    "obvhs_cuda_cwbvh_device_ptrs": (_i32, [_vp, _PP, _PP, _PP]),
+    "obvhs_cuda_cwbvh_alloc": (_i32, [_vp, _sz, _sz, _i32, _vp, _PP]),
+    "obvhs_cuda_cwbvh_ray_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "obvhs_cuda_make_rays": (_i32, [_vp, _vp, _sz, _f32, _f32, _vp]),
+}
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and bind every declared symbol. Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(path):
+            raise ObvhsError(-2, f"{path} not built (run `python -m obvhs_b200.build`); there is no CPU fallback")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _is_torch(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_contiguous(), "tensors passed to libobvhs_cuda must be contiguous"
+        return C.c_void_p(x.data_ptr())
+    return x.ctypes.data_as(C.c_void_p)
+
+
+def _as_f32(x, cols):
+    """numpy -> contiguous float32 (n, cols); torch tensors are checked and passed through."""
+    if _is_torch(x):
+        assert x.dim() == 2 and x.shape[1] == cols and str(x.dtype) == "torch.float32", (x.shape, x.dtype)
+        return x.contiguous()
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    if a.size == 0:
+        a = a.reshape(0, cols)
+    assert a.ndim == 2 and a.shape[1] == cols, a.shape
+    return a
+
+
+class Context:
+    """One device + stream + reusable builder scratch (obvhs_cuda_create)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.obvhs_cuda_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise ObvhsError(rc, "obvhs_cuda_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise ObvhsError(rc, (self.lib.obvhs_cuda_last_error(self.h) or b"").decode())
+
+    def synchronize(self):
+        self.check(self.lib.obvhs_cuda_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.obvhs_cuda_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.obvhs_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class PlocSearchDistance(enum.IntEnum):
+    """src/ploc/mod.rs:534-548"""
+
+    Minimum = 1
+    VeryLow = 2
+    Low = 6
+    Medium = 14
+    High = 24
+    VeryHigh = 32
+
+
+class SortPrecision(enum.IntEnum):
+    """src/ploc/mod.rs:658-661"""
+
+    U128 = 128
+    U64 = 64
+
+
+@dataclass
+class BvhBuildParams:
+    """src/lib.rs:208-231"""
+
+    pre_split: bool
+    ploc_search_distance: PlocSearchDistance
+    search_depth_threshold: int
+    reinsertion_batch_ratio: float
+    post_collapse_reinsertion_batch_ratio_multiplier: float
+    sort_precision: SortPrecision
+    max_prims_per_leaf: int
+    collapse_traversal_cost: float
+
+    @classmethod
+    def preset(cls, name: str) -> "BvhBuildParams":
+        c = BuildParamsC()
+        if load_library().obvhs_cuda_build_params_preset(name.encode(), C.byref(c)) != 0:
+            raise ValueError(f"unknown preset {name}")
+        return cls(bool(c.pre_split), PlocSearchDistance(c.ploc_search_distance), int(c.search_depth_threshold),
+                   float(c.reinsertion_batch_ratio), float(c.post_collapse_reinsertion_batch_ratio_multiplier),
+                   SortPrecision(c.sort_precision), int(c.max_prims_per_leaf), float(c.collapse_traversal_cost))
+
+    # src/lib.rs:233-305
+    @classmethod
+    def fastest_build(cls): return cls.preset("fastest_build")
+    @classmethod
+    def very_fast_build(cls): return cls.preset("very_fast_build")
+    @classmethod
+    def fast_build(cls): return cls.preset("fast_build")
+    @classmethod
+    def medium_build(cls): return cls.preset("medium_build")
+    @classmethod
+    def slow_build(cls): return cls.preset("slow_build")
+    @classmethod
+    def very_slow_build(cls): return cls.preset("very_slow_build")
+
+    def to_c(self) -> BuildParamsC:
+        return BuildParamsC(int(self.pre_split), int(self.ploc_search_distance), int(self.search_depth_threshold),
+                            float(self.reinsertion_batch_ratio), float(self.post_collapse_reinsertion_batch_ratio_multiplier),
+                            int(self.sort_precision), int(self.max_prims_per_leaf), float(self.collapse_traversal_cost))
+
+
+class Bvh2:
+    """Device-resident Bvh2 (src/bvh2/mod.rs:31-85)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.obvhs_cuda_bvh2_free(self.h)
+        self.h = None
+
+    node_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_node_count(s.h)))
+    prim_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_prim_count(s.h)))
+    max_depth = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_max_depth(s.h)))
+    ploc_iterations = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_ploc_iterations(s.h)))
+    children_are_ordered_after_parents = property(lambda s: bool(s.ctx.lib.obvhs_cuda_bvh2_children_ordered_after_parents(s.h)))
+
+    @classmethod
+    def upload(cls, nodes, primitive_indices, max_depth=96, children_ordered_after_parents=False, ctx: Context | None = None):
+        ctx = ctx or default_context()
+        nodes = np.ascontiguousarray(nodes, dtype=BVH2_NODE)
+        prims = np.ascontiguousarray(primitive_indices, dtype=np.uint32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.obvhs_cuda_bvh2_upload(ctx.h, _ptr(nodes), nodes.shape[0], _ptr(prims), prims.shape[0], max_depth,
+                                                  int(children_ordered_after_parents), C.byref(h)))
+        return cls(ctx, h)
+
+    def download(self, with_parents=False):
+        """-> (nodes[BVH2_NODE], primitive_indices[u32][, parents[u32]]) as numpy arrays"""
+        nodes = np.zeros(self.node_count, dtype=BVH2_NODE)
+        prims = np.zeros(self.prim_count, dtype=np.uint32)
+        parents = np.zeros(self.node_count, dtype=np.uint32) if with_parents else None
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_download(self.ctx.h, self.h, _ptr(nodes), _ptr(prims), _ptr(parents)))
+        return (nodes, prims, parents) if with_parents else (nodes, prims)
+
+    def compute_parents(self):
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_compute_parents(self.ctx.h, self.h))
+
+    def refit_all(self):
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_refit_all(self.ctx.h, self.h))
+
+    def set_leaf_aabbs(self, prim_aabbs):
+        a = _as_f32(prim_aabbs, 8)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_leaf_aabbs(self.ctx.h, self.h, _ptr(a), a.shape[0]))
+
+
+class PlocBuilder:
+    """src/ploc/mod.rs:35-159. The context keeps the scratch the reference's builder keeps for reuse."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+
+    @classmethod
+    def with_capacity(cls, _prim_count: int, ctx: Context | None = None):
+        return cls(ctx)
+
+    def build(self, search_distance, aabbs, indices=None, sort_precision=SortPrecision.U64, search_depth_threshold: int = 0) -> Bvh2:
+        a = _as_f32(aabbs, 8)
+        n = a.shape[0]
+        idx = None
+        if indices is not None:
+            idx = indices if _is_torch(indices) else np.ascontiguousarray(indices, dtype=np.uint32)
+            assert idx.shape[0] == n
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.obvhs_cuda_ploc_build(self.ctx.h, _ptr(a), _ptr(idx), n, int(search_distance), int(sort_precision),
+                                                         int(search_depth_threshold), C.byref(h)))
+        return Bvh2(self.ctx, h)
+
+    def build_tris(self, search_distance, tris, sort_precision=SortPrecision.U64, search_depth_threshold: int = 0) -> Bvh2:
+        """PlocBuilder::build over &[Triangle] (Boundable, src/triangle.rs:28-30)."""
+        t = _as_f32(tris, 12)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.obvhs_cuda_ploc_build_tris(self.ctx.h, _ptr(t), t.shape[0], int(search_distance), int(sort_precision),
+                                                              int(search_depth_threshold), C.byref(h)))
+        return Bvh2(self.ctx, h)
+
+    def morton_sort(self, aabbs, sort_precision=SortPrecision.U64):
+        """Stage probe: (codes_lo, codes_hi, sorted order, scene AABB) -- see obvhs_cuda_morton_sort."""
+        a = _as_f32(aabbs, 8)
+        n = a.shape[0]
+        lo, hi = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        order, total = np.zeros(n, np.uint32), np.zeros(8, np.float32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_morton_sort(self.ctx.h, _ptr(a), n, int(sort_precision), _ptr(lo), _ptr(hi), _ptr(order),
+                                                          _ptr(total)))
+        return lo, hi, order, total
+
+
+class ReinsertionOptimizer:
+    """src/bvh2/reinsertion.rs:22-57"""
+
+    def __init__(self):
+        self.applied = 0
+
+    def run(self, bvh: Bvh2, batch_size_ratio: float, ratio_sequence=None):
+        seq = None if ratio_sequence is None else np.ascontiguousarray(ratio_sequence, dtype=np.float32)
+        applied = C.c_uint64(0)
+        bvh.ctx.check(bvh.ctx.lib.obvhs_cuda_reinsertion_run(bvh.ctx.h, bvh.h, float(batch_size_ratio), _ptr(seq),
+                                                            0 if seq is None else seq.shape[0], C.byref(applied)))
+        self.applied = int(applied.value)
+        return self.applied
+
+
+class CwBvh:
+    """Device-resident CwBvh (src/cwbvh/mod.rs:43-55) with, optionally, the triangles permuted by primitive_indices."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+        self.core_build_seconds = 0.0
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.obvhs_cuda_cwbvh_free(self.h)
+        self.h = None
+
+    node_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_cwbvh_node_count(s.h)))
+    prim_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_cwbvh_prim_count(s.h)))
+
+    @classmethod
+    def upload(cls, nodes, primitive_indices, total_aabb=None, ctx: Context | None = None):
+        ctx = ctx or default_context()
+        nodes = np.ascontiguousarray(nodes, dtype=CWBVH_NODE)
+        prims = np.ascontiguousarray(primitive_indices, dtype=np.uint32)
+        total = np.ascontiguousarray(np.zeros(8) if total_aabb is None else total_aabb, dtype=np.float32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.obvhs_cuda_cwbvh_upload(ctx.h, _ptr(nodes), nodes.shape[0], _ptr(prims), prims.shape[0], _ptr(total), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def alloc(cls, node_count, prim_count, with_triangles=True, total_aabb=None, ctx: Context | None = None):
+        ctx = ctx or default_context()
+        total = np.ascontiguousarray(np.zeros(8) if total_aabb is None else total_aabb, dtype=np.float32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.obvhs_cuda_cwbvh_alloc(ctx.h, node_count, prim_count, int(with_triangles), _ptr(total), C.byref(h)))
+        return cls(ctx, h)
+
+    def download(self):
+        nodes = np.zeros(self.node_count, dtype=CWBVH_NODE)
+        prims = np.zeros(self.prim_count, dtype=np.uint32)
+        total = np.zeros(8, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_download(self.ctx.h, self.h, _ptr(nodes), _ptr(prims), _ptr(total)))
+        return nodes, prims, total
+
+    def set_triangles(self, tris):
+        t = _as_f32(tris, 12)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_set_triangles(self.ctx.h, self.h, _ptr(t), t.shape[0]))
+
+    def device_ptrs(self):
+        """(nodes, primitive_indices, bvh_tris) device addresses as ints (0 = absent)."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value or 0, b.value or 0, c.value or 0
+
+    def _out(self, out, n, dtype, torch_dtype_name, cols=None):
+        if out is not None:
+            return out
+        return np.zeros(n, dtype=dtype)
+
+    def ray_traverse(self, rays, out=None, counters=None):
+        """Batched CwBvh::ray_traverse with the triangle closure: -> RayHit per ray (numpy RAY_HIT array, or `out`).
+
+        `out` may be a torch CUDA tensor of shape (n, 4) int32/float32-viewable (16 bytes per ray) to keep hits on device.
+        counters: optional np.uint64[2] (or device tensor) accumulating nodes visited / triangles tested."""
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
+        if counters is None:
+            self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
+        else:
+            self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
+        return hits
+
+    def ray_traverse_miss(self, rays, out=None):
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        miss = out if out is not None else np.zeros(n, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_miss_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
+        return miss
+
+    def ray_traverse_anyhit_count(self, rays, out=None):
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        counts = out if out is not None else np.zeros(n, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(counts)))
+        return counts
+
+
+def bvh2_to_cwbvh(bvh2: Bvh2, max_prims_per_leaf: int = 3, order_children: bool = True, include_exact_node_aabbs: bool = False) -> CwBvh:
+    """src/cwbvh/bvh2_to_cwbvh.rs:490-510"""
+    h = C.c_void_p()
+    bvh2.ctx.check(bvh2.ctx.lib.obvhs_cuda_bvh2_to_cwbvh(bvh2.ctx.h, bvh2.h, int(max_prims_per_leaf), int(order_children),
+                                                        int(include_exact_node_aabbs), C.byref(h)))
+    return CwBvh(bvh2.ctx, h)
+
+
+def build_cwbvh_from_tris(triangles, config: BvhBuildParams, core_build_time: list | None = None, ctx: Context | None = None) -> CwBvh:
+    """src/cwbvh/builder.rs:20-85. `core_build_time` is a one-element list of seconds that is incremented (the
+    reference's `&mut Duration`). The result carries the permuted triangles and is ready to traverse."""
+    ctx = ctx or default_context()
+    t = _as_f32(triangles, 12)
+    secs = C.c_double(0.0)
+    params = config.to_c()
+    h = C.c_void_p()
+    ctx.check(ctx.lib.obvhs_cuda_build_cwbvh_from_tris(ctx.h, _ptr(t), t.shape[0], C.byref(params), C.byref(secs), C.byref(h)))
+    bvh = CwBvh(ctx, h)
+    bvh.core_build_seconds = secs.value
+    if core_build_time is not None:
+        core_build_time[0] += secs.value
+    return bvh
+
+
+def make_rays(origin_dir, tmin=0.0, tmax=3.4028234663852886e38, out=None, ctx: Context | None = None):
+    """Ray::new for n rays (src/ray.rs:34-52). origin_dir: (n,6) float32."""
+    ctx = ctx or default_context()
+    od = _as_f32(origin_dir, 6)
+    n = od.shape[0]
+    rays = out if out is not None else np.zeros((n, 16), dtype=np.float32)
+    ctx.check(ctx.lib.obvhs_cuda_make_rays(ctx.h, _ptr(od), n, float(tmin), float(tmax), _ptr(rays)))
+    return rays

@@ -1,0 +1,512 @@
+// api.cu -- the extern "C" surface declared in include/obvhs_cuda.h. Thin: argument checks, host<->device staging,
+// and the orchestration of build_cwbvh_from_tris (src/cwbvh/builder.rs:20-85).
+#include <string.h>
+
+#include "common.cuh"
+
+int bvh2_set_leaf_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* d_aabbs);
+int bvh2_expand_nodes_device(ObvhsContext* ctx, const Node32* in, size_t n, ObvhsBvh2Node* d_out);
+int bvh2_pack_nodes_device(ObvhsContext* ctx, const ObvhsBvh2Node* d_in, size_t n, Node32* out);
+
+bool obvhs_is_device_ptr(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+struct DeviceScope {  // makes the context's device current for the duration of a call
+    int prev = -1;
+    explicit DeviceScope(const ObvhsContext* ctx) {
+        cudaGetDevice(&prev);
+        if (prev != ctx->device) cudaSetDevice(ctx->device);
+        else prev = -1;
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define API_ENTER(ctx)                                     \
+    if (!(ctx)) return OBVHS_ERR_INVALID_ARG;              \
+    DeviceScope _scope(ctx);                               \
+    (ctx)->last_error.clear()
+#define ARG_CHECK(ctx, cond, msg)                          \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            OBVHS_SET_ERR(ctx, "invalid argument: %s", msg); \
+            return OBVHS_ERR_INVALID_ARG;                  \
+        }                                                  \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
+    if (!out) return OBVHS_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return OBVHS_ERR_CUDA;  // no CPU fallback: without a CUDA device there is no context
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return OBVHS_ERR_CUDA;
+    ObvhsContext* ctx = new ObvhsContext();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return OBVHS_ERR_CUDA;
+        }
+        ctx->owns_stream = true;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaMallocHost(&ctx->pinned, 4096) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        obvhs_cuda_destroy(ctx);
+        return OBVHS_ERR_CUDA;
+    }
+    // keep freed scratch in the pool: the reference's builders keep their Vecs for reuse (ploc/mod.rs:35-54)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return OBVHS_OK;
+}
+
+void obvhs_cuda_destroy(ObvhsContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* obvhs_cuda_last_error(const ObvhsContext* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int obvhs_cuda_synchronize(ObvhsContext* ctx) {
+    API_ENTER(ctx);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx) { return ctx ? ctx->launches : 0; }
+
+int obvhs_cuda_build_params_preset(const char* name, ObvhsBuildParams* out) {
+    if (!name || !out) return OBVHS_ERR_INVALID_ARG;
+    struct P {
+        const char* n;
+        ObvhsBuildParams p;
+    };
+    // src/lib.rs:233-305
+    static const P presets[] = {
+        {"fastest_build", {0, 1, 0, 0.0f, 0.0f, 64, 1, 1.0f}},
+        {"very_fast_build", {0, 1, 0, 0.01f, 0.0f, 64, 8, 3.0f}},
+        {"fast_build", {0, 6, 2, 0.02f, 0.0f, 64, 8, 3.0f}},
+        {"medium_build", {0, 14, 3, 0.05f, 2.0f, 64, 8, 3.0f}},
+        {"slow_build", {1, 24, 2, 0.2f, 2.0f, 128, 8, 3.0f}},
+        {"very_slow_build", {1, 14, 1, 1.0f, 1.0f, 128, 8, 3.0f}},
+    };
+    for (const P& p : presets)
+        if (strcmp(p.n, name) == 0) {
+            *out = p.p;
+            return OBVHS_OK;
+        }
+    return OBVHS_ERR_INVALID_ARG;
+}
+
+// ---- PLOC ---------------------------------------------------------------------------------------------------
+int obvhs_cuda_morton_sort(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, uint32_t sort_precision, uint64_t* codes_lo,
+                           uint64_t* codes_hi, uint32_t* order, ObvhsAabb* total_aabb) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, n == 0 || aabbs, "aabbs is null");
+    DevBuf<ObvhsAabb> st_aabbs, d_total;
+    DevBuf<u64> d_lo, d_hi;
+    DevBuf<u32> d_order;
+    const ObvhsAabb* d_aabbs = nullptr;
+    ST_TRY(stage_in(ctx, aabbs, n, st_aabbs, &d_aabbs));
+    PlocMortonOut probe;
+    if (codes_lo) { CU_TRY(ctx, d_lo.alloc(n, ctx->stream)); probe.codes_lo = d_lo.p; }
+    if (codes_hi) { CU_TRY(ctx, d_hi.alloc(n, ctx->stream)); probe.codes_hi = d_hi.p; }
+    if (order) { CU_TRY(ctx, d_order.alloc(n, ctx->stream)); probe.order = d_order.p; }
+    CU_TRY(ctx, d_total.alloc(1, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_total.p, 0, sizeof(ObvhsAabb), ctx->stream));
+    probe.total = d_total.p;
+    ObvhsBvh2* bvh = nullptr;
+    // search distance 1 keeps the (unused) PLOC iterations cheap; the probe outputs are captured before them
+    ST_TRY(ploc_build_device(ctx, d_aabbs, nullptr, nullptr, n, 1, sort_precision, 0, &bvh, &probe));
+    obvhs_cuda_bvh2_free(bvh);
+    ST_TRY(copy_out(ctx, codes_lo, (const u64*)d_lo.p, n));
+    ST_TRY(copy_out(ctx, codes_hi, (const u64*)d_hi.p, n));
+    ST_TRY(copy_out(ctx, order, (const u32*)d_order.p, n));
+    ST_TRY(copy_out(ctx, total_aabb, (const ObvhsAabb*)d_total.p, (size_t)1));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_ploc_build(ObvhsContext* ctx, const ObvhsAabb* aabbs, const uint32_t* indices, size_t n, uint32_t search_distance,
+                          uint32_t sort_precision, size_t search_depth_threshold, ObvhsBvh2** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, out, "out is null");
+    ARG_CHECK(ctx, n == 0 || aabbs, "aabbs is null");
+    DevBuf<ObvhsAabb> st_aabbs;
+    DevBuf<u32> st_idx;
+    const ObvhsAabb* d_aabbs = nullptr;
+    const u32* d_idx = nullptr;
+    ST_TRY(stage_in(ctx, aabbs, n, st_aabbs, &d_aabbs));
+    ST_TRY(stage_in(ctx, indices, n, st_idx, &d_idx));
+    return ploc_build_device(ctx, d_aabbs, nullptr, d_idx, n, search_distance, sort_precision, search_depth_threshold, out, nullptr);
+}
+
+int obvhs_cuda_ploc_build_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, uint32_t search_distance, uint32_t sort_precision,
+                               size_t search_depth_threshold, ObvhsBvh2** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, out, "out is null");
+    ARG_CHECK(ctx, n == 0 || tris, "tris is null");
+    DevBuf<ObvhsTriangle> st_tris;
+    const ObvhsTriangle* d_tris = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
+    return ploc_build_device(ctx, nullptr, d_tris, nullptr, n, search_distance, sort_precision, search_depth_threshold, out, nullptr);
+}
+
+// ---- Bvh2 ---------------------------------------------------------------------------------------------------
+void obvhs_cuda_bvh2_free(ObvhsBvh2* bvh) {
+    if (!bvh) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != bvh->device) cudaSetDevice(bvh->device);
+    if (bvh->nodes) cudaFree(bvh->nodes);
+    if (bvh->primitive_indices) cudaFree(bvh->primitive_indices);
+    if (bvh->parents) cudaFree(bvh->parents);
+    if (prev >= 0 && prev != bvh->device) cudaSetDevice(prev);
+    delete bvh;
+}
+size_t obvhs_cuda_bvh2_node_count(const ObvhsBvh2* bvh) { return bvh ? bvh->node_count : 0; }
+size_t obvhs_cuda_bvh2_prim_count(const ObvhsBvh2* bvh) { return bvh ? bvh->prim_count : 0; }
+size_t obvhs_cuda_bvh2_max_depth(const ObvhsBvh2* bvh) { return bvh ? bvh->max_depth : 0; }
+size_t obvhs_cuda_bvh2_ploc_iterations(const ObvhsBvh2* bvh) { return bvh ? bvh->ploc_iterations : 0; }
+int obvhs_cuda_bvh2_children_ordered_after_parents(const ObvhsBvh2* bvh) { return bvh && bvh->children_are_ordered_after_parents ? 1 : 0; }
+
+int obvhs_cuda_bvh2_download(ObvhsContext* ctx, const ObvhsBvh2* bvh, ObvhsBvh2Node* nodes, uint32_t* primitive_indices, uint32_t* parents) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    if (nodes && bvh->node_count) {
+        if (obvhs_is_device_ptr(nodes)) {
+            ST_TRY(bvh2_expand_nodes_device(ctx, bvh->nodes, bvh->node_count, nodes));
+        } else {
+            DevBuf<ObvhsBvh2Node> tmp;
+            CU_TRY(ctx, tmp.alloc(bvh->node_count, ctx->stream));
+            ST_TRY(bvh2_expand_nodes_device(ctx, bvh->nodes, bvh->node_count, tmp.p));
+            ST_TRY(copy_out(ctx, nodes, (const ObvhsBvh2Node*)tmp.p, bvh->node_count));
+        }
+    }
+    ST_TRY(copy_out(ctx, primitive_indices, (const u32*)bvh->primitive_indices, bvh->prim_count));
+    if (parents) {
+        ARG_CHECK(ctx, bvh->parents || bvh->node_count == 0, "parents requested but not computed (Bvh2::parents is None)");
+        ST_TRY(copy_out(ctx, parents, (const u32*)bvh->parents, bvh->node_count));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_bvh2_upload(ObvhsContext* ctx, const ObvhsBvh2Node* nodes, size_t node_count, const uint32_t* primitive_indices,
+                           size_t prim_count, size_t max_depth, int children_ordered_after_parents, ObvhsBvh2** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, out, "out is null");
+    ARG_CHECK(ctx, node_count == 0 || nodes, "nodes is null");
+    ARG_CHECK(ctx, prim_count == 0 || primitive_indices, "primitive_indices is null");
+    ObvhsBvh2* bvh = new ObvhsBvh2();
+    bvh->device = ctx->device;
+    bvh->node_count = node_count;
+    bvh->prim_count = prim_count;
+    bvh->max_depth = max_depth ? max_depth : 96;
+    bvh->children_are_ordered_after_parents = children_ordered_after_parents != 0;
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }
+    } guard{bvh};
+    if (node_count) {
+        DevBuf<ObvhsBvh2Node> st;
+        const ObvhsBvh2Node* d_nodes = nullptr;
+        ST_TRY(stage_in(ctx, nodes, node_count, st, &d_nodes));
+        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->nodes, node_count * sizeof(Node32), ctx->stream));
+        ST_TRY(bvh2_pack_nodes_device(ctx, d_nodes, node_count, bvh->nodes));
+    }
+    if (prim_count) {
+        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->primitive_indices, prim_count * 4, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(bvh->primitive_indices, primitive_indices, prim_count * 4, cudaMemcpyDefault, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    guard.b = nullptr;
+    *out = bvh;
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_bvh2_compute_parents(ObvhsContext* ctx, ObvhsBvh2* bvh) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    return bvh2_compute_parents_device(ctx, bvh);
+}
+int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    return bvh2_refit_all_device(ctx, bvh);
+}
+int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* prim_aabbs, size_t n) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || prim_aabbs), "null argument");
+    ARG_CHECK(ctx, n >= bvh->prim_count, "fewer AABBs than primitives");
+    DevBuf<ObvhsAabb> st;
+    const ObvhsAabb* d = nullptr;
+    ST_TRY(stage_in(ctx, prim_aabbs, n, st, &d));
+    ST_TRY(bvh2_set_leaf_aabbs_device(ctx, bvh, d));
+    return bvh2_refit_all_device(ctx, bvh);
+}
+
+int obvhs_cuda_reinsertion_run(ObvhsContext* ctx, ObvhsBvh2* bvh, float batch_size_ratio, const float* ratio_sequence, size_t n_sequence,
+                               uint64_t* applied_out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    ARG_CHECK(ctx, !ratio_sequence || !obvhs_is_device_ptr(ratio_sequence), "ratio_sequence must be host memory");
+    u64 applied = 0;
+    int rc = reinsertion_run_device(ctx, bvh, batch_size_ratio, ratio_sequence, n_sequence, &applied);
+    if (applied_out) *applied_out = applied;
+    return rc;
+}
+
+// ---- CwBvh --------------------------------------------------------------------------------------------------
+int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t max_prims_per_leaf, int order_children,
+                             int include_exact_node_aabbs, ObvhsCwBvh** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && out, "null argument");
+    if (include_exact_node_aabbs) {
+        OBVHS_SET_ERR(ctx, "include_exact_node_aabbs is not supported");
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    return bvh2_to_cwbvh_device(ctx, bvh, max_prims_per_leaf, order_children != 0, out);
+}
+
+int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
+                                     double* core_build_seconds, ObvhsCwBvh** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, params && out, "null argument");
+    ARG_CHECK(ctx, n == 0 || tris, "tris is null");
+    if (params->pre_split) {
+        OBVHS_SET_ERR(ctx, "pre_split (src/splits.rs) is outside the GPU hot path");
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    DevBuf<ObvhsTriangle> st_tris;
+    const ObvhsTriangle* d_tris = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
+    // core_build_time brackets PLOC -> reinsertion -> collapse (cwbvh/builder.rs:62-76), measured on the device
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    ObvhsBvh2* bvh2 = nullptr;
+    ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                             (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { obvhs_cuda_bvh2_free(b); }
+    } guard{bvh2};
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 3 ? 3 : params->max_prims_per_leaf);  // builder.rs:74
+    ObvhsCwBvh* cw = nullptr;
+    ST_TRY(bvh2_to_cwbvh_device(ctx, bvh2, mp, true, &cw));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    int rc = cwbvh_permute_tris_device(ctx, cw, d_tris, n);
+    if (rc == OBVHS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = OBVHS_ERR_CUDA;
+    if (rc != OBVHS_OK) {
+        obvhs_cuda_cwbvh_free(cw);
+        return rc;
+    }
+    if (core_build_seconds) {
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *core_build_seconds += (double)ms * 1e-3;
+    }
+    *out = cw;
+    return OBVHS_OK;
+}
+
+void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh) {
+    if (!bvh) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != bvh->device) cudaSetDevice(bvh->device);
+    if (bvh->nodes) cudaFree(bvh->nodes);
+    if (bvh->primitive_indices) cudaFree(bvh->primitive_indices);
+    if (bvh->bvh_tris) cudaFree(bvh->bvh_tris);
+    if (prev >= 0 && prev != bvh->device) cudaSetDevice(prev);
+    delete bvh;
+}
+size_t obvhs_cuda_cwbvh_node_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->node_count : 0; }
+size_t obvhs_cuda_cwbvh_prim_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->prim_count : 0; }
+
+int obvhs_cuda_cwbvh_download(ObvhsContext* ctx, const ObvhsCwBvh* bvh, ObvhsCwBvhNode* nodes, uint32_t* primitive_indices,
+                              ObvhsAabb* total_aabb) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    ST_TRY(copy_out(ctx, nodes, (const ObvhsCwBvhNode*)bvh->nodes, bvh->node_count));
+    ST_TRY(copy_out(ctx, primitive_indices, (const u32*)bvh->primitive_indices, bvh->prim_count));
+    if (total_aabb) {
+        if (obvhs_is_device_ptr(total_aabb)) CU_TRY(ctx, cudaMemcpyAsync(total_aabb, &bvh->total_aabb, 32, cudaMemcpyHostToDevice, ctx->stream));
+        else *total_aabb = bvh->total_aabb;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_cwbvh_alloc(ObvhsContext* ctx, size_t node_count, size_t prim_count, int with_triangles, const ObvhsAabb* total_aabb,
+                           ObvhsCwBvh** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, out, "out is null");
+    ObvhsCwBvh* cw = new ObvhsCwBvh();
+    cw->device = ctx->device;
+    cw->node_count = node_count;
+    cw->prim_count = prim_count;
+    if (total_aabb) cw->total_aabb = *total_aabb;
+    struct Guard {
+        ObvhsCwBvh* b;
+        ~Guard() { if (b) obvhs_cuda_cwbvh_free(b); }
+    } guard{cw};
+    if (node_count) CU_TRY(ctx, cudaMallocAsync((void**)&cw->nodes, node_count * sizeof(ObvhsCwBvhNode), ctx->stream));
+    if (prim_count) CU_TRY(ctx, cudaMallocAsync((void**)&cw->primitive_indices, prim_count * 4, ctx->stream));
+    if (prim_count && with_triangles) CU_TRY(ctx, cudaMallocAsync((void**)&cw->bvh_tris, prim_count * sizeof(ObvhsTriangle), ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    guard.b = nullptr;
+    *out = cw;
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_cwbvh_upload(ObvhsContext* ctx, const ObvhsCwBvhNode* nodes, size_t node_count, const uint32_t* primitive_indices,
+                            size_t prim_count, const ObvhsAabb* total_aabb, ObvhsCwBvh** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, out, "out is null");
+    ARG_CHECK(ctx, node_count == 0 || nodes, "nodes is null");
+    ARG_CHECK(ctx, prim_count == 0 || primitive_indices, "primitive_indices is null");
+    ObvhsCwBvh* cw = nullptr;
+    ObvhsAabb total = {};
+    if (total_aabb) {
+        if (obvhs_is_device_ptr(total_aabb)) CU_TRY(ctx, cudaMemcpy(&total, total_aabb, 32, cudaMemcpyDeviceToHost));
+        else total = *total_aabb;
+    }
+    ST_TRY(obvhs_cuda_cwbvh_alloc(ctx, node_count, prim_count, 0, &total, &cw));
+    cudaError_t e = cudaSuccess;
+    if (node_count) e = cudaMemcpyAsync(cw->nodes, nodes, node_count * sizeof(ObvhsCwBvhNode), cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess && prim_count) e = cudaMemcpyAsync(cw->primitive_indices, primitive_indices, prim_count * 4, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        OBVHS_SET_ERR(ctx, "cwbvh_upload: %s", cudaGetErrorString(e));
+        obvhs_cuda_cwbvh_free(cw);
+        return OBVHS_ERR_CUDA;
+    }
+    *out = cw;
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_cwbvh_set_triangles(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* tris, size_t n) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || tris), "null argument");
+    DevBuf<ObvhsTriangle> st;
+    const ObvhsTriangle* d = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st, &d));
+    ST_TRY(cwbvh_permute_tris_device(ctx, bvh, d, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** primitive_indices, void** bvh_tris) {
+    if (!bvh) return OBVHS_ERR_INVALID_ARG;
+    if (nodes) *nodes = bvh->nodes;
+    if (primitive_indices) *primitive_indices = bvh->primitive_indices;
+    if (bvh_tris) *bvh_tris = bvh->bvh_tris;
+    return OBVHS_OK;
+}
+
+static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
+                           uint64_t* counters) {
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    ARG_CHECK(ctx, n == 0 || (rays && out), "null rays/out");
+    if (n == 0) return OBVHS_OK;
+    DevBuf<ObvhsRay> st_rays;
+    DevBuf<unsigned char> st_out;
+    DevBuf<u64> st_cnt;
+    const ObvhsRay* d_rays = nullptr;
+    ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
+    const bool out_dev = obvhs_is_device_ptr(out);
+    void* d_out = out;
+    if (!out_dev) {
+        CU_TRY(ctx, st_out.alloc(n * out_elem, ctx->stream));
+        d_out = st_out.p;
+    }
+    u64* d_cnt = nullptr;
+    bool cnt_dev = false;
+    if (counters) {
+        cnt_dev = obvhs_is_device_ptr(counters);
+        if (cnt_dev) d_cnt = counters;
+        else {
+            CU_TRY(ctx, st_cnt.alloc(2, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(st_cnt.p, counters, 16, cudaMemcpyHostToDevice, ctx->stream));
+            d_cnt = st_cnt.p;
+        }
+    }
+    ST_TRY(cwbvh_traverse_device(ctx, bvh, d_rays, n, mode, d_out, d_cnt));
+    if (counters && !cnt_dev) CU_TRY(ctx, cudaMemcpyAsync(counters, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!out_dev) {
+        CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (counters && !cnt_dev) {
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return OBVHS_OK;
+}
+
+int obvhs_cuda_cwbvh_ray_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return traverse_common(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
+}
+int obvhs_cuda_cwbvh_ray_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, uint8_t* miss) {
+    API_ENTER(ctx);
+    return traverse_common(ctx, bvh, rays, n, 1, miss, 1, nullptr);
+}
+int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
+                                                     uint32_t* counts) {
+    API_ENTER(ctx);
+    return traverse_common(ctx, bvh, rays, n, 2, counts, 4, nullptr);
+}
+int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits,
+                                                uint64_t* counters) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, counters, "counters is null");
+    return traverse_common(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+
+int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, n == 0 || (origin_dir && rays), "null argument");
+    if (n == 0) return OBVHS_OK;
+    DevBuf<float> st_od;
+    DevBuf<ObvhsRay> st_rays;
+    const float* d_od = nullptr;
+    ST_TRY(stage_in(ctx, origin_dir, n * 6, st_od, &d_od));
+    const bool out_dev = obvhs_is_device_ptr(rays);
+    ObvhsRay* d_rays = rays;
+    if (!out_dev) {
+        CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
+        d_rays = st_rays.p;
+    }
+    ST_TRY(make_rays_device(ctx, d_od, n, tmin, tmax, d_rays));
+    if (!out_dev) ST_TRY(copy_out(ctx, rays, (const ObvhsRay*)d_rays, n));
+    return OBVHS_OK;
+}
+
+}  // extern "C"

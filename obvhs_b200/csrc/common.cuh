@@ -1,0 +1,250 @@
+// common.cuh -- shared device helpers and host-side containers of libobvhs_cuda (sm_100a only).
+//
+// Float rules that make the GPU path bit-exact with the reference's CPU arithmetic:
+//   * the library is compiled with -fmad=false: rustc never contracts a*b+c;
+//   * glam Vec3A::min/max are _mm_min_ps/_mm_max_ps: min(a,b) = a<b ? a : b (second operand on ties/NaN).
+//     fminf/fmaxf order -0 < +0 and drop NaNs, so they are NOT used for tree AABBs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/obvhs_cuda.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+static_assert(sizeof(ObvhsAabb) == 32, "Aabb");
+static_assert(sizeof(ObvhsTriangle) == 48, "Triangle");
+static_assert(sizeof(ObvhsBvh2Node) == 48, "Bvh2Node");
+static_assert(sizeof(ObvhsCwBvhNode) == 80, "CwBvhNode");
+static_assert(sizeof(ObvhsRay) == 64, "Ray");
+static_assert(sizeof(ObvhsRayHit) == 16, "RayHit");
+
+#define OBVHS_SM_COUNT 148  // B200: grids are sized in multiples of this
+
+// ----------------------------------------------------------------------------------------------------------
+// Device-side BVH2 node: the reference's own 32-byte `small_bvh2_node` layout (bvh2/node.rs:12-36):
+// {min.xyz, prim_count, max.xyz, first_index} = two 16-byte vectors. Expanded to the 48-byte default layout only
+// on download.
+// ----------------------------------------------------------------------------------------------------------
+struct __align__(16) Node32 {
+    float minx, miny, minz;
+    u32 prim_count;
+    float maxx, maxy, maxz;
+    u32 first_index;
+};
+static_assert(sizeof(Node32) == 32, "Node32");
+
+struct Box {
+    float minx, miny, minz, maxx, maxy, maxz;
+};
+
+__device__ __forceinline__ float smin(float a, float b) { return a < b ? a : b; }  // _mm_min_ps(a,b)
+__device__ __forceinline__ float smax(float a, float b) { return a > b ? a : b; }  // _mm_max_ps(a,b)
+
+// aabb.rs:84-89  self.union(other): min(self,other), max(self,other) per lane
+__device__ __forceinline__ Box box_union(const Box& a, const Box& b) {
+    Box r;
+    r.minx = smin(a.minx, b.minx);
+    r.miny = smin(a.miny, b.miny);
+    r.minz = smin(a.minz, b.minz);
+    r.maxx = smax(a.maxx, b.maxx);
+    r.maxy = smax(a.maxy, b.maxy);
+    r.maxz = smax(a.maxz, b.maxz);
+    return r;
+}
+// aabb.rs:151-154  (d.x + d.y) * d.z + d.x * d.y, no contraction
+__device__ __forceinline__ float box_half_area(const Box& a) {
+    float dx = __fsub_rn(a.maxx, a.minx), dy = __fsub_rn(a.maxy, a.miny), dz = __fsub_rn(a.maxz, a.minz);
+    return __fadd_rn(__fmul_rn(__fadd_rn(dx, dy), dz), __fmul_rn(dx, dy));
+}
+__device__ __forceinline__ Box node_box(const Node32& n) { return Box{n.minx, n.miny, n.minz, n.maxx, n.maxy, n.maxz}; }
+__device__ __forceinline__ Node32 make_node32(const Box& b, u32 prim_count, u32 first_index) {
+    Node32 n;
+    n.minx = b.minx; n.miny = b.miny; n.minz = b.minz; n.prim_count = prim_count;
+    n.maxx = b.maxx; n.maxy = b.maxy; n.maxz = b.maxz; n.first_index = first_index;
+    return n;
+}
+__device__ __forceinline__ Node32 load_node(const Node32* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = q[0], b = q[1];
+    Node32 n;
+    n.minx = a.x; n.miny = a.y; n.minz = a.z; n.prim_count = __float_as_uint(a.w);
+    n.maxx = b.x; n.maxy = b.y; n.maxz = b.z; n.first_index = __float_as_uint(b.w);
+    return n;
+}
+// L2-coherent load (bypasses the non-coherent L1) for data written by other CTAs of the same launch
+__device__ __forceinline__ Node32 load_node_cg(const Node32* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = __ldcg(q), b = __ldcg(q + 1);
+    Node32 n;
+    n.minx = a.x; n.miny = a.y; n.minz = a.z; n.prim_count = __float_as_uint(a.w);
+    n.maxx = b.x; n.maxy = b.y; n.maxz = b.z; n.first_index = __float_as_uint(b.w);
+    return n;
+}
+__device__ __forceinline__ void store_node(Node32* p, const Node32& n) {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(n.minx, n.miny, n.minz, __uint_as_float(n.prim_count));
+    q[1] = make_float4(n.maxx, n.maxy, n.maxz, __uint_as_float(n.first_index));
+}
+// bvh2/node.rs:154-180: siblings are adjacent, the left one has an odd index
+__device__ __host__ __forceinline__ u32 sibling_id(u32 id) { return (id & 1u) ? id + 1 : id - 1; }
+__device__ __host__ __forceinline__ u32 left_sibling_id(u32 id) { return (id & 1u) ? id : id - 1; }
+
+// ----------------------------------------------------------------------------------------------------------
+// Host-side objects
+// ----------------------------------------------------------------------------------------------------------
+struct ObvhsContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::string last_error;
+    u64 launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* pinned = nullptr;  // 4 KB of pinned host memory for small read-backs
+    int sm_count = OBVHS_SM_COUNT;
+};
+
+struct ObvhsBvh2 {
+    int device = 0;
+    Node32* nodes = nullptr;          // node_count
+    u32* primitive_indices = nullptr;  // prim_count
+    u32* parents = nullptr;            // node_count, or null when not computed (Bvh2::parents: Option)
+    size_t node_count = 0, prim_count = 0;
+    size_t max_depth = 96;  // bvh2/mod.rs:87 DEFAULT_MAX_STACK_DEPTH
+    size_t ploc_iterations = 0;
+    bool children_are_ordered_after_parents = false;
+};
+
+struct ObvhsCwBvh {
+    int device = 0;
+    ObvhsCwBvhNode* nodes = nullptr;
+    u32* primitive_indices = nullptr;
+    ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices, or null
+    size_t node_count = 0, prim_count = 0;
+    ObvhsAabb total_aabb = {};
+};
+
+#define OBVHS_SET_ERR(ctx, ...)                       \
+    do {                                              \
+        char _b[512];                                 \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);        \
+        (ctx)->last_error = _b;                       \
+    } while (0)
+
+#define CU_TRY(ctx, expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            OBVHS_SET_ERR(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return OBVHS_ERR_CUDA;                                                                  \
+        }                                                                                           \
+    } while (0)
+
+#define ST_TRY(expr)              \
+    do {                          \
+        int _s = (expr);          \
+        if (_s != OBVHS_OK) return _s; \
+    } while (0)
+
+// checks the launch and counts it (obvhs_cuda_launch_count)
+#define KERNEL_CHECK(ctx)                      \
+    do {                                       \
+        (ctx)->launches++;                     \
+        CU_TRY(ctx, cudaGetLastError());       \
+    } while (0)
+
+static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// stream-ordered scratch allocation that frees itself (cudaFreeAsync) at scope exit
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        if (count == 0) count = 1;
+        return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    T* take() {
+        T* q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+// true when ptr is device (or managed) memory
+bool obvhs_is_device_ptr(const void* ptr);
+// Returns a device view of `src` (count elements of T). Host memory is copied into `stage` on the stream.
+template <class T>
+static inline int stage_in(ObvhsContext* ctx, const T* src, size_t count, DevBuf<T>& stage, const T** out) {
+    if (count == 0 || src == nullptr) {
+        *out = nullptr;
+        return OBVHS_OK;
+    }
+    if (obvhs_is_device_ptr(src)) {
+        *out = src;
+        return OBVHS_OK;
+    }
+    CU_TRY(ctx, stage.alloc(count, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(stage.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = stage.p;
+    return OBVHS_OK;
+}
+// copies device data to a caller pointer that may be host or device; host copies are synchronised
+template <class T>
+static inline int copy_out(ObvhsContext* ctx, T* dst, const T* src_dev, size_t count) {
+    if (!dst || count == 0) return OBVHS_OK;
+    if (obvhs_is_device_ptr(dst)) {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, src_dev, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, src_dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return OBVHS_OK;
+}
+
+// ---- stage entry points implemented across the .cu files ---------------------------------------------------
+// ploc.cu
+struct PlocMortonOut {
+    u64* codes_lo = nullptr;  // device, original order (optional)
+    u64* codes_hi = nullptr;
+    u32* order = nullptr;
+    ObvhsAabb* total = nullptr;  // device, 1 element
+};
+int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
+                      u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
+                      const PlocMortonOut* probe);
+// sort.cu : stable LSD radix sort (onesweep) of (key, value) pairs; keys in `keys` / `vals`, scratch in *_alt.
+// On return *sorted_keys / *sorted_vals point at whichever buffer holds the result.
+int radix_sort_pairs_u64(ObvhsContext* ctx, u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, size_t n, int key_bytes,
+                         u64** sorted_keys, u32** sorted_vals);
+int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals, u32* vals_alt, size_t n, int key_bytes,
+                         u32** sorted_keys, u32** sorted_vals);
+// bvh2.cu
+int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+// reinsertion.cu
+int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);
+// cwbvh_build.cu
+int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out);
+// traverse.cu
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
+                          u64* d_counters);
+int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
+int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays);

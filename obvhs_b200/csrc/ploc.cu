@@ -1,0 +1,515 @@
+// ploc.cu -- PLOC BVH2 build on one B200 (sm_100a).
+//
+// Replaces PlocBuilder::build / build_with_bvh / build_ploc / build_ploc_from_leaves  (src/ploc/mod.rs:95-503),
+// sort_nodes_by_morton (:771-847) and morton_encode_u64_unorm (src/ploc/morton.rs:35-58):
+//   K1  leaf_init_kernel      leaf nodes + scene AABB (block reduce -> 6 ordered-int atomics)      ploc/mod.rs:187-243
+//   K2  morton_kernel         f64 normalise, 21 bits/axis, bit interleave                         ploc/mod.rs:287-288,782-785
+//   K3  onesweep radix sort   (sort.cu), stable: ties by ascending original index                  ploc/mod.rs:811-827
+//   K4  gather_nodes_kernel   nodes into sorted order                                             ploc/mod.rs:829-846
+//   K5  ploc_search_kernel    radius-r nearest neighbour; window staged in smem by a TMA bulk copy ploc/mod.rs:329-419,575-651
+//   K6  ploc_merge_kernel     the reference's SEQUENTIAL merge sweep restated as flags + a decoupled-look-back scan
+//                             (kept/parent outputs, merges) + scatter                             ploc/mod.rs:420-487
+// Node order, child slots (allocated from the END of bvh.nodes in sweep order) and AABB bits equal the sequential
+// reference sweep exactly.
+#include "common.cuh"
+
+namespace {
+
+// ---- ordered-int float atomics -----------------------------------------------------------------------------
+__device__ __forceinline__ u32 f2ord(float f) {
+    u32 u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(u32 o) {
+    u32 u = o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu);
+    return __uint_as_float(u);
+}
+
+struct PlocState {       // device-side loop state, double buffered by iteration parity
+    u32 count;           // nodes alive in this iteration
+    u32 insert_index;    // ploc/mod.rs:464-469 running allocator, counts DOWN from 2n-1
+};
+struct PlocGlobals {
+    u32 total_ord[6];    // scene AABB as ordered ints: min xyz (atomicMin), max xyz (atomicMax)
+    u32 nan_flag;
+    u32 pad;
+    double scale[3], offset[3];  // ploc/mod.rs:287-288
+    float total[8];      // decoded scene AABB (Aabb layout)
+    PlocState state[2];
+    u32 ticket;
+    u32 pad2;
+};
+
+__global__ void ploc_globals_init_kernel(PlocGlobals* g, u32 n) {
+    if (threadIdx.x < 3) {
+        g->total_ord[threadIdx.x] = 0xffffffffu;
+        g->total_ord[3 + threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) {
+        g->nan_flag = 0;
+        g->state[0].count = n;
+        g->state[0].insert_index = 2 * n - 1;
+        g->state[1].count = 0;
+        g->state[1].insert_index = 0;
+        g->ticket = 0;
+    }
+}
+
+// K1. One leaf per primitive: Bvh2Node::new(aabb, 1, prim_index) (ploc/mod.rs:188-194). TRIS: the AABB comes from
+// Triangle::aabb (triangle.rs:28-30 -> Aabb::from_points: first vertex, then extend with v1, v2).
+template <bool TRIS>
+__global__ void __launch_bounds__(256) leaf_init_kernel(const float4* __restrict__ src, const u32* __restrict__ indices, u32 n,
+                                                        Node32* __restrict__ leaves, PlocGlobals* g) {
+    float mnx = __int_as_float(0x7f800000), mny = mnx, mnz = mnx, mxx = -mnx, mxy = -mnx, mxz = -mnx;
+    bool nan = false;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Box b;
+        if (TRIS) {
+            float4 v0 = __ldg(src + (size_t)i * 3), v1 = __ldg(src + (size_t)i * 3 + 1), v2 = __ldg(src + (size_t)i * 3 + 2);
+            b.minx = smin(smin(v0.x, v1.x), v2.x); b.miny = smin(smin(v0.y, v1.y), v2.y); b.minz = smin(smin(v0.z, v1.z), v2.z);
+            b.maxx = smax(smax(v0.x, v1.x), v2.x); b.maxy = smax(smax(v0.y, v1.y), v2.y); b.maxz = smax(smax(v0.z, v1.z), v2.z);
+        } else {
+            float4 lo = __ldg(src + (size_t)i * 2), hi = __ldg(src + (size_t)i * 2 + 1);
+            b = Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+        }
+        nan |= (b.minx != b.minx) | (b.miny != b.miny) | (b.minz != b.minz) | (b.maxx != b.maxx) | (b.maxy != b.maxy) | (b.maxz != b.maxz);
+        store_node(leaves + i, make_node32(b, 1u, indices ? indices[i] : i));
+        // total_aabb.extend(min).extend(max) (ploc/mod.rs:189-190): min and max of both corners
+        mnx = fminf(mnx, fminf(b.minx, b.maxx)); mny = fminf(mny, fminf(b.miny, b.maxy)); mnz = fminf(mnz, fminf(b.minz, b.maxz));
+        mxx = fmaxf(mxx, fmaxf(b.minx, b.maxx)); mxy = fmaxf(mxy, fmaxf(b.miny, b.maxy)); mxz = fmaxf(mxz, fmaxf(b.minz, b.maxz));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+    __shared__ float red[8][6];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[w][0] = mnx; red[w][1] = mny; red[w][2] = mnz; red[w][3] = mxx; red[w][4] = mxy; red[w][5] = mxz;
+    }
+    if (__syncthreads_or(nan) && threadIdx.x == 0) g->nan_flag = 1;
+    if (threadIdx.x < 6) {
+        float v = red[0][threadIdx.x];
+        for (int k = 1; k < 8; k++) v = threadIdx.x < 3 ? fminf(v, red[k][threadIdx.x]) : fmaxf(v, red[k][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&g->total_ord[threadIdx.x], f2ord(v));
+        else atomicMax(&g->total_ord[threadIdx.x], f2ord(v));
+    }
+}
+
+// ploc/mod.rs:287-288: scale = 1/diag (f64), offset = -min*scale. diag is computed in f32 (aabb.rs:106-108) then widened.
+__global__ void morton_params_kernel(PlocGlobals* g) {
+    int k = threadIdx.x;
+    if (k < 3) {
+        float mn = ord2f(g->total_ord[k]), mx = ord2f(g->total_ord[3 + k]);
+        float diag = mx - mn;
+        double scale = 1.0 / (double)diag;
+        g->scale[k] = scale;
+        g->offset[k] = -(double)mn * scale;
+        g->total[k] = mn;
+        g->total[4 + k] = mx;
+    }
+    if (k == 3) g->total[3] = g->total[7] = 0.f;
+}
+
+// morton.rs:35-44
+__device__ __forceinline__ u64 split_by_3_u64(u32 a) {
+    u64 x = (u64)a & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+// K2. ploc/mod.rs:782-785: center (f32) -> f64 * scale + offset (mul then add, no FMA) -> morton_encode_u64_unorm.
+// `as u32` saturates and maps NaN to 0 == cvt.rzi.u32.f64 (__double2uint_rz).
+__global__ void __launch_bounds__(256) morton_kernel(const Node32* __restrict__ leaves, u32 n, const PlocGlobals* __restrict__ g,
+                                                     u64* __restrict__ keys, u32* __restrict__ vals) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Node32 nd = load_node(leaves + i);
+    float cx = (nd.maxx + nd.minx) * 0.5f, cy = (nd.maxy + nd.miny) * 0.5f, cz = (nd.maxz + nd.minz) * 0.5f;  // aabb.rs:113-115
+    double px = __dadd_rn(__dmul_rn((double)cx, g->scale[0]), g->offset[0]);
+    double py = __dadd_rn(__dmul_rn((double)cy, g->scale[1]), g->offset[1]);
+    double pz = __dadd_rn(__dmul_rn((double)cz, g->scale[2]), g->offset[2]);
+    u32 x = __double2uint_rz(__dmul_rn(px, 2097152.0)), y = __double2uint_rz(__dmul_rn(py, 2097152.0)),
+        z = __double2uint_rz(__dmul_rn(pz, 2097152.0));
+    keys[i] = split_by_3_u64(x) | split_by_3_u64(y) << 1 | split_by_3_u64(z) << 2;
+    vals[i] = i;
+}
+
+// K4. ploc/mod.rs:829: sorted[i] = leaves[order[i]]
+__global__ void __launch_bounds__(256) gather_nodes_kernel(const Node32* __restrict__ leaves, const u32* __restrict__ order, u32 n,
+                                                           Node32* __restrict__ sorted) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;  // two threads per node, one float4 each
+    if (t >= 2 * n) return;
+    u32 i = t >> 1, h = t & 1;
+    reinterpret_cast<float4*>(sorted)[t] = __ldg(reinterpret_cast<const float4*>(leaves + order[i]) + h);
+}
+
+// ---- TMA bulk copy (global -> shared, 1-D) completing on an mbarrier -----------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+constexpr int SEARCH_TILE = 256;
+
+__device__ __forceinline__ Box smem_box(const Node32* w, int j) {
+    const float4* q = reinterpret_cast<const float4*>(w + j);
+    float4 a = q[0], b = q[1];
+    return Box{a.x, a.y, a.z, b.x, b.y, b.z};
+}
+
+// K5. One thread per node. The tile's window [tile-R, tile+TILE+R) of sorted cluster AABBs is brought into shared
+// memory by one TMA bulk copy. r1: the reference's r=1 fast path (ploc/mod.rs:329-382): -1 iff cost(i-1,i) < cost(i,i+1),
+// first element +1, last element -1. Otherwise find_best_node (ploc/mod.rs:624-650): scan i-R..i-1 then i+1..i+R with
+// `cost <= best` so the LAST minimum wins; cost(lo,hi) = half_area(union(nodes[lo], nodes[hi])) with the lower index first.
+template <int R>
+__global__ void __launch_bounds__(SEARCH_TILE) ploc_search_kernel(const Node32* __restrict__ cur, const PlocGlobals* __restrict__ g,
+                                                                  int parity, int r1, signed char* __restrict__ merge, u64* scan_status,
+                                                                  u32* ticket) {
+    __shared__ __align__(128) Node32 win[SEARCH_TILE + 2 * R];
+    __shared__ __align__(8) u64 bar;
+    const u32 count = g->state[parity].count;
+    // reset the chained-scan state the merge kernel of this iteration uses
+    if (threadIdx.x == 0) {
+        scan_status[blockIdx.x] = 0;
+        if (blockIdx.x == 0) *ticket = 0;
+    }
+    const u32 tile0 = blockIdx.x * SEARCH_TILE;
+    if (tile0 >= count) return;
+    const u32 lo = tile0 >= (u32)R ? tile0 - R : 0u;
+    const u32 hi = min(count, tile0 + SEARCH_TILE + R);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        u32 bytes = (hi - lo) * (u32)sizeof(Node32);
+        mbar_expect_tx(&bar, bytes);
+        tma_bulk_g2s(win, cur + lo, bytes, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const u32 i = tile0 + threadIdx.x;
+    if (i >= count) return;
+    const int li = (int)(i - lo);
+    const Box me = smem_box(win, li);
+    int off;
+    if (r1) {
+        if (i == count - 1) {
+            off = -1;
+        } else {
+            float last = i > 0 ? box_half_area(box_union(smem_box(win, li - 1), me)) : __int_as_float(0x7f800000);
+            float cost = box_half_area(box_union(me, smem_box(win, li + 1)));
+            off = last < cost ? -1 : 1;
+        }
+    } else {
+        int best = 0;
+        float best_cost = __int_as_float(0x7f800000);
+        const int nb = (int)min((u32)R, i), ne = (int)min((u32)R, count - 1 - i);
+        for (int o = -nb; o < 0; o++) {
+            float c = box_half_area(box_union(smem_box(win, li + o), me));
+            if (c <= best_cost) {
+                best = o;
+                best_cost = c;
+            }
+        }
+        for (int o = 1; o <= ne; o++) {
+            float c = box_half_area(box_union(me, smem_box(win, li + o)));
+            if (c <= best_cost) {
+                best = o;
+                best_cost = c;
+            }
+        }
+        off = best;
+    }
+    merge[i] = (signed char)off;
+}
+
+constexpr int MERGE_THREADS = 256, MERGE_ITEMS = 4, MERGE_TILE = MERGE_THREADS * MERGE_ITEMS;
+constexpr int MERGE_HALO = 32;  // >= largest search distance
+constexpr u64 SCAN_AGG = 1ull << 62, SCAN_INCL = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
+
+// K6. The sequential sweep of ploc/mod.rs:423-487 visits index = 0..count: a node whose choice is not mutual is
+// carried to `next`; of a mutual pair the LOWER index is skipped and the HIGHER index emits the parent at its own
+// position, with left = nodes[higher], right = nodes[lower] stored at insert_index-2, -1 (slots taken downwards in
+// sweep order). Positions are therefore exclusive prefix sums of (carried | emits) and of (emits): one chained scan
+// over a packed (outputs, merges) pair.
+__global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32* __restrict__ cur, Node32* __restrict__ next,
+                                                                   Node32* __restrict__ bvh_nodes, const signed char* __restrict__ merge,
+                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket) {
+    __shared__ signed char sm[MERGE_TILE + 2 * MERGE_HALO];
+    __shared__ u64 s_wsum[MERGE_THREADS / 32];
+    __shared__ u64 s_excl;
+    __shared__ u32 s_tile;
+    const u32 count = g->state[parity].count;
+    const u32 insert_base = g->state[parity].insert_index;
+    const u32 tiles = (count + MERGE_TILE - 1) / MERGE_TILE;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= tiles) return;
+    const u32 tile0 = tile * MERGE_TILE;
+    for (int j = threadIdx.x; j < MERGE_TILE + 2 * MERGE_HALO; j += MERGE_THREADS) {
+        long long gi = (long long)tile0 - MERGE_HALO + j;
+        sm[j] = (gi >= 0 && gi < (long long)count) ? merge[gi] : (signed char)0;
+    }
+    __syncthreads();
+    u32 flags = 0;  // per item: bit0 = writes an output, bit1 = emits a parent
+    u64 local = 0;
+#pragma unroll
+    for (int k = 0; k < MERGE_ITEMS; k++) {
+        u32 i = tile0 + threadIdx.x * MERGE_ITEMS + k;
+        if (i < count) {
+            int li = threadIdx.x * MERGE_ITEMS + k + MERGE_HALO;
+            int m = sm[li];
+            int mb = sm[li + m];
+            bool mutual = (m + mb) == 0;
+            bool emits = mutual && m < 0;
+            bool outp = !mutual || emits;
+            flags |= (outp ? 1u : 0u) << (2 * k) | (emits ? 2u : 0u) << (2 * k);
+            local += (outp ? 1ull : 0ull) + (emits ? (1ull << 31) : 0ull);
+        }
+    }
+    // block exclusive scan of the packed pair
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u64 x = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_wsum[w] = x;
+    __syncthreads();
+    u64 wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < MERGE_THREADS / 32; k++) {
+        u64 s = s_wsum[k];
+        if (k < w) wbase += s;
+        total += s;
+    }
+    u64 thread_excl = wbase + x - local;
+    // decoupled look-back over tiles (one thread)
+    if (threadIdx.x == 0) {
+        volatile u64* st = scan_status;
+        u64 excl = 0;
+        if (tile == 0) {
+            st[0] = SCAN_INCL | total;
+        } else {
+            st[tile] = SCAN_AGG | total;
+            u32 t = tile - 1;
+            for (;;) {
+                u64 s = st[t];
+                if (s & SCAN_INCL) {
+                    excl += s & SCAN_MASK;
+                    break;
+                }
+                if (s & SCAN_AGG) {
+                    excl += s & SCAN_MASK;
+                    t--;
+                }
+            }
+            st[tile] = SCAN_INCL | (excl + total);
+        }
+        s_excl = excl;
+        if (tile == tiles - 1) {  // loop state of the next iteration
+            u64 all = excl + total;
+            u32 outs = (u32)(all & 0x7fffffffull), merges = (u32)(all >> 31);
+            g->state[parity ^ 1].count = outs;
+            g->state[parity ^ 1].insert_index = insert_base - 2 * merges;
+        }
+    }
+    __syncthreads();
+    u64 run = s_excl + thread_excl;
+#pragma unroll
+    for (int k = 0; k < MERGE_ITEMS; k++) {
+        u32 f = (flags >> (2 * k)) & 3u;
+        if (f & 1u) {
+            u32 i = tile0 + threadIdx.x * MERGE_ITEMS + k;
+            u32 pos = (u32)(run & 0x7fffffffull);
+            Node32 left = load_node(cur + i);
+            if (f & 2u) {
+                u32 mi = (u32)(run >> 31);
+                int m = sm[threadIdx.x * MERGE_ITEMS + k + MERGE_HALO];
+                Node32 right = load_node(cur + (i + m));
+                u32 slot = insert_base - 2 * (mi + 1);
+                store_node(bvh_nodes + slot, left);
+                store_node(bvh_nodes + slot + 1, right);
+                store_node(next + pos, make_node32(box_union(node_box(left), node_box(right)), 0u, slot));
+                run += 1ull + (1ull << 31);
+            } else {
+                store_node(next + pos, left);
+                run += 1ull;
+            }
+        }
+    }
+}
+
+__global__ void ploc_finish_kernel(const Node32* __restrict__ cur, Node32* __restrict__ bvh_nodes) {
+    if (threadIdx.x < 2) reinterpret_cast<float4*>(bvh_nodes)[threadIdx.x] = reinterpret_cast<const float4*>(cur)[threadIdx.x];  // ploc/mod.rs:499
+}
+
+__global__ void iota_kernel(u32* p, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+template <int R>
+void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGlobals* g, int parity, int r1, signed char* merge,
+                   u64* scan_status, u32* ticket) {
+    ploc_search_kernel<R><<<div_up(count, SEARCH_TILE), SEARCH_TILE, 0, ctx->stream>>>(cur, g, parity, r1, merge, scan_status, ticket);
+}
+
+}  // namespace
+
+int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
+                      u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
+                      const PlocMortonOut* probe) {
+    if (sort_precision != 64) {
+        OBVHS_SET_ERR(ctx, "SortPrecision::U128 is not implemented on the GPU path yet (ploc/mod.rs:686-701)");
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    switch (search_distance) {  // PlocSearchDistance::from(u32), ploc/mod.rs:550-562
+        case 1: case 2: case 6: case 14: case 24: case 32: break;
+        default:
+            OBVHS_SET_ERR(ctx, "search distance %u is not one of 1,2,6,14,24,32", search_distance);
+            return OBVHS_ERR_INVALID_ARG;
+    }
+    if (n >= (1u << 30)) {
+        OBVHS_SET_ERR(ctx, "too many primitives: %zu", n);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = ctx->stream;
+    ObvhsBvh2* bvh = new ObvhsBvh2();
+    bvh->device = ctx->device;
+    bvh->prim_count = n;
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }
+    } guard{bvh};
+    // bvh2/mod.rs:106-121 reset_for_reuse: primitive_indices = indices
+    if (n) {
+        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->primitive_indices, n * 4, s));
+        if (d_indices) CU_TRY(ctx, cudaMemcpyAsync(bvh->primitive_indices, d_indices, n * 4, cudaMemcpyDeviceToDevice, s));
+        else {
+            iota_kernel<<<div_up(n, 256), 256, 0, s>>>(bvh->primitive_indices, (u32)n);
+            KERNEL_CHECK(ctx);
+        }
+    }
+    if (n == 0) {  // ploc/mod.rs:183-185
+        if (probe && probe->total) CU_TRY(ctx, cudaMemsetAsync(probe->total, 0, sizeof(ObvhsAabb), s));
+        guard.b = nullptr;
+        *out = bvh;
+        return OBVHS_OK;
+    }
+    const u32 un = (u32)n;
+    bvh->node_count = 2 * n - 1;
+    CU_TRY(ctx, cudaMallocAsync((void**)&bvh->nodes, bvh->node_count * sizeof(Node32), s));
+
+    DevBuf<PlocGlobals> g;
+    DevBuf<Node32> bufA, bufB;
+    DevBuf<u64> keys, keys_alt;
+    DevBuf<u32> vals, vals_alt;
+    DevBuf<signed char> merge;
+    DevBuf<u64> scan_status;
+    CU_TRY(ctx, g.alloc(1, s));
+    CU_TRY(ctx, bufA.alloc(n, s));
+    CU_TRY(ctx, bufB.alloc(n, s));
+    CU_TRY(ctx, keys.alloc(n, s));
+    CU_TRY(ctx, keys_alt.alloc(n, s));
+    CU_TRY(ctx, vals.alloc(n, s));
+    CU_TRY(ctx, vals_alt.alloc(n, s));
+    CU_TRY(ctx, merge.alloc(n, s));
+    CU_TRY(ctx, scan_status.alloc(div_up(n, SEARCH_TILE) + 1, s));
+
+    ploc_globals_init_kernel<<<1, 32, 0, s>>>(g.p, un);
+    KERNEL_CHECK(ctx);
+    const int grid_stride_blocks = (int)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 8);
+    if (d_tris) leaf_init_kernel<true><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_tris), d_indices, un, bufA.p, g.p);
+    else leaf_init_kernel<false><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_aabbs), d_indices, un, bufA.p, g.p);
+    KERNEL_CHECK(ctx);
+    morton_params_kernel<<<1, 32, 0, s>>>(g.p);
+    KERNEL_CHECK(ctx);
+    morton_kernel<<<div_up(n, 256), 256, 0, s>>>(bufA.p, un, g.p, keys.p, vals.p);
+    KERNEL_CHECK(ctx);
+    if (probe) {
+        if (probe->codes_lo) CU_TRY(ctx, cudaMemcpyAsync(probe->codes_lo, keys.p, n * 8, cudaMemcpyDeviceToDevice, s));
+        if (probe->codes_hi) CU_TRY(ctx, cudaMemsetAsync(probe->codes_hi, 0, n * 8, s));
+        if (probe->total) CU_TRY(ctx, cudaMemcpyAsync(probe->total, g.p->total, sizeof(ObvhsAabb), cudaMemcpyDeviceToDevice, s));
+    }
+    u64* skeys;
+    u32* order;
+    ST_TRY(radix_sort_pairs_u64(ctx, keys.p, keys_alt.p, vals.p, vals_alt.p, n, 8, &skeys, &order));
+    if (probe && probe->order) CU_TRY(ctx, cudaMemcpyAsync(probe->order, order, n * 4, cudaMemcpyDeviceToDevice, s));
+    gather_nodes_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(bufA.p, order, un, bufB.p);
+    KERNEL_CHECK(ctx);
+
+    Node32 *cur = bufB.p, *next = bufA.p;
+    u32* h_state = reinterpret_cast<u32*>(ctx->pinned);
+    u32 count = un;
+    size_t depth = 0;
+    while (count > 1) {
+        const int parity = (int)(depth & 1);
+        const int r1 = (search_distance == 1 || depth < search_depth_threshold) ? 1 : 0;
+        u32* ticket = &g.p->ticket;
+        switch (search_distance) {
+            case 1: launch_search<1>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+            case 2: launch_search<2>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+            case 6: launch_search<6>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+            case 14: launch_search<14>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+            case 24: launch_search<24>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+            default: launch_search<32>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+        }
+        KERNEL_CHECK(ctx);
+        ploc_merge_kernel<<<div_up(count, MERGE_TILE), MERGE_THREADS, 0, s>>>(cur, next, bvh->nodes, merge.p, g.p, parity, scan_status.p,
+                                                                            ticket);
+        KERNEL_CHECK(ctx);
+        CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[parity ^ 1], sizeof(PlocState), cudaMemcpyDeviceToHost, s));
+        if (depth == 0) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        if (depth == 0 && h_state[4]) {
+            OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
+            return OBVHS_ERR_NAN_INPUT;
+        }
+        u32 new_count = h_state[0];
+        if (new_count >= count || new_count == 0) {
+            OBVHS_SET_ERR(ctx, "PLOC made no progress (count %u -> %u); non-finite AABBs?", count, new_count);
+            return OBVHS_ERR_NAN_INPUT;
+        }
+        count = new_count;
+        std::swap(cur, next);
+        depth++;
+    }
+    ploc_finish_kernel<<<1, 32, 0, s>>>(cur, bvh->nodes);
+    KERNEL_CHECK(ctx);
+    bvh->max_depth = std::max<size_t>(96, depth + 1);  // ploc/mod.rs:501
+    bvh->ploc_iterations = depth;
+    bvh->children_are_ordered_after_parents = true;  // ploc/mod.rs:502
+    guard.b = nullptr;
+    *out = bvh;
+    return OBVHS_OK;
+}

@@ -1,0 +1,228 @@
+// sort.cu -- stable LSD radix sort of (key, u32 value) pairs: "onesweep" (one read + one write of the pairs per
+// 8-bit digit, chained-scan / decoupled look-back across tiles) with warp-level multisplit ranking (__match_any).
+//
+// Replaces the reference's sorts on the hot path:
+//   Morton sort            src/ploc/mod.rs:811-827  (par_sort_unstable_by_key / sort_unstable_by_key / rdst radix)
+//   candidate sort         src/bvh2/reinsertion.rs:138 (rdst radix on -cost, 4 levels :224-231)
+//   gain sort              src/bvh2/reinsertion.rs:167-173
+// The reference's sorts are unstable and tie order is unpinned; the contract shared with the oracle is
+// "ties keep ascending original order", i.e. a STABLE sort. Stability here comes from: tiles are taken in ticket
+// order and chained by look-back; inside a tile warps own consecutive chunks; inside a warp items are ranked item by
+// item with lanes ordered by lane id (warp-striped layout == memory order).
+#include "common.cuh"
+
+namespace {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
+constexpr u32 FLAG_AGG = 1u << 30, FLAG_INCL = 2u << 30, STATUS_MASK = (1u << 30) - 1;
+
+// all digit histograms in one read of the keys
+template <typename K>
+__global__ void __launch_bounds__(256) sort_hist_kernel(const K* __restrict__ keys, size_t n, int passes, u32* __restrict__ ghist) {
+    __shared__ u32 sh[8 * 256];
+    for (int t = threadIdx.x; t < passes * 256; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        K k = keys[i];
+        for (int p = 0; p < passes; p++) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < passes * 256; t += blockDim.x) {
+        u32 c = sh[t];
+        if (c) atomicAdd(&ghist[t], c);
+    }
+}
+
+// exclusive scan of each pass's 256 bins (one block per pass)
+__global__ void __launch_bounds__(256) sort_scan_kernel(const u32* __restrict__ ghist, u32* __restrict__ goffs) {
+    __shared__ u32 wsum[8];
+    int d = threadIdx.x, lane = d & 31, w = d >> 5;
+    u32 c = ghist[blockIdx.x * 256 + d];
+    u32 x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    u32 base = 0;
+    for (int k = 0; k < w; k++) base += wsum[k];
+    goffs[blockIdx.x * 256 + d] = base + x - c;
+}
+
+__device__ __forceinline__ u32 ld_status(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
+__device__ __forceinline__ void st_status(u32* p, u32 v) { *reinterpret_cast<volatile u32*>(p) = v; }
+
+template <typename K, bool WRITE_KEYS>
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+                                                                const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
+                                                                int shift, const u32* __restrict__ goffs, u32* status, u32* ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* skeys = reinterpret_cast<K*>(smem_raw);
+    u32* svals = reinterpret_cast<u32*>(skeys + SORT_TILE);
+    u32* whist = svals + SORT_TILE;          // [SORT_WARPS][256] per-warp digit counts -> exclusive offsets across warps
+    u32* dstart = whist + SORT_WARPS * 256;  // [256] start of each digit inside the tile
+    u32* gbase = dstart + 256;               // [256] global position of local position 0 of each digit
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wsum[SORT_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int k = 0; k < SORT_WARPS; k++) whist[k * 256 + tid] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const size_t base = (size_t)tile * SORT_TILE;
+    const u32 valid = (u32)min((size_t)SORT_TILE, n - base);
+    const size_t wstart = base + (size_t)warp * (SORT_ITEMS * 32);
+
+    K key[SORT_ITEMS];
+    u32 val[SORT_ITEMS];
+    u32 rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        size_t idx = wstart + i * 32 + lane;
+        bool ok = idx < n;
+        key[i] = ok ? kin[idx] : (K)~(K)0;  // padding sorts behind every valid key of the tile
+        val[i] = ok ? vin[idx] : 0u;
+    }
+    u32* mywh = whist + warp * 256;
+    const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        u32 d = (u32)((key[i] >> shift) & 0xff);
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 pre = mywh[d];
+        rank[i] = pre + __popc(peers & lt);
+        __syncwarp();
+        if ((peers & lt) == 0) mywh[d] = pre + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit `tid`: exclusive scan across warps, tile count
+    u32 run = 0;
+#pragma unroll
+    for (int k = 0; k < SORT_WARPS; k++) {
+        u32 c = whist[k * 256 + tid];
+        whist[k * 256 + tid] = run;
+        run += c;
+    }
+    // exclusive scan over digits -> dstart
+    u32 x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    u32 wbase = 0;
+    for (int k = 0; k < warp; k++) wbase += s_wsum[k];
+    const u32 my_start = wbase + x - run;
+    dstart[tid] = my_start;
+    // decoupled look-back per digit; padding keys all carry digit 255 and are not counted
+    u32 agg = run - ((tid == 255) ? (SORT_TILE - valid) : 0u);
+    u32 excl = 0;
+    u32* st = status + (size_t)tile * 256 + tid;
+    if (tile == 0) {
+        st_status(st, FLAG_INCL | agg);
+    } else {
+        st_status(st, FLAG_AGG | agg);
+        const u32* prev = st - 256;
+        for (;;) {
+            u32 s = ld_status(prev);
+            if (s & FLAG_INCL) {
+                excl += s & STATUS_MASK;
+                break;
+            }
+            if (s & FLAG_AGG) {
+                excl += s & STATUS_MASK;
+                prev -= 256;
+            }
+        }
+        st_status(st, FLAG_INCL | (excl + agg));
+    }
+    gbase[tid] = goffs[tid] + excl - my_start;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        u32 d = (u32)((key[i] >> shift) & 0xff);
+        u32 pos = dstart[d] + mywh[d] + rank[i];
+        skeys[pos] = key[i];
+        svals[pos] = val[i];
+    }
+    __syncthreads();
+    for (u32 j = tid; j < valid; j += SORT_THREADS) {
+        K k = skeys[j];
+        u32 d = (u32)((k >> shift) & 0xff);
+        u32 o = gbase[d] + j;
+        if (WRITE_KEYS) kout[o] = k;
+        vout[o] = svals[j];
+    }
+}
+
+template <typename K>
+constexpr size_t onesweep_smem() {
+    return (size_t)SORT_TILE * (sizeof(K) + 4) + (SORT_WARPS * 256 + 512) * 4;
+}
+
+template <typename K>
+int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* vals_alt, size_t n, int passes, K** sorted_keys,
+                     u32** sorted_vals) {
+    *sorted_keys = keys;
+    *sorted_vals = vals;
+    if (n < 2 || passes <= 0) return OBVHS_OK;
+    if (passes > 8 || n >= (size_t)STATUS_MASK) {
+        OBVHS_SET_ERR(ctx, "radix sort: unsupported size n=%zu passes=%d", n, passes);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    // scratch: ghist[passes*256] goffs[passes*256] ticket[passes (padded to 8)] status[passes*tiles*256]
+    const size_t words = (size_t)passes * 512 + 8 + (size_t)passes * tiles * 256;
+    DevBuf<u32> scratch;
+    CU_TRY(ctx, scratch.alloc(words, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, words * 4, ctx->stream));
+    u32* ghist = scratch.p;
+    u32* goffs = ghist + (size_t)passes * 256;
+    u32* ticket = goffs + (size_t)passes * 256;
+    u32* status = ticket + 8;
+    int hist_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    sort_hist_kernel<K><<<hist_blocks, 256, 0, ctx->stream>>>(keys, n, passes, ghist);
+    KERNEL_CHECK(ctx);
+    sort_scan_kernel<<<passes, 256, 0, ctx->stream>>>(ghist, goffs);
+    KERNEL_CHECK(ctx);
+    static bool attr_set[2] = {false, false};
+    const int which = sizeof(K) == 8 ? 1 : 0;
+    if (!attr_set[which]) {
+        CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
+        CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
+        attr_set[which] = true;
+    }
+    K *kin = keys, *kout = keys_alt;
+    u32 *vin = vals, *vout = vals_alt;
+    for (int p = 0; p < passes; p++) {
+        onesweep_kernel<K, true><<<(unsigned)tiles, SORT_THREADS, onesweep_smem<K>(), ctx->stream>>>(
+            kin, kout, vin, vout, n, 8 * p, goffs + p * 256, status + (size_t)p * tiles * 256, ticket + p);
+        KERNEL_CHECK(ctx);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    *sorted_keys = kin;
+    *sorted_vals = vin;
+    return OBVHS_OK;
+}
+
+}  // namespace
+
+int radix_sort_pairs_u64(ObvhsContext* ctx, u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, size_t n, int key_bytes,
+                         u64** sorted_keys, u32** sorted_vals) {
+    return radix_sort_pairs<u64>(ctx, keys, keys_alt, vals, vals_alt, n, key_bytes, sorted_keys, sorted_vals);
+}
+int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals, u32* vals_alt, size_t n, int key_bytes,
+                         u32** sorted_keys, u32** sorted_vals) {
+    return radix_sort_pairs<u32>(ctx, keys, keys_alt, vals, vals_alt, n, key_bytes, sorted_keys, sorted_vals);
+}

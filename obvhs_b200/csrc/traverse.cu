@@ -1,0 +1,260 @@
+// traverse.cu -- batched CWBVH ray traversal over triangles (closest hit / miss / all-hit count).
+//
+// Replaces, for a batch of rays, the reference's per-ray
+//   CwBvh::ray_traverse / ray_traverse_miss / ray_traverse_anyhit      src/cwbvh/mod.rs:169-245
+//   traverse! state machine                                            src/cwbvh/traverse_macro.rs:59-126
+//   CwBvhNode::intersect_ray (SSE2 4-wide x2 slab test)                src/cwbvh/node.rs:86-231, src/cwbvh/simd.rs:17-100
+//   Triangle::intersect (Moller-Trumbore)                              src/triangle.rs:35-76
+//
+// One ray per thread. Every ray performs the reference's exact visit order (highest set bit first for node and
+// primitive groups, remainder pushed only when non-empty, primitives of a node drained before the next node test,
+// strict t < tmax), so hit primitive ids are bit-exact including exact-t ties. The 80-byte node is
+// fetched as five 16-byte ld.global.nc vectors; the 8 child slab tests are unrolled per thread; the octant order
+// comes from the bit index (slot ^ oct_inv) packed into the hit mask; the group stack is 32 x uint2 like the
+// reference's StackStack<UVec2, 32> (saturating push).
+#include "common.cuh"
+
+namespace {
+
+constexpr float NODE_EPSILON = 0.0001f;  // cwbvh/node.rs:82 / simd.rs:83
+
+struct RayRegs {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin, tmax;
+};
+
+// triangle.rs:35-76; glam sse2 cross/dot operand order, no FMA.
+__device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, u32 id, const RayRegs& r) {
+    const float4* t = tris + (size_t)id * 3;
+    float4 a = __ldg(t), b = __ldg(t + 1), c4 = __ldg(t + 2);
+    float e1x = a.x - b.x, e1y = a.y - b.y, e1z = a.z - b.z;        // v0 - v1
+    float e2x = c4.x - a.x, e2y = c4.y - a.y, e2z = c4.z - a.z;     // v2 - v0
+    float nx = e1y * e2z - e2y * e1z, ny = e1z * e2x - e2z * e1x, nz = e1x * e2y - e2x * e1y;  // e1 x e2
+    float cx = a.x - r.ox, cy = a.y - r.oy, cz = a.z - r.oz;        // v0 - origin
+    float rx = r.dy * cz - cy * r.dz, ry = r.dz * cx - cz * r.dx, rz = r.dx * cy - cx * r.dy;  // d x c
+    float inv_det = 1.0f / ((nx * r.dx + ny * r.dy) + nz * r.dz);
+    float u = ((rx * e2x + ry * e2y) + rz * e2z) * inv_det;
+    float v = ((rx * e1x + ry * e1y) + rz * e1z) * inv_det;
+    float w = 1.0f - u - v;
+    u32 sign = __float_as_uint(u) | __float_as_uint(v) | __float_as_uint(w);
+    bool valid = (inv_det != 0.0f) && ((sign & 0x80000000u) == 0);
+    if (valid) {
+        float tt = ((nx * cx + ny * cy) + nz * cz) * inv_det;
+        if (tt >= r.tmin && tt <= r.tmax) return tt;
+    }
+    return __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ float byte_f(u32 w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+
+// node.rs:86-231 + simd.rs:17-100: returns the 32-bit hit mask (hi 8 bits inner children by octant priority,
+// lo 24 bits primitive bits).
+__device__ __forceinline__ u32 node_intersect(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
+                                              const RayRegs& r, u32 oct_inv4) {
+    float px = __uint_as_float(q0.x), py = __uint_as_float(q0.y), pz = __uint_as_float(q0.z);
+    float ex = __uint_as_float((q0.w & 0xffu) << 23), ey = __uint_as_float(((q0.w >> 8) & 0xffu) << 23),
+          ez = __uint_as_float(((q0.w >> 16) & 0xffu) << 23);  // node.rs:269-275
+    float adx = ex * r.ix, ady = ey * r.iy, adz = ez * r.iz;
+    float aox = (px - r.ox) * r.ix, aoy = (py - r.oy) * r.iy, aoz = (pz - r.oz) * r.iz;
+    bool rdx = r.dx < 0.0f, rdy = r.dy < 0.0f, rdz = r.dz < 0.0f;
+    // q2 = {min_x[0..3], min_x[4..7], max_x[0..3], max_x[4..7]}
+    u32 xlo[2] = {rdx ? q2.z : q2.x, rdx ? q2.w : q2.y}, xhi[2] = {rdx ? q2.x : q2.z, rdx ? q2.y : q2.w};
+    u32 ylo[2] = {rdy ? q3.z : q3.x, rdy ? q3.w : q3.y}, yhi[2] = {rdy ? q3.x : q3.z, rdy ? q3.y : q3.w};
+    u32 zlo[2] = {rdz ? q4.z : q4.x, rdz ? q4.w : q4.y}, zhi[2] = {rdz ? q4.x : q4.z, rdz ? q4.y : q4.w};
+    u32 meta[2] = {q1.z, q1.w};
+    u32 hit_mask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        // node.rs:207-231 get_child_and_index_bits on 4 bytes at a time
+        u32 m = meta[h];
+        u32 is_inner = (m & (m << 1)) & 0x10101010u;
+        u32 inner_mask = (is_inner >> 4) * 0xffu;
+        u32 bit_index = (m ^ (oct_inv4 & inner_mask)) & 0x1f1f1f1fu;
+        u32 child_bits = (m >> 5) & 0x07070707u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float tminx = byte_f(xlo[h], j) * adx + aox, tmaxx = byte_f(xhi[h], j) * adx + aox;
+            float tminy = byte_f(ylo[h], j) * ady + aoy, tmaxy = byte_f(yhi[h], j) * ady + aoy;
+            float tminz = byte_f(zlo[h], j) * adz + aoz, tmaxz = byte_f(zhi[h], j) * adz + aoz;
+            float tmn = smax(tminx, smax(tminy, tminz));  // simd.rs:81-84 nesting
+            float tmx = smin(tmaxx, smin(tmaxy, tmaxz));
+            tmn = smax(tmn, NODE_EPSILON);
+            tmx = smin(tmx, r.tmax);
+            if (tmn <= tmx) hit_mask |= ((child_bits >> (8 * j)) & 0xffu) << ((bit_index >> (8 * j)) & 0xffu);
+        }
+    }
+    return hit_mask;
+}
+
+// MODE 0 closest hit -> ObvhsRayHit; 1 miss -> u8; 2 all-hit count -> u32
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) traverse_kernel(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                       const float4* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                       unsigned long long* __restrict__ counters, u32 root_group) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 nodes_visited = 0, tris_tested = 0;
+    if (i < n) {
+        const float4* rp = rays + i * 4;
+        float4 ro = __ldg(rp), rd = __ldg(rp + 1), ri = __ldg(rp + 2), rt = __ldg(rp + 3);
+        RayRegs r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ri.x, ri.y, ri.z, rt.x, rt.y};
+        // cwbvh/mod.rs:1001-1010
+        u32 oct_inv4 = (r.dx < 0.0f ? 0u : 0x04040404u) | (r.dy < 0.0f ? 0u : 0x02020202u) | (r.dz < 0.0f ? 0u : 0x01010101u);
+        uint2 stack[32];
+        u32 sp = 0;
+        uint2 cur = make_uint2(0u, root_group);  // cwbvh/mod.rs:146-165
+        uint2 prim = make_uint2(0u, 0u);
+        u32 hit_id = 0xffffffffu;
+        float hit_t = __int_as_float(0x7f800000);
+        bool is_miss = true;
+        u32 count = 0;
+        for (;;) {
+            while (prim.y != 0) {  // traverse_macro.rs:64-72
+                u32 local = 31u - __clz(prim.y);
+                prim.y &= ~(1u << local);
+                u32 pid = prim.x + local;
+                float t = tri_intersect(tris, pid, r);
+                if (COUNT) tris_tested++;
+                if (MODE == 0) {
+                    if (t < r.tmax) {  // cwbvh/mod.rs:184-189
+                        hit_id = pid;
+                        hit_t = t;
+                        r.tmax = t;
+                    }
+                } else if (MODE == 1) {
+                    if (t < r.tmax) {  // cwbvh/mod.rs:216-220
+                        is_miss = false;
+                        goto done;
+                    }
+                } else {
+                    if (t < __int_as_float(0x7f800000)) count++;
+                }
+            }
+            prim = make_uint2(0u, 0u);
+            if (cur.y & 0xff000000u) {  // traverse_macro.rs:76-103
+                u32 hits_imask = cur.y;
+                u32 child_index_offset = 31u - __clz(hits_imask);
+                u32 child_index_base = cur.x;
+                cur.y &= ~(1u << child_index_offset);
+                if (cur.y & 0xff000000u) {  // faststack.rs:299-303 saturating push
+                    stack[sp] = cur;
+                    sp = min(sp + 1u, 31u);
+                }
+                u32 slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
+                u32 relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+                const uint4* np = nodes + (size_t)(child_index_base + relative_index) * 5;
+                uint4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3), q4 = __ldg(np + 4);
+                if (COUNT) nodes_visited++;
+                u32 hitmask = node_intersect(q0, q1, q2, q3, q4, r, oct_inv4);
+                cur.x = q1.x;                                  // child_base_idx
+                prim.x = q1.y;                                 // primitive_base_idx
+                cur.y = (hitmask & 0xff000000u) | (q0.w >> 24);  // | imask
+                prim.y = hitmask & 0x00ffffffu;
+            } else {
+                cur = make_uint2(0u, 0u);
+            }
+            if (prim.y == 0 && (cur.y & 0xff000000u) == 0) {  // traverse_macro.rs:112-123
+                if (sp == 0) break;
+                sp--;
+                cur = stack[sp];
+            }
+        }
+    done:
+        if (MODE == 0) {
+            reinterpret_cast<uint4*>(out)[i] = make_uint4(hit_id, 0xffffffffu, 0xffffffffu, __float_as_uint(hit_t));
+        } else if (MODE == 1) {
+            reinterpret_cast<u8*>(out)[i] = is_miss ? 1 : 0;
+        } else {
+            reinterpret_cast<u32*>(out)[i] = count;
+        }
+    }
+    if (COUNT) {
+        unsigned long long a = nodes_visited, b = tris_tested;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters, a);
+            atomicAdd(counters + 1, b);
+        }
+    }
+}
+
+// examples/obj_cwbvh.rs:63-67: bvh_tris[i] = tris[primitive_indices[i]]
+__global__ void permute_tris_kernel(const float4* __restrict__ tris, const u32* __restrict__ prim_idx, float4* __restrict__ out,
+                                    size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread, 3 per triangle
+    if (i >= n * 3) return;
+    size_t t = i / 3, k = i - t * 3;
+    out[i] = __ldg(tris + (size_t)prim_idx[t] * 3 + k);
+}
+
+// ray.rs:6-12, 34-52
+__device__ __forceinline__ float safe_inverse(float x) {
+    const float EPS = 1.1920929e-07f;
+    if (fabsf(x) <= EPS) return copysignf(1.0f, x) / EPS;
+    return 1.0f / x;
+}
+__global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float tmin, float tmax, float4* __restrict__ rays) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = od + i * 6;
+    float ox = p[0], oy = p[1], oz = p[2], dx = p[3], dy = p[4], dz = p[5];
+    rays[i * 4 + 0] = make_float4(ox, oy, oz, 0.f);
+    rays[i * 4 + 1] = make_float4(dx, dy, dz, 0.f);
+    rays[i * 4 + 2] = make_float4(safe_inverse(dx), safe_inverse(dy), safe_inverse(dz), 0.f);
+    rays[i * 4 + 3] = make_float4(tmin, tmax, 0.f, 0.f);
+}
+
+}  // namespace
+
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
+                          u64* d_counters) {
+    if (n == 0) return OBVHS_OK;
+    if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
+        OBVHS_SET_ERR(ctx, "CwBvh has no triangles attached (call obvhs_cuda_cwbvh_set_triangles)");
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    const uint4* nodes = reinterpret_cast<const uint4*>(bvh->nodes);
+    const float4* tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    u32 root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
+    dim3 block(128), grid(div_up(n, 128));
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
+    cudaStream_t s = ctx->stream;
+    if (d_counters) {
+        if (mode == 0) traverse_kernel<0, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        else if (mode == 1) traverse_kernel<1, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        else traverse_kernel<2, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+    } else {
+        if (mode == 0) traverse_kernel<0, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        else if (mode == 1) traverse_kernel<1, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        else traverse_kernel<2, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+    }
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
+int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n) {
+    if (n != bvh->prim_count) {
+        OBVHS_SET_ERR(ctx, "set_triangles: %zu triangles for a CwBvh over %zu primitives", n, bvh->prim_count);
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    if (bvh->bvh_tris) {
+        cudaFreeAsync(bvh->bvh_tris, ctx->stream);
+        bvh->bvh_tris = nullptr;
+    }
+    if (n == 0) return OBVHS_OK;
+    CU_TRY(ctx, cudaMallocAsync((void**)&bvh->bvh_tris, n * sizeof(ObvhsTriangle), ctx->stream));
+    permute_tris_kernel<<<div_up(n * 3, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
+                                                                    reinterpret_cast<float4*>(bvh->bvh_tris), n);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
+int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays) {
+    if (n == 0) return OBVHS_OK;
+    make_rays_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(d_od, n, tmin, tmax, reinterpret_cast<float4*>(d_rays));
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}

@@ -1,0 +1,136 @@
+"""Pins the CPU oracle (oracle/obvhs_oracle.cpp) against every known answer the reference's own tests hold for the
+hot path. CPU only."""
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+from obvhs_b200 import camera, test_util as tu
+from obvhs_b200.types import make_rays
+
+F32_MAX = np.float32(3.4028235e38)
+
+
+def shade_normals(c, tris, rays):
+    """examples/obj_cwbvh.rs:94-117: double-sided geometric normal of the closest hit, (0,0,0) on a miss."""
+    bt = c.bvh_tris(tris)
+    hits = c.ray_traverse(bt, rays)
+    with np.errstate(invalid="ignore"):
+        nrm = ob.triangle_normals(bt)
+    hit = hits["t"] < F32_MAX
+    out = np.zeros((rays.shape[0], 3), np.float32)
+    nn = nrm[hits["primitive_id"][hit]]
+    d = rays[hit, 4:7]
+    s = np.sign((nn[:, 0] * -d[:, 0] + nn[:, 1] * -d[:, 1]) + nn[:, 2] * -d[:, 2]).astype(np.float32)
+    out[hit] = nn * s[:, None]
+    return out, hits
+
+
+@pytest.mark.parametrize("preset", ["fastest_build", "very_fast_build", "fast_build", "medium_build"])
+def test_kitchen_golden_hash(kitchen_tris, preset):
+    # examples/obj_cwbvh.rs:142-181: width 32 render, hash of per-pixel normals == 1343358762
+    rays = camera.primary_rays(camera.kitchen_camera(32))
+    c = ob.build_cwbvh_from_tris(kitchen_tris, preset)
+    normals, _ = shade_normals(c, kitchen_tris, rays)
+    assert tu.hash_vec3a_vec(normals) == 1343358762
+    rc, msg = c.validate(ob.tri_aabbs(kitchen_tris))
+    assert rc == 0, msg
+
+
+def test_icosphere_plane_hits_primitive_62():
+    # src/cwbvh/traverse_macro.rs:33-56 and src/lib.rs:16-67
+    tris = np.concatenate([tu.icosphere(1), tu.plane()], axis=0)
+    c = ob.build_cwbvh_from_tris(tris, "medium_build")
+    _, prims, _ = c.get()
+    rays = make_rays(np.array([[0.1, 0.1, 4.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    hits = c.ray_traverse(c.bvh_tris(tris), rays)
+    assert hits["t"][0] < np.inf
+    assert prims[hits["primitive_id"][0]] == 62
+
+
+def test_flat_plane_all_hit_normal_up():
+    # tests/mod.rs:105-124: 256x256 render of a flat 4x4 plane, every pixel hits and the normal is exactly +Y
+    tris = tu.flat_plane(4)
+    cam = camera.Camera(256, 256, 90.0, (0.0, 0.9, 0.0), (0.0, 0.0, 0.0), up=(1.0, 0.0, 0.0))
+    rays = camera.primary_rays(cam, tmax=np.inf, column_major=True)
+    for preset in ob.PRESETS:
+        c = ob.build_cwbvh_from_tris(tris, preset)
+        bt = c.bvh_tris(tris)
+        hits = c.ray_traverse(bt, rays)
+        assert np.all(hits["t"] < np.inf)
+        n = ob.triangle_normals(bt)[hits["primitive_id"]]
+        assert np.all(n == np.array([0.0, 1.0, 0.0], np.float32))
+
+
+def test_degenerate_builds_do_not_hit():
+    # tests/mod.rs:65-88: one empty AABB, and nothing at all
+    ray = make_rays(np.array([[0.0, 0.0, 1.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    empty = np.array([[F32_MAX, F32_MAX, F32_MAX, 0, -F32_MAX, -F32_MAX, -F32_MAX, 0]], np.float32)
+    for sd, thr, ratio, prec, mp in ob.PRESETS.values():
+        b = ob.ploc_build(empty, None, sd, prec, thr)
+        b.reinsertion_run(ratio)
+        c = b.to_cwbvh(min(max(mp, 1), 3))
+        assert c.node_count == 1
+        # the closure of the reference test returns +inf for every primitive: use a far-away degenerate triangle
+        tri = np.zeros((1, 12), np.float32)
+        hits = c.ray_traverse(tri, ray)
+        assert not (hits["t"][0] < np.inf)
+        b0 = ob.ploc_build(np.zeros((0, 8), np.float32), None, sd, prec, thr)
+        b0.reinsertion_run(ratio)
+        c0 = b0.to_cwbvh(3)
+        assert c0.node_count == 0
+        assert not (c0.ray_traverse(np.zeros((0, 12), np.float32), ray)["t"][0] < np.inf)
+
+
+def test_varying_prim_counts_validate():
+    # tests/mod.rs:91-102: 31 .. 1 triangles x presets, Bvh2 + CwBvh validate
+    tris = tu.flat_plane(4)
+    assert tris.shape[0] == 32
+    for n in range(31, 0, -1):
+        t = tris[:n]
+        aabbs = ob.tri_aabbs(t)
+        for sd, thr, ratio, prec, mp in ob.PRESETS.values():
+            b = ob.ploc_build(aabbs, None, sd, prec, thr)
+            rc, msg = b.validate(aabbs)
+            assert rc == 0, (n, msg)
+            b.reinsertion_run(ratio)
+            rc, msg = b.validate(aabbs)
+            assert rc == 0, (n, msg)
+            c = b.to_cwbvh(min(max(mp, 1), 3))
+            rc, msg = c.validate(aabbs)
+            assert rc == 0, (n, msg)
+
+
+def test_morton_split_matches_naive_interleave():
+    # src/ploc/morton.rs:35-58 magic masks == bit by bit interleave
+    rng = np.random.default_rng(1)
+    for a in list(rng.integers(0, 1 << 21, 200)) + [0, 1, (1 << 21) - 1]:
+        want = 0
+        for i in range(21):
+            want |= ((int(a) >> i) & 1) << (3 * i)
+        assert ob.lib().orc_test_split3_64(int(a)) == want
+
+
+def test_sort_is_stable_by_index(kitchen_tris):
+    # ties keep ascending original index
+    aabbs = ob.tri_aabbs(kitchen_tris)
+    lo, hi, order, total = ob.morton_sort(aabbs)
+    keys = lo[order]
+    assert np.all(keys[:-1] <= keys[1:])
+    same = keys[:-1] == keys[1:]
+    assert same.sum() > 1000  # the kitchen has thousands of tied codes
+    assert np.all(order[:-1][same] < order[1:][same])
+
+
+def test_refit_fast_equals_full(scenes):
+    # bvh2/mod.rs:722-751 early-out refit vs walking to the root give the same tree
+    for name in ("cornell", "terrain32", "soup4k"):
+        aabbs = ob.tri_aabbs(scenes[name])
+        res = []
+        for full in (0, 1):
+            ob.lib().orc_set_refit_full(full)
+            b = ob.ploc_build(aabbs, None, 6, 64, 2)
+            b.reinsertion_run(0.5)
+            nodes, prims = b.get()
+            res.append(nodes.tobytes())
+        ob.lib().orc_set_refit_full(0)
+        assert res[0] == res[1], name
