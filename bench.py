@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- device-timed PLOC+CWBVH build (Mtris/s) and CWBVH closest-hit traversal (Mrays/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitchen|soup|terrain]
+
+One "step" = one pass of the hot path over one batch: build_cwbvh_from_tris (PLOC -> reinsertion -> CWBVH collapse) on
+the scene, then closest-hit traversal of the ray batch, both through the C ABI with inputs resident in HBM. The headline
+`value` is traversal Mrays/s (BASELINE.json metric, first half), `build` carries the Mtris/s half. N > 1: rank 0 builds,
+the tree is broadcast with NCCL, every rank traverses its own ray batch against its replica (weak scaling, no collective
+on the traversal path). `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP on all host cores;
+the rustc/rayon binary cannot be produced in this image) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "CWBVH closest-hit traversal Mrays/s (PLOC+CWBVH build Mtris/s in `build`)"
+
+
+def make_workload(name: str, n_tris: int, seed: int = 0):
+    """-> (tris (n,12) f32, rays (m,16) f32, description, preset)"""
+    from obvhs_b200 import camera, test_util as tu
+
+    if name == "kitchen":
+        # BASELINE.json configs[1]: assets/kitchen.obj, fast_build (examples/obj_cwbvh.rs:47), 1920x1080 primary rays
+        tris = tu.kitchen()
+        rays = camera.primary_rays(camera.kitchen_camera(1920))
+        return tris, rays, "kitchen.obj 56939 tris, fast_build, 1920x1080 primary rays (examples/obj_cwbvh.rs camera)", "fast_build"
+    if name == "terrain":
+        res = int(round((n_tris / 2) ** 0.5))
+        tris = tu.demoscene(res, 0)
+        cam = camera.demoscene_camera(1920)
+        rays = camera.demoscene_primary(cam, 0)
+        return tris, rays, f"demoscene({res},0) {tris.shape[0]} tris, fast_build, {cam.width}x{cam.height} jittered primary rays", "fast_build"
+    if name == "soup":
+        tris = tu.triangle_soup(n_tris, seed)
+        rng = np.random.default_rng(seed)
+        m = 1920 * 1080
+        o = rng.random((m, 3), dtype=np.float32) * np.float32(1.2) - np.float32(0.1)
+        t = rng.random((m, 3), dtype=np.float32)
+        d = t - o
+        d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+        from obvhs_b200.types import make_rays
+
+        rays = make_rays(o, d.astype(np.float32), 0.0, np.inf)
+        return tris, rays, f"hashed triangle soup {n_tris} tris, fast_build, {m} incoherent rays", "fast_build"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_leg(tris, rays, preset, steps, warmup):
+    """The reference's CPU algorithm (C++ restatement in oracle/, OpenMP over all host cores) on the same workload."""
+    import oracle_bind as ob
+
+    threads = ob.lib().orc_max_threads()
+    build_s, trav_s = [], []
+    hits = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        c = ob.build_cwbvh_from_tris(tris, preset, threads=threads)
+        bt = c.bvh_tris(tris)
+        t1 = time.perf_counter()
+        hits = c.ray_traverse(bt, rays, threads=threads, use_simd=True)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            build_s.append(c.core_build_seconds)
+            trav_s.append(t2 - t1)
+    return {"threads": threads, "build_s": float(np.mean(build_s)), "trav_s": float(np.mean(trav_s)), "hits": hits}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tris, rays, desc, preset = make_workload(args.workload, args.tris)
+    # bounded sample so `--steps K --warmup W` ends within a few minutes on the host cores
+    max_rays = args.ref_rays
+    sample = rays[:: max(1, rays.shape[0] // max_rays)][:max_rays] if rays.shape[0] > max_rays else rays
+    r = cpu_reference_leg(tris, sample, preset, args.steps, min(args.warmup, 1))
+    mrays = sample.shape[0] / r["trav_s"] / 1e6
+    mtris = tris.shape[0] / r["build_s"] / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (r["trav_s"] + r["build_s"]) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload != "kitchen" else "kitchen.obj fixture (reference asset)",
+        "config": {"workload": desc, "preset": preset},
+        "build": {"value": mtris, "unit": "Mtris/s", "ms": r["build_s"] * 1e3},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{sample.shape[0]} of {rays.shape[0]} rays (strided), full build; C++ restatement of the obvhs CPU path, not the rustc/rayon binary",
+                         "build_mtris_per_s": mtris},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+
+    from obvhs_b200 import api, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local_rank, stream=stream.cuda_stream)
+
+    tris, rays, desc, preset = make_workload(args.workload, args.tris)
+    params = api.BvhBuildParams.preset(preset)
+    n_tris, n_rays = tris.shape[0], rays.shape[0]
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(tris).to(dev)
+        d_rays = torch.from_numpy(rays).to(dev)
+        d_hits = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        d_counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    stream.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def one_step(timed):
+        """build (rank 0) -> [broadcast] -> traverse. Returns (build_ms, bcast_ms, trav_ms) events' readings."""
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between iterations, outside the timed events
+            e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+            e0.record(stream)
+            bvh = api.build_cwbvh_from_tris(d_tris, params, ctx=ctx) if rank == 0 else None
+            e1.record(stream)
+            if world > 1:
+                bvh = sharding.broadcast_cwbvh(bvh, ctx, src=0)
+            e2.record(stream)
+            bvh.ray_traverse(d_rays, out=d_hits)
+            e3.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), bvh
+
+    for _ in range(args.warmup):
+        one_step(False)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    b_ms, c_ms, t_ms = [], [], []
+    bvh = None
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        b, c, t, bvh = one_step(True)
+        b_ms.append(b)
+        c_ms.append(c)
+        t_ms.append(t)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    tot = torch.tensor([sum(b_ms), sum(c_ms), sum(t_ms)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)  # max over ranks
+    build_ms, bcast_ms, trav_ms = (tot / args.steps).tolist()
+    value = world * n_rays / (trav_ms * 1e-3) / 1e6
+    build_mtris = n_tris / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None
+
+    # ---- roofline of the dominant kernel (traverse_kernel): algorithmic bytes from the per-launch counters ----------
+    with torch.cuda.stream(stream):
+        d_counters.zero_()
+        bvh.ray_traverse(d_rays, out=d_hits, counters=d_counters)
+    stream.synchronize()
+    nodes_visited, tris_tested = [int(x) for x in d_counters.tolist()]
+    alg_bytes = n_rays * (32 + 16) + 80 * nodes_visited + 48 * tris_tested  # SURVEY.md section 8(d) B_trav
+    peak, peak_src = measured_peak_hbm()
+    achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
+    hit_count = int((d_hits[:, 3].view(torch.float32) < 3.0e38).sum().item())
+
+    line = None
+    if rank == 0:
+        # ---- e2e: same step through the C ABI with HOST buffers (pinned), copies inside the timed region -------------
+        h_tris = torch.from_numpy(tris).pin_memory()
+        h_rays = torch.from_numpy(rays).pin_memory()
+        h_hits = torch.empty((n_rays, 4), dtype=torch.int32).pin_memory()
+        from obvhs_b200.types import RAY_HIT
+
+        hits_np = h_hits.numpy().view(RAY_HIT).reshape(-1)
+        e_b, e_t = [], []
+        for it in range(2 + max(2, min(args.steps, 5))):
+            t0 = time.perf_counter()
+            eb = api.build_cwbvh_from_tris(h_tris.numpy(), params, ctx=ctx)
+            t1 = time.perf_counter()
+            eb.ray_traverse(h_rays.numpy(), out=hits_np)
+            t2 = time.perf_counter()
+            if it >= 2:
+                e_b.append(t1 - t0)
+                e_t.append(t2 - t1)
+        e2e_mrays = world * n_rays / float(np.mean(e_t)) / 1e6
+        e2e_mtris = n_tris / float(np.mean(e_b)) / 1e6
+        assert int((hits_np["t"] < 3.0e38).sum()) == hit_count
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            max_rays = args.ref_rays
+            sample = rays[:: max(1, n_rays // max_rays)][:max_rays] if n_rays > max_rays else rays
+            r = cpu_reference_leg(tris, sample, preset, 2, 1)
+            cpu = {"value": sample.shape[0] / r["trav_s"] / 1e6, "unit": "Mrays/s", "cores": r["threads"], "kind": "port",
+                   "sample": f"{sample.shape[0]} of {n_rays} rays (strided) + full build; C++ restatement of the obvhs CPU path "
+                             "(OpenMP), not the rustc/rayon binary",
+                   "build_mtris_per_s": n_tris / r["build_s"] / 1e6}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": build_ms + bcast_ms + trav_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic" if args.workload != "kitchen" else "kitchen.obj fixture (reference asset), generated rays",
+            "config": {"workload": desc, "preset": preset, "rays_per_gpu": n_rays, "tris": n_tris, "l2": "flushed between steps (256 MB write)",
+                       "multi_gpu": "build on rank 0, NCCL broadcast, rays sharded (one batch per GPU)" if world > 1 else "single GPU"},
+            "build": {"value": build_mtris, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count},
+            "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "traverse_kernel<closest>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "nodes_visited": nodes_visited, "tris_tested": tris_tested,
+                         "note": "B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); kitchen tree+tris fit in L2, "
+                                 "so a fraction near or above 1 means L2-served reuse, not DRAM streaming"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 64 * n_rays + 48 * n_tris, "d2h_bytes_per_step": 16 * n_rays,
+                    "build_mtris_per_s": e2e_mtris, "how": "obvhs_cuda_build_cwbvh_from_tris + obvhs_cuda_cwbvh_ray_traverse_batch with pinned HOST buffers"},
+            "gpu_launches": launches, "hits": hit_count, "clocks": clocks, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain"])
+    ap.add_argument("--tris", type=int, default=10_000_000)
+    ap.add_argument("--ref-rays", type=int, default=2_073_600, help="ray sample bound for the CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

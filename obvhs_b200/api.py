@@ -390,10 +390,11 @@ class CwBvh:
         self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value or 0, b.value or 0, c.value or 0
 
-    def _out(self, out, n, dtype, torch_dtype_name, cols=None):
-        if out is not None:
-            return out
-        return np.zeros(n, dtype=dtype)
+    def total_aabb(self):
+        """CwBvh::total_aabb as 8 floats (Aabb layout) without downloading the tree."""
+        total = np.zeros(8, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_download(self.ctx.h, self.h, None, None, _ptr(total)))
+        return total
 
     def ray_traverse(self, rays, out=None, counters=None):
         """Batched CwBvh::ray_traverse with the triangle closure: -> RayHit per ray (numpy RAY_HIT array, or `out`).

@@ -1,0 +1,343 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI (obvhs_b200.api -> libobvhs_cuda.so), against the
+CPU oracle on the same inputs. Integer / byte / index results are compared bit for bit; hit distances too (the contract
+allows 1e-6 relative, the implementation is bit-exact because it keeps the reference's operation order without FMA)."""
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+from obvhs_b200 import camera, test_util as tu
+from obvhs_b200.types import make_rays
+
+pytestmark = pytest.mark.gpu
+
+F32_MAX = np.float32(3.4028235e38)
+SCENES = ["cornell", "ico_plane", "flat4", "terrain32", "soup4k", "kitchen"]
+PLOC_CONFIGS = [(1, 0), (2, 0), (6, 2), (14, 3), (24, 1), (32, 0)]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from obvhs_b200 import api as a
+
+    a.default_context(0)  # raises if the CUDA library or device is missing: no fallback
+    return a
+
+
+def node_fields(nodes):
+    """Comparable view of Bvh2Node arrays (the Vec3A padding lanes are unspecified)."""
+    a = np.ascontiguousarray(nodes["aabb"][:, [0, 1, 2, 4, 5, 6]]).view(np.uint32)
+    return a, nodes["prim_count"], nodes["first_index"]
+
+
+def assert_nodes_equal(got, want, what):
+    ga, gp, gf = node_fields(got)
+    wa, wp, wf = node_fields(want)
+    assert got.shape == want.shape, what
+    bad = np.nonzero((ga != wa).any(axis=1) | (gp != wp) | (gf != wf))[0]
+    assert bad.size == 0, f"{what}: {bad.size} of {got.shape[0]} nodes differ, first {bad[:5]}: got {got[bad[:2]]} want {want[bad[:2]]}"
+
+
+def rays_for(tris, n_side=96, seed=7):
+    """Primary-style rays from a camera outside the scene box plus random incoherent rays through it."""
+    lo = tris.reshape(-1, 4)[:, :3].min(axis=0)
+    hi = tris.reshape(-1, 4)[:, :3].max(axis=0)
+    c = (lo + hi) * 0.5
+    ext = max(float(np.max(hi - lo)), 1e-3)
+    eye = c + np.array([0.9, 0.7, 1.3], np.float32) * ext
+    cam = camera.Camera(n_side, n_side, 60.0, eye.astype(np.float32), c.astype(np.float32))
+    prim = camera.primary_rays(cam)
+    rng = np.random.default_rng(seed)
+    m = n_side * n_side
+    o = (c + (rng.random((m, 3), dtype=np.float32) - 0.5) * ext * 2.5).astype(np.float32)
+    t = (c + (rng.random((m, 3), dtype=np.float32) - 0.5) * ext).astype(np.float32)
+    d = t - o
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    rnd = make_rays(o, d.astype(np.float32), 0.0, np.inf)
+    # axis-aligned directions exercise the safe_inverse / zero-direction paths
+    axis = make_rays(np.tile(c, (6, 1)).astype(np.float32) + np.float32(0.01), np.array(
+        [[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32), 0.0, np.inf)
+    return np.concatenate([prim, rnd, axis], axis=0)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_morton_codes_and_sorted_order(api, scenes, scene):
+    aabbs = ob.tri_aabbs(scenes[scene])
+    lo, hi, order, total = ob.morton_sort(aabbs)
+    glo, ghi, gorder, gtotal = api.PlocBuilder().morton_sort(aabbs)
+    assert np.array_equal(glo, lo)
+    assert np.array_equal(gorder, order)
+    assert np.array_equal(gtotal[[0, 1, 2, 4, 5, 6]], total[[0, 1, 2, 4, 5, 6]])
+
+
+def test_sort_heavy_ties_and_sizes(api):
+    # every primitive identical (all codes tie), and sizes around the tile boundaries of the onesweep sort
+    tri = tu.cube()[:1]
+    for n in (1, 2, 3, 255, 256, 257, 4095, 4096, 4097, 8193, 70001):
+        aabbs = ob.tri_aabbs(np.repeat(tri, n, axis=0))
+        _, _, order, _ = api.PlocBuilder().morton_sort(aabbs)
+        assert np.array_equal(order, np.arange(n, dtype=np.uint32)), n
+    soup = tu.triangle_soup(70001, 11)
+    aabbs = ob.tri_aabbs(soup)
+    lo, _, order, _ = ob.morton_sort(aabbs)
+    glo, _, gorder, _ = api.PlocBuilder().morton_sort(aabbs)
+    assert np.array_equal(glo, lo) and np.array_equal(gorder, order)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("cfg", PLOC_CONFIGS)
+def test_ploc_bvh2_bit_exact(api, scenes, scene, cfg):
+    sd, thr = cfg
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, sd, 64, thr)
+    wn, wp = want.get()
+    got = api.PlocBuilder().build(sd, aabbs, None, api.SortPrecision.U64, thr)
+    gn, gp = got.download()
+    assert got.ploc_iterations == want.ploc_iterations
+    assert got.max_depth == want.max_depth
+    assert np.array_equal(gp, wp)
+    assert_nodes_equal(gn, wn, f"{scene} ploc r={sd} thr={thr}")
+    assert got.children_are_ordered_after_parents
+
+
+def test_ploc_from_triangles_equals_from_aabbs(api, scenes):
+    tris = scenes["kitchen"]
+    a = api.PlocBuilder().build_tris(6, tris, api.SortPrecision.U64, 2).download()
+    b = api.PlocBuilder().build(6, ob.tri_aabbs(tris), None, api.SortPrecision.U64, 2).download()
+    assert_nodes_equal(a[0], b[0], "tris vs aabbs")
+
+
+def test_ploc_with_custom_indices(api, scenes):
+    aabbs = ob.tri_aabbs(scenes["soup4k"])
+    idx = np.random.default_rng(0).permutation(aabbs.shape[0]).astype(np.uint32)
+    wn, wp = ob.ploc_build(aabbs, idx, 6, 64, 2).get()
+    gn, gp = api.PlocBuilder().build(6, aabbs, idx, api.SortPrecision.U64, 2).download()
+    assert np.array_equal(gp, wp)
+    assert_nodes_equal(gn, wn, "custom indices")
+
+
+def test_compute_parents_and_refit_all(api, scenes):
+    aabbs = ob.tri_aabbs(scenes["kitchen"])
+    want = ob.ploc_build(aabbs, None, 6, 64, 2)
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    got.compute_parents()
+    want.compute_parents()
+    _, _, wpar = want.get(with_parents=True)
+    gn, gp, gpar = got.download(with_parents=True)
+    assert np.array_equal(gpar, wpar)
+    # move the leaves, refit (config 5): bvh2/mod.rs:527-569
+    rng = np.random.default_rng(5)
+    moved = aabbs.copy()
+    delta = (rng.random((aabbs.shape[0], 3), dtype=np.float32) - 0.5) * np.float32(0.05)
+    moved[:, 0:3] += delta
+    moved[:, 4:7] += delta
+    want.set_leaf_aabbs(moved)
+    want.refit_all()
+    got.set_leaf_aabbs(moved)
+    assert_nodes_equal(got.download()[0], want.get()[0], "refit_all")
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("ratio", [0.02, 0.5, 1.0])
+def test_reinsertion_bit_exact(api, scenes, scene, ratio):
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, 6, 64, 2)
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    applied_want = want.reinsertion_run(ratio)
+    opt = api.ReinsertionOptimizer()
+    applied_got = opt.run(got, ratio)
+    wn2, _, wpar = want.get(with_parents=True)
+    gn2, _, gpar = got.download(with_parents=True)
+    assert applied_got == applied_want
+    assert_nodes_equal(gn2, wn2, f"{scene} reinsertion ratio={ratio}")
+    assert np.array_equal(gpar[1:], wpar[1:])
+    assert not got.children_are_ordered_after_parents
+    rc, msg = ob.bvh2_from(gn2, wp, want.max_depth).validate(aabbs)
+    assert rc == 0, msg
+
+
+def test_reinsertion_custom_sequence(api, scenes):
+    aabbs = ob.tri_aabbs(scenes["terrain32"])
+    want = ob.ploc_build(aabbs, None, 1, 64, 0)
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    seq = [1.0, 0.5, 0.25, 1.0]
+    want.reinsertion_run(0.7, seq)
+    api.ReinsertionOptimizer().run(got, 0.7, seq)
+    assert_nodes_equal(got.download()[0], want.get()[0], "custom ratio sequence")
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("max_prims,order", [(1, True), (3, True), (2, False)])
+def test_cwbvh_collapse_bytes(api, scenes, scene, max_prims, order):
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want2 = ob.ploc_build(aabbs, None, 6, 64, 2)
+    want2.reinsertion_run(0.1)
+    wn, wp = want2.get()
+    want = want2.to_cwbvh(max_prims, order)
+    wnodes, wprims, wtotal = want.get()
+    got = api.bvh2_to_cwbvh(api.Bvh2.upload(wn, wp, want2.max_depth, False), max_prims, order)
+    gnodes, gprims, gtotal = got.download()
+    assert gnodes.shape == wnodes.shape
+    assert np.array_equal(gprims, wprims)
+    bad = np.nonzero(gnodes.view(np.uint8).reshape(-1, 80) != wnodes.view(np.uint8).reshape(-1, 80))[0]
+    assert bad.size == 0, f"{np.unique(bad).size} CWBVH nodes differ, first: got {gnodes[bad[0]]} want {wnodes[bad[0]]}"
+    assert np.array_equal(gtotal[[0, 1, 2, 4, 5, 6]], wtotal[[0, 1, 2, 4, 5, 6]])
+
+
+def test_cwbvh_from_fresh_ploc_without_parents(api, scenes):
+    # fastest_build: no reinsertion, Bvh2::parents is None when the converter runs
+    aabbs = ob.tri_aabbs(scenes["kitchen"])
+    want = ob.ploc_build(aabbs, None, 1, 64, 0).to_cwbvh(1, True).get()
+    got = api.bvh2_to_cwbvh(api.PlocBuilder().build(1, aabbs), 1, True).download()
+    assert got[0].tobytes() == want[0].tobytes()
+    assert np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_traversal_hits_bit_exact(api, scenes, scene):
+    tris = scenes[scene]
+    c = ob.build_cwbvh_from_tris(tris, "fast_build")
+    nodes, prims, total = c.get()
+    bt = c.bvh_tris(tris)
+    rays = rays_for(tris)
+    wc = np.zeros(2, np.uint64)
+    want = c.ray_traverse(bt, rays, counters=wc)
+    g = api.CwBvh.upload(nodes, prims, total)
+    g.set_triangles(tris)
+    gc = np.zeros(2, np.uint64)
+    got = g.ray_traverse(rays, counters=gc)
+    assert np.array_equal(got["primitive_id"], want["primitive_id"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert np.array_equal(got["geometry_id"], want["geometry_id"]) and np.array_equal(got["instance_id"], want["instance_id"])
+    assert np.array_equal(gc, wc), "nodes visited / triangles tested differ: the visit order is not the reference's"
+    assert np.array_equal(g.ray_traverse(rays)["primitive_id"], want["primitive_id"])  # uncounted kernel variant
+    # shadow / any-hit flavours with a finite tmax (cwbvh/mod.rs:201-245)
+    srays = rays.copy()
+    finite = np.isfinite(want["t"])
+    srays[:, 13] = np.where(finite, want["t"] * np.float32(0.999), np.float32(5.0))
+    srays[::3, 13] = np.float32(1e30)
+    assert np.array_equal(g.ray_traverse_miss(srays), c.ray_traverse_miss(bt, srays))
+    assert np.array_equal(g.ray_traverse_anyhit_count(srays), c.ray_traverse_anyhit_count(bt, srays))
+
+
+@pytest.mark.parametrize("preset", ["fastest_build", "very_fast_build", "fast_build", "medium_build"])
+@pytest.mark.parametrize("scene", ["cornell", "terrain32", "kitchen"])
+def test_build_cwbvh_from_tris_end_to_end(api, scenes, scene, preset):
+    tris = scenes[scene]
+    want = ob.build_cwbvh_from_tris(tris, preset)
+    wnodes, wprims, wtotal = want.get()
+    t = [0.0]
+    got = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.preset(preset), t)
+    gnodes, gprims, gtotal = got.download()
+    assert t[0] > 0.0
+    assert gnodes.shape == wnodes.shape
+    assert np.array_equal(gprims, wprims)
+    assert gnodes.tobytes() == wnodes.tobytes()
+    rc, msg = ob.cwbvh_from(gnodes, gprims, gtotal).validate(ob.tri_aabbs(tris))
+    assert rc == 0, msg
+
+
+def test_kitchen_golden_hash_on_gpu(api, kitchen_tris):
+    # examples/obj_cwbvh.rs:142-181 through the GPU path only (build + traversal), normals on the host
+    rays = camera.primary_rays(camera.kitchen_camera(32))
+    for preset in ("fastest_build", "fast_build", "medium_build"):
+        bvh = api.build_cwbvh_from_tris(kitchen_tris, api.BvhBuildParams.preset(preset))
+        hits = bvh.ray_traverse(rays)
+        _, prims, _ = bvh.download()
+        with np.errstate(invalid="ignore"):
+            nrm = ob.triangle_normals(kitchen_tris[prims])
+        hit = hits["t"] < F32_MAX
+        out = np.zeros((rays.shape[0], 3), np.float32)
+        nn = nrm[hits["primitive_id"][hit]]
+        d = rays[hit, 4:7]
+        s = np.sign((nn[:, 0] * -d[:, 0] + nn[:, 1] * -d[:, 1]) + nn[:, 2] * -d[:, 2]).astype(np.float32)
+        out[hit] = nn * s[:, None]
+        assert tu.hash_vec3a_vec(out) == 1343358762, preset
+
+
+def test_icosphere_known_answer_on_gpu(api):
+    tris = np.concatenate([tu.icosphere(1), tu.plane()], axis=0)
+    bvh = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.medium_build())
+    rays = api.make_rays(np.array([[0.1, 0.1, 4.0, 0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    hits = bvh.ray_traverse(rays)
+    _, prims, _ = bvh.download()
+    assert hits["t"][0] < np.inf and prims[hits["primitive_id"][0]] == 62
+
+
+def test_make_rays_matches_ray_new(api):
+    rng = np.random.default_rng(3)
+    od = rng.standard_normal((1000, 6)).astype(np.float32)
+    od[:10, 3] = 0.0
+    od[10:20, 4] = -0.0
+    od[20:30, 5] = np.float32(1e-8)
+    want = make_rays(od[:, 0:3], od[:, 3:6], 0.25, 77.0)
+    got = api.make_rays(od, 0.25, 77.0)
+    assert np.array_equal(got[:, [0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13]].view(np.uint32), want[:, [0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13]].view(np.uint32))
+
+
+def test_degenerate_inputs(api):
+    # tests/mod.rs:35-102: nothing, one empty AABB, tiny counts
+    ray = make_rays(np.array([[0.0, 0.0, 1.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    for preset in ("fastest_build", "fast_build", "medium_build"):
+        p = api.BvhBuildParams.preset(preset)
+        bvh = api.build_cwbvh_from_tris(np.zeros((0, 12), np.float32), p)
+        assert bvh.node_count == 0 and bvh.prim_count == 0
+        assert not (bvh.ray_traverse(ray)["t"][0] < np.inf)
+        assert bvh.ray_traverse_miss(ray)[0] == 1
+    empty = np.array([[F32_MAX, F32_MAX, F32_MAX, 0, -F32_MAX, -F32_MAX, -F32_MAX, 0]], np.float32)
+    b = api.PlocBuilder().build(14, empty)
+    assert b.node_count == 1
+    c = api.bvh2_to_cwbvh(b, 3, True)
+    want = ob.ploc_build(empty, None, 14, 64, 0).to_cwbvh(3, True).get()
+    assert c.download()[0].tobytes() == want[0].tobytes()
+    tris = tu.flat_plane(4)
+    for n in range(31, 0, -3):
+        for preset in ("fastest_build", "fast_build", "medium_build"):
+            want = ob.build_cwbvh_from_tris(tris[:n], preset).get()
+            got = api.build_cwbvh_from_tris(tris[:n], api.BvhBuildParams.preset(preset)).download()
+            assert got[0].tobytes() == want[0].tobytes(), (n, preset)
+            assert np.array_equal(got[1], want[1])
+
+
+def test_nan_input_is_an_error_not_a_hang(api):
+    aabbs = ob.tri_aabbs(tu.triangle_soup(1000, 1))
+    aabbs[17, 1] = np.nan
+    with pytest.raises(api.ObvhsError) as e:
+        api.PlocBuilder().build(6, aabbs)
+    assert e.value.code == -4
+
+
+def test_unsupported_paths_fail_loudly(api):
+    tris = tu.cornell_box()
+    with pytest.raises(api.ObvhsError):
+        api.build_cwbvh_from_tris(tris, api.BvhBuildParams.slow_build())  # pre_split
+    with pytest.raises(api.ObvhsError):
+        api.PlocBuilder().build(7, ob.tri_aabbs(tris))  # not a PlocSearchDistance
+
+
+def test_large_scene_full_parity_and_properties(api):
+    # 1M-triangle soup + 0.5M terrain: full byte parity against the oracle (seconds on the CPU) plus size-independent
+    # properties: sorted keys, stable ties, valid trees, closest hit <= any brute-force sample
+    for name, tris in (("soup1m", tu.triangle_soup(1_000_000, 2)), ("terrain500", tu.demoscene(500, 1))):
+        aabbs = ob.tri_aabbs(tris)
+        lo, _, order, _ = api.PlocBuilder().morton_sort(aabbs)
+        k = lo[order]
+        assert np.all(k[:-1] <= k[1:])
+        tie = k[:-1] == k[1:]
+        assert np.all(order[:-1][tie] < order[1:][tie])
+        want = ob.build_cwbvh_from_tris(tris, "fast_build", threads=0)
+        got = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build())
+        gnodes, gprims, gtotal = got.download()
+        wnodes, wprims, _ = want.get()
+        assert gnodes.shape == wnodes.shape, name
+        assert np.array_equal(gprims, wprims), name
+        assert gnodes.tobytes() == wnodes.tobytes(), name
+        rc, msg = ob.cwbvh_from(gnodes, gprims, gtotal).validate(aabbs)
+        assert rc == 0, msg
+        rays = rays_for(tris, n_side=256)
+        wh = want.ray_traverse(want.bvh_tris(tris), rays)
+        gh = got.ray_traverse(rays)
+        assert np.array_equal(gh["primitive_id"], wh["primitive_id"]), name
+        assert np.array_equal(gh["t"].view(np.uint32), wh["t"].view(np.uint32)), name
