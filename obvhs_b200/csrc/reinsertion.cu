@@ -229,18 +229,20 @@ __global__ void __launch_bounds__(256) apply_kernel(const u32* __restrict__ cell
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->applied, (u32)__popc(b));
 }
 
-// dirty paths: every accepted entry dirties `to` and the old parent of `from` and all their ancestors
+// Dirty paths: every accepted entry dirties `to` and the old parent of `from`, and all their ancestors. pending[x] counts
+// the arrivals node x waits for before it can be refit: one per dirty child, plus one "self" token when x is a start
+// node. Whoever brings pending[x] to zero refits x and carries on to its parent, so every dirty node is refit exactly
+// once, after all dirty nodes below it.
 __global__ void __launch_bounds__(256) refit_mark_kernel(const u32* __restrict__ cells, u32* __restrict__ status, const ReinsertState* st,
                                                          const u32* __restrict__ parents, u32* mark, u32* pending, u32 round_stamp) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= st->active || (status[r] & 3u) != 1) return;
     const u32* c = cells + (size_t)r * 5;
     u32 starts[2] = {c[0], c[4]};
-    u32 own = 0;
     for (int k = 0; k < 2; k++) {
         u32 node = starts[k];
+        atomicAdd(&pending[node], 1u);  // self token, released by this entry's thread in refit_dirty_kernel
         if (atomicExch(&mark[node], round_stamp) == round_stamp) continue;
-        own |= 4u << k;
         while (node != 0) {
             u32 p = parents[node];
             atomicAdd(&pending[p], 1u);
@@ -248,7 +250,6 @@ __global__ void __launch_bounds__(256) refit_mark_kernel(const u32* __restrict__
             node = p;
         }
     }
-    status[r] = 1u | own;
 }
 
 __global__ void __launch_bounds__(256) refit_dirty_kernel(const u32* __restrict__ cells, const u32* __restrict__ status, const ReinsertState* st,
@@ -258,10 +259,9 @@ __global__ void __launch_bounds__(256) refit_dirty_kernel(const u32* __restrict_
     const u32* c = cells + (size_t)r * 5;
     u32 starts[2] = {c[0], c[4]};
     for (int k = 0; k < 2; k++) {
-        if (!(status[r] & (4u << k))) continue;
         u32 node = starts[k];
-        if (__ldcg(&pending[node]) != 0) continue;  // a dirty descendant will arrive here later
         for (;;) {
+            if (atomicSub(&pending[node], 1u) != 1u) break;  // somebody below is still due
             Node32 me = load_node_cg(nodes + node);
             if (me.prim_count == 0) {
                 Node32 c0 = load_node_cg(nodes + me.first_index), c1 = load_node_cg(nodes + me.first_index + 1);
@@ -269,9 +269,7 @@ __global__ void __launch_bounds__(256) refit_dirty_kernel(const u32* __restrict_
             }
             if (node == 0) break;
             __threadfence();
-            u32 p = parents[node];
-            if (atomicSub(&pending[p], 1u) != 1u) break;
-            node = p;
+            node = parents[node];
         }
     }
 }

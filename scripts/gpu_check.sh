@@ -10,3 +10,11 @@ echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout -s KILL 600 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench.log
 tail -5 gpurun_out/pytest.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log
+if [ "${PROFILE:-0}" = "1" ]; then
+  # launch list of one bench run (cold-cache, serialised: compare SHARES) and one full capture of the top kernel
+  timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-4000} --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+  timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:traverse_kernel -s 3 -c 1 -f -o gpurun_out/prof_traverse \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+  ls -la gpurun_out
+fi

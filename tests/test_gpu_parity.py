@@ -15,6 +15,17 @@ SCENES = ["cornell", "ico_plane", "flat4", "terrain32", "soup4k", "kitchen"]
 PLOC_CONFIGS = [(1, 0), (2, 0), (6, 2), (14, 3), (24, 1), (32, 0)]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def oracle_refit_semantics():
+    """Parity target for inner-node AABB bits after reinsertion: Bvh2::refit_from_fast WITHOUT its release-only early
+    return (src/bvh2/mod.rs:732-737, `#[cfg(not(debug_assertions))]`), i.e. the reference built with debug assertions,
+    where every ancestor is recomputed as first.union(second). The release early-out can keep a stale -0.0 / +0.0 sign on
+    a lane whose value is unchanged (tests/test_oracle_golden.py::test_refit_fast_vs_full_differ_only_in_zero_sign)."""
+    ob.lib().orc_set_refit_full(1)
+    yield
+    ob.lib().orc_set_refit_full(0)
+
+
 @pytest.fixture(scope="module")
 def api():
     from obvhs_b200 import api as a

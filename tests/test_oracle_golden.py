@@ -121,16 +121,22 @@ def test_sort_is_stable_by_index(kitchen_tris):
     assert np.all(order[:-1][same] < order[1:][same])
 
 
-def test_refit_fast_equals_full(scenes):
-    # bvh2/mod.rs:722-751 early-out refit vs walking to the root give the same tree
-    for name in ("cornell", "terrain32", "soup4k"):
+def test_refit_fast_vs_full_differ_only_in_zero_sign(scenes):
+    # bvh2/mod.rs:722-751: the release build returns early after two unchanged ancestors, the debug build walks to the
+    # root. Both give the same tree VALUES; the early return can only keep the old sign of a zero lane. The GPU path
+    # matches the walk-to-the-root bits (a full bottom-up refit of the dirty paths).
+    for name in ("cornell", "terrain32", "soup4k", "kitchen"):
         aabbs = ob.tri_aabbs(scenes[name])
-        res = []
-        for full in (0, 1):
-            ob.lib().orc_set_refit_full(full)
-            b = ob.ploc_build(aabbs, None, 6, 64, 2)
-            b.reinsertion_run(0.5)
-            nodes, prims = b.get()
-            res.append(nodes.tobytes())
-        ob.lib().orc_set_refit_full(0)
-        assert res[0] == res[1], name
+        for ratio in (0.02, 0.5):
+            res, applied = [], []
+            for full in (0, 1):
+                ob.lib().orc_set_refit_full(full)
+                b = ob.ploc_build(aabbs, None, 6, 64, 2)
+                applied.append(b.reinsertion_run(ratio))
+                res.append(b.get()[0])
+            ob.lib().orc_set_refit_full(0)
+            assert applied[0] == applied[1]
+            assert np.array_equal(res[0]["first_index"], res[1]["first_index"]) and np.array_equal(res[0]["prim_count"], res[1]["prim_count"])
+            assert np.array_equal(res[0]["aabb"], res[1]["aabb"]), name  # value compare: -0.0 == +0.0
+            bits_differ = res[0]["aabb"].view(np.uint32) != res[1]["aabb"].view(np.uint32)
+            assert np.all(res[0]["aabb"][bits_differ] == 0.0)
