@@ -8,6 +8,10 @@ int bvh2_set_leaf_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAab
 int bvh2_expand_nodes_device(ObvhsContext* ctx, const Node32* in, size_t n, ObvhsBvh2Node* d_out);
 int bvh2_pack_nodes_device(ObvhsContext* ctx, const ObvhsBvh2Node* d_in, size_t n, Node32* out);
 
+#include <chrono>
+#include <cstdlib>
+double TraceScope::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 bool obvhs_is_device_ptr(const void* ptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
@@ -17,15 +21,85 @@ bool obvhs_is_device_ptr(const void* ptr) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+static thread_local ObvhsContext* tls_ctx = nullptr;
+
+void* obvhs_arena_alloc(size_t bytes) {
+    ObvhsContext* ctx = tls_ctx;
+    if (!ctx) return nullptr;
+    bytes = (bytes + 255) & ~(size_t)255;
+    // first block (from the current one on) with room; blocks after the current one are empty
+    while (ctx->arena_block < ctx->arena_blocks.size()) {
+        ObvhsContext::ArenaBlock& b = ctx->arena_blocks[ctx->arena_block];
+        if (ctx->arena_off + bytes <= b.cap) {
+            void* p = b.p + ctx->arena_off;
+            ctx->arena_off += bytes;
+            ctx->arena_used += bytes;
+            if (ctx->arena_used > ctx->arena_peak) ctx->arena_peak = ctx->arena_used;
+            return p;
+        }
+        ctx->arena_block++;
+        ctx->arena_off = 0;
+    }
+    size_t total = 0;
+    for (auto& b : ctx->arena_blocks) total += b.cap;
+    size_t cap = bytes > total ? bytes : total;  // at least double the arena
+    if (cap < ((size_t)8 << 20)) cap = (size_t)8 << 20;
+    char* p = nullptr;
+    if (cudaMalloc((void**)&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        cap = bytes;
+        if (cudaMalloc((void**)&p, cap) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    ctx->arena_blocks.push_back({p, cap});
+    ctx->arena_block = ctx->arena_blocks.size() - 1;
+    ctx->arena_off = bytes;
+    ctx->arena_used += bytes;
+    if (ctx->arena_used > ctx->arena_peak) ctx->arena_peak = ctx->arena_used;
+    return p;
+}
+
 namespace {
-struct DeviceScope {  // makes the context's device current for the duration of a call
+struct DeviceScope {  // makes the context's device current for the duration of a call and scopes its scratch
     int prev = -1;
-    explicit DeviceScope(const ObvhsContext* ctx) {
+    ObvhsContext* ctx;
+    ObvhsContext* prev_ctx;
+    size_t mark_block, mark_off, mark_used;
+    explicit DeviceScope(ObvhsContext* c) : ctx(c) {
         cudaGetDevice(&prev);
         if (prev != ctx->device) cudaSetDevice(ctx->device);
         else prev = -1;
+        prev_ctx = tls_ctx;
+        tls_ctx = ctx;
+        mark_block = ctx->arena_block;
+        mark_off = ctx->arena_off;
+        mark_used = ctx->arena_used;
+        ctx->api_depth++;
     }
     ~DeviceScope() {
+        ctx->api_depth--;
+        ctx->arena_block = mark_block;
+        ctx->arena_off = mark_off;
+        ctx->arena_used = mark_used;
+        if (ctx->api_depth == 0 && ctx->arena_blocks.size() > 1) {
+            // consolidate into one block sized for the peak so the next call bumps through contiguous memory
+            cudaStreamSynchronize(ctx->stream);
+            size_t total = 0;
+            for (auto& b : ctx->arena_blocks) {
+                total += b.cap;
+                cudaFree(b.p);
+            }
+            ctx->arena_blocks.clear();
+            char* p = nullptr;
+            if (cudaMalloc((void**)&p, total) == cudaSuccess) ctx->arena_blocks.push_back({p, total});
+            else cudaGetLastError();
+            ctx->arena_block = 0;
+            ctx->arena_off = 0;
+            ctx->arena_used = 0;
+        }
+        tls_ctx = prev_ctx;
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
@@ -55,6 +129,8 @@ int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
     if (cudaSetDevice(device) != cudaSuccess) return OBVHS_ERR_CUDA;
     ObvhsContext* ctx = new ObvhsContext();
     ctx->device = device;
+    const char* tr = getenv("OBVHS_TRACE");
+    ctx->trace = tr && tr[0] == '1';
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -88,6 +164,7 @@ void obvhs_cuda_destroy(ObvhsContext* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& b : ctx->arena_blocks) cudaFree(b.p);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -311,16 +388,25 @@ int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tri
     // core_build_time brackets PLOC -> reinsertion -> collapse (cwbvh/builder.rs:62-76), measured on the device
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     ObvhsBvh2* bvh2 = nullptr;
-    ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
-                             (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    {
+        TraceScope ts(ctx, "build_ploc");
+        ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                                 (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    }
     struct Guard {
         ObvhsBvh2* b;
         ~Guard() { obvhs_cuda_bvh2_free(b); }
     } guard{bvh2};
-    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    {
+        TraceScope ts(ctx, "reinsertion_optimize");
+        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    }
     u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 3 ? 3 : params->max_prims_per_leaf);  // builder.rs:74
     ObvhsCwBvh* cw = nullptr;
-    ST_TRY(bvh2_to_cwbvh_device(ctx, bvh2, mp, true, &cw));
+    {
+        TraceScope ts(ctx, "bvh2_to_cwbvh");
+        ST_TRY(bvh2_to_cwbvh_device(ctx, bvh2, mp, true, &cw));
+    }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int rc = cwbvh_permute_tris_device(ctx, cw, d_tris, n);
     if (rc == OBVHS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = OBVHS_ERR_CUDA;

@@ -81,6 +81,13 @@ int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     return OBVHS_OK;
 }
 
+int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents) {
+    if (bvh->node_count == 0) return OBVHS_OK;
+    compute_parents_kernel<<<div_up(bvh->node_count, 256), 256, 0, ctx->stream>>>(bvh->nodes, (u32)bvh->node_count, d_parents);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     if (bvh->node_count < 2) return OBVHS_OK;
     if (!bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));

@@ -109,6 +109,39 @@ struct ObvhsContext {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* pinned = nullptr;  // 4 KB of pinned host memory for small read-backs
     int sm_count = OBVHS_SM_COUNT;
+    // Scratch arena: grow-only device blocks reused by every call (the reference's builders keep their Vecs for reuse,
+    // ploc/mod.rs:35-54). Allocation is a pointer bump; API calls release back to their entry mark.
+    struct ArenaBlock {
+        char* p;
+        size_t cap;
+    };
+    std::vector<ArenaBlock> arena_blocks;
+    size_t arena_block = 0, arena_off = 0;  // bump position: block index + offset inside it
+    size_t arena_peak = 0, arena_used = 0;
+    int api_depth = 0;
+    bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
+};
+
+// Stage scope: when tracing, synchronises the stream at exit and prints the elapsed wall time of the stage.
+struct TraceScope {
+    ObvhsContext* ctx;
+    const char* name;
+    double t0 = 0;
+    u64 l0 = 0;
+    static double now();
+    TraceScope(ObvhsContext* c, const char* n) : ctx(c), name(n) {
+        if (ctx->trace) {
+            cudaStreamSynchronize(ctx->stream);
+            t0 = now();
+            l0 = ctx->launches;
+        }
+    }
+    ~TraceScope() {
+        if (ctx->trace) {
+            cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[obvhs trace] %-28s %9.3f ms  %5llu launches\n", name, (now() - t0) * 1e3, (unsigned long long)(ctx->launches - l0));
+        }
+    }
 };
 
 struct ObvhsBvh2 {
@@ -162,29 +195,18 @@ struct ObvhsCwBvh {
 
 static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
-// stream-ordered scratch allocation that frees itself (cudaFreeAsync) at scope exit
+// Scratch from the context's arena (see ObvhsContext). Released in bulk when the API call that allocated it returns.
+void* obvhs_arena_alloc(size_t bytes);  // uses the context of the API call in flight on this thread; nullptr on failure
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    cudaStream_t s = nullptr;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }
-    cudaError_t alloc(size_t count, cudaStream_t stream) {
-        release();
-        s = stream;
+    cudaError_t alloc(size_t count, cudaStream_t) {
         if (count == 0) count = 1;
-        return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
-    }
-    void release() {
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr;
-    }
-    T* take() {
-        T* q = p;
-        p = nullptr;
-        return q;
+        p = static_cast<T*>(obvhs_arena_alloc(count * sizeof(T)));
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
 };
 
@@ -238,6 +260,7 @@ int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals,
                          u32** sorted_keys, u32** sorted_vals);
 // bvh2.cu
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents);
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 // reinsertion.cu
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);

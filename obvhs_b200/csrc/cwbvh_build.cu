@@ -401,13 +401,11 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     DevBuf<float> root_box;
     const u32* parents = bvh->parents;
     if (!parents) {  // the converter does not need Bvh2::parents; the bottom-up pass does -> scratch copy
-        ObvhsBvh2 tmp = *bvh;
-        tmp.parents = nullptr;
-        ST_TRY(bvh2_compute_parents_device(ctx, &tmp));
-        parents_tmp.p = tmp.parents;
-        parents_tmp.s = s;
-        parents = tmp.parents;
+        CU_TRY(ctx, parents_tmp.alloc(n_nodes, s));
+        ST_TRY(bvh2_compute_parents_into(ctx, bvh, parents_tmp.p));
+        parents = parents_tmp.p;
     }
+    TraceScope* tsp = new TraceScope(ctx, "  cwbvh_cost");
     CU_TRY(ctx, P.alloc(n_nodes, s));
     CU_TRY(ctx, K.alloc(n_nodes, s));
     CU_TRY(ctx, arrivals.alloc(n_nodes, s));
@@ -424,6 +422,8 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, cudaMemcpyAsync(h, K.p, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaMemcpyAsync(h + 8, root_box.p, 32, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
+    delete tsp;
+    TraceScope ts_emit(ctx, "  cwbvh_emit");
     const u32 M = h[0];
     memcpy(&cw->total_aabb, h + 8, 32);  // bvh2_to_cwbvh.rs:506 total_aabb = bvh2.nodes[0].aabb
     if (M == 0 || M > n_nodes) {

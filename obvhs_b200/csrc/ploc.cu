@@ -446,6 +446,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     CU_TRY(ctx, merge.alloc(n, s));
     CU_TRY(ctx, scan_status.alloc(div_up(n, SEARCH_TILE) + 1, s));
 
+    TraceScope* tsp = new TraceScope(ctx, "  ploc_leaves_morton");
     ploc_globals_init_kernel<<<1, 32, 0, s>>>(g.p, un);
     KERNEL_CHECK(ctx);
     const int grid_stride_blocks = (int)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 8);
@@ -461,6 +462,8 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
         if (probe->codes_hi) CU_TRY(ctx, cudaMemsetAsync(probe->codes_hi, 0, n * 8, s));
         if (probe->total) CU_TRY(ctx, cudaMemcpyAsync(probe->total, g.p->total, sizeof(ObvhsAabb), cudaMemcpyDeviceToDevice, s));
     }
+    delete tsp;
+    tsp = new TraceScope(ctx, "  ploc_sort_gather");
     u64* skeys;
     u32* order;
     ST_TRY(radix_sort_pairs_u64(ctx, keys.p, keys_alt.p, vals.p, vals_alt.p, n, 8, &skeys, &order));
@@ -468,6 +471,8 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     gather_nodes_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(bufA.p, order, un, bufB.p);
     KERNEL_CHECK(ctx);
 
+    delete tsp;
+    TraceScope ts_iter(ctx, "  ploc_iterations");
     Node32 *cur = bufB.p, *next = bufA.p;
     u32* h_state = reinterpret_cast<u32*>(ctx->pinned);
     u32 count = un;

@@ -353,13 +353,18 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
         if (count == 0 || take < 2) continue;
         const u32 round_stamp = (u32)k + 1;
         const u32 m = take - 1;
+        TraceScope* tsp = new TraceScope(ctx, "  reins_candidates_sort");
         cand_init_kernel<<<div_up(m, 256), 256, 0, s>>>(bvh->nodes, m, ckeys.p, cvals.p);
         KERNEL_CHECK(ctx);
         u32 *sk, *cand_ids;
         ST_TRY(radix_sort_pairs_u32(ctx, ckeys.p, ckeys_alt.p, cvals.p, cvals_alt.p, m, 4, &sk, &cand_ids));
+        delete tsp;
+        tsp = new TraceScope(ctx, "  reins_find");
         find_reinsertion_kernel<<<div_up(count, 128), 128, 0, s>>>(bvh->nodes, bvh->parents, cand_ids, count, r_from.p, r_to.p, r_diff.p,
                                                                   gkeys.p, gvals.p);
         KERNEL_CHECK(ctx);
+        delete tsp;
+        tsp = new TraceScope(ctx, "  reins_gain_sort_resolve");
         u32 *gk, *order;
         ST_TRY(radix_sort_pairs_u32(ctx, gkeys.p, gkeys_alt.p, gvals.p, gvals_alt.p, count, 4, &gk, &order));
         reinsert_state_reset_kernel<<<1, 1, 0, s>>>(st.p, 0);
@@ -369,7 +374,10 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
         CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
         const u32 active = h[0];
-        if (active == 0) continue;
+        if (active == 0) {
+            delete tsp;
+            continue;
+        }
         const int blocks = div_up(active, 256);
         for (;;) {
             iter_stamp++;
@@ -383,6 +391,8 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
             CU_TRY(ctx, cudaStreamSynchronize(s));
             if (h[1] == 0) break;
         }
+        delete tsp;
+        TraceScope ts_apply(ctx, "  reins_apply_refit");
         apply_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, bvh->nodes, bvh->parents);
         KERNEL_CHECK(ctx);
         refit_mark_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, bvh->parents, mark.p, pending.p, round_stamp);
