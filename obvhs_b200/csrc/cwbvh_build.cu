@@ -14,8 +14,12 @@
 //                              child_base(c_j) = child_base(N) + k(N) + sum_{i<j} (K(c_i) - 1)
 //                              prim_base(c_j)  = prim_base(N) + direct_prims(N) + sum_{i<j} P(c_i)
 //                          so every node lands at the index and with the bytes the sequential recursion gives.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "cwbvh_exponent.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -38,8 +42,10 @@ __device__ __forceinline__ u32 dec_meta(const Dec* __restrict__ dec, u32 node, u
 }
 
 struct CwGlobals {
-    u32 error;       // 1: DISTRIBUTE/INVALID decision on the emit path (non-finite costs), 2: child left unassigned
-    u32 queue_count; // wide nodes queued for the next level
+    u32 error;           // 1: DISTRIBUTE/INVALID decision on the emit path (non-finite costs), 2: child left unassigned, 3: count mismatch
+    u32 queue_count[3];  // wide nodes queued by level L for level L+1, in slot L % 3
+    u32 emitted;         // wide nodes written
+    u32 levels;
 };
 
 // get_children (bvh2_to_cwbvh.rs:346-397), iterative. Returns child_count; children in the recursion's order.
@@ -202,16 +208,14 @@ struct WorkItem {
     u32 bvh2_node, child_base, prim_base;
 };
 
-// K12: convert_to_cwbvh_impl (bvh2_to_cwbvh.rs:75-193) for one wide node per thread.
-__global__ void __launch_bounds__(128) cwbvh_emit_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ bvh2_prims,
-                                                         const Dec* __restrict__ dec, const u32* __restrict__ P, const u32* __restrict__ K,
-                                                         const u32* __restrict__ queue, u32 queue_len, u32* __restrict__ next_queue,
-                                                         WorkItem* work, uint4* __restrict__ out_nodes, u32* __restrict__ out_prims,
-                                                         int order_children, CwGlobals* g) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= queue_len) return;
-    const u32 x = queue[t];  // CWBVH node index
-    const WorkItem w = work[x];
+// K12: convert_to_cwbvh_impl (bvh2_to_cwbvh.rs:75-193) for one wide node (CWBVH index x).
+__device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __restrict__ bvh2_prims, const Dec* __restrict__ dec,
+                               const u32* __restrict__ P, const u32* __restrict__ K, u32 x, u32* __restrict__ next_queue, u32* queue_counter,
+                               WorkItem* work, uint4* __restrict__ out_nodes, u32* __restrict__ out_prims, int order_children, CwGlobals* g) {
+    WorkItem w;
+    w.bvh2_node = __ldcg(&work[x].bvh2_node);
+    w.child_base = __ldcg(&work[x].child_base);
+    w.prim_base = __ldcg(&work[x].prim_base);
     const Node32 me = load_node(nodes + w.bvh2_node);
     const Box aabb = node_box(me);
     // node.p, node.e (bvh2_to_cwbvh.rs:82-99)
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(128) cwbvh_emit_kernel(const Node32* __restric
     }
     // pass 2: work items of the internal children
     if (num_internal) {
-        u32 qbase = atomicAdd(&g->queue_count, num_internal);
+        u32 qbase = atomicAdd(queue_counter, num_internal);
         u32 j = 0, k_before = 0, p_before = 0;
 #pragma unroll
         for (int s = 0; s < 8; s++) {
@@ -364,13 +368,59 @@ __global__ void __launch_bounds__(128) cwbvh_emit_kernel(const Node32* __restric
     o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3; o[4] = q4;
 }
 
-__global__ void cwbvh_root_kernel(WorkItem* work, u32* queue, CwGlobals* g) {
-    work[0] = WorkItem{0u, 1u, 0u};  // convert_to_cwbvh_impl(0, 0): nodes = [default] -> child_base = 1
-    queue[0] = 0;
-    g->queue_count = 0;
-    g->error = 0;
+struct EmitArgs {
+    const Node32* nodes;
+    const u32* bvh2_prims;
+    const Dec* dec;
+    const u32* P;
+    const u32* K;
+    u32* queue_a;
+    u32* queue_b;
+    WorkItem* work;
+    uint4* out_nodes;
+    u32* out_prims;
+    int order_children;
+    u32 expected;  // M = K[root]
+    CwGlobals* g;
+};
+
+// All CWBVH levels in ONE cooperative launch: level L's wide nodes are emitted by a grid-stride loop, their INTERNAL
+// children are queued for level L+1, a grid-wide barrier separates the levels. No host round trips.
+__global__ void __launch_bounds__(128) cwbvh_emit_all_kernel(EmitArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    CwGlobals* g = a.g;
+    if (tid == 0) {
+        a.work[0] = WorkItem{0u, 1u, 0u};  // convert_to_cwbvh_impl(0, 0): nodes = [default] -> child_base = 1
+        a.queue_a[0] = 0;
+        g->queue_count[0] = g->queue_count[1] = g->queue_count[2] = 0;
+        g->error = 0;
+        g->emitted = 0;
+        g->levels = 0;
+    }
+    grid.sync();
+    u32 qlen = 1, emitted = 0;
+    u32 *cur = a.queue_a, *nxt = a.queue_b;
+    for (u32 level = 0; qlen > 0; level++) {
+        if (tid == 0) g->queue_count[(level + 1) % 3] = 0;  // slot of the next level
+        for (u32 t = tid; t < qlen; t += nthreads)
+            emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, a.K, __ldcg(&cur[t]), nxt, &g->queue_count[level % 3], a.work, a.out_nodes, a.out_prims,
+                           a.order_children, g);
+        grid.sync();
+        emitted += qlen;
+        qlen = __ldcg(&g->queue_count[level % 3]);
+        if (__ldcg(&g->error) != 0) break;
+        if (emitted + qlen > a.expected) {
+            if (tid == 0) g->error = 3;
+            break;
+        }
+        u32* t2 = cur;
+        cur = nxt;
+        nxt = t2;
+        if (tid == 0) g->levels = level + 1;
+    }
+    if (tid == 0) g->emitted = emitted;
 }
-__global__ void cwbvh_reset_queue_kernel(CwGlobals* g) { g->queue_count = 0; }
 
 __global__ void root_aabb_kernel(const Node32* nodes, float* out8) {
     Node32 r = load_node(nodes);
@@ -437,35 +487,25 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, work.alloc(M, s));
     CU_TRY(ctx, queue_a.alloc(M, s));
     CU_TRY(ctx, queue_b.alloc(M, s));
-    cwbvh_root_kernel<<<1, 1, 0, s>>>(work.p, queue_a.p, g.p);
-    KERNEL_CHECK(ctx);
-    u32 qlen = 1, emitted = 0;
-    u32 *qc = queue_a.p, *qn = queue_b.p;
-    while (qlen > 0) {
-        cwbvh_emit_kernel<<<div_up(qlen, 128), 128, 0, s>>>(bvh->nodes, bvh->primitive_indices, dec.p, P.p, K.p, qc, qlen, qn, work.p,
-                                                           reinterpret_cast<uint4*>(cw->nodes), cw->primitive_indices, order_children ? 1 : 0,
-                                                           g.p);
+    {
+        EmitArgs ea;
+        ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.dec = dec.p; ea.P = P.p; ea.K = K.p;
+        ea.queue_a = queue_a.p; ea.queue_b = queue_b.p; ea.work = work.p; ea.out_nodes = reinterpret_cast<uint4*>(cw->nodes);
+        ea.out_prims = cw->primitive_indices; ea.order_children = order_children ? 1 : 0; ea.expected = M; ea.g = g.p;
+        int per_sm = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_emit_all_kernel, 128, 0));
+        int blocks = std::min(std::max(1, per_sm) * ctx->sm_count, std::max(1, div_up(M, 128)));
+        void* args[] = {&ea};
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)cwbvh_emit_all_kernel, dim3(blocks), dim3(128), args, 0, s));
         KERNEL_CHECK(ctx);
-        CU_TRY(ctx, cudaMemcpyAsync(h, g.p, sizeof(CwGlobals), cudaMemcpyDeviceToHost, s));
-        cwbvh_reset_queue_kernel<<<1, 1, 0, s>>>(g.p);
-        KERNEL_CHECK(ctx);
-        CU_TRY(ctx, cudaStreamSynchronize(s));
-        if (h[0] != 0) {
-            OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: %s (non-finite AABBs? the reference panics here)",
-                          h[0] == 2 ? "order_children left a child unassigned" : "invalid decision on the emit path");
-            return OBVHS_ERR_NAN_INPUT;
-        }
-        emitted += qlen;
-        qlen = h[1];
-        if (emitted + qlen > M) {
-            OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: emitted %u + %u nodes > expected %u", emitted, qlen, M);
-            return OBVHS_ERR_CUDA;
-        }
-        std::swap(qc, qn);
     }
-    if (emitted != M) {
-        OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: emitted %u nodes, expected %u", emitted, M);
-        return OBVHS_ERR_CUDA;
+    CU_TRY(ctx, cudaMemcpyAsync(h, g.p, sizeof(CwGlobals), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (h[0] != 0 || h[4] != M) {
+        OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: %s (emitted %u of %u nodes; non-finite AABBs? the reference panics here)",
+                      h[0] == 2 ? "order_children left a child unassigned" : h[0] == 3 ? "node count mismatch" : "invalid decision on the emit path",
+                      h[4], M);
+        return OBVHS_ERR_NAN_INPUT;
     }
     guard.b = nullptr;
     *out = cw;

@@ -186,6 +186,39 @@ __device__ __forceinline__ Box smem_box(const Node32* w, int j) {
     return Box{a.x, a.y, a.z, b.x, b.y, b.z};
 }
 
+// The neighbour choice of cluster i (window entry li). r1: the reference's r=1 fast path (ploc/mod.rs:329-382): -1 iff
+// cost(i-1,i) < cost(i,i+1), first element +1, last element -1. Otherwise find_best_node (ploc/mod.rs:624-650): scan
+// i-R..i-1 then i+1..i+R with `cost <= best` so the LAST minimum wins; cost(lo,hi) = half_area(union(nodes[lo], nodes[hi]))
+// with the lower index first.
+template <int R>
+__device__ __forceinline__ int search_offset(const Node32* win, int li, u32 i, u32 count, int r1) {
+    const Box me = smem_box(win, li);
+    if (r1) {
+        if (i == count - 1) return -1;
+        float last = i > 0 ? box_half_area(box_union(smem_box(win, li - 1), me)) : __int_as_float(0x7f800000);
+        float cost = box_half_area(box_union(me, smem_box(win, li + 1)));
+        return last < cost ? -1 : 1;
+    }
+    int best = 0;
+    float best_cost = __int_as_float(0x7f800000);
+    const int nb = (int)min((u32)R, i), ne = (int)min((u32)R, count - 1 - i);
+    for (int o = -nb; o < 0; o++) {
+        float c = box_half_area(box_union(smem_box(win, li + o), me));
+        if (c <= best_cost) {
+            best = o;
+            best_cost = c;
+        }
+    }
+    for (int o = 1; o <= ne; o++) {
+        float c = box_half_area(box_union(me, smem_box(win, li + o)));
+        if (c <= best_cost) {
+            best = o;
+            best_cost = c;
+        }
+    }
+    return best;
+}
+
 // K5. One thread per node. The tile's window [tile-R, tile+TILE+R) of sorted cluster AABBs is brought into shared
 // memory by one TMA bulk copy. r1: the reference's r=1 fast path (ploc/mod.rs:329-382): -1 iff cost(i-1,i) < cost(i,i+1),
 // first element +1, last element -1. Otherwise find_best_node (ploc/mod.rs:624-650): scan i-R..i-1 then i+1..i+R with
@@ -216,37 +249,7 @@ __global__ void __launch_bounds__(SEARCH_TILE) ploc_search_kernel(const Node32* 
     mbar_wait(&bar, 0);
     const u32 i = tile0 + threadIdx.x;
     if (i >= count) return;
-    const int li = (int)(i - lo);
-    const Box me = smem_box(win, li);
-    int off;
-    if (r1) {
-        if (i == count - 1) {
-            off = -1;
-        } else {
-            float last = i > 0 ? box_half_area(box_union(smem_box(win, li - 1), me)) : __int_as_float(0x7f800000);
-            float cost = box_half_area(box_union(me, smem_box(win, li + 1)));
-            off = last < cost ? -1 : 1;
-        }
-    } else {
-        int best = 0;
-        float best_cost = __int_as_float(0x7f800000);
-        const int nb = (int)min((u32)R, i), ne = (int)min((u32)R, count - 1 - i);
-        for (int o = -nb; o < 0; o++) {
-            float c = box_half_area(box_union(smem_box(win, li + o), me));
-            if (c <= best_cost) {
-                best = o;
-                best_cost = c;
-            }
-        }
-        for (int o = 1; o <= ne; o++) {
-            float c = box_half_area(box_union(me, smem_box(win, li + o)));
-            if (c <= best_cost) {
-                best = o;
-                best_cost = c;
-            }
-        }
-        off = best;
-    }
+    const int off = search_offset<R>(win, (int)(i - lo), i, count, r1);
     merge[i] = (signed char)off;
 }
 
@@ -369,8 +372,97 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
     }
 }
 
-__global__ void ploc_finish_kernel(const Node32* __restrict__ cur, Node32* __restrict__ bvh_nodes) {
-    if (threadIdx.x < 2) reinterpret_cast<float4*>(bvh_nodes)[threadIdx.x] = reinterpret_cast<const float4*>(cur)[threadIdx.x];  // ploc/mod.rs:499
+// The last iterations (count <= PLOC_TAIL) in ONE CTA: clusters live in shared memory, each iteration is search ->
+// flags -> block scan -> scatter, separated by __syncthreads instead of kernel launches and host round trips. Same
+// arithmetic, same slots as K5/K6. Ends with bvh.nodes[0] = the last cluster (ploc/mod.rs:499).
+constexpr int PLOC_TAIL = 2048, TAIL_THREADS = 1024, TAIL_ITEMS = PLOC_TAIL / TAIL_THREADS;
+template <int R>
+__global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* __restrict__ cur_g, Node32* __restrict__ bvh_nodes, PlocGlobals* g,
+                                                                 int parity, u32 depth, u32 search_depth_threshold) {
+    extern __shared__ __align__(128) unsigned char tail_smem[];
+    Node32* buf[2] = {reinterpret_cast<Node32*>(tail_smem), reinterpret_cast<Node32*>(tail_smem) + PLOC_TAIL};
+    __shared__ signed char sm[PLOC_TAIL];
+    __shared__ u32 s_wsum[TAIL_THREADS / 32];
+    u32 count = g->state[parity].count;
+    u32 insert = g->state[parity].insert_index;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (u32 j = tid; j < count * 2; j += TAIL_THREADS) reinterpret_cast<float4*>(buf[0])[j] = __ldg(reinterpret_cast<const float4*>(cur_g) + j);
+    int src = 0;
+    __syncthreads();
+    while (count > 1) {
+        const Node32* cur = buf[src];
+        Node32* next = buf[src ^ 1];
+        const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < TAIL_ITEMS; k++) {
+            u32 i = tid * TAIL_ITEMS + k;
+            if (i < count) sm[i] = (signed char)search_offset<R>(cur, (int)i, i, count, r1);
+        }
+        __syncthreads();
+        u32 flags = 0, local = 0;  // packed: outputs in the low 16 bits, merges in the high 16
+#pragma unroll
+        for (int k = 0; k < TAIL_ITEMS; k++) {
+            u32 i = tid * TAIL_ITEMS + k;
+            if (i < count) {
+                int m = sm[i];
+                int mb = sm[(int)i + m];
+                bool mutual = (m + mb) == 0;
+                bool emits = mutual && m < 0;
+                bool outp = !mutual || emits;
+                flags |= ((outp ? 1u : 0u) | (emits ? 2u : 0u)) << (2 * k);
+                local += (outp ? 1u : 0u) + (emits ? 0x10000u : 0u);
+            }
+        }
+        u32 x = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_wsum[w] = x;
+        __syncthreads();
+        u32 wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < TAIL_THREADS / 32; k++) {
+            u32 sv = s_wsum[k];
+            if (k < w) wbase += sv;
+            total += sv;
+        }
+        u32 run = wbase + x - local;
+#pragma unroll
+        for (int k = 0; k < TAIL_ITEMS; k++) {
+            u32 f = (flags >> (2 * k)) & 3u;
+            if (f & 1u) {
+                u32 i = tid * TAIL_ITEMS + k;
+                u32 pos = run & 0xffffu;
+                Node32 left = cur[i];
+                if (f & 2u) {
+                    u32 mi = run >> 16;
+                    Node32 right = cur[(int)i + sm[i]];
+                    u32 slot = insert - 2 * (mi + 1);
+                    store_node(bvh_nodes + slot, left);
+                    store_node(bvh_nodes + slot + 1, right);
+                    next[pos] = make_node32(box_union(node_box(left), node_box(right)), 0u, slot);
+                    run += 0x10001u;
+                } else {
+                    next[pos] = left;
+                    run += 1u;
+                }
+            }
+        }
+        __syncthreads();
+        if ((total & 0xffffu) >= count) break;  // no progress (non-finite boxes): leave count > 1, the host reports it
+        count = total & 0xffffu;
+        insert -= 2 * (total >> 16);
+        src ^= 1;
+        depth++;
+    }
+    if (tid < 2) reinterpret_cast<float4*>(bvh_nodes)[tid] = reinterpret_cast<const float4*>(buf[src])[tid];  // ploc/mod.rs:499
+    if (tid == 0) {
+        g->state[0].count = count;
+        g->state[0].insert_index = insert;
+        g->state[1].count = depth;  // total iterations, read back by the host
+    }
 }
 
 __global__ void iota_kernel(u32* p, u32 n) {
@@ -382,6 +474,19 @@ template <int R>
 void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGlobals* g, int parity, int r1, signed char* merge,
                    u64* scan_status, u32* ticket) {
     ploc_search_kernel<R><<<div_up(count, SEARCH_TILE), SEARCH_TILE, 0, ctx->stream>>>(cur, g, parity, r1, merge, scan_status, ticket);
+}
+
+template <int R>
+cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth, u32 thr) {
+    constexpr int smem = 2 * PLOC_TAIL * (int)sizeof(Node32);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(ploc_tail_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    ploc_tail_kernel<R><<<1, TAIL_THREADS, smem, ctx->stream>>>(cur, bvh_nodes, g, parity, depth, thr);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -477,7 +582,8 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     u32* h_state = reinterpret_cast<u32*>(ctx->pinned);
     u32 count = un;
     size_t depth = 0;
-    while (count > 1) {
+    bool nan_checked = false;
+    while (count > PLOC_TAIL) {
         const int parity = (int)(depth & 1);
         const int r1 = (search_distance == 1 || depth < search_depth_threshold) ? 1 : 0;
         u32* ticket = &g.p->ticket;
@@ -496,6 +602,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
         CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[parity ^ 1], sizeof(PlocState), cudaMemcpyDeviceToHost, s));
         if (depth == 0) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
+        nan_checked = true;
         if (depth == 0 && h_state[4]) {
             OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
             return OBVHS_ERR_NAN_INPUT;
@@ -509,8 +616,34 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
         std::swap(cur, next);
         depth++;
     }
-    ploc_finish_kernel<<<1, 32, 0, s>>>(cur, bvh->nodes);
-    KERNEL_CHECK(ctx);
+    {
+        // tail: everything that is left (count <= PLOC_TAIL, possibly the whole build) in one single-CTA launch
+        const int parity = (int)(depth & 1);
+        const u32 thr = (u32)std::min<size_t>(search_depth_threshold, 0xffffffffu);
+        cudaError_t e;
+        switch (search_distance) {
+            case 1: e = launch_tail<1>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            case 2: e = launch_tail<2>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            case 6: e = launch_tail<6>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            case 14: e = launch_tail<14>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            case 24: e = launch_tail<24>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            default: e = launch_tail<32>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+        }
+        ctx->launches++;
+        CU_TRY(ctx, e);
+        CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[0], 2 * sizeof(PlocState), cudaMemcpyDeviceToHost, s));
+        if (!nan_checked) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        if (!nan_checked && h_state[4]) {
+            OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
+            return OBVHS_ERR_NAN_INPUT;
+        }
+        if (h_state[0] != 1) {
+            OBVHS_SET_ERR(ctx, "PLOC tail ended with %u clusters; non-finite AABBs?", h_state[0]);
+            return OBVHS_ERR_NAN_INPUT;
+        }
+        depth = h_state[2];
+    }
     bvh->max_depth = std::max<size_t>(96, depth + 1);  // ploc/mod.rs:501
     bvh->ploc_iterations = depth;
     bvh->children_are_ordered_after_parents = true;  // ploc/mod.rs:502

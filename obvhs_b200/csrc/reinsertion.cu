@@ -16,7 +16,11 @@
 //                           repeat. Accepted entries write disjoint nodes/parents and are applied in one kernel; the
 //                           dirty ancestor paths are then refit bottom-up (pending-child counters), which produces the
 //                           same tight boxes as the reference's per-entry refit_from_fast walks.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -123,164 +127,174 @@ __global__ void __launch_bounds__(128) find_reinsertion_kernel(const Node32* __r
 }
 
 struct ReinsertState {
-    u32 active;     // entries with area_diff > 0 (they form a prefix of the gain-sorted list)
-    u32 undecided;  // entries still undecided after the current resolution iteration
-    u32 applied;    // running total of applied reinsertions
-    u32 pad;
+    u32 active;        // entries with area_diff > 0 (they form a prefix of the gain-sorted list)
+    u32 undecided[3];  // entries still undecided after resolution iteration i, in slot i % 3
+    u32 applied;       // running total of applied reinsertions
+    u32 error;         // 1: resolution iteration counter overflow
+    u32 pad[2];
 };
 
-// cells of entry r (gain order): {to, from, sibling(from), parent(to), parent(from)} (reinsertion.rs:198-208)
-__global__ void __launch_bounds__(256) conflicts_prep_kernel(const u32* __restrict__ order, const u32* __restrict__ r_from,
-                                                             const u32* __restrict__ r_to, const float* __restrict__ r_diff,
-                                                             const u32* __restrict__ parents, u32 count, u32* __restrict__ cells,
-                                                             u32* __restrict__ status, ReinsertState* st) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= count) return;
-    u32 j = order[r];
-    float d = r_diff[j];
-    if (!(d > 0.0f)) {  // reinsertion.rs:178-180
-        status[r] = 2;
-        return;
-    }
-    u32 from = r_from[j], to = r_to[j];
-    u32* c = cells + (size_t)r * 5;
-    c[0] = to;
-    c[1] = from;
-    c[2] = sibling_id(from);
-    c[3] = parents[to];
-    c[4] = parents[from];
-    status[r] = 0;
-    atomicMax(&st->active, r + 1);
-}
+struct ResolveArgs {
+    const u32* order;      // gain-sorted rank -> candidate rank
+    const u32* r_from;
+    const u32* r_to;
+    const float* r_diff;
+    u32 count;
+    u32* cells;            // 5 per entry
+    u32* status;           // 0 undecided, 1 accepted, 2 rejected / inactive
+    ReinsertState* st;
+    u32* touched;          // per node, == round_stamp when touched this round
+    unsigned long long* reserve;  // per node, min over ((~stamp) << 32 | rank)
+    u32* mark;             // per node, == round_stamp when on a dirty path
+    u32* pending;          // per node, arrivals still due before the node can be refit
+    Node32* nodes;
+    u32* parents;
+    u32 round_stamp;       // 1-based round index
+};
 
-__global__ void __launch_bounds__(256) resolve_reserve_kernel(const u32* __restrict__ cells, u32* __restrict__ status, const ReinsertState* st,
-                                                              const u32* __restrict__ touched, u32 round_stamp,
-                                                              unsigned long long* __restrict__ reserve, u32 iter_stamp) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= st->active || status[r] != 0) return;
-    const u32* c = cells + (size_t)r * 5;
-    u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
-    if (touched[c0] == round_stamp || touched[c1] == round_stamp || touched[c2] == round_stamp || touched[c3] == round_stamp ||
-        touched[c4] == round_stamp) {
-        status[r] = 2;
-        return;
-    }
-    // newer iterations carry a smaller high word, so stale reservations of earlier iterations always lose
-    unsigned long long v = ((unsigned long long)(~iter_stamp) << 32) | r;
-    atomicMin(reserve + c0, v);
-    atomicMin(reserve + c1, v);
-    atomicMin(reserve + c2, v);
-    atomicMin(reserve + c3, v);
-    atomicMin(reserve + c4, v);
-}
-
-__global__ void __launch_bounds__(256) resolve_commit_kernel(const u32* __restrict__ cells, u32* __restrict__ status, ReinsertState* st,
-                                                             u32* __restrict__ touched, u32 round_stamp,
-                                                             const unsigned long long* __restrict__ reserve, u32 iter_stamp) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    bool undecided = false;
-    if (r < st->active && status[r] == 0) {
-        const u32* c = cells + (size_t)r * 5;
-        unsigned long long v = ((unsigned long long)(~iter_stamp) << 32) | r;
-        u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
-        if (reserve[c0] == v && reserve[c1] == v && reserve[c2] == v && reserve[c3] == v && reserve[c4] == v) {
-            status[r] = 1;
-            touched[c0] = round_stamp;
-            touched[c1] = round_stamp;
-            touched[c2] = round_stamp;
-            touched[c3] = round_stamp;
-            touched[c4] = round_stamp;
-        } else {
-            undecided = true;
+// K10, one cooperative launch per round: conflict cells -> greedy-MIS resolution by deterministic reservations ->
+// apply -> dirty-path marking -> bottom-up refit. Phases are separated by grid-wide barriers; no host round trips.
+__global__ void __launch_bounds__(256) reinsert_resolve_apply_kernel(ResolveArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    ReinsertState* st = a.st;
+    if (tid == 0) st->undecided[0] = st->undecided[1] = st->undecided[2] = 0;
+    // ---- cells of entry r (gain order): {to, from, sibling(from), parent(to), parent(from)} (reinsertion.rs:198-208)
+    for (u32 r = tid; r < a.count; r += nthreads) {
+        u32 j = a.order[r];
+        float d = a.r_diff[j];
+        if (!(d > 0.0f)) {  // reinsertion.rs:178-180
+            a.status[r] = 2;
+            continue;
         }
+        u32 from = a.r_from[j], to = a.r_to[j];
+        u32* c = a.cells + (size_t)r * 5;
+        c[0] = to;
+        c[1] = from;
+        c[2] = sibling_id(from);
+        c[3] = a.parents[to];
+        c[4] = a.parents[from];
+        a.status[r] = 0;
+        atomicMax(&st->active, r + 1);
     }
-    u32 b = __ballot_sync(0xffffffffu, undecided);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->undecided, (u32)__popc(b));
-}
-
-// reinsert_node without its two refits (reinsertion.rs:336-382). Accepted entries touch disjoint nodes/parents.
-__global__ void __launch_bounds__(256) apply_kernel(const u32* __restrict__ cells, const u32* __restrict__ status, ReinsertState* st,
-                                                    Node32* nodes, u32* parents) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    bool acc = r < st->active && status[r] == 1;
-    if (acc) {
-        const u32* c = cells + (size_t)r * 5;
+    grid.sync();
+    const u32 active = __ldcg(&st->active);
+    // ---- resolution: the accepted set of the reference's sequential sweep (see the file header)
+    for (u32 iter = 1;; iter++) {
+        if (iter > 0xffffu) {
+            if (tid == 0) st->error = 1;
+            break;
+        }
+        const u32 stamp = (a.round_stamp << 16) | iter;  // strictly increasing over the whole run
+        if (tid == 0) st->undecided[(iter + 1) % 3] = 0;  // slot of the NEXT iteration; the previous one may still be read
+        for (u32 r = tid; r < active; r += nthreads) {
+            if (__ldcg(&a.status[r]) != 0) continue;
+            const u32* c = a.cells + (size_t)r * 5;
+            u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+            if (__ldcg(&a.touched[c0]) == a.round_stamp || __ldcg(&a.touched[c1]) == a.round_stamp || __ldcg(&a.touched[c2]) == a.round_stamp ||
+                __ldcg(&a.touched[c3]) == a.round_stamp || __ldcg(&a.touched[c4]) == a.round_stamp) {
+                a.status[r] = 2;
+                continue;
+            }
+            // newer stamps carry a smaller high word, so stale reservations always lose against current ones
+            unsigned long long v = ((unsigned long long)(~stamp) << 32) | r;
+            atomicMin(a.reserve + c0, v);
+            atomicMin(a.reserve + c1, v);
+            atomicMin(a.reserve + c2, v);
+            atomicMin(a.reserve + c3, v);
+            atomicMin(a.reserve + c4, v);
+        }
+        grid.sync();
+        u32 und = 0;
+        for (u32 r = tid; r < active; r += nthreads) {
+            if (__ldcg(&a.status[r]) != 0) continue;
+            const u32* c = a.cells + (size_t)r * 5;
+            unsigned long long v = ((unsigned long long)(~stamp) << 32) | r;
+            u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+            if (__ldcg(a.reserve + c0) == v && __ldcg(a.reserve + c1) == v && __ldcg(a.reserve + c2) == v && __ldcg(a.reserve + c3) == v &&
+                __ldcg(a.reserve + c4) == v) {
+                a.status[r] = 1;
+                a.touched[c0] = a.round_stamp;
+                a.touched[c1] = a.round_stamp;
+                a.touched[c2] = a.round_stamp;
+                a.touched[c3] = a.round_stamp;
+                a.touched[c4] = a.round_stamp;
+            } else {
+                und++;
+            }
+        }
+        if (und) atomicAdd(&st->undecided[iter % 3], und);
+        grid.sync();
+        if (__ldcg(&st->undecided[iter % 3]) == 0) break;
+    }
+    // ---- apply: reinsert_node without its two refits (reinsertion.rs:336-382); accepted entries are disjoint
+    u32 applied = 0;
+    for (u32 r = tid; r < active; r += nthreads) {
+        if (__ldcg(&a.status[r]) != 1) continue;
+        const u32* c = a.cells + (size_t)r * 5;
         u32 to = c[0], from = c[1], sib = c[2], parent_id = c[4];
-        Node32 sibling_node = load_node(nodes + sib);
-        Node32 dst_node = load_node(nodes + to);
+        Node32 sibling_node = load_node_cg(a.nodes + sib);
+        Node32 dst_node = load_node_cg(a.nodes + to);
         Node32 new_to = dst_node;
         new_to.prim_count = 0;  // make_inner(left_sibling(from)); its box is refit below
         new_to.first_index = left_sibling_id(from);
-        store_node(nodes + to, new_to);
-        store_node(nodes + sib, dst_node);
-        store_node(nodes + parent_id, sibling_node);
+        store_node(a.nodes + to, new_to);
+        store_node(a.nodes + sib, dst_node);
+        store_node(a.nodes + parent_id, sibling_node);
         if (dst_node.prim_count == 0) {
-            parents[dst_node.first_index] = sib;
-            parents[dst_node.first_index + 1] = sib;
+            a.parents[dst_node.first_index] = sib;
+            a.parents[dst_node.first_index + 1] = sib;
         }
         if (sibling_node.prim_count == 0) {
-            parents[sibling_node.first_index] = parent_id;
-            parents[sibling_node.first_index + 1] = parent_id;
+            a.parents[sibling_node.first_index] = parent_id;
+            a.parents[sibling_node.first_index + 1] = parent_id;
         }
-        parents[sib] = to;
-        parents[from] = to;
+        a.parents[sib] = to;
+        a.parents[from] = to;
+        applied++;
     }
-    u32 b = __ballot_sync(0xffffffffu, acc);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->applied, (u32)__popc(b));
-}
-
-// Dirty paths: every accepted entry dirties `to` and the old parent of `from`, and all their ancestors. pending[x] counts
-// the arrivals node x waits for before it can be refit: one per dirty child, plus one "self" token when x is a start
-// node. Whoever brings pending[x] to zero refits x and carries on to its parent, so every dirty node is refit exactly
-// once, after all dirty nodes below it.
-__global__ void __launch_bounds__(256) refit_mark_kernel(const u32* __restrict__ cells, u32* __restrict__ status, const ReinsertState* st,
-                                                         const u32* __restrict__ parents, u32* mark, u32* pending, u32 round_stamp) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= st->active || (status[r] & 3u) != 1) return;
-    const u32* c = cells + (size_t)r * 5;
-    u32 starts[2] = {c[0], c[4]};
-    for (int k = 0; k < 2; k++) {
-        u32 node = starts[k];
-        atomicAdd(&pending[node], 1u);  // self token, released by this entry's thread in refit_dirty_kernel
-        if (atomicExch(&mark[node], round_stamp) == round_stamp) continue;
-        while (node != 0) {
-            u32 p = parents[node];
-            atomicAdd(&pending[p], 1u);
-            if (atomicExch(&mark[p], round_stamp) == round_stamp) break;
-            node = p;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) refit_dirty_kernel(const u32* __restrict__ cells, const u32* __restrict__ status, const ReinsertState* st,
-                                                          const u32* __restrict__ parents, Node32* nodes, u32* pending) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= st->active || (status[r] & 3u) != 1) return;
-    const u32* c = cells + (size_t)r * 5;
-    u32 starts[2] = {c[0], c[4]};
-    for (int k = 0; k < 2; k++) {
-        u32 node = starts[k];
-        for (;;) {
-            if (atomicSub(&pending[node], 1u) != 1u) break;  // somebody below is still due
-            Node32 me = load_node_cg(nodes + node);
-            if (me.prim_count == 0) {
-                Node32 c0 = load_node_cg(nodes + me.first_index), c1 = load_node_cg(nodes + me.first_index + 1);
-                store_node(nodes + node, make_node32(box_union(node_box(c0), node_box(c1)), 0u, me.first_index));
+    if (applied) atomicAdd(&st->applied, applied);
+    grid.sync();
+    // ---- dirty paths: every accepted entry dirties `to` and the old parent of `from`, and all their ancestors.
+    // pending[x] = arrivals node x waits for: one per dirty child plus one self token when x is a start node.
+    for (u32 r = tid; r < active; r += nthreads) {
+        if (__ldcg(&a.status[r]) != 1) continue;
+        const u32* c = a.cells + (size_t)r * 5;
+        u32 starts[2] = {c[0], c[4]};
+        for (int k = 0; k < 2; k++) {
+            u32 node = starts[k];
+            atomicAdd(&a.pending[node], 1u);  // self token, released by this entry in the refit phase
+            if (atomicExch(&a.mark[node], a.round_stamp) == a.round_stamp) continue;
+            while (node != 0) {
+                u32 p = __ldcg(&a.parents[node]);
+                atomicAdd(&a.pending[p], 1u);
+                if (atomicExch(&a.mark[p], a.round_stamp) == a.round_stamp) break;
+                node = p;
             }
-            if (node == 0) break;
-            __threadfence();
-            node = parents[node];
         }
     }
-}
-
-__global__ void reinsert_state_reset_kernel(ReinsertState* st, int what) {
-    if (what == 0) {
-        st->active = 0;
-        st->undecided = 0;
-    } else {
-        st->undecided = 0;
+    grid.sync();
+    // ---- refit: whoever brings pending[x] to zero refits x (first.union(second)) and carries on to its parent
+    for (u32 r = tid; r < active; r += nthreads) {
+        if (__ldcg(&a.status[r]) != 1) continue;
+        const u32* c = a.cells + (size_t)r * 5;
+        u32 starts[2] = {c[0], c[4]};
+        for (int k = 0; k < 2; k++) {
+            u32 node = starts[k];
+            for (;;) {
+                if (atomicSub(&a.pending[node], 1u) != 1u) break;  // somebody below is still due
+                Node32 me = load_node_cg(a.nodes + node);
+                if (me.prim_count == 0) {
+                    Node32 c0 = load_node_cg(a.nodes + me.first_index), c1 = load_node_cg(a.nodes + me.first_index + 1);
+                    store_node(a.nodes + node, make_node32(box_union(node_box(c0), node_box(c1)), 0u, me.first_index));
+                }
+                if (node == 0) break;
+                __threadfence();
+                node = __ldcg(&a.parents[node]);
+            }
+        }
     }
+    if (tid == 0) st->active = 0;  // next round starts from zero (nobody reads `active` after the last barrier)
 }
 
 }  // namespace
@@ -346,7 +360,13 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
     CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
     CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
     u32* h = reinterpret_cast<u32*>(ctx->pinned);
-    u32 iter_stamp = 0;
+    if (n_seq > 60000) {
+        OBVHS_SET_ERR(ctx, "reinsertion: ratio sequence too long (%zu)", n_seq);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    int coop_blocks = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, 256, 0));
+    coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
     for (size_t k = 0; k < n_seq; k++) {
         const size_t nc = node_counts[k];
         const u32 take = (u32)std::min(len, nc * 2), count = (u32)(nc - 1);
@@ -367,41 +387,24 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
         tsp = new TraceScope(ctx, "  reins_gain_sort_resolve");
         u32 *gk, *order;
         ST_TRY(radix_sort_pairs_u32(ctx, gkeys.p, gkeys_alt.p, gvals.p, gvals_alt.p, count, 4, &gk, &order));
-        reinsert_state_reset_kernel<<<1, 1, 0, s>>>(st.p, 0);
-        KERNEL_CHECK(ctx);
-        conflicts_prep_kernel<<<div_up(count, 256), 256, 0, s>>>(order, r_from.p, r_to.p, r_diff.p, bvh->parents, count, cells.p, status.p, st.p);
-        KERNEL_CHECK(ctx);
-        CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
-        CU_TRY(ctx, cudaStreamSynchronize(s));
-        const u32 active = h[0];
-        if (active == 0) {
-            delete tsp;
-            continue;
-        }
-        const int blocks = div_up(active, 256);
-        for (;;) {
-            iter_stamp++;
-            resolve_reserve_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, touched.p, round_stamp, reserve.p, iter_stamp);
+        {
+            ResolveArgs ra;
+            ra.order = order; ra.r_from = r_from.p; ra.r_to = r_to.p; ra.r_diff = r_diff.p; ra.count = count;
+            ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
+            ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
+            void* args[] = {&ra};
+            int blocks = std::min(coop_blocks, std::max(1, div_up(count, 256)));
+            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(256), args, 0, s));
             KERNEL_CHECK(ctx);
-            resolve_commit_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, touched.p, round_stamp, reserve.p, iter_stamp);
-            KERNEL_CHECK(ctx);
-            CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
-            reinsert_state_reset_kernel<<<1, 1, 0, s>>>(st.p, 1);
-            KERNEL_CHECK(ctx);
-            CU_TRY(ctx, cudaStreamSynchronize(s));
-            if (h[1] == 0) break;
         }
         delete tsp;
-        TraceScope ts_apply(ctx, "  reins_apply_refit");
-        apply_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, bvh->nodes, bvh->parents);
-        KERNEL_CHECK(ctx);
-        refit_mark_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, bvh->parents, mark.p, pending.p, round_stamp);
-        KERNEL_CHECK(ctx);
-        refit_dirty_kernel<<<blocks, 256, 0, s>>>(cells.p, status.p, st.p, bvh->parents, bvh->nodes, pending.p);
-        KERNEL_CHECK(ctx);
     }
     CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
-    if (applied_out) *applied_out = h[2];
+    if (h[5]) {
+        OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
+        return OBVHS_ERR_CUDA;
+    }
+    if (applied_out) *applied_out = h[4];
     return OBVHS_OK;
 }

@@ -165,6 +165,92 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restr
     }
 }
 
+// ---- single-block sort for small inputs: every pass of the same stable LSD scheme inside one CTA, data in shared memory
+constexpr int BS_THREADS = 1024, BS_WARPS = BS_THREADS / 32;
+template <typename K>
+struct BlockSortCfg {
+    static constexpr int ITEMS = sizeof(K) == 8 ? 4 : 8;
+    static constexpr int MAX_N = BS_THREADS * ITEMS;
+    static constexpr size_t SMEM = (size_t)MAX_N * (sizeof(K) + 4) * 2 + (size_t)(BS_WARPS * 256 + 256) * 4;
+};
+
+template <typename K>
+__global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
+                                                               u32* __restrict__ vout, u32 n, int passes) {
+    constexpr int ITEMS = BlockSortCfg<K>::ITEMS, MAX_N = BlockSortCfg<K>::MAX_N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* kbuf[2] = {reinterpret_cast<K*>(smem_raw), reinterpret_cast<K*>(smem_raw) + MAX_N};
+    u32* vbuf[2] = {reinterpret_cast<u32*>(kbuf[1] + MAX_N), reinterpret_cast<u32*>(kbuf[1] + MAX_N) + MAX_N};
+    u32* whist = vbuf[1] + MAX_N;            // [BS_WARPS][256]
+    u32* dstart = whist + BS_WARPS * 256;    // [256]
+    __shared__ u32 s_wsum[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < MAX_N; j += BS_THREADS) {
+        bool ok = (u32)j < n;
+        kbuf[0][j] = ok ? kin[j] : (K)~(K)0;  // padding sorts behind every valid key and stays there (stable)
+        vbuf[0][j] = ok ? vin[j] : 0u;
+    }
+    int src = 0;
+    const u32 lt = (1u << lane) - 1u;
+    u32* mywh = whist + warp * 256;
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        for (int j = tid; j < BS_WARPS * 256; j += BS_THREADS) whist[j] = 0;
+        __syncthreads();
+        K key[ITEMS];
+        u32 val[ITEMS], rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            int idx = warp * (ITEMS * 32) + i * 32 + lane;
+            key[i] = kbuf[src][idx];
+            val[i] = vbuf[src][idx];
+            u32 d = (u32)((key[i] >> shift) & 0xff);
+            u32 peers = __match_any_sync(0xffffffffu, d);
+            u32 pre = mywh[d];
+            rank[i] = pre + __popc(peers & lt);
+            __syncwarp();
+            if ((peers & lt) == 0) mywh[d] = pre + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        u32 run = 0, x = 0;
+        if (tid < 256) {
+            for (int k = 0; k < BS_WARPS; k++) {
+                u32 c = whist[k * 256 + tid];
+                whist[k * 256 + tid] = run;
+                run += c;
+            }
+            x = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_wsum[warp] = x;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            u32 wbase = 0;
+            for (int k = 0; k < warp; k++) wbase += s_wsum[k];
+            dstart[tid] = wbase + x - run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            u32 d = (u32)((key[i] >> shift) & 0xff);
+            u32 pos = dstart[d] + mywh[d] + rank[i];
+            kbuf[src ^ 1][pos] = key[i];
+            vbuf[src ^ 1][pos] = val[i];
+        }
+        __syncthreads();
+        src ^= 1;
+    }
+    for (u32 j = tid; j < n; j += BS_THREADS) {
+        kout[j] = kbuf[src][j];
+        vout[j] = vbuf[src][j];
+    }
+}
+
 template <typename K>
 constexpr size_t onesweep_smem() {
     return (size_t)SORT_TILE * (sizeof(K) + 4) + (SORT_WARPS * 256 + 512) * 4;
@@ -179,6 +265,19 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
     if (passes > 8 || n >= (size_t)STATUS_MASK) {
         OBVHS_SET_ERR(ctx, "radix sort: unsupported size n=%zu passes=%d", n, passes);
         return OBVHS_ERR_UNSUPPORTED;
+    }
+    if (n <= (size_t)BlockSortCfg<K>::MAX_N) {  // one launch, no scratch
+        static bool bs_attr[2] = {false, false};
+        const int w = sizeof(K) == 8 ? 1 : 0;
+        if (!bs_attr[w]) {
+            CU_TRY(ctx, cudaFuncSetAttribute(block_sort_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BlockSortCfg<K>::SMEM));
+            bs_attr[w] = true;
+        }
+        block_sort_kernel<K><<<1, BS_THREADS, BlockSortCfg<K>::SMEM, ctx->stream>>>(keys, vals, keys_alt, vals_alt, (u32)n, passes);
+        KERNEL_CHECK(ctx);
+        *sorted_keys = keys_alt;
+        *sorted_vals = vals_alt;
+        return OBVHS_OK;
     }
     const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
     // scratch: ghist[passes*256] goffs[passes*256] ticket[passes (padded to 8)] status[passes*tiles*256]
