@@ -526,10 +526,13 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
     DevBuf<ObvhsRay> st_rays;
     DevBuf<unsigned char> st_out;
     DevBuf<u64> st_cnt;
+    // Host rays are staged with one bulk DMA: letting the kernel read pinned host memory directly (zero-copy) measured
+    // 1.5x SLOWER on B200/PCIe (425 vs 630 Mrays/s on the kitchen), small PCIe reads being latency-bound.
     const ObvhsRay* d_rays = nullptr;
     ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
-    const bool out_dev = obvhs_is_device_ptr(out);
+    bool out_dev = obvhs_is_device_ptr(out);
     void* d_out = out;
+    bool out_mapped = false;
     if (!out_dev) {
         CU_TRY(ctx, st_out.alloc(n * out_elem, ctx->stream));
         d_out = st_out.p;
@@ -548,8 +551,8 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
     ST_TRY(cwbvh_traverse_device(ctx, bvh, d_rays, n, mode, d_out, d_cnt));
     if (counters && !cnt_dev) CU_TRY(ctx, cudaMemcpyAsync(counters, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (!out_dev) {
-        CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!out_mapped) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host-visible results: the call is synchronous like the reference's
     } else if (counters && !cnt_dev) {
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }

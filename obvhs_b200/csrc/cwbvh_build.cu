@@ -30,86 +30,49 @@ constexpr u32 INVALID32 = 0xffffffffu;
 
 // Decision (bvh2_to_cwbvh.rs:470-484), 7 per BVH2 node: cost[i] and meta[i] = kind | left << 2 | right << 5
 // (left/right = 7 encodes the reference's INVALID 0xff).
-struct Dec {
+// S[i] = number of CWBVH nodes created BELOW this node when it is expanded with decision i, i.e. the sum over the
+// children get_children(node, i) collects of (1 + S[0] of the child) for the INTERNAL ones. It turns the reference's
+// running node allocator into a bottom-up quantity that only needs the two children's records. 64 bytes = 4 x 16-B vectors.
+struct __align__(16) Dec {
     float cost[7];
-    u32 meta_lo, meta_hi;
+    u32 meta_lo;
+    u32 meta_hi;
+    u32 S[7];
 };
-static_assert(sizeof(Dec) == 36, "Dec");
+static_assert(sizeof(Dec) == 64, "Dec");
 
-__device__ __forceinline__ u32 dec_meta(const Dec* __restrict__ dec, u32 node, u32 i) {
-    const u8* m = reinterpret_cast<const u8*>(&dec[node].meta_lo);
-    return __ldcg(m + i);
+__device__ __forceinline__ Dec load_dec_cg(const Dec* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+    Dec r;
+    r.cost[0] = __uint_as_float(a.x); r.cost[1] = __uint_as_float(a.y); r.cost[2] = __uint_as_float(a.z); r.cost[3] = __uint_as_float(a.w);
+    r.cost[4] = __uint_as_float(b.x); r.cost[5] = __uint_as_float(b.y); r.cost[6] = __uint_as_float(b.z); r.meta_lo = b.w;
+    r.meta_hi = c.x; r.S[0] = c.y; r.S[1] = c.z; r.S[2] = c.w;
+    r.S[3] = d.x; r.S[4] = d.y; r.S[5] = d.z; r.S[6] = d.w;
+    return r;
 }
+__device__ __forceinline__ void store_dec(Dec* p, const Dec& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(__float_as_uint(r.cost[0]), __float_as_uint(r.cost[1]), __float_as_uint(r.cost[2]), __float_as_uint(r.cost[3]));
+    q[1] = make_uint4(__float_as_uint(r.cost[4]), __float_as_uint(r.cost[5]), __float_as_uint(r.cost[6]), r.meta_lo);
+    q[2] = make_uint4(r.meta_hi, r.S[0], r.S[1], r.S[2]);
+    q[3] = make_uint4(r.S[3], r.S[4], r.S[5], r.S[6]);
+}
+__device__ __forceinline__ u32 dec_meta_of(const Dec& d, u32 i) { return ((i < 4 ? d.meta_lo >> (8 * i) : d.meta_hi >> (8 * (i - 4)))) & 0xffu; }
 
 struct CwGlobals {
     u32 error;           // 1: DISTRIBUTE/INVALID decision on the emit path (non-finite costs), 2: child left unassigned, 3: count mismatch
     u32 queue_count[3];  // wide nodes queued by level L for level L+1, in slot L % 3
     u32 emitted;         // wide nodes written
     u32 levels;
+    unsigned long long level_ns[48];  // OBVHS_TRACE: globaltimer at the end of each level
+    u32 level_len[48];
 };
 
-// get_children (bvh2_to_cwbvh.rs:346-397), iterative. Returns child_count; children in the recursion's order.
-__device__ __forceinline__ u32 get_children(const Node32* __restrict__ nodes, const Dec* __restrict__ dec, u32 node_index, u32 children[8],
-                                            bool coherent, u32* err) {
-    u32 child_count = 0;
-    u32 n0_prim, n0_first;
-    {
-        Node32 nd = coherent ? load_node_cg(nodes + node_index) : load_node(nodes + node_index);
-        n0_prim = nd.prim_count;
-        n0_first = nd.first_index;
-    }
-    if (n0_prim != 0) {
-        children[0] = node_index;
-        return 1;
-    }
-    // stack entries: node (bits 0..27 are not enough for 2^30 nodes -> two arrays), decision index i, or a direct child
-    u32 st_node[8];
-    u8 st_i[8];  // 0..6 = expand with decision i; 0xff = emit as child
-    int sp = 0;
-    st_node[0] = node_index;
-    st_i[0] = 0;
-    sp = 1;
-    u32 first_of_root = n0_first;
-    while (sp > 0) {
-        sp--;
-        u32 node = st_node[sp];
-        u32 i = st_i[sp];
-        if (i == 0xff) {
-            if (child_count < 8) children[child_count] = node;
-            child_count++;
-            continue;
-        }
-        u32 first = (node == node_index) ? first_of_root : __ldcg(&nodes[node].first_index);
-        u32 m = dec_meta(dec, node, i);
-        u32 dl = (m >> 2) & 7u, dr = (m >> 5) & 7u;
-        if (dl == 7u || dr == 7u) {
-            *err = 1;
-            return 0;
-        }
-        bool left_dist = (dec_meta(dec, first, dl) & 3u) == KIND_DISTRIBUTE;
-        bool right_dist = (dec_meta(dec, first + 1, dr) & 3u) == KIND_DISTRIBUTE;
-        if (sp + 2 > 8) {
-            *err = 1;
-            return 0;
-        }
-        // right is handled after everything the left expands to
-        st_node[sp] = first + 1;
-        st_i[sp] = right_dist ? (u8)dr : (u8)0xff;
-        sp++;
-        st_node[sp] = first;
-        st_i[sp] = left_dist ? (u8)dl : (u8)0xff;
-        sp++;
-    }
-    if (child_count > 8) {
-        *err = 1;
-        return 0;
-    }
-    return child_count;
-}
-
-// K11: calculate_cost_impl (bvh2_to_cwbvh.rs:220-344), bottom-up.
+// K11: calculate_cost_impl (bvh2_to_cwbvh.rs:220-344), bottom-up: one thread per BVH2 leaf climbs, the second arriver at
+// an inner node computes its record from the two children's records only.
 __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ parents, u32 n_nodes,
-                                                         u32 max_prims_per_leaf, Dec* dec, u32* P, u32* K, u32* arrivals, CwGlobals* g) {
+                                                         u32 max_prims_per_leaf, Dec* dec, u32* P, u32* arrivals) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     Node32 nd = load_node(nodes + i);
@@ -119,12 +82,14 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
         float cost_leaf = ha * (float)nd.prim_count * PRIM_COST;
         Dec d;
 #pragma unroll
-        for (int k = 0; k < 7; k++) d.cost[k] = cost_leaf;
+        for (int k = 0; k < 7; k++) {
+            d.cost[k] = cost_leaf;
+            d.S[k] = 0;
+        }
         d.meta_lo = 0;  // kind LEAF, left/right 0 (Decision::default indices)
         d.meta_hi = 0;
-        dec[i] = d;
+        store_dec(dec + i, d);
         P[i] = nd.prim_count;
-        K[i] = 1;
     }
     if (i == 0) return;
     u32 node = parents[i];
@@ -134,22 +99,17 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
         Node32 me = load_node_cg(nodes + node);
         const u32 first = me.first_index;
         float ha = box_half_area(node_box(me));
-        float lc[7], rc[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            lc[k] = __ldcg(&dec[first].cost[k]);
-            rc[k] = __ldcg(&dec[first + 1].cost[k]);
-        }
+        const Dec L = load_dec_cg(dec + first), R = load_dec_cg(dec + first + 1);
         u32 num_primitives = __ldcg(&P[first]) + __ldcg(&P[first + 1]);
         Dec d;
-        u8 meta[8];
+        u32 meta[7];
         {  // i = 0
             float cost_leaf = num_primitives <= max_prims_per_leaf ? ((float)num_primitives * ha) * PRIM_COST : __int_as_float(0x7f800000);
             float cost_distribute = __int_as_float(0x7f800000);
             u32 dl = 7, dr = 7;
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                float c = lc[k] + rc[6 - k];
+                float c = L.cost[k] + R.cost[6 - k];
                 if (c < cost_distribute) {
                     cost_distribute = c;
                     dl = k;
@@ -159,10 +119,10 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
             float cost_internal = cost_distribute + ha;
             if (cost_leaf < cost_internal) {
                 d.cost[0] = cost_leaf;
-                meta[0] = (u8)(KIND_LEAF | dl << 2 | dr << 5);
+                meta[0] = KIND_LEAF | dl << 2 | dr << 5;
             } else {
                 d.cost[0] = cost_internal;
-                meta[0] = (u8)(KIND_INTERNAL | dl << 2 | dr << 5);
+                meta[0] = KIND_INTERNAL | dl << 2 | dr << 5;
             }
         }
 #pragma unroll
@@ -171,7 +131,7 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
             u32 dl = 7, dr = 7;
 #pragma unroll
             for (int k = 0; k < ii; k++) {
-                float c = lc[k] + rc[ii - k - 1];
+                float c = L.cost[k] + R.cost[ii - k - 1];
                 if (c < cost_distribute) {
                     cost_distribute = c;
                     dl = k;
@@ -179,193 +139,326 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
                 }
             }
             d.cost[ii] = cost_distribute;
-            if (dl != 7) meta[ii] = (u8)(KIND_DISTRIBUTE | dl << 2 | dr << 5);
+            if (dl != 7) meta[ii] = KIND_DISTRIBUTE | dl << 2 | dr << 5;
             else meta[ii] = meta[ii - 1];  // decisions[node_i] = decisions[node_i - 1]
         }
-        meta[7] = 0;
-        d.meta_lo = meta[0] | meta[1] << 8 | meta[2] << 16 | (u32)meta[3] << 24;
-        d.meta_hi = meta[4] | meta[5] << 8 | meta[6] << 16;
-        dec[node] = d;
-        P[node] = num_primitives;
-        __threadfence();  // get_children below reads this node's own decisions through L2
-        // K(node): CWBVH nodes produced by this subtree when `node` is emitted as a wide node
-        u32 children[8];
-        u32 err = 0;
-        u32 cc = get_children(nodes, dec, node, children, true, &err);
-        u32 k_total = 1;
-        for (u32 c = 0; c < cc && c < 8; c++) {
-            u32 ch = children[c];
-            if ((dec_meta(dec, ch, 0) & 3u) == KIND_INTERNAL) k_total += __ldcg(&K[ch]);
+        // what a wide-node child contributes when it is collected as a child (not expanded): itself + everything below
+        const u32 wideL = (dec_meta_of(L, 0) & 3u) == KIND_INTERNAL ? 1u + L.S[0] : 0u;
+        const u32 wideR = (dec_meta_of(R, 0) & 3u) == KIND_INTERNAL ? 1u + R.S[0] : 0u;
+#pragma unroll
+        for (int ii = 0; ii < 7; ii++) {
+            u32 dl = (meta[ii] >> 2) & 7u, dr = (meta[ii] >> 5) & 7u;
+            u32 sv = 0;
+            if (dl != 7u && dr != 7u) {  // get_children (bvh2_to_cwbvh.rs:346-397): expand a DISTRIBUTE child, else collect it
+                sv += (dec_meta_of(L, dl) & 3u) == KIND_DISTRIBUTE ? L.S[dl] : wideL;
+                sv += (dec_meta_of(R, dr) & 3u) == KIND_DISTRIBUTE ? R.S[dr] : wideR;
+            }
+            d.S[ii] = sv;
         }
-        // an INVALID decision only matters if this node is really emitted; the emit kernel reports it
-        K[node] = k_total;
+        d.meta_lo = meta[0] | meta[1] << 8 | meta[2] << 16 | meta[3] << 24;
+        d.meta_hi = meta[4] | meta[5] << 8 | meta[6] << 16;
+        store_dec(dec + node, d);
+        P[node] = num_primitives;
         if (node == 0) return;
         node = parents[node];
     }
 }
 
-struct WorkItem {
-    u32 bvh2_node, child_base, prim_base;
+// What a group lane knows about one BVH2 node while get_children runs: everything comes from ONE round trip
+// (node, both meta words and S[0] of its decision record, subtree primitive count).
+struct Entry {
+    u32 node;     // BVH2 node index, INVALID32 = empty
+    u32 idx;      // decision index to expand with (meaningful when expand != 0)
+    u32 expand;   // 1: still a DISTRIBUTE entry, to be replaced by its two children
+    u32 meta_lo, meta_hi, S0, P;
+    Node32 n;
 };
+__device__ __forceinline__ u32 entry_meta(const Entry& e, u32 i) { return ((i < 4 ? e.meta_lo >> (8 * i) : e.meta_hi >> (8 * (i - 4)))) & 0xffu; }
+__device__ __forceinline__ void entry_load(Entry& e, const Node32* __restrict__ nodes, const Dec* __restrict__ dec, const u32* __restrict__ P) {
+    const uint4* dq = reinterpret_cast<const uint4*>(dec + e.node);
+    e.n = load_node(nodes + e.node);
+    uint4 q1 = __ldcg(dq + 1), q2 = __ldcg(dq + 2);
+    e.meta_lo = q1.w;
+    e.meta_hi = q2.x;
+    e.S0 = q2.y;
+    e.P = __ldcg(P + e.node);
+}
 
-// K12: convert_to_cwbvh_impl (bvh2_to_cwbvh.rs:75-193) for one wide node (CWBVH index x).
+// K12: convert_to_cwbvh_impl (bvh2_to_cwbvh.rs:75-193) for one wide node, executed by a GROUP OF 8 LANES (four nodes per
+// warp). Lane c ends up owning child c: its box, kind, quantised bytes, primitives and work item. The whole routine is a
+// chain of dependent memory round trips, so it is organised to make that chain short and identical for the four groups
+// of a warp (loops are warp-uniform, every round is one trip):
+//   get_children (bvh2_to_cwbvh.rs:346-397) is run breadth-wise: in every round all DISTRIBUTE entries of the group are
+//   replaced by their two children at once, positions by an 8-lane prefix sum (keeps the recursion's left-to-right order);
+//   order_children (:402-467) is an 8-lane arg-min per round; slot-ordered prefix sums give the allocator offsets.
+// `gmask` = lanes of the group, `gl` = lane in group, `sbuf` = 80 bytes of shared memory of the group.
+struct GroupOut {
+    u32 x;  // CWBVH node index being written
+};
 __device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __restrict__ bvh2_prims, const Dec* __restrict__ dec,
-                               const u32* __restrict__ P, const u32* __restrict__ K, u32 x, u32* __restrict__ next_queue, u32* queue_counter,
-                               WorkItem* work, uint4* __restrict__ out_nodes, u32* __restrict__ out_prims, int order_children, CwGlobals* g) {
-    WorkItem w;
-    w.bvh2_node = __ldcg(&work[x].bvh2_node);
-    w.child_base = __ldcg(&work[x].child_base);
-    w.prim_base = __ldcg(&work[x].prim_base);
-    const Node32 me = load_node(nodes + w.bvh2_node);
-    const Box aabb = node_box(me);
-    // node.p, node.e (bvh2_to_cwbvh.rs:82-99)
-    float px = aabb.minx, py = aabb.miny, pz = aabb.minz;
-    float rcpx, rcpy, rcpz;
-    u32 ex = obvhs_cwbvh_exponent(smax(aabb.maxx - aabb.minx, 1e-20f) * DENOM, &rcpx);
-    u32 ey = obvhs_cwbvh_exponent(smax(aabb.maxy - aabb.miny, 1e-20f) * DENOM, &rcpy);
-    u32 ez = obvhs_cwbvh_exponent(smax(aabb.maxz - aabb.minz, 1e-20f) * DENOM, &rcpz);
-    u32 children[8];
-    u32 err = 0;
-    u32 child_count = get_children(nodes, dec, w.bvh2_node, children, false, &err);
-    if (err) {
-        g->error = 1;
-        return;
+                               const u32* __restrict__ P, bool have, uint4 item, u32* __restrict__ next_queue_idx, uint4* __restrict__ next_queue,
+                               u32* queue_counter, uint4* __restrict__ out_nodes, u32* __restrict__ out_prims, int order_children, CwGlobals* g,
+                               u32 gmask, int gl, u32* sbuf) {
+    const int lane = threadIdx.x & 31, gbase = lane & ~7;
+    const u32 x = item.x, child_base = item.z, prim_base = item.w;
+    // ---- get_children, breadth-wise ------------------------------------------------------------------------------
+    Entry e;
+    e.node = INVALID32;
+    e.idx = 0;
+    e.expand = 0;
+    e.meta_lo = e.meta_hi = e.S0 = e.P = 0;
+    e.n = Node32{0, 0, 0, 0, 0, 0, 0, 0};
+    if (have && gl == 0) {
+        e.node = item.y;
+        entry_load(e, nodes, dec, P);
+        e.expand = e.n.prim_count == 0 ? 1u : 0u;  // a leaf root is its own single child
     }
-    for (u32 c = child_count; c < 8; c++) children[c] = INVALID32;
-    Box cbox[8];  // boxes of the children, indexed like children[] (get_children order)
-    for (u32 c = 0; c < child_count; c++) cbox[c] = node_box(load_node(nodes + children[c]));
-    // slot_of[c]: slot of child c. order_children (bvh2_to_cwbvh.rs:402-467), greedy assignment
-    int slot_child[8];  // slot -> child position in children[] or -1
-#pragma unroll
-    for (int s = 0; s < 8; s++) slot_child[s] = -1;
-    if (order_children) {
-        float cx = (aabb.maxx + aabb.minx) * 0.5f, cy = (aabb.maxy + aabb.miny) * 0.5f, cz = (aabb.maxz + aabb.minz) * 0.5f;
-        float vx[8], vy[8], vz[8];
-        for (u32 c = 0; c < child_count; c++) {
-            vx[c] = (cbox[c].maxx + cbox[c].minx) * 0.5f - cx;
-            vy[c] = (cbox[c].maxy + cbox[c].miny) * 0.5f - cy;
-            vz[c] = (cbox[c].maxz + cbox[c].minz) * 0.5f - cz;
+    // the wide node's own box (lane 0 holds the BVH2 node) and exponents: lanes 0..2 take one axis each
+    Box aabb;
+    aabb.minx = __shfl_sync(0xffffffffu, e.n.minx, gbase); aabb.miny = __shfl_sync(0xffffffffu, e.n.miny, gbase);
+    aabb.minz = __shfl_sync(0xffffffffu, e.n.minz, gbase); aabb.maxx = __shfl_sync(0xffffffffu, e.n.maxx, gbase);
+    aabb.maxy = __shfl_sync(0xffffffffu, e.n.maxy, gbase); aabb.maxz = __shfl_sync(0xffffffffu, e.n.maxz, gbase);
+    u32 err = 0;
+    // staging for the in-group re-arrangement: 8 entries x 14 words {node, idx | flags, meta_lo, meta_hi, S0, P, node[8]}
+    constexpr u32 FRESH = 0x100u;
+    for (int round = 0; round < 8; round++) {
+        if (!__ballot_sync(0xffffffffu, e.expand)) break;  // warp-uniform: the four groups of the warp stay in step
+        u32 dl = 0, dr = 0;
+        if (e.expand) {
+            u32 m = entry_meta(e, e.idx);
+            dl = (m >> 2) & 7u;
+            dr = (m >> 5) & 7u;
+            if (dl == 7u || dr == 7u) err = 1;  // INVALID decision (non-finite costs): the reference indexes out of bounds
         }
-        u32 assigned = 0, filled = 0;  // bit masks over children / slots
-        for (;;) {
-            float min_cost = 3.40282347e+38f;
-            int min_slot = -1, min_index = -1;
-            for (u32 c = 0; c < child_count; c++) {
-                if (assigned & (1u << c)) continue;
+        const u32 sz = e.node == INVALID32 ? 0u : (e.expand ? 2u : 1u);
+        u32 off = sz;
 #pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    // direction_lut (bvh2_to_cwbvh.rs:40-50): bit 2 -> -x, bit 1 -> -y, bit 0 -> -z; dot = (x + y) + z
-                    float dx = (s & 4) ? -1.0f : 1.0f, dy = (s & 2) ? -1.0f : 1.0f, dz = (s & 1) ? -1.0f : 1.0f;
-                    float cost = (dx * vx[c] + dy * vy[c]) + dz * vz[c];
-                    if (!(filled & (1u << s)) && cost < min_cost) {
-                        min_cost = cost;
-                        min_slot = s;
-                        min_index = (int)c;
+        for (int o = 1; o < 8; o <<= 1) {
+            u32 y = __shfl_up_sync(0xffffffffu, off, o, 8);
+            if (gl >= o) off += y;
+        }
+        const u32 total = __shfl_sync(0xffffffffu, off, gbase + 7);
+        off -= sz;
+        if (total > 8) err = 1;
+        __syncwarp();
+        if (total <= 8) {
+            if (sz == 2) {  // replaced by its two children, left first (the recursion's order)
+                sbuf[off * 14] = e.n.first_index;
+                sbuf[off * 14 + 1] = dl | FRESH;
+                sbuf[off * 14 + 14] = e.n.first_index + 1;
+                sbuf[off * 14 + 15] = dr | FRESH;
+            } else if (sz == 1) {  // a settled child only moves
+                u32* d = sbuf + off * 14;
+                d[0] = e.node; d[1] = e.idx; d[2] = e.meta_lo; d[3] = e.meta_hi; d[4] = e.S0; d[5] = e.P;
+                d[6] = __float_as_uint(e.n.minx); d[7] = __float_as_uint(e.n.miny); d[8] = __float_as_uint(e.n.minz); d[9] = e.n.prim_count;
+                d[10] = __float_as_uint(e.n.maxx); d[11] = __float_as_uint(e.n.maxy); d[12] = __float_as_uint(e.n.maxz); d[13] = e.n.first_index;
+            }
+        }
+        __syncwarp();
+        e.node = INVALID32;
+        e.expand = 0;
+        if ((u32)gl < total && total <= 8) {
+            const u32* d = sbuf + gl * 14;
+            e.node = d[0];
+            e.idx = d[1] & 0xffu;
+            if (d[1] & FRESH) {
+                entry_load(e, nodes, dec, P);  // ONE trip: node, decision record, primitive count
+                e.expand = (entry_meta(e, e.idx) & 3u) == KIND_DISTRIBUTE ? 1u : 0u;
+            } else {
+                e.meta_lo = d[2]; e.meta_hi = d[3]; e.S0 = d[4]; e.P = d[5];
+                e.n.minx = __uint_as_float(d[6]); e.n.miny = __uint_as_float(d[7]); e.n.minz = __uint_as_float(d[8]); e.n.prim_count = d[9];
+                e.n.maxx = __uint_as_float(d[10]); e.n.maxy = __uint_as_float(d[11]); e.n.maxz = __uint_as_float(d[12]); e.n.first_index = d[13];
+            }
+        }
+        __syncwarp();
+    }
+    if (__ballot_sync(0xffffffffu, e.expand) & gmask) err = 1;  // did not settle in 8 rounds
+    if (__ballot_sync(0xffffffffu, err != 0) & gmask) {
+        if (gl == 0 && have) g->error = 1;
+        have = false;
+    }
+    const bool active = have && e.node != INVALID32;
+    const u32 child = e.node;
+    const Box cb = node_box(e.n);
+    const u32 kind = active ? (e.meta_lo & 3u) : 3u;  // decisions[child * 7].kind
+    const u32 child_count = __popc(__ballot_sync(0xffffffffu, active) & gmask);
+    // node.e (bvh2_to_cwbvh.rs:82-99)
+    const float pmin = gl == 0 ? aabb.minx : gl == 1 ? aabb.miny : aabb.minz;
+    const float pmax = gl == 0 ? aabb.maxx : gl == 1 ? aabb.maxy : aabb.maxz;
+    float rcp_mine = 0.f;
+    u32 e_mine = gl < 3 ? obvhs_cwbvh_exponent(smax(pmax - pmin, 1e-20f) * DENOM, &rcp_mine) : 0u;
+    const u32 ex = __shfl_sync(0xffffffffu, e_mine, gbase + 0), ey = __shfl_sync(0xffffffffu, e_mine, gbase + 1),
+              ez = __shfl_sync(0xffffffffu, e_mine, gbase + 2);
+    const float rcpx = __shfl_sync(0xffffffffu, rcp_mine, gbase + 0), rcpy = __shfl_sync(0xffffffffu, rcp_mine, gbase + 1),
+                rcpz = __shfl_sync(0xffffffffu, rcp_mine, gbase + 2);
+    // ---- order_children (bvh2_to_cwbvh.rs:402-467): greedy, globally cheapest (child, slot) first, ties to the first in
+    // (child, slot) scan order, costs that are not < f32::MAX never assigned
+    int my_slot = -1;
+    if (order_children) {
+        float cost[8];
+        {
+            float cx = (aabb.maxx + aabb.minx) * 0.5f, cy = (aabb.maxy + aabb.miny) * 0.5f, cz = (aabb.maxz + aabb.minz) * 0.5f;
+            float vx = (cb.maxx + cb.minx) * 0.5f - cx, vy = (cb.maxy + cb.miny) * 0.5f - cy, vz = (cb.maxz + cb.minz) * 0.5f - cz;
+#pragma unroll
+            for (int sl = 0; sl < 8; sl++) {
+                // direction_lut (bvh2_to_cwbvh.rs:40-50): bit 2 -> -x, bit 1 -> -y, bit 0 -> -z; dot = (x + y) + z
+                float dx = (sl & 4) ? -1.0f : 1.0f, dy = (sl & 2) ? -1.0f : 1.0f, dz = (sl & 1) ? -1.0f : 1.0f;
+                cost[sl] = (dx * vx + dy * vy) + dz * vz;
+            }
+        }
+        u32 filled = 0;
+#pragma unroll 1
+        for (int round = 0; round < 8; round++) {
+            float best_cost = 3.40282347e+38f;
+            int best_s = -1;
+            if (active && my_slot < 0) {
+#pragma unroll
+                for (int sl = 0; sl < 8; sl++) {
+                    if (!(filled & (1u << sl)) && cost[sl] < best_cost) {
+                        best_cost = cost[sl];
+                        best_s = sl;
                     }
                 }
             }
-            if (min_slot < 0) break;
-            filled |= 1u << min_slot;
-            assigned |= 1u << min_index;
-            slot_child[min_slot] = min_index;
-        }
-        if (assigned != ((1u << child_count) - 1u)) {  // the reference indexes out of bounds (panics) here
-            g->error = 2;
-            return;
-        }
-    } else {
-        for (u32 c = 0; c < child_count; c++) slot_child[c] = (int)c;
-    }
-    // pass 1 over the slots: kinds, direct primitives, internal child bookkeeping
-    u32 imask = 0, num_internal = 0, num_primitives = 0;
-    u32 meta_b[8], qlo[3][8], qhi[3][8];
-    u32 kind_of[8];
+            // group arg-min over (cost, lane); lanes without a candidate never win
+            float wc = best_cost;
+            int wl = best_s >= 0 ? gl : 99, ws = best_s;
 #pragma unroll
-    for (int s = 0; s < 8; s++) {
-        meta_b[s] = 0;
-        qlo[0][s] = qlo[1][s] = qlo[2][s] = 0;
-        qhi[0][s] = qhi[1][s] = qhi[2][s] = 0;
-        kind_of[s] = 3;
-        int c = slot_child[s];
-        if (c < 0) continue;
-        const Box cb = cbox[c];
-        // bvh2_to_cwbvh.rs:128-141: floor/ceil, clamp 0..255 (glam clamp = max then min, SSE operand rule), `as u8`
-        float lo[3] = {floorf((cb.minx - px) * rcpx), floorf((cb.miny - py) * rcpy), floorf((cb.minz - pz) * rcpz)};
-        float hi[3] = {ceilf((cb.maxx - px) * rcpx), ceilf((cb.maxy - py) * rcpy), ceilf((cb.maxz - pz) * rcpz)};
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            float l = smin(smax(lo[a], 0.0f), 255.0f), h = smin(smax(hi[a], 0.0f), 255.0f);
-            qlo[a][s] = (u32)l;  // values are integers in [0,255] (NaN -> 0 by smax)
-            qhi[a][s] = (u32)h;
-        }
-        u32 child = children[c];
-        u32 kind = dec_meta(dec, child, 0) & 3u;
-        kind_of[s] = kind;
-        if (kind == KIND_LEAF) {
-            // count_primitives (bvh2_to_cwbvh.rs:197-211): DFS, left first, pushes primitive ids
-            u32 pc = 0;
-            u32 stk[8];
-            int sp = 0;
-            stk[sp++] = child;
-            while (sp > 0) {
-                u32 nidx = stk[--sp];
-                Node32 nn = load_node(nodes + nidx);
-                if (nn.prim_count != 0) {
-                    if (pc < 3) out_prims[w.prim_base + num_primitives + pc] = bvh2_prims[nn.first_index];
-                    pc += nn.prim_count;
-                } else if (sp + 2 <= 8) {
-                    stk[sp++] = nn.first_index + 1;
-                    stk[sp++] = nn.first_index;
-                } else {
-                    pc = 99;
-                    break;
+            for (int o = 1; o < 8; o <<= 1) {
+                float oc = __shfl_xor_sync(0xffffffffu, wc, o);
+                int ol = __shfl_xor_sync(0xffffffffu, wl, o), os = __shfl_xor_sync(0xffffffffu, ws, o);
+                bool take = (ol != 99) && (wl == 99 || oc < wc || (oc == wc && ol < wl));
+                if (take) {
+                    wc = oc;
+                    wl = ol;
+                    ws = os;
                 }
             }
-            u32 unary = pc == 1 ? 0x20u : pc == 2 ? 0x60u : pc == 3 ? 0xe0u : 0u;
-            if (!unary) {
-                g->error = 1;
-                return;
+            if (!__ballot_sync(0xffffffffu, wl != 99)) break;  // warp-uniform exit
+            if (wl != 99) {
+                filled |= 1u << ws;
+                if (wl == gl) my_slot = ws;
             }
-            meta_b[s] = (num_primitives & 0xffu) | unary;
-            num_primitives += pc;
-        } else if (kind == KIND_INTERNAL) {
-            imask |= 1u << s;
-            meta_b[s] = (24u + (u32)s) | 0x20u;
-            num_internal++;
+        }
+    } else if (active) {
+        my_slot = gl;
+    }
+    if (__ballot_sync(0xffffffffu, active && my_slot < 0) & gmask) {  // the reference indexes out of bounds (panics) here
+        if (gl == 0) g->error = 2;
+        have = false;
+    }
+    // ---- LEAF children: count_primitives (bvh2_to_cwbvh.rs:197-211): DFS, left first; at most 3 primitives, 5 nodes
+    u32 pc = 0, prim_ids[3] = {0, 0, 0};
+    bool bad = false;
+    const bool is_leaf_kind = have && active && kind == KIND_LEAF;
+    if (is_leaf_kind) {
+        pc = e.P;
+        if (pc < 1 || pc > 3) {
+            bad = true;
+        } else if (e.n.prim_count != 0) {
+            prim_ids[0] = bvh2_prims[e.n.first_index];
         } else {
-            g->error = 1;
-            return;
+            Node32 l = load_node(nodes + e.n.first_index), r = load_node(nodes + e.n.first_index + 1);
+            u32 k = 0;
+            if (l.prim_count != 0) {
+                prim_ids[k++] = bvh2_prims[l.first_index];
+            } else {
+                Node32 ll = load_node(nodes + l.first_index), lr = load_node(nodes + l.first_index + 1);
+                bad |= ll.prim_count == 0 || lr.prim_count == 0;
+                prim_ids[k++] = bvh2_prims[ll.first_index];
+                prim_ids[k++] = bvh2_prims[lr.first_index];
+            }
+            if (!bad && r.prim_count != 0) {
+                if (k < 3) prim_ids[k++] = bvh2_prims[r.first_index];
+                else bad = true;
+            } else if (!bad) {
+                Node32 rl = load_node(nodes + r.first_index), rr = load_node(nodes + r.first_index + 1);
+                bad |= rl.prim_count == 0 || rr.prim_count == 0 || k != 1;
+                if (!bad) {
+                    prim_ids[k++] = bvh2_prims[rl.first_index];
+                    prim_ids[k++] = bvh2_prims[rr.first_index];
+                }
+            }
+            bad |= k != pc;
         }
+    } else if (have && active && kind != KIND_INTERNAL) {
+        bad = true;  // DISTRIBUTE is unreachable here in the reference
     }
-    // pass 2: work items of the internal children
-    if (num_internal) {
-        u32 qbase = atomicAdd(queue_counter, num_internal);
-        u32 j = 0, k_before = 0, p_before = 0;
+    if (__ballot_sync(0xffffffffu, bad) & gmask) {
+        if (gl == 0) g->error = 1;
+        have = false;
+    }
+    const bool internal = have && active && kind == KIND_INTERNAL;
+    // ---- prefix sums in SLOT order over the group (the recursion visits slots 0..7)
+    u32 prims_before = 0, int_before = 0, k_before = 0, p_before = 0, num_internal = 0, num_primitives = 0, imask = 0;
 #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            if (kind_of[s] != KIND_INTERNAL) continue;
-            u32 child = children[slot_child[s]];
-            WorkItem wi;
-            wi.bvh2_node = child;
-            wi.child_base = w.child_base + num_internal + k_before;
-            wi.prim_base = w.prim_base + num_primitives + p_before;
-            u32 ci = w.child_base + j;
-            work[ci] = wi;
-            next_queue[qbase + j] = ci;
-            k_before += K[child] - 1;
-            p_before += P[child];
-            j++;
+    for (int c = 0; c < 8; c++) {
+        int os = __shfl_sync(0xffffffffu, my_slot, gbase + c);
+        u32 opc = __shfl_sync(0xffffffffu, pc, gbase + c);
+        u32 oint = __shfl_sync(0xffffffffu, internal ? 1u : 0u, gbase + c);
+        u32 oS = __shfl_sync(0xffffffffu, e.S0, gbase + c), oP = __shfl_sync(0xffffffffu, e.P, gbase + c);
+        if (os < 0) continue;
+        num_primitives += opc;
+        num_internal += oint;
+        if (oint) imask |= 1u << os;
+        if (os < my_slot) {
+            prims_before += opc;
+            int_before += oint;
+            if (oint) {
+                k_before += oS;
+                p_before += oP;
+            }
         }
     }
-    // the 80 bytes (cwbvh/node.rs:14-54)
-    auto pack4 = [](const u32* b) { return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24; };
-    uint4 q0 = make_uint4(__float_as_uint(px), __float_as_uint(py), __float_as_uint(pz), ex | ey << 8 | ez << 16 | imask << 24);
-    uint4 q1 = make_uint4(w.child_base, w.prim_base, pack4(meta_b), pack4(meta_b + 4));
-    uint4 q2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
-    uint4 q3 = make_uint4(pack4(qlo[1]), pack4(qlo[1] + 4), pack4(qhi[1]), pack4(qhi[1] + 4));
-    uint4 q4 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
-    uint4* o = out_nodes + (size_t)x * 5;
-    o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3; o[4] = q4;
+    // ---- the group's 80-byte image of the node in shared memory
+    __syncwarp();
+    for (int k = gl; k < 20; k += 8) sbuf[k] = 0;
+    __syncwarp();
+    u8* sb = reinterpret_cast<u8*>(sbuf);
+    if (have && gl == 0) {
+        sbuf[0] = __float_as_uint(aabb.minx);
+        sbuf[1] = __float_as_uint(aabb.miny);
+        sbuf[2] = __float_as_uint(aabb.minz);
+        sbuf[3] = ex | ey << 8 | ez << 16 | imask << 24;
+        sbuf[4] = child_base;
+        sbuf[5] = prim_base;
+    }
+    if (have && active) {
+        // bvh2_to_cwbvh.rs:128-141: floor/ceil, clamp 0..255 (glam clamp = max then min, SSE operand rule), `as u8`
+        float lo0 = floorf((cb.minx - aabb.minx) * rcpx), lo1 = floorf((cb.miny - aabb.miny) * rcpy), lo2 = floorf((cb.minz - aabb.minz) * rcpz);
+        float hi0 = ceilf((cb.maxx - aabb.minx) * rcpx), hi1 = ceilf((cb.maxy - aabb.miny) * rcpy), hi2 = ceilf((cb.maxz - aabb.minz) * rcpz);
+        sb[32 + my_slot] = (u8)(u32)smin(smax(lo0, 0.0f), 255.0f);
+        sb[40 + my_slot] = (u8)(u32)smin(smax(hi0, 0.0f), 255.0f);
+        sb[48 + my_slot] = (u8)(u32)smin(smax(lo1, 0.0f), 255.0f);
+        sb[56 + my_slot] = (u8)(u32)smin(smax(hi1, 0.0f), 255.0f);
+        sb[64 + my_slot] = (u8)(u32)smin(smax(lo2, 0.0f), 255.0f);
+        sb[72 + my_slot] = (u8)(u32)smin(smax(hi2, 0.0f), 255.0f);
+        if (internal) {
+            sb[24 + my_slot] = (u8)((24u + (u32)my_slot) | 0x20u);
+        } else {
+            u32 unary = pc == 1 ? 0x20u : pc == 2 ? 0x60u : 0xe0u;
+            sb[24 + my_slot] = (u8)((prims_before & 0xffu) | unary);
+            for (u32 k = 0; k < pc; k++) out_prims[prim_base + prims_before + k] = prim_ids[k];
+        }
+    }
+    // ---- work items of the INTERNAL children; one queue reservation per group
+    u32 qbase = 0;
+    if (have && gl == 0 && num_internal) qbase = atomicAdd(queue_counter, num_internal);
+    qbase = __shfl_sync(0xffffffffu, qbase, gbase);
+    if (internal) {
+        // child_base(c_j) = child_base(N) + k(N) + sum over earlier INTERNAL slots of (K - 1) = S[0]; prim_base likewise with P
+        next_queue[qbase + int_before] =
+            make_uint4(child_base + int_before, child, child_base + num_internal + k_before, prim_base + num_primitives + p_before);
+    }
+    __syncwarp();
+    if (have && gl < 5) {
+        const uint4* src = reinterpret_cast<const uint4*>(sbuf);
+        out_nodes[(size_t)x * 5 + gl] = src[gl];
+    }
+    __syncwarp();
+    (void)next_queue_idx;
+    (void)child_count;
+    (void)lane;
 }
 
 struct EmitArgs {
@@ -373,39 +466,54 @@ struct EmitArgs {
     const u32* bvh2_prims;
     const Dec* dec;
     const u32* P;
-    const u32* K;
-    u32* queue_a;
-    u32* queue_b;
-    WorkItem* work;
+    uint4* queue_a;  // work items {cwbvh node index, bvh2 node, child_base, prim_base}
+    uint4* queue_b;
     uint4* out_nodes;
     u32* out_prims;
     int order_children;
-    u32 expected;  // M = K[root]
+    u32 expected;  // M = 1 + S(root, 0)
     CwGlobals* g;
 };
 
-// All CWBVH levels in ONE cooperative launch: level L's wide nodes are emitted by a grid-stride loop, their INTERNAL
-// children are queued for level L+1, a grid-wide barrier separates the levels. No host round trips.
-__global__ void __launch_bounds__(128) cwbvh_emit_all_kernel(EmitArgs a) {
+constexpr int EMIT_THREADS = 512;
+
+// All CWBVH levels in ONE cooperative launch: level L's wide nodes are emitted by 8-lane groups in a grid-stride loop,
+// their INTERNAL children are queued for level L+1, a grid-wide barrier separates the levels. No host round trips.
+__global__ void __launch_bounds__(EMIT_THREADS) cwbvh_emit_all_kernel(EmitArgs a) {
     cg::grid_group grid = cg::this_grid();
     const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const u32 warp_id = tid >> 5, nwarps = nthreads >> 5;
+    const int gl = threadIdx.x & 7, giw = (threadIdx.x & 31) >> 3;  // lane in group, group in warp
+    const u32 gmask = 0xffu << (giw * 8);
+    __shared__ __align__(16) u32 s_buf[(EMIT_THREADS / 8) * 112];
+    u32* sbuf = s_buf + (threadIdx.x >> 3) * 112;
     CwGlobals* g = a.g;
     if (tid == 0) {
-        a.work[0] = WorkItem{0u, 1u, 0u};  // convert_to_cwbvh_impl(0, 0): nodes = [default] -> child_base = 1
-        a.queue_a[0] = 0;
+        a.queue_a[0] = make_uint4(0u, 0u, 1u, 0u);  // convert_to_cwbvh_impl(0, 0): nodes = [default] -> child_base = 1
         g->queue_count[0] = g->queue_count[1] = g->queue_count[2] = 0;
         g->error = 0;
         g->emitted = 0;
         g->levels = 0;
     }
     grid.sync();
+    if (tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g->level_ns[0] = t;
+        g->level_len[0] = 1;
+    }
     u32 qlen = 1, emitted = 0;
-    u32 *cur = a.queue_a, *nxt = a.queue_b;
+    uint4 *cur = a.queue_a, *nxt = a.queue_b;
     for (u32 level = 0; qlen > 0; level++) {
         if (tid == 0) g->queue_count[(level + 1) % 3] = 0;  // slot of the next level
-        for (u32 t = tid; t < qlen; t += nthreads)
-            emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, a.K, __ldcg(&cur[t]), nxt, &g->queue_count[level % 3], a.work, a.out_nodes, a.out_prims,
-                           a.order_children, g);
+        for (u32 t0 = warp_id * 4; t0 < qlen; t0 += nwarps * 4) {  // warp-uniform trip count, four nodes per warp
+            const u32 t = t0 + giw;
+            const bool have = t < qlen;
+            uint4 item = make_uint4(0, 0, 0, 0);
+            if (have) item = __ldcg(&cur[t]);
+            emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, have, item, nullptr, nxt, &g->queue_count[level % 3], a.out_nodes, a.out_prims,
+                           a.order_children, g, gmask, gl, sbuf);
+        }
         grid.sync();
         emitted += qlen;
         qlen = __ldcg(&g->queue_count[level % 3]);
@@ -414,10 +522,18 @@ __global__ void __launch_bounds__(128) cwbvh_emit_all_kernel(EmitArgs a) {
             if (tid == 0) g->error = 3;
             break;
         }
-        u32* t2 = cur;
+        uint4* t2 = cur;
         cur = nxt;
         nxt = t2;
-        if (tid == 0) g->levels = level + 1;
+        if (tid == 0) {
+            g->levels = level + 1;
+            if (level < 47) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                g->level_ns[level + 1] = t;
+                g->level_len[level + 1] = qlen;
+            }
+        }
     }
     if (tid == 0) g->emitted = emitted;
 }
@@ -444,10 +560,10 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
         return OBVHS_OK;
     }
     const u32 n_nodes = (u32)bvh->node_count;
-    DevBuf<u32> parents_tmp, P, K, arrivals, queue_a, queue_b;
+    DevBuf<u32> parents_tmp, P, arrivals;
+    DevBuf<uint4> queue_a, queue_b;
     DevBuf<Dec> dec;
     DevBuf<CwGlobals> g;
-    DevBuf<WorkItem> work;
     DevBuf<float> root_box;
     const u32* parents = bvh->parents;
     if (!parents) {  // the converter does not need Bvh2::parents; the bottom-up pass does -> scratch copy
@@ -457,24 +573,23 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     TraceScope* tsp = new TraceScope(ctx, "  cwbvh_cost");
     CU_TRY(ctx, P.alloc(n_nodes, s));
-    CU_TRY(ctx, K.alloc(n_nodes, s));
     CU_TRY(ctx, arrivals.alloc(n_nodes, s));
     CU_TRY(ctx, dec.alloc(n_nodes, s));
     CU_TRY(ctx, g.alloc(1, s));
     CU_TRY(ctx, root_box.alloc(8, s));
     CU_TRY(ctx, cudaMemsetAsync(arrivals.p, 0, (size_t)n_nodes * 4, s));
     CU_TRY(ctx, cudaMemsetAsync(g.p, 0, sizeof(CwGlobals), s));
-    cwbvh_cost_kernel<<<div_up(n_nodes, 256), 256, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, K.p, arrivals.p, g.p);
+    cwbvh_cost_kernel<<<div_up(n_nodes, 256), 256, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
     KERNEL_CHECK(ctx);
     root_aabb_kernel<<<1, 1, 0, s>>>(bvh->nodes, root_box.p);
     KERNEL_CHECK(ctx);
     u32* h = reinterpret_cast<u32*>(ctx->pinned);
-    CU_TRY(ctx, cudaMemcpyAsync(h, K.p, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h, &dec.p->S[0], 4, cudaMemcpyDeviceToHost, s));  // M = 1 + S(root, 0)
     CU_TRY(ctx, cudaMemcpyAsync(h + 8, root_box.p, 32, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
     delete tsp;
     TraceScope ts_emit(ctx, "  cwbvh_emit");
-    const u32 M = h[0];
+    const u32 M = h[0] + 1;
     memcpy(&cw->total_aabb, h + 8, 32);  // bvh2_to_cwbvh.rs:506 total_aabb = bvh2.nodes[0].aabb
     if (M == 0 || M > n_nodes) {
         OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: invalid wide node count %u", M);
@@ -484,23 +599,28 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     cw->prim_count = bvh->prim_count;
     CU_TRY(ctx, cudaMallocAsync((void**)&cw->nodes, (size_t)M * sizeof(ObvhsCwBvhNode), s));
     CU_TRY(ctx, cudaMallocAsync((void**)&cw->primitive_indices, std::max<size_t>(1, cw->prim_count) * 4, s));
-    CU_TRY(ctx, work.alloc(M, s));
     CU_TRY(ctx, queue_a.alloc(M, s));
     CU_TRY(ctx, queue_b.alloc(M, s));
     {
         EmitArgs ea;
-        ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.dec = dec.p; ea.P = P.p; ea.K = K.p;
-        ea.queue_a = queue_a.p; ea.queue_b = queue_b.p; ea.work = work.p; ea.out_nodes = reinterpret_cast<uint4*>(cw->nodes);
+        ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.dec = dec.p; ea.P = P.p;
+        ea.queue_a = queue_a.p; ea.queue_b = queue_b.p; ea.out_nodes = reinterpret_cast<uint4*>(cw->nodes);
         ea.out_prims = cw->primitive_indices; ea.order_children = order_children ? 1 : 0; ea.expected = M; ea.g = g.p;
         int per_sm = 0;
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_emit_all_kernel, 128, 0));
-        int blocks = std::min(std::max(1, per_sm) * ctx->sm_count, std::max(1, div_up(M, 128)));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_emit_all_kernel, EMIT_THREADS, 0));
+        // few, fat blocks: the cost of a grid-wide barrier grows with the number of participating blocks
+        int blocks = std::min(std::max(1, per_sm) * ctx->sm_count, std::max(1, div_up((size_t)M * 8, EMIT_THREADS)));
         void* args[] = {&ea};
-        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)cwbvh_emit_all_kernel, dim3(blocks), dim3(128), args, 0, s));
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)cwbvh_emit_all_kernel, dim3(blocks), dim3(EMIT_THREADS), args, 0, s));
         KERNEL_CHECK(ctx);
     }
     CU_TRY(ctx, cudaMemcpyAsync(h, g.p, sizeof(CwGlobals), cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (ctx->trace) {
+        const CwGlobals* hg = reinterpret_cast<const CwGlobals*>(h);
+        for (u32 l = 0; l + 1 <= hg->levels && l < 46; l++)
+            fprintf(stderr, "[obvhs trace]     emit level %2u: %8u nodes %9.1f us\n", l, hg->level_len[l], (hg->level_ns[l + 1] - hg->level_ns[l]) * 1e-3);
+    }
     if (h[0] != 0 || h[4] != M) {
         OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: %s (emitted %u of %u nodes; non-finite AABBs? the reference panics here)",
                       h[0] == 2 ? "order_children left a child unassigned" : h[0] == 3 ? "node count mismatch" : "invalid decision on the emit path",

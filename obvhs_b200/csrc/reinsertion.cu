@@ -154,7 +154,8 @@ struct ResolveArgs {
 
 // K10, one cooperative launch per round: conflict cells -> greedy-MIS resolution by deterministic reservations ->
 // apply -> dirty-path marking -> bottom-up refit. Phases are separated by grid-wide barriers; no host round trips.
-__global__ void __launch_bounds__(256) reinsert_resolve_apply_kernel(ResolveArgs a) {
+constexpr int RESOLVE_THREADS = 1024;  // few, fat blocks: a grid-wide barrier costs more the more blocks take part
+__global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel(ResolveArgs a) {
     cg::grid_group grid = cg::this_grid();
     const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     ReinsertState* st = a.st;
@@ -365,7 +366,7 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
         return OBVHS_ERR_UNSUPPORTED;
     }
     int coop_blocks = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, 256, 0));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, RESOLVE_THREADS, 0));
     coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
     for (size_t k = 0; k < n_seq; k++) {
         const size_t nc = node_counts[k];
@@ -393,8 +394,8 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
             ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
             ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
             void* args[] = {&ra};
-            int blocks = std::min(coop_blocks, std::max(1, div_up(count, 256)));
-            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(256), args, 0, s));
+            int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
+            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
             KERNEL_CHECK(ctx);
         }
         delete tsp;

@@ -44,52 +44,86 @@ __device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, 
     return __int_as_float(0x7f800000);
 }
 
-__device__ __forceinline__ float byte_f(u32 w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+// u8 -> f32 without the (quarter-rate) I2F pipe: 0x4B000000 | byte is the float 8388608 + byte, and subtracting 8388608
+// is exact, so the result is bit-identical to (float)byte. One PRMT + one FADD, both full-rate.
+// `magic` is 0x4B000000 passed as a kernel argument: kept in a register so the byte selector can be the immediate
+// operand of PRMT (with a literal magic the compiler rebuilds the selector register for every byte).
+template <int J>
+__device__ __forceinline__ float byte_f(u32 w, u32 magic) {
+    return __uint_as_float(__byte_perm(w, magic, 0x7550 + J)) - 8388608.0f;
+}
+
+// The reference's `max(a,b) = a > b ? a : b` (SSE) and fmaxf only differ when an operand is NaN (the sign of a zero cannot
+// change the `tmin <= tmax` decision). EXACT = false is used for nodes whose six affine coefficients are finite and rays
+// whose tmax is not NaN: then every slab value is finite or +-inf, never NaN, and FMNMX gives the same hit mask.
+template <bool EXACT>
+__device__ __forceinline__ float tmax2(float a, float b) { return EXACT ? smax(a, b) : fmaxf(a, b); }
+template <bool EXACT>
+__device__ __forceinline__ float tmin2(float a, float b) { return EXACT ? smin(a, b) : fminf(a, b); }
+
+template <bool EXACT, int H, int J>
+__device__ __forceinline__ u32 child_test(const u32 (&xlo)[2], const u32 (&xhi)[2], const u32 (&ylo)[2], const u32 (&yhi)[2], const u32 (&zlo)[2],
+                                          const u32 (&zhi)[2], float adx, float ady, float adz, float aox, float aoy, float aoz, float ray_tmax,
+                                          u32 child_bits, u32 bit_index, u32 magic) {
+    float tminx = byte_f<J>(xlo[H], magic) * adx + aox, tmaxx = byte_f<J>(xhi[H], magic) * adx + aox;
+    float tminy = byte_f<J>(ylo[H], magic) * ady + aoy, tmaxy = byte_f<J>(yhi[H], magic) * ady + aoy;
+    float tminz = byte_f<J>(zlo[H], magic) * adz + aoz, tmaxz = byte_f<J>(zhi[H], magic) * adz + aoz;
+    float tmn = tmax2<EXACT>(tminx, tmax2<EXACT>(tminy, tminz));  // simd.rs:81-84 nesting
+    float tmx = tmin2<EXACT>(tmaxx, tmin2<EXACT>(tmaxy, tmaxz));
+    tmn = tmax2<EXACT>(tmn, NODE_EPSILON);
+    tmx = tmin2<EXACT>(tmx, ray_tmax);
+    return (tmn <= tmx) ? ((child_bits >> (8 * J)) & 0xffu) << ((bit_index >> (8 * J)) & 0xffu) : 0u;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ u32 node_children(const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4, bool rdx, bool rdy, bool rdz, float adx,
+                                             float ady, float adz, float aox, float aoy, float aoz, float ray_tmax, u32 oct_inv4, u32 magic) {
+    // q2 = {min_x[0..3], min_x[4..7], max_x[0..3], max_x[4..7]}
+    const u32 xlo[2] = {rdx ? q2.z : q2.x, rdx ? q2.w : q2.y}, xhi[2] = {rdx ? q2.x : q2.z, rdx ? q2.y : q2.w};
+    const u32 ylo[2] = {rdy ? q3.z : q3.x, rdy ? q3.w : q3.y}, yhi[2] = {rdy ? q3.x : q3.z, rdy ? q3.y : q3.w};
+    const u32 zlo[2] = {rdz ? q4.z : q4.x, rdz ? q4.w : q4.y}, zhi[2] = {rdz ? q4.x : q4.z, rdz ? q4.y : q4.w};
+    u32 hit_mask = 0;
+#define OBVHS_HALF(H, M)                                                                                                          \
+    {                                                                                                                             \
+        /* node.rs:207-231 get_child_and_index_bits on 4 bytes at a time */                                                       \
+        const u32 m = (M);                                                                                                        \
+        const u32 is_inner = (m & (m << 1)) & 0x10101010u;                                                                        \
+        const u32 inner_mask = (is_inner >> 4) * 0xffu;                                                                           \
+        const u32 bit_index = (m ^ (oct_inv4 & inner_mask)) & 0x1f1f1f1fu;                                                        \
+        const u32 child_bits = (m >> 5) & 0x07070707u;                                                                            \
+        hit_mask |= child_test<EXACT, H, 0>(xlo, xhi, ylo, yhi, zlo, zhi, adx, ady, adz, aox, aoy, aoz, ray_tmax, child_bits, bit_index, magic); \
+        hit_mask |= child_test<EXACT, H, 1>(xlo, xhi, ylo, yhi, zlo, zhi, adx, ady, adz, aox, aoy, aoz, ray_tmax, child_bits, bit_index, magic); \
+        hit_mask |= child_test<EXACT, H, 2>(xlo, xhi, ylo, yhi, zlo, zhi, adx, ady, adz, aox, aoy, aoz, ray_tmax, child_bits, bit_index, magic); \
+        hit_mask |= child_test<EXACT, H, 3>(xlo, xhi, ylo, yhi, zlo, zhi, adx, ady, adz, aox, aoy, aoz, ray_tmax, child_bits, bit_index, magic); \
+    }
+    OBVHS_HALF(0, q1.z)
+    OBVHS_HALF(1, q1.w)
+#undef OBVHS_HALF
+    return hit_mask;
+}
 
 // node.rs:86-231 + simd.rs:17-100: returns the 32-bit hit mask (hi 8 bits inner children by octant priority,
-// lo 24 bits primitive bits).
+// lo 24 bits primitive bits). ray_nan: the ray's tmax is NaN (forces the exact-select path).
 __device__ __forceinline__ u32 node_intersect(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
-                                              const RayRegs& r, u32 oct_inv4) {
+                                              const RayRegs& r, u32 oct_inv4, u32 magic) {
     float px = __uint_as_float(q0.x), py = __uint_as_float(q0.y), pz = __uint_as_float(q0.z);
     float ex = __uint_as_float((q0.w & 0xffu) << 23), ey = __uint_as_float(((q0.w >> 8) & 0xffu) << 23),
           ez = __uint_as_float(((q0.w >> 16) & 0xffu) << 23);  // node.rs:269-275
     float adx = ex * r.ix, ady = ey * r.iy, adz = ez * r.iz;
     float aox = (px - r.ox) * r.ix, aoy = (py - r.oy) * r.iy, aoz = (pz - r.oz) * r.iz;
     bool rdx = r.dx < 0.0f, rdy = r.dy < 0.0f, rdz = r.dz < 0.0f;
-    // q2 = {min_x[0..3], min_x[4..7], max_x[0..3], max_x[4..7]}
-    u32 xlo[2] = {rdx ? q2.z : q2.x, rdx ? q2.w : q2.y}, xhi[2] = {rdx ? q2.x : q2.z, rdx ? q2.y : q2.w};
-    u32 ylo[2] = {rdy ? q3.z : q3.x, rdy ? q3.w : q3.y}, yhi[2] = {rdy ? q3.x : q3.z, rdy ? q3.y : q3.w};
-    u32 zlo[2] = {rdz ? q4.z : q4.x, rdz ? q4.w : q4.y}, zhi[2] = {rdz ? q4.x : q4.z, rdz ? q4.y : q4.w};
-    u32 meta[2] = {q1.z, q1.w};
-    u32 hit_mask = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        // node.rs:207-231 get_child_and_index_bits on 4 bytes at a time
-        u32 m = meta[h];
-        u32 is_inner = (m & (m << 1)) & 0x10101010u;
-        u32 inner_mask = (is_inner >> 4) * 0xffu;
-        u32 bit_index = (m ^ (oct_inv4 & inner_mask)) & 0x1f1f1f1fu;
-        u32 child_bits = (m >> 5) & 0x07070707u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float tminx = byte_f(xlo[h], j) * adx + aox, tmaxx = byte_f(xhi[h], j) * adx + aox;
-            float tminy = byte_f(ylo[h], j) * ady + aoy, tmaxy = byte_f(yhi[h], j) * ady + aoy;
-            float tminz = byte_f(zlo[h], j) * adz + aoz, tmaxz = byte_f(zhi[h], j) * adz + aoz;
-            float tmn = smax(tminx, smax(tminy, tminz));  // simd.rs:81-84 nesting
-            float tmx = smin(tmaxx, smin(tmaxy, tmaxz));
-            tmn = smax(tmn, NODE_EPSILON);
-            tmx = smin(tmx, r.tmax);
-            if (tmn <= tmx) hit_mask |= ((child_bits >> (8 * j)) & 0xffu) << ((bit_index >> (8 * j)) & 0xffu);
-        }
-    }
-    return hit_mask;
+    // all six finite (a huge finite sum that overflows only sends us to the exact path) and tmax not NaN
+    float mag = fabsf(adx) + fabsf(ady) + fabsf(adz) + fabsf(aox) + fabsf(aoy) + fabsf(aoz);
+    if (mag < __int_as_float(0x7f800000) && r.tmax == r.tmax)
+        return node_children<false>(q1, q2, q3, q4, rdx, rdy, rdz, adx, ady, adz, aox, aoy, aoz, r.tmax, oct_inv4, magic);
+    return node_children<true>(q1, q2, q3, q4, rdx, rdy, rdz, adx, ady, adz, aox, aoy, aoz, r.tmax, oct_inv4, magic);
 }
 
 // MODE 0 closest hit -> ObvhsRayHit; 1 miss -> u8; 2 all-hit count -> u32
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) traverse_kernel(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
                                                        const float4* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                       unsigned long long* __restrict__ counters, u32 root_group) {
+                                                       unsigned long long* __restrict__ counters, u32 root_group, u32 magic) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 nodes_visited = 0, tris_tested = 0;
     if (i < n) {
@@ -143,7 +177,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const uint4* __restrict__
                 const uint4* np = nodes + (size_t)(child_index_base + relative_index) * 5;
                 uint4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3), q4 = __ldg(np + 4);
                 if (COUNT) nodes_visited++;
-                u32 hitmask = node_intersect(q0, q1, q2, q3, q4, r, oct_inv4);
+                u32 hitmask = node_intersect(q0, q1, q2, q3, q4, r, oct_inv4, magic);
                 cur.x = q1.x;                                  // child_base_idx
                 prim.x = q1.y;                                 // primitive_base_idx
                 cur.y = (hitmask & 0xff000000u) | (q0.w >> 24);  // | imask
@@ -223,13 +257,13 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
     if (d_counters) {
-        if (mode == 0) traverse_kernel<0, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
-        else if (mode == 1) traverse_kernel<1, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
-        else traverse_kernel<2, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        if (mode == 0) traverse_kernel<0, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
+        else if (mode == 1) traverse_kernel<1, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
+        else traverse_kernel<2, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
     } else {
-        if (mode == 0) traverse_kernel<0, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
-        else if (mode == 1) traverse_kernel<1, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
-        else traverse_kernel<2, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group);
+        if (mode == 0) traverse_kernel<0, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
+        else if (mode == 1) traverse_kernel<1, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
+        else traverse_kernel<2, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u);
     }
     KERNEL_CHECK(ctx);
     return OBVHS_OK;

@@ -50,13 +50,18 @@ def broadcast_cwbvh(bvh, ctx, src: int = 0):
 
     from . import api
 
+    import torch
+
     rank = dist.get_rank()
-    meta = None
+    # sizes + scene AABB travel as one small NCCL broadcast (11 float64: exact for counts < 2^53 and for f32 bounds)
+    meta = torch.zeros(11, dtype=torch.float64, device=f"cuda:{ctx.device}")
     if rank == src:
         nodes_p, prims_p, tris_p = bvh.device_ptrs()
-        total = bvh.total_aabb()
-        meta = (bvh.node_count, bvh.prim_count, bool(tris_p), total.tolist())
-    node_count, prim_count, has_tris, total = broadcast_meta(meta, src)
+        meta[:3] = torch.tensor([bvh.node_count, bvh.prim_count, 1.0 if tris_p else 0.0], dtype=torch.float64)
+        meta[3:] = torch.from_numpy(bvh.total_aabb().astype(np.float64))
+    dist.broadcast(meta, src=src)
+    m = meta.tolist()
+    node_count, prim_count, has_tris, total = int(m[0]), int(m[1]), bool(m[2]), m[3:]
     if rank != src:
         bvh = api.CwBvh.alloc(node_count, prim_count, has_tris, np.asarray(total, np.float32), ctx=ctx)
         nodes_p, prims_p, tris_p = bvh.device_ptrs()

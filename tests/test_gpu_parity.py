@@ -352,3 +352,25 @@ def test_large_scene_full_parity_and_properties(api):
         gh = got.ray_traverse(rays)
         assert np.array_equal(gh["primitive_id"], wh["primitive_id"]), name
         assert np.array_equal(gh["t"].view(np.uint32), wh["t"].view(np.uint32)), name
+
+
+def test_traversal_pinned_host_buffers_zero_copy(api, scenes):
+    # pinned host rays / hits are read and written by the kernel directly (no staging copies): same results
+    import torch
+
+    tris = scenes["kitchen"]
+    bvh = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build())
+    rays = rays_for(tris)
+    want = bvh.ray_traverse(rays)  # pageable host path (staged)
+    from obvhs_b200.types import RAY_HIT
+
+    h_rays = torch.from_numpy(rays).pin_memory()
+    h_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32).pin_memory()
+    got = bvh.ray_traverse(h_rays.numpy(), out=h_hits.numpy().view(RAY_HIT).reshape(-1))
+    assert np.array_equal(got["primitive_id"], want["primitive_id"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    d_rays = h_rays.cuda()
+    d_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32, device="cuda")
+    bvh.ray_traverse(d_rays, out=d_hits)
+    bvh.ctx.synchronize()
+    assert np.array_equal(d_hits.cpu().numpy().view(RAY_HIT).reshape(-1)["primitive_id"], want["primitive_id"])
