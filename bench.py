@@ -57,58 +57,109 @@ def make_workload(name: str, n_tris: int, seed: int = 0):
 
         rays = make_rays(o, d.astype(np.float32), 0.0, np.inf)
         return tris, rays, f"hashed triangle soup {n_tris} tris, fast_build, {m} incoherent rays", "fast_build"
+    if name == "bounce":
+        # BASELINE.json configs[3] / SURVEY.md 8(d) S3: 10M-triangle terrain, demoscene camera 1280x475, `samples` AA samples;
+        # the timed set is the cosine-hemisphere bounce ray leaving every primary hit (examples/demoscene.rs:126-178).
+        # rays=None: they are generated after the build, by tracing the primary rays with the implementation under test.
+        res = int(round((n_tris / 2) ** 0.5))
+        tris = tu.demoscene(res, 0)
+        return tris, None, f"demoscene({res},0) {tris.shape[0]} tris, fast_build, diffuse bounce rays of 1280x475 px", "fast_build"
     raise SystemExit(f"unknown workload {name}")
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+def bounce_samples(total_samples: int, rank: int, world: int):
+    """AA samples traced by `rank` (strong scaling: the sample set is fixed, ranks take contiguous slices)."""
+    from obvhs_b200.sharding import shard_range
 
+    lo, hi = shard_range(total_samples, rank, world)
+    return range(lo, hi)
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line), through NVML in a
+    thread of this process (the same calls `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons...` makes).
+    OBVHS_CLOCK_SAMPLER=smi uses an nvidia-smi -lms 100 subprocess instead, =off disables sampling."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index: int, period_s: float = 0.1):
+        self.gpu, self.period = gpu_index, period_s
+        self.mode = os.environ.get("OBVHS_CLOCK_SAMPLER", "nvml")
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc = self.thread = None
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            if self.mode == "off":
+                return
+            if self.mode == "smi":
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._pump_smi, daemon=True)
+            else:
+                import pynvml
+
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+                self.nv = pynvml
+                self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self.thread = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _pump_nvml(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(self.period)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _pump_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.proc.stdout:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                self.sm.append(float(f[1]))
+                self.mx.append(float(f[2]))
             except ValueError:
                 continue
             for k, nm in enumerate(names):
                 if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(nm)
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable: " + getattr(self, "err", self.mode)]}
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        else:
+            if not self.sm:
+                time.sleep(0.02)
+            self.stop_flag.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.mode}
 
 
 def measured_peak_hbm():
@@ -143,11 +194,26 @@ def cpu_reference_leg(tris, rays, preset, steps, warmup):
     return {"threads": threads, "build_s": float(np.mean(build_s)), "trav_s": float(np.mean(trav_s)), "hits": hits}
 
 
+def cpu_bounce_rays(tris, preset, n_samples):
+    """Bounce set for the CPU legs: primary hits come from the CPU restatement (bit-identical to the GPU path's)."""
+    import oracle_bind as ob
+    from obvhs_b200 import camera
+
+    threads = len(os.sched_getaffinity(0))
+    c = ob.build_cwbvh_from_tris(tris, preset, threads=threads)
+    bt = c.bvh_tris(tris)
+    rays, _ = camera.demoscene_bounce_set(camera.demoscene_camera(1280), range(n_samples), bt,
+                                          lambda r: c.ray_traverse(bt, r, threads=threads, use_simd=True))
+    return rays
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     tris, rays, desc, preset = make_workload(args.workload, args.tris)
+    if rays is None:  # bounce set of a bounded number of AA samples, primary hits from the CPU path itself
+        rays = cpu_bounce_rays(tris, preset, max(1, args.ref_rays // (1280 * 475)))
     # bounded sample so `--steps K --warmup W` ends within a few minutes on the host cores
     max_rays = args.ref_rays
     sample = rays[:: max(1, rays.shape[0] // max_rays)][:max_rays] if rays.shape[0] > max_rays else rays
@@ -192,14 +258,37 @@ def run_ours(args):
 
     tris, rays, desc, preset = make_workload(args.workload, args.tris)
     params = api.BvhBuildParams.preset(preset)
-    n_tris, n_rays = tris.shape[0], rays.shape[0]
+    n_tris = tris.shape[0]
+    strong = rays is None
     with torch.cuda.stream(stream):
         d_tris = torch.from_numpy(tris).to(dev)
+    if strong:
+        # rank 0 builds once, every rank gets a replica and generates the bounce rays of ITS slice of the AA samples
+        from obvhs_b200 import camera
+        from obvhs_b200.types import RAY_HIT
+
+        with torch.cuda.stream(stream):
+            bvh0 = api.build_cwbvh_from_tris(d_tris, params, ctx=ctx) if rank == 0 else None
+            if world > 1:
+                bvh0 = sharding.broadcast_cwbvh(bvh0, ctx, src=0)
+            _, prim_idx, _ = bvh0.download()
+            bvh_tris = tris[prim_idx]
+            rays, n_primary = camera.demoscene_bounce_set(camera.demoscene_camera(1280), bounce_samples(args.samples, rank, world), bvh_tris,
+                                                          lambda r: bvh0.ray_traverse(r))
+        del bvh0, bvh_tris
+        desc += f", {args.samples} AA samples"
+    n_rays = rays.shape[0]
+    with torch.cuda.stream(stream):
         d_rays = torch.from_numpy(rays).to(dev)
         d_hits = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
         d_counters = torch.zeros(2, dtype=torch.int64, device=dev)
     stream.synchronize()
+    n_rays_all = n_rays
+    if dist:
+        t = torch.tensor([n_rays], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_rays_all = int(t.item())
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -248,7 +337,7 @@ def run_ours(args):
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)  # max over ranks
     build_ms, bcast_ms, trav_ms = (tot / args.steps).tolist()
-    value = world * n_rays / (trav_ms * 1e-3) / 1e6
+    value = n_rays_all / (trav_ms * 1e-3) / 1e6  # all ranks' rays / max-over-ranks time
     build_mtris = n_tris / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None
 
     # ---- roofline of the dominant kernel (traverse_kernel): algorithmic bytes from the per-launch counters ----------
@@ -285,7 +374,7 @@ def run_ours(args):
     if dist:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_trav_s, e2e_build_s = e2e_t.tolist()
-    e2e_mrays = world * n_rays / e2e_trav_s / 1e6
+    e2e_mrays = n_rays_all / e2e_trav_s / 1e6
     e2e_mtris = n_tris / e2e_build_s / 1e6
     assert int((hits_np["t"] < 3.0e38).sum()) == hit_count
 
@@ -295,16 +384,16 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             max_rays = args.ref_rays
             sample = rays[:: max(1, n_rays // max_rays)][:max_rays] if n_rays > max_rays else rays
-            r = cpu_reference_leg(tris, sample, preset, 2, 1)
+            r = cpu_reference_leg(tris, sample, preset, 1 if n_tris > 2_000_000 else 2, 1 if n_tris <= 2_000_000 else 0)
             cpu = {"value": sample.shape[0] / r["trav_s"] / 1e6, "unit": "Mrays/s", "cores": r["threads"], "kind": "port",
                    "sample": f"{sample.shape[0]} of {n_rays} rays (strided) + full build; C++ restatement of the obvhs CPU path "
                              "(OpenMP), not the rustc/rayon binary",
                    "build_mtris_per_s": n_tris / r["build_s"] / 1e6}
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": build_ms + bcast_ms + trav_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": build_ms + bcast_ms + trav_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic" if args.workload != "kitchen" else "kitchen.obj fixture (reference asset), generated rays",
-            "config": {"workload": desc, "preset": preset, "rays_per_gpu": n_rays, "tris": n_tris, "l2": "flushed between steps (256 MB write)",
+            "config": {"workload": desc, "preset": preset, "rays_per_gpu": n_rays, "rays_total": n_rays_all, "tris": n_tris, "l2": "flushed between steps (256 MB write)",
                        "multi_gpu": "build on rank 0, NCCL broadcast, rays sharded (one batch per GPU)" if world > 1 else "single GPU"},
             "build": {"value": build_mtris, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count},
             "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
@@ -324,19 +413,182 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def dynamic_frames(tris, n_frames):
+    """BASELINE config 5 / SURVEY.md 8(d) S4: per frame every vertex is displaced by 0.01*(hash_noise-0.5); returns the
+    per-primitive AABBs of each frame, (n_frames, n, 8) f32."""
+    from obvhs_b200 import test_util as tu
+
+    t0 = tris.reshape(-1, 3, 4)
+    k = np.arange(t0.shape[0] * 9, dtype=np.uint32)
+    out = np.zeros((n_frames, t0.shape[0], 8), dtype=np.float32)
+    for f in range(n_frames):
+        noise = tu.hash_noise(k, np.uint32(f), np.uint32(17)).reshape(-1, 3, 3)
+        v = t0[:, :, 0:3] + (noise - np.float32(0.5)) * np.float32(0.01)
+        out[f, :, 0:3] = v.min(axis=1)
+        out[f, :, 4:7] = v.max(axis=1)
+    return out
+
+
+def run_dynamic(args):
+    """--workload dynamic: dynamic Bvh2 maintenance (examples/physics.rs update loop): a step = one frame = rewrite the leaf
+    AABBs of 1M moving triangles, refit_all (bvh2/mod.rs:527-569), ReinsertionOptimizer::run(0.01) (reinsertion.rs:40-57)."""
+    from obvhs_b200 import test_util as tu
+
+    rank = int(os.environ.get("RANK", "0"))
+    res = int(round((args.tris / 2) ** 0.5)) if args.tris != 10_000_000 else 708
+    tris = tu.demoscene(res, 0)
+    n = tris.shape[0]
+    n_frames = 8
+    frames = dynamic_frames(tris, n_frames)
+    desc = f"demoscene({res},0) {n} moving tris: per frame set leaf AABBs + refit_all + reinsertion(0.01); {n_frames} distinct frames cycled"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_bind as ob
+
+        threads = len(os.sched_getaffinity(0))
+        b = ob.ploc_build(ob.tri_aabbs(tris), None, 6, 64, 2, threads=threads)
+        b.reinsertion_run(0.02, threads=threads)
+        ts = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            b.set_leaf_aabbs(frames[it % n_frames])
+            b.refit_all()
+            b.reinsertion_run(0.01, threads=threads)
+            if it >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        ms = float(np.mean(ts)) * 1e3
+        v = n / ms / 1e3
+        print(json.dumps({"impl": "reference", "metric": "dynamic Bvh2 refit + reinsertion Mtris/s", "value": v, "unit": "Mtris/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": desc},
+                          "cpu_baseline": {"value": v, "unit": "Mtris/s", "cores": threads, "kind": "port", "sample": f"{args.steps} full frames"},
+                          "e2e": {"value": v, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+
+    from obvhs_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:  # replicas only: the maintenance loop is globally ordered, every rank runs its own copy
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local_rank, stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(tris).to(dev)
+        d_frames = torch.from_numpy(frames).to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        bvh = api.PlocBuilder(ctx).build_tris(api.PlocSearchDistance.Low, d_tris, api.SortPrecision.U64, 2)
+        opt = api.ReinsertionOptimizer()
+        opt.run(bvh, 0.02)
+    stream.synchronize()
+
+    def frame(it, src):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            bvh.set_leaf_aabbs(src[it % n_frames])
+            e1.record(stream)
+            opt.run(bvh, 0.01)
+            e2.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    for it in range(args.warmup):
+        frame(it, d_frames)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    refit_ms, reins_ms = [], []
+    for it in range(args.steps):
+        a, b = frame(args.warmup + it, d_frames)
+        refit_ms.append(a)
+        reins_ms.append(b)
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([sum(refit_ms), sum(reins_ms)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    refit, reins = (tot / args.steps).tolist()
+    value = world * n / ((refit + reins) * 1e-3) / 1e6
+    # e2e: per-frame AABBs come from pinned HOST memory
+    h_frames = torch.from_numpy(frames).pin_memory()
+    hs = [h_frames[f].numpy() for f in range(n_frames)]
+    e_t = []
+    for it in range(2 + max(2, min(args.steps, 5))):
+        t0 = time.perf_counter()
+        bvh.set_leaf_aabbs(hs[it % n_frames])
+        opt.run(bvh, 0.01)
+        ctx.synchronize()
+        if it >= 2:
+            e_t.append(time.perf_counter() - t0)
+    e2e = torch.tensor([float(np.mean(e_t))], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    peak, peak_src = measured_peak_hbm()
+    refit_bytes = 32 * n + 64 * (2 * n - 1) + 4 * (2 * n - 1)  # leaf AABBs in; every node read by its parent + written; parents
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle_bind as ob
+
+            threads = len(os.sched_getaffinity(0))
+            b = ob.ploc_build(ob.tri_aabbs(tris), None, 6, 64, 2, threads=threads)
+            b.reinsertion_run(0.02, threads=threads)
+            ts = []
+            for it in range(4):
+                t0 = time.perf_counter()
+                b.set_leaf_aabbs(frames[it % n_frames])
+                b.refit_all()
+                b.reinsertion_run(0.01, threads=threads)
+                ts.append(time.perf_counter() - t0)
+            cpu = {"value": n / float(np.mean(ts[1:])) / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "port", "sample": "3 full frames"}
+        print(json.dumps({
+            "metric": "dynamic Bvh2 refit + reinsertion Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": refit + reins, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": desc, "tris": n, "l2": "flushed between steps (256 MB write)",
+                                            "multi_gpu": "replicas only" if world > 1 else "single GPU"},
+            "refit_ms": refit, "reinsertion_ms": reins, "reinsertions_applied_last_frame": opt.applied,
+            "roofline": {"bound": "hbm", "achieved": refit_bytes / (refit * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": refit_bytes / (refit * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "set_leaf_aabbs + refit_bottom_up_kernel",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": refit_bytes},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * n / e2e.item() / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 0,
+                    "how": "obvhs_cuda_bvh2_set_leaf_aabbs (pinned HOST AABBs) + obvhs_cuda_reinsertion_run, synchronised per frame"},
+            "gpu_launches": launches, "clocks": clocks}))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain"])
+    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain", "bounce", "dynamic"])
+    ap.add_argument("--samples", type=int, default=24, help="AA samples of the bounce workload (165 = the 100M-ray set of SURVEY.md 8d)")
     ap.add_argument("--tris", type=int, default=10_000_000)
     ap.add_argument("--ref-rays", type=int, default=2_073_600, help="ray sample bound for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "dynamic":
+        run_dynamic(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -84,6 +84,11 @@ const char* obvhs_cuda_last_error(const ObvhsContext* ctx);
 int obvhs_cuda_synchronize(ObvhsContext* ctx);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx);
+/* Tuning knobs that do not change any result. key "traverse": "auto" (default: a device-side probe of the batch picks the
+ * kernel), "static" (one ray per thread) or "persistent[:refill[:chunk]]" (persistent warps refilled from a ray cursor when
+ * `refill` of 32 lanes have finished, `chunk` consecutive rays per fetch). key "trace": "1"/"0" stage timing on stderr
+ * (the reference's scope!/timeit! macros, lib.rs:158-205). Environment: OBVHS_TRAVERSE, OBVHS_TRACE set the defaults. */
+int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value);
 /* 6 built-in presets of src/lib.rs:233-305 by name: fastest_build, very_fast_build, fast_build, medium_build,
  * slow_build, very_slow_build. */
 int obvhs_cuda_build_params_preset(const char* name, ObvhsBuildParams* out);
@@ -127,6 +132,12 @@ int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const Obvh
  * reinsertions applied. */
 int obvhs_cuda_reinsertion_run(ObvhsContext* ctx, ObvhsBvh2* bvh, float batch_size_ratio, const float* ratio_sequence,
                                size_t n_sequence, uint64_t* applied_out);
+
+/* ReinsertionOptimizer::run_with_candidates(&mut bvh, candidates, iterations) (bvh2/reinsertion.rs:66-90,113-118): the
+ * given node ids (each in [1, node_count), host or device memory), in the given order, are the candidates of every one
+ * of `iterations` rounds. The root or an out-of-range id is OBVHS_ERR_INVALID_ARG (the reference panics). */
+int obvhs_cuda_reinsertion_run_with_candidates(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint32_t* node_ids, size_t n,
+                                               uint32_t iterations, uint64_t* applied_out);
 
 /* ---- CwBvh (src/cwbvh) ------------------------------------------------------------------------------------ */
 /* bvh2_to_cwbvh(&bvh2, max_prims_per_leaf, order_children, include_exact_node_aabbs) (bvh2_to_cwbvh.rs:490-510).

@@ -60,6 +60,7 @@ SIGNATURES = {
     "obvhs_cuda_last_error": (C.c_char_p, [_vp]),
     "obvhs_cuda_synchronize": (_i32, [_vp]),
     "obvhs_cuda_launch_count": (_u64, [_vp]),
+    "obvhs_cuda_set_option": (_i32, [_vp, C.c_char_p, C.c_char_p]),
     "obvhs_cuda_build_params_preset": (_i32, [C.c_char_p, C.POINTER(BuildParamsC)]),
     "obvhs_cuda_morton_sort": (_i32, [_vp, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_ploc_build": (_i32, [_vp, _vp, _vp, _sz, _u32, _u32, _sz, _PP]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "obvhs_cuda_bvh2_refit_all": (_i32, [_vp, _vp]),
     "obvhs_cuda_bvh2_set_leaf_aabbs": (_i32, [_vp, _vp, _vp, _sz]),
     "obvhs_cuda_reinsertion_run": (_i32, [_vp, _vp, _f32, _vp, _sz, C.POINTER(_u64)]),
+    "obvhs_cuda_reinsertion_run_with_candidates": (_i32, [_vp, _vp, _vp, _sz, _u32, C.POINTER(_u64)]),
     "obvhs_cuda_bvh2_to_cwbvh": (_i32, [_vp, _vp, _u32, _i32, _i32, _PP]),
     "obvhs_cuda_build_cwbvh_from_tris": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
     "obvhs_cuda_cwbvh_free": (None, [_vp]),
@@ -137,7 +139,7 @@ def _as_f32(x, cols):
 class Context:
     """One device + stream + reusable builder scratch (obvhs_cuda_create)."""
 
-    def __init__(self, device: int = 0, stream=None):
+    def __init__(self, device: int = 0, stream=None, traverse: str | None = None):
         self.lib = load_library()
         h = C.c_void_p()
         rc = self.lib.obvhs_cuda_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
@@ -145,6 +147,12 @@ class Context:
             raise ObvhsError(rc, "obvhs_cuda_create failed (no CUDA device? there is no CPU fallback)")
         self.h = h
         self.device = device
+        if traverse is not None:
+            self.set_option("traverse", traverse)
+
+    def set_option(self, key: str, value: str):
+        """obvhs_cuda_set_option: tuning knobs that never change a result (traversal kernel choice, stage tracing)."""
+        self.check(self.lib.obvhs_cuda_set_option(self.h, key.encode(), str(value).encode()))
 
     def check(self, rc: int):
         if rc != 0:
@@ -245,7 +253,7 @@ class Bvh2:
         self.ctx, self.h = ctx, handle
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None):  # the native handle keeps its context alive, so the order of destruction is free
             self.ctx.lib.obvhs_cuda_bvh2_free(self.h)
         self.h = None
 
@@ -339,6 +347,15 @@ class ReinsertionOptimizer:
         self.applied = int(applied.value)
         return self.applied
 
+    def run_with_candidates(self, bvh: Bvh2, candidates, iterations: int):
+        """src/bvh2/reinsertion.rs:66-90"""
+        ids = candidates if _is_torch(candidates) else np.ascontiguousarray(candidates, dtype=np.uint32)
+        applied = C.c_uint64(0)
+        bvh.ctx.check(bvh.ctx.lib.obvhs_cuda_reinsertion_run_with_candidates(bvh.ctx.h, bvh.h, _ptr(ids), int(ids.shape[0]), int(iterations),
+                                                                            C.byref(applied)))
+        self.applied = int(applied.value)
+        return self.applied
+
 
 class CwBvh:
     """Device-resident CwBvh (src/cwbvh/mod.rs:43-55) with, optionally, the triangles permuted by primitive_indices."""
@@ -348,7 +365,7 @@ class CwBvh:
         self.core_build_seconds = 0.0
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None):
             self.ctx.lib.obvhs_cuda_cwbvh_free(self.h)
         self.h = None
 

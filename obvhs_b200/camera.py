@@ -193,3 +193,38 @@ def diffuse_bounce_rays(rays, hit_t, normals, cam: Camera, aa_sample: int):
     c0, c1, c2 = tu.build_orthonormal_basis(normals[hit])
     world = (c0 * local[:, 0:1] + c1 * local[:, 1:2]) + c2 * local[:, 2:3]
     return make_rays(hit_p.astype(np.float32), _norm3(world), 0.0, np.inf), hit
+
+
+def shading_normals(bvh_tris, prim_ids, directions):
+    """triangle.rs:20-24 `compute_normal` ((v1-v0)x(v2-v0), normalize_or_zero) of the hit triangle, flipped towards the
+    ray (`normal *= normal.dot(-ray.direction).signum()`, examples/demoscene.rs:166-167). prim_ids index bvh_tris
+    (CwBvh primitive order); entries >= len(bvh_tris) (misses) give (0,0,0)."""
+    t = np.asarray(bvh_tris, dtype=np.float32).reshape(-1, 12)
+    ok = np.asarray(prim_ids) < t.shape[0]
+    tt = t[np.where(ok, prim_ids, 0)]
+    v0, v1, v2 = tt[:, 0:3], tt[:, 4:7], tt[:, 8:11]
+    a, b = v1 - v0, v2 - v0
+    n = np.stack([a[:, 1] * b[:, 2] - b[:, 1] * a[:, 2], a[:, 2] * b[:, 0] - b[:, 2] * a[:, 0], a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]], axis=1)
+    d = (n[:, 0] * n[:, 0] + n[:, 1] * n[:, 1]) + n[:, 2] * n[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = f32(1.0) / np.sqrt(d)
+    r = np.where(np.isfinite(r) & (r > 0) & ok, r, f32(0.0)).astype(np.float32)
+    n = n * r[:, None]
+    dirs = np.asarray(directions, dtype=np.float32)
+    s = -((n[:, 0] * dirs[:, 0] + n[:, 1] * dirs[:, 1]) + n[:, 2] * dirs[:, 2])
+    return (n * np.where(np.signbit(s), f32(-1.0), f32(1.0))[:, None]).astype(np.float32)
+
+
+def demoscene_bounce_set(cam: Camera, samples, bvh_tris, trace):
+    """The incoherent ray set of examples/demoscene.rs:126-178: for each AA sample the jittered primary rays are traced
+    with `trace(rays) -> RayHit array` (closest hit, primitive ids in CwBvh order), and one cosine-hemisphere bounce ray
+    leaves every hit point. Returns (bounce rays (m,16) f32, number of primary rays traced)."""
+    out, n_primary = [], 0
+    for s in samples:
+        prim = demoscene_primary(cam, int(s))
+        hits = trace(prim)
+        n_primary += prim.shape[0]
+        nrm = shading_normals(bvh_tris, hits["primitive_id"], prim[:, 4:7])
+        b, _ = diffuse_bounce_rays(prim, hits["t"], nrm, cam, int(s))
+        out.append(b)
+    return (np.concatenate(out, axis=0) if out else np.zeros((0, 16), np.float32)), n_primary

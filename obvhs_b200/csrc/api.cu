@@ -10,6 +10,67 @@ int bvh2_pack_nodes_device(ObvhsContext* ctx, const ObvhsBvh2Node* d_in, size_t 
 
 #include <chrono>
 #include <cstdlib>
+cudaError_t obvhs_result_alloc(ObvhsContext* ctx, void** p, size_t bytes) {
+    const size_t GRAIN = (size_t)2 << 20;
+    size_t cap = (bytes + GRAIN - 1) / GRAIN * GRAIN;
+    if (cap == 0) cap = GRAIN;
+    {
+        std::lock_guard<std::mutex> lock(ctx->result_mu);
+        // best fit among cached blocks that waste at most 25 % (+ one grain)
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < ctx->result_cache.size(); i++) {
+            const size_t c = ctx->result_cache[i].cap;
+            if (c >= cap && c <= cap + cap / 4 + GRAIN && (best == (size_t)-1 || c < ctx->result_cache[best].cap)) best = i;
+        }
+        if (best != (size_t)-1) {
+            *p = ctx->result_cache[best].p;
+            ctx->result_live[*p] = ctx->result_cache[best].cap;
+            ctx->result_cache.erase(ctx->result_cache.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    double t0 = ctx->trace ? TraceScope::now() : 0.0;
+    cudaError_t e = cudaMalloc(p, cap);
+    if (e != cudaSuccess) {  // make room: drop the cache and retry once
+        cudaGetLastError();
+        std::vector<ObvhsContext::ResultBlock> drop;
+        {
+            std::lock_guard<std::mutex> lock(ctx->result_mu);
+            drop.swap(ctx->result_cache);
+        }
+        for (auto& b : drop) cudaFree(b.p);
+        e = cudaMalloc(p, cap);
+    }
+    if (ctx->trace) fprintf(stderr, "[obvhs trace]     result cudaMalloc %zu MB took %.3f ms\n", cap >> 20, (TraceScope::now() - t0) * 1e3);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(ctx->result_mu);
+        ctx->result_live[*p] = cap;
+    }
+    return e;
+}
+// The block goes back to the context's cache. Work that still reads it was enqueued on ctx->stream, and so is whatever
+// reuses it, so stream order makes the hand-over safe without a synchronisation.
+void obvhs_result_free(ObvhsContext* ctx, void* p) {
+    if (!p) return;
+    void* evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ctx->result_mu);
+        auto it = ctx->result_live.find(p);
+        if (it == ctx->result_live.end()) return;
+        ctx->result_cache.push_back({p, it->second});
+        ctx->result_live.erase(it);
+        if (ctx->result_cache.size() > 32) {  // bound the cache: the oldest block goes back to the driver
+            evict = ctx->result_cache.front().p;
+            ctx->result_cache.erase(ctx->result_cache.begin());
+        }
+    }
+    if (evict) cudaFree(evict);
+}
+void obvhs_context_retain(ObvhsContext* ctx) { ctx->refs.fetch_add(1); }
+static void context_teardown(ObvhsContext* ctx);
+void obvhs_context_release(ObvhsContext* ctx) {
+    if (ctx->refs.fetch_sub(1) == 1) context_teardown(ctx);
+}
 double TraceScope::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 bool obvhs_is_device_ptr(const void* ptr) {
@@ -116,6 +177,25 @@ struct DeviceScope {  // makes the context's device current for the duration of 
     } while (0)
 }  // namespace
 
+static void context_teardown(ObvhsContext* ctx) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto& b : ctx->arena_blocks) cudaFree(b.p);
+    for (auto& b : ctx->result_cache) cudaFree(b.p);
+    for (auto& kv : ctx->result_live) cudaFree(kv.first);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    delete ctx;
+}
+
 extern "C" {
 
 int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
@@ -131,6 +211,7 @@ int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
     ctx->device = device;
     const char* tr = getenv("OBVHS_TRACE");
     ctx->trace = tr && tr[0] == '1';
+    if (const char* tm = getenv("OBVHS_TRAVERSE")) obvhs_cuda_set_option(ctx, "traverse", tm);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -147,26 +228,18 @@ int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
         obvhs_cuda_destroy(ctx);
         return OBVHS_ERR_CUDA;
     }
-    // keep freed scratch in the pool: the reference's builders keep their Vecs for reuse (ploc/mod.rs:35-54)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     *out = ctx;
     return OBVHS_OK;
 }
 
 void obvhs_cuda_destroy(ObvhsContext* ctx) {
     if (!ctx) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    for (auto& b : ctx->arena_blocks) cudaFree(b.p);
-    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    obvhs_context_release(ctx);  // trees built on this context keep it alive until they are freed
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 const char* obvhs_cuda_last_error(const ObvhsContext* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
@@ -178,6 +251,36 @@ int obvhs_cuda_synchronize(ObvhsContext* ctx) {
 }
 
 uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx) { return ctx ? ctx->launches : 0; }
+
+int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value) {
+    if (!ctx || !key || !value) return OBVHS_ERR_INVALID_ARG;
+    if (strcmp(key, "traverse") == 0) {
+        if (strcmp(value, "auto") == 0) ctx->traverse_mode = 2;
+        else if (strcmp(value, "static") == 0) ctx->traverse_mode = 0;
+        else if (strncmp(value, "persistent", 10) == 0 && (value[10] == 0 || value[10] == ':')) {
+            ctx->traverse_mode = 1;
+            if (value[10] == ':') {
+                int refill = atoi(value + 11);
+                if (refill != 1 && refill != 4 && refill != 8 && refill != 16 && refill != 32) {
+                    OBVHS_SET_ERR(ctx, "traverse refill threshold must be 1, 4, 8, 16 or 32");
+                    return OBVHS_ERR_INVALID_ARG;
+                }
+                ctx->traverse_refill = refill;
+                if (const char* c2 = strchr(value + 11, ':')) ctx->traverse_chunk = atoi(c2 + 1) < 32 ? 32 : atoi(c2 + 1);
+            }
+        } else {
+            OBVHS_SET_ERR(ctx, "traverse must be auto, static or persistent[:refill[:chunk]]");
+            return OBVHS_ERR_INVALID_ARG;
+        }
+        return OBVHS_OK;
+    }
+    if (strcmp(key, "trace") == 0) {
+        ctx->trace = value[0] == '1';
+        return OBVHS_OK;
+    }
+    OBVHS_SET_ERR(ctx, "unknown option %s", key);
+    return OBVHS_ERR_INVALID_ARG;
+}
 
 int obvhs_cuda_build_params_preset(const char* name, ObvhsBuildParams* out) {
     if (!name || !out) return OBVHS_ERR_INVALID_ARG;
@@ -259,14 +362,12 @@ int obvhs_cuda_ploc_build_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, siz
 // ---- Bvh2 ---------------------------------------------------------------------------------------------------
 void obvhs_cuda_bvh2_free(ObvhsBvh2* bvh) {
     if (!bvh) return;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != bvh->device) cudaSetDevice(bvh->device);
-    if (bvh->nodes) cudaFree(bvh->nodes);
-    if (bvh->primitive_indices) cudaFree(bvh->primitive_indices);
-    if (bvh->parents) cudaFree(bvh->parents);
-    if (prev >= 0 && prev != bvh->device) cudaSetDevice(prev);
+    ObvhsContext* ctx = bvh->owner;
+    obvhs_result_free(ctx, bvh->nodes);
+    obvhs_result_free(ctx, bvh->primitive_indices);
+    obvhs_result_free(ctx, bvh->parents);
     delete bvh;
+    obvhs_context_release(ctx);
 }
 size_t obvhs_cuda_bvh2_node_count(const ObvhsBvh2* bvh) { return bvh ? bvh->node_count : 0; }
 size_t obvhs_cuda_bvh2_prim_count(const ObvhsBvh2* bvh) { return bvh ? bvh->prim_count : 0; }
@@ -304,6 +405,8 @@ int obvhs_cuda_bvh2_upload(ObvhsContext* ctx, const ObvhsBvh2Node* nodes, size_t
     ARG_CHECK(ctx, prim_count == 0 || primitive_indices, "primitive_indices is null");
     ObvhsBvh2* bvh = new ObvhsBvh2();
     bvh->device = ctx->device;
+    bvh->owner = ctx;
+    obvhs_context_retain(ctx);
     bvh->node_count = node_count;
     bvh->prim_count = prim_count;
     bvh->max_depth = max_depth ? max_depth : 96;
@@ -316,11 +419,11 @@ int obvhs_cuda_bvh2_upload(ObvhsContext* ctx, const ObvhsBvh2Node* nodes, size_t
         DevBuf<ObvhsBvh2Node> st;
         const ObvhsBvh2Node* d_nodes = nullptr;
         ST_TRY(stage_in(ctx, nodes, node_count, st, &d_nodes));
-        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->nodes, node_count * sizeof(Node32), ctx->stream));
+        CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->nodes, node_count * sizeof(Node32)));
         ST_TRY(bvh2_pack_nodes_device(ctx, d_nodes, node_count, bvh->nodes));
     }
     if (prim_count) {
-        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->primitive_indices, prim_count * 4, ctx->stream));
+        CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->primitive_indices, prim_count * 4));
         CU_TRY(ctx, cudaMemcpyAsync(bvh->primitive_indices, primitive_indices, prim_count * 4, cudaMemcpyDefault, ctx->stream));
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -357,6 +460,37 @@ int obvhs_cuda_reinsertion_run(ObvhsContext* ctx, ObvhsBvh2* bvh, float batch_si
     ARG_CHECK(ctx, !ratio_sequence || !obvhs_is_device_ptr(ratio_sequence), "ratio_sequence must be host memory");
     u64 applied = 0;
     int rc = reinsertion_run_device(ctx, bvh, batch_size_ratio, ratio_sequence, n_sequence, &applied);
+    if (applied_out) *applied_out = applied;
+    return rc;
+}
+
+int obvhs_cuda_reinsertion_run_with_candidates(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint32_t* node_ids, size_t n, uint32_t iterations,
+                                               uint64_t* applied_out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    ARG_CHECK(ctx, n == 0 || node_ids, "node_ids is null");
+    if (applied_out) *applied_out = 0;
+    if (n == 0) return OBVHS_OK;
+    // find_reinsertion asserts node_id != 0 and indexes nodes[node_id] (reinsertion.rs:233-240): check instead of panicking
+    std::vector<u32> host_ids;
+    const u32* h_ids = node_ids;
+    if (obvhs_is_device_ptr(node_ids)) {
+        host_ids.resize(n);
+        CU_TRY(ctx, cudaMemcpyAsync(host_ids.data(), node_ids, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        h_ids = host_ids.data();
+    }
+    if (bvh->node_count > 1)
+        for (size_t i = 0; i < n; i++)
+            if (h_ids[i] == 0 || h_ids[i] >= bvh->node_count) {
+                OBVHS_SET_ERR(ctx, "reinsertion candidate %zu = node %u is the root or out of range (%zu nodes)", i, h_ids[i], bvh->node_count);
+                return OBVHS_ERR_INVALID_ARG;
+            }
+    DevBuf<u32> st;
+    const u32* d_ids = nullptr;
+    ST_TRY(stage_in(ctx, node_ids, n, st, &d_ids));
+    u64 applied = 0;
+    int rc = reinsertion_run_candidates_device(ctx, bvh, d_ids, n, iterations, &applied);
     if (applied_out) *applied_out = applied;
     return rc;
 }
@@ -425,14 +559,12 @@ int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tri
 
 void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh) {
     if (!bvh) return;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != bvh->device) cudaSetDevice(bvh->device);
-    if (bvh->nodes) cudaFree(bvh->nodes);
-    if (bvh->primitive_indices) cudaFree(bvh->primitive_indices);
-    if (bvh->bvh_tris) cudaFree(bvh->bvh_tris);
-    if (prev >= 0 && prev != bvh->device) cudaSetDevice(prev);
+    ObvhsContext* ctx = bvh->owner;
+    obvhs_result_free(ctx, bvh->nodes);
+    obvhs_result_free(ctx, bvh->primitive_indices);
+    obvhs_result_free(ctx, bvh->bvh_tris);
     delete bvh;
+    obvhs_context_release(ctx);
 }
 size_t obvhs_cuda_cwbvh_node_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->node_count : 0; }
 size_t obvhs_cuda_cwbvh_prim_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->prim_count : 0; }
@@ -457,6 +589,8 @@ int obvhs_cuda_cwbvh_alloc(ObvhsContext* ctx, size_t node_count, size_t prim_cou
     ARG_CHECK(ctx, out, "out is null");
     ObvhsCwBvh* cw = new ObvhsCwBvh();
     cw->device = ctx->device;
+    cw->owner = ctx;
+    obvhs_context_retain(ctx);
     cw->node_count = node_count;
     cw->prim_count = prim_count;
     if (total_aabb) cw->total_aabb = *total_aabb;
@@ -464,9 +598,9 @@ int obvhs_cuda_cwbvh_alloc(ObvhsContext* ctx, size_t node_count, size_t prim_cou
         ObvhsCwBvh* b;
         ~Guard() { if (b) obvhs_cuda_cwbvh_free(b); }
     } guard{cw};
-    if (node_count) CU_TRY(ctx, cudaMallocAsync((void**)&cw->nodes, node_count * sizeof(ObvhsCwBvhNode), ctx->stream));
-    if (prim_count) CU_TRY(ctx, cudaMallocAsync((void**)&cw->primitive_indices, prim_count * 4, ctx->stream));
-    if (prim_count && with_triangles) CU_TRY(ctx, cudaMallocAsync((void**)&cw->bvh_tris, prim_count * sizeof(ObvhsTriangle), ctx->stream));
+    if (node_count) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->nodes, node_count * sizeof(ObvhsCwBvhNode)));
+    if (prim_count) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->primitive_indices, prim_count * 4));
+    if (prim_count && with_triangles) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->bvh_tris, prim_count * sizeof(ObvhsTriangle)));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     guard.b = nullptr;
     *out = cw;
@@ -518,6 +652,21 @@ int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** pri
     return OBVHS_OK;
 }
 
+// Host-resident ray batches are pipelined in chunks over three streams: H2D of chunk k+1 (copy_in), traversal of chunk k
+// (the context's stream) and D2H of chunk k-1 (copy_out) run concurrently, so a batch costs about max(H2D, kernel, D2H)
+// instead of their sum (PCIe is full duplex). Letting the kernel read pinned host memory directly (zero-copy) measured
+// 1.5x SLOWER on B200/PCIe (425 vs 630 Mrays/s on the kitchen), small PCIe reads being latency-bound.
+static int ensure_pipeline(ObvhsContext* ctx, size_t n_events) {
+    if (!ctx->copy_in) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    while (ctx->event_pool.size() < n_events) {
+        cudaEvent_t e;
+        CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->event_pool.push_back(e);
+    }
+    return OBVHS_OK;
+}
+
 static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
                            uint64_t* counters) {
     ARG_CHECK(ctx, bvh, "bvh is null");
@@ -526,13 +675,9 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
     DevBuf<ObvhsRay> st_rays;
     DevBuf<unsigned char> st_out;
     DevBuf<u64> st_cnt;
-    // Host rays are staged with one bulk DMA: letting the kernel read pinned host memory directly (zero-copy) measured
-    // 1.5x SLOWER on B200/PCIe (425 vs 630 Mrays/s on the kitchen), small PCIe reads being latency-bound.
-    const ObvhsRay* d_rays = nullptr;
-    ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
-    bool out_dev = obvhs_is_device_ptr(out);
+    const bool rays_dev = obvhs_is_device_ptr(rays);
+    const bool out_dev = obvhs_is_device_ptr(out);
     void* d_out = out;
-    bool out_mapped = false;
     if (!out_dev) {
         CU_TRY(ctx, st_out.alloc(n * out_elem, ctx->stream));
         d_out = st_out.p;
@@ -548,14 +693,51 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
             d_cnt = st_cnt.p;
         }
     }
-    ST_TRY(cwbvh_traverse_device(ctx, bvh, d_rays, n, mode, d_out, d_cnt));
-    if (counters && !cnt_dev) CU_TRY(ctx, cudaMemcpyAsync(counters, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!out_dev) {
-        if (!out_mapped) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host-visible results: the call is synchronous like the reference's
-    } else if (counters && !cnt_dev) {
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t MIN_CHUNK = 32768;
+    if (rays_dev) {
+        ST_TRY(cwbvh_traverse_device(ctx, bvh, rays, n, mode, d_out, d_cnt));
+        if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (n < 2 * MIN_CHUNK) {
+        const ObvhsRay* d_rays = nullptr;
+        ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
+        ST_TRY(cwbvh_traverse_device(ctx, bvh, d_rays, n, mode, d_out, d_cnt));
+        if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
+        size_t chunk = (n + 15) / 16;  // ~16 stages: the un-overlapped head and tail are 1/16 of the copy time each
+        if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+        if (chunk > ((size_t)1 << 21)) chunk = (size_t)1 << 21;
+        chunk = (chunk + 127) & ~(size_t)127;
+        const size_t n_chunks = (n + chunk - 1) / chunk;
+        ST_TRY(ensure_pipeline(ctx, 2 * n_chunks + 2));
+        cudaEvent_t* ev = ctx->event_pool.data();
+        // the staging areas come from the arena, whose reuse is ordered on ctx->stream: the copy streams start after it
+        CU_TRY(ctx, cudaEventRecord(ev[0], ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ev[0], 0));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev[0], 0));
+        const unsigned char* h_rays = reinterpret_cast<const unsigned char*>(rays);
+        for (size_t c = 0; c < n_chunks; c++) {
+            const size_t off = c * chunk, cnt = (off + chunk <= n) ? chunk : n - off;
+            cudaEvent_t e_in = ev[2 + 2 * c], e_k = ev[3 + 2 * c];
+            CU_TRY(ctx, cudaMemcpyAsync(st_rays.p + off, h_rays + off * sizeof(ObvhsRay), cnt * sizeof(ObvhsRay), cudaMemcpyHostToDevice, ctx->copy_in));
+            CU_TRY(ctx, cudaEventRecord(e_in, ctx->copy_in));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
+            ST_TRY(cwbvh_traverse_device(ctx, bvh, st_rays.p + off, cnt, mode, (unsigned char*)d_out + off * out_elem, d_cnt));
+            if (!out_dev) {
+                CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
+                CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
+                CU_TRY(ctx, cudaMemcpyAsync((unsigned char*)out + off * out_elem, (unsigned char*)d_out + off * out_elem, cnt * out_elem,
+                                            cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
+        }
+        if (!out_dev) {  // join the copy-out stream back into the context's stream
+            CU_TRY(ctx, cudaEventRecord(ev[1], ctx->copy_out));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev[1], 0));
+        }
     }
+    if (counters && !cnt_dev) CU_TRY(ctx, cudaMemcpyAsync(counters, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    // host-visible results (or host-staged inputs whose arena slot is released on return): synchronous like the reference
+    if (!out_dev || !rays_dev || (counters && !cnt_dev)) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return OBVHS_OK;
 }
 

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const float4* __restric
 
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     if (bvh->node_count == 0) return OBVHS_OK;
-    if (!bvh->parents) CU_TRY(ctx, cudaMallocAsync((void**)&bvh->parents, bvh->node_count * 4, ctx->stream));
+    if (!bvh->parents) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->parents, bvh->node_count * 4));
     compute_parents_kernel<<<div_up(bvh->node_count, 256), 256, 0, ctx->stream>>>(bvh->nodes, (u32)bvh->node_count, bvh->parents);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;

@@ -9,7 +9,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/obvhs_cuda.h"
@@ -119,6 +122,22 @@ struct ObvhsContext {
     size_t arena_block = 0, arena_off = 0;  // bump position: block index + offset inside it
     size_t arena_peak = 0, arena_used = 0;
     int api_depth = 0;
+    // Result buffers (trees outlive the call that built them): a size-matched cache of cudaMalloc blocks owned by the context.
+    // Freed trees return their blocks here, so a rebuild of a same-sized scene allocates nothing (the driver's stream-ordered
+    // pool was measured to hand back fresh memory every few rebuilds of the 10M-triangle scene: 5-50 ms per allocation).
+    // Handles keep the context alive (refs); obvhs_cuda_destroy only drops the creator's reference.
+    std::atomic<int> refs{1};
+    std::mutex result_mu;
+    struct ResultBlock {
+        void* p;
+        size_t cap;
+    };
+    std::vector<ResultBlock> result_cache;
+    std::unordered_map<void*, size_t> result_live;
+    // host-batch pipeline (traverse_common): copy-in / copy-out streams beside `stream`, and a pool of timing-free events
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> event_pool;
+    int traverse_mode = 2, traverse_refill = 8, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
 };
 
@@ -145,6 +164,7 @@ struct TraceScope {
 };
 
 struct ObvhsBvh2 {
+    ObvhsContext* owner = nullptr;  // holds a reference
     int device = 0;
     Node32* nodes = nullptr;          // node_count
     u32* primitive_indices = nullptr;  // prim_count
@@ -156,6 +176,7 @@ struct ObvhsBvh2 {
 };
 
 struct ObvhsCwBvh {
+    ObvhsContext* owner = nullptr;  // holds a reference
     int device = 0;
     ObvhsCwBvhNode* nodes = nullptr;
     u32* primitive_indices = nullptr;
@@ -209,6 +230,12 @@ struct DevBuf {
         return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
 };
+
+// Result buffers (they outlive the call, so they do not come from the arena): stream-ordered pool allocations.
+cudaError_t obvhs_result_alloc(ObvhsContext* ctx, void** p, size_t bytes);
+void obvhs_result_free(ObvhsContext* ctx, void* p);
+void obvhs_context_retain(ObvhsContext* ctx);
+void obvhs_context_release(ObvhsContext* ctx);  // destroys the context when the last reference goes
 
 // true when ptr is device (or managed) memory
 bool obvhs_is_device_ptr(const void* ptr);
@@ -264,6 +291,7 @@ int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_pa
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 // reinsertion.cu
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);
+int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, size_t n, u32 iterations, u64* applied_out);
 // cwbvh_build.cu
 int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out);
 // traverse.cu

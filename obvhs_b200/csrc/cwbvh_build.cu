@@ -550,6 +550,8 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     cudaStream_t s = ctx->stream;
     ObvhsCwBvh* cw = new ObvhsCwBvh();
     cw->device = ctx->device;
+    cw->owner = ctx;
+    obvhs_context_retain(ctx);
     struct Guard {
         ObvhsCwBvh* b;
         ~Guard() { if (b) obvhs_cuda_cwbvh_free(b); }
@@ -597,8 +599,8 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     cw->node_count = M;
     cw->prim_count = bvh->prim_count;
-    CU_TRY(ctx, cudaMallocAsync((void**)&cw->nodes, (size_t)M * sizeof(ObvhsCwBvhNode), s));
-    CU_TRY(ctx, cudaMallocAsync((void**)&cw->primitive_indices, std::max<size_t>(1, cw->prim_count) * 4, s));
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->nodes, (size_t)M * sizeof(ObvhsCwBvhNode)));
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->primitive_indices, std::max<size_t>(1, cw->prim_count) * 4));
     CU_TRY(ctx, queue_a.alloc(M, s));
     CU_TRY(ctx, queue_b.alloc(M, s));
     {

@@ -511,6 +511,8 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     cudaStream_t s = ctx->stream;
     ObvhsBvh2* bvh = new ObvhsBvh2();
     bvh->device = ctx->device;
+    bvh->owner = ctx;
+    obvhs_context_retain(ctx);
     bvh->prim_count = n;
     struct Guard {
         ObvhsBvh2* b;
@@ -518,7 +520,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     } guard{bvh};
     // bvh2/mod.rs:106-121 reset_for_reuse: primitive_indices = indices
     if (n) {
-        CU_TRY(ctx, cudaMallocAsync((void**)&bvh->primitive_indices, n * 4, s));
+        CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->primitive_indices, n * 4));
         if (d_indices) CU_TRY(ctx, cudaMemcpyAsync(bvh->primitive_indices, d_indices, n * 4, cudaMemcpyDeviceToDevice, s));
         else {
             iota_kernel<<<div_up(n, 256), 256, 0, s>>>(bvh->primitive_indices, (u32)n);
@@ -533,7 +535,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     }
     const u32 un = (u32)n;
     bvh->node_count = 2 * n - 1;
-    CU_TRY(ctx, cudaMallocAsync((void**)&bvh->nodes, bvh->node_count * sizeof(Node32), s));
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->nodes, bvh->node_count * sizeof(Node32)));
 
     DevBuf<PlocGlobals> g;
     DevBuf<Node32> bufA, bufB;

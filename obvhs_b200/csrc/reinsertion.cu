@@ -300,23 +300,122 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel
 
 }  // namespace
 
+// Scratch of one optimisation run + one round of optimize_candidates (reinsertion.rs:141-208): find_reinsertion for the
+// first `count` candidates, stable sort by descending gain, conflict-checked apply (greedy in gain order) + refit.
+struct ReinsertRun {
+    ObvhsContext* ctx;
+    ObvhsBvh2* bvh;
+    DevBuf<u32> r_from, r_to, gkeys, gkeys_alt, gvals, gvals_alt, cells, status, touched, mark, pending;
+    DevBuf<float> r_diff;
+    DevBuf<unsigned long long> reserve;
+    DevBuf<ReinsertState> st;
+    int coop_blocks = 0;
+
+    int init(ObvhsContext* c, ObvhsBvh2* b, size_t max_count) {
+        ctx = c;
+        bvh = b;
+        cudaStream_t s = ctx->stream;
+        const size_t len = bvh->node_count;
+        CU_TRY(ctx, r_from.alloc(max_count, s));
+        CU_TRY(ctx, r_to.alloc(max_count, s));
+        CU_TRY(ctx, r_diff.alloc(max_count, s));
+        CU_TRY(ctx, gkeys.alloc(max_count, s));
+        CU_TRY(ctx, gkeys_alt.alloc(max_count, s));
+        CU_TRY(ctx, gvals.alloc(max_count, s));
+        CU_TRY(ctx, gvals_alt.alloc(max_count, s));
+        CU_TRY(ctx, cells.alloc(max_count * 5, s));
+        CU_TRY(ctx, status.alloc(max_count, s));
+        CU_TRY(ctx, touched.alloc(len, s));
+        CU_TRY(ctx, mark.alloc(len, s));
+        CU_TRY(ctx, pending.alloc(len, s));
+        CU_TRY(ctx, reserve.alloc(len, s));
+        CU_TRY(ctx, st.alloc(1, s));
+        CU_TRY(ctx, cudaMemsetAsync(touched.p, 0, len * 4, s));
+        CU_TRY(ctx, cudaMemsetAsync(mark.p, 0, len * 4, s));
+        CU_TRY(ctx, cudaMemsetAsync(pending.p, 0, len * 4, s));
+        CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
+        CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, RESOLVE_THREADS, 0));
+        coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
+        return OBVHS_OK;
+    }
+
+    int round(const u32* cand_ids, u32 count, u32 round_stamp) {
+        cudaStream_t s = ctx->stream;
+        TraceScope* tsp = new TraceScope(ctx, "  reins_find");
+        find_reinsertion_kernel<<<div_up(count, 128), 128, 0, s>>>(bvh->nodes, bvh->parents, cand_ids, count, r_from.p, r_to.p, r_diff.p,
+                                                                  gkeys.p, gvals.p);
+        KERNEL_CHECK(ctx);
+        delete tsp;
+        TraceScope ts(ctx, "  reins_gain_sort_resolve");
+        u32 *gk, *order;
+        ST_TRY(radix_sort_pairs_u32(ctx, gkeys.p, gkeys_alt.p, gvals.p, gvals_alt.p, count, 4, &gk, &order));
+        ResolveArgs ra;
+        ra.order = order; ra.r_from = r_from.p; ra.r_to = r_to.p; ra.r_diff = r_diff.p; ra.count = count;
+        ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
+        ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
+        void* args[] = {&ra};
+        int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
+        KERNEL_CHECK(ctx);
+        return OBVHS_OK;
+    }
+
+    int finish(u64* applied_out) {
+        u32* h = reinterpret_cast<u32*>(ctx->pinned);
+        CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[5]) {
+            OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
+            return OBVHS_ERR_CUDA;
+        }
+        if (applied_out) *applied_out = h[4];
+        return OBVHS_OK;
+    }
+};
+
+static int reinsertion_prologue(ObvhsContext* ctx, ObvhsBvh2* bvh) {
+    if (bvh->max_depth > 96) {
+        OBVHS_SET_ERR(ctx, "reinsertion: max_depth %zu > 96 needs a heap stack (faststack.rs) -- not supported", bvh->max_depth);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    if (!bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));  // init_parents_if_uninit
+    bvh->children_are_ordered_after_parents = false;                    // reinsertion.rs:93,113
+    return OBVHS_OK;
+}
+
+// ReinsertionOptimizer::run_with_candidates (reinsertion.rs:66-90, 113-118): the given node ids, in the given order, are
+// the candidates of every one of `iterations` rounds.
+int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, size_t n, u32 iterations, u64* applied_out) {
+    if (applied_out) *applied_out = 0;
+    if (bvh->node_count <= 1 || n == 0 || iterations == 0) return OBVHS_OK;  // reinsertion.rs:69-71
+    if (iterations > 60000) {
+        OBVHS_SET_ERR(ctx, "reinsertion: too many iterations (%u)", iterations);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    ST_TRY(reinsertion_prologue(ctx, bvh));
+    ReinsertRun run;
+    ST_TRY(run.init(ctx, bvh, n));
+    for (u32 k = 0; k < iterations; k++) ST_TRY(run.round(d_node_ids, (u32)n, k + 1));
+    return run.finish(applied_out);
+}
+
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out) {
     if (applied_out) *applied_out = 0;
     cudaStream_t s = ctx->stream;
     const size_t len = bvh->node_count;
     if (len == 0 || !(ratio > 0.0f)) return OBVHS_OK;  // reinsertion.rs:43-45 (NaN ratio: `<=` is false in Rust; treated as no-op here)
     if (len == 1) return OBVHS_OK;                      // root is a leaf
-    if (bvh->max_depth > 96) {
-        OBVHS_SET_ERR(ctx, "reinsertion: max_depth %zu > 96 needs a heap stack (faststack.rs) -- not supported", bvh->max_depth);
-        return OBVHS_ERR_UNSUPPORTED;
-    }
-    if (!bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));  // init_parents_if_uninit
-    bvh->children_are_ordered_after_parents = false;                    // reinsertion.rs:93
+    ST_TRY(reinsertion_prologue(ctx, bvh));
     std::vector<float> default_seq;
     if (!seq) {
         for (int k = 1; k < 32; k += 2) default_seq.push_back(1.0f / (float)k);
         seq = default_seq.data();
         n_seq = default_seq.size();
+    }
+    if (n_seq > 60000) {
+        OBVHS_SET_ERR(ctx, "reinsertion: ratio sequence too long (%zu)", n_seq);
+        return OBVHS_ERR_UNSUPPORTED;
     }
     // reinsertion.rs:104-107 per round sizes
     std::vector<size_t> node_counts(n_seq);
@@ -333,79 +432,26 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
     }
     const size_t max_take = std::min(len, max_nc * 2), max_count = max_nc - 1;
     if (max_count == 0) return OBVHS_OK;
-    DevBuf<u32> ckeys, ckeys_alt, cvals, cvals_alt, r_from, r_to, gkeys, gkeys_alt, gvals, gvals_alt, cells, status, touched, mark, pending;
-    DevBuf<float> r_diff;
-    DevBuf<unsigned long long> reserve;
-    DevBuf<ReinsertState> st;
+    DevBuf<u32> ckeys, ckeys_alt, cvals, cvals_alt;
     CU_TRY(ctx, ckeys.alloc(max_take, s));
     CU_TRY(ctx, ckeys_alt.alloc(max_take, s));
     CU_TRY(ctx, cvals.alloc(max_take, s));
     CU_TRY(ctx, cvals_alt.alloc(max_take, s));
-    CU_TRY(ctx, r_from.alloc(max_count, s));
-    CU_TRY(ctx, r_to.alloc(max_count, s));
-    CU_TRY(ctx, r_diff.alloc(max_count, s));
-    CU_TRY(ctx, gkeys.alloc(max_count, s));
-    CU_TRY(ctx, gkeys_alt.alloc(max_count, s));
-    CU_TRY(ctx, gvals.alloc(max_count, s));
-    CU_TRY(ctx, gvals_alt.alloc(max_count, s));
-    CU_TRY(ctx, cells.alloc(max_count * 5, s));
-    CU_TRY(ctx, status.alloc(max_count, s));
-    CU_TRY(ctx, touched.alloc(len, s));
-    CU_TRY(ctx, mark.alloc(len, s));
-    CU_TRY(ctx, pending.alloc(len, s));
-    CU_TRY(ctx, reserve.alloc(len, s));
-    CU_TRY(ctx, st.alloc(1, s));
-    CU_TRY(ctx, cudaMemsetAsync(touched.p, 0, len * 4, s));
-    CU_TRY(ctx, cudaMemsetAsync(mark.p, 0, len * 4, s));
-    CU_TRY(ctx, cudaMemsetAsync(pending.p, 0, len * 4, s));
-    CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
-    CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
-    u32* h = reinterpret_cast<u32*>(ctx->pinned);
-    if (n_seq > 60000) {
-        OBVHS_SET_ERR(ctx, "reinsertion: ratio sequence too long (%zu)", n_seq);
-        return OBVHS_ERR_UNSUPPORTED;
-    }
-    int coop_blocks = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, RESOLVE_THREADS, 0));
-    coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
+    ReinsertRun run;
+    ST_TRY(run.init(ctx, bvh, max_count));
     for (size_t k = 0; k < n_seq; k++) {
         const size_t nc = node_counts[k];
         const u32 take = (u32)std::min(len, nc * 2), count = (u32)(nc - 1);
         if (count == 0 || take < 2) continue;
-        const u32 round_stamp = (u32)k + 1;
         const u32 m = take - 1;
-        TraceScope* tsp = new TraceScope(ctx, "  reins_candidates_sort");
-        cand_init_kernel<<<div_up(m, 256), 256, 0, s>>>(bvh->nodes, m, ckeys.p, cvals.p);
-        KERNEL_CHECK(ctx);
         u32 *sk, *cand_ids;
-        ST_TRY(radix_sort_pairs_u32(ctx, ckeys.p, ckeys_alt.p, cvals.p, cvals_alt.p, m, 4, &sk, &cand_ids));
-        delete tsp;
-        tsp = new TraceScope(ctx, "  reins_find");
-        find_reinsertion_kernel<<<div_up(count, 128), 128, 0, s>>>(bvh->nodes, bvh->parents, cand_ids, count, r_from.p, r_to.p, r_diff.p,
-                                                                  gkeys.p, gvals.p);
-        KERNEL_CHECK(ctx);
-        delete tsp;
-        tsp = new TraceScope(ctx, "  reins_gain_sort_resolve");
-        u32 *gk, *order;
-        ST_TRY(radix_sort_pairs_u32(ctx, gkeys.p, gkeys_alt.p, gvals.p, gvals_alt.p, count, 4, &gk, &order));
         {
-            ResolveArgs ra;
-            ra.order = order; ra.r_from = r_from.p; ra.r_to = r_to.p; ra.r_diff = r_diff.p; ra.count = count;
-            ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
-            ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
-            void* args[] = {&ra};
-            int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
-            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
+            TraceScope ts(ctx, "  reins_candidates_sort");
+            cand_init_kernel<<<div_up(m, 256), 256, 0, s>>>(bvh->nodes, m, ckeys.p, cvals.p);
             KERNEL_CHECK(ctx);
+            ST_TRY(radix_sort_pairs_u32(ctx, ckeys.p, ckeys_alt.p, cvals.p, cvals_alt.p, m, 4, &sk, &cand_ids));
         }
-        delete tsp;
+        ST_TRY(run.round(cand_ids, count, (u32)k + 1));
     }
-    CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaStreamSynchronize(s));
-    if (h[5]) {
-        OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
-        return OBVHS_ERR_CUDA;
-    }
-    if (applied_out) *applied_out = h[4];
-    return OBVHS_OK;
+    return run.finish(applied_out);
 }

@@ -731,6 +731,16 @@ struct ReinsertionOptimizer {
             applied++;
         }
     }
+    // reinsertion.rs:66-90, 113-118: the given ids, in the given order, are the candidates of every iteration
+    void run_with_candidates(OrcBvh2& bvh, const u32* ids, size_t n, u32 iterations) {
+        if (bvh.nodes.empty() || is_leaf(bvh.nodes[0])) return;
+        if (bvh.parents.empty()) compute_parents(bvh);
+        candidates.clear();
+        for (size_t i = 0; i < n; i++) candidates.push_back(Candidate{ids[i], half_area(bvh.nodes[ids[i]].aabb)});
+        touched.assign(bvh.nodes.size(), 0);
+        bvh.children_are_ordered_after_parents = false;
+        for (u32 k = 0; k < iterations; k++) optimize_candidates(bvh, candidates.size());
+    }
     // reinsertion.rs:40-57, 92-111
     void run(OrcBvh2& bvh, float ratio, const float* seq, size_t n_seq) {
         if (bvh.nodes.empty() || is_leaf(bvh.nodes[0]) || ratio <= 0.0f) return;
@@ -1491,6 +1501,12 @@ void orc_reinsertion_run(OrcBvh2* b, float ratio, const float* seq, size_t n_seq
     ReinsertionOptimizer opt;
     opt.threads = clamp_threads(threads);
     opt.run(*b, ratio, seq, n_seq);
+    b->last_applied = opt.applied;
+}
+void orc_reinsertion_run_with_candidates(OrcBvh2* b, const u32* ids, size_t n, u32 iterations, int threads) {
+    ReinsertionOptimizer opt;
+    opt.threads = clamp_threads(threads);
+    opt.run_with_candidates(*b, ids, n, iterations);
     b->last_applied = opt.applied;
 }
 size_t orc_reinsertion_last_applied(const OrcBvh2* b) { return b->last_applied; }

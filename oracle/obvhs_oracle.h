@@ -72,6 +72,7 @@ void     orc_bvh2_set_leaf_aabbs(OrcBvh2*, const OrcAabb* prim_aabbs);          
 /* -- reinsertion (bvh2/reinsertion.rs:40-382) --------------------------------------------------------- */
 void     orc_reinsertion_run(OrcBvh2*, float batch_size_ratio, const float* ratio_seq, size_t n_seq, int threads);
 /* one batch, exposing the intermediate products for stage-by-stage parity */
+void     orc_reinsertion_run_with_candidates(OrcBvh2*, const uint32_t* node_ids, size_t n, uint32_t iterations, int threads); /* reinsertion.rs:66-90 */
 size_t   orc_reinsertion_last_applied(const OrcBvh2*);
 
 /* -- BVH2 -> CWBVH (cwbvh/bvh2_to_cwbvh.rs:490-510) --------------------------------------------------- */

@@ -52,6 +52,7 @@ def lib():
             "orc_bvh2_refit_all": (None, [vp]),
             "orc_bvh2_set_leaf_aabbs": (None, [vp, vp]),
             "orc_reinsertion_run": (None, [vp, f32, vp, sz, i32]),
+            "orc_reinsertion_run_with_candidates": (None, [vp, vp, sz, u32, i32]),
             "orc_reinsertion_last_applied": (sz, [vp]),
             "orc_set_refit_full": (None, [i32]),
             "orc_bvh2_to_cwbvh": (vp, [vp, u32, i32, i32]),
@@ -161,6 +162,11 @@ class Bvh2:
         else:
             s = np.ascontiguousarray(seq, dtype=np.float32)
             lib().orc_reinsertion_run(self.h, ratio, _p(s), s.shape[0], threads)
+        return lib().orc_reinsertion_last_applied(self.h)
+
+    def reinsertion_run_with_candidates(self, node_ids, iterations, threads=1):
+        ids = np.ascontiguousarray(node_ids, dtype=np.uint32)
+        lib().orc_reinsertion_run_with_candidates(self.h, _p(ids), ids.shape[0], int(iterations), threads)
         return lib().orc_reinsertion_last_applied(self.h)
 
     def to_cwbvh(self, max_prims_per_leaf=3, order_children=True, include_exact=False):

@@ -179,6 +179,32 @@ def test_reinsertion_custom_sequence(api, scenes):
     assert_nodes_equal(got.download()[0], want.get()[0], "custom ratio sequence")
 
 
+@pytest.mark.parametrize("scene", ["terrain32", "kitchen"])
+def test_reinsertion_run_with_candidates(api, scenes, scene):
+    # ReinsertionOptimizer::run_with_candidates (reinsertion.rs:66-90): caller-chosen node ids, unsorted, with duplicates
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, 2, 64, 0)
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    rng = np.random.default_rng(11)
+    ids = rng.integers(1, wn.shape[0], size=min(3000, wn.shape[0]), dtype=np.uint32)
+    a_want = want.reinsertion_run_with_candidates(ids, 3)
+    opt = api.ReinsertionOptimizer()
+    a_got = opt.run_with_candidates(got, ids, 3)
+    assert a_got == a_want and a_got > 0
+    assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} run_with_candidates")
+    assert not got.children_are_ordered_after_parents
+    import torch
+
+    a_want = want.reinsertion_run_with_candidates(ids[::2], 1)
+    assert opt.run_with_candidates(got, torch.from_numpy(ids[::2].astype(np.int64)).to(torch.int32).cuda(), 1) == a_want  # device-resident ids
+    assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} run_with_candidates (device ids)")
+    with pytest.raises(api.ObvhsError):
+        opt.run_with_candidates(got, np.array([0], np.uint32), 1)  # the root cannot be reinserted (the reference asserts)
+    with pytest.raises(api.ObvhsError):
+        opt.run_with_candidates(got, np.array([wn.shape[0]], np.uint32), 1)
+
+
 @pytest.mark.parametrize("scene", SCENES)
 @pytest.mark.parametrize("max_prims,order", [(1, True), (3, True), (2, False)])
 def test_cwbvh_collapse_bytes(api, scenes, scene, max_prims, order):
@@ -206,8 +232,14 @@ def test_cwbvh_from_fresh_ploc_without_parents(api, scenes):
     assert np.array_equal(got[1], want[1])
 
 
+TRAVERSE_MODES = ["auto", "static", "persistent:8:32", "persistent:1:32", "persistent:32:64", "persistent:16:128"]
+
+
+@pytest.mark.parametrize("mode", TRAVERSE_MODES)
 @pytest.mark.parametrize("scene", SCENES)
-def test_traversal_hits_bit_exact(api, scenes, scene):
+def test_traversal_hits_bit_exact(api, scenes, scene, mode):
+    # every kernel variant (one ray per thread, persistent warps with ray refill, and the probe-driven choice between
+    # them) runs the reference's per-ray state machine: hits, distances AND the visit counters are identical
     tris = scenes[scene]
     c = ob.build_cwbvh_from_tris(tris, "fast_build")
     nodes, prims, total = c.get()
@@ -215,7 +247,7 @@ def test_traversal_hits_bit_exact(api, scenes, scene):
     rays = rays_for(tris)
     wc = np.zeros(2, np.uint64)
     want = c.ray_traverse(bt, rays, counters=wc)
-    g = api.CwBvh.upload(nodes, prims, total)
+    g = api.CwBvh.upload(nodes, prims, total, ctx=api.Context(0, traverse=mode))
     g.set_triangles(tris)
     gc = np.zeros(2, np.uint64)
     got = g.ray_traverse(rays, counters=gc)
@@ -374,3 +406,64 @@ def test_traversal_pinned_host_buffers_zero_copy(api, scenes):
     bvh.ray_traverse(d_rays, out=d_hits)
     bvh.ctx.synchronize()
     assert np.array_equal(d_hits.cpu().numpy().view(RAY_HIT).reshape(-1)["primitive_id"], want["primitive_id"])
+
+
+@pytest.mark.parametrize("n_side", [190, 301])
+def test_traversal_host_batches_are_pipelined_in_chunks(api, scenes, n_side):
+    # host ray batches >= 64 Ki rays take the chunked three-stream path (H2D | kernel | D2H overlapped): results must
+    # equal the single-launch device-resident path for closest hit, miss and all-hit counts, ragged tail included
+    import torch
+
+    tris = scenes["kitchen"]
+    bvh = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build())
+    rays = rays_for(tris, n_side=n_side)
+    assert rays.shape[0] >= 65536 and rays.shape[0] % 128 != 0
+    d_rays = torch.from_numpy(rays).cuda()
+    d_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32, device="cuda")
+    bvh.ray_traverse(d_rays, out=d_hits)
+    bvh.ctx.synchronize()
+    want = d_hits.cpu().numpy()
+    got = bvh.ray_traverse(rays)  # pageable host memory
+    assert np.array_equal(got["primitive_id"], want[:, 0].view(np.uint32))
+    assert np.array_equal(got["t"].view(np.uint32), want[:, 3].view(np.uint32))
+    from obvhs_b200.types import RAY_HIT
+
+    h_rays = torch.from_numpy(rays).pin_memory()
+    h_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32).pin_memory()
+    got = bvh.ray_traverse(h_rays.numpy(), out=h_hits.numpy().view(RAY_HIT).reshape(-1))
+    assert np.array_equal(h_hits.numpy(), want)
+    miss = bvh.ray_traverse_miss(rays)
+    assert np.array_equal(miss.astype(bool), want[:, 3].view(np.float32) >= F32_MAX)
+
+
+def displaced_aabbs(tris, frame):
+    """BASELINE config 5 / SURVEY.md 8(d) S4: every vertex moved by 0.01*(hash_noise-0.5) seeded by the frame."""
+    t = tris.reshape(-1, 3, 4).copy()
+    k = np.arange(t.shape[0] * 9, dtype=np.uint32)
+    noise = tu.hash_noise(k, np.uint32(frame), np.uint32(17)).reshape(-1, 3, 3)
+    t[:, :, 0:3] += (noise - np.float32(0.5)) * np.float32(0.01)
+    return ob.tri_aabbs(np.ascontiguousarray(t.reshape(-1, 12)))
+
+
+@pytest.mark.parametrize("scene", ["terrain32", "kitchen"])
+def test_dynamic_frames_refit_and_reinsertion(api, scenes, scene):
+    # config 5 (examples/physics.rs update loop): per frame rewrite leaf AABBs, refit_all (bvh2/mod.rs:527-569, both the
+    # ordered sweep and, after the first reinsertion, the unordered path), then ReinsertionOptimizer::run(0.01)
+    tris = scenes[scene]
+    aabbs = ob.tri_aabbs(tris)
+    want = ob.ploc_build(aabbs, None, 6, 64, 2)
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    opt = api.ReinsertionOptimizer()
+    for frame in range(4):
+        moved = displaced_aabbs(tris, frame)
+        want.set_leaf_aabbs(moved)
+        want.refit_all()
+        got.set_leaf_aabbs(moved)
+        assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} frame {frame} refit")
+        a_want = want.reinsertion_run(0.01)
+        a_got = opt.run(got, 0.01)
+        assert a_got == a_want
+        assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} frame {frame} reinsertion")
+        rc, msg = ob.bvh2_from(got.download()[0], wp, want.max_depth).validate(moved)
+        assert rc == 0, msg
