@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 nproc >> gpurun_out/smi.txt
-timeout -s KILL ${PYTEST_TIMEOUT:-1200} python -m pytest tests -m gpu -q --tb=short --maxfail=${MAXFAIL:-30} -p no:cacheprovider > gpurun_out/pytest.log 2>&1
+timeout -s KILL ${PYTEST_TIMEOUT:-1200} python -m pytest tests -m gpu -q --tb=short --maxfail=${MAXFAIL:-30} -p no:cacheprovider --timeout 300 > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest.log
 timeout -s KILL 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU regression: parity tests + stage traces
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -q --tb=short --maxfail=10 -p no:cacheprovider > gpurun_out/pytest.log 2>&1
+timeout -s KILL 900 python -m pytest tests -m gpu -q --tb=short --maxfail=10 -p no:cacheprovider --timeout 300 > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest.log
 tail -4 gpurun_out/pytest.log
 for w in ${WORKLOADS:-kitchen soup terrain}; do
