@@ -1250,6 +1250,249 @@ static void traverse_batch(const OrcCwBvh& bvh, const OrcTriangle* tris, const O
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// SAH leaf collapse (bvh2/leaf_collapser.rs:21-192)
+// ---------------------------------------------------------------------------------------------------------
+static void collapse(OrcBvh2& bvh, u32 max_prims, float traversal_cost) {
+    const size_t nodes_qty = bvh.nodes.size();
+    if (max_prims <= 1 || (u32)nodes_qty <= max_prims * 2 + 1) return;                                        // :25-27
+    if (!bvh.primitive_indices.empty() && (u32)bvh.primitive_indices.size() <= max_prims) return;            // :29-31
+    if (bvh.nodes.empty() || is_leaf(bvh.nodes[0])) return;                                                   // :33-35
+    const bool previously_had_parents = !bvh.parents.empty();
+    if (bvh.parents.empty()) compute_parents(bvh);
+    std::vector<u32> node_counts(nodes_qty, 1), prim_counts(nodes_qty, 0);
+    // bottom-up traversal (:48-87 + bottom_up_traverse :195-236): every inner node after both of its children
+    auto process = [&](bool leaf, size_t i) {
+        if (leaf) {
+            prim_counts[i] = bvh.nodes[i].prim_count;
+            return;
+        }
+        const OrcBvh2Node& node = bvh.nodes[i];
+        const size_t first_child = node.first_index;
+        const u32 left_count = prim_counts[first_child], right_count = prim_counts[first_child + 1];
+        const u32 total_count = left_count + right_count;
+        if (left_count > 0 && right_count > 0 && total_count <= max_prims) {
+            const OrcBvh2Node& left = bvh.nodes[first_child];
+            const OrcBvh2Node& right = bvh.nodes[first_child + 1];
+            const float collapse_cost = half_area(node.aabb) * ((float)total_count - traversal_cost);
+            const float base_cost = half_area(left.aabb) * (float)left_count + half_area(right.aabb) * (float)right_count;
+            const bool both_have_same_prim = (left.first_index == right.first_index) && total_count == 2;
+            if (collapse_cost <= base_cost || both_have_same_prim) {
+                prim_counts[i] = total_count;
+                prim_counts[first_child] = 0;
+                prim_counts[first_child + 1] = 0;
+                node_counts[first_child] = 0;
+                node_counts[first_child + 1] = 0;
+            }
+        }
+    };
+    {
+        std::vector<u8> flags(nodes_qty, 0);
+        for (size_t i = 1; i < nodes_qty; i++) {
+            if (!is_leaf(bvh.nodes[i])) continue;
+            process(true, i);
+            size_t j = i;
+            while (j != 0) {
+                j = bvh.parents[j];
+                u8 prev = flags[j];
+                flags[j] = (u8)std::min<int>(prev + 1, 255);
+                if (prev != 1) break;
+                flags[j] = 0;
+                process(false, j);
+            }
+        }
+    }
+    // inclusive prefix sums (:89-98)
+    for (size_t i = 1; i < nodes_qty; i++) {
+        node_counts[i] += node_counts[i - 1];
+        prim_counts[i] += prim_counts[i - 1];
+    }
+    std::vector<u32> indices_copy;
+    std::vector<OrcBvh2Node> nodes_copy;
+    const u32 node_count = node_counts[nodes_qty - 1];
+    const bool root_became_leaf = prim_counts[0] > 0;
+    if (root_became_leaf) {  // :104-110 (unreachable for trees whose leaves all hold >= 1 primitive; kept for fidelity)
+        bvh.nodes[0].first_index = 0;
+        bvh.nodes[0].prim_count = prim_counts[0];
+        std::swap(bvh.primitive_indices, indices_copy);
+        std::swap(bvh.nodes, nodes_copy);
+    } else {
+        nodes_copy.assign(node_count, OrcBvh2Node{});
+        indices_copy.assign(prim_counts[nodes_qty - 1], 0);
+        nodes_copy[0] = bvh.nodes[0];
+        nodes_copy[0].first_index = node_counts[nodes_copy[0].first_index - 1];
+    }
+    auto top_down = [&](size_t i) {  // :122-151: the primitives of the subtree of i, depth first, left to right
+        u32 first_prim = prim_counts[i - 1];
+        size_t j = i;
+        for (;;) {
+            const OrcBvh2Node node = bvh.nodes[j];
+            if (is_leaf(node)) {
+                for (u32 n = 0; n < node.prim_count; n++) indices_copy[first_prim + n] = bvh.primitive_indices[node.first_index + n];
+                first_prim += node.prim_count;
+                while (!(j % 2 == 1) && j != i) j = bvh.parents[j];  // !is_left_sibling(j)
+                if (j == i) break;
+                j = sibling_id(j);
+            } else {
+                j = node.first_index;
+            }
+        }
+    };
+    for (size_t i = 1; i < bvh.nodes.size(); i++) {  // :153-174 (bvh.nodes is empty here when the root became a leaf)
+        const size_t node_id = node_counts[i - 1];
+        if (node_id == node_counts[i]) continue;
+        nodes_copy[node_id] = bvh.nodes[i];
+        const u32 first_prim = prim_counts[i - 1];
+        if (first_prim == prim_counts[i]) {
+            nodes_copy[node_id].first_index = node_counts[nodes_copy[node_id].first_index - 1];
+        } else {
+            nodes_copy[node_id].prim_count = prim_counts[i] - first_prim;
+            nodes_copy[node_id].first_index = first_prim;
+            top_down(i);
+        }
+    }
+    std::swap(bvh.nodes, nodes_copy);
+    std::swap(bvh.primitive_indices, indices_copy);
+    if (previously_had_parents) compute_parents(bvh);  // update_parents (:183-186)
+    else bvh.parents.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bvh2 ray traversal (bvh2/mod.rs:148-334, aabb.rs:186-206)
+// ---------------------------------------------------------------------------------------------------------
+static inline float aabb_intersect_ray(const OrcAabb& a, const OrcRay& ray) {
+    float t1[3], t2[3], tmn[3], tmx[3];
+    for (int k = 0; k < 3; k++) {
+        t1[k] = (a.min[k] - ray.origin[k]) * ray.inv_direction[k];
+        t2[k] = (a.max[k] - ray.origin[k]) * ray.inv_direction[k];
+        tmn[k] = smin(t1[k], t2[k]);
+        tmx[k] = smax(t1[k], t2[k]);
+    }
+    // glam sse2 Vec3A::max_element / min_element: combine (x,z) and (y,z), then the two results
+    float tmin_n = smax(smax(tmn[0], tmn[2]), smax(tmn[1], tmn[2]));
+    float tmax_n = smin(smin(tmx[0], tmx[2]), smin(tmx[1], tmx[2]));
+    if (tmax_n >= tmin_n && tmax_n >= 0.0f) return tmin_n;
+    return INFINITY;
+}
+
+// MODE 0 closest hit (ray_traverse :148-172), 1 miss (:185-213), 2 counting any-hit (:225-238)
+template <int MODE>
+static inline void bvh2_traverse_one(const OrcBvh2& bvh, const OrcTriangle* tris, const OrcRay& ray_in, OrcRayHit* hit, u8* miss,
+                                     u32* anycount, u64& nodes_tested, u64& tris_tested) {
+    OrcRay ray = ray_in;
+    bool is_miss = true;
+    u32 count = 0;
+    // the leaf callback; returns false to halt the traversal
+    auto intersect_prims = [&](const OrcBvh2Node& node) -> bool {
+        for (u32 primitive_id = node.first_index; primitive_id < node.first_index + node.prim_count; primitive_id++) {
+            float t = tri_intersect(tris[primitive_id], ray);
+            tris_tested++;
+            if (MODE == 0) {
+                if (t < ray.tmax) {
+                    hit->primitive_id = primitive_id;
+                    hit->t = t;
+                    ray.tmax = t;
+                }
+            } else if (MODE == 1) {
+                if (t < ray.tmax) {
+                    is_miss = false;
+                    return false;
+                }
+            } else {
+                if (t < INFINITY) count++;
+            }
+        }
+        return true;
+    };
+    auto finish = [&]() {
+        if (MODE == 1) *miss = is_miss ? 1 : 0;
+        if (MODE == 2) *anycount = count;
+    };
+    // ray_traverse_dynamic :260-334
+    if (bvh.nodes.empty()) return finish();
+    const OrcBvh2Node& root = bvh.nodes[0];
+    nodes_tested++;
+    if (!(aabb_intersect_ray(root.aabb, ray) < ray.tmax)) return finish();
+    if (is_leaf(root)) {
+        intersect_prims(root);
+        return finish();
+    }
+    std::vector<u32> heap_stack;  // fast_stack!(u32, (96, 192), max_depth): saturating fixed stacks, heap beyond 192
+    const size_t cap = bvh.max_depth <= 96 ? 96 : (bvh.max_depth <= 192 ? 192 : 0);
+    u32 fixed[192];
+    size_t sp = 0;
+    u32 current = root.first_index;
+    for (;;) {
+        const OrcBvh2Node* left = &bvh.nodes[current];
+        const OrcBvh2Node* right = &bvh.nodes[(size_t)current + 1];
+        float left_t = aabb_intersect_ray(left->aabb, ray), right_t = aabb_intersect_ray(right->aabb, ray);
+        nodes_tested += 2;
+        if (left_t > right_t) {
+            std::swap(left_t, right_t);
+            std::swap(left, right);
+        }
+        const bool hit_left = left_t < ray.tmax;
+        bool go_left = hit_left;
+        if (hit_left && is_leaf(*left)) {
+            if (!intersect_prims(*left)) return finish();
+            go_left = false;
+        }
+        const bool hit_right = right_t < ray.tmax;
+        bool go_right = hit_right;
+        if (hit_right && is_leaf(*right)) {
+            if (!intersect_prims(*right)) return finish();
+            go_right = false;
+        }
+        if (go_left && go_right) {
+            current = left->first_index;
+            if (cap) {
+                fixed[sp] = right->first_index;
+                sp = std::min(sp + 1, cap - 1);
+            } else {
+                heap_stack.push_back(right->first_index);
+            }
+        } else if (go_left) {
+            current = left->first_index;
+        } else if (go_right) {
+            current = right->first_index;
+        } else {
+            if (cap ? sp == 0 : heap_stack.empty()) {
+                hit->t = ray.tmax;  // :326
+                return finish();
+            }
+            if (cap) current = fixed[--sp];
+            else {
+                current = heap_stack.back();
+                heap_stack.pop_back();
+            }
+        }
+    }
+}
+
+template <int MODE>
+static void bvh2_traverse_batch(const OrcBvh2& bvh, const OrcTriangle* tris, const OrcRay* rays, size_t n, OrcRayHit* hits, u8* miss,
+                                u32* counts, int threads, u64* counters) {
+    threads = clamp_threads(threads);
+    u64 nv = 0, tt = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 256) reduction(+ : nv, tt)
+    for (long i = 0; i < (long)n; i++) {
+        OrcRayHit h{0xffffffffu, 0xffffffffu, 0xffffffffu, INFINITY};
+        u8 m = 1;
+        u32 c = 0;
+        u64 a = 0, b = 0;
+        bvh2_traverse_one<MODE>(bvh, tris, rays[i], &h, &m, &c, a, b);
+        if (MODE == 0) hits[i] = h;
+        if (MODE == 1) miss[i] = m;
+        if (MODE == 2) counts[i] = c;
+        nv += a;
+        tt += b;
+    }
+    if (counters) {
+        counters[0] += nv;
+        counters[1] += tt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // validation (bvh2/mod.rs:786-981, cwbvh/mod.rs:747-908) -- invariants restated, not the stats
 // ---------------------------------------------------------------------------------------------------------
 #define VFAIL(code, ...)                     \
@@ -1264,7 +1507,11 @@ static int bvh2_validate(const OrcBvh2& bvh, const OrcAabb* prim_aabbs, size_t n
         if (!bvh.nodes.empty()) VFAIL(-1, "empty input but %zu nodes", bvh.nodes.size());
         return 0;
     }
-    if (bvh.nodes.size() != 2 * n - 1) VFAIL(-2, "node count %zu != 2n-1 (n=%zu)", bvh.nodes.size(), n);
+    {  // 2*leaves - 1 nodes; leaves == n unless leaves were collapsed (leaf_collapser.rs)
+        size_t leaves = 0;
+        for (const OrcBvh2Node& nd : bvh.nodes) leaves += is_leaf(nd) ? 1 : 0;
+        if (bvh.nodes.size() != 2 * leaves - 1 || leaves > n) VFAIL(-2, "node count %zu != 2*leaves-1 (leaves=%zu, n=%zu)", bvh.nodes.size(), leaves, n);
+    }
     if (bvh.primitive_indices.size() != n) VFAIL(-3, "primitive_indices len %zu != %zu", bvh.primitive_indices.size(), n);
     std::vector<u8> seen_node(bvh.nodes.size(), 0), seen_prim(n, 0);
     std::vector<std::pair<u32, u32>> stack;  // node, depth
@@ -1486,6 +1733,41 @@ int orc_bvh2_validate(const OrcBvh2* b, const OrcAabb* prim_aabbs, size_t n, int
     return bvh2_validate(*b, prim_aabbs, n, tight_fit != 0, msg);
 }
 void orc_bvh2_compute_parents(OrcBvh2* b) { compute_parents(*b); }
+void orc_bvh2_collapse(OrcBvh2* b, u32 max_prims, float traversal_cost) { collapse(*b, max_prims, traversal_cost); }
+int orc_bvh2_has_parents(const OrcBvh2* b) { return b->parents.empty() ? 0 : 1; }
+void orc_bvh2_ray_traverse(const OrcBvh2* b, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, OrcRayHit* hits, int threads,
+                           u64* counters) {
+    bvh2_traverse_batch<0>(*b, bvh_tris, rays, n, hits, nullptr, nullptr, threads, counters);
+}
+void orc_bvh2_ray_traverse_miss(const OrcBvh2* b, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, u8* miss, int threads,
+                                u64* counters) {
+    bvh2_traverse_batch<1>(*b, bvh_tris, rays, n, nullptr, miss, nullptr, threads, counters);
+}
+void orc_bvh2_ray_traverse_anyhit_count(const OrcBvh2* b, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, u32* counts,
+                                        int threads) {
+    bvh2_traverse_batch<2>(*b, bvh_tris, rays, n, nullptr, nullptr, counts, threads, nullptr);
+}
+// bvh2/builder.rs:17-91 (pre_split = false): PLOC -> reinsertion -> collapse -> reinsertion
+OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, u32 search_distance, size_t search_depth_threshold,
+                                  float reinsertion_batch_ratio, float post_collapse_multiplier, int precision, u32 max_prims_per_leaf,
+                                  float collapse_traversal_cost, int threads, double* core_seconds) {
+    threads = clamp_threads(threads);
+    std::vector<OrcAabb> aabbs(n);
+    std::vector<u32> indices(n);
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for num_threads(threads) if (n > 100000)
+    for (long i = 0; i < (long)n; i++) {
+        aabbs[i] = tri_aabb(tris[i]);
+        indices[i] = (u32)i;
+    }
+    OrcBvh2* bvh2 = orc_ploc_build(aabbs.data(), indices.data(), n, search_distance, precision, search_depth_threshold, threads);
+    orc_reinsertion_run(bvh2, reinsertion_batch_ratio, nullptr, 0, threads);
+    collapse(*bvh2, std::min<u32>(std::max<u32>(max_prims_per_leaf, 1), 255), collapse_traversal_cost);
+    orc_reinsertion_run(bvh2, reinsertion_batch_ratio * post_collapse_multiplier, nullptr, 0, threads);
+    auto t1 = std::chrono::steady_clock::now();
+    if (core_seconds) *core_seconds += std::chrono::duration<double>(t1 - t0).count();
+    return bvh2;
+}
 void orc_bvh2_refit_all(OrcBvh2* b) { refit_all(*b); }
 void orc_bvh2_set_leaf_aabbs(OrcBvh2* b, const OrcAabb* prim_aabbs) {
     for (auto& nd : b->nodes)

@@ -66,6 +66,8 @@ OrcBvh2* orc_bvh2_from(const OrcBvh2Node* nodes, size_t n_nodes, const uint32_t*
 /* returns 0 when valid, else a negative code; msg (>=256 B) receives a description (bvh2/mod.rs:786-981) */
 int      orc_bvh2_validate(const OrcBvh2*, const OrcAabb* prim_aabbs, size_t n, int tight_fit, char* msg);
 void     orc_bvh2_compute_parents(OrcBvh2*);                                            /* bvh2/mod.rs:586-619 */
+void     orc_bvh2_collapse(OrcBvh2*, uint32_t max_prims, float traversal_cost);             /* bvh2/leaf_collapser.rs:21-192 */
+int      orc_bvh2_has_parents(const OrcBvh2*);
 void     orc_bvh2_refit_all(OrcBvh2*);                                                  /* bvh2/mod.rs:527-569 */
 void     orc_bvh2_set_leaf_aabbs(OrcBvh2*, const OrcAabb* prim_aabbs);                  /* config 5 helper */
 
@@ -101,6 +103,18 @@ void orc_cwbvh_ray_traverse_miss(const OrcCwBvh*, const OrcTriangle* bvh_tris, c
 /* all-hit variant (cwbvh/mod.rs:233-245): counts intersections with t < +inf per ray */
 void orc_cwbvh_ray_traverse_anyhit_count(const OrcCwBvh*, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n,
                                          uint32_t* counts, int threads);
+/* Bvh2::ray_traverse / ray_traverse_miss / counting ray_traverse_anyhit (bvh2/mod.rs:148-334) over triangles permuted by
+ * primitive_indices; counters[0] += node AABB tests, counters[1] += triangle tests */
+void orc_bvh2_ray_traverse(const OrcBvh2*, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, OrcRayHit* hits, int threads,
+                           uint64_t* counters);
+void orc_bvh2_ray_traverse_miss(const OrcBvh2*, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, uint8_t* miss, int threads,
+                                uint64_t* counters);
+void orc_bvh2_ray_traverse_anyhit_count(const OrcBvh2*, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, uint32_t* counts,
+                                        int threads);
+/* build_bvh2_from_tris (bvh2/builder.rs:17-91) without pre-splits */
+OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, uint32_t search_distance, size_t search_depth_threshold,
+                                  float reinsertion_batch_ratio, float post_collapse_multiplier, int precision,
+                                  uint32_t max_prims_per_leaf, float collapse_traversal_cost, int threads, double* core_seconds);
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray);               /* triangle.rs:35-76 */
 void  orc_triangle_normal(const OrcTriangle* tri, float* out3);                         /* triangle.rs:20-24 */
 int   orc_max_threads(void);

@@ -50,6 +50,12 @@ def lib():
             "orc_bvh2_validate": (i32, [vp, vp, sz, i32, C.c_char_p]),
             "orc_bvh2_compute_parents": (None, [vp]),
             "orc_bvh2_refit_all": (None, [vp]),
+            "orc_bvh2_collapse": (None, [vp, u32, f32]),
+            "orc_bvh2_has_parents": (i32, [vp]),
+            "orc_bvh2_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, vp]),
+            "orc_bvh2_ray_traverse_miss": (None, [vp, vp, vp, sz, vp, i32, vp]),
+            "orc_bvh2_ray_traverse_anyhit_count": (None, [vp, vp, vp, sz, vp, i32]),
+            "orc_build_bvh2_from_tris": (vp, [vp, sz, u32, sz, f32, f32, i32, u32, f32, i32, vp]),
             "orc_bvh2_set_leaf_aabbs": (None, [vp, vp]),
             "orc_reinsertion_run": (None, [vp, f32, vp, sz, i32]),
             "orc_reinsertion_run_with_candidates": (None, [vp, vp, sz, u32, i32]),
@@ -169,6 +175,37 @@ class Bvh2:
         lib().orc_reinsertion_run_with_candidates(self.h, _p(ids), ids.shape[0], int(iterations), threads)
         return lib().orc_reinsertion_last_applied(self.h)
 
+    def collapse(self, max_prims, traversal_cost):
+        """bvh2/leaf_collapser.rs:21-192"""
+        lib().orc_bvh2_collapse(self.h, int(max_prims), float(traversal_cost))
+
+    @property
+    def has_parents(self):
+        return bool(lib().orc_bvh2_has_parents(self.h))
+
+    def bvh_tris(self, tris):
+        """tris[primitive_indices] (examples/demoscene.rs: triangles reordered so that hit.primitive_id indexes them)"""
+        _, prims = self.get()
+        return np.ascontiguousarray(_f32c(tris, 12)[prims])
+
+    def ray_traverse(self, bvh_tris, rays, threads=0, counters=None):
+        bvh_tris, rays = _f32c(bvh_tris, 12), _f32c(rays, 16)
+        hits = np.zeros(rays.shape[0], dtype=RAY_HIT)
+        lib().orc_bvh2_ray_traverse(self.h, _p(bvh_tris), _p(rays), rays.shape[0], _p(hits), threads, None if counters is None else _p(counters))
+        return hits
+
+    def ray_traverse_miss(self, bvh_tris, rays, threads=0, counters=None):
+        bvh_tris, rays = _f32c(bvh_tris, 12), _f32c(rays, 16)
+        miss = np.zeros(rays.shape[0], dtype=np.uint8)
+        lib().orc_bvh2_ray_traverse_miss(self.h, _p(bvh_tris), _p(rays), rays.shape[0], _p(miss), threads, None if counters is None else _p(counters))
+        return miss
+
+    def ray_traverse_anyhit_count(self, bvh_tris, rays, threads=0):
+        bvh_tris, rays = _f32c(bvh_tris, 12), _f32c(rays, 16)
+        counts = np.zeros(rays.shape[0], dtype=np.uint32)
+        lib().orc_bvh2_ray_traverse_anyhit_count(self.h, _p(bvh_tris), _p(rays), rays.shape[0], _p(counts), threads)
+        return counts
+
     def to_cwbvh(self, max_prims_per_leaf=3, order_children=True, include_exact=False):
         return CwBvh(lib().orc_bvh2_to_cwbvh(self.h, max_prims_per_leaf, int(order_children), int(include_exact)))
 
@@ -272,6 +309,25 @@ def build_cwbvh_from_tris(tris, preset="medium_build", threads=1):
     c = CwBvh(h)
     c.core_build_seconds = secs.value
     return c
+
+
+# (search distance, depth threshold, reinsertion ratio, post-collapse multiplier, precision, max prims/leaf, collapse cost)
+BVH2_PRESETS = {
+    "fastest_build": (1, 0, 0.0, 0.0, 64, 1, 1.0),
+    "very_fast_build": (1, 0, 0.01, 0.0, 64, 8, 3.0),
+    "fast_build": (6, 2, 0.02, 0.0, 64, 8, 3.0),
+    "medium_build": (14, 3, 0.05, 2.0, 64, 8, 3.0),
+}
+
+
+def build_bvh2_from_tris(tris, preset="medium_build", threads=1) -> Bvh2:
+    """bvh2/builder.rs:17-91 without pre-splits"""
+    tris = _f32c(tris, 12) if len(tris) else np.zeros((0, 12), np.float32)
+    sd, thr, ratio, mult, prec, mp, cost = BVH2_PRESETS[preset] if isinstance(preset, str) else preset
+    secs = C.c_double(0.0)
+    b = Bvh2(lib().orc_build_bvh2_from_tris(_p(tris), tris.shape[0], sd, thr, ratio, mult, prec, mp, cost, threads, C.byref(secs)))
+    b.core_build_seconds = secs.value
+    return b
 
 
 def triangle_normals(tris) -> np.ndarray:

@@ -1,0 +1,127 @@
+"""Pins the CPU oracle for the Bvh2 side of the path: SAH leaf collapse
+(bvh2/leaf_collapser.rs), build_bvh2_from_tris (bvh2/builder.rs:17-91) and Bvh2 ray traversal (bvh2/mod.rs:148-334).
+Known answers: the reference's own collapse test (leaf_collapser.rs:401-439: validate before/after, with and without
+parents), tests/mod.rs degenerate + varying-prim-count builds, and the kitchen golden hash of examples/obj_cwbvh.rs (the
+hash depends only on WHICH triangle every pixel sees, so any exact closest-hit traversal of any valid tree reproduces it).
+CPU only."""
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+from obvhs_b200 import camera, test_util as tu
+from obvhs_b200.types import make_rays
+
+from test_oracle_golden import shade_normals
+
+F32_MAX = np.float32(3.4028235e38)
+
+
+def test_collapse_reference_test():
+    # leaf_collapser.rs:401-439
+    tris = tu.demoscene(32, 0)
+    aabbs = ob.tri_aabbs(tris)
+    for with_parents in (False, True):
+        bvh = ob.ploc_build(aabbs, None, 2, 64, 1)
+        rc, msg = bvh.validate(aabbs, tight_fit=False)
+        assert rc == 0, msg
+        if with_parents:
+            bvh.compute_parents()
+        n_before = bvh.node_count
+        bvh.collapse(8, 1.0)
+        rc, msg = bvh.validate(aabbs, tight_fit=False)
+        assert rc == 0, msg
+        assert bvh.node_count < n_before and bvh.prim_count == tris.shape[0]
+        assert bvh.has_parents == with_parents  # :183-190 parents recomputed only if they existed
+        nodes, prims = bvh.get()
+        leaves = nodes[nodes["prim_count"] > 0]
+        assert leaves["prim_count"].max() <= 8 and int(leaves["prim_count"].sum()) == tris.shape[0]
+        assert np.array_equal(np.sort(prims), np.arange(tris.shape[0], dtype=np.uint32))
+
+
+def test_collapse_early_outs():
+    tris = tu.demoscene(8, 0)
+    aabbs = ob.tri_aabbs(tris)
+    bvh = ob.ploc_build(aabbs, None, 2, 64, 1)
+    n0 = bvh.get()[0].tobytes()
+    bvh.collapse(1, 1.0)  # max_prims <= 1 (:25)
+    assert bvh.get()[0].tobytes() == n0
+    bvh.collapse(200, 1.0)  # nodes <= 2*max_prims+1 (:25) / prims <= max_prims (:29)
+    assert bvh.get()[0].tobytes() == n0
+
+
+@pytest.mark.parametrize("preset", list(ob.BVH2_PRESETS))
+def test_kitchen_golden_hash_through_bvh2(kitchen_tris, preset):
+    rays = camera.primary_rays(camera.kitchen_camera(32))
+    b = ob.build_bvh2_from_tris(kitchen_tris, preset)
+    rc, msg = b.validate(ob.tri_aabbs(kitchen_tris), tight_fit=False)
+    assert rc == 0, msg
+    normals, hits = shade_normals(b, kitchen_tris, rays)
+    assert tu.hash_vec3a_vec(normals) == 1343358762
+    # the CwBvh built from the same triangles sees the same distances
+    c = ob.build_cwbvh_from_tris(kitchen_tris, preset)
+    ch = c.ray_traverse(c.bvh_tris(kitchen_tris), rays)
+    hit = ch["t"] < F32_MAX
+    assert np.array_equal(hits["t"][hit].view(np.uint32), ch["t"][hit].view(np.uint32))
+    # bvh2/mod.rs:326: a ray that runs out of stack without a hit leaves hit.t = ray.tmax (f32::MAX here), not +inf
+    assert np.all((hits["t"][~hit] == F32_MAX) | np.isinf(hits["t"][~hit]))
+
+
+def test_bvh2_degenerate_builds_never_hit():
+    # tests/mod.rs:35-88 (the Bvh2 flavours)
+    ray = make_rays(np.array([[0.0, 0.0, 1.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    inf = np.float32(np.inf)
+    mx = np.float32(3.4028235e38)
+    cases = {
+        "empty": np.array([[inf, inf, inf, 0, -inf, -inf, -inf, 0]], np.float32),
+        "inf": np.tile(np.array([[-inf, -inf, -inf, 0, inf, inf, inf, 0]], np.float32), (10, 1)),
+        "max": np.tile(np.array([[-mx, -mx, -mx, 0, mx, mx, mx, 0]], np.float32), (10, 1)),
+        "nothing": np.zeros((0, 8), np.float32),
+    }
+    for name, aabbs in cases.items():
+        for sd, thr, ratio, mult, prec, mp, cost in ob.BVH2_PRESETS.values():
+            b = ob.ploc_build(aabbs, None, sd, prec, thr)
+            b.reinsertion_run(ratio)
+            b.collapse(mp, cost)
+            b.reinsertion_run(ratio * mult)
+            # the closure of the reference test never reports a hit: traverse over triangles that cannot be hit
+            far = np.zeros((max(1, aabbs.shape[0]), 12), np.float32)
+            far[:, [0, 4, 8]] = 1e30
+            hits = b.ray_traverse(far, ray)
+            assert not (hits["t"][0] < np.inf), name
+
+
+def test_bvh2_varying_prim_counts_validate():
+    # tests/mod.rs:91-102
+    tris = tu.flat_plane(4)
+    while tris.shape[0] > 1:
+        tris = tris[:-1]
+        aabbs = ob.tri_aabbs(tris)
+        for preset in ob.BVH2_PRESETS:
+            b = ob.build_bvh2_from_tris(tris, preset)
+            rc, msg = b.validate(aabbs, tight_fit=False)
+            assert rc == 0, f"{tris.shape[0]} tris {preset}: {msg}"
+
+
+def test_bvh2_and_cwbvh_agree_on_incoherent_rays():
+    tris = tu.triangle_soup(4096, 3)
+    rng = np.random.default_rng(2)
+    o = rng.random((20000, 3), dtype=np.float32) * np.float32(1.4) - np.float32(0.2)
+    d = rng.standard_normal((20000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = make_rays(o, d.astype(np.float32), 0.0, np.inf)
+    b = ob.build_bvh2_from_tris(tris, "medium_build")
+    c = ob.build_cwbvh_from_tris(tris, "medium_build")
+    hb = b.ray_traverse(b.bvh_tris(tris), rays)
+    hc = c.ray_traverse(c.bvh_tris(tris), rays)
+    hit = hc["t"] < np.inf
+    assert hit.sum() > 1000
+    assert np.array_equal(hb["t"][hit].view(np.uint32), hc["t"][hit].view(np.uint32))
+    assert np.array_equal(np.isinf(hb["t"]), ~hit)  # tmax = inf: the no-hit value is ray.tmax = inf
+    _, pb = b.get()
+    _, pc, _ = c.get()
+    assert np.array_equal(pb[hb["primitive_id"][hit]], pc[hc["primitive_id"][hit]])  # same original triangle (no exact ties here)
+    # miss / any-hit flavours agree with the closest-hit result
+    srays = rays.copy()
+    srays[:, 13] = np.where(hit, hc["t"] * np.float32(1.001), np.float32(5.0))
+    assert np.array_equal(b.ray_traverse_miss(b.bvh_tris(tris), srays).astype(bool), ~hit)
+    assert np.array_equal(b.ray_traverse_anyhit_count(b.bvh_tris(tris), srays) > 0, hit)
