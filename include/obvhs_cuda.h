@@ -139,6 +139,26 @@ int obvhs_cuda_reinsertion_run(ObvhsContext* ctx, ObvhsBvh2* bvh, float batch_si
 int obvhs_cuda_reinsertion_run_with_candidates(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint32_t* node_ids, size_t n,
                                                uint32_t iterations, uint64_t* applied_out);
 
+/* collapse(&mut bvh, max_prims, traversal_cost) (bvh2/leaf_collapser.rs:21-192): SAH leaf collapse; nodes and
+ * primitive_indices are rewritten in the reference's order, parents are recomputed only if they existed. */
+int obvhs_cuda_bvh2_collapse(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t max_prims, float traversal_cost);
+/* build_bvh2_from_tris(triangles, config, core_build_time) (bvh2/builder.rs:17-91): PLOC -> reinsertion -> collapse ->
+ * reinsertion(ratio * post_collapse multiplier). The permuted triangles are attached to the result. */
+int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
+                                    double* core_build_seconds, ObvhsBvh2** out);
+/* bvh_tris[i] = tris[primitive_indices[i]] kept on the device inside the handle (examples/demoscene.rs:66-70) */
+int obvhs_cuda_bvh2_set_triangles(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* tris, size_t n);
+/* Batched Bvh2::ray_traverse / ray_traverse_miss / counting ray_traverse_anyhit over triangles (bvh2/mod.rs:148-334,
+ * aabb.rs:186-206, triangle.rs:35-76). hit.primitive_id indexes primitive_indices order; as in the reference a ray that
+ * exhausts its stack without a hit leaves hit.t = ray.tmax (bvh2/mod.rs:326), a ray that misses the root leaves +inf.
+ * counters (host or device, 2 x u64): [0] += node AABB tests, [1] += triangle tests. */
+int obvhs_cuda_bvh2_ray_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits);
+int obvhs_cuda_bvh2_ray_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, uint8_t* miss);
+int obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n,
+                                                    uint32_t* counts);
+int obvhs_cuda_bvh2_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n,
+                                               ObvhsRayHit* hits, uint64_t* counters);
+
 /* ---- CwBvh (src/cwbvh) ------------------------------------------------------------------------------------ */
 /* bvh2_to_cwbvh(&bvh2, max_prims_per_leaf, order_children, include_exact_node_aabbs) (bvh2_to_cwbvh.rs:490-510).
  * include_exact_node_aabbs must be 0. */

@@ -78,6 +78,13 @@ SIGNATURES = {
     "obvhs_cuda_bvh2_set_leaf_aabbs": (_i32, [_vp, _vp, _vp, _sz]),
     "obvhs_cuda_reinsertion_run": (_i32, [_vp, _vp, _f32, _vp, _sz, C.POINTER(_u64)]),
     "obvhs_cuda_reinsertion_run_with_candidates": (_i32, [_vp, _vp, _vp, _sz, _u32, C.POINTER(_u64)]),
+    "obvhs_cuda_bvh2_collapse": (_i32, [_vp, _vp, _u32, _f32]),
+    "obvhs_cuda_build_bvh2_from_tris": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
+    "obvhs_cuda_bvh2_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
+    "obvhs_cuda_bvh2_ray_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_ray_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "obvhs_cuda_bvh2_to_cwbvh": (_i32, [_vp, _vp, _u32, _i32, _i32, _PP]),
     "obvhs_cuda_build_cwbvh_from_tris": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
     "obvhs_cuda_cwbvh_free": (None, [_vp]),
@@ -291,6 +298,42 @@ class Bvh2:
         a = _as_f32(prim_aabbs, 8)
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_leaf_aabbs(self.ctx.h, self.h, _ptr(a), a.shape[0]))
 
+    def collapse(self, max_prims: int, traversal_cost: float):
+        """src/bvh2/leaf_collapser.rs:21 `collapse(bvh, max_prims, traversal_cost)`"""
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_collapse(self.ctx.h, self.h, int(max_prims), float(traversal_cost)))
+
+    def set_triangles(self, tris):
+        """Attach tris[primitive_indices] for ray traversal (examples/demoscene.rs:66-70)."""
+        t = _as_f32(tris, 12)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_triangles(self.ctx.h, self.h, _ptr(t), t.shape[0]))
+
+    def ray_traverse(self, rays, out=None, counters=None):
+        """Batched Bvh2::ray_traverse (src/bvh2/mod.rs:148-172); returns / fills a RAY_HIT array (or an (n,4) int32 device tensor)."""
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
+        if counters is None:
+            self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
+        else:
+            self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
+        return hits
+
+    def ray_traverse_miss(self, rays, out=None):
+        """src/bvh2/mod.rs:185-213"""
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        miss = out if out is not None else np.zeros(n, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_miss_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
+        return miss
+
+    def ray_traverse_anyhit_count(self, rays, out=None):
+        """src/bvh2/mod.rs:225-238 with a counting closure"""
+        r = _as_f32(rays, 16)
+        n = r.shape[0]
+        counts = out if out is not None else np.zeros(n, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(counts)))
+        return counts
+
 
 class PlocBuilder:
     """src/ploc/mod.rs:35-159. The context keeps the scratch the reference's builder keeps for reuse."""
@@ -460,6 +503,21 @@ def build_cwbvh_from_tris(triangles, config: BvhBuildParams, core_build_time: li
     h = C.c_void_p()
     ctx.check(ctx.lib.obvhs_cuda_build_cwbvh_from_tris(ctx.h, _ptr(t), t.shape[0], C.byref(params), C.byref(secs), C.byref(h)))
     bvh = CwBvh(ctx, h)
+    bvh.core_build_seconds = secs.value
+    if core_build_time is not None:
+        core_build_time[0] += secs.value
+    return bvh
+
+
+def build_bvh2_from_tris(triangles, config: BvhBuildParams, core_build_time: list | None = None, ctx: Context | None = None) -> Bvh2:
+    """src/bvh2/builder.rs:17-91 (no pre-splits). The result carries the permuted triangles and is ready to traverse."""
+    ctx = ctx or default_context()
+    t = _as_f32(triangles, 12)
+    secs = C.c_double(0.0)
+    params = config.to_c()
+    h = C.c_void_p()
+    ctx.check(ctx.lib.obvhs_cuda_build_bvh2_from_tris(ctx.h, _ptr(t), t.shape[0], C.byref(params), C.byref(secs), C.byref(h)))
+    bvh = Bvh2(ctx, h)
     bvh.core_build_seconds = secs.value
     if core_build_time is not None:
         core_build_time[0] += secs.value

@@ -366,6 +366,7 @@ void obvhs_cuda_bvh2_free(ObvhsBvh2* bvh) {
     obvhs_result_free(ctx, bvh->nodes);
     obvhs_result_free(ctx, bvh->primitive_indices);
     obvhs_result_free(ctx, bvh->parents);
+    obvhs_result_free(ctx, bvh->bvh_tris);
     delete bvh;
     obvhs_context_release(ctx);
 }
@@ -652,6 +653,8 @@ int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** pri
     return OBVHS_OK;
 }
 
+}  // extern "C"
+
 // Host-resident ray batches are pipelined in chunks over three streams: H2D of chunk k+1 (copy_in), traversal of chunk k
 // (the context's stream) and D2H of chunk k-1 (copy_out) run concurrently, so a batch costs about max(H2D, kernel, D2H)
 // instead of their sum (PCIe is full duplex). Letting the kernel read pinned host memory directly (zero-copy) measured
@@ -667,8 +670,10 @@ static int ensure_pipeline(ObvhsContext* ctx, size_t n_events) {
     return OBVHS_OK;
 }
 
-static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
-                           uint64_t* counters) {
+// `launch(d_rays, count, d_out, d_counters)` enqueues the traversal of a device-resident slice on ctx->stream
+template <class Launch>
+static int traverse_common(ObvhsContext* ctx, const void* bvh, const ObvhsRay* rays, size_t n, void* out, size_t out_elem, uint64_t* counters,
+                           Launch launch) {
     ARG_CHECK(ctx, bvh, "bvh is null");
     ARG_CHECK(ctx, n == 0 || (rays && out), "null rays/out");
     if (n == 0) return OBVHS_OK;
@@ -695,12 +700,12 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
     }
     const size_t MIN_CHUNK = 32768;
     if (rays_dev) {
-        ST_TRY(cwbvh_traverse_device(ctx, bvh, rays, n, mode, d_out, d_cnt));
+        ST_TRY(launch(rays, n, d_out, d_cnt));
         if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (n < 2 * MIN_CHUNK) {
         const ObvhsRay* d_rays = nullptr;
         ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
-        ST_TRY(cwbvh_traverse_device(ctx, bvh, d_rays, n, mode, d_out, d_cnt));
+        ST_TRY(launch(d_rays, n, d_out, d_cnt));
         if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
         CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
@@ -722,7 +727,7 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
             CU_TRY(ctx, cudaMemcpyAsync(st_rays.p + off, h_rays + off * sizeof(ObvhsRay), cnt * sizeof(ObvhsRay), cudaMemcpyHostToDevice, ctx->copy_in));
             CU_TRY(ctx, cudaEventRecord(e_in, ctx->copy_in));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
-            ST_TRY(cwbvh_traverse_device(ctx, bvh, st_rays.p + off, cnt, mode, (unsigned char*)d_out + off * out_elem, d_cnt));
+            ST_TRY(launch(st_rays.p + off, cnt, (unsigned char*)d_out + off * out_elem, d_cnt));
             if (!out_dev) {
                 CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
                 CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
@@ -741,24 +746,123 @@ static int traverse_common(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const Obvhs
     return OBVHS_OK;
 }
 
+static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
+                       uint64_t* counters) {
+    return traverse_common(ctx, bvh, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+        return cwbvh_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
+    });
+}
+extern "C" {
+
 int obvhs_cuda_cwbvh_ray_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits) {
     API_ENTER(ctx);
-    return traverse_common(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
+    return cw_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
 }
 int obvhs_cuda_cwbvh_ray_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, uint8_t* miss) {
     API_ENTER(ctx);
-    return traverse_common(ctx, bvh, rays, n, 1, miss, 1, nullptr);
+    return cw_traverse(ctx, bvh, rays, n, 1, miss, 1, nullptr);
 }
 int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
                                                      uint32_t* counts) {
     API_ENTER(ctx);
-    return traverse_common(ctx, bvh, rays, n, 2, counts, 4, nullptr);
+    return cw_traverse(ctx, bvh, rays, n, 2, counts, 4, nullptr);
 }
 int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits,
                                                 uint64_t* counters) {
     API_ENTER(ctx);
     ARG_CHECK(ctx, counters, "counters is null");
-    return traverse_common(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+    return cw_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+
+// ---- Bvh2 ray traversal, collapse, builder -----------------------------------------------
+static int b2_traverse(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
+                       uint64_t* counters) {
+    return traverse_common(ctx, bvh, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+        return bvh2_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
+    });
+}
+int obvhs_cuda_bvh2_ray_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
+}
+int obvhs_cuda_bvh2_ray_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, uint8_t* miss) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, rays, n, 1, miss, 1, nullptr);
+}
+int obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, uint32_t* counts) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, rays, n, 2, counts, 4, nullptr);
+}
+int obvhs_cuda_bvh2_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits,
+                                               uint64_t* counters) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, counters, "counters is null");
+    return b2_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+int obvhs_cuda_bvh2_set_triangles(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* tris, size_t n) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || tris), "null argument");
+    DevBuf<ObvhsTriangle> st;
+    const ObvhsTriangle* d = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st, &d));
+    ST_TRY(bvh2_permute_tris_device(ctx, bvh, d, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+int obvhs_cuda_bvh2_collapse(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t max_prims, float traversal_cost) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    if (bvh->bvh_tris) {  // primitive_indices is about to change: the permuted triangles would be stale
+        obvhs_result_free(bvh->owner, bvh->bvh_tris);
+        bvh->bvh_tris = nullptr;
+    }
+    return bvh2_collapse_device(ctx, bvh, max_prims, traversal_cost);
+}
+int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
+                                    double* core_build_seconds, ObvhsBvh2** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, params && out, "null argument");
+    ARG_CHECK(ctx, n == 0 || tris, "tris is null");
+    if (params->pre_split) {
+        OBVHS_SET_ERR(ctx, "pre_split (src/splits.rs) is outside the GPU hot path");
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    DevBuf<ObvhsTriangle> st_tris;
+    const ObvhsTriangle* d_tris = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));  // core_build_time: bvh2/builder.rs:41,60 .. 83
+    ObvhsBvh2* bvh2 = nullptr;
+    {
+        TraceScope ts(ctx, "build_ploc");
+        ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                                 (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    }
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }
+    } guard{bvh2};
+    {
+        TraceScope ts(ctx, "reinsertion_optimize");
+        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    }
+    u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 255 ? 255 : params->max_prims_per_leaf);  // builder.rs:75
+    ST_TRY(bvh2_collapse_device(ctx, bvh2, mp, params->collapse_traversal_cost));
+    {
+        TraceScope ts(ctx, "reinsertion_optimize (post collapse)");
+        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio * params->post_collapse_reinsertion_batch_ratio_multiplier,
+                                      nullptr, 0, nullptr));
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ST_TRY(bvh2_permute_tris_device(ctx, bvh2, d_tris, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (core_build_seconds) {
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *core_build_seconds += (double)ms * 1e-3;
+    }
+    guard.b = nullptr;
+    *out = bvh2;
+    return OBVHS_OK;
 }
 
 int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays) {

@@ -169,6 +169,7 @@ struct ObvhsBvh2 {
     Node32* nodes = nullptr;          // node_count
     u32* primitive_indices = nullptr;  // prim_count
     u32* parents = nullptr;            // node_count, or null when not computed (Bvh2::parents: Option)
+    ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices (for ray traversal), or null
     size_t node_count = 0, prim_count = 0;
     size_t max_depth = 96;  // bvh2/mod.rs:87 DEFAULT_MAX_STACK_DEPTH
     size_t ploc_iterations = 0;
@@ -289,6 +290,8 @@ int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals,
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents);
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+// collapse.cu
+int bvh2_collapse_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 max_prims, float traversal_cost);
 // reinsertion.cu
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);
 int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, size_t n, u32 iterations, u64* applied_out);
@@ -298,4 +301,6 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
 int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
                           u64* d_counters);
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters);
+int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris);
 int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays);

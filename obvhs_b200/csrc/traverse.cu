@@ -161,101 +161,236 @@ __global__ void __launch_bounds__(128) ray_coherence_kernel(const float4* __rest
     }
 }
 
-// ---- per-ray state machine shared by both kernels ---------------------------------------------------------------
+// ---- per-ray state machines ---------------------------------------------------------------------------------------
+// Both kernels below are generic over a TREE policy (CwTree, Bvh2Tree): State, stack element, begin(), step(), store().
 // MODE 0 closest hit -> ObvhsRayHit; 1 miss -> u8; 2 all-hit count -> u32
-struct TravState {
-    RayRegs r;
-    u32 oct_inv4;
-    u32 sp;
-    uint2 cur, prim;  // cwbvh/mod.rs:84-120 current_group / primitive_group
+struct RayResult {
     u32 hit_id;
     float hit_t;
     u32 count;
     bool is_miss;
 };
-
-__device__ __forceinline__ void trav_begin(TravState& st, const float4* __restrict__ rp, u32 root_group) {
+__device__ __forceinline__ void ray_load(RayRegs& r, const float4* __restrict__ rp) {
     float4 ro = __ldg(rp), rd = __ldg(rp + 1), ri = __ldg(rp + 2), rt = __ldg(rp + 3);
-    st.r = RayRegs{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ri.x, ri.y, ri.z, rt.x, rt.y};
-    // cwbvh/mod.rs:1001-1010
-    st.oct_inv4 = (st.r.dx < 0.0f ? 0u : 0x04040404u) | (st.r.dy < 0.0f ? 0u : 0x02020202u) | (st.r.dz < 0.0f ? 0u : 0x01010101u);
-    st.sp = 0;
-    st.cur = make_uint2(0u, root_group);  // cwbvh/mod.rs:146-165
-    st.prim = make_uint2(0u, 0u);
-    st.hit_id = 0xffffffffu;
-    st.hit_t = __int_as_float(0x7f800000);
-    st.count = 0;
-    st.is_miss = true;
+    r = RayRegs{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ri.x, ri.y, ri.z, rt.x, rt.y};
 }
-
-// One turn of the traverse! loop (traverse_macro.rs:59-126): drain the primitive group, test one node, pop when both groups
-// are empty. Returns true when the ray is done. The loop has ONE exit: in miss mode the first hit clears all pending work
-// (cwbvh/mod.rs:216-220 returns there) and the state machine runs out on its own. An early `break`/`goto` out of the
-// primitive loop made ptxas (12.9, sm_100a) share convergence-barrier registers between the primitive loop and the node
-// test, and the persistent kernel then dead-locked on scenes where lanes of one warp sat in both at once.
-template <int MODE, bool COUNT>
-__device__ __forceinline__ bool trav_step(TravState& st, uint2* __restrict__ stack, const uint4* __restrict__ nodes,
-                                          const float4* __restrict__ tris, u32 magic, u32& nodes_visited, u32& tris_tested) {
-    while (st.prim.y != 0) {  // traverse_macro.rs:64-72
-        u32 local = 31u - __clz(st.prim.y);
-        st.prim.y &= ~(1u << local);
-        u32 pid = st.prim.x + local;
-        float t = tri_intersect(tris, pid, st.r);
-        if (COUNT) tris_tested++;
-        if (MODE == 0) {
-            if (t < st.r.tmax) {  // cwbvh/mod.rs:184-189
-                st.hit_id = pid;
-                st.hit_t = t;
-                st.r.tmax = t;
-            }
-        } else if (MODE == 1) {
-            if (t < st.r.tmax) {
-                st.is_miss = false;
-                st.prim.y = 0;
-                st.cur.y = 0;
-                st.sp = 0;
-            }
-        } else {
-            if (t < __int_as_float(0x7f800000)) st.count++;
-        }
-    }
-    st.prim = make_uint2(0u, 0u);
-    if (st.cur.y & 0xff000000u) {  // traverse_macro.rs:76-103
-        u32 hits_imask = st.cur.y;
-        u32 child_index_offset = 31u - __clz(hits_imask);
-        u32 child_index_base = st.cur.x;
-        st.cur.y &= ~(1u << child_index_offset);
-        if (st.cur.y & 0xff000000u) {  // faststack.rs:299-303 saturating push
-            stack[st.sp] = st.cur;
-            st.sp = min(st.sp + 1u, 31u);
-        }
-        u32 slot_index = (child_index_offset - 24u) ^ (st.oct_inv4 & 0xffu);
-        u32 relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
-        const uint4* np = nodes + (size_t)(child_index_base + relative_index) * 5;
-        uint4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3), q4 = __ldg(np + 4);
-        if (COUNT) nodes_visited++;
-        u32 hitmask = node_intersect(q0, q1, q2, q3, q4, st.r, st.oct_inv4, magic);
-        st.cur.x = q1.x;                                   // child_base_idx
-        st.prim.x = q1.y;                                  // primitive_base_idx
-        st.cur.y = (hitmask & 0xff000000u) | (q0.w >> 24);  // | imask
-        st.prim.y = hitmask & 0x00ffffffu;
-    } else {
-        st.cur = make_uint2(0u, 0u);
-    }
-    if (st.prim.y == 0 && (st.cur.y & 0xff000000u) == 0) {  // traverse_macro.rs:112-123
-        if (st.sp == 0) return true;
-        st.sp--;
-        st.cur = stack[st.sp];
-    }
-    return false;
+__device__ __forceinline__ void result_reset(RayResult& o) {
+    o.hit_id = 0xffffffffu;  // RayHit::none(), ray.rs:74-83
+    o.hit_t = __int_as_float(0x7f800000);
+    o.count = 0;
+    o.is_miss = true;
 }
-
 template <int MODE>
-__device__ __forceinline__ void trav_store(const TravState& st, void* __restrict__ out, size_t i) {
-    if (MODE == 0) reinterpret_cast<uint4*>(out)[i] = make_uint4(st.hit_id, 0xffffffffu, 0xffffffffu, __float_as_uint(st.hit_t));
-    else if (MODE == 1) reinterpret_cast<u8*>(out)[i] = st.is_miss ? 1 : 0;
-    else reinterpret_cast<u32*>(out)[i] = st.count;
+__device__ __forceinline__ void result_store(const RayResult& o, void* __restrict__ out, size_t i) {
+    if (MODE == 0) reinterpret_cast<uint4*>(out)[i] = make_uint4(o.hit_id, 0xffffffffu, 0xffffffffu, __float_as_uint(o.hit_t));
+    else if (MODE == 1) reinterpret_cast<u8*>(out)[i] = o.is_miss ? 1 : 0;
+    else reinterpret_cast<u32*>(out)[i] = o.count;
 }
+
+// CwBvh: cwbvh/mod.rs:169-245 + traverse_macro.rs:59-126
+struct CwTree {
+    const uint4* nodes;
+    const float4* tris;
+    u32 root_group;  // 0x80000000, or 0 for an empty tree (cwbvh/mod.rs:147-151)
+    u32 magic;       // 0x4B000000 (see byte_f)
+    typedef uint2 StackT;
+    static constexpr int STACK = 32;  // StackStack<UVec2, 32>, cwbvh/mod.rs:60
+    struct State {
+        RayRegs r;
+        u32 oct_inv4;
+        u32 sp;
+        uint2 cur, prim;  // cwbvh/mod.rs:84-120 current_group / primitive_group
+        RayResult o;
+    };
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rp) const {
+        ray_load(st.r, rp);
+        // cwbvh/mod.rs:1001-1010
+        st.oct_inv4 = (st.r.dx < 0.0f ? 0u : 0x04040404u) | (st.r.dy < 0.0f ? 0u : 0x02020202u) | (st.r.dz < 0.0f ? 0u : 0x01010101u);
+        st.sp = 0;
+        st.cur = make_uint2(0u, root_group);  // cwbvh/mod.rs:146-165
+        st.prim = make_uint2(0u, 0u);
+        result_reset(st.o);
+    }
+    // One turn of the traverse! loop (traverse_macro.rs:59-126): drain the primitive group, test one node, pop when both
+    // groups are empty. Returns true when the ray is done. The loop has ONE exit: in miss mode the first hit clears all
+    // pending work (cwbvh/mod.rs:216-220 returns there) and the state machine runs out on its own. An early `break`/`goto`
+    // out of the primitive loop made ptxas (12.9, sm_100a) share convergence-barrier registers between the primitive loop
+    // and the node test, and the persistent kernel then dead-locked on scenes where lanes of one warp sat in both at once.
+    template <int MODE, bool COUNT>
+    __device__ __forceinline__ bool step(State& st, uint2* __restrict__ stack, u32& nodes_visited, u32& tris_tested) const {
+        while (st.prim.y != 0) {  // traverse_macro.rs:64-72
+            u32 local = 31u - __clz(st.prim.y);
+            st.prim.y &= ~(1u << local);
+            u32 pid = st.prim.x + local;
+            float t = tri_intersect(tris, pid, st.r);
+            if (COUNT) tris_tested++;
+            if (MODE == 0) {
+                if (t < st.r.tmax) {  // cwbvh/mod.rs:184-189
+                    st.o.hit_id = pid;
+                    st.o.hit_t = t;
+                    st.r.tmax = t;
+                }
+            } else if (MODE == 1) {
+                if (t < st.r.tmax) {
+                    st.o.is_miss = false;
+                    st.prim.y = 0;
+                    st.cur.y = 0;
+                    st.sp = 0;
+                }
+            } else {
+                if (t < __int_as_float(0x7f800000)) st.o.count++;
+            }
+        }
+        st.prim = make_uint2(0u, 0u);
+        if (st.cur.y & 0xff000000u) {  // traverse_macro.rs:76-103
+            u32 hits_imask = st.cur.y;
+            u32 child_index_offset = 31u - __clz(hits_imask);
+            u32 child_index_base = st.cur.x;
+            st.cur.y &= ~(1u << child_index_offset);
+            if (st.cur.y & 0xff000000u) {  // faststack.rs:299-303 saturating push
+                stack[st.sp] = st.cur;
+                st.sp = min(st.sp + 1u, 31u);
+            }
+            u32 slot_index = (child_index_offset - 24u) ^ (st.oct_inv4 & 0xffu);
+            u32 relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+            const uint4* np = nodes + (size_t)(child_index_base + relative_index) * 5;
+            uint4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3), q4 = __ldg(np + 4);
+            if (COUNT) nodes_visited++;
+            u32 hitmask = node_intersect(q0, q1, q2, q3, q4, st.r, st.oct_inv4, magic);
+            st.cur.x = q1.x;                                   // child_base_idx
+            st.prim.x = q1.y;                                  // primitive_base_idx
+            st.cur.y = (hitmask & 0xff000000u) | (q0.w >> 24);  // | imask
+            st.prim.y = hitmask & 0x00ffffffu;
+        } else {
+            st.cur = make_uint2(0u, 0u);
+        }
+        if (st.prim.y == 0 && (st.cur.y & 0xff000000u) == 0) {  // traverse_macro.rs:112-123
+            if (st.sp == 0) return true;
+            st.sp--;
+            st.cur = stack[st.sp];
+        }
+        return false;
+    }
+};
+
+// Bvh2: bvh2/mod.rs:148-334 (ray_traverse / ray_traverse_miss / ray_traverse_anyhit over ray_traverse_dynamic), node AABB test
+// aabb.rs:186-206. Nodes are the 32-byte device layout; a sibling pair is 64 contiguous bytes (4 x 16-byte loads).
+// CAP is the reference's fixed stack size: fast_stack!(u32, (96, 192), max_depth) -> StackStack<u32, 96 | 192>.
+template <int CAP>
+struct Bvh2Tree {
+    const float4* nodes;
+    const float4* tris;
+    u32 node_count;
+    typedef u32 StackT;
+    static constexpr int STACK = CAP;
+    static constexpr u32 AT_ROOT = 0xffffffffu;
+    struct State {
+        RayRegs r;
+        u32 cur;  // left child of the pair to test next, or AT_ROOT before the root test
+        u32 sp;
+        RayResult o;
+    };
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rp) const {
+        ray_load(st.r, rp);
+        st.cur = AT_ROOT;
+        st.sp = 0;
+        result_reset(st.o);
+    }
+    // aabb.rs:186-206; glam sse2 min/max (a<b?a:b) and max_element/min_element pairing (x,z),(y,z)
+    static __device__ __forceinline__ float box_t(const float4 lo, const float4 hi, const RayRegs& r) {
+        float t1x = (lo.x - r.ox) * r.ix, t1y = (lo.y - r.oy) * r.iy, t1z = (lo.z - r.oz) * r.iz;
+        float t2x = (hi.x - r.ox) * r.ix, t2y = (hi.y - r.oy) * r.iy, t2z = (hi.z - r.oz) * r.iz;
+        float mnx = smin(t1x, t2x), mny = smin(t1y, t2y), mnz = smin(t1z, t2z);
+        float mxx = smax(t1x, t2x), mxy = smax(t1y, t2y), mxz = smax(t1z, t2z);
+        float tmin_n = smax(smax(mnx, mnz), smax(mny, mnz));
+        float tmax_n = smin(smin(mxx, mxz), smin(mxy, mxz));
+        return (tmax_n >= tmin_n && tmax_n >= 0.0f) ? tmin_n : __int_as_float(0x7f800000);
+    }
+    // the leaf callbacks of bvh2/mod.rs:155-165, 191-200, 226-231. Returns false when the traversal must halt (miss mode).
+    template <int MODE, bool COUNT>
+    __device__ __forceinline__ bool leaf(State& st, u32 first, u32 count, u32& tris_tested) const {
+        bool go_on = true;
+        for (u32 k = 0; k < count; k++) {
+            const u32 pid = first + k;
+            float t = tri_intersect(tris, pid, st.r);
+            if (COUNT) tris_tested++;
+            if (MODE == 0) {
+                if (t < st.r.tmax) {
+                    st.o.hit_id = pid;
+                    st.o.hit_t = t;
+                    st.r.tmax = t;
+                }
+            } else if (MODE == 1) {
+                if (t < st.r.tmax) {
+                    st.o.is_miss = false;
+                    go_on = false;
+                    count = 0;  // single loop exit (see CwTree::step)
+                }
+            } else {
+                if (t < __int_as_float(0x7f800000)) st.o.count++;
+            }
+        }
+        return go_on;
+    }
+    // one iteration of ray_traverse_dynamic's loop (:284-331); the first call performs the root test (:273-282)
+    template <int MODE, bool COUNT>
+    __device__ __forceinline__ bool step(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
+        bool done = false;
+        if (st.cur == AT_ROOT) {
+            if (node_count == 0) return true;
+            const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
+            if (COUNT) nodes_tested++;
+            const u32 prim_count = __float_as_uint(lo.w), first_index = __float_as_uint(hi.w);
+            if (!(box_t(lo, hi, st.r) < st.r.tmax)) done = true;
+            else if (prim_count != 0) {
+                leaf<MODE, COUNT>(st, first_index, prim_count, tris_tested);
+                done = true;
+            } else st.cur = first_index;
+            return done;
+        }
+        const float4* np = nodes + (size_t)st.cur * 2;
+        float4 llo = __ldg(np), lhi = __ldg(np + 1), rlo = __ldg(np + 2), rhi = __ldg(np + 3);
+        if (COUNT) nodes_tested += 2;
+        float left_t = box_t(llo, lhi, st.r), right_t = box_t(rlo, rhi, st.r);
+        u32 l_count = __float_as_uint(llo.w), l_first = __float_as_uint(lhi.w);
+        u32 r_count = __float_as_uint(rlo.w), r_first = __float_as_uint(rhi.w);
+        if (left_t > right_t) {  // :294-297
+            float tf = left_t; left_t = right_t; right_t = tf;
+            u32 tu = l_count; l_count = r_count; r_count = tu;
+            tu = l_first; l_first = r_first; r_first = tu;
+        }
+        const bool hit_left = left_t < st.r.tmax;
+        bool go_left = hit_left;
+        if (hit_left && l_count != 0) {
+            done = !leaf<MODE, COUNT>(st, l_first, l_count, tris_tested);
+            go_left = false;
+        }
+        const bool hit_right = !done && right_t < st.r.tmax;  // ray.tmax may have shrunk in the left leaf (:310)
+        bool go_right = hit_right;
+        if (hit_right && r_count != 0) {
+            done = !leaf<MODE, COUNT>(st, r_first, r_count, tris_tested);
+            go_right = false;
+        }
+        if (done) return true;
+        if (go_left) {
+            st.cur = l_first;
+            if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
+                stack[st.sp] = r_first;
+                st.sp = min(st.sp + 1u, (u32)(CAP - 1));
+            }
+        } else if (go_right) {
+            st.cur = r_first;
+        } else {
+            if (st.sp == 0) {
+                st.o.hit_t = st.r.tmax;  // :326 `hit.t = ray.tmax`
+                return true;
+            }
+            st.sp--;
+            st.cur = stack[st.sp];
+        }
+        return false;
+    }
+};
 
 template <bool COUNT>
 __device__ __forceinline__ void trav_flush_counters(unsigned long long* __restrict__ counters, u32 nodes_visited, u32 tris_tested) {
@@ -273,21 +408,19 @@ __device__ __forceinline__ void trav_flush_counters(unsigned long long* __restri
 }
 
 // One ray per thread: the fastest form for coherent batches (primary / shadow rays of neighbouring pixels).
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) traverse_kernel(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                       const float4* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                       unsigned long long* __restrict__ counters, u32 root_group, u32 magic,
-                                                       const u32* __restrict__ probe) {
+template <class Tree, int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                       unsigned long long* __restrict__ counters, const u32* __restrict__ probe) {
     if (probe && !probe_says_coherent(probe)) return;  // auto mode: the persistent kernel handles this batch
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 nodes_visited = 0, tris_tested = 0;
     if (i < n) {
-        TravState st;
-        uint2 stack[32];
-        trav_begin(st, rays + i * 4, root_group);
-        while (!trav_step<MODE, COUNT>(st, stack, nodes, tris, magic, nodes_visited, tris_tested)) {
+        typename Tree::State st;
+        typename Tree::StackT stack[Tree::STACK];
+        tree.begin(st, rays + i * 4);
+        while (!tree.template step<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
         }
-        trav_store<MODE>(st, out, i);
+        result_store<MODE>(st.o, out, i);
     }
     trav_flush_counters<COUNT>(counters, nodes_visited, tris_tested);
 }
@@ -297,19 +430,18 @@ __global__ void __launch_bounds__(128) traverse_kernel(const uint4* __restrict__
 // instead of idling until its longest ray ends (measured on the 10M-triangle soup with the one-ray-per-thread kernel:
 // 5.8 of 32 lanes active per issued instruction, issue slots 75 % busy -- divergence-bound, not memory-bound). Every ray
 // still runs the reference's exact per-ray state machine, so results and counters are identical to traverse_kernel's.
-template <int MODE, bool COUNT, int REFILL>
-__global__ void __launch_bounds__(128) traverse_persistent_kernel(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                                  const float4* __restrict__ rays, u32 n, void* __restrict__ out,
-                                                                  unsigned long long* __restrict__ counters, u32 root_group, u32 magic,
-                                                                  u32* __restrict__ next_ray, u32 chunk, const u32* __restrict__ probe) {
+template <class Tree, int MODE, bool COUNT, int REFILL>
+__global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n, void* __restrict__ out,
+                                                                  unsigned long long* __restrict__ counters, u32* __restrict__ next_ray, u32 chunk,
+                                                                  const u32* __restrict__ probe) {
     if (probe && probe_says_coherent(probe)) return;  // auto mode: the one-ray-per-thread kernel handles this batch
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
     u32 nodes_visited = 0, tris_tested = 0;
     bool active = false, exhausted = false;
     u32 my = 0;
-    TravState st = {};
-    uint2 stack[32];
+    typename Tree::State st = {};
+    typename Tree::StackT stack[Tree::STACK];
     // the warp owns [chunk_pos, chunk_end): consecutive rays, so refills stay close to the rays still in flight
     u32 chunk_pos = 0, chunk_end = 0;  // (n + warps * chunk < 2^32: the host splits larger batches)
     for (;;) {
@@ -328,7 +460,7 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const uint4* _
                 const u32 rank = __popc(idle & lt_mask);
                 if (rank < take) {
                     my = chunk_pos + rank;
-                    trav_begin(st, rays + (size_t)my * 4, root_group);
+                    tree.begin(st, rays + (size_t)my * 4);
                     active = true;
                 }
             }
@@ -337,8 +469,8 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const uint4* _
         if (!__any_sync(0xffffffffu, active)) break;
         const u32 min_active = (exhausted && chunk_pos == chunk_end) ? 1u : (u32)(33 - REFILL);
         do {
-            if (active && trav_step<MODE, COUNT>(st, stack, nodes, tris, magic, nodes_visited, tris_tested)) {
-                trav_store<MODE>(st, out, my);
+            if (active && tree.template step<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
+                result_store<MODE>(st.o, out, my);
                 active = false;
             }
         } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
@@ -374,56 +506,67 @@ __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float t
 
 }  // namespace
 
-template <int MODE, bool COUNT, int REFILL>
-static int launch_persistent_t(ObvhsContext* ctx, const uint4* nodes, const float4* tris, const float4* rays, size_t n, void* d_out,
-                               unsigned long long* c, u32 root_group, u32* next, const u32* probe) {
+template <class Tree, int MODE, bool COUNT, int REFILL>
+static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, void* d_out, unsigned long long* c, u32* next,
+                               const u32* probe) {
     int per_sm = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<MODE, COUNT, REFILL>, 128, 0));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL>, 128, 0));
     if (per_sm < 1) per_sm = 1;
     size_t blocks = (size_t)ctx->sm_count * per_sm, need = (n + 127) / 128;
     if (blocks > need) blocks = need;
-    traverse_persistent_kernel<MODE, COUNT, REFILL><<<(unsigned)blocks, 128, 0, ctx->stream>>>(nodes, tris, rays, (u32)n, d_out, c, root_group, 0x4B000000u, next,
-                                                                                              (u32)ctx->traverse_chunk, probe);
+    traverse_persistent_kernel<Tree, MODE, COUNT, REFILL><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
+                                                                                                      (u32)ctx->traverse_chunk, probe);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
-template <int REFILL>
-static int launch_persistent_r(ObvhsContext* ctx, const uint4* nodes, const float4* tris, const float4* rays, size_t n, int mode, void* d_out,
-                               unsigned long long* c, u32 root_group, u32* next, const u32* probe) {
+template <class Tree, int REFILL>
+static int launch_persistent_r(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
+                               u32* next, const u32* probe) {
     if (c) {
-        if (mode == 0) return launch_persistent_t<0, true, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
-        if (mode == 1) return launch_persistent_t<1, true, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
-        return launch_persistent_t<2, true, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
+        if (mode == 0) return launch_persistent_t<Tree, 0, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+        if (mode == 1) return launch_persistent_t<Tree, 1, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+        return launch_persistent_t<Tree, 2, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
     }
-    if (mode == 0) return launch_persistent_t<0, false, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
-    if (mode == 1) return launch_persistent_t<1, false, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
-    return launch_persistent_t<2, false, REFILL>(ctx, nodes, tris, rays, n, d_out, c, root_group, next, probe);
+    if (mode == 0) return launch_persistent_t<Tree, 0, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+    if (mode == 1) return launch_persistent_t<Tree, 1, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+    return launch_persistent_t<Tree, 2, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
 }
-static int launch_persistent(ObvhsContext* ctx, const uint4* nodes, const float4* tris, const float4* rays, size_t n, int mode, void* d_out,
-                             unsigned long long* c, u32 root_group, u32* next, const u32* probe) {
+template <class Tree>
+static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
+                             u32* next, const u32* probe) {
     switch (ctx->traverse_refill) {
-        case 1: return launch_persistent_r<1>(ctx, nodes, tris, rays, n, mode, d_out, c, root_group, next, probe);
-        case 4: return launch_persistent_r<4>(ctx, nodes, tris, rays, n, mode, d_out, c, root_group, next, probe);
-        case 16: return launch_persistent_r<16>(ctx, nodes, tris, rays, n, mode, d_out, c, root_group, next, probe);
-        case 32: return launch_persistent_r<32>(ctx, nodes, tris, rays, n, mode, d_out, c, root_group, next, probe);
-        default: return launch_persistent_r<8>(ctx, nodes, tris, rays, n, mode, d_out, c, root_group, next, probe);
+        case 1: return launch_persistent_r<Tree, 1>(ctx, tree, rays, n, mode, d_out, c, next, probe);
+        case 4: return launch_persistent_r<Tree, 4>(ctx, tree, rays, n, mode, d_out, c, next, probe);
+        case 16: return launch_persistent_r<Tree, 16>(ctx, tree, rays, n, mode, d_out, c, next, probe);
+        case 32: return launch_persistent_r<Tree, 32>(ctx, tree, rays, n, mode, d_out, c, next, probe);
+        default: return launch_persistent_r<Tree, 8>(ctx, tree, rays, n, mode, d_out, c, next, probe);
     }
+}
+template <class Tree>
+static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
+                         const u32* probe) {
+    dim3 block(128), grid(div_up(n, 128));
+    cudaStream_t s = ctx->stream;
+    if (c) {
+        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+    } else {
+        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+    }
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
 }
 
-int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
-                          u64* d_counters) {
-    if (n == 0) return OBVHS_OK;
-    if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
-        OBVHS_SET_ERR(ctx, "CwBvh has no triangles attached (call obvhs_cuda_cwbvh_set_triangles)");
-        return OBVHS_ERR_INVALID_ARG;
-    }
-    const uint4* nodes = reinterpret_cast<const uint4*>(bvh->nodes);
-    const float4* tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
-    const float4* rays = reinterpret_cast<const float4*>(d_rays);
-    u32 root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
+// Kernel choice shared by both tree types. ctx->traverse_mode: 0 static (one ray per thread), 1 persistent refill, 2 auto
+// (a probe of the batch decides on the device; small batches are static).
+template <class Tree>
+static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, const float4* rays, size_t n, int mode,
+                             void* d_out, u64* d_counters) {
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
-    // mode: 0 static (one ray per thread), 1 persistent refill, 2 auto (probe decides on the device; small batches static)
     int tm = ctx->traverse_mode;
     if (tm == 2 && n < 16384) tm = 0;
     // 32-bit ray indices inside the persistent kernel: batches beyond 2^31 rays are split into several launches
@@ -433,14 +576,14 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
     DevBuf<u32> scratch;  // [0..1] probe votes, [2..] one ray cursor per persistent launch
     u32* probe = nullptr;
     if (tm != 0) {
-        CU_TRY(ctx, scratch.alloc(2 + n_launches + 8, s));
-        CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, (2 + n_launches + 8) * sizeof(u32), s));
+        CU_TRY(ctx, scratch.alloc(2 + n_launches, s));
+        CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, (2 + n_launches) * sizeof(u32), s));
     }
     if (tm == 2) {
         probe = scratch.p;
         const size_t n_groups = n / 32, stride = n_groups > 1024 ? n_groups / 1024 : 1, sampled = (n_groups + stride - 1) / stride;
-        const float dx = bvh->total_aabb.max[0] - bvh->total_aabb.min[0], dy = bvh->total_aabb.max[1] - bvh->total_aabb.min[1],
-                    dz = bvh->total_aabb.max[2] - bvh->total_aabb.min[2];
+        const float dx = total_aabb.max[0] - total_aabb.min[0], dy = total_aabb.max[1] - total_aabb.min[1],
+                    dz = total_aabb.max[2] - total_aabb.min[2];
         float diag2 = dx * dx + dy * dy + dz * dz;
         if (!(diag2 > 0.0f) || !(diag2 < 3.0e38f)) diag2 = 3.0e38f;  // unknown scene extent (uploaded tree): directions decide
         ray_coherence_kernel<<<div_up(sampled, 4), 128, 0, s>>>(rays, n_groups, stride, diag2 * 0.0004f, probe);
@@ -449,20 +592,60 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
     if (tm != 0) {
         for (size_t l = 0; l < n_launches; l++) {
             const size_t off = l * MAX_LAUNCH, cnt = n - off < MAX_LAUNCH ? n - off : MAX_LAUNCH;
-            ST_TRY(launch_persistent(ctx, nodes, tris, rays + off * 4, cnt, mode, (char*)d_out + off * out_elem, c, root_group, scratch.p + 2 + l, probe));
+            ST_TRY(launch_persistent(ctx, tree, rays + off * 4, cnt, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, probe));
         }
         if (tm == 1) return OBVHS_OK;
     }
-    dim3 block(128), grid(div_up(n, 128));
-    if (d_counters) {
-        if (mode == 0) traverse_kernel<0, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
-        else if (mode == 1) traverse_kernel<1, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
-        else traverse_kernel<2, true><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
-    } else {
-        if (mode == 0) traverse_kernel<0, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
-        else if (mode == 1) traverse_kernel<1, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
-        else traverse_kernel<2, false><<<grid, block, 0, s>>>(nodes, tris, rays, n, d_out, c, root_group, 0x4B000000u, probe);
+    return launch_static(ctx, tree, rays, n, mode, d_out, c, probe);
+}
+
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
+                          u64* d_counters) {
+    if (n == 0) return OBVHS_OK;
+    if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
+        OBVHS_SET_ERR(ctx, "CwBvh has no triangles attached (call obvhs_cuda_cwbvh_set_triangles)");
+        return OBVHS_ERR_INVALID_ARG;
     }
+    CwTree tree;
+    tree.nodes = reinterpret_cast<const uint4*>(bvh->nodes);
+    tree.tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
+    tree.root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
+    tree.magic = 0x4B000000u;
+    return traverse_dispatch(ctx, tree, bvh->total_aabb, reinterpret_cast<const float4*>(d_rays), n, mode, d_out, d_counters);
+}
+
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters) {
+    if (n == 0) return OBVHS_OK;
+    if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
+        OBVHS_SET_ERR(ctx, "Bvh2 has no triangles attached (call obvhs_cuda_bvh2_set_triangles)");
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    ObvhsAabb unknown = {};  // the Bvh2 handle does not keep the scene box: the probe then judges directions only
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    if (bvh->max_depth <= 96) {  // fast_stack!(u32, (96, 192), self.max_depth, ...) bvh2/mod.rs:166
+        Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
+        return traverse_dispatch(ctx, tree, unknown, rays, n, mode, d_out, d_counters);
+    }
+    if (bvh->max_depth <= 192) {
+        Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
+        return traverse_dispatch(ctx, tree, unknown, rays, n, mode, d_out, d_counters);
+    }
+    OBVHS_SET_ERR(ctx, "Bvh2 traversal: max_depth %zu > 192 needs the reference's heap stack -- not supported", bvh->max_depth);
+    return OBVHS_ERR_UNSUPPORTED;
+}
+
+// bvh_tris[i] = tris[primitive_indices[i]] for a Bvh2 (examples/demoscene.rs:66-70)
+int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris) {
+    if (bvh->bvh_tris) {
+        obvhs_result_free(bvh->owner, bvh->bvh_tris);
+        bvh->bvh_tris = nullptr;
+    }
+    const size_t n = bvh->prim_count;
+    if (n == 0) return OBVHS_OK;
+    (void)n_tris;  // indices are < n_tris by construction of the builders; uploaded trees are the caller's responsibility
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * sizeof(ObvhsTriangle)));
+    permute_tris_kernel<<<div_up(n * 3, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
+                                                                    reinterpret_cast<float4*>(bvh->bvh_tris), n);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
