@@ -400,7 +400,7 @@ def run_ours(args):
                        "multi_gpu": "build on rank 0, NCCL broadcast, rays sharded (one batch per GPU)" if world > 1 else "single GPU"},
             "build": {"value": build_mtris, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count},
             "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "kernel": "traverse_kernel<closest>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "nodes_visited": nodes_visited, "tris_tested": tris_tested,
                          "note": "B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); kitchen tree+tris fit in L2, "
@@ -414,6 +414,15 @@ def run_ours(args):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get("bytes")
+    except (OSError, ValueError):
+        return None
 
 
 def dynamic_frames(tris, n_frames):

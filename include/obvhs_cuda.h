@@ -30,9 +30,10 @@ typedef enum {
     OBVHS_OK = 0,
     OBVHS_ERR_INVALID_ARG = -1,
     OBVHS_ERR_CUDA = -2,
-    OBVHS_ERR_UNSUPPORTED = -3, /* pre_split presets, depth beyond the fixed stacks */
+    OBVHS_ERR_UNSUPPORTED = -3, /* include_exact_node_aabbs, depth beyond the fixed stacks, >= 2^30 primitives */
     OBVHS_ERR_NAN_INPUT = -4,   /* the reference panics / goes out of bounds on NaN AABBs (ploc/mod.rs:451) */
-    OBVHS_ERR_STACK_OVERFLOW = -5
+    OBVHS_ERR_STACK_OVERFLOW = -5,
+    OBVHS_ERR_CAPACITY = -6     /* a growing output (Vec::push in the reference) does not fit the caller's arrays */
 } ObvhsStatus;
 
 /* src/aabb.rs:11-16 -- two Vec3A lanes; the 4th float of each lane is padding (never read, never compared). */
@@ -62,7 +63,7 @@ typedef struct { uint32_t primitive_id, geometry_id, instance_id; float t; } Obv
 /* src/lib.rs:208-231 BvhBuildParams, field for field. ploc_search_distance is the u32 form of PlocSearchDistance
  * (ploc/mod.rs:534-562: 1,2,6,14,24,32); sort_precision is 64 or 128 (ploc/mod.rs:658-661). */
 typedef struct {
-    uint32_t pre_split; /* must be 0: spatial pre-splits (src/splits.rs) are outside this library's path */
+    uint32_t pre_split; /* spatial pre-splits of large triangles (src/splits.rs) before PLOC; triangle builders only */
     uint32_t ploc_search_distance;
     uint64_t search_depth_threshold;
     float reinsertion_batch_ratio;
@@ -92,6 +93,33 @@ int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value)
 /* 6 built-in presets of src/lib.rs:233-305 by name: fastest_build, very_fast_build, fast_build, medium_build,
  * slow_build, very_slow_build. */
 int obvhs_cuda_build_params_preset(const char* name, ObvhsBuildParams* out);
+
+/* ---- spatial pre-splits (src/splits.rs) ------------------------------------------------------------------ */
+/* split_aabbs_precise(&mut aabbs, &mut indices, triangles, area_thresh_low, area_thresh_high, split_factor_low,
+ * split_factor_high, max_iterations, split_tests)  (splits.rs:49-125). aabbs / indices hold n entries and have room
+ * for `capacity`; entries may shrink in place and the right halves are appended in the reference's order.
+ * *count_out receives the new length; when it exceeds capacity nothing is written and OBVHS_ERR_CAPACITY is returned
+ * (the Vec would have grown: call again with at least *count_out entries of room). */
+int obvhs_cuda_split_aabbs_precise(ObvhsContext* ctx, ObvhsAabb* aabbs, uint32_t* indices, size_t n, size_t capacity,
+                                   const ObvhsTriangle* tris, size_t n_tris, float area_thresh_low, float area_thresh_high,
+                                   float split_factor_low, float split_factor_high, uint32_t max_iterations,
+                                   uint32_t split_tests, size_t* count_out);
+/* split_aabbs_preset(&mut aabbs, &mut indices, triangles, avg_half_area, largest_half_area)  (splits.rs:16-34) */
+int obvhs_cuda_split_aabbs_preset(ObvhsContext* ctx, ObvhsAabb* aabbs, uint32_t* indices, size_t n, size_t capacity,
+                                  const ObvhsTriangle* tris, size_t n_tris, float avg_half_area, float largest_half_area,
+                                  size_t* count_out);
+/* The pre-split prologue of build_cwbvh_from_tris / build_bvh2_from_tris (cwbvh/builder.rs:27-54): triangle AABBs,
+ * their average (sequential f32 sum, as the reference) and largest half area, then split_aabbs_preset. aabbs_out /
+ * indices_out may be NULL to query the count. */
+int obvhs_cuda_presplit_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, ObvhsAabb* aabbs_out,
+                             uint32_t* indices_out, size_t capacity, size_t* count_out, float* avg_half_area,
+                             float* largest_half_area);
+/* Bvh2::uses_spatial_splits / CwBvh::uses_spatial_splits (bvh2/mod.rs:84, cwbvh/mod.rs:54): primitive_indices may name a
+ * triangle several times, so set_triangles accepts fewer triangles than primitives. Set by the builders. */
+int obvhs_cuda_bvh2_uses_spatial_splits(const ObvhsBvh2* bvh);
+void obvhs_cuda_bvh2_set_uses_spatial_splits(ObvhsBvh2* bvh, int value);
+int obvhs_cuda_cwbvh_uses_spatial_splits(const ObvhsCwBvh* bvh);
+void obvhs_cuda_cwbvh_set_uses_spatial_splits(ObvhsCwBvh* bvh, int value);
 
 /* ---- PLOC (src/ploc/mod.rs) ----------------------------------------------------------------------------- */
 /* Stage probe for parity tests: leaf init + scene AABB (ploc/mod.rs:187-243), Morton codes (:287-288,782-785;

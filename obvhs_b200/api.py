@@ -62,6 +62,13 @@ SIGNATURES = {
     "obvhs_cuda_launch_count": (_u64, [_vp]),
     "obvhs_cuda_set_option": (_i32, [_vp, C.c_char_p, C.c_char_p]),
     "obvhs_cuda_build_params_preset": (_i32, [C.c_char_p, C.POINTER(BuildParamsC)]),
+    "obvhs_cuda_split_aabbs_precise": (_i32, [_vp, _vp, _vp, _sz, _sz, _vp, _sz, _f32, _f32, _f32, _f32, _u32, _u32, C.POINTER(_sz)]),
+    "obvhs_cuda_split_aabbs_preset": (_i32, [_vp, _vp, _vp, _sz, _sz, _vp, _sz, _f32, _f32, C.POINTER(_sz)]),
+    "obvhs_cuda_presplit_tris": (_i32, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_f32), C.POINTER(_f32)]),
+    "obvhs_cuda_bvh2_uses_spatial_splits": (_i32, [_vp]),
+    "obvhs_cuda_bvh2_set_uses_spatial_splits": (None, [_vp, _i32]),
+    "obvhs_cuda_cwbvh_uses_spatial_splits": (_i32, [_vp]),
+    "obvhs_cuda_cwbvh_set_uses_spatial_splits": (None, [_vp, _i32]),
     "obvhs_cuda_morton_sort": (_i32, [_vp, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_ploc_build": (_i32, [_vp, _vp, _vp, _sz, _u32, _u32, _sz, _PP]),
     "obvhs_cuda_ploc_build_tris": (_i32, [_vp, _vp, _sz, _u32, _u32, _sz, _PP]),
@@ -269,6 +276,8 @@ class Bvh2:
     max_depth = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_max_depth(s.h)))
     ploc_iterations = property(lambda s: int(s.ctx.lib.obvhs_cuda_bvh2_ploc_iterations(s.h)))
     children_are_ordered_after_parents = property(lambda s: bool(s.ctx.lib.obvhs_cuda_bvh2_children_ordered_after_parents(s.h)))
+    uses_spatial_splits = property(lambda s: bool(s.ctx.lib.obvhs_cuda_bvh2_uses_spatial_splits(s.h)),
+                                   lambda s, v: s.ctx.lib.obvhs_cuda_bvh2_set_uses_spatial_splits(s.h, int(v)))
 
     @classmethod
     def upload(cls, nodes, primitive_indices, max_depth=96, children_ordered_after_parents=False, ctx: Context | None = None):
@@ -333,6 +342,75 @@ class Bvh2:
         counts = out if out is not None else np.zeros(n, dtype=np.uint32)
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(counts)))
         return counts
+
+
+ERR_CAPACITY = -6
+
+
+def _split_retry(n, run):
+    """Vec growth over the C ABI: run(aabbs, indices, capacity, count) until the grown arrays fit."""
+    cap = n + n // 8 + 1024
+    while True:
+        a = np.zeros((cap, 8), np.float32)
+        idx = np.zeros(cap, np.uint32)
+        count = _sz(0)
+        try:
+            run(a, idx, cap, count)
+            return a[: count.value].copy(), idx[: count.value].copy()
+        except ObvhsError as e:
+            if e.code != ERR_CAPACITY:
+                raise
+            cap = int(count.value)
+
+
+def split_aabbs_precise(aabbs, indices, triangles, area_thresh_low, area_thresh_high, split_factor_low, split_factor_high,
+                        max_iterations, split_tests, ctx: Context | None = None):
+    """src/splits.rs:49-125. Returns the grown (aabbs, indices) (the reference mutates its two Vecs)."""
+    ctx = ctx or default_context()
+    src = _as_f32(aabbs, 8)
+    src_idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    t = _as_f32(triangles, 12)
+    n = src.shape[0]
+
+    def run(a, idx, cap, count):
+        a[:n] = src
+        idx[:n] = src_idx
+        ctx.check(ctx.lib.obvhs_cuda_split_aabbs_precise(ctx.h, _ptr(a), _ptr(idx), n, cap, _ptr(t), t.shape[0], area_thresh_low,
+                                                         area_thresh_high, split_factor_low, split_factor_high, max_iterations,
+                                                         split_tests, C.byref(count)))
+
+    return _split_retry(n, run)
+
+
+def split_aabbs_preset(aabbs, indices, triangles, avg_half_area, largest_half_area, ctx: Context | None = None):
+    """src/splits.rs:16-34"""
+    ctx = ctx or default_context()
+    src = _as_f32(aabbs, 8)
+    src_idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    t = _as_f32(triangles, 12)
+    n = src.shape[0]
+
+    def run(a, idx, cap, count):
+        a[:n] = src
+        idx[:n] = src_idx
+        ctx.check(ctx.lib.obvhs_cuda_split_aabbs_preset(ctx.h, _ptr(a), _ptr(idx), n, cap, _ptr(t), t.shape[0], float(avg_half_area),
+                                                        float(largest_half_area), C.byref(count)))
+
+    return _split_retry(n, run)
+
+
+def presplit_tris(triangles, ctx: Context | None = None):
+    """The builders' pre-split prologue (src/cwbvh/builder.rs:27-54): -> (aabbs, indices, avg_half_area, largest_half_area)."""
+    ctx = ctx or default_context()
+    t = _as_f32(triangles, 12)
+    avg, largest = _f32(0), _f32(0)
+
+    def run(a, idx, cap, count):
+        ctx.check(ctx.lib.obvhs_cuda_presplit_tris(ctx.h, _ptr(t), t.shape[0], _ptr(a), _ptr(idx), cap, C.byref(count), C.byref(avg),
+                                                   C.byref(largest)))
+
+    a, idx = _split_retry(t.shape[0], run)
+    return a, idx, np.float32(avg.value), np.float32(largest.value)
 
 
 class PlocBuilder:
@@ -414,6 +492,8 @@ class CwBvh:
 
     node_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_cwbvh_node_count(s.h)))
     prim_count = property(lambda s: int(s.ctx.lib.obvhs_cuda_cwbvh_prim_count(s.h)))
+    uses_spatial_splits = property(lambda s: bool(s.ctx.lib.obvhs_cuda_cwbvh_uses_spatial_splits(s.h)),
+                                   lambda s, v: s.ctx.lib.obvhs_cuda_cwbvh_set_uses_spatial_splits(s.h, int(v)))
 
     @classmethod
     def upload(cls, nodes, primitive_indices, total_aabb=None, ctx: Context | None = None):
@@ -510,7 +590,7 @@ def build_cwbvh_from_tris(triangles, config: BvhBuildParams, core_build_time: li
 
 
 def build_bvh2_from_tris(triangles, config: BvhBuildParams, core_build_time: list | None = None, ctx: Context | None = None) -> Bvh2:
-    """src/bvh2/builder.rs:17-91 (no pre-splits). The result carries the permuted triangles and is ready to traverse."""
+    """src/bvh2/builder.rs:17-91. The result carries the permuted triangles and is ready to traverse."""
     ctx = ctx or default_context()
     t = _as_f32(triangles, 12)
     secs = C.c_double(0.0)

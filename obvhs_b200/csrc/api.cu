@@ -8,6 +8,7 @@ int bvh2_set_leaf_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAab
 int bvh2_expand_nodes_device(ObvhsContext* ctx, const Node32* in, size_t n, ObvhsBvh2Node* d_out);
 int bvh2_pack_nodes_device(ObvhsContext* ctx, const ObvhsBvh2Node* d_in, size_t n, Node32* out);
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 cudaError_t obvhs_result_alloc(ObvhsContext* ctx, void** p, size_t bytes) {
@@ -195,6 +196,57 @@ static void context_teardown(ObvhsContext* ctx) {
     if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
     delete ctx;
 }
+
+namespace {
+// in/out caller arrays -> arena arrays -> splitter -> back (Vec growth becomes "count_out may exceed capacity")
+template <class Run>
+int split_in_out(ObvhsContext* ctx, ObvhsAabb* aabbs, uint32_t* indices, size_t n, size_t capacity, size_t* count_out, Run run) {
+    SplitArrays a;
+    a.cap = std::max(capacity, n) + 1;
+    a.len = n;
+    a.aabbs = static_cast<ObvhsAabb*>(obvhs_arena_alloc(a.cap * sizeof(ObvhsAabb)));
+    a.indices = static_cast<u32*>(obvhs_arena_alloc(a.cap * 4));
+    if (!a.aabbs || !a.indices) {
+        OBVHS_SET_ERR(ctx, "split_aabbs: out of device memory");
+        return OBVHS_ERR_CUDA;
+    }
+    if (n) {
+        CU_TRY(ctx, cudaMemcpyAsync(a.aabbs, aabbs, n * sizeof(ObvhsAabb), cudaMemcpyDefault, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(a.indices, indices, n * 4, cudaMemcpyDefault, ctx->stream));
+    }
+    ST_TRY(run(a));
+    *count_out = a.len;
+    if (a.len > capacity) {
+        OBVHS_SET_ERR(ctx, "split_aabbs: %zu entries after splitting, capacity %zu (call again with more room)", a.len, capacity);
+        return OBVHS_ERR_CAPACITY;
+    }
+    if (a.len > n) {  // entries [0, n) may have been shrunk in place, [n, len) are the appended right halves
+        CU_TRY(ctx, cudaMemcpyAsync(aabbs, a.aabbs, a.len * sizeof(ObvhsAabb), cudaMemcpyDefault, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(indices, a.indices, a.len * 4, cudaMemcpyDefault, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
+// First stage of both triangle builders: PlocBuilder::build over the triangles, or -- with params->pre_split -- over the
+// split AABBs with their index map (cwbvh/builder.rs:27-71 == bvh2/builder.rs:24-68). Records ctx->ev0 where the
+// reference starts its core_build_time clock.
+int ploc_from_tris(ObvhsContext* ctx, const ObvhsTriangle* d_tris, size_t n, const ObvhsBuildParams* params, ObvhsBvh2** out) {
+    if (!params->pre_split) {
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        TraceScope ts(ctx, "build_ploc");
+        return ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                                 (size_t)params->search_depth_threshold, out, nullptr);
+    }
+    SplitArrays a;
+    ST_TRY(presplit_tris_device(ctx, d_tris, n, a, nullptr, ctx->ev0));
+    TraceScope ts(ctx, "build_ploc");
+    ST_TRY(ploc_build_device(ctx, a.aabbs, nullptr, a.indices, a.len, params->ploc_search_distance, params->sort_precision,
+                             (size_t)params->search_depth_threshold, out, nullptr));
+    (*out)->uses_spatial_splits = true;  // cwbvh/builder.rs:72
+    return OBVHS_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -496,6 +548,58 @@ int obvhs_cuda_reinsertion_run_with_candidates(ObvhsContext* ctx, ObvhsBvh2* bvh
     return rc;
 }
 
+// ---- spatial pre-splits (src/splits.rs) ------------------------------------------------------------------------
+
+int obvhs_cuda_split_aabbs_precise(ObvhsContext* ctx, ObvhsAabb* aabbs, uint32_t* indices, size_t n, size_t capacity,
+                                   const ObvhsTriangle* tris, size_t n_tris, float area_thresh_low, float area_thresh_high,
+                                   float split_factor_low, float split_factor_high, uint32_t max_iterations, uint32_t split_tests,
+                                   size_t* count_out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, count_out && (n == 0 || (aabbs && indices && tris)) && capacity >= n, "null argument or capacity < n");
+    DevBuf<ObvhsTriangle> st_tris;
+    const ObvhsTriangle* d_tris = nullptr;
+    ST_TRY(stage_in(ctx, tris, n_tris, st_tris, &d_tris));
+    return split_in_out(ctx, aabbs, indices, n, capacity, count_out, [&](SplitArrays& a) {
+        return split_aabbs_precise_device(ctx, a, d_tris, area_thresh_low, area_thresh_high, split_factor_low, split_factor_high,
+                                          max_iterations, split_tests);
+    });
+}
+
+int obvhs_cuda_split_aabbs_preset(ObvhsContext* ctx, ObvhsAabb* aabbs, uint32_t* indices, size_t n, size_t capacity,
+                                  const ObvhsTriangle* tris, size_t n_tris, float avg_half_area, float largest_half_area,
+                                  size_t* count_out) {
+    // splits.rs:23-33 (host f32 arithmetic; this translation unit is compiled without contraction)
+    volatile float lo = avg_half_area * 3.0f, hi_a = avg_half_area * 4.0f, t0 = avg_half_area * 0.9f, t1 = largest_half_area * 0.1f;
+    volatile float hi_b = t0 + t1;
+    const float hi = fmaxf(hi_a, hi_b);
+    return obvhs_cuda_split_aabbs_precise(ctx, aabbs, indices, n, capacity, tris, n_tris, lo, hi, 1.8f, 1.6f, 12, 12, count_out);
+}
+
+int obvhs_cuda_presplit_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, ObvhsAabb* aabbs_out, uint32_t* indices_out,
+                             size_t capacity, size_t* count_out, float* avg_half_area, float* largest_half_area) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, count_out && (n == 0 || tris), "null argument");
+    DevBuf<ObvhsTriangle> st_tris;
+    const ObvhsTriangle* d_tris = nullptr;
+    ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
+    SplitArrays a;
+    float al[2] = {0.f, 0.f};
+    ST_TRY(presplit_tris_device(ctx, d_tris, n, a, al, nullptr));
+    if (avg_half_area) *avg_half_area = al[0];
+    if (largest_half_area) *largest_half_area = al[1];
+    *count_out = a.len;
+    if (aabbs_out || indices_out) {
+        if (a.len > capacity) {
+            OBVHS_SET_ERR(ctx, "presplit_tris: %zu entries, capacity %zu (call again with more room)", a.len, capacity);
+            return OBVHS_ERR_CAPACITY;
+        }
+        ST_TRY(copy_out(ctx, aabbs_out, (const ObvhsAabb*)a.aabbs, a.len));
+        ST_TRY(copy_out(ctx, indices_out, (const u32*)a.indices, a.len));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
 // ---- CwBvh --------------------------------------------------------------------------------------------------
 int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t max_prims_per_leaf, int order_children,
                              int include_exact_node_aabbs, ObvhsCwBvh** out) {
@@ -513,21 +617,12 @@ int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tri
     API_ENTER(ctx);
     ARG_CHECK(ctx, params && out, "null argument");
     ARG_CHECK(ctx, n == 0 || tris, "tris is null");
-    if (params->pre_split) {
-        OBVHS_SET_ERR(ctx, "pre_split (src/splits.rs) is outside the GPU hot path");
-        return OBVHS_ERR_UNSUPPORTED;
-    }
     DevBuf<ObvhsTriangle> st_tris;
     const ObvhsTriangle* d_tris = nullptr;
     ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
-    // core_build_time brackets PLOC -> reinsertion -> collapse (cwbvh/builder.rs:62-76), measured on the device
-    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    // core_build_time brackets [splits ->] PLOC -> reinsertion -> collapse (cwbvh/builder.rs:45,62-76), measured on the device
     ObvhsBvh2* bvh2 = nullptr;
-    {
-        TraceScope ts(ctx, "build_ploc");
-        ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
-                                 (size_t)params->search_depth_threshold, &bvh2, nullptr));
-    }
+    ST_TRY(ploc_from_tris(ctx, d_tris, n, params, &bvh2));
     struct Guard {
         ObvhsBvh2* b;
         ~Guard() { obvhs_cuda_bvh2_free(b); }
@@ -567,6 +662,10 @@ void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh) {
     delete bvh;
     obvhs_context_release(ctx);
 }
+int obvhs_cuda_cwbvh_uses_spatial_splits(const ObvhsCwBvh* bvh) { return bvh && bvh->uses_spatial_splits; }
+void obvhs_cuda_cwbvh_set_uses_spatial_splits(ObvhsCwBvh* bvh, int v) { if (bvh) bvh->uses_spatial_splits = v != 0; }
+int obvhs_cuda_bvh2_uses_spatial_splits(const ObvhsBvh2* bvh) { return bvh && bvh->uses_spatial_splits; }
+void obvhs_cuda_bvh2_set_uses_spatial_splits(ObvhsBvh2* bvh, int v) { if (bvh) bvh->uses_spatial_splits = v != 0; }
 size_t obvhs_cuda_cwbvh_node_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->node_count : 0; }
 size_t obvhs_cuda_cwbvh_prim_count(const ObvhsCwBvh* bvh) { return bvh ? bvh->prim_count : 0; }
 
@@ -823,20 +922,11 @@ int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris
     API_ENTER(ctx);
     ARG_CHECK(ctx, params && out, "null argument");
     ARG_CHECK(ctx, n == 0 || tris, "tris is null");
-    if (params->pre_split) {
-        OBVHS_SET_ERR(ctx, "pre_split (src/splits.rs) is outside the GPU hot path");
-        return OBVHS_ERR_UNSUPPORTED;
-    }
     DevBuf<ObvhsTriangle> st_tris;
     const ObvhsTriangle* d_tris = nullptr;
     ST_TRY(stage_in(ctx, tris, n, st_tris, &d_tris));
-    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));  // core_build_time: bvh2/builder.rs:41,60 .. 83
     ObvhsBvh2* bvh2 = nullptr;
-    {
-        TraceScope ts(ctx, "build_ploc");
-        ST_TRY(ploc_build_device(ctx, nullptr, d_tris, nullptr, n, params->ploc_search_distance, params->sort_precision,
-                                 (size_t)params->search_depth_threshold, &bvh2, nullptr));
-    }
+    ST_TRY(ploc_from_tris(ctx, d_tris, n, params, &bvh2));  // core_build_time: bvh2/builder.rs:41,60 .. 83
     struct Guard {
         ObvhsBvh2* b;
         ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }

@@ -174,6 +174,7 @@ struct ObvhsBvh2 {
     size_t max_depth = 96;  // bvh2/mod.rs:87 DEFAULT_MAX_STACK_DEPTH
     size_t ploc_iterations = 0;
     bool children_are_ordered_after_parents = false;
+    bool uses_spatial_splits = false;  // bvh2/mod.rs:84: primitive_indices may name a primitive more than once
 };
 
 struct ObvhsCwBvh {
@@ -184,6 +185,7 @@ struct ObvhsCwBvh {
     ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices, or null
     size_t node_count = 0, prim_count = 0;
     ObvhsAabb total_aabb = {};
+    bool uses_spatial_splits = false;  // cwbvh/mod.rs:54
 };
 
 #define OBVHS_SET_ERR(ctx, ...)                       \
@@ -280,6 +282,15 @@ struct PlocMortonOut {
 int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
                       u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
                       const PlocMortonOut* probe);
+// splits.cu : spatial pre-splits (src/splits.rs). Arrays live in the arena of the API call in flight and grow like the Vecs.
+struct SplitArrays {
+    ObvhsAabb* aabbs = nullptr;
+    u32* indices = nullptr;
+    size_t len = 0, cap = 0;
+};
+int split_aabbs_precise_device(ObvhsContext* ctx, SplitArrays& a, const ObvhsTriangle* d_tris, float area_thresh_low, float area_thresh_high,
+                               float split_factor_low, float split_factor_high, u32 max_iterations, u32 split_tests);
+int presplit_tris_device(ObvhsContext* ctx, const ObvhsTriangle* d_tris, size_t n, SplitArrays& a, float* avg_largest_host, cudaEvent_t ev_start);
 // sort.cu : stable LSD radix sort (onesweep) of (key, value) pairs; keys in `keys` / `vals`, scratch in *_alt.
 // On return *sorted_keys / *sorted_vals point at whichever buffer holds the result.
 int radix_sort_pairs_u64(ObvhsContext* ctx, u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, size_t n, int key_bytes,

@@ -551,6 +551,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     ObvhsCwBvh* cw = new ObvhsCwBvh();
     cw->device = ctx->device;
     cw->owner = ctx;
+    cw->uses_spatial_splits = bvh->uses_spatial_splits;  // bvh2_to_cwbvh.rs:508
     obvhs_context_retain(ctx);
     struct Guard {
         ObvhsCwBvh* b;

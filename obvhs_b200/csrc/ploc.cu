@@ -141,6 +141,35 @@ __global__ void __launch_bounds__(256) morton_kernel(const Node32* __restrict__ 
     vals[i] = i;
 }
 
+// K2 for SortPrecision::U128 (ploc/mod.rs:686-701,726-747; morton.rs:65-89): 42 bits per axis, `as u64` saturating cast
+// (cvt.rzi.u64.f64), masked to 42 bits, interleaved into a 126-bit code kept as two 64-bit words. Code bit 3i+a is bit i
+// of axis a, so the low word holds x[0..21], y[0..20], z[0..20] and the high word (code >> 64) holds y[21..41] at 3j,
+// z[21..41] at 3j+1 and x[22..41] at 3j+2.
+__global__ void __launch_bounds__(256) morton128_kernel(const Node32* __restrict__ leaves, u32 n, const PlocGlobals* __restrict__ g,
+                                                        u64* __restrict__ keys_lo, u64* __restrict__ keys_hi, u32* __restrict__ vals) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Node32 nd = load_node(leaves + i);
+    float cx = (nd.maxx + nd.minx) * 0.5f, cy = (nd.maxy + nd.miny) * 0.5f, cz = (nd.maxz + nd.minz) * 0.5f;  // aabb.rs:113-115
+    double px = __dadd_rn(__dmul_rn((double)cx, g->scale[0]), g->offset[0]);
+    double py = __dadd_rn(__dmul_rn((double)cy, g->scale[1]), g->offset[1]);
+    double pz = __dadd_rn(__dmul_rn((double)cz, g->scale[2]), g->offset[2]);
+    const double k42 = 4398046511104.0;  // (1u64 << 42) as f64
+    const u64 m42 = 0x3ffffffffffull;
+    u64 x = __double2ull_rz(__dmul_rn(px, k42)) & m42, y = __double2ull_rz(__dmul_rn(py, k42)) & m42,
+        z = __double2ull_rz(__dmul_rn(pz, k42)) & m42;
+    keys_lo[i] = split_by_3_u64((u32)x) | split_by_3_u64((u32)y) << 1 | split_by_3_u64((u32)z) << 2 | ((x >> 21) & 1ull) << 63;
+    keys_hi[i] = split_by_3_u64((u32)(y >> 21)) | split_by_3_u64((u32)(z >> 21)) << 1 | split_by_3_u64((u32)(x >> 22)) << 2;
+    vals[i] = i;
+}
+
+// second half of the 16-level LSD sort: high words brought into the order the low-word sort produced
+__global__ void __launch_bounds__(256) gather_keys_kernel(const u64* __restrict__ src, const u32* __restrict__ order, u32 n,
+                                                          u64* __restrict__ dst) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __ldg(src + order[i]);
+}
+
 // K4. ploc/mod.rs:829: sorted[i] = leaves[order[i]]
 __global__ void __launch_bounds__(256) gather_nodes_kernel(const Node32* __restrict__ leaves, const u32* __restrict__ order, u32 n,
                                                            Node32* __restrict__ sorted) {
@@ -494,9 +523,9 @@ cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes,
 int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
                       u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
                       const PlocMortonOut* probe) {
-    if (sort_precision != 64) {
-        OBVHS_SET_ERR(ctx, "SortPrecision::U128 is not implemented on the GPU path yet (ploc/mod.rs:686-701)");
-        return OBVHS_ERR_UNSUPPORTED;
+    if (sort_precision != 64 && sort_precision != 128) {
+        OBVHS_SET_ERR(ctx, "sort precision %u is not SortPrecision::U64 (64) or ::U128 (128)", sort_precision);
+        return OBVHS_ERR_INVALID_ARG;
     }
     switch (search_distance) {  // PlocSearchDistance::from(u32), ploc/mod.rs:550-562
         case 1: case 2: case 6: case 14: case 24: case 32: break;
@@ -562,11 +591,21 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     KERNEL_CHECK(ctx);
     morton_params_kernel<<<1, 32, 0, s>>>(g.p);
     KERNEL_CHECK(ctx);
-    morton_kernel<<<div_up(n, 256), 256, 0, s>>>(bufA.p, un, g.p, keys.p, vals.p);
+    const bool wide = sort_precision == 128;
+    DevBuf<u64> keys_hi;
+    if (wide) {
+        CU_TRY(ctx, keys_hi.alloc(n, s));
+        morton128_kernel<<<div_up(n, 256), 256, 0, s>>>(bufA.p, un, g.p, keys.p, keys_hi.p, vals.p);
+    } else {
+        morton_kernel<<<div_up(n, 256), 256, 0, s>>>(bufA.p, un, g.p, keys.p, vals.p);
+    }
     KERNEL_CHECK(ctx);
     if (probe) {
         if (probe->codes_lo) CU_TRY(ctx, cudaMemcpyAsync(probe->codes_lo, keys.p, n * 8, cudaMemcpyDeviceToDevice, s));
-        if (probe->codes_hi) CU_TRY(ctx, cudaMemsetAsync(probe->codes_hi, 0, n * 8, s));
+        if (probe->codes_hi) {
+            if (wide) CU_TRY(ctx, cudaMemcpyAsync(probe->codes_hi, keys_hi.p, n * 8, cudaMemcpyDeviceToDevice, s));
+            else CU_TRY(ctx, cudaMemsetAsync(probe->codes_hi, 0, n * 8, s));
+        }
         if (probe->total) CU_TRY(ctx, cudaMemcpyAsync(probe->total, g.p->total, sizeof(ObvhsAabb), cudaMemcpyDeviceToDevice, s));
     }
     delete tsp;
@@ -574,6 +613,15 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     u64* skeys;
     u32* order;
     ST_TRY(radix_sort_pairs_u64(ctx, keys.p, keys_alt.p, vals.p, vals_alt.p, n, 8, &skeys, &order));
+    if (wide) {
+        // Morton128::LEVELS = 16 (ploc/mod.rs:694-701): a stable LSD sort over the low word followed by a stable LSD sort over
+        // the high word. The sorted low words are dead after the first half, so their buffer receives the gathered high words.
+        gather_keys_kernel<<<div_up(n, 256), 256, 0, s>>>(keys_hi.p, order, un, skeys);
+        KERNEL_CHECK(ctx);
+        u64* k_alt = skeys == keys.p ? keys_alt.p : keys.p;
+        u32* v_alt = order == vals.p ? vals_alt.p : vals.p;
+        ST_TRY(radix_sort_pairs_u64(ctx, skeys, k_alt, order, v_alt, n, 8, &skeys, &order));
+    }
     if (probe && probe->order) CU_TRY(ctx, cudaMemcpyAsync(probe->order, order, n * 4, cudaMemcpyDeviceToDevice, s));
     gather_nodes_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(bufA.p, order, un, bufB.p);
     KERNEL_CHECK(ctx);

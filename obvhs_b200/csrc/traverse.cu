@@ -651,7 +651,8 @@ int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTrian
 }
 
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n) {
-    if (n != bvh->prim_count) {
+    // with spatial splits primitive_indices names some triangles several times (cwbvh/mod.rs:752-755)
+    if (n != bvh->prim_count && !(bvh->uses_spatial_splits && n <= bvh->prim_count)) {
         OBVHS_SET_ERR(ctx, "set_triangles: %zu triangles for a CwBvh over %zu primitives", n, bvh->prim_count);
         return OBVHS_ERR_INVALID_ARG;
     }
@@ -659,6 +660,7 @@ int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTri
         obvhs_result_free(bvh->owner, bvh->bvh_tris);
         bvh->bvh_tris = nullptr;
     }
+    n = bvh->prim_count;
     if (n == 0) return OBVHS_OK;
     CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * sizeof(ObvhsTriangle)));
     permute_tris_kernel<<<div_up(n * 3, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,

@@ -247,7 +247,7 @@ def demoscene(terrain_res: int, seed: int) -> np.ndarray:
 
 def triangle_soup(n: int, seed: int = 0) -> np.ndarray:
     """n hashed small triangles in the unit cube (incoherent stress scene)."""
-    i = np.arange(n, dtype=np.uint32) + np.uint32(seed) * np.uint32(0x9E3779B9)
+    i = np.arange(n, dtype=np.uint32) + np.uint32((seed * 0x9E3779B9) & 0xFFFFFFFF)
     c = np.stack([unormf(uhash2(i, k)) for k in (1, 2, 3)], axis=1)
     s = np.float32(0.5 * float(n) ** (-1.0 / 3.0))
     vs = []
@@ -255,6 +255,21 @@ def triangle_soup(n: int, seed: int = 0) -> np.ndarray:
         off = np.stack([unormf(uhash2(i, 4 + 3 * k + a)) for a in range(3)], axis=1)
         vs.append(c + s * (np.float32(2.0) * off - np.float32(1.0)))
     return triangles_from_vertices(vs[0], vs[1], vs[2])
+
+
+def soup_with_large_triangles(n: int, n_large: int, seed: int = 0) -> np.ndarray:
+    """A triangle soup plus a few long, thin, diagonal triangles spanning the unit cube: the case spatial pre-splits
+    (src/splits.rs) exist for; the large ones are split through several iterations."""
+    small = triangle_soup(n, seed) if n else np.zeros((0, 12), np.float32)
+    i = np.arange(n_large, dtype=np.uint32) + np.uint32(977) + np.uint32(seed)
+    vs = [np.stack([unormf(uhash2(i, 31 + 3 * k + a)) for a in range(3)], axis=1) for k in range(3)]
+    # slivers along a random diagonal: the third vertex sits near the middle of the long edge
+    v2 = (vs[0] + vs[1]) * np.float32(0.5) + (vs[2] - np.float32(0.5)) * np.float32(0.04)
+    large = triangles_from_vertices(vs[0], vs[1], v2.astype(np.float32))
+    out = np.concatenate([small, large], axis=0)
+    # interleave so the large ones are not all at the end of the index range
+    perm = np.argsort(uhash2(np.arange(out.shape[0], dtype=np.uint32), np.uint32(99) + np.uint32(seed)), kind="stable")
+    return np.ascontiguousarray(out[perm])
 
 
 # ----------------------------------------------------------------------------------------------------------

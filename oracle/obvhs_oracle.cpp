@@ -228,11 +228,13 @@ struct OrcBvh2 {
     size_t max_depth = 96;  // bvh2/mod.rs:87 DEFAULT_MAX_STACK_DEPTH
     size_t ploc_iterations = 0;
     size_t last_applied = 0;
+    bool uses_spatial_splits = false;  // bvh2/mod.rs:84
 };
 struct OrcCwBvh {
     std::vector<OrcCwBvhNode> nodes;
     std::vector<u32> primitive_indices;
     OrcAabb total_aabb;
+    bool uses_spatial_splits = false;  // cwbvh/mod.rs:54
     std::vector<OrcAabb> exact_node_aabbs;
 };
 
@@ -1036,6 +1038,7 @@ struct Bvh2Converter {
 static OrcCwBvh* bvh2_to_cwbvh(const OrcBvh2& bvh2, u32 max_prims_per_leaf, bool order_children, bool include_exact) {
     OrcCwBvh* out = new OrcCwBvh();
     out->total_aabb = OrcAabb{};
+    out->uses_spatial_splits = bvh2.uses_spatial_splits;  // bvh2_to_cwbvh.rs:508
     if (bvh2.nodes.empty()) return out;  // CwBvh::default()
     Bvh2Converter conv(bvh2, order_children, include_exact);
     conv.calculate_cost_impl(0, max_prims_per_leaf);
@@ -1495,6 +1498,122 @@ static void bvh2_traverse_batch(const OrcBvh2& bvh, const OrcTriangle* tris, con
 // ---------------------------------------------------------------------------------------------------------
 // validation (bvh2/mod.rs:786-981, cwbvh/mod.rs:747-908) -- invariants restated, not the stats
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// splits.rs: spatial pre-splits of large triangles
+// ---------------------------------------------------------------------------------------------------------
+// aabb.rs:124-134
+static inline int largest_axis(const OrcAabb& a) {
+    float dx = a.max[0] - a.min[0], dy = a.max[1] - a.min[1], dz = a.max[2] - a.min[2];
+    if (dx < dy) return dy < dz ? 2 : 1;
+    return dx < dz ? 2 : 0;
+}
+// aabb.rs:97-103: min = self.min.max(other.min), max = self.max.min(other.max)
+static inline OrcAabb aabb_intersection(const OrcAabb& a, const OrcAabb& b) {
+    OrcAabb r;
+    for (int i = 0; i < 3; i++) {
+        r.min[i] = smax(a.min[i], b.min[i]);
+        r.max[i] = smin(a.max[i], b.max[i]);
+    }
+    r._p0 = r._p1 = 0.f;
+    return r;
+}
+// splits.rs:129-158 split_triangle(dim, pos, [v0,v1,v2,v0]). Aabb::INVALID (aabb.rs:23-26) = (f32::MAX, f32::MIN);
+// Vec3A::mul_add is a fused multiply-add per lane on every glam backend (_mm_fmadd_ps or f32::mul_add).
+static inline void split_triangle(int dim, float pos, const OrcTriangle& t, OrcAabb& left, OrcAabb& right) {
+    left = aabb_empty();
+    right = aabb_empty();
+    const float* v[4] = {t.v0, t.v1, t.v2, t.v0};
+    for (int i = 0; i < 3; i++) {
+        const float* v0 = v[i];
+        const float* v1 = v[i + 1];
+        float v0d = v0[dim], v1d = v1[dim];
+        if (v0d <= pos) aabb_extend(left, v0);
+        if (v0d >= pos) aabb_extend(right, v0);
+        if ((v0d < pos && pos < v1d) || (v1d < pos && pos < v0d)) {
+            float inv_length = 1.0f / (v1d - v0d);
+            float tt = (pos - v0d) * inv_length;
+            float c[3];
+            for (int k = 0; k < 3; k++) c[k] = fmaf(tt, v1[k] - v0[k], v0[k]);
+            aabb_extend(left, c);
+            aabb_extend(right, c);
+        }
+    }
+}
+// splits.rs:49-125
+static void split_aabbs_precise(std::vector<OrcAabb>& aabbs, std::vector<u32>& indices, const OrcTriangle* triangles, float area_thresh_low,
+                                float area_thresh_high, float split_factor_low, float split_factor_high, u32 max_iterations,
+                                u32 split_tests) {
+    std::vector<size_t> candidates;
+    for (size_t i = 0; i < aabbs.size(); i++)
+        if (half_area(aabbs[i]) > area_thresh_low) candidates.push_back(i);
+    size_t old_candidates_len = candidates.size();
+    for (u32 it = 0; it < max_iterations; it++) {
+        const size_t count = candidates.size();  // the range 0..candidates.len() is evaluated once (:71)
+        for (size_t ci = 0; ci < count; ci++) {
+            OrcAabb aabb = aabbs[candidates[ci]];
+            u32 index = indices[candidates[ci]];
+            int axis = largest_axis(aabb);
+            const OrcTriangle& tri = triangles[index];
+            float best_cost = 3.40282347e+38f;
+            OrcAabb left = aabb, right = aabb;
+            for (u32 i = 1; i < split_tests; i++) {
+                float n = (float)i / (float)split_tests;
+                float pos = aabb.min[axis] * n + aabb.max[axis] * (1.0f - n);
+                OrcAabb tmp_left = aabb, tmp_right = aabb;
+                tmp_left.max[axis] = pos;
+                tmp_right.min[axis] = pos;
+                OrcAabb t_left, t_right;
+                split_triangle(axis, pos, tri, t_left, t_right);
+                tmp_left = aabb_intersection(t_left, tmp_left);
+                tmp_right = aabb_intersection(t_right, tmp_right);
+                float area = half_area(tmp_left) + half_area(tmp_right);
+                if (area < best_cost) {
+                    best_cost = area;
+                    left = tmp_left;
+                    right = tmp_right;
+                }
+            }
+            float old_cost = half_area(aabb);
+            if ((area_thresh_high > old_cost && best_cost * split_factor_high < old_cost) || best_cost * split_factor_low < old_cost) {
+                aabbs[candidates[ci]] = left;
+                candidates.push_back(aabbs.size());
+                aabbs.push_back(right);
+                indices.push_back(index);
+            }
+        }
+        if (old_candidates_len == candidates.size()) break;
+        size_t w = 0;  // Vec::retain keeps order (:121)
+        for (size_t k = 0; k < candidates.size(); k++)
+            if (half_area(aabbs[candidates[k]]) > area_thresh_low) candidates[w++] = candidates[k];
+        candidates.resize(w);
+        old_candidates_len = candidates.size();
+    }
+}
+// splits.rs:16-34
+static void split_aabbs_preset(std::vector<OrcAabb>& aabbs, std::vector<u32>& indices, const OrcTriangle* triangles, float avg_half_area,
+                               float largest_half_area) {
+    float hi_a = avg_half_area * 4.0f, hi_b = avg_half_area * 0.9f + largest_half_area * 0.1f;
+    float hi = fmaxf(hi_a, hi_b);  // f32::max
+    split_aabbs_precise(aabbs, indices, triangles, avg_half_area * 3.0f, hi, 1.8f, 1.6f, 12, 12);
+}
+// cwbvh/builder.rs:28-54 == bvh2/builder.rs:25-51: triangle AABBs, sequential f32 sum and f32::max of their half areas
+static void presplit_inputs(const OrcTriangle* tris, size_t n, std::vector<OrcAabb>& aabbs, std::vector<u32>& indices, float* avg_out,
+                            float* largest_out) {
+    float largest_half_area = 0.0f, avg_area = 0.0f;
+    aabbs.resize(n);
+    indices.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        aabbs[i] = tri_aabb(tris[i]);
+        float h = half_area(aabbs[i]);
+        largest_half_area = fmaxf(h, largest_half_area);
+        avg_area += h;
+        indices[i] = (u32)i;
+    }
+    avg_area /= (float)n;
+    *avg_out = avg_area;
+    *largest_out = largest_half_area;
+}
+
 #define VFAIL(code, ...)                     \
     do {                                     \
         if (msg) snprintf(msg, 256, __VA_ARGS__); \
@@ -1510,10 +1629,13 @@ static int bvh2_validate(const OrcBvh2& bvh, const OrcAabb* prim_aabbs, size_t n
     {  // 2*leaves - 1 nodes; leaves == n unless leaves were collapsed (leaf_collapser.rs)
         size_t leaves = 0;
         for (const OrcBvh2Node& nd : bvh.nodes) leaves += is_leaf(nd) ? 1 : 0;
-        if (bvh.nodes.size() != 2 * leaves - 1 || leaves > n) VFAIL(-2, "node count %zu != 2*leaves-1 (leaves=%zu, n=%zu)", bvh.nodes.size(), leaves, n);
+        if (bvh.nodes.size() != 2 * leaves - 1 || (leaves > n && !bvh.uses_spatial_splits)) VFAIL(-2, "node count %zu != 2*leaves-1 (leaves=%zu, n=%zu)", bvh.nodes.size(), leaves, n);
     }
-    if (bvh.primitive_indices.size() != n) VFAIL(-3, "primitive_indices len %zu != %zu", bvh.primitive_indices.size(), n);
-    std::vector<u8> seen_node(bvh.nodes.size(), 0), seen_prim(n, 0);
+    // with spatial splits a primitive shows up in several leaves and may extend outside them (bvh2/mod.rs:823-829,928-945)
+    const bool splits = bvh.uses_spatial_splits;
+    const size_t n_slots = bvh.primitive_indices.size();
+    if (!splits && n_slots != n) VFAIL(-3, "primitive_indices len %zu != %zu", n_slots, n);
+    std::vector<u8> seen_node(bvh.nodes.size(), 0), seen_prim(n, 0), seen_slot2(n_slots, 0);
     std::vector<std::pair<u32, u32>> stack;  // node, depth
     stack.push_back({0, 0});
     size_t max_depth = 0, visited = 0;
@@ -1529,11 +1651,14 @@ static int bvh2_validate(const OrcBvh2& bvh, const OrcAabb* prim_aabbs, size_t n
         if (is_leaf(nd)) {
             for (u32 k = 0; k < nd.prim_count; k++) {
                 u32 slot = nd.first_index + k;
-                if (slot >= n) VFAIL(-6, "leaf %u prim slot %u out of range", id, slot);
+                if (slot >= n_slots) VFAIL(-6, "leaf %u prim slot %u out of range", id, slot);
+                if (seen_slot2[slot]) VFAIL(-8, "primitive slot %u referenced twice", slot);
+                seen_slot2[slot] = 1;
                 u32 prim = bvh.primitive_indices[slot];
                 if (prim >= n) VFAIL(-7, "primitive id %u out of range", prim);
-                if (seen_prim[prim]) VFAIL(-8, "primitive %u referenced twice", prim);
+                if (seen_prim[prim] && !splits) VFAIL(-8, "primitive %u referenced twice", prim);
                 seen_prim[prim] = 1;
+                if (splits) continue;
                 for (int a = 0; a < 3; a++) {
                     if (!(prim_aabbs[prim].min[a] >= nd.aabb.min[a]) || !(prim_aabbs[prim].max[a] <= nd.aabb.max[a]))
                         VFAIL(-9, "primitive %u not inside leaf %u", prim, id);
@@ -1563,12 +1688,14 @@ static int bvh2_validate(const OrcBvh2& bvh, const OrcAabb* prim_aabbs, size_t n
 
 static int cwbvh_validate(const OrcCwBvh& bvh, const OrcAabb* prim_aabbs, size_t n, char* msg) {
     if (msg) msg[0] = 0;
-    if (bvh.primitive_indices.size() != n) VFAIL(-1, "primitive_indices len %zu != %zu", bvh.primitive_indices.size(), n);
+    const bool splits = bvh.uses_spatial_splits;  // cwbvh/mod.rs:752-755,893
+    const size_t n_slots = bvh.primitive_indices.size();
+    if (!splits && n_slots != n) VFAIL(-1, "primitive_indices len %zu != %zu", n_slots, n);
     if (bvh.nodes.empty()) {
         if (n != 0) VFAIL(-2, "no nodes for %zu primitives", n);
         return 0;
     }
-    std::vector<u8> seen_node(bvh.nodes.size(), 0), seen_slot(n, 0), seen_prim(n, 0);
+    std::vector<u8> seen_node(bvh.nodes.size(), 0), seen_slot(n_slots, 0), seen_prim(n, 0);
     struct Item {
         u32 node;
         u32 depth;
@@ -1629,13 +1756,14 @@ static int cwbvh_validate(const OrcCwBvh& bvh, const OrcAabb* prim_aabbs, size_t
                 for (int i = 0; i < 3; i++) {
                     if (!(meta & (0x20 << i))) continue;
                     u32 slot = first + i;
-                    if (slot >= n) VFAIL(-11, "prim slot %u out of range", slot);
+                    if (slot >= n_slots) VFAIL(-11, "prim slot %u out of range", slot);
                     if (seen_slot[slot]) VFAIL(-12, "prim slot %u referenced twice", slot);
                     seen_slot[slot] = 1;
                     u32 prim = bvh.primitive_indices[slot];
                     if (prim >= n) VFAIL(-13, "prim id %u out of range", prim);
-                    if (seen_prim[prim]) VFAIL(-14, "primitive %u referenced twice", prim);
+                    if (seen_prim[prim] && !splits) VFAIL(-14, "primitive %u referenced twice", prim);
                     seen_prim[prim] = 1;
+                    if (splits) continue;
                     for (int a = 0; a < 3; a++) {
                         if (!(prim_aabbs[prim].min[a] >= it.bounds.min[a] - 1.0e-5f) || !(prim_aabbs[prim].max[a] <= it.bounds.max[a] + 1.0e-5f))
                             VFAIL(-15, "primitive %u does not fit in node %u bounds", prim, it.node);
@@ -1747,20 +1875,28 @@ void orc_bvh2_ray_traverse_anyhit_count(const OrcBvh2* b, const OrcTriangle* bvh
                                         int threads) {
     bvh2_traverse_batch<2>(*b, bvh_tris, rays, n, nullptr, nullptr, counts, threads, nullptr);
 }
-// bvh2/builder.rs:17-91 (pre_split = false): PLOC -> reinsertion -> collapse -> reinsertion
+// bvh2/builder.rs:17-91: [pre-splits ->] PLOC -> reinsertion -> collapse -> reinsertion
 OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, u32 search_distance, size_t search_depth_threshold,
                                   float reinsertion_batch_ratio, float post_collapse_multiplier, int precision, u32 max_prims_per_leaf,
-                                  float collapse_traversal_cost, int threads, double* core_seconds) {
+                                  float collapse_traversal_cost, int pre_split, int threads, double* core_seconds) {
     threads = clamp_threads(threads);
     std::vector<OrcAabb> aabbs(n);
     std::vector<u32> indices(n);
     auto t0 = std::chrono::steady_clock::now();
+    if (pre_split) {  // bvh2/builder.rs:24-58
+        float avg, largest;
+        presplit_inputs(tris, n, aabbs, indices, &avg, &largest);
+        t0 = std::chrono::steady_clock::now();
+        split_aabbs_preset(aabbs, indices, tris, avg, largest);
+    } else {
 #pragma omp parallel for num_threads(threads) if (n > 100000)
-    for (long i = 0; i < (long)n; i++) {
-        aabbs[i] = tri_aabb(tris[i]);
-        indices[i] = (u32)i;
+        for (long i = 0; i < (long)n; i++) {
+            aabbs[i] = tri_aabb(tris[i]);
+            indices[i] = (u32)i;
+        }
     }
-    OrcBvh2* bvh2 = orc_ploc_build(aabbs.data(), indices.data(), n, search_distance, precision, search_depth_threshold, threads);
+    OrcBvh2* bvh2 = orc_ploc_build(aabbs.data(), indices.data(), aabbs.size(), search_distance, precision, search_depth_threshold, threads);
+    bvh2->uses_spatial_splits = pre_split != 0;  // :69
     orc_reinsertion_run(bvh2, reinsertion_batch_ratio, nullptr, 0, threads);
     collapse(*bvh2, std::min<u32>(std::max<u32>(max_prims_per_leaf, 1), 255), collapse_traversal_cost);
     orc_reinsertion_run(bvh2, reinsertion_batch_ratio * post_collapse_multiplier, nullptr, 0, threads);
@@ -1794,6 +1930,37 @@ void orc_reinsertion_run_with_candidates(OrcBvh2* b, const u32* ids, size_t n, u
 size_t orc_reinsertion_last_applied(const OrcBvh2* b) { return b->last_applied; }
 void orc_set_refit_full(int full) { g_refit_full = full != 0; }
 
+// splits.rs:49-125 on caller arrays with room for `cap` entries; returns the new count (which may exceed cap: nothing is
+// written past cap, call again with more room)
+size_t orc_split_aabbs_precise(OrcAabb* aabbs, u32* indices, size_t n, size_t cap, const OrcTriangle* tris, float area_thresh_low,
+                               float area_thresh_high, float split_factor_low, float split_factor_high, u32 max_iterations,
+                               u32 split_tests) {
+    std::vector<OrcAabb> a(aabbs, aabbs + n);
+    std::vector<u32> idx(indices, indices + n);
+    split_aabbs_precise(a, idx, tris, area_thresh_low, area_thresh_high, split_factor_low, split_factor_high, max_iterations, split_tests);
+    size_t m = std::min(cap, a.size());
+    memcpy(aabbs, a.data(), m * sizeof(OrcAabb));
+    memcpy(indices, idx.data(), m * 4);
+    return a.size();
+}
+// the builders' pre-split prologue (cwbvh/builder.rs:27-54): triangle AABBs, avg / largest half area, split_aabbs_preset
+size_t orc_presplit_tris(const OrcTriangle* tris, size_t n, OrcAabb* aabbs_out, u32* indices_out, size_t cap, float* avg_half_area,
+                         float* largest_half_area) {
+    std::vector<OrcAabb> a;
+    std::vector<u32> idx;
+    float avg = 0.f, largest = 0.f;
+    presplit_inputs(tris, n, a, idx, &avg, &largest);
+    if (avg_half_area) *avg_half_area = avg;
+    if (largest_half_area) *largest_half_area = largest;
+    split_aabbs_preset(a, idx, tris, avg, largest);
+    size_t m = std::min(cap, a.size());
+    if (aabbs_out) memcpy(aabbs_out, a.data(), m * sizeof(OrcAabb));
+    if (indices_out) memcpy(indices_out, idx.data(), m * 4);
+    return a.size();
+}
+void orc_bvh2_set_uses_spatial_splits(OrcBvh2* b, int v) { b->uses_spatial_splits = v != 0; }
+void orc_cwbvh_set_uses_spatial_splits(OrcCwBvh* c, int v) { c->uses_spatial_splits = v != 0; }
+
 OrcCwBvh* orc_bvh2_to_cwbvh(const OrcBvh2* b, u32 max_prims_per_leaf, int order_children, int include_exact) {
     return bvh2_to_cwbvh(*b, max_prims_per_leaf, order_children != 0, include_exact != 0);
 }
@@ -1816,19 +1983,27 @@ void orc_cwbvh_get(const OrcCwBvh* c, OrcCwBvhNode* nodes, u32* primitive_indice
 int orc_cwbvh_validate(const OrcCwBvh* c, const OrcAabb* prim_aabbs, size_t n, char* msg) { return cwbvh_validate(*c, prim_aabbs, n, msg); }
 
 OrcCwBvh* orc_build_cwbvh_from_tris(const OrcTriangle* tris, size_t n, u32 search_distance, size_t search_depth_threshold,
-                                    float reinsertion_batch_ratio, int precision, u32 max_prims_per_leaf, int threads,
+                                    float reinsertion_batch_ratio, int precision, u32 max_prims_per_leaf, int pre_split, int threads,
                                     double* core_seconds) {
     threads = clamp_threads(threads);
     auto t0 = std::chrono::steady_clock::now();  // cwbvh/builder.rs:62
     // PlocBuilder::build over &[Triangle]: aabbs[i].aabb() is evaluated inside the leaf-init loop (ploc/mod.rs:221,240)
     std::vector<OrcAabb> aabbs(n);
     std::vector<u32> indices(n);
+    if (pre_split) {  // cwbvh/builder.rs:27-61; the clock starts after the AABB / average pass (:45)
+        float avg, largest;
+        presplit_inputs(tris, n, aabbs, indices, &avg, &largest);
+        t0 = std::chrono::steady_clock::now();
+        split_aabbs_preset(aabbs, indices, tris, avg, largest);
+    } else {
 #pragma omp parallel for num_threads(threads) schedule(static) if (threads > 1 && n >= 500000)
-    for (long i = 0; i < (long)n; i++) {
-        aabbs[i] = tri_aabb(tris[i]);
-        indices[i] = (u32)i;
+        for (long i = 0; i < (long)n; i++) {
+            aabbs[i] = tri_aabb(tris[i]);
+            indices[i] = (u32)i;
+        }
     }
-    OrcBvh2* bvh2 = orc_ploc_build(aabbs.data(), indices.data(), n, search_distance, precision, search_depth_threshold, threads);
+    OrcBvh2* bvh2 = orc_ploc_build(aabbs.data(), indices.data(), aabbs.size(), search_distance, precision, search_depth_threshold, threads);
+    bvh2->uses_spatial_splits = pre_split != 0;  // :72
     orc_reinsertion_run(bvh2, reinsertion_batch_ratio, nullptr, 0, threads);
     u32 mp = std::min<u32>(std::max<u32>(max_prims_per_leaf, 1), 3);  // cwbvh/builder.rs:74 clamp(1,3)
     OrcCwBvh* c = bvh2_to_cwbvh(*bvh2, mp, true, false);

@@ -87,10 +87,23 @@ size_t    orc_cwbvh_prim_count(const OrcCwBvh*);
 void      orc_cwbvh_get(const OrcCwBvh*, OrcCwBvhNode* nodes, uint32_t* primitive_indices, OrcAabb* total_aabb);
 int       orc_cwbvh_validate(const OrcCwBvh*, const OrcAabb* prim_aabbs, size_t n, char* msg); /* cwbvh/mod.rs:747-908 */
 
-/* one-call builder (cwbvh/builder.rs:20-85; pre_split must be 0). core_seconds mirrors core_build_time. */
+/* one-call builder (cwbvh/builder.rs:20-85). core_seconds mirrors core_build_time. */
 OrcCwBvh* orc_build_cwbvh_from_tris(const OrcTriangle* tris, size_t n, uint32_t search_distance,
                                     size_t search_depth_threshold, float reinsertion_batch_ratio, int precision,
-                                    uint32_t max_prims_per_leaf, int threads, double* core_seconds);
+                                    uint32_t max_prims_per_leaf, int pre_split, int threads, double* core_seconds);
+
+/* -- spatial pre-splits (splits.rs:16-158) ------------------------------------------------------------- */
+/* split_aabbs_precise on caller arrays holding n entries with room for cap; returns the new count (> cap: nothing past
+ * cap was written). */
+size_t orc_split_aabbs_precise(OrcAabb* aabbs, uint32_t* indices, size_t n, size_t cap, const OrcTriangle* tris,
+                               float area_thresh_low, float area_thresh_high, float split_factor_low, float split_factor_high,
+                               uint32_t max_iterations, uint32_t split_tests);
+/* the builders' prologue (cwbvh/builder.rs:27-54): triangle AABBs, sequential-f32 average and max half area, then
+ * split_aabbs_preset; returns the split count */
+size_t orc_presplit_tris(const OrcTriangle* tris, size_t n, OrcAabb* aabbs_out, uint32_t* indices_out, size_t cap,
+                         float* avg_half_area, float* largest_half_area);
+void   orc_bvh2_set_uses_spatial_splits(OrcBvh2*, int);   /* bvh2/mod.rs:84: relaxes validate() as the reference does */
+void   orc_cwbvh_set_uses_spatial_splits(OrcCwBvh*, int); /* cwbvh/mod.rs:54 */
 
 /* -- traversal (cwbvh/mod.rs:169-245, traverse_macro.rs:59-126, node.rs:86-231, simd.rs:17-100) -------- */
 /* bvh_tris are the triangles pre-permuted by primitive_indices (examples/obj_cwbvh.rs:63-67).
@@ -111,10 +124,11 @@ void orc_bvh2_ray_traverse_miss(const OrcBvh2*, const OrcTriangle* bvh_tris, con
                                 uint64_t* counters);
 void orc_bvh2_ray_traverse_anyhit_count(const OrcBvh2*, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, uint32_t* counts,
                                         int threads);
-/* build_bvh2_from_tris (bvh2/builder.rs:17-91) without pre-splits */
+/* build_bvh2_from_tris (bvh2/builder.rs:17-91) */
 OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, uint32_t search_distance, size_t search_depth_threshold,
                                   float reinsertion_batch_ratio, float post_collapse_multiplier, int precision,
-                                  uint32_t max_prims_per_leaf, float collapse_traversal_cost, int threads, double* core_seconds);
+                                  uint32_t max_prims_per_leaf, float collapse_traversal_cost, int pre_split, int threads,
+                                  double* core_seconds);
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray);               /* triangle.rs:35-76 */
 void  orc_triangle_normal(const OrcTriangle* tri, float* out3);                         /* triangle.rs:20-24 */
 int   orc_max_threads(void);

@@ -33,4 +33,5 @@ def scenes(kitchen_tris):
         "terrain32": tu.demoscene(32, 0),
         "soup4k": tu.triangle_soup(4096, 3),
         "kitchen": kitchen_tris,
+        "splitty": tu.soup_with_large_triangles(3000, 40, 5),
     }

@@ -55,7 +55,11 @@ def lib():
             "orc_bvh2_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, vp]),
             "orc_bvh2_ray_traverse_miss": (None, [vp, vp, vp, sz, vp, i32, vp]),
             "orc_bvh2_ray_traverse_anyhit_count": (None, [vp, vp, vp, sz, vp, i32]),
-            "orc_build_bvh2_from_tris": (vp, [vp, sz, u32, sz, f32, f32, i32, u32, f32, i32, vp]),
+            "orc_build_bvh2_from_tris": (vp, [vp, sz, u32, sz, f32, f32, i32, u32, f32, i32, i32, vp]),
+            "orc_split_aabbs_precise": (sz, [vp, vp, sz, sz, vp, f32, f32, f32, f32, u32, u32]),
+            "orc_presplit_tris": (sz, [vp, sz, vp, vp, sz, vp, vp]),
+            "orc_bvh2_set_uses_spatial_splits": (None, [vp, i32]),
+            "orc_cwbvh_set_uses_spatial_splits": (None, [vp, i32]),
             "orc_bvh2_set_leaf_aabbs": (None, [vp, vp]),
             "orc_reinsertion_run": (None, [vp, f32, vp, sz, i32]),
             "orc_reinsertion_run_with_candidates": (None, [vp, vp, sz, u32, i32]),
@@ -68,7 +72,7 @@ def lib():
             "orc_cwbvh_prim_count": (sz, [vp]),
             "orc_cwbvh_get": (None, [vp, vp, vp, vp]),
             "orc_cwbvh_validate": (i32, [vp, vp, sz, C.c_char_p]),
-            "orc_build_cwbvh_from_tris": (vp, [vp, sz, u32, sz, f32, i32, u32, i32, vp]),
+            "orc_build_cwbvh_from_tris": (vp, [vp, sz, u32, sz, f32, i32, u32, i32, i32, vp]),
             "orc_cwbvh_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
             "orc_cwbvh_ray_traverse_miss": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
             "orc_cwbvh_ray_traverse_anyhit_count": (None, [vp, vp, vp, sz, vp, i32]),
@@ -292,20 +296,56 @@ def cwbvh_from(nodes, prims, total_aabb=None) -> CwBvh:
 
 
 # BvhBuildParams presets (reference src/lib.rs:233-305) as (search_distance, depth_threshold, reinsertion_ratio,
-# precision, max_prims_per_leaf); pre_split presets are listed for completeness and rejected by build_cwbvh_from_tris.
+# precision, max_prims_per_leaf[, pre_split])
 PRESETS = {
     "fastest_build": (1, 0, 0.0, 64, 1),
     "very_fast_build": (1, 0, 0.01, 64, 8),
     "fast_build": (6, 2, 0.02, 64, 8),
     "medium_build": (14, 3, 0.05, 64, 8),
+    "slow_build": (24, 2, 0.2, 128, 8, 1),
+    "very_slow_build": (14, 1, 1.0, 128, 8, 1),
 }
+
+
+def split_aabbs_precise(aabbs, indices, tris, lo, hi, f_lo, f_hi, max_iterations, split_tests):
+    """splits.rs:49-125; returns the grown (aabbs, indices)"""
+    aabbs = _f32c(aabbs, 8)
+    tris = _f32c(tris, 12)
+    n = aabbs.shape[0]
+    cap = max(2 * n, 1024)
+    while True:
+        a = np.zeros((cap, 8), np.float32)
+        idx = np.zeros(cap, np.uint32)
+        a[:n] = aabbs
+        idx[:n] = np.asarray(indices, dtype=np.uint32)
+        m = lib().orc_split_aabbs_precise(_p(a), _p(idx), n, cap, _p(tris), lo, hi, f_lo, f_hi, max_iterations, split_tests)
+        if m <= cap:
+            return a[:m].copy(), idx[:m].copy()
+        cap = m
+
+
+def presplit_tris(tris):
+    """cwbvh/builder.rs:27-54 prologue + split_aabbs_preset: returns (aabbs, indices, avg_half_area, largest_half_area)"""
+    tris = _f32c(tris, 12)
+    n = tris.shape[0]
+    cap = max(2 * n, 1024)
+    avg, largest = C.c_float(0), C.c_float(0)
+    while True:
+        a = np.zeros((cap, 8), np.float32)
+        idx = np.zeros(cap, np.uint32)
+        m = lib().orc_presplit_tris(_p(tris), n, _p(a), _p(idx), cap, C.byref(avg), C.byref(largest))
+        if m <= cap:
+            return a[:m].copy(), idx[:m].copy(), np.float32(avg.value), np.float32(largest.value)
+        cap = m
 
 
 def build_cwbvh_from_tris(tris, preset="medium_build", threads=1):
     tris = _f32c(tris, 12) if len(tris) else np.zeros((0, 12), np.float32)
-    sd, thr, ratio, prec, mp = PRESETS[preset] if isinstance(preset, str) else preset
+    cfg = PRESETS[preset] if isinstance(preset, str) else preset
+    sd, thr, ratio, prec, mp = cfg[:5]
+    pre_split = int(cfg[5]) if len(cfg) > 5 else 0
     secs = C.c_double(0.0)
-    h = lib().orc_build_cwbvh_from_tris(_p(tris), tris.shape[0], sd, thr, ratio, prec, mp, threads, C.byref(secs))
+    h = lib().orc_build_cwbvh_from_tris(_p(tris), tris.shape[0], sd, thr, ratio, prec, mp, pre_split, threads, C.byref(secs))
     c = CwBvh(h)
     c.core_build_seconds = secs.value
     return c
@@ -317,15 +357,19 @@ BVH2_PRESETS = {
     "very_fast_build": (1, 0, 0.01, 0.0, 64, 8, 3.0),
     "fast_build": (6, 2, 0.02, 0.0, 64, 8, 3.0),
     "medium_build": (14, 3, 0.05, 2.0, 64, 8, 3.0),
+    "slow_build": (24, 2, 0.2, 2.0, 128, 8, 3.0, 1),
+    "very_slow_build": (14, 1, 1.0, 1.0, 128, 8, 3.0, 1),
 }
 
 
 def build_bvh2_from_tris(tris, preset="medium_build", threads=1) -> Bvh2:
-    """bvh2/builder.rs:17-91 without pre-splits"""
+    """bvh2/builder.rs:17-91"""
     tris = _f32c(tris, 12) if len(tris) else np.zeros((0, 12), np.float32)
-    sd, thr, ratio, mult, prec, mp, cost = BVH2_PRESETS[preset] if isinstance(preset, str) else preset
+    cfg = BVH2_PRESETS[preset] if isinstance(preset, str) else preset
+    sd, thr, ratio, mult, prec, mp, cost = cfg[:7]
+    pre_split = int(cfg[7]) if len(cfg) > 7 else 0
     secs = C.c_double(0.0)
-    b = Bvh2(lib().orc_build_bvh2_from_tris(_p(tris), tris.shape[0], sd, thr, ratio, mult, prec, mp, cost, threads, C.byref(secs)))
+    b = Bvh2(lib().orc_build_bvh2_from_tris(_p(tris), tris.shape[0], sd, thr, ratio, mult, prec, mp, cost, pre_split, threads, C.byref(secs)))
     b.core_build_seconds = secs.value
     return b
 

@@ -70,12 +70,15 @@ def rays_for(tris, n_side=96, seed=7):
     return np.concatenate([prim, rnd, axis], axis=0)
 
 
+@pytest.mark.parametrize("precision", [64, 128])
 @pytest.mark.parametrize("scene", SCENES)
-def test_morton_codes_and_sorted_order(api, scenes, scene):
+def test_morton_codes_and_sorted_order(api, scenes, scene, precision):
     aabbs = ob.tri_aabbs(scenes[scene])
-    lo, hi, order, total = ob.morton_sort(aabbs)
-    glo, ghi, gorder, gtotal = api.PlocBuilder().morton_sort(aabbs)
+    lo, hi, order, total = ob.morton_sort(aabbs, precision)
+    glo, ghi, gorder, gtotal = api.PlocBuilder().morton_sort(aabbs, api.SortPrecision(precision))
     assert np.array_equal(glo, lo)
+    assert np.array_equal(ghi, hi)
+    assert precision == 64 or hi.any()
     assert np.array_equal(gorder, order)
     assert np.array_equal(gtotal[[0, 1, 2, 4, 5, 6]], total[[0, 1, 2, 4, 5, 6]])
 
@@ -108,6 +111,43 @@ def test_ploc_bvh2_bit_exact(api, scenes, scene, cfg):
     assert np.array_equal(gp, wp)
     assert_nodes_equal(gn, wn, f"{scene} ploc r={sd} thr={thr}")
     assert got.children_are_ordered_after_parents
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("cfg", [(24, 2), (14, 1), (1, 0)])
+def test_ploc_u128_bvh2_bit_exact(api, scenes, scene, cfg):
+    # SortPrecision::U128 (ploc/mod.rs:686-701, morton.rs:65-89): the sort of the slow / very_slow presets (lib.rs:282-305)
+    sd, thr = cfg
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, sd, 128, thr)
+    wn, wp = want.get()
+    got = api.PlocBuilder().build(sd, aabbs, None, api.SortPrecision.U128, thr)
+    gn, gp = got.download()
+    assert got.ploc_iterations == want.ploc_iterations
+    assert np.array_equal(gp, wp)
+    assert_nodes_equal(gn, wn, f"{scene} ploc u128 r={sd} thr={thr}")
+
+
+def test_u128_sort_separates_points_that_tie_in_63_bits(api):
+    # centres closer than 2^-21 of the scene extent share a 63-bit code but not a 126-bit one; order must follow the
+    # 126-bit code (and stay stable for exact duplicates)
+    rng = np.random.default_rng(5)
+    n = 20000
+    c = np.zeros((n, 3), np.float64)
+    c[:] = rng.random((n // 100, 3)).repeat(100, axis=0) + rng.random((n, 3)) * 2.0 ** -24
+    c[-1] = 0.0
+    c[-2] = 1.0
+    c[1000:1100] = c[1000]  # exact duplicates
+    aabbs = np.zeros((n, 8), np.float32)
+    aabbs[:, 0:3] = c
+    aabbs[:, 4:7] = c
+    lo, hi, order, _ = ob.morton_sort(aabbs, 128)
+    glo, ghi, gorder, _ = api.PlocBuilder().morton_sort(aabbs, api.SortPrecision.U128)
+    assert np.array_equal(glo, lo) and np.array_equal(ghi, hi) and np.array_equal(gorder, order)
+    lo64, _, order64, _ = ob.morton_sort(aabbs, 64)
+    assert not np.array_equal(order64, order)
+    k = [(int(h) << 64) | int(l) for h, l in zip(ghi[gorder], glo[gorder])]
+    assert all(a <= b for a, b in zip(k, k[1:]))
 
 
 def test_ploc_from_triangles_equals_from_aabbs(api, scenes):
@@ -355,9 +395,11 @@ def test_nan_input_is_an_error_not_a_hang(api):
 def test_unsupported_paths_fail_loudly(api):
     tris = tu.cornell_box()
     with pytest.raises(api.ObvhsError):
-        api.build_cwbvh_from_tris(tris, api.BvhBuildParams.slow_build())  # pre_split
-    with pytest.raises(api.ObvhsError):
         api.PlocBuilder().build(7, ob.tri_aabbs(tris))  # not a PlocSearchDistance
+    with pytest.raises(api.ObvhsError):
+        api.PlocBuilder().build(6, ob.tri_aabbs(tris), None, 96)  # not a SortPrecision
+    with pytest.raises(api.ObvhsError):
+        api.bvh2_to_cwbvh(api.PlocBuilder().build(6, ob.tri_aabbs(tris)), 3, True, True)  # include_exact_node_aabbs
 
 
 def test_large_scene_full_parity_and_properties(api):

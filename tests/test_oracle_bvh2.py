@@ -78,7 +78,7 @@ def test_bvh2_degenerate_builds_never_hit():
         "nothing": np.zeros((0, 8), np.float32),
     }
     for name, aabbs in cases.items():
-        for sd, thr, ratio, mult, prec, mp, cost in ob.BVH2_PRESETS.values():
+        for sd, thr, ratio, mult, prec, mp, cost in (cfg[:7] for cfg in ob.BVH2_PRESETS.values()):
             b = ob.ploc_build(aabbs, None, sd, prec, thr)
             b.reinsertion_run(ratio)
             b.collapse(mp, cost)

@@ -25,7 +25,7 @@ def shade_normals(c, tris, rays):
     return out, hits
 
 
-@pytest.mark.parametrize("preset", ["fastest_build", "very_fast_build", "fast_build", "medium_build"])
+@pytest.mark.parametrize("preset", ["fastest_build", "very_fast_build", "fast_build", "medium_build", "slow_build", "very_slow_build"])
 def test_kitchen_golden_hash(kitchen_tris, preset):
     # examples/obj_cwbvh.rs:142-181: width 32 render, hash of per-pixel normals == 1343358762
     rays = camera.primary_rays(camera.kitchen_camera(32))
@@ -65,7 +65,7 @@ def test_degenerate_builds_do_not_hit():
     # tests/mod.rs:65-88: one empty AABB, and nothing at all
     ray = make_rays(np.array([[0.0, 0.0, 1.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
     empty = np.array([[F32_MAX, F32_MAX, F32_MAX, 0, -F32_MAX, -F32_MAX, -F32_MAX, 0]], np.float32)
-    for sd, thr, ratio, prec, mp in ob.PRESETS.values():
+    for sd, thr, ratio, prec, mp in (cfg[:5] for cfg in ob.PRESETS.values()):
         b = ob.ploc_build(empty, None, sd, prec, thr)
         b.reinsertion_run(ratio)
         c = b.to_cwbvh(min(max(mp, 1), 3))
@@ -88,7 +88,7 @@ def test_varying_prim_counts_validate():
     for n in range(31, 0, -1):
         t = tris[:n]
         aabbs = ob.tri_aabbs(t)
-        for sd, thr, ratio, prec, mp in ob.PRESETS.values():
+        for name, (sd, thr, ratio, prec, mp) in ((k, cfg[:5]) for k, cfg in ob.PRESETS.items()):
             b = ob.ploc_build(aabbs, None, sd, prec, thr)
             rc, msg = b.validate(aabbs)
             assert rc == 0, (n, msg)
@@ -98,6 +98,12 @@ def test_varying_prim_counts_validate():
             c = b.to_cwbvh(min(max(mp, 1), 3))
             rc, msg = c.validate(aabbs)
             assert rc == 0, (n, msg)
+            # the reference's loop goes through the triangle builders, pre-splits included (tests/mod.rs:95-98)
+            b2 = ob.build_bvh2_from_tris(t, name)
+            rc, msg = b2.validate(aabbs, tight_fit=name not in ("slow_build", "very_slow_build"))
+            assert rc == 0, (n, name, msg)
+            rc, msg = ob.build_cwbvh_from_tris(t, name).validate(aabbs)
+            assert rc == 0, (n, name, msg)
 
 
 def test_morton_split_matches_naive_interleave():
