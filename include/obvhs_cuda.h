@@ -136,6 +136,25 @@ int obvhs_cuda_ploc_build(ObvhsContext* ctx, const ObvhsAabb* aabbs, const uint3
 int obvhs_cuda_ploc_build_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, uint32_t search_distance,
                                uint32_t sort_precision, size_t search_depth_threshold, ObvhsBvh2** out);
 
+/* PlocBuilder::full_rebuild(&mut bvh, search_distance, sort_precision, search_depth_threshold)  (ploc/rebuild.rs:56-80):
+ * rebuilds the tree in place from its current leaves (inner nodes are ignored; multi-primitive leaves stay as they are). */
+int obvhs_cuda_ploc_full_rebuild(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t search_distance, uint32_t sort_precision,
+                                 size_t search_depth_threshold);
+/* PlocBuilder::partial_rebuild(&mut bvh, should_remove, ...)  (ploc/rebuild.rs:101-135). should_remove holds one byte per
+ * node (the reference takes a closure Fn(usize) -> bool; compute_rebuild_path_flags produces exactly this array). Flagged
+ * chains are dissolved, the untouched subtrees and the flagged leaves are merged again by PLOC, and the new inner nodes
+ * reuse the freed slot pairs from the end of the node array downwards (ploc/mod.rs:449-462). Tie rule: collected nodes
+ * with equal Morton codes keep ascending node index. */
+int obvhs_cuda_ploc_partial_rebuild(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint8_t* should_remove, uint32_t search_distance,
+                                    uint32_t sort_precision, size_t search_depth_threshold);
+/* compute_rebuild_path_flags(&bvh, leaves, &mut flags)  (ploc/rebuild.rs:12-43): flags[i] = 1 for the given leaf nodes and
+ * every ancestor. Needs parents (obvhs_cuda_bvh2_compute_parents) like the reference, else OBVHS_ERR_INVALID_ARG.
+ * flags: node_count bytes, host or device. */
+int obvhs_cuda_compute_rebuild_path_flags(ObvhsContext* ctx, const ObvhsBvh2* bvh, const uint32_t* leaves, size_t n_leaves,
+                                          uint8_t* flags);
+/* Bvh2Node::set_aabb (bvh2/node.rs) for n nodes: bvh.nodes[node_ids[k]].set_aabb(aabbs[k]) (examples/physics.rs:446) */
+int obvhs_cuda_bvh2_set_node_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint32_t* node_ids, const ObvhsAabb* aabbs, size_t n);
+
 /* ---- Bvh2 (src/bvh2/mod.rs) ------------------------------------------------------------------------------ */
 void obvhs_cuda_bvh2_free(ObvhsBvh2* bvh);
 size_t obvhs_cuda_bvh2_node_count(const ObvhsBvh2* bvh);

@@ -72,6 +72,10 @@ SIGNATURES = {
     "obvhs_cuda_morton_sort": (_i32, [_vp, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_ploc_build": (_i32, [_vp, _vp, _vp, _sz, _u32, _u32, _sz, _PP]),
     "obvhs_cuda_ploc_build_tris": (_i32, [_vp, _vp, _sz, _u32, _u32, _sz, _PP]),
+    "obvhs_cuda_ploc_full_rebuild": (_i32, [_vp, _vp, _u32, _u32, _sz]),
+    "obvhs_cuda_ploc_partial_rebuild": (_i32, [_vp, _vp, _vp, _u32, _u32, _sz]),
+    "obvhs_cuda_compute_rebuild_path_flags": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_set_node_aabbs": (_i32, [_vp, _vp, _vp, _vp, _sz]),
     "obvhs_cuda_bvh2_free": (None, [_vp]),
     "obvhs_cuda_bvh2_node_count": (_sz, [_vp]),
     "obvhs_cuda_bvh2_prim_count": (_sz, [_vp]),
@@ -303,6 +307,13 @@ class Bvh2:
     def refit_all(self):
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_refit_all(self.ctx.h, self.h))
 
+    def set_node_aabbs(self, node_ids, aabbs):
+        """bvh.nodes[id].set_aabb(aabb) for a list of nodes (examples/physics.rs:446)"""
+        ids = np.ascontiguousarray(node_ids, dtype=np.uint32)
+        a = _as_f32(aabbs, 8)
+        assert a.shape[0] == ids.shape[0]
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_node_aabbs(self.ctx.h, self.h, _ptr(ids), _ptr(a), ids.shape[0]))
+
     def set_leaf_aabbs(self, prim_aabbs):
         a = _as_f32(prim_aabbs, 8)
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_leaf_aabbs(self.ctx.h, self.h, _ptr(a), a.shape[0]))
@@ -413,6 +424,14 @@ def presplit_tris(triangles, ctx: Context | None = None):
     return a, idx, np.float32(avg.value), np.float32(largest.value)
 
 
+def compute_rebuild_path_flags(bvh: Bvh2, leaves, flags=None):
+    """src/ploc/rebuild.rs:12-43: one byte per node, 1 for the given leaf nodes and all their ancestors."""
+    ids = np.ascontiguousarray(leaves, dtype=np.uint32)
+    out = flags if flags is not None else np.zeros(bvh.node_count, dtype=np.uint8)
+    bvh.ctx.check(bvh.ctx.lib.obvhs_cuda_compute_rebuild_path_flags(bvh.ctx.h, bvh.h, _ptr(ids), ids.shape[0], _ptr(out)))
+    return out
+
+
 class PlocBuilder:
     """src/ploc/mod.rs:35-159. The context keeps the scratch the reference's builder keeps for reuse."""
 
@@ -442,6 +461,21 @@ class PlocBuilder:
         self.ctx.check(self.ctx.lib.obvhs_cuda_ploc_build_tris(self.ctx.h, _ptr(t), t.shape[0], int(search_distance), int(sort_precision),
                                                               int(search_depth_threshold), C.byref(h)))
         return Bvh2(self.ctx, h)
+
+    def full_rebuild(self, bvh: Bvh2, search_distance, sort_precision=SortPrecision.U64, search_depth_threshold: int = 0):
+        """src/ploc/rebuild.rs:56-80"""
+        self.ctx.check(self.ctx.lib.obvhs_cuda_ploc_full_rebuild(self.ctx.h, bvh.h, int(search_distance), int(sort_precision),
+                                                                 int(search_depth_threshold)))
+
+    def partial_rebuild(self, bvh: Bvh2, should_remove, search_distance, sort_precision=SortPrecision.U64, search_depth_threshold: int = 0):
+        """src/ploc/rebuild.rs:101-135. should_remove: one flag per node (array / device tensor), or a callable node_id -> bool
+        like the reference's closure (evaluated on the host for every node)."""
+        if callable(should_remove):
+            should_remove = np.fromiter((bool(should_remove(i)) for i in range(bvh.node_count)), dtype=np.uint8, count=bvh.node_count)
+        flags = should_remove if _is_torch(should_remove) else np.ascontiguousarray(should_remove, dtype=np.uint8)
+        assert flags.shape[0] == bvh.node_count
+        self.ctx.check(self.ctx.lib.obvhs_cuda_ploc_partial_rebuild(self.ctx.h, bvh.h, _ptr(flags), int(search_distance), int(sort_precision),
+                                                                    int(search_depth_threshold)))
 
     def morton_sort(self, aabbs, sort_precision=SortPrecision.U64):
         """Stage probe: (codes_lo, codes_hi, sorted order, scene AABB) -- see obvhs_cuda_morton_sort."""

@@ -495,6 +495,60 @@ int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     ARG_CHECK(ctx, bvh, "bvh is null");
     return bvh2_refit_all_device(ctx, bvh);
 }
+// PlocBuilder::full_rebuild / partial_rebuild / compute_rebuild_path_flags (src/ploc/rebuild.rs)
+int obvhs_cuda_ploc_full_rebuild(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t search_distance, uint32_t sort_precision,
+                                 size_t search_depth_threshold) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    ST_TRY(ploc_full_rebuild_device(ctx, bvh, search_distance, sort_precision, search_depth_threshold));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+int obvhs_cuda_ploc_partial_rebuild(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint8_t* should_remove, uint32_t search_distance,
+                                    uint32_t sort_precision, size_t search_depth_threshold) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (bvh->node_count < 2 || should_remove), "null argument");
+    DevBuf<u8> st;
+    const u8* d_flags = nullptr;
+    ST_TRY(stage_in(ctx, should_remove, bvh->node_count, st, &d_flags));
+    ST_TRY(ploc_partial_rebuild_device(ctx, bvh, d_flags, search_distance, sort_precision, search_depth_threshold));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+int obvhs_cuda_compute_rebuild_path_flags(ObvhsContext* ctx, const ObvhsBvh2* bvh, const uint32_t* leaves, size_t n_leaves, uint8_t* flags) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n_leaves == 0 || leaves) && (bvh->node_count < 2 || flags), "null argument");
+    if (bvh->node_count < 2) return OBVHS_OK;
+    DevBuf<u32> st;
+    DevBuf<u8> d_out;
+    const u32* d_leaves = nullptr;
+    ST_TRY(stage_in(ctx, leaves, n_leaves, st, &d_leaves));
+    u8* d_flags = flags;
+    const bool out_dev = obvhs_is_device_ptr(flags);
+    if (!out_dev) {
+        CU_TRY(ctx, d_out.alloc(bvh->node_count, ctx->stream));
+        d_flags = d_out.p;
+    }
+    ST_TRY(ploc_compute_rebuild_path_flags_device(ctx, bvh, d_leaves, n_leaves, d_flags));
+    if (!out_dev) ST_TRY(copy_out(ctx, flags, (const u8*)d_flags, bvh->node_count));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+// Bvh2Node::set_aabb on a list of nodes (examples/physics.rs:446): the leaves get their new boxes before a partial rebuild
+int obvhs_cuda_bvh2_set_node_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const uint32_t* node_ids, const ObvhsAabb* aabbs, size_t n) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || (node_ids && aabbs)), "null argument");
+    DevBuf<u32> st_ids;
+    DevBuf<ObvhsAabb> st_aabbs;
+    const u32* d_ids = nullptr;
+    const ObvhsAabb* d_aabbs = nullptr;
+    ST_TRY(stage_in(ctx, node_ids, n, st_ids, &d_ids));
+    ST_TRY(stage_in(ctx, aabbs, n, st_aabbs, &d_aabbs));
+    ST_TRY(bvh2_set_node_aabbs_device(ctx, bvh, d_ids, d_aabbs, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+
 int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* prim_aabbs, size_t n) {
     API_ENTER(ctx);
     ARG_CHECK(ctx, bvh && (n == 0 || prim_aabbs), "null argument");

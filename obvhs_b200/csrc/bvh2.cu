@@ -71,6 +71,20 @@ __global__ void __launch_bounds__(256) pack_nodes_kernel(const float4* __restric
     store_node(out + i, make_node32(Box{a.x, a.y, a.z, b.x, b.y, b.z}, __float_as_uint(c.x), __float_as_uint(c.y)));
 }
 
+// Bvh2Node::set_aabb (bvh2/node.rs:103-107) for a list of nodes; prim_count / first_index are kept
+__global__ void __launch_bounds__(256) set_node_aabbs_kernel(Node32* nodes, u32 n_nodes, const u32* __restrict__ ids, const float4* __restrict__ aabbs,
+                                                             u32 n) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const u32 id = ids[k];
+    if (id >= n_nodes) return;
+    Node32 nd = load_node(nodes + id);
+    const float4 lo = aabbs[2 * (size_t)k], hi = aabbs[2 * (size_t)k + 1];
+    nd.minx = lo.x; nd.miny = lo.y; nd.minz = lo.z;
+    nd.maxx = hi.x; nd.maxy = hi.y; nd.maxz = hi.z;
+    store_node(nodes + id, nd);
+}
+
 }  // namespace
 
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
@@ -84,6 +98,14 @@ int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
 int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents) {
     if (bvh->node_count == 0) return OBVHS_OK;
     compute_parents_kernel<<<div_up(bvh->node_count, 256), 256, 0, ctx->stream>>>(bvh->nodes, (u32)bvh->node_count, d_parents);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
+int bvh2_set_node_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, const ObvhsAabb* d_aabbs, size_t n) {
+    if (n == 0) return OBVHS_OK;
+    set_node_aabbs_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(bvh->nodes, (u32)bvh->node_count, d_node_ids,
+                                                                  reinterpret_cast<const float4*>(d_aabbs), (u32)n);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }

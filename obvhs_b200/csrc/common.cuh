@@ -282,6 +282,11 @@ struct PlocMortonOut {
 int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
                       u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
                       const PlocMortonOut* probe);
+// ploc.cu : PlocBuilder::full_rebuild / partial_rebuild / compute_rebuild_path_flags (src/ploc/rebuild.rs); flags are one byte per node
+int ploc_full_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 search_distance, u32 sort_precision, size_t search_depth_threshold);
+int ploc_partial_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u8* d_should_remove, u32 search_distance, u32 sort_precision,
+                                size_t search_depth_threshold);
+int ploc_compute_rebuild_path_flags_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const u32* d_leaves, size_t n_leaves, u8* d_flags);
 // splits.cu : spatial pre-splits (src/splits.rs). Arrays live in the arena of the API call in flight and grow like the Vecs.
 struct SplitArrays {
     ObvhsAabb* aabbs = nullptr;
@@ -301,6 +306,7 @@ int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals,
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents);
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+int bvh2_set_node_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, const ObvhsAabb* d_aabbs, size_t n);
 // collapse.cu
 int bvh2_collapse_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 max_prims, float traversal_cost);
 // reinsertion.cu

@@ -291,9 +291,17 @@ constexpr u64 SCAN_AGG = 1ull << 62, SCAN_INCL = 2ull << 62, SCAN_MASK = (1ull <
 // position, with left = nodes[higher], right = nodes[lower] stored at insert_index-2, -1 (slots taken downwards in
 // sweep order). Positions are therefore exclusive prefix sums of (carried | emits) and of (emits): one chained scan
 // over a packed (outputs, merges) pair.
+// free_slots != null is the reference's REBUILD mode (ploc/mod.rs:449-462): the m-th merge of the whole build (in sweep
+// order) takes the m-th freed slot pair counted from the END of bvh.nodes, i.e. free_slots[m] with the table sorted
+// descending; insert_index then only counts merges (insert_start - 2 * merges).
+__device__ __forceinline__ u32 child_slot(const u32* __restrict__ free_slots, u32 insert_start, u32 insert_base, u32 mi) {
+    return free_slots ? free_slots[(insert_start - insert_base) / 2 + mi] : insert_base - 2 * (mi + 1);
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32* __restrict__ cur, Node32* __restrict__ next,
                                                                    Node32* __restrict__ bvh_nodes, const signed char* __restrict__ merge,
-                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket) {
+                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket,
+                                                                   const u32* __restrict__ free_slots, u32 insert_start) {
     __shared__ signed char sm[MERGE_TILE + 2 * MERGE_HALO];
     __shared__ u64 s_wsum[MERGE_THREADS / 32];
     __shared__ u64 s_excl;
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
                 u32 mi = (u32)(run >> 31);
                 int m = sm[threadIdx.x * MERGE_ITEMS + k + MERGE_HALO];
                 Node32 right = load_node(cur + (i + m));
-                u32 slot = insert_base - 2 * (mi + 1);
+                u32 slot = child_slot(free_slots, insert_start, insert_base, mi);
                 store_node(bvh_nodes + slot, left);
                 store_node(bvh_nodes + slot + 1, right);
                 store_node(next + pos, make_node32(box_union(node_box(left), node_box(right)), 0u, slot));
@@ -407,7 +415,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
 constexpr int PLOC_TAIL = 2048, TAIL_THREADS = 1024, TAIL_ITEMS = PLOC_TAIL / TAIL_THREADS;
 template <int R>
 __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* __restrict__ cur_g, Node32* __restrict__ bvh_nodes, PlocGlobals* g,
-                                                                 int parity, u32 depth, u32 search_depth_threshold) {
+                                                                 int parity, u32 depth, u32 search_depth_threshold,
+                                                                 const u32* __restrict__ free_slots, u32 insert_start) {
     extern __shared__ __align__(128) unsigned char tail_smem[];
     Node32* buf[2] = {reinterpret_cast<Node32*>(tail_smem), reinterpret_cast<Node32*>(tail_smem) + PLOC_TAIL};
     __shared__ signed char sm[PLOC_TAIL];
@@ -468,7 +477,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* _
                 if (f & 2u) {
                     u32 mi = run >> 16;
                     Node32 right = cur[(int)i + sm[i]];
-                    u32 slot = insert - 2 * (mi + 1);
+                    u32 slot = child_slot(free_slots, insert_start, insert, mi);
                     store_node(bvh_nodes + slot, left);
                     store_node(bvh_nodes + slot + 1, right);
                     next[pos] = make_node32(box_union(node_box(left), node_box(right)), 0u, slot);
@@ -506,7 +515,8 @@ void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGl
 }
 
 template <int R>
-cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth, u32 thr) {
+cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth, u32 thr,
+                        const u32* free_slots, u32 insert_start) {
     constexpr int smem = 2 * PLOC_TAIL * (int)sizeof(Node32);
     static bool attr = false;
     if (!attr) {
@@ -514,11 +524,15 @@ cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes,
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    ploc_tail_kernel<R><<<1, TAIL_THREADS, smem, ctx->stream>>>(cur, bvh_nodes, g, parity, depth, thr);
+    ploc_tail_kernel<R><<<1, TAIL_THREADS, smem, ctx->stream>>>(cur, bvh_nodes, g, parity, depth, thr, free_slots, insert_start);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, Node32* bufA_p, Node32* bufB_p, size_t n, u32 search_distance,
+                            u32 sort_precision, size_t search_depth_threshold, const PlocMortonOut* probe, const u32* free_slots,
+                            bool check_nan);
 
 int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTriangle* d_tris, const u32* d_indices, size_t n,
                       u32 search_distance, u32 sort_precision, size_t search_depth_threshold, ObvhsBvh2** out,
@@ -568,13 +582,44 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
 
     DevBuf<PlocGlobals> g;
     DevBuf<Node32> bufA, bufB;
+    CU_TRY(ctx, g.alloc(1, s));
+    CU_TRY(ctx, bufA.alloc(n, s));
+    CU_TRY(ctx, bufB.alloc(n, s));
+    {
+        TraceScope ts(ctx, "  ploc_leaves");
+        ploc_globals_init_kernel<<<1, 32, 0, s>>>(g.p, un);
+        KERNEL_CHECK(ctx);
+        const int grid_stride_blocks = (int)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 8);
+        if (d_tris) leaf_init_kernel<true><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_tris), d_indices, un, bufA.p, g.p);
+        else leaf_init_kernel<false><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_aabbs), d_indices, un, bufA.p, g.p);
+        KERNEL_CHECK(ctx);
+    }
+    ST_TRY(ploc_from_leaves(ctx, bvh, g.p, bufA.p, bufB.p, n, search_distance, sort_precision, search_depth_threshold, probe, nullptr, true));
+    bvh->children_are_ordered_after_parents = true;  // ploc/mod.rs:502
+    guard.b = nullptr;
+    *out = bvh;
+    return OBVHS_OK;
+}
+
+// build_ploc_from_leaves (ploc/mod.rs:265-503) on `n` leaves/subtree roots in bufA (any order): Morton codes against the scene
+// box held in g->total_ord, sort, gather, then the search/merge iterations writing children into bvh->nodes (allocated by
+// the caller) and the last cluster into bvh->nodes[0]. free_slots: see child_slot(). Sets max_depth / ploc_iterations.
+static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, Node32* bufA_p, Node32* bufB_p, size_t n, u32 search_distance,
+                            u32 sort_precision, size_t search_depth_threshold, const PlocMortonOut* probe, const u32* free_slots,
+                            bool check_nan) {
+    cudaStream_t s = ctx->stream;
+    const u32 un = (u32)n;
+    const u32 insert_start = 2 * un - 1;
+    struct P {  // keeps the names of the code below
+        PlocGlobals* p;
+    } g{gp};
+    struct B {
+        Node32* p;
+    } bufA{bufA_p}, bufB{bufB_p};
     DevBuf<u64> keys, keys_alt;
     DevBuf<u32> vals, vals_alt;
     DevBuf<signed char> merge;
     DevBuf<u64> scan_status;
-    CU_TRY(ctx, g.alloc(1, s));
-    CU_TRY(ctx, bufA.alloc(n, s));
-    CU_TRY(ctx, bufB.alloc(n, s));
     CU_TRY(ctx, keys.alloc(n, s));
     CU_TRY(ctx, keys_alt.alloc(n, s));
     CU_TRY(ctx, vals.alloc(n, s));
@@ -582,13 +627,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     CU_TRY(ctx, merge.alloc(n, s));
     CU_TRY(ctx, scan_status.alloc(div_up(n, SEARCH_TILE) + 1, s));
 
-    TraceScope* tsp = new TraceScope(ctx, "  ploc_leaves_morton");
-    ploc_globals_init_kernel<<<1, 32, 0, s>>>(g.p, un);
-    KERNEL_CHECK(ctx);
-    const int grid_stride_blocks = (int)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 8);
-    if (d_tris) leaf_init_kernel<true><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_tris), d_indices, un, bufA.p, g.p);
-    else leaf_init_kernel<false><<<grid_stride_blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_aabbs), d_indices, un, bufA.p, g.p);
-    KERNEL_CHECK(ctx);
+    TraceScope* tsp = new TraceScope(ctx, "  ploc_morton");
     morton_params_kernel<<<1, 32, 0, s>>>(g.p);
     KERNEL_CHECK(ctx);
     const bool wide = sort_precision == 128;
@@ -632,7 +671,7 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     u32* h_state = reinterpret_cast<u32*>(ctx->pinned);
     u32 count = un;
     size_t depth = 0;
-    bool nan_checked = false;
+    bool nan_checked = !check_nan;
     while (count > PLOC_TAIL) {
         const int parity = (int)(depth & 1);
         const int r1 = (search_distance == 1 || depth < search_depth_threshold) ? 1 : 0;
@@ -647,13 +686,14 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
         }
         KERNEL_CHECK(ctx);
         ploc_merge_kernel<<<div_up(count, MERGE_TILE), MERGE_THREADS, 0, s>>>(cur, next, bvh->nodes, merge.p, g.p, parity, scan_status.p,
-                                                                            ticket);
+                                                                            ticket, free_slots, insert_start);
         KERNEL_CHECK(ctx);
         CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[parity ^ 1], sizeof(PlocState), cudaMemcpyDeviceToHost, s));
-        if (depth == 0) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
+        const bool read_nan = !nan_checked;
+        if (read_nan) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
         nan_checked = true;
-        if (depth == 0 && h_state[4]) {
+        if (read_nan && h_state[4]) {
             OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
             return OBVHS_ERR_NAN_INPUT;
         }
@@ -672,12 +712,12 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
         const u32 thr = (u32)std::min<size_t>(search_depth_threshold, 0xffffffffu);
         cudaError_t e;
         switch (search_distance) {
-            case 1: e = launch_tail<1>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
-            case 2: e = launch_tail<2>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
-            case 6: e = launch_tail<6>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
-            case 14: e = launch_tail<14>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
-            case 24: e = launch_tail<24>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
-            default: e = launch_tail<32>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr); break;
+            case 1: e = launch_tail<1>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
+            case 2: e = launch_tail<2>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
+            case 6: e = launch_tail<6>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
+            case 14: e = launch_tail<14>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
+            case 24: e = launch_tail<24>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
+            default: e = launch_tail<32>(ctx, cur, bvh->nodes, g.p, parity, (u32)depth, thr, free_slots, insert_start); break;
         }
         ctx->launches++;
         CU_TRY(ctx, e);
@@ -696,8 +736,200 @@ int ploc_build_device(ObvhsContext* ctx, const ObvhsAabb* d_aabbs, const ObvhsTr
     }
     bvh->max_depth = std::max<size_t>(96, depth + 1);  // ploc/mod.rs:501
     bvh->ploc_iterations = depth;
-    bvh->children_are_ordered_after_parents = true;  // ploc/mod.rs:502
-    guard.b = nullptr;
-    *out = bvh;
     return OBVHS_OK;
+}
+
+// ---- PlocBuilder::full_rebuild / partial_rebuild, compute_rebuild_path_flags (src/ploc/rebuild.rs) ---------------------------
+#include "compact.cuh"
+
+namespace {
+
+// rebuild.rs:153: total_aabb = *bvh.nodes[0].aabb() -- the root box (possibly stale) only scales the Morton codes
+__global__ void rebuild_globals_kernel(PlocGlobals* g, const Node32* __restrict__ nodes, u32 n_leaves) {
+    if (threadIdx.x == 0) {
+        const Node32 root = load_node(nodes);
+        g->total_ord[0] = f2ord(root.minx); g->total_ord[1] = f2ord(root.miny); g->total_ord[2] = f2ord(root.minz);
+        g->total_ord[3] = f2ord(root.maxx); g->total_ord[4] = f2ord(root.maxy); g->total_ord[5] = f2ord(root.maxz);
+        g->nan_flag = 0;
+        g->state[0].count = n_leaves;
+        g->state[0].insert_index = 2 * n_leaves - 1;
+        g->state[1].count = 0;
+        g->state[1].insert_index = 0;
+        g->ticket = 0;
+    }
+}
+
+// rebuild.rs:27-42: every given leaf flags itself and its ancestors. A thread may stop at a node another thread has
+// flagged: whoever set that flag keeps climbing, so every path still reaches the root.
+__global__ void __launch_bounds__(256) path_flags_kernel(const u32* __restrict__ leaves, u32 n_leaves, const u32* __restrict__ parents,
+                                                         u32 n_nodes, u8* flags) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_leaves) return;
+    u32 index = leaves[k];
+    if (index >= n_nodes) return;
+    volatile u8* vf = flags;
+    vf[index] = 1;
+    while (index > 0) {
+        index = parents[index];
+        if (vf[index]) break;
+        vf[index] = 1;
+    }
+}
+
+// rebuild.rs:112-131: the stack walk reaches a node iff every proper ancestor below the root is flagged (they are inner by
+// construction). A reached node is collected when it is unflagged or a leaf, otherwise its children are reached too.
+// cls: bit 0 = collected, bit 1 = reached (its slot is freed by set_invalid).
+__global__ void __launch_bounds__(256) rebuild_classify_kernel(const Node32* __restrict__ nodes, u32 n, const u32* __restrict__ parents,
+                                                               const u8* __restrict__ should_remove, u8* __restrict__ cls) {
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    if (v == 0) {
+        cls[0] = 0;
+        return;
+    }
+    bool reached = true;
+    for (u32 a = parents[v]; a != 0; a = parents[a])
+        if (!should_remove[a]) {
+            reached = false;
+            break;
+        }
+    const u32 prim_count = __float_as_uint(__ldg(reinterpret_cast<const float4*>(nodes + v)).w);
+    const bool collected = reached && (!should_remove[v] || prim_count != 0);
+    cls[v] = (collected ? 1 : 0) | (reached ? 2 : 0);
+}
+
+struct IsLeaf {  // rebuild.rs:70-74
+    const Node32* nodes;
+    __device__ bool operator()(u32 i) const { return __float_as_uint(__ldg(reinterpret_cast<const float4*>(nodes + i)).w) != 0; }
+};
+struct IsCollected {
+    const u8* cls;
+    __device__ bool operator()(u32 i) const { return (cls[i] & 1) != 0; }
+};
+struct IsFreedPairDesc {  // item i <-> the i-th odd node index counted from the end of the array
+    const u8* cls;
+    u32 last_odd;
+    __device__ bool operator()(u32 i) const { return (cls[last_odd - 2 * i] & 2) != 0; }
+};
+struct EmitNode {
+    const Node32* nodes;
+    Node32* out;
+    __device__ void operator()(u32 i, u32 rank) const { store_node(out + rank, load_node(nodes + i)); }
+};
+struct EmitFreedPair {
+    u32* out;
+    u32 last_odd;
+    __device__ void operator()(u32 i, u32 rank) const { out[rank] = last_odd - 2 * i; }
+};
+
+int read_u32(ObvhsContext* ctx, const u32* d, u32* out) {
+    u32* h = reinterpret_cast<u32*>(ctx->pinned);
+    CU_TRY(ctx, cudaMemcpyAsync(h, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = h[0];
+    return OBVHS_OK;
+}
+
+int rebuild_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* g, Node32* leaves, u32 n_leaves, const u32* free_slots,
+                        u32 search_distance, u32 sort_precision, size_t search_depth_threshold) {
+    DevBuf<Node32> bufB;
+    CU_TRY(ctx, bufB.alloc(n_leaves, ctx->stream));
+    rebuild_globals_kernel<<<1, 32, 0, ctx->stream>>>(g, bvh->nodes, n_leaves);
+    KERNEL_CHECK(ctx);
+    ST_TRY(ploc_from_leaves(ctx, bvh, g, leaves, bufB.p, n_leaves, search_distance, sort_precision, search_depth_threshold, nullptr, free_slots,
+                            false));
+    bvh->children_are_ordered_after_parents = free_slots == nullptr;  // ploc/mod.rs:502: !REBUILD
+    if (bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));   // rebuild.rs:177-179
+    if (bvh->bvh_tris) {  // primitive_indices did not change: the permuted triangles stay valid
+    }
+    return OBVHS_OK;
+}
+
+int check_rebuild_args(ObvhsContext* ctx, u32 search_distance, u32 sort_precision) {
+    if (sort_precision != 64 && sort_precision != 128) {
+        OBVHS_SET_ERR(ctx, "sort precision %u is not SortPrecision::U64 (64) or ::U128 (128)", sort_precision);
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    switch (search_distance) {
+        case 1: case 2: case 6: case 14: case 24: case 32: return OBVHS_OK;
+        default:
+            OBVHS_SET_ERR(ctx, "search distance %u is not one of 1,2,6,14,24,32", search_distance);
+            return OBVHS_ERR_INVALID_ARG;
+    }
+}
+
+}  // namespace
+
+int ploc_compute_rebuild_path_flags_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const u32* d_leaves, size_t n_leaves, u8* d_flags) {
+    if (bvh->node_count < 2) return OBVHS_OK;  // rebuild.rs:17-19
+    if (!bvh->parents) {                       // rebuild.rs:20-24 panics
+        OBVHS_SET_ERR(ctx, "parents must be computed before compute_rebuild_path_flags (call bvh2_compute_parents first)");
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    CU_TRY(ctx, cudaMemsetAsync(d_flags, 0, bvh->node_count, ctx->stream));
+    if (n_leaves) {
+        path_flags_kernel<<<div_up(n_leaves, 256), 256, 0, ctx->stream>>>(d_leaves, (u32)n_leaves, bvh->parents, (u32)bvh->node_count, d_flags);
+        KERNEL_CHECK(ctx);
+    }
+    return OBVHS_OK;
+}
+
+int ploc_full_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 search_distance, u32 sort_precision, size_t search_depth_threshold) {
+    if (bvh->node_count < 2) return OBVHS_OK;  // rebuild.rs:63-65
+    ST_TRY(check_rebuild_args(ctx, search_distance, sort_precision));
+    TraceScope ts(ctx, "full_rebuild");
+    const u32 n = (u32)bvh->node_count;
+    DevBuf<PlocGlobals> g;
+    DevBuf<Node32> leaves;
+    DevBuf<u32> tiles;
+    CU_TRY(ctx, g.alloc(1, ctx->stream));
+    CU_TRY(ctx, leaves.alloc((n + 1) / 2, ctx->stream));
+    CU_TRY(ctx, tiles.alloc((size_t)div_up(n, CP_TILE) + 1, ctx->stream));
+    // a tree over L leaves has 2L-1 nodes, so the leaves fit; collect them in node order (rebuild.rs:69-74)
+    ST_TRY(compact(ctx, IsLeaf{bvh->nodes}, EmitNode{bvh->nodes, leaves.p}, n, tiles.p, &g.p->ticket));
+    u32 n_leaves = 0;
+    ST_TRY(read_u32(ctx, &g.p->ticket, &n_leaves));
+    if (2 * (size_t)n_leaves - 1 != bvh->node_count) {
+        OBVHS_SET_ERR(ctx, "full_rebuild: %u leaves in a tree of %zu nodes (not a full binary tree)", n_leaves, bvh->node_count);
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    return rebuild_from_leaves(ctx, bvh, g.p, leaves.p, n_leaves, nullptr, search_distance, sort_precision, search_depth_threshold);
+}
+
+int ploc_partial_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u8* d_should_remove, u32 search_distance, u32 sort_precision,
+                                size_t search_depth_threshold) {
+    if (bvh->node_count < 2) return OBVHS_OK;  // rebuild.rs:108-110
+    ST_TRY(check_rebuild_args(ctx, search_distance, sort_precision));
+    TraceScope ts(ctx, "partial_rebuild");
+    const u32 n = (u32)bvh->node_count;
+    DevBuf<PlocGlobals> g;
+    DevBuf<u32> tmp_parents, tiles, free_slots;
+    DevBuf<u8> cls;
+    DevBuf<Node32> leaves;
+    const u32* parents = bvh->parents;
+    if (!parents) {  // the walk needs them; Bvh2::parents stays None as in the reference
+        CU_TRY(ctx, tmp_parents.alloc(n, ctx->stream));
+        ST_TRY(bvh2_compute_parents_into(ctx, bvh, tmp_parents.p));
+        parents = tmp_parents.p;
+    }
+    CU_TRY(ctx, g.alloc(1, ctx->stream));
+    CU_TRY(ctx, cls.alloc(n, ctx->stream));
+    CU_TRY(ctx, tiles.alloc((size_t)div_up(n, CP_TILE) + 1, ctx->stream));
+    rebuild_classify_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(bvh->nodes, n, parents, d_should_remove, cls.p);
+    KERNEL_CHECK(ctx);
+    // collected nodes in ascending node index (the tie rule of partial rebuilds), freed slot pairs in descending order
+    const u32 last_odd = n - 2, n_pairs = (n - 1) / 2;
+    CU_TRY(ctx, leaves.alloc((n + 1) / 2, ctx->stream));
+    CU_TRY(ctx, free_slots.alloc(n_pairs, ctx->stream));
+    // more collected nodes than (n+1)/2 cannot happen: they are the leaves of the binary tree formed by the reached nodes
+    ST_TRY(compact(ctx, IsCollected{cls.p}, EmitNode{bvh->nodes, leaves.p}, n, tiles.p, &g.p->ticket));
+    u32 n_leaves = 0, n_free = 0;
+    ST_TRY(read_u32(ctx, &g.p->ticket, &n_leaves));
+    ST_TRY(compact(ctx, IsFreedPairDesc{cls.p, last_odd}, EmitFreedPair{free_slots.p, last_odd}, n_pairs, tiles.p, &g.p->ticket));
+    ST_TRY(read_u32(ctx, &g.p->ticket, &n_free));
+    if (n_leaves < 2 || n_free + 1 != n_leaves) {
+        OBVHS_SET_ERR(ctx, "partial_rebuild: %u collected nodes but %u freed slot pairs (inconsistent tree)", n_leaves, n_free);
+        return OBVHS_ERR_INVALID_ARG;
+    }
+    return rebuild_from_leaves(ctx, bvh, g.p, leaves.p, n_leaves, free_slots.p, search_distance, sort_precision, search_depth_threshold);
 }

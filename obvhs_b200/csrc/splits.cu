@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "compact.cuh"
 
 namespace {
 
@@ -92,31 +93,6 @@ __global__ void __launch_bounds__(SUM_THREADS) presplit_sum_kernel(const float* 
     }
 }
 
-// ---- order-preserving compaction / prefix sums of one flag per item: tile counts -> offsets -> scatter ----------------
-constexpr int CP_THREADS = 256, CP_ITEMS = 8, CP_TILE = CP_THREADS * CP_ITEMS;
-
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total) {
-    __shared__ u32 warp_sums[CP_THREADS / 32];
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    u32 incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 x = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (u32)o) incl += x;
-    }
-    if (lane == 31) warp_sums[w] = incl;
-    __syncthreads();
-    u32 base = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < CP_THREADS / 32; k++) {
-        if ((u32)k < w) base += warp_sums[k];
-        tot += warp_sums[k];
-    }
-    __syncthreads();
-    *total = tot;
-    return base + incl - v;
-}
-
 // flag sources
 struct AreaOfAabb {      // splits.rs:62-66: aabb.half_area() > area_thresh_low, over all aabbs
     const float4* aabbs;
@@ -134,28 +110,6 @@ struct StoredFlag {
     __device__ bool operator()(u32 i) const { return flags[i] != 0; }
 };
 
-template <class F>
-__global__ void __launch_bounds__(CP_THREADS) cp_count_kernel(F f, u32 n, u32* __restrict__ tile_sums) {
-    const u32 base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
-    u32 s = 0;
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++)
-        if (base + k < n && f(base + k)) s++;
-    u32 tot;
-    block_exclusive_scan(s, &tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(CP_THREADS) cp_offsets_kernel(u32* tile_sums, u32 tiles, SplitState* st) {  // one block, in place
-    u32 carry = 0;
-    for (u32 base = 0; base < tiles; base += CP_THREADS) {
-        const u32 i = base + threadIdx.x;
-        u32 v = i < tiles ? tile_sums[i] : 0u, tot;
-        const u32 ex = block_exclusive_scan(v, &tot);
-        if (i < tiles) tile_sums[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) st->total = carry;
-}
 // sinks: called as sink(item, rank) for every flagged item, rank = number of flagged items before it
 struct EmitIndex {  // candidates.push(i) in index order (splits.rs:62-66)
     u32* out;
@@ -180,35 +134,6 @@ struct EmitSplit {  // splits.rs:112-116: candidates.push(aabbs.len()); aabbs.pu
         cand[count + rank] = slot;
     }
 };
-template <class F, class S>
-__global__ void __launch_bounds__(CP_THREADS) cp_scatter_kernel(F f, S sink, u32 n, const u32* __restrict__ tile_offsets) {
-    const u32 base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
-    bool fl[CP_ITEMS];
-    u32 s = 0;
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++) {
-        fl[k] = base + k < n && f(base + k);
-        s += fl[k] ? 1u : 0u;
-    }
-    u32 tot;
-    u32 run = block_exclusive_scan(s, &tot) + tile_offsets[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++)
-        if (fl[k]) sink(base + k, run++);
-}
-
-template <class F, class S>
-int compact(ObvhsContext* ctx, F f, S sink, u32 n, u32* tile_sums, SplitState* st) {
-    const u32 tiles = (u32)div_up(n, CP_TILE);
-    cp_count_kernel<F><<<tiles, CP_THREADS, 0, ctx->stream>>>(f, n, tile_sums);
-    KERNEL_CHECK(ctx);
-    cp_offsets_kernel<<<1, CP_THREADS, 0, ctx->stream>>>(tile_sums, tiles, st);
-    KERNEL_CHECK(ctx);
-    cp_scatter_kernel<F, S><<<tiles, CP_THREADS, 0, ctx->stream>>>(f, sink, n, tile_sums);
-    KERNEL_CHECK(ctx);
-    return OBVHS_OK;
-}
-
 // ---- one candidate: splits.rs:71-117 ------------------------------------------------------------------------------
 __device__ __forceinline__ float axis_of(const float4& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 __device__ __forceinline__ void extend(Box& b, float x, float y, float z) {  // aabb.rs:76-80: union(self, from_point(p))
@@ -339,7 +264,7 @@ int split_loop(ObvhsContext* ctx, SplitArrays& a, const ObvhsTriangle* d_tris, S
         AreaOfAabb f{reinterpret_cast<const float4*>(a.aabbs), st};
         cp_count_kernel<AreaOfAabb><<<tiles, CP_THREADS, 0, s>>>(f, (u32)n, tiles_p);
         KERNEL_CHECK(ctx);
-        cp_offsets_kernel<<<1, CP_THREADS, 0, s>>>(tiles_p, tiles, st);
+        cp_offsets_kernel<<<1, CP_THREADS, 0, s>>>(tiles_p, tiles, &st->total);
         KERNEL_CHECK(ctx);
         ST_TRY(read_total(ctx, st, &count));
         if (count == 0) return OBVHS_OK;
@@ -371,14 +296,14 @@ int split_loop(ObvhsContext* ctx, SplitArrays& a, const ObvhsTriangle* d_tris, S
         KERNEL_CHECK(ctx);
         ST_TRY(compact(ctx, StoredFlag{flags},
                        EmitSplit{reinterpret_cast<float4*>(a.aabbs), a.indices, cand, reinterpret_cast<const float4*>(rights), (u32)a.len, count},
-                       count, tiles_p, st));
+                       count, tiles_p, &st->total));
         u32 added = 0;
         ST_TRY(read_total(ctx, st, &added));
         if (added == 0) break;  // :118-119
         a.len += added;
         const u32 all = count + added;
         ST_TRY(grow(ctx, cand_alt, cand_alt_cap, 0, (size_t)all * 2));
-        ST_TRY(compact(ctx, AreaOfCandidate{reinterpret_cast<const float4*>(a.aabbs), cand, st}, EmitCandidate{cand, cand_alt}, all, tiles_p, st));
+        ST_TRY(compact(ctx, AreaOfCandidate{reinterpret_cast<const float4*>(a.aabbs), cand, st}, EmitCandidate{cand, cand_alt}, all, tiles_p, &st->total));
         ST_TRY(read_total(ctx, st, &count));  // :121-122
         std::swap(cand, cand_alt);
         std::swap(cand_cap, cand_alt_cap);

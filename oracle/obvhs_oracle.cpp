@@ -414,13 +414,23 @@ static inline int8_t find_best_node(size_t index, const OrcBvh2Node* nodes, size
 }
 
 // ploc/mod.rs:258-503 (REBUILD = false)
+static inline bool node_valid(const OrcBvh2Node& n) { return (n.prim_count & 0x80000000u) == 0; }  // bvh2/node.rs:137-139
+// ploc/mod.rs:265-503. rebuild == the REBUILD const generic (partial rebuilds): children go into the slot pairs that
+// partial_rebuild freed (marked invalid), searched downwards from the end of bvh.nodes (:449-462).
 static void build_ploc_from_leaves(OrcBvh2& bvh, std::vector<OrcBvh2Node>& cur, const OrcAabb& total, size_t R, int precision,
-                                   size_t search_depth_threshold, int threads) {
+                                   size_t search_depth_threshold, int threads, bool rebuild = false) {
     size_t prim_count = cur.size();
     if (prim_count == 0) return;
     size_t nodes_count = 2 * prim_count - 1;
-    bvh.nodes.assign(nodes_count, OrcBvh2Node{});
-    size_t insert_index = nodes_count;
+    size_t insert_index;
+    if (rebuild) {  // :283-288
+        if (bvh.nodes.empty()) return;
+        if (bvh.nodes.size() < nodes_count) abort();
+        insert_index = bvh.nodes.size() - 1;
+    } else {
+        bvh.nodes.assign(nodes_count, OrcBvh2Node{});
+        insert_index = nodes_count;
+    }
 
     std::vector<Morton> mortons;
     gen_mortons(cur, total, precision, mortons, threads);
@@ -479,10 +489,25 @@ static void build_ploc_from_leaves(OrcBvh2& bvh, std::vector<OrcBvh2Node>& cur, 
             }
             OrcBvh2Node left = cur[index];
             OrcBvh2Node right = cur[best_index];
-            insert_index -= 2;
-            bvh.nodes[insert_index] = left;
-            bvh.nodes[insert_index + 1] = right;
-            size_t first_child = insert_index;
+            size_t first_child;
+            if (rebuild) {  // :449-462
+                for (;;) {
+                    OrcBvh2Node& left_slot = bvh.nodes[insert_index - 1];
+                    if (!node_valid(left_slot)) {
+                        left_slot = left;
+                        bvh.nodes[insert_index] = right;
+                        first_child = insert_index - 1;
+                        insert_index -= 2;
+                        break;
+                    }
+                    insert_index -= 2;
+                }
+            } else {
+                insert_index -= 2;
+                bvh.nodes[insert_index] = left;
+                bvh.nodes[insert_index + 1] = right;
+                first_child = insert_index;
+            }
             next[next_idx++] = make_node(aabb_union(left.aabb, right.aabb), 0, (u32)first_child);
             if (R == 1 && index_offset == 1)
                 index += 2;
@@ -494,8 +519,8 @@ static void build_ploc_from_leaves(OrcBvh2& bvh, std::vector<OrcBvh2Node>& cur, 
         depth++;
     }
     bvh.nodes[0] = cur[0];
-    bvh.max_depth = std::max<size_t>(96, depth + 1);  // ploc/mod.rs:501
-    bvh.children_are_ordered_after_parents = true;    // ploc/mod.rs:502
+    bvh.max_depth = std::max<size_t>(96, depth + 1);     // ploc/mod.rs:501
+    bvh.children_are_ordered_after_parents = !rebuild;  // ploc/mod.rs:502
     bvh.ploc_iterations = depth;
 }
 
@@ -509,6 +534,63 @@ static void compute_parents(OrcBvh2& bvh) {
             bvh.parents[n.first_index + 1] = (u32)i;
         }
     }
+}
+
+// ploc/rebuild.rs:12-43
+static void compute_rebuild_path_flags(const OrcBvh2& bvh, const u32* leaves, size_t n_leaves, std::vector<u8>& flags) {
+    if (bvh.nodes.size() < 2) return;
+    if (bvh.parents.empty()) abort();  // the reference panics: parents must be initialised first
+    flags.assign(bvh.nodes.size(), 0);
+    for (size_t k = 0; k < n_leaves; k++) {
+        size_t index = leaves[k];
+        flags[index] = 1;
+        while (index > 0) {
+            index = bvh.parents[index];
+            if (flags[index]) break;
+            flags[index] = 1;
+        }
+    }
+}
+// ploc/rebuild.rs:137-183
+static void rebuild_from_leaves(OrcBvh2& bvh, std::vector<OrcBvh2Node>& cur, bool partial, size_t R, int precision, size_t thr, int threads) {
+    if (bvh.nodes.size() < 2) return;
+    bool had_parents = !bvh.parents.empty();
+    OrcAabb total = bvh.nodes[0].aabb;  // :153: the (possibly stale) root box only scales the Morton codes
+    build_ploc_from_leaves(bvh, cur, total, R, precision, thr, threads, partial);
+    if (had_parents) compute_parents(bvh);  // :177-179
+}
+// ploc/rebuild.rs:56-80
+static void full_rebuild(OrcBvh2& bvh, size_t R, int precision, size_t thr, int threads) {
+    if (bvh.nodes.size() < 2) return;
+    std::vector<OrcBvh2Node> cur;
+    for (const OrcBvh2Node& n : bvh.nodes)
+        if (is_leaf(n)) cur.push_back(n);
+    rebuild_from_leaves(bvh, cur, false, R, precision, thr, threads);
+}
+// ploc/rebuild.rs:101-135. The reference collects the surviving subtrees in the order of its stack walk and then sorts them
+// with an UNSTABLE sort, so the order among equal Morton codes is unspecified there. Tie rule of this restatement (and of
+// the CUDA path): equal codes keep ascending NODE INDEX, i.e. the collected nodes are put in node-index order before the
+// stable sort.
+static void partial_rebuild(OrcBvh2& bvh, const u8* should_remove, size_t R, int precision, size_t thr, int threads) {
+    if (bvh.nodes.size() < 2) return;
+    std::vector<std::pair<u32, OrcBvh2Node>> collected;
+    std::vector<u32> stack;
+    stack.push_back(bvh.nodes[0].first_index);
+    while (!stack.empty()) {
+        u32 left_node_index = stack.back();
+        stack.pop_back();
+        for (u32 node_index : {left_node_index, left_node_index + 1}) {
+            OrcBvh2Node& node = bvh.nodes[node_index];
+            if (!should_remove[node_index] || is_leaf(node)) collected.push_back({node_index, node});
+            else stack.push_back(node.first_index);
+            node.prim_count |= 0x80000000u;  // set_invalid, bvh2/node.rs:143-145
+        }
+    }
+    std::sort(collected.begin(), collected.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<OrcBvh2Node> cur;
+    cur.reserve(collected.size());
+    for (auto& c : collected) cur.push_back(c.second);
+    rebuild_from_leaves(bvh, cur, true, R, precision, thr, threads);
 }
 
 // bvh2/mod.rs:527-569
@@ -1905,6 +1987,24 @@ OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, u32 search_
     return bvh2;
 }
 void orc_bvh2_refit_all(OrcBvh2* b) { refit_all(*b); }
+void orc_ploc_full_rebuild(OrcBvh2* b, u32 search_distance, int precision, size_t search_depth_threshold, int threads) {
+    full_rebuild(*b, search_distance, precision, search_depth_threshold, clamp_threads(threads));
+}
+void orc_ploc_partial_rebuild(OrcBvh2* b, const u8* should_remove, u32 search_distance, int precision, size_t search_depth_threshold,
+                              int threads) {
+    partial_rebuild(*b, should_remove, search_distance, precision, search_depth_threshold, clamp_threads(threads));
+}
+void orc_compute_rebuild_path_flags(const OrcBvh2* b, const u32* leaves, size_t n, u8* flags_out) {
+    std::vector<u8> f;
+    compute_rebuild_path_flags(*b, leaves, n, f);
+    if (!f.empty()) memcpy(flags_out, f.data(), f.size());
+}
+void orc_bvh2_set_node_aabbs(OrcBvh2* b, const u32* node_ids, const OrcAabb* aabbs, size_t n) {  // Bvh2Node::set_aabb, physics.rs:446
+    for (size_t k = 0; k < n; k++) {
+        b->nodes[node_ids[k]].aabb = aabbs[k];
+        b->nodes[node_ids[k]].aabb._p0 = b->nodes[node_ids[k]].aabb._p1 = 0.f;
+    }
+}
 void orc_bvh2_set_leaf_aabbs(OrcBvh2* b, const OrcAabb* prim_aabbs) {
     for (auto& nd : b->nodes)
         if (is_leaf(nd)) {

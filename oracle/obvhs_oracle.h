@@ -69,6 +69,13 @@ void     orc_bvh2_compute_parents(OrcBvh2*);                                    
 void     orc_bvh2_collapse(OrcBvh2*, uint32_t max_prims, float traversal_cost);             /* bvh2/leaf_collapser.rs:21-192 */
 int      orc_bvh2_has_parents(const OrcBvh2*);
 void     orc_bvh2_refit_all(OrcBvh2*);                                                  /* bvh2/mod.rs:527-569 */
+/* PlocBuilder::full_rebuild / partial_rebuild, compute_rebuild_path_flags (ploc/rebuild.rs:12-183). should_remove and
+ * flags_out hold one byte per node. Tie rule of partial rebuilds: equal Morton codes keep ascending node index. */
+void     orc_ploc_full_rebuild(OrcBvh2*, uint32_t search_distance, int precision, size_t search_depth_threshold, int threads);
+void     orc_ploc_partial_rebuild(OrcBvh2*, const uint8_t* should_remove, uint32_t search_distance, int precision,
+                                  size_t search_depth_threshold, int threads);
+void     orc_compute_rebuild_path_flags(const OrcBvh2*, const uint32_t* leaves, size_t n, uint8_t* flags_out);
+void     orc_bvh2_set_node_aabbs(OrcBvh2*, const uint32_t* node_ids, const OrcAabb* aabbs, size_t n); /* Bvh2Node::set_aabb */
 void     orc_bvh2_set_leaf_aabbs(OrcBvh2*, const OrcAabb* prim_aabbs);                  /* config 5 helper */
 
 /* -- reinsertion (bvh2/reinsertion.rs:40-382) --------------------------------------------------------- */

@@ -50,6 +50,10 @@ def lib():
             "orc_bvh2_validate": (i32, [vp, vp, sz, i32, C.c_char_p]),
             "orc_bvh2_compute_parents": (None, [vp]),
             "orc_bvh2_refit_all": (None, [vp]),
+            "orc_ploc_full_rebuild": (None, [vp, u32, i32, sz, i32]),
+            "orc_ploc_partial_rebuild": (None, [vp, vp, u32, i32, sz, i32]),
+            "orc_compute_rebuild_path_flags": (None, [vp, vp, sz, vp]),
+            "orc_bvh2_set_node_aabbs": (None, [vp, vp, vp, sz]),
             "orc_bvh2_collapse": (None, [vp, u32, f32]),
             "orc_bvh2_has_parents": (i32, [vp]),
             "orc_bvh2_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, vp]),
@@ -165,6 +169,28 @@ class Bvh2:
     def set_leaf_aabbs(self, prim_aabbs):
         prim_aabbs = _f32c(prim_aabbs, 8)
         lib().orc_bvh2_set_leaf_aabbs(self.h, _p(prim_aabbs))
+
+    def set_node_aabbs(self, node_ids, aabbs):
+        ids = np.ascontiguousarray(node_ids, dtype=np.uint32)
+        a = _f32c(aabbs, 8)
+        lib().orc_bvh2_set_node_aabbs(self.h, _p(ids), _p(a), ids.shape[0])
+
+    def full_rebuild(self, sd, precision=64, thr=0, threads=1):
+        """ploc/rebuild.rs:56-80"""
+        lib().orc_ploc_full_rebuild(self.h, sd, precision, thr, threads)
+
+    def partial_rebuild(self, should_remove, sd, precision=64, thr=0, threads=1):
+        """ploc/rebuild.rs:101-135"""
+        f = np.ascontiguousarray(should_remove, dtype=np.uint8)
+        assert f.shape[0] == self.node_count
+        lib().orc_ploc_partial_rebuild(self.h, _p(f), sd, precision, thr, threads)
+
+    def rebuild_path_flags(self, leaves):
+        """ploc/rebuild.rs:12-43 (parents must be computed)"""
+        ids = np.ascontiguousarray(leaves, dtype=np.uint32)
+        f = np.zeros(self.node_count, dtype=np.uint8)
+        lib().orc_compute_rebuild_path_flags(self.h, _p(ids), ids.shape[0], _p(f))
+        return f
 
     def reinsertion_run(self, ratio, seq=None, threads=1):
         if seq is None:
