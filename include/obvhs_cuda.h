@@ -248,6 +248,27 @@ int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const Ob
  * counters[0] += nodes visited, counters[1] += triangles tested (host or device pointer to 2 x u64). */
 int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
                                                 ObvhsRayHit* hits, uint64_t* counters);
+/* ---- broad-phase queries (batched; the per-report closure of the reference becomes a list of reports) ---------------
+ * Bvh2::aabb_traverse(aabb, eval) / Bvh2::point_traverse(point, eval)  (src/bvh2/mod.rs:365-456) for n queries with an eval
+ * that always continues: counts[i] = number of leaf nodes reported for query i; leaf_ids receives the reported leaf NODE
+ * ids query after query (query i starts at the sum of counts[0..i)), each query's ids in exactly the order the reference
+ * calls eval. counts / leaf_ids may be NULL; *total = sum of counts. When leaf_ids != NULL and *total > capacity nothing
+ * is written to leaf_ids and OBVHS_ERR_CAPACITY is returned (counts and *total are valid). points: Vec3A, 4 floats each. */
+int obvhs_cuda_bvh2_aabb_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsAabb* queries, size_t n,
+                                        uint32_t* counts, uint32_t* leaf_ids, size_t capacity, size_t* total);
+int obvhs_cuda_bvh2_point_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const float* points, size_t n,
+                                         uint32_t* counts, uint32_t* leaf_ids, size_t capacity, size_t* total);
+/* traverse!(bvh, node, state, node.intersect_aabb(&aabb, state.oct_inv4), { state.primitive_id }) and the contains_point
+ * form (src/cwbvh/traverse_macro.rs:59-126, src/cwbvh/node.rs:157-200): reports primitive slots (indices into
+ * primitive_indices). traversal_direction: 3 host floats ordering the children (CwBvh::new_traversal, cwbvh/mod.rs:146),
+ * NULL = Vec3A::ZERO as in the reference's tests. Same output convention as above. */
+int obvhs_cuda_cwbvh_aabb_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsAabb* queries, size_t n,
+                                         const float* traversal_direction, uint32_t* counts, uint32_t* primitive_ids,
+                                         size_t capacity, size_t* total);
+int obvhs_cuda_cwbvh_point_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const float* points, size_t n,
+                                          const float* traversal_direction, uint32_t* counts, uint32_t* primitive_ids,
+                                          size_t capacity, size_t* total);
+
 /* Ray::new for n rays (src/ray.rs:34-52): origin_dir is n x 6 floats (ox,oy,oz,dx,dy,dz). */
 int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays);
 

@@ -110,6 +110,10 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_ray_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "obvhs_cuda_bvh2_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "obvhs_cuda_bvh2_point_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "obvhs_cuda_cwbvh_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "obvhs_cuda_cwbvh_point_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_make_rays": (_i32, [_vp, _vp, _sz, _f32, _f32, _vp]),
 }
 
@@ -264,6 +268,29 @@ class BvhBuildParams:
                             int(self.sort_precision), int(self.max_prims_per_leaf), float(self.collapse_traversal_cost))
 
 
+def _query_batch(ctx, fn, handle, q, extra=()):
+    """count pass, then fill: -> (counts[n], ids[total]) with every query's ids in the reference's call order"""
+    n = q.shape[0]
+    counts = np.zeros(n, dtype=np.uint32)
+    total = _sz(0)
+    ctx.check(fn(ctx.h, handle, _ptr(q), n, *extra, _ptr(counts), None, 0, C.byref(total)))
+    ids = np.zeros(max(1, total.value), dtype=np.uint32)
+    if total.value:
+        ctx.check(fn(ctx.h, handle, _ptr(q), n, *extra, _ptr(counts), _ptr(ids), total.value, C.byref(total)))
+    return counts, ids[: total.value]
+
+
+def _points4(points):
+    if _is_torch(points):
+        return _as_f32(points, 4)
+    p = np.asarray(points, dtype=np.float32)
+    if p.ndim == 2 and p.shape[1] == 4:
+        return np.ascontiguousarray(p)
+    out = np.zeros((p.shape[0], 4), np.float32)
+    out[:, :3] = p[:, :3]
+    return out
+
+
 class Bvh2:
     """Device-resident Bvh2 (src/bvh2/mod.rs:31-85)."""
 
@@ -326,6 +353,14 @@ class Bvh2:
         """Attach tris[primitive_indices] for ray traversal (examples/demoscene.rs:66-70)."""
         t = _as_f32(tris, 12)
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_set_triangles(self.ctx.h, self.h, _ptr(t), t.shape[0]))
+
+    def aabb_traverse(self, aabbs):
+        """Batched Bvh2::aabb_traverse (src/bvh2/mod.rs:365-407) with eval -> true: (counts per query, leaf node ids)."""
+        return _query_batch(self.ctx, self.ctx.lib.obvhs_cuda_bvh2_aabb_traverse_batch, self.h, _as_f32(aabbs, 8))
+
+    def point_traverse(self, points):
+        """Batched Bvh2::point_traverse (src/bvh2/mod.rs:414-456): (counts per query, leaf node ids)."""
+        return _query_batch(self.ctx, self.ctx.lib.obvhs_cuda_bvh2_point_traverse_batch, self.h, _points4(points))
 
     def ray_traverse(self, rays, out=None, counters=None):
         """Batched Bvh2::ray_traverse (src/bvh2/mod.rs:148-172); returns / fills a RAY_HIT array (or an (n,4) int32 device tensor)."""
@@ -569,6 +604,17 @@ class CwBvh:
         total = np.zeros(8, dtype=np.float32)
         self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_download(self.ctx.h, self.h, None, None, _ptr(total)))
         return total
+
+    def aabb_traverse(self, aabbs, traversal_direction=(0.0, 0.0, 0.0)):
+        """traverse!(.., node.intersect_aabb(&aabb, state.oct_inv4), ..) per query box (src/cwbvh/node.rs:157-177):
+        (counts per query, primitive slots in call order)."""
+        d = np.ascontiguousarray(traversal_direction, dtype=np.float32)
+        return _query_batch(self.ctx, self.ctx.lib.obvhs_cuda_cwbvh_aabb_traverse_batch, self.h, _as_f32(aabbs, 8), (_ptr(d),))
+
+    def point_traverse(self, points, traversal_direction=(0.0, 0.0, 0.0)):
+        """traverse!(.., node.contains_point(&point, state.oct_inv4), ..) per point (src/cwbvh/node.rs:180-200)."""
+        d = np.ascontiguousarray(traversal_direction, dtype=np.float32)
+        return _query_batch(self.ctx, self.ctx.lib.obvhs_cuda_cwbvh_point_traverse_batch, self.h, _points4(points), (_ptr(d),))
 
     def ray_traverse(self, rays, out=None, counters=None):
         """Batched CwBvh::ray_traverse with the triangle closure: -> RayHit per ray (numpy RAY_HIT array, or `out`).

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libobvhs_cuda.so")
-SOURCES = ["api.cu", "ploc.cu", "sort.cu", "bvh2.cu", "collapse.cu", "splits.cu", "reinsertion.cu", "cwbvh_build.cu", "traverse.cu"]
+SOURCES = ["api.cu", "ploc.cu", "sort.cu", "bvh2.cu", "collapse.cu", "splits.cu", "reinsertion.cu", "cwbvh_build.cu", "traverse.cu", "query.cu"]
 HEADERS = ["common.cuh", "compact.cuh", "cwbvh_exponent.h", os.path.join("..", "..", "include", "obvhs_cuda.h")]
 
 NVCC_FLAGS = [

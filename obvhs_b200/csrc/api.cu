@@ -1009,7 +1009,57 @@ int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris
     return OBVHS_OK;
 }
 
-int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays) {
+}  // extern "C"
+
+// ---- broad-phase queries (query.cu) -----------------------------------------------------------------------------
+namespace {
+template <class Run>
+int query_entry(ObvhsContext* ctx, const float* queries, size_t n, int floats_per_query, Run run) {
+    DevBuf<float> st;
+    const float* d = nullptr;
+    ST_TRY(stage_in(ctx, queries, n * floats_per_query, st, &d));
+    ST_TRY(run(reinterpret_cast<const float4*>(d)));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
+}  // namespace
+extern "C" {
+int obvhs_cuda_bvh2_aabb_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsAabb* queries, size_t n, uint32_t* counts,
+                                        uint32_t* leaf_ids, size_t capacity, size_t* total) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || queries), "null argument");
+    return query_entry(ctx, reinterpret_cast<const float*>(queries), n, 8,
+                       [&](const float4* d) { return bvh2_query_device(ctx, bvh, 0, d, n, counts, leaf_ids, capacity, total); });
+}
+int obvhs_cuda_bvh2_point_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const float* points, size_t n, uint32_t* counts,
+                                         uint32_t* leaf_ids, size_t capacity, size_t* total) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || points), "null argument");
+    return query_entry(ctx, points, n, 4, [&](const float4* d) { return bvh2_query_device(ctx, bvh, 1, d, n, counts, leaf_ids, capacity, total); });
+}
+int obvhs_cuda_cwbvh_aabb_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsAabb* queries, size_t n,
+                                         const float* traversal_direction, uint32_t* counts, uint32_t* primitive_ids, size_t capacity,
+                                         size_t* total) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || queries), "null argument");
+    ARG_CHECK(ctx, !traversal_direction || !obvhs_is_device_ptr(traversal_direction), "traversal_direction must be host memory");
+    return query_entry(ctx, reinterpret_cast<const float*>(queries), n, 8, [&](const float4* d) {
+        return cwbvh_query_device(ctx, bvh, 0, d, n, traversal_direction, counts, primitive_ids, capacity, total);
+    });
+}
+int obvhs_cuda_cwbvh_point_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const float* points, size_t n,
+                                          const float* traversal_direction, uint32_t* counts, uint32_t* primitive_ids, size_t capacity,
+                                          size_t* total) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || points), "null argument");
+    ARG_CHECK(ctx, !traversal_direction || !obvhs_is_device_ptr(traversal_direction), "traversal_direction must be host memory");
+    return query_entry(ctx, points, n, 4, [&](const float4* d) {
+        return cwbvh_query_device(ctx, bvh, 1, d, n, traversal_direction, counts, primitive_ids, capacity, total);
+    });
+}
+}  // extern "C"
+
+extern "C" int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, float tmin, float tmax, ObvhsRay* rays) {
     API_ENTER(ctx);
     ARG_CHECK(ctx, n == 0 || (origin_dir && rays), "null argument");
     if (n == 0) return OBVHS_OK;
@@ -1028,4 +1078,4 @@ int obvhs_cuda_make_rays(ObvhsContext* ctx, const float* origin_dir, size_t n, f
     return OBVHS_OK;
 }
 
-}  // extern "C"
+

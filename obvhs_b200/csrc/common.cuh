@@ -287,6 +287,12 @@ int ploc_full_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 search_dista
 int ploc_partial_rebuild_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u8* d_should_remove, u32 search_distance, u32 sort_precision,
                                 size_t search_depth_threshold);
 int ploc_compute_rebuild_path_flags_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const u32* d_leaves, size_t n_leaves, u8* d_flags);
+// query.cu : batched Bvh2::aabb_traverse / point_traverse and the CwBvh traverse! macro over intersect_aabb / contains_point.
+// query_kind 0 = boxes (2 float4 per query), 1 = points (1 float4). counts / ids may be host or device.
+int bvh2_query_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, int query_kind, const float4* d_queries, size_t n, u32* counts, u32* ids,
+                      size_t capacity, size_t* total_out);
+int cwbvh_query_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, int query_kind, const float4* d_queries, size_t n, const float* host_dir3,
+                       u32* counts, u32* ids, size_t capacity, size_t* total_out);
 // splits.cu : spatial pre-splits (src/splits.rs). Arrays live in the arena of the API call in flight and grow like the Vecs.
 struct SplitArrays {
     ObvhsAabb* aabbs = nullptr;

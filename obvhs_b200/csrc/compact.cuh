@@ -82,4 +82,47 @@ int compact(ObvhsContext* ctx, F f, S sink, u32 n, u32* tile_sums, u32* total_ou
     return OBVHS_OK;
 }
 
+// ---- exclusive prefix sums over one u32 VALUE per item: F is u32(u32 item); S is void(u32 item, u32 exclusive, u32 value) ----
+template <class F>
+__global__ void __launch_bounds__(CP_THREADS) cpv_sum_kernel(F f, u32 n, u32* __restrict__ tile_sums) {
+    const u32 base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++)
+        if (base + k < n) s += f(base + k);
+    u32 tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+template <class F, class S>
+__global__ void __launch_bounds__(CP_THREADS) cpv_scatter_kernel(F f, S sink, u32 n, const u32* __restrict__ tile_offsets) {
+    const u32 base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
+    u32 v[CP_ITEMS];
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        v[k] = base + k < n ? f(base + k) : 0u;
+        s += v[k];
+    }
+    u32 tot;
+    u32 run = block_exclusive_scan(s, &tot) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++)
+        if (base + k < n) {
+            sink(base + k, run, v[k]);
+            run += v[k];
+        }
+}
+template <class F, class S>
+int scan_values(ObvhsContext* ctx, F f, S sink, u32 n, u32* tile_sums, u32* total_out) {
+    const u32 tiles = (u32)div_up(n, CP_TILE);
+    cpv_sum_kernel<F><<<tiles, CP_THREADS, 0, ctx->stream>>>(f, n, tile_sums);
+    KERNEL_CHECK(ctx);
+    cp_offsets_kernel<<<1, CP_THREADS, 0, ctx->stream>>>(tile_sums, tiles, total_out);
+    KERNEL_CHECK(ctx);
+    cpv_scatter_kernel<F, S><<<tiles, CP_THREADS, 0, ctx->stream>>>(f, sink, n, tile_sums);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
 }  // namespace

@@ -1581,6 +1581,136 @@ static void bvh2_traverse_batch(const OrcBvh2& bvh, const OrcTriangle* tris, con
 // validation (bvh2/mod.rs:786-981, cwbvh/mod.rs:747-908) -- invariants restated, not the stats
 // ---------------------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------------------
+// Broad-phase queries: Bvh2::aabb_traverse / point_traverse (bvh2/mod.rs:365-456) and the traverse! macro over
+// CwBvhNode::intersect_aabb / contains_point (cwbvh/node.rs:157-200), with an `eval` that always returns true.
+// ---------------------------------------------------------------------------------------------------------
+// aabb.rs:181-183: (self.min.cmpgt(other.max) | self.max.cmplt(other.min)).bitmask() == 0   (three lanes)
+static inline bool aabb_intersect_aabb(const float* smin_, const float* smax_, const float* omin, const float* omax) {
+    for (int k = 0; k < 3; k++)
+        if (smin_[k] > omax[k] || smax_[k] < omin[k]) return false;
+    return true;
+}
+// aabb.rs:70-72: (point.cmpge(self.min) & point.cmple(self.max)).all()
+static inline bool aabb_contains_point(const float* mn, const float* mx, const float* p) {
+    for (int k = 0; k < 3; k++)
+        if (!(p[k] >= mn[k]) || !(p[k] <= mx[k])) return false;
+    return true;
+}
+// QUERY 0: q = Aabb (min at q[0..3], max at q[4..7]); QUERY 1: q = point (Vec3A)
+template <int QUERY>
+static inline bool bvh2_node_test(const OrcBvh2Node& n, const float* q) {
+    return QUERY == 0 ? aabb_intersect_aabb(n.aabb.min, n.aabb.max, q, q + 4) : aabb_contains_point(n.aabb.min, n.aabb.max, q);
+}
+template <int QUERY, class Emit>
+static void bvh2_query_one(const OrcBvh2& bvh, const float* q, Emit emit) {
+    if (bvh.nodes.empty()) return;
+    const OrcBvh2Node& root = bvh.nodes[0];
+    if (is_leaf(root)) {  // :370-376
+        if (bvh2_node_test<QUERY>(root, q)) emit(0u);
+        return;
+    }
+    const size_t cap = bvh.max_depth <= 96 ? 96 : (bvh.max_depth <= 192 ? 192 : bvh.max_depth);  // fast_stack!(u32, (96, 192), max_depth)
+    std::vector<u32> stack(cap);
+    size_t sp = 0;
+    auto push = [&](u32 v) {  // StackStack::push saturates at the last slot (faststack.rs:299-303)
+        stack[sp] = v;
+        sp = std::min(sp + 1, cap - 1);
+    };
+    push(root.first_index);
+    while (sp > 0) {
+        u32 node_index = stack[--sp];
+        for (u32 k = 0; k < 2; k++) {  // left, then right
+            const OrcBvh2Node& node = bvh.nodes[node_index + k];
+            if (bvh2_node_test<QUERY>(node, q)) {
+                if (is_leaf(node)) emit(node_index + k);
+                else push(node.first_index);
+            }
+        }
+    }
+}
+// cwbvh/node.rs:157-200
+template <int QUERY>
+static inline u32 cw_node_query(const OrcCwBvhNode& n, const float* q, u32 oct_inv4) {
+    float rcp[3], lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        float e = u2f((u32)n.e[k] << 23);
+        rcp[k] = 1.0f / e;
+        lo[k] = (q[k] - n.p[k]) * rcp[k];
+        if (QUERY == 0) hi[k] = (q[4 + k] - n.p[k]) * rcp[k];
+    }
+    u64 child_bits8, bit_index8;
+    get_child_and_index_bits(n, oct_inv4, child_bits8, bit_index8);
+    u32 hit_mask = 0;
+    for (int child = 0; child < 8; child++) {
+        float cmin[3] = {(float)n.child_min_x[child], (float)n.child_min_y[child], (float)n.child_min_z[child]};
+        float cmax[3] = {(float)n.child_max_x[child], (float)n.child_max_y[child], (float)n.child_max_z[child]};
+        bool hit = QUERY == 0 ? aabb_intersect_aabb(cmin, cmax, lo, hi) : aabb_contains_point(cmin, cmax, lo);
+        if (hit) hit_mask |= extract_byte64(child_bits8, child) << extract_byte64(bit_index8, child);
+    }
+    return hit_mask;
+}
+// traverse_macro.rs:59-126 with $node_intersection = node.intersect_aabb / contains_point and a primitive block that
+// reports state.primitive_id
+template <int QUERY, class Emit>
+static void cwbvh_query_one(const OrcCwBvh& bvh, const float* q, const float* dir, Emit emit) {
+    struct G {
+        u32 x, y;
+    };
+    G stack[32];
+    size_t sp = 0;
+    G current_group = bvh.nodes.empty() ? G{0, 0} : G{0, 0x80000000u};
+    G primitive_group = G{0, 0};
+    u32 oct_inv4 = ray_get_octant_inv4(dir);
+    for (;;) {
+        while (primitive_group.y != 0) {
+            u32 local = firstbithigh(primitive_group.y);
+            primitive_group.y &= ~(1u << local);
+            emit(primitive_group.x + local);
+        }
+        primitive_group = G{0, 0};
+        if (current_group.y & 0xff000000u) {
+            u32 hits_imask = current_group.y;
+            u32 child_index_offset = firstbithigh(hits_imask);
+            u32 child_index_base = current_group.x;
+            current_group.y &= ~(1u << child_index_offset);
+            if (current_group.y & 0xff000000u) {
+                stack[sp] = current_group;
+                sp = std::min<size_t>(sp + 1, 31);
+            }
+            u32 slot_index = (child_index_offset - 24) ^ (oct_inv4 & 0xff);
+            u32 relative_index = (u32)__builtin_popcount(hits_imask & ~(0xffffffffu << slot_index));
+            const OrcCwBvhNode& node = bvh.nodes[child_index_base + relative_index];
+            u32 hitmask = cw_node_query<QUERY>(node, q, oct_inv4);
+            current_group.x = node.child_base_idx;
+            primitive_group.x = node.primitive_base_idx;
+            current_group.y = (hitmask & 0xff000000u) | (u32)node.imask;
+            primitive_group.y = hitmask & 0x00ffffffu;
+        } else {
+            current_group = G{0, 0};
+        }
+        if (primitive_group.y == 0 && (current_group.y & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            current_group = stack[--sp];
+        }
+    }
+}
+// batch drivers: counts[i] = reports of query i; ids_out receives them query after query, in call order, up to cap; returns the total
+template <class One>
+static size_t query_batch(size_t n, u32* counts, u32* ids_out, size_t cap, One one) {
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        u32 c = 0;
+        one(i, [&](u32 id) {
+            if (ids_out && total < cap) ids_out[total] = id;
+            total++;
+            c++;
+        });
+        if (counts) counts[i] = c;
+    }
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // splits.rs: spatial pre-splits of large triangles
 // ---------------------------------------------------------------------------------------------------------
 // aabb.rs:124-134
@@ -2029,6 +2159,19 @@ void orc_reinsertion_run_with_candidates(OrcBvh2* b, const u32* ids, size_t n, u
 }
 size_t orc_reinsertion_last_applied(const OrcBvh2* b) { return b->last_applied; }
 void orc_set_refit_full(int full) { g_refit_full = full != 0; }
+
+size_t orc_bvh2_aabb_traverse(const OrcBvh2* b, const OrcAabb* queries, size_t n, u32* counts, u32* leaf_ids, size_t cap) {
+    return query_batch(n, counts, leaf_ids, cap, [&](size_t i, auto emit) { bvh2_query_one<0>(*b, queries[i].min, emit); });
+}
+size_t orc_bvh2_point_traverse(const OrcBvh2* b, const float* points4, size_t n, u32* counts, u32* leaf_ids, size_t cap) {
+    return query_batch(n, counts, leaf_ids, cap, [&](size_t i, auto emit) { bvh2_query_one<1>(*b, points4 + 4 * i, emit); });
+}
+size_t orc_cwbvh_aabb_traverse(const OrcCwBvh* c, const OrcAabb* queries, size_t n, const float* dir3, u32* counts, u32* prim_ids, size_t cap) {
+    return query_batch(n, counts, prim_ids, cap, [&](size_t i, auto emit) { cwbvh_query_one<0>(*c, queries[i].min, dir3, emit); });
+}
+size_t orc_cwbvh_point_traverse(const OrcCwBvh* c, const float* points4, size_t n, const float* dir3, u32* counts, u32* prim_ids, size_t cap) {
+    return query_batch(n, counts, prim_ids, cap, [&](size_t i, auto emit) { cwbvh_query_one<1>(*c, points4 + 4 * i, dir3, emit); });
+}
 
 // splits.rs:49-125 on caller arrays with room for `cap` entries; returns the new count (which may exceed cap: nothing is
 // written past cap, call again with more room)

@@ -136,6 +136,17 @@ OrcBvh2* orc_build_bvh2_from_tris(const OrcTriangle* tris, size_t n, uint32_t se
                                   float reinsertion_batch_ratio, float post_collapse_multiplier, int precision,
                                   uint32_t max_prims_per_leaf, float collapse_traversal_cost, int pre_split, int threads,
                                   double* core_seconds);
+/* Broad-phase queries with an `eval` that always continues: Bvh2::aabb_traverse / point_traverse (bvh2/mod.rs:365-456) report
+ * leaf NODE ids; the traverse! macro over CwBvhNode::intersect_aabb / contains_point (cwbvh/node.rs:157-200,
+ * traverse_macro.rs:59-126) reports primitive slots (state.primitive_id), children ordered by dir3 (new_traversal).
+ * counts[i] = reports of query i; ids receive them query after query in call order, up to cap. Returns the total.
+ * OrcAabb queries use the min/max lanes; points are Vec3A (4 floats each). */
+size_t orc_bvh2_aabb_traverse(const OrcBvh2*, const OrcAabb* queries, size_t n, uint32_t* counts, uint32_t* leaf_ids, size_t cap);
+size_t orc_bvh2_point_traverse(const OrcBvh2*, const float* points4, size_t n, uint32_t* counts, uint32_t* leaf_ids, size_t cap);
+size_t orc_cwbvh_aabb_traverse(const OrcCwBvh*, const OrcAabb* queries, size_t n, const float* dir3, uint32_t* counts,
+                               uint32_t* prim_ids, size_t cap);
+size_t orc_cwbvh_point_traverse(const OrcCwBvh*, const float* points4, size_t n, const float* dir3, uint32_t* counts,
+                                uint32_t* prim_ids, size_t cap);
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray);               /* triangle.rs:35-76 */
 void  orc_triangle_normal(const OrcTriangle* tri, float* out3);                         /* triangle.rs:20-24 */
 int   orc_max_threads(void);

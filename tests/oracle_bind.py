@@ -80,6 +80,10 @@ def lib():
             "orc_cwbvh_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
             "orc_cwbvh_ray_traverse_miss": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
             "orc_cwbvh_ray_traverse_anyhit_count": (None, [vp, vp, vp, sz, vp, i32]),
+            "orc_bvh2_aabb_traverse": (sz, [vp, vp, sz, vp, vp, sz]),
+            "orc_bvh2_point_traverse": (sz, [vp, vp, sz, vp, vp, sz]),
+            "orc_cwbvh_aabb_traverse": (sz, [vp, vp, sz, vp, vp, vp, sz]),
+            "orc_cwbvh_point_traverse": (sz, [vp, vp, sz, vp, vp, vp, sz]),
             "orc_triangle_intersect": (f32, [vp, vp]),
             "orc_triangle_normal": (None, [vp, vp]),
             "orc_max_threads": (i32, []),
@@ -175,6 +179,14 @@ class Bvh2:
         a = _f32c(aabbs, 8)
         lib().orc_bvh2_set_node_aabbs(self.h, _p(ids), _p(a), ids.shape[0])
 
+    def aabb_traverse(self, queries):
+        """Bvh2::aabb_traverse (bvh2/mod.rs:365-407) per query box: (counts, leaf node ids in call order)"""
+        return _query(lib().orc_bvh2_aabb_traverse, self.h, queries, 8)
+
+    def point_traverse(self, points):
+        """Bvh2::point_traverse (bvh2/mod.rs:414-456)"""
+        return _query(lib().orc_bvh2_point_traverse, self.h, points4(points), 4)
+
     def full_rebuild(self, sd, precision=64, thr=0, threads=1):
         """ploc/rebuild.rs:56-80"""
         lib().orc_ploc_full_rebuild(self.h, sd, precision, thr, threads)
@@ -240,6 +252,23 @@ class Bvh2:
         return CwBvh(lib().orc_bvh2_to_cwbvh(self.h, max_prims_per_leaf, int(order_children), int(include_exact)))
 
 
+def _query(fn, handle, queries, cols, extra=()):
+    """two calls: count, then fill. -> (counts, ids) with ids grouped by query in call order"""
+    q = _f32c(queries, cols)
+    n = q.shape[0]
+    counts = np.zeros(n, dtype=np.uint32)
+    total = fn(handle, _p(q), n, *extra, _p(counts), None, 0)
+    ids = np.zeros(max(1, total), dtype=np.uint32)
+    fn(handle, _p(q), n, *extra, _p(counts), _p(ids), total)
+    return counts, ids[:total]
+
+
+def points4(points):
+    p = np.zeros((len(points), 4), np.float32)
+    p[:, :3] = np.asarray(points, dtype=np.float32)[:, :3]
+    return p
+
+
 def bvh2_from(nodes, prims, max_depth=96) -> Bvh2:
     nodes = np.ascontiguousarray(nodes, dtype=BVH2_NODE)
     prims = np.ascontiguousarray(prims, dtype=np.uint32)
@@ -289,6 +318,15 @@ class CwBvh:
         """examples/obj_cwbvh.rs:63-67: triangles permuted by primitive_indices."""
         _, prims, _ = self.get()
         return np.ascontiguousarray(np.asarray(tris, dtype=np.float32)[prims])
+
+    def aabb_traverse(self, queries, direction=(0.0, 0.0, 0.0)):
+        """traverse!(.., node.intersect_aabb(&aabb, state.oct_inv4), ..) per query: (counts, primitive slots in call order)"""
+        d = np.ascontiguousarray(direction, dtype=np.float32)
+        return _query(lib().orc_cwbvh_aabb_traverse, self.h, queries, 8, (_p(d),))
+
+    def point_traverse(self, points, direction=(0.0, 0.0, 0.0)):
+        d = np.ascontiguousarray(direction, dtype=np.float32)
+        return _query(lib().orc_cwbvh_point_traverse, self.h, points4(points), 4, (_p(d),))
 
     def ray_traverse(self, bvh_tris, rays, threads=0, use_simd=True, counters=None):
         bvh_tris = _f32c(bvh_tris, 12) if len(bvh_tris) else np.zeros((0, 12), np.float32)
