@@ -193,6 +193,10 @@ int obvhs_cuda_bvh2_collapse(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t max_pri
  * reinsertion(ratio * post_collapse multiplier). The permuted triangles are attached to the result. */
 int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
                                     double* core_build_seconds, ObvhsBvh2** out);
+/* build_bvh2<T: Boundable>(primitives, config, core_build_time) -> Bvh2  (src/bvh2/builder.rs:103-140) over AABBs:
+ * PLOC -> reinsertion -> SAH leaf collapse -> reinsertion. config.pre_split is ignored, as in the reference. */
+int obvhs_cuda_build_bvh2(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, const ObvhsBuildParams* params,
+                          double* core_build_seconds, ObvhsBvh2** out);
 /* bvh_tris[i] = tris[primitive_indices[i]] kept on the device inside the handle (examples/demoscene.rs:66-70) */
 int obvhs_cuda_bvh2_set_triangles(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* tris, size_t n);
 /* Batched Bvh2::ray_traverse / ray_traverse_miss / counting ray_traverse_anyhit over triangles (bvh2/mod.rs:148-334,
@@ -216,6 +220,10 @@ int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t m
  * triangle array (examples/obj_cwbvh.rs:63-67) is attached to the result so it can be traversed directly. */
 int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
                                      double* core_build_seconds, ObvhsCwBvh** out);
+/* build_cwbvh<T: Boundable>(primitives, config, core_build_time) -> CwBvh  (src/cwbvh/builder.rs:98-123) over AABBs:
+ * PLOC -> reinsertion -> collapse. config.pre_split is ignored, as in the reference. The handle carries no triangles. */
+int obvhs_cuda_build_cwbvh(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, const ObvhsBuildParams* params,
+                           double* core_build_seconds, ObvhsCwBvh** out);
 void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh);
 size_t obvhs_cuda_cwbvh_node_count(const ObvhsCwBvh* bvh);
 size_t obvhs_cuda_cwbvh_prim_count(const ObvhsCwBvh* bvh);

@@ -97,6 +97,8 @@ SIGNATURES = {
     "obvhs_cuda_bvh2_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_bvh2_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "obvhs_cuda_bvh2_to_cwbvh": (_i32, [_vp, _vp, _u32, _i32, _i32, _PP]),
+    "obvhs_cuda_build_cwbvh": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
+    "obvhs_cuda_build_bvh2": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
     "obvhs_cuda_build_cwbvh_from_tris": (_i32, [_vp, _vp, _sz, C.POINTER(BuildParamsC), C.POINTER(C.c_double), _PP]),
     "obvhs_cuda_cwbvh_free": (None, [_vp]),
     "obvhs_cuda_cwbvh_node_count": (_sz, [_vp]),
@@ -682,6 +684,30 @@ def build_bvh2_from_tris(triangles, config: BvhBuildParams, core_build_time: lis
     if core_build_time is not None:
         core_build_time[0] += secs.value
     return bvh
+
+
+def _build_from_aabbs(fn_name, cls, primitives, config, core_build_time, ctx):
+    ctx = ctx or default_context()
+    a = _as_f32(primitives, 8)
+    secs = C.c_double(0.0)
+    params = config.to_c()
+    h = C.c_void_p()
+    ctx.check(getattr(ctx.lib, fn_name)(ctx.h, _ptr(a), a.shape[0], C.byref(params), C.byref(secs), C.byref(h)))
+    bvh = cls(ctx, h)
+    bvh.core_build_seconds = secs.value
+    if core_build_time is not None:
+        core_build_time[0] += secs.value
+    return bvh
+
+
+def build_cwbvh(primitives, config: BvhBuildParams, core_build_time: list | None = None, ctx: Context | None = None) -> CwBvh:
+    """src/cwbvh/builder.rs:98-123 `build_cwbvh<T: Boundable>`; primitives are AABBs (n, 8). pre_split is ignored."""
+    return _build_from_aabbs("obvhs_cuda_build_cwbvh", CwBvh, primitives, config, core_build_time, ctx)
+
+
+def build_bvh2(primitives, config: BvhBuildParams, core_build_time: list | None = None, ctx: Context | None = None) -> Bvh2:
+    """src/bvh2/builder.rs:103-140 `build_bvh2<T: Boundable>`; primitives are AABBs (n, 8). pre_split is ignored."""
+    return _build_from_aabbs("obvhs_cuda_build_bvh2", Bvh2, primitives, config, core_build_time, ctx)
 
 
 def make_rays(origin_dir, tmin=0.0, tmax=3.4028234663852886e38, out=None, ctx: Context | None = None):

@@ -707,6 +707,45 @@ int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tri
     return OBVHS_OK;
 }
 
+// build_cwbvh<T: Boundable> (cwbvh/builder.rs:98-123): PLOC over the AABBs -> reinsertion -> collapse; pre_split is ignored
+int obvhs_cuda_build_cwbvh(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, const ObvhsBuildParams* params, double* core_build_seconds,
+                           ObvhsCwBvh** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, params && out, "null argument");
+    ARG_CHECK(ctx, n == 0 || aabbs, "aabbs is null");
+    DevBuf<ObvhsAabb> st;
+    const ObvhsAabb* d_aabbs = nullptr;
+    ST_TRY(stage_in(ctx, aabbs, n, st, &d_aabbs));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    ObvhsBvh2* bvh2 = nullptr;
+    {
+        TraceScope ts(ctx, "build_ploc");
+        ST_TRY(ploc_build_device(ctx, d_aabbs, nullptr, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                                 (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    }
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { obvhs_cuda_bvh2_free(b); }
+    } guard{bvh2};
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 3 ? 3 : params->max_prims_per_leaf);  // builder.rs:112
+    ObvhsCwBvh* cw = nullptr;
+    ST_TRY(bvh2_to_cwbvh_device(ctx, bvh2, mp, true, &cw));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        obvhs_cuda_cwbvh_free(cw);
+        OBVHS_SET_ERR(ctx, "build_cwbvh: stream synchronisation failed");
+        return OBVHS_ERR_CUDA;
+    }
+    if (core_build_seconds) {
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *core_build_seconds += (double)ms * 1e-3;
+    }
+    *out = cw;
+    return OBVHS_OK;
+}
+
 void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh) {
     if (!bvh) return;
     ObvhsContext* ctx = bvh->owner;
@@ -971,6 +1010,40 @@ int obvhs_cuda_bvh2_collapse(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t max_pri
     }
     return bvh2_collapse_device(ctx, bvh, max_prims, traversal_cost);
 }
+// build_bvh2<T: Boundable> (bvh2/builder.rs:103-140): PLOC -> reinsertion -> collapse -> reinsertion; pre_split is ignored
+int obvhs_cuda_build_bvh2(ObvhsContext* ctx, const ObvhsAabb* aabbs, size_t n, const ObvhsBuildParams* params, double* core_build_seconds,
+                          ObvhsBvh2** out) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, params && out, "null argument");
+    ARG_CHECK(ctx, n == 0 || aabbs, "aabbs is null");
+    DevBuf<ObvhsAabb> st;
+    const ObvhsAabb* d_aabbs = nullptr;
+    ST_TRY(stage_in(ctx, aabbs, n, st, &d_aabbs));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    ObvhsBvh2* bvh2 = nullptr;
+    ST_TRY(ploc_build_device(ctx, d_aabbs, nullptr, nullptr, n, params->ploc_search_distance, params->sort_precision,
+                             (size_t)params->search_depth_threshold, &bvh2, nullptr));
+    struct Guard {
+        ObvhsBvh2* b;
+        ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }
+    } guard{bvh2};
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
+    u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 255 ? 255 : params->max_prims_per_leaf);  // builder.rs:121
+    ST_TRY(bvh2_collapse_device(ctx, bvh2, mp, params->collapse_traversal_cost));
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio * params->post_collapse_reinsertion_batch_ratio_multiplier,
+                                  nullptr, 0, nullptr));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (core_build_seconds) {
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *core_build_seconds += (double)ms * 1e-3;
+    }
+    guard.b = nullptr;
+    *out = bvh2;
+    return OBVHS_OK;
+}
+
 int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
                                     double* core_build_seconds, ObvhsBvh2** out) {
     API_ENTER(ctx);

@@ -6,6 +6,7 @@ import pytest
 
 import oracle_bind as ob
 from obvhs_b200 import camera, test_util as tu
+from obvhs_b200.types import make_rays
 
 from test_gpu_parity import TRAVERSE_MODES, assert_nodes_equal, rays_for
 
@@ -152,3 +153,65 @@ def test_large_collapse_and_bvh2_traversal_properties(api):
     assert hit.sum() > 1000
     assert np.array_equal(hb["t"][hit].view(np.uint32), hc["t"][hit].view(np.uint32))
     assert np.array_equal(np.isinf(hb["t"]), ~hit)
+
+
+PRESET_NAMES = ["fastest_build", "very_fast_build", "fast_build", "medium_build", "slow_build", "very_slow_build"]
+
+
+@pytest.mark.parametrize("preset", PRESET_NAMES)
+def test_reference_degenerate_builds_over_aabbs(api, preset):
+    # tests/mod.rs:35-88: build_bvh2 / build_cwbvh over one empty AABB, ten infinite, ten LARGEST, and nothing; a ray must never
+    # report a hit (the test's closure returns +inf for every primitive: here triangles that cannot be hit)
+    inf, mx = np.float32(np.inf), np.float32(3.4028235e38)
+    cases = {
+        "empty": np.array([[mx, mx, mx, 0, -mx, -mx, -mx, 0]], np.float32),
+        "inf": np.tile(np.array([[-inf, -inf, -inf, 0, inf, inf, inf, 0]], np.float32), (10, 1)),
+        "max": np.tile(np.array([[-mx, -mx, -mx, 0, mx, mx, mx, 0]], np.float32), (10, 1)),
+        "nothing": np.zeros((0, 8), np.float32),
+    }
+    ray = make_rays(np.array([[0.0, 0.0, 1.0]], np.float32), np.array([[0.0, 0.0, -1.0]], np.float32), 0.0, np.inf)
+    p = api.BvhBuildParams.preset(preset)
+    sd, thr, ratio, mult, prec, mp, cost = ob.BVH2_PRESETS[preset][:7]
+    for name, aabbs in cases.items():
+        far = np.zeros((max(1, aabbs.shape[0]), 12), np.float32)
+        far[:, [0, 4, 8]] = 1e30
+        b = api.build_bvh2(aabbs, p)
+        want = ob.ploc_build(aabbs, None, sd, prec, thr)
+        want.reinsertion_run(ratio)
+        want.collapse(mp, cost)
+        want.reinsertion_run(ratio * mult)
+        gn, gp = b.download()
+        wn, wp = want.get()
+        assert np.array_equal(gp, wp), (name, preset)
+        assert_nodes_equal(gn, wn, f"build_bvh2 {name} {preset}")
+        if aabbs.shape[0]:
+            b.set_triangles(far)
+        assert not (b.ray_traverse(ray)["t"][0] < np.inf), name
+        if name in ("inf", "max"):
+            # the reference only builds CwBvhs over the empty box and over nothing (tests/mod.rs:62-88); with infinite boxes its
+            # child ordering panics (bvh2_to_cwbvh.rs order_children, NaN centres). The library reports an error instead.
+            with pytest.raises(api.ObvhsError):
+                api.build_cwbvh(aabbs, p)
+            continue
+        c = api.build_cwbvh(aabbs, p)
+        wc = ob.ploc_build(aabbs, None, sd, prec, thr)
+        wc.reinsertion_run(ratio)
+        wc = wc.to_cwbvh(min(max(mp, 1), 3))
+        assert c.download()[0].tobytes() == wc.get()[0].tobytes(), (name, preset)
+        if aabbs.shape[0]:
+            c.set_triangles(far)
+        assert not (c.ray_traverse(ray)["t"][0] < np.inf), name
+
+
+def test_build_over_aabbs_equals_component_calls(api, scenes):
+    tris = scenes["kitchen"]
+    aabbs = ob.tri_aabbs(tris)
+    for preset in ("fast_build", "medium_build"):
+        p = api.BvhBuildParams.preset(preset)
+        t = [0.0]
+        a = api.build_cwbvh(aabbs, p, t).download()
+        b = api.build_cwbvh_from_tris(tris, p).download()
+        assert t[0] > 0 and a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1])
+        a = api.build_bvh2(aabbs, p).download()
+        b = api.build_bvh2_from_tris(tris, p).download()
+        assert_nodes_equal(a[0], b[0], preset)
