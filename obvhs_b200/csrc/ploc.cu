@@ -353,30 +353,38 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
         total += s;
     }
     u64 thread_excl = wbase + x - local;
-    // decoupled look-back over tiles (one thread)
-    if (threadIdx.x == 0) {
+    // decoupled look-back over tiles by warp 0: 32 predecessors per L2 round trip (a one-thread walk pays the full latency per
+    // predecessor, and the first wave of a 10M-cluster iteration has > 1000 tiles with aggregates only)
+    if (threadIdx.x < 32) {
         volatile u64* st = scan_status;
         u64 excl = 0;
         if (tile == 0) {
-            st[0] = SCAN_INCL | total;
+            if (lane == 0) st[0] = SCAN_INCL | total;
         } else {
-            st[tile] = SCAN_AGG | total;
-            u32 t = tile - 1;
+            if (lane == 0) st[tile] = SCAN_AGG | total;
+            long long t = (long long)tile - 1;  // lane k looks at tile t - k
             for (;;) {
-                u64 s = st[t];
-                if (s & SCAN_INCL) {
-                    excl += s & SCAN_MASK;
-                    break;
-                }
-                if (s & SCAN_AGG) {
-                    excl += s & SCAN_MASK;
-                    t--;
-                }
+                const long long mine = t - lane;
+                u64 sv = 2ull << 62;  // SCAN_INCL | 0: tiles before the first one
+                if (mine >= 0) sv = st[mine];
+                const u32 incl = __ballot_sync(0xffffffffu, (sv & SCAN_INCL) != 0);
+                const u32 ready = __ballot_sync(0xffffffffu, (sv & (SCAN_INCL | SCAN_AGG)) != 0);
+                // consume lanes 0..first-1 while they are ready; stop at the first inclusive value (tiles < 0 count as one)
+                const u32 not_ready = ~ready;
+                const int first_gap = not_ready ? __ffs(not_ready) - 1 : 32;
+                const int first_incl = incl ? __ffs(incl) - 1 : 32;
+                const int upto = min(first_gap, first_incl + 1);  // number of lanes whose value is consumed
+                u64 v = lane < upto ? (sv & SCAN_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (first_incl < first_gap) break;
+                t -= upto;
             }
-            st[tile] = SCAN_INCL | (excl + total);
+            if (lane == 0) st[tile] = SCAN_INCL | (excl + total);
         }
-        s_excl = excl;
-        if (tile == tiles - 1) {  // loop state of the next iteration
+        if (lane == 0) s_excl = excl;
+        if (lane == 0 && tile == tiles - 1) {  // loop state of the next iteration
             u64 all = excl + total;
             u32 outs = (u32)(all & 0x7fffffffull), merges = (u32)(all >> 31);
             g->state[parity ^ 1].count = outs;

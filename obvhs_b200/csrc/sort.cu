@@ -1,5 +1,5 @@
 // sort.cu -- stable LSD radix sort of (key, u32 value) pairs: "onesweep" (one read + one write of the pairs per
-// 8-bit digit, chained-scan / decoupled look-back across tiles) with warp-level multisplit ranking (__match_any).
+// 8-bit digit, chained-scan / decoupled look-back across tiles) with warp-level multisplit ranking (ballot per digit bit).
 //
 // Replaces the reference's sorts on the hot path:
 //   Morton sort            src/ploc/mod.rs:811-827  (par_sort_unstable_by_key / sort_unstable_by_key / rdst radix)
@@ -15,8 +15,14 @@ namespace {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
+// pairs per thread / per tile: the 10M-key Morton sort (u64 keys) streams best with 4096-pair tiles at 3 CTAs per SM; the
+// reinsertion sorts (u32 keys, at most a few hundred thousand pairs) want more, smaller tiles to fill the 148 SMs
+template <typename K>
+struct SortCfg {
+    static constexpr int ITEMS = sizeof(K) == 8 ? 16 : 8;
+    static constexpr int TILE = SORT_THREADS * ITEMS;
+    static constexpr int MIN_CTAS = sizeof(K) == 8 ? 3 : 4;
+};
 constexpr u32 FLAG_AGG = 1u << 30, FLAG_INCL = 2u << 30, STATUS_MASK = (1u << 30) - 1;
 
 // all digit histograms in one read of the keys
@@ -58,10 +64,25 @@ __global__ void __launch_bounds__(256) sort_scan_kernel(const u32* __restrict__ 
 __device__ __forceinline__ u32 ld_status(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
 __device__ __forceinline__ void st_status(u32* p, u32 v) { *reinterpret_cast<volatile u32*>(p) = v; }
 
+// Lanes of the warp holding the same 8-bit digit. Eight ballots instead of `match.any.sync`: MATCH iterates once per
+// DISTINCT value in the warp (about 30 for random digits), which made the ranking loop the bottleneck of a 10M-key pass
+// (164 us for 240 MB); the ballots are full-rate and independent of the data.
+__device__ __forceinline__ u32 digit_peers(u32 d) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const u32 bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 template <typename K, bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+__global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
                                                                 const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
                                                                 int shift, const u32* __restrict__ goffs, u32* status, u32* ticket) {
+    constexpr int SORT_ITEMS = SortCfg<K>::ITEMS, SORT_TILE = SortCfg<K>::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* skeys = reinterpret_cast<K*>(smem_raw);
     u32* svals = reinterpret_cast<u32*>(skeys + SORT_TILE);
@@ -82,7 +103,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restr
 
     K key[SORT_ITEMS];
     u32 val[SORT_ITEMS];
-    u32 rank[SORT_ITEMS];
+    u32 rank2[SORT_ITEMS / 2];  // ranks are < 4096: two per register (register budget: 3-4 CTAs per SM)
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         size_t idx = wstart + i * 32 + lane;
@@ -95,9 +116,11 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restr
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         u32 d = (u32)((key[i] >> shift) & 0xff);
-        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 peers = digit_peers(d);
         u32 pre = mywh[d];
-        rank[i] = pre + __popc(peers & lt);
+        const u32 r = pre + __popc(peers & lt);
+        if (i & 1) rank2[i / 2] |= r << 16;
+        else rank2[i / 2] = r;
         __syncwarp();
         if ((peers & lt) == 0) mywh[d] = pre + __popc(peers);
         __syncwarp();
@@ -132,17 +155,31 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restr
         st_status(st, FLAG_INCL | agg);
     } else {
         st_status(st, FLAG_AGG | agg);
-        const u32* prev = st - 256;
-        for (;;) {
-            u32 s = ld_status(prev);
-            if (s & FLAG_INCL) {
-                excl += s & STATUS_MASK;
-                break;
+        // Windowed look-back: LOOKBACK predecessor words are requested at once (independent L2 round trips in flight) and
+        // then consumed in order. A one-word-at-a-time walk made the first wave of CTAs (hundreds of tiles that only have
+        // aggregates yet) pay one full L2 latency per predecessor: 160 of the 164 us of a 10M-key pass.
+        constexpr int LOOKBACK = 8;
+        long long t = (long long)tile - 1;
+        bool done = false;
+        while (!done) {
+            u32 w[LOOKBACK];
+#pragma unroll
+            for (int k = 0; k < LOOKBACK; k++) w[k] = (t - k >= 0) ? ld_status(status + (size_t)(t - k) * 256 + tid) : FLAG_INCL;
+            int used = 0;
+#pragma unroll
+            for (int k = 0; k < LOOKBACK; k++) {
+                if (!done && used == k) {
+                    const u32 sv = w[k];
+                    if (sv & FLAG_INCL) {
+                        excl += sv & STATUS_MASK;
+                        done = true;
+                    } else if (sv & FLAG_AGG) {
+                        excl += sv & STATUS_MASK;
+                        used = k + 1;
+                    }  // else: not published yet -- stop consuming, re-read from this tile
+                }
             }
-            if (s & FLAG_AGG) {
-                excl += s & STATUS_MASK;
-                prev -= 256;
-            }
+            t -= used;
         }
         st_status(st, FLAG_INCL | (excl + agg));
     }
@@ -151,7 +188,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const K* __restr
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         u32 d = (u32)((key[i] >> shift) & 0xff);
-        u32 pos = dstart[d] + mywh[d] + rank[i];
+        u32 pos = dstart[d] + mywh[d] + ((rank2[i / 2] >> ((i & 1) * 16)) & 0xffffu);
         skeys[pos] = key[i];
         svals[pos] = val[i];
     }
@@ -205,7 +242,7 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
             key[i] = kbuf[src][idx];
             val[i] = vbuf[src][idx];
             u32 d = (u32)((key[i] >> shift) & 0xff);
-            u32 peers = __match_any_sync(0xffffffffu, d);
+            u32 peers = digit_peers(d);
             u32 pre = mywh[d];
             rank[i] = pre + __popc(peers & lt);
             __syncwarp();
@@ -253,7 +290,7 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
 
 template <typename K>
 constexpr size_t onesweep_smem() {
-    return (size_t)SORT_TILE * (sizeof(K) + 4) + (SORT_WARPS * 256 + 512) * 4;
+    return (size_t)SortCfg<K>::TILE * (sizeof(K) + 4) + (SORT_WARPS * 256 + 512) * 4;
 }
 
 template <typename K>
@@ -279,7 +316,7 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
         *sorted_vals = vals_alt;
         return OBVHS_OK;
     }
-    const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const size_t tiles = (n + SortCfg<K>::TILE - 1) / SortCfg<K>::TILE;
     // scratch: ghist[passes*256] goffs[passes*256] ticket[passes (padded to 8)] status[passes*tiles*256]
     const size_t words = (size_t)passes * 512 + 8 + (size_t)passes * tiles * 256;
     DevBuf<u32> scratch;
@@ -299,6 +336,9 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
     if (!attr_set[which]) {
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
+        // four CTAs per SM need ~140 KB of shared memory: ask for the largest carve-out
+        CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[which] = true;
     }
     K *kin = keys, *kout = keys_alt;

@@ -70,5 +70,49 @@ def full(src, dst, title):
     print(dst)
 
 
+def build(src, dst, title, peak_gbs="6553.3"):
+    """per-kernel DRAM traffic / achieved bandwidth of ONE build (a csv of `ncu --metrics duration,dram bytes` over
+    scripts/trace_build.py): launches between the last leaf_init and the end."""
+    peak = float(peak_gbs)
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        key = (row["ID"], row["Kernel Name"])
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        if row["Metric Name"] == "gpu__time_duration.sum":
+            v = v / 1000 if unit == "ns" else v * 1000 if unit == "ms" else v * 1e6 if unit == "s" else v  # -> us
+        else:
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        per.setdefault(key, {})[row["Metric Name"]] = v
+    rows = [(k[1], m) for k, m in per.items()]
+    idx = [i for i, (n, _) in enumerate(rows) if "leaf_init" in n or "presplit_aabb" in n]
+    rows = rows[idx[-1]:] if idx else rows
+    agg = collections.OrderedDict()
+    for n, m in rows:
+        n = re.sub(r"\(.*", "", n)
+        n = re.sub(r"void |\(anonymous namespace\)::|<unnamed>::", "", n)
+        a = agg.setdefault(n, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += m.get("gpu__time_duration.sum", 0.0)
+        a[2] += m.get("dram__bytes_read.sum", 0.0)
+        a[3] += m.get("dram__bytes_write.sum", 0.0)
+    tot_t = sum(a[1] for a in agg.values())
+    tot_b = sum(a[2] + a[3] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# {title}\n\n")
+        f.write("Source: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` over one "
+                "`build_cwbvh_from_tris` (third build of scripts/trace_build.py: arena and result cache warm).\n")
+        f.write("Per-launch times under ncu are serialised and cold-cache; achieved GB/s = DRAM bytes / that time, against the measured "
+                f"copy bandwidth of {peak:.0f} GB/s (MEASURED_PEAKS.json).\n\n")
+        f.write(f"Total: {len(rows)} launches, {tot_t / 1000:.2f} ms of kernel time, {tot_b / 1e9:.2f} GB of DRAM traffic "
+                f"({tot_b / 1e9 / (tot_t * 1e-6) if tot_t else 0:.0f} GB/s average, {100 * tot_b / 1e9 / (tot_t * 1e-6) / peak if tot_t else 0:.0f} % of peak).\n\n")
+        f.write("| kernel | launches | time us | share | DRAM read MB | DRAM write MB | GB/s | % of HBM peak |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
+        for n, (c, t, r, w) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            gbs = (r + w) / 1e9 / (t * 1e-6) if t else 0.0
+            f.write(f"| `{n[:90]}` | {c} | {t:.1f} | {100 * t / tot_t:.1f}% | {r / 1e6:.1f} | {w / 1e6:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f}% |\n")
+    print(dst, len(rows), "launches", f"{tot_t:.1f} us")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:5])
+    {"launches": launches, "full": full, "build": build}[sys.argv[1]](*sys.argv[2:6])
