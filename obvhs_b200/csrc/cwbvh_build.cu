@@ -69,44 +69,77 @@ struct CwGlobals {
     u32 level_len[48];
 };
 
+// bvh2_to_cwbvh.rs:246-257: every decision of a leaf is LEAF with cost area * prims * 0.3
+__device__ __forceinline__ Dec leaf_dec(const Node32& nd) {
+    const float cost_leaf = box_half_area(node_box(nd)) * (float)nd.prim_count * PRIM_COST;
+    Dec d;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        d.cost[k] = cost_leaf;
+        d.S[k] = 0;
+    }
+    d.meta_lo = 0;  // kind LEAF, left/right 0 (Decision::default indices)
+    d.meta_hi = 0;
+    return d;
+}
+
 // K11: calculate_cost_impl (bvh2_to_cwbvh.rs:220-344), bottom-up: one thread per BVH2 leaf climbs, the second arriver at
-// an inner node computes its record from the two children's records only.
-__global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ parents, u32 n_nodes,
+// an inner node computes its record. A climbing thread CARRIES the record of the child it comes from in registers, so only the
+// sibling's record is read back; records of leaves are never stored (they are a function of the leaf node itself and are
+// recomputed by whoever needs them, here and in the emit pass), which halves the pass's DRAM writes.
+constexpr int COST_THREADS = 64;  // small CTAs: a CTA lives as long as its longest climber, and most threads stop after one or two levels
+__global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ parents, u32 n_nodes,
                                                          u32 max_prims_per_leaf, Dec* dec, u32* P, u32* arrivals) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     Node32 nd = load_node(nodes + i);
     if (nd.prim_count == 0) return;  // start at leaves
-    {
-        float ha = box_half_area(node_box(nd));
-        float cost_leaf = ha * (float)nd.prim_count * PRIM_COST;
-        Dec d;
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            d.cost[k] = cost_leaf;
-            d.S[k] = 0;
-        }
-        d.meta_lo = 0;  // kind LEAF, left/right 0 (Decision::default indices)
-        d.meta_hi = 0;
-        store_dec(dec + i, d);
-        P[i] = nd.prim_count;
+    Dec mine = leaf_dec(nd);
+    u32 my_prims = nd.prim_count, me = i;
+    bool mine_is_leaf = true;
+    if (i == 0) {  // a single-leaf tree: the host reads S[0] of the root record
+        store_dec(dec, mine);
+        P[0] = my_prims;
+        return;
     }
-    if (i == 0) return;
-    u32 node = parents[i];
     for (;;) {
-        __threadfence();
+        const u32 node = parents[me];
+        if (!mine_is_leaf) {  // publish before signalling: the sibling's thread (or the emit pass) reads it
+            store_dec(dec + me, mine);
+            P[me] = my_prims;
+            __threadfence();
+        }
         if (atomicAdd(&arrivals[node], 1u) == 0) return;
-        Node32 me = load_node_cg(nodes + node);
-        const u32 first = me.first_index;
-        float ha = box_half_area(node_box(me));
-        const Dec L = load_dec_cg(dec + first), R = load_dec_cg(dec + first + 1);
-        u32 num_primitives = __ldcg(&P[first]) + __ldcg(&P[first + 1]);
+        const u32 sib = sibling_id(me);
+        const Node32 pn = load_node(nodes + node), sn = load_node(nodes + sib);
+        Dec sd = load_dec_cg(dec + sib);  // (unwritten memory when the sibling is a leaf: replaced below)
+        u32 sib_prims = __ldcg(&P[sib]);
+        if (sn.prim_count != 0) {
+            sd = leaf_dec(sn);
+            sib_prims = sn.prim_count;
+        }
+        const bool me_left = (me & 1u) != 0;  // bvh2/node.rs:154-180: the left sibling has the odd index
+        const Dec L = me_left ? mine : sd, R = me_left ? sd : mine;
+        const float ha = box_half_area(node_box(pn));
+        const u32 num_primitives = my_prims + sib_prims;
         Dec d;
         u32 meta[7];
+        // What child k of a side contributes to S when the parent's decision picks index k for it (get_children,
+        // bvh2_to_cwbvh.rs:346-397): a DISTRIBUTE child is expanded (its own S[k]), anything else is collected as a child
+        // (a wide node counts itself plus everything below it). Computed once with static indices and carried through the
+        // arg-min below, instead of indexing the records with the winning (run-time) indices afterwards.
+        const u32 wideL = (dec_meta_of(L, 0) & 3u) == KIND_INTERNAL ? 1u + L.S[0] : 0u;
+        const u32 wideR = (dec_meta_of(R, 0) & 3u) == KIND_INTERNAL ? 1u + R.S[0] : 0u;
+        u32 effL[7], effR[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            effL[k] = (dec_meta_of(L, k) & 3u) == KIND_DISTRIBUTE ? L.S[k] : wideL;
+            effR[k] = (dec_meta_of(R, k) & 3u) == KIND_DISTRIBUTE ? R.S[k] : wideR;
+        }
         {  // i = 0
             float cost_leaf = num_primitives <= max_prims_per_leaf ? ((float)num_primitives * ha) * PRIM_COST : __int_as_float(0x7f800000);
             float cost_distribute = __int_as_float(0x7f800000);
-            u32 dl = 7, dr = 7;
+            u32 dl = 7, dr = 7, sv = 0;
 #pragma unroll
             for (int k = 0; k < 7; k++) {
                 float c = L.cost[k] + R.cost[6 - k];
@@ -114,6 +147,7 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
                     cost_distribute = c;
                     dl = k;
                     dr = 6 - k;
+                    sv = effL[k] + effR[6 - k];
                 }
             }
             float cost_internal = cost_distribute + ha;
@@ -124,11 +158,12 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
                 d.cost[0] = cost_internal;
                 meta[0] = KIND_INTERNAL | dl << 2 | dr << 5;
             }
+            d.S[0] = sv;  // 0 while no pair was chosen (dl == dr == 7)
         }
 #pragma unroll
         for (int ii = 1; ii < 7; ii++) {
             float cost_distribute = d.cost[ii - 1];
-            u32 dl = 7, dr = 7;
+            u32 dl = 7, dr = 7, sv = d.S[ii - 1];
 #pragma unroll
             for (int k = 0; k < ii; k++) {
                 float c = L.cost[k] + R.cost[ii - k - 1];
@@ -136,31 +171,25 @@ __global__ void __launch_bounds__(256) cwbvh_cost_kernel(const Node32* __restric
                     cost_distribute = c;
                     dl = k;
                     dr = ii - k - 1;
+                    sv = effL[k] + effR[ii - k - 1];
                 }
             }
             d.cost[ii] = cost_distribute;
             if (dl != 7) meta[ii] = KIND_DISTRIBUTE | dl << 2 | dr << 5;
-            else meta[ii] = meta[ii - 1];  // decisions[node_i] = decisions[node_i - 1]
-        }
-        // what a wide-node child contributes when it is collected as a child (not expanded): itself + everything below
-        const u32 wideL = (dec_meta_of(L, 0) & 3u) == KIND_INTERNAL ? 1u + L.S[0] : 0u;
-        const u32 wideR = (dec_meta_of(R, 0) & 3u) == KIND_INTERNAL ? 1u + R.S[0] : 0u;
-#pragma unroll
-        for (int ii = 0; ii < 7; ii++) {
-            u32 dl = (meta[ii] >> 2) & 7u, dr = (meta[ii] >> 5) & 7u;
-            u32 sv = 0;
-            if (dl != 7u && dr != 7u) {  // get_children (bvh2_to_cwbvh.rs:346-397): expand a DISTRIBUTE child, else collect it
-                sv += (dec_meta_of(L, dl) & 3u) == KIND_DISTRIBUTE ? L.S[dl] : wideL;
-                sv += (dec_meta_of(R, dr) & 3u) == KIND_DISTRIBUTE ? R.S[dr] : wideR;
-            }
+            else meta[ii] = meta[ii - 1];  // decisions[node_i] = decisions[node_i - 1] (and with it the same S)
             d.S[ii] = sv;
         }
         d.meta_lo = meta[0] | meta[1] << 8 | meta[2] << 16 | meta[3] << 24;
         d.meta_hi = meta[4] | meta[5] << 8 | meta[6] << 16;
-        store_dec(dec + node, d);
-        P[node] = num_primitives;
-        if (node == 0) return;
-        node = parents[node];
+        if (node == 0) {
+            store_dec(dec, d);
+            P[0] = num_primitives;
+            return;
+        }
+        mine = d;
+        my_prims = num_primitives;
+        me = node;
+        mine_is_leaf = false;
     }
 }
 
@@ -182,6 +211,12 @@ __device__ __forceinline__ void entry_load(Entry& e, const Node32* __restrict__ 
     e.meta_hi = q2.x;
     e.S0 = q2.y;
     e.P = __ldcg(P + e.node);
+    if (e.n.prim_count != 0) {  // leaves have no stored record (see cwbvh_cost_kernel): all LEAF decisions, nothing below
+        e.meta_lo = 0;
+        e.meta_hi = 0;
+        e.S0 = 0;
+        e.P = e.n.prim_count;
+    }
 }
 
 // K12: convert_to_cwbvh_impl (bvh2_to_cwbvh.rs:75-193) for one wide node, executed by a GROUP OF 8 LANES (four nodes per
@@ -582,7 +617,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, root_box.alloc(8, s));
     CU_TRY(ctx, cudaMemsetAsync(arrivals.p, 0, (size_t)n_nodes * 4, s));
     CU_TRY(ctx, cudaMemsetAsync(g.p, 0, sizeof(CwGlobals), s));
-    cwbvh_cost_kernel<<<div_up(n_nodes, 256), 256, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
+    cwbvh_cost_kernel<<<div_up(n_nodes, COST_THREADS), COST_THREADS, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
     KERNEL_CHECK(ctx);
     root_aabb_kernel<<<1, 1, 0, s>>>(bvh->nodes, root_box.p);
     KERNEL_CHECK(ctx);
