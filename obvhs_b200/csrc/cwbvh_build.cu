@@ -15,6 +15,7 @@
 //                              prim_base(c_j)  = prim_base(N) + direct_prims(N) + sum_{i<j} P(c_i)
 //                          so every node lands at the index and with the bytes the sequential recursion gives.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "cwbvh_exponent.h"
@@ -83,8 +84,72 @@ __device__ __forceinline__ Dec leaf_dec(const Node32& nd) {
     return d;
 }
 
-// K11: calculate_cost_impl (bvh2_to_cwbvh.rs:220-344), bottom-up: one thread per BVH2 leaf climbs, the second arriver at
-// an inner node computes its record. A climbing thread CARRIES the record of the child it comes from in registers, so only the
+// One inner node of calculate_cost_impl (bvh2_to_cwbvh.rs:259-343) from the records of its two children.
+__device__ __forceinline__ Dec inner_dec(const Dec& L, const Dec& R, float ha, u32 num_primitives, u32 max_prims_per_leaf) {
+    Dec d;
+    u32 meta[7];
+    // What child k of a side contributes to S when the parent's decision picks index k for it (get_children,
+    // bvh2_to_cwbvh.rs:346-397): a DISTRIBUTE child is expanded (its own S[k]), anything else is collected as a child
+    // (a wide node counts itself plus everything below it). Computed once with static indices and carried through the
+    // arg-min below, instead of indexing the records with the winning (run-time) indices afterwards.
+    const u32 wideL = (dec_meta_of(L, 0) & 3u) == KIND_INTERNAL ? 1u + L.S[0] : 0u;
+    const u32 wideR = (dec_meta_of(R, 0) & 3u) == KIND_INTERNAL ? 1u + R.S[0] : 0u;
+    u32 effL[7], effR[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        effL[k] = (dec_meta_of(L, k) & 3u) == KIND_DISTRIBUTE ? L.S[k] : wideL;
+        effR[k] = (dec_meta_of(R, k) & 3u) == KIND_DISTRIBUTE ? R.S[k] : wideR;
+    }
+    {  // i = 0
+        float cost_leaf = num_primitives <= max_prims_per_leaf ? ((float)num_primitives * ha) * PRIM_COST : __int_as_float(0x7f800000);
+        float cost_distribute = __int_as_float(0x7f800000);
+        u32 dl = 7, dr = 7, sv = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            float c = L.cost[k] + R.cost[6 - k];
+            if (c < cost_distribute) {
+                cost_distribute = c;
+                dl = k;
+                dr = 6 - k;
+                sv = effL[k] + effR[6 - k];
+            }
+        }
+        float cost_internal = cost_distribute + ha;
+        if (cost_leaf < cost_internal) {
+            d.cost[0] = cost_leaf;
+            meta[0] = KIND_LEAF | dl << 2 | dr << 5;
+        } else {
+            d.cost[0] = cost_internal;
+            meta[0] = KIND_INTERNAL | dl << 2 | dr << 5;
+        }
+        d.S[0] = sv;  // 0 while no pair was chosen (dl == dr == 7)
+    }
+#pragma unroll
+    for (int ii = 1; ii < 7; ii++) {
+        float cost_distribute = d.cost[ii - 1];
+        u32 dl = 7, dr = 7, sv = d.S[ii - 1];
+#pragma unroll
+        for (int k = 0; k < ii; k++) {
+            float c = L.cost[k] + R.cost[ii - k - 1];
+            if (c < cost_distribute) {
+                cost_distribute = c;
+                dl = k;
+                dr = ii - k - 1;
+                sv = effL[k] + effR[ii - k - 1];
+            }
+        }
+        d.cost[ii] = cost_distribute;
+        if (dl != 7) meta[ii] = KIND_DISTRIBUTE | dl << 2 | dr << 5;
+        else meta[ii] = meta[ii - 1];  // decisions[node_i] = decisions[node_i - 1] (and with it the same S)
+        d.S[ii] = sv;
+    }
+    d.meta_lo = meta[0] | meta[1] << 8 | meta[2] << 16 | meta[3] << 24;
+    d.meta_hi = meta[4] | meta[5] << 8 | meta[6] << 16;
+    return d;
+}
+
+// K11 (climbing form, used for small trees): calculate_cost_impl (bvh2_to_cwbvh.rs:220-344), bottom-up: one thread per BVH2
+// leaf climbs, the second arriver at an inner node computes its record. A climbing thread CARRIES the record of the child it comes from in registers, so only the
 // sibling's record is read back; records of leaves are never stored (they are a function of the leaf node itself and are
 // recomputed by whoever needs them, here and in the emit pass), which halves the pass's DRAM writes.
 constexpr int COST_THREADS = 64;  // small CTAs: a CTA lives as long as its longest climber, and most threads stop after one or two levels
@@ -122,65 +187,7 @@ __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* 
         const Dec L = me_left ? mine : sd, R = me_left ? sd : mine;
         const float ha = box_half_area(node_box(pn));
         const u32 num_primitives = my_prims + sib_prims;
-        Dec d;
-        u32 meta[7];
-        // What child k of a side contributes to S when the parent's decision picks index k for it (get_children,
-        // bvh2_to_cwbvh.rs:346-397): a DISTRIBUTE child is expanded (its own S[k]), anything else is collected as a child
-        // (a wide node counts itself plus everything below it). Computed once with static indices and carried through the
-        // arg-min below, instead of indexing the records with the winning (run-time) indices afterwards.
-        const u32 wideL = (dec_meta_of(L, 0) & 3u) == KIND_INTERNAL ? 1u + L.S[0] : 0u;
-        const u32 wideR = (dec_meta_of(R, 0) & 3u) == KIND_INTERNAL ? 1u + R.S[0] : 0u;
-        u32 effL[7], effR[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            effL[k] = (dec_meta_of(L, k) & 3u) == KIND_DISTRIBUTE ? L.S[k] : wideL;
-            effR[k] = (dec_meta_of(R, k) & 3u) == KIND_DISTRIBUTE ? R.S[k] : wideR;
-        }
-        {  // i = 0
-            float cost_leaf = num_primitives <= max_prims_per_leaf ? ((float)num_primitives * ha) * PRIM_COST : __int_as_float(0x7f800000);
-            float cost_distribute = __int_as_float(0x7f800000);
-            u32 dl = 7, dr = 7, sv = 0;
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                float c = L.cost[k] + R.cost[6 - k];
-                if (c < cost_distribute) {
-                    cost_distribute = c;
-                    dl = k;
-                    dr = 6 - k;
-                    sv = effL[k] + effR[6 - k];
-                }
-            }
-            float cost_internal = cost_distribute + ha;
-            if (cost_leaf < cost_internal) {
-                d.cost[0] = cost_leaf;
-                meta[0] = KIND_LEAF | dl << 2 | dr << 5;
-            } else {
-                d.cost[0] = cost_internal;
-                meta[0] = KIND_INTERNAL | dl << 2 | dr << 5;
-            }
-            d.S[0] = sv;  // 0 while no pair was chosen (dl == dr == 7)
-        }
-#pragma unroll
-        for (int ii = 1; ii < 7; ii++) {
-            float cost_distribute = d.cost[ii - 1];
-            u32 dl = 7, dr = 7, sv = d.S[ii - 1];
-#pragma unroll
-            for (int k = 0; k < ii; k++) {
-                float c = L.cost[k] + R.cost[ii - k - 1];
-                if (c < cost_distribute) {
-                    cost_distribute = c;
-                    dl = k;
-                    dr = ii - k - 1;
-                    sv = effL[k] + effR[ii - k - 1];
-                }
-            }
-            d.cost[ii] = cost_distribute;
-            if (dl != 7) meta[ii] = KIND_DISTRIBUTE | dl << 2 | dr << 5;
-            else meta[ii] = meta[ii - 1];  // decisions[node_i] = decisions[node_i - 1] (and with it the same S)
-            d.S[ii] = sv;
-        }
-        d.meta_lo = meta[0] | meta[1] << 8 | meta[2] << 16 | meta[3] << 24;
-        d.meta_hi = meta[4] | meta[5] << 8 | meta[6] << 16;
+        const Dec d = inner_dec(L, R, ha, num_primitives, max_prims_per_leaf);
         if (node == 0) {
             store_dec(dec, d);
             P[0] = num_primitives;
@@ -190,6 +197,136 @@ __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* 
         my_prims = num_primitives;
         me = node;
         mine_is_leaf = false;
+    }
+}
+
+// K11 (frontier form). The climbing kernel above runs at 5.6 of 32 lanes per issued instruction: every level halves the live
+// lanes of a warp and the survivors of different warps are never packed together. Here a ROUND processes the dense list of
+// nodes whose two children are finished (the frontier); the second arriver at a parent appends it to the next round's list
+// (one global atomic per CTA chunk). Rounds are separated by grid-wide barriers, which also publish the records, so no
+// per-node fences are needed. Round count = height of the tree.
+struct CostArgs {
+    const Node32* nodes;
+    const u32* parents;
+    u32 n_nodes, max_prims_per_leaf;
+    Dec* dec;
+    u32* P;
+    u32* arrivals;
+    u32* queue[2];   // frontier lists, (n_nodes + 1) / 2 entries each
+    u32* qcount;     // [3], slot = round % 3
+};
+constexpr int FRONT_THREADS = 256;
+
+// appends `item` of every thread with `flag` to q (count in *qn): block scan + one atomic per call. Whole CTA must call.
+__device__ __forceinline__ void frontier_push(bool flag, u32 item, u32* q, u32* qn) {
+    __shared__ u32 s_w[FRONT_THREADS / 32];
+    __shared__ u32 s_base;
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_w[w] = __popc(bal);
+    __syncthreads();
+    u32 before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < FRONT_THREADS / 32; k++) {
+        const u32 c = s_w[k];
+        if ((u32)k < w) before += c;
+        total += c;
+    }
+    if (threadIdx.x == 0 && total) s_base = atomicAdd(qn, total);
+    __syncthreads();
+    if (flag) q[s_base + before + __popc(bal & ((1u << lane) - 1u))] = item;
+}
+
+// record of inner node `node` from its two finished children (leaf children are recomputed from their nodes)
+__device__ __forceinline__ void frontier_node(const CostArgs& a, u32 node) {
+    const Node32 me = load_node(a.nodes + node);
+    const u32 first = me.first_index;
+    const Node32 ln = load_node(a.nodes + first), rn = load_node(a.nodes + first + 1);
+    Dec L, R;
+    u32 lp, rp;
+    if (ln.prim_count != 0) {
+        L = leaf_dec(ln);
+        lp = ln.prim_count;
+    } else {
+        L = load_dec_cg(a.dec + first);
+        lp = __ldcg(&a.P[first]);
+    }
+    if (rn.prim_count != 0) {
+        R = leaf_dec(rn);
+        rp = rn.prim_count;
+    } else {
+        R = load_dec_cg(a.dec + first + 1);
+        rp = __ldcg(&a.P[first + 1]);
+    }
+    const u32 num_primitives = lp + rp;
+    store_dec(a.dec + node, inner_dec(L, R, box_half_area(node_box(me)), num_primitives, a.max_prims_per_leaf));
+    a.P[node] = num_primitives;
+}
+
+// Below this many ready nodes a round is cheaper as plain climbing (the rest of the tree is a few thousand nodes, and every
+// further round would cost a grid-wide barrier): each thread takes one ready node and keeps going up while it is the
+// second arriver, publishing with a fence as in cwbvh_cost_kernel.
+constexpr u32 FRONT_CLIMB_BELOW = 32768;
+
+__global__ void __launch_bounds__(FRONT_THREADS) cwbvh_cost_frontier_kernel(CostArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const u32 nthreads = gridDim.x * blockDim.x;
+    // round 0: every leaf arrives at its parent
+    for (u32 base = blockIdx.x * blockDim.x; base < a.n_nodes; base += nthreads) {
+        const u32 i = base + threadIdx.x;
+        bool push = false;
+        u32 p = 0;
+        if (i < a.n_nodes) {
+            const u32 prim_count = __float_as_uint(__ldg(reinterpret_cast<const float4*>(a.nodes + i)).w);
+            if (prim_count != 0) {
+                if (i == 0) {  // a single-leaf tree: the host reads S[0] of the root record
+                    store_dec(a.dec, leaf_dec(load_node(a.nodes)));
+                    a.P[0] = prim_count;
+                } else {
+                    p = a.parents[i];
+                    push = atomicAdd(&a.arrivals[p], 1u) == 1u;
+                }
+            }
+        }
+        frontier_push(push, p, a.queue[0], &a.qcount[1]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[2] = 0;
+    grid.sync();
+    for (u32 round = 1;; round++) {
+        const u32* q = a.queue[(round - 1) & 1];
+        u32* qnext = a.queue[round & 1];
+        const u32 n = __ldcg(&a.qcount[round % 3]);
+        if (n == 0) break;
+        if (n < FRONT_CLIMB_BELOW) {
+            for (u32 idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += nthreads) {
+                u32 node = __ldcg(q + idx);
+                for (;;) {
+                    frontier_node(a, node);
+                    if (node == 0) break;
+                    __threadfence();
+                    node = a.parents[node];
+                    if (atomicAdd(&a.arrivals[node], 1u) == 0) break;  // the other child's thread will do this node
+                }
+            }
+            break;
+        }
+        u32* qn_next = &a.qcount[(round + 1) % 3];
+        for (u32 base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
+            const u32 idx = base + threadIdx.x;
+            bool push = false;
+            u32 p = 0;
+            if (idx < n) {
+                const u32 node = __ldcg(q + idx);
+                frontier_node(a, node);
+                if (node != 0) {
+                    p = a.parents[node];
+                    push = atomicAdd(&a.arrivals[p], 1u) == 1u;
+                }
+            }
+            frontier_push(push, p, qnext, qn_next);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[(round + 2) % 3] = 0;  // the slot of round + 2; nobody reads or writes it now
+        grid.sync();
     }
 }
 
@@ -617,8 +754,27 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, root_box.alloc(8, s));
     CU_TRY(ctx, cudaMemsetAsync(arrivals.p, 0, (size_t)n_nodes * 4, s));
     CU_TRY(ctx, cudaMemsetAsync(g.p, 0, sizeof(CwGlobals), s));
-    cwbvh_cost_kernel<<<div_up(n_nodes, COST_THREADS), COST_THREADS, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
-    KERNEL_CHECK(ctx);
+    // small trees: the frontier kernel would switch to climbing after its first round anyway, and a plain launch is cheaper
+    // than a cooperative one (kitchen, 114 k nodes: 0.11 vs 0.14 ms)
+    if (n_nodes < 8 * FRONT_CLIMB_BELOW) {
+        cwbvh_cost_kernel<<<div_up(n_nodes, COST_THREADS), COST_THREADS, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
+        KERNEL_CHECK(ctx);
+    } else {
+        DevBuf<u32> q0, q1, qcount;
+        CU_TRY(ctx, q0.alloc((size_t)n_nodes / 2 + 1, s));
+        CU_TRY(ctx, q1.alloc((size_t)n_nodes / 2 + 1, s));
+        CU_TRY(ctx, qcount.alloc(4, s));
+        CU_TRY(ctx, cudaMemsetAsync(qcount.p, 0, 16, s));
+        CostArgs ca;
+        ca.nodes = bvh->nodes; ca.parents = parents; ca.n_nodes = n_nodes; ca.max_prims_per_leaf = max_prims_per_leaf;
+        ca.dec = dec.p; ca.P = P.p; ca.arrivals = arrivals.p; ca.queue[0] = q0.p; ca.queue[1] = q1.p; ca.qcount = qcount.p;
+        int per_sm = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_cost_frontier_kernel, FRONT_THREADS, 0));
+        const int blocks = std::min(std::max(1, per_sm) * ctx->sm_count, std::max(1, div_up(n_nodes, FRONT_THREADS)));
+        void* args[] = {&ca};
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)cwbvh_cost_frontier_kernel, dim3(blocks), dim3(FRONT_THREADS), args, 0, s));
+        KERNEL_CHECK(ctx);
+    }
     root_aabb_kernel<<<1, 1, 0, s>>>(bvh->nodes, root_box.p);
     KERNEL_CHECK(ctx);
     u32* h = reinterpret_cast<u32*>(ctx->pinned);
