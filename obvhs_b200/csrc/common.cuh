@@ -137,7 +137,7 @@ struct ObvhsContext {
     // host-batch pipeline (traverse_common): copy-in / copy-out streams beside `stream`, and a pool of timing-free events
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> event_pool;
-    int traverse_mode = 2, traverse_refill = 8, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
+    int traverse_mode = 2, traverse_refill = 4, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
 };
 

@@ -14,6 +14,13 @@
 // reference's StackStack<UVec2, 32> (saturating push).
 #include "common.cuh"
 
+#ifndef OBVHS_STATIC_ONE_TRI
+#define OBVHS_STATIC_ONE_TRI false
+#endif
+#ifndef OBVHS_PERSISTENT_ONE_TRI
+#define OBVHS_PERSISTENT_ONE_TRI true
+#endif
+
 namespace {
 
 constexpr float NODE_EPSILON = 0.0001f;  // cwbvh/node.rs:82 / simd.rs:83
@@ -216,9 +223,13 @@ struct CwTree {
     // pending work (cwbvh/mod.rs:216-220 returns there) and the state machine runs out on its own. An early `break`/`goto`
     // out of the primitive loop made ptxas (12.9, sm_100a) share convergence-barrier registers between the primitive loop
     // and the node test, and the persistent kernel then dead-locked on scenes where lanes of one warp sat in both at once.
-    template <int MODE, bool COUNT>
+    // ONE_TRI: at most one triangle per call, and no node test while triangles of the current group are pending. The per-ray
+    // sequence of tests is unchanged (a ray still drains its group before its next node), only the interleaving with the other
+    // lanes of the warp differs: in an incoherent warp the `while` form makes all lanes wait for the lane with the most
+    // triangles before every node test.
+    template <int MODE, bool COUNT, bool ONE_TRI = false>
     __device__ __forceinline__ bool step(State& st, uint2* __restrict__ stack, u32& nodes_visited, u32& tris_tested) const {
-        while (st.prim.y != 0) {  // traverse_macro.rs:64-72
+        for (bool first = true; st.prim.y != 0 && (!ONE_TRI || first); first = false) {  // traverse_macro.rs:64-72
             u32 local = 31u - __clz(st.prim.y);
             st.prim.y &= ~(1u << local);
             u32 pid = st.prim.x + local;
@@ -241,6 +252,8 @@ struct CwTree {
                 if (t < __int_as_float(0x7f800000)) st.o.count++;
             }
         }
+        bool done = false;
+        if (!ONE_TRI || st.prim.y == 0) {  // (ONE_TRI: triangles of this group still pending -> next call)
         st.prim = make_uint2(0u, 0u);
         if (st.cur.y & 0xff000000u) {  // traverse_macro.rs:76-103
             u32 hits_imask = st.cur.y;
@@ -265,11 +278,14 @@ struct CwTree {
             st.cur = make_uint2(0u, 0u);
         }
         if (st.prim.y == 0 && (st.cur.y & 0xff000000u) == 0) {  // traverse_macro.rs:112-123
-            if (st.sp == 0) return true;
-            st.sp--;
-            st.cur = stack[st.sp];
+            if (st.sp == 0) done = true;
+            else {
+                st.sp--;
+                st.cur = stack[st.sp];
+            }
         }
-        return false;
+        }
+        return done;
     }
 };
 
@@ -333,7 +349,7 @@ struct Bvh2Tree {
         return go_on;
     }
     // one iteration of ray_traverse_dynamic's loop (:284-331); the first call performs the root test (:273-282)
-    template <int MODE, bool COUNT>
+    template <int MODE, bool COUNT, bool ONE_TRI = false>
     __device__ __forceinline__ bool step(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
         bool done = false;
         if (st.cur == AT_ROOT) {
@@ -418,7 +434,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const fl
         typename Tree::State st;
         typename Tree::StackT stack[Tree::STACK];
         tree.begin(st, rays + i * 4);
-        while (!tree.template step<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
+        while (!tree.template step<MODE, COUNT, OBVHS_STATIC_ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
         }
         result_store<MODE>(st.o, out, i);
     }
@@ -435,6 +451,7 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
                                                                   unsigned long long* __restrict__ counters, u32* __restrict__ next_ray, u32 chunk,
                                                                   const u32* __restrict__ probe) {
     if (probe && probe_says_coherent(probe)) return;  // auto mode: the one-ray-per-thread kernel handles this batch
+    constexpr bool ONE_TRI = OBVHS_PERSISTENT_ONE_TRI;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
     u32 nodes_visited = 0, tris_tested = 0;
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
         if (!__any_sync(0xffffffffu, active)) break;
         const u32 min_active = (exhausted && chunk_pos == chunk_end) ? 1u : (u32)(33 - REFILL);
         do {
-            if (active && tree.template step<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
+            if (active && tree.template step<MODE, COUNT, ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
                 result_store<MODE>(st.o, out, my);
                 active = false;
             }
