@@ -579,13 +579,18 @@ static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays
 
 // Kernel choice shared by both tree types. ctx->traverse_mode: 0 static (one ray per thread), 1 persistent refill, 2 auto
 // (a probe of the batch decides on the device; small batches are static).
+constexpr size_t AUTO_STATIC_MAX_PRIMS = 262144;
 template <class Tree>
-static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, const float4* rays, size_t n, int mode,
-                             void* d_out, u64* d_counters) {
+static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, size_t prim_count, const float4* rays, size_t n,
+                             int mode, void* d_out, u64* d_counters) {
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
     int tm = ctx->traverse_mode;
     if (tm == 2 && n < 16384) tm = 0;
+    // Large scenes: even camera rays vary a lot in work per ray (depth complexity, cache misses), and the refill kernel wins
+    // regardless of coherence (terrain, jittered primary rays: +3 % at 0.3 M triangles, +16 % at 1 M, +41 % at 3 M, +36 % at
+    // 10 M; the 57 k-triangle kitchen is 41 % faster one-ray-per-thread). The probe only decides for small scenes.
+    if (tm == 2 && prim_count > AUTO_STATIC_MAX_PRIMS) tm = 1;
     // 32-bit ray indices inside the persistent kernel: batches beyond 2^31 rays are split into several launches
     const size_t MAX_LAUNCH = (size_t)1 << 31;
     const size_t out_elem = mode == 0 ? sizeof(ObvhsRayHit) : (mode == 1 ? 1 : 4);
@@ -628,7 +633,7 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
     tree.tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
     tree.root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
     tree.magic = 0x4B000000u;
-    return traverse_dispatch(ctx, tree, bvh->total_aabb, reinterpret_cast<const float4*>(d_rays), n, mode, d_out, d_counters);
+    return traverse_dispatch(ctx, tree, bvh->total_aabb, bvh->prim_count, reinterpret_cast<const float4*>(d_rays), n, mode, d_out, d_counters);
 }
 
 int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters) {
@@ -641,11 +646,11 @@ int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     if (bvh->max_depth <= 96) {  // fast_stack!(u32, (96, 192), self.max_depth, ...) bvh2/mod.rs:166
         Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
-        return traverse_dispatch(ctx, tree, unknown, rays, n, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, mode, d_out, d_counters);
     }
     if (bvh->max_depth <= 192) {
         Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
-        return traverse_dispatch(ctx, tree, unknown, rays, n, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, mode, d_out, d_counters);
     }
     OBVHS_SET_ERR(ctx, "Bvh2 traversal: max_depth %zu > 192 needs the reference's heap stack -- not supported", bvh->max_depth);
     return OBVHS_ERR_UNSUPPORTED;
