@@ -155,8 +155,19 @@ struct ResolveArgs {
 // K10, one cooperative launch per round: conflict cells -> greedy-MIS resolution by deterministic reservations ->
 // apply -> dirty-path marking -> bottom-up refit. Phases are separated by grid-wide barriers; no host round trips.
 constexpr int RESOLVE_THREADS = 1024;  // few, fat blocks: a grid-wide barrier costs more the more blocks take part
+// SINGLE: the whole round fits one CTA (a few thousand entries): the phases are separated by __syncthreads instead of
+// grid-wide barriers (about 2 us each; a round has ~20 of them, which was the entire 40 us of a kitchen-sized round).
+struct PhaseBarrier {
+    cg::grid_group grid;
+    bool single;
+    __device__ __forceinline__ void sync() {
+        if (single) __syncthreads();
+        else grid.sync();
+    }
+};
+template <bool SINGLE>
 __global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel(ResolveArgs a) {
-    cg::grid_group grid = cg::this_grid();
+    PhaseBarrier grid{cg::this_grid(), SINGLE};
     const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     ReinsertState* st = a.st;
     if (tid == 0) st->undecided[0] = st->undecided[1] = st->undecided[2] = 0;
@@ -335,7 +346,7 @@ struct ReinsertRun {
         CU_TRY(ctx, cudaMemsetAsync(pending.p, 0, len * 4, s));
         CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
         CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel, RESOLVE_THREADS, 0));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel<false>, RESOLVE_THREADS, 0));
         coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
         return OBVHS_OK;
     }
@@ -355,8 +366,12 @@ struct ReinsertRun {
         ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
         ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
         void* args[] = {&ra};
-        int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
-        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
+        if (count <= 4 * RESOLVE_THREADS) {  // one CTA, block-level barriers, a plain launch
+            reinsert_resolve_apply_kernel<true><<<1, RESOLVE_THREADS, 0, s>>>(ra);
+        } else {
+            int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
+            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel<false>, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
+        }
         KERNEL_CHECK(ctx);
         return OBVHS_OK;
     }
