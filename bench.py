@@ -402,7 +402,8 @@ def run_ours(args):
             "build": {"value": build_mtris, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count},
             "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                         "kernel": "traverse_kernel<closest>", "peak_source": peak_src,
+                         "kernel": ("traverse_persistent_kernel<CwTree, closest>" if n_tris > 262144 or args.workload in ("soup", "bounce")
+                                    else "traverse_kernel<CwTree, closest>"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "nodes_visited": nodes_visited, "tris_tested": tris_tested,
                          "note": "B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); kitchen tree+tris fit in L2, "
                                  "so a fraction near or above 1 means L2-served reuse, not DRAM streaming"},

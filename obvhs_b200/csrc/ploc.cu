@@ -11,6 +11,8 @@
 //                             (kept/parent outputs, merges) + scatter                             ploc/mod.rs:420-487
 // Node order, child slots (allocated from the END of bvh.nodes in sweep order) and AABB bits equal the sequential
 // reference sweep exactly.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -38,6 +40,7 @@ struct PlocGlobals {
     PlocState state[2];
     u32 ticket;
     u32 pad2;
+    u32 mid_depth, mid_parity;  // written by ploc_mid_kernel: iterations done so far / parity of the live state
 };
 
 __global__ void ploc_globals_init_kernel(PlocGlobals* g, u32 n) {
@@ -298,25 +301,20 @@ __device__ __forceinline__ u32 child_slot(const u32* __restrict__ free_slots, u3
     return free_slots ? free_slots[(insert_start - insert_base) / 2 + mi] : insert_base - 2 * (mi + 1);
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32* __restrict__ cur, Node32* __restrict__ next,
-                                                                   Node32* __restrict__ bvh_nodes, const signed char* __restrict__ merge,
-                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket,
-                                                                   const u32* __restrict__ free_slots, u32 insert_start) {
+// One tile of the merge sweep. CG: the inputs were written earlier in the SAME launch by other CTAs (ploc_mid_kernel), so
+// they are read through L2 (ld.global.cg) instead of the non-coherent L1.
+template <bool CG>
+__device__ __forceinline__ void ploc_merge_tile(const Node32* cur, Node32* next, Node32* bvh_nodes, const signed char* merge, PlocGlobals* g,
+                                                int parity, u32 count, u32 insert_base, u32 tile, u64* scan_status,
+                                                const u32* __restrict__ free_slots, u32 insert_start) {
     __shared__ signed char sm[MERGE_TILE + 2 * MERGE_HALO];
     __shared__ u64 s_wsum[MERGE_THREADS / 32];
     __shared__ u64 s_excl;
-    __shared__ u32 s_tile;
-    const u32 count = g->state[parity].count;
-    const u32 insert_base = g->state[parity].insert_index;
     const u32 tiles = (count + MERGE_TILE - 1) / MERGE_TILE;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    if (tile >= tiles) return;
     const u32 tile0 = tile * MERGE_TILE;
     for (int j = threadIdx.x; j < MERGE_TILE + 2 * MERGE_HALO; j += MERGE_THREADS) {
         long long gi = (long long)tile0 - MERGE_HALO + j;
-        sm[j] = (gi >= 0 && gi < (long long)count) ? merge[gi] : (signed char)0;
+        sm[j] = (gi >= 0 && gi < (long long)count) ? (CG ? __ldcg(merge + gi) : merge[gi]) : (signed char)0;
     }
     __syncthreads();
     u32 flags = 0;  // per item: bit0 = writes an output, bit1 = emits a parent
@@ -399,11 +397,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
         if (f & 1u) {
             u32 i = tile0 + threadIdx.x * MERGE_ITEMS + k;
             u32 pos = (u32)(run & 0x7fffffffull);
-            Node32 left = load_node(cur + i);
+            Node32 left = CG ? load_node_cg(cur + i) : load_node(cur + i);
             if (f & 2u) {
                 u32 mi = (u32)(run >> 31);
                 int m = sm[threadIdx.x * MERGE_ITEMS + k + MERGE_HALO];
-                Node32 right = load_node(cur + (i + m));
+                Node32 right = CG ? load_node_cg(cur + (i + m)) : load_node(cur + (i + m));
                 u32 slot = child_slot(free_slots, insert_start, insert_base, mi);
                 store_node(bvh_nodes + slot, left);
                 store_node(bvh_nodes + slot + 1, right);
@@ -415,12 +413,80 @@ __global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32*
             }
         }
     }
+    __syncthreads();  // the shared arrays are reused by the caller's next tile
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32* __restrict__ cur, Node32* __restrict__ next,
+                                                                   Node32* __restrict__ bvh_nodes, const signed char* __restrict__ merge,
+                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket,
+                                                                   const u32* __restrict__ free_slots, u32 insert_start) {
+    __shared__ u32 s_tile;
+    const u32 count = g->state[parity].count;
+    const u32 insert_base = g->state[parity].insert_index;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= (count + MERGE_TILE - 1) / MERGE_TILE) return;
+    ploc_merge_tile<false>(cur, next, bvh_nodes, merge, g, parity, count, insert_base, tile, scan_status, free_slots, insert_start);
+}
+
+// Iterations between "too small to be worth a launch + a host round trip each" and the single-CTA tail: ONE cooperative
+// launch loops search -> grid barrier -> merge -> grid barrier until at most PLOC_TAIL clusters are left. Tiles are dealt
+// round-robin (tile t to CTA t % gridDim.x), so the merge scan's look-back only ever waits for CTAs that are running.
+// The window is loaded with plain L2 loads (the clusters were written by other CTAs of this launch).
+// g->state[2] receives {count, insert_index} bookkeeping as usual; g->mid_depth / mid_parity report where the loop stopped.
+constexpr int PLOC_TAIL = 2048;  // clusters the single-CTA tail kernel takes over at
+constexpr u32 PLOC_MID_MAX = 262144;
+template <int R>
+__global__ void __launch_bounds__(SEARCH_TILE) ploc_mid_kernel(Node32* bufA, Node32* bufB, Node32* bvh_nodes, signed char* merge, PlocGlobals* g,
+                                                              int parity, u32 depth, u32 search_depth_threshold, u64* scan_status,
+                                                              const u32* __restrict__ free_slots, u32 insert_start) {
+    static_assert(SEARCH_TILE == MERGE_THREADS, "one block size for both phases");
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ __align__(16) Node32 win[SEARCH_TILE + 2 * R];
+    Node32 *cur = bufA, *next = bufB;  // the caller passes them in the order of `parity`
+    for (;;) {
+        const u32 count = __ldcg(&g->state[parity].count);
+        const u32 insert_base = __ldcg(&g->state[parity].insert_index);
+        if (count <= PLOC_TAIL) break;
+        const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
+        // ---- search
+        const u32 stiles = (count + SEARCH_TILE - 1) / SEARCH_TILE;
+        for (u32 tile = blockIdx.x; tile < stiles; tile += gridDim.x) {
+            const u32 tile0 = tile * SEARCH_TILE;
+            const u32 lo = tile0 >= (u32)R ? tile0 - R : 0u;
+            const u32 hi = min(count, tile0 + SEARCH_TILE + R);
+            for (u32 j = threadIdx.x; j < (hi - lo) * 2; j += SEARCH_TILE)
+                reinterpret_cast<float4*>(win)[j] = __ldcg(reinterpret_cast<const float4*>(cur + lo) + j);
+            __syncthreads();
+            const u32 i = tile0 + threadIdx.x;
+            if (i < count) merge[i] = (signed char)search_offset<R>(win, (int)(i - lo), i, count, r1);
+            __syncthreads();
+        }
+        const u32 mtiles = (count + MERGE_TILE - 1) / MERGE_TILE;
+        for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < mtiles; t += gridDim.x * blockDim.x) scan_status[t] = 0;
+        grid.sync();
+        // ---- merge
+        for (u32 tile = blockIdx.x; tile < mtiles; tile += gridDim.x)
+            ploc_merge_tile<true>(cur, next, bvh_nodes, merge, g, parity, count, insert_base, tile, scan_status, free_slots, insert_start);
+        grid.sync();
+        Node32* tmp = cur;
+        cur = next;
+        next = tmp;
+        parity ^= 1;
+        depth++;
+        if (__ldcg(&g->state[parity].count) >= count) break;  // no progress (non-finite boxes): the host reports it
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        g->mid_depth = depth;
+        g->mid_parity = (u32)parity;
+    }
 }
 
 // The last iterations (count <= PLOC_TAIL) in ONE CTA: clusters live in shared memory, each iteration is search ->
 // flags -> block scan -> scatter, separated by __syncthreads instead of kernel launches and host round trips. Same
 // arithmetic, same slots as K5/K6. Ends with bvh.nodes[0] = the last cluster (ploc/mod.rs:499).
-constexpr int PLOC_TAIL = 2048, TAIL_THREADS = 1024, TAIL_ITEMS = PLOC_TAIL / TAIL_THREADS;
+constexpr int TAIL_THREADS = 1024, TAIL_ITEMS = PLOC_TAIL / TAIL_THREADS;
 template <int R>
 __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* __restrict__ cur_g, Node32* __restrict__ bvh_nodes, PlocGlobals* g,
                                                                  int parity, u32 depth, u32 search_depth_threshold,
@@ -520,6 +586,21 @@ template <int R>
 void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGlobals* g, int parity, int r1, signed char* merge,
                    u64* scan_status, u32* ticket) {
     ploc_search_kernel<R><<<div_up(count, SEARCH_TILE), SEARCH_TILE, 0, ctx->stream>>>(cur, g, parity, r1, merge, scan_status, ticket);
+}
+
+template <int R>
+cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, Node32* bvh_nodes, signed char* merge, PlocGlobals* g, int parity,
+                       u32 depth, u32 thr, u64* scan_status, const u32* free_slots, u32 insert_start) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_mid_kernel<R>, SEARCH_TILE, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    // as few CTAs as the work needs: the cost of a grid-wide barrier grows with the number of participants
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, SEARCH_TILE)));
+    void* args[] = {&cur, &next, &bvh_nodes, &merge, &g, &parity, &depth, &thr, &scan_status, &free_slots, &insert_start};
+    return cudaLaunchCooperativeKernel((void*)ploc_mid_kernel<R>, dim3(blocks), dim3(SEARCH_TILE), args, 0, ctx->stream);
 }
 
 template <int R>
@@ -682,6 +763,39 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
     bool nan_checked = !check_nan;
     while (count > PLOC_TAIL) {
         const int parity = (int)(depth & 1);
+        if (count <= PLOC_MID_MAX) {
+            // every remaining iteration above the tail size in one cooperative launch (no launches / host round trips per iteration)
+            const u32 thr32 = (u32)std::min<size_t>(search_depth_threshold, 0xffffffffu);
+            cudaError_t e;
+            switch (search_distance) {
+                case 1: e = launch_mid<1>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                case 2: e = launch_mid<2>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                case 6: e = launch_mid<6>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                case 14: e = launch_mid<14>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                case 24: e = launch_mid<24>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                default: e = launch_mid<32>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+            }
+            ctx->launches++;
+            CU_TRY(ctx, e);
+            CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[0], 2 * sizeof(PlocState), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaMemcpyAsync(h_state + 6, &g.p->mid_depth, 8, cudaMemcpyDeviceToHost, s));
+            if (!nan_checked) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaStreamSynchronize(s));
+            if (!nan_checked && h_state[4]) {
+                OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
+                return OBVHS_ERR_NAN_INPUT;
+            }
+            nan_checked = true;
+            const u32 new_depth = h_state[6], new_parity = h_state[7], new_count = h_state[2 * new_parity];
+            if (new_count > PLOC_TAIL) {  // the kernel only stops early when an iteration made no progress
+                OBVHS_SET_ERR(ctx, "PLOC made no progress (%u clusters left); non-finite AABBs?", new_count);
+                return OBVHS_ERR_NAN_INPUT;
+            }
+            if (((new_depth - (u32)depth) & 1u) != 0) std::swap(cur, next);
+            depth = new_depth;
+            count = new_count;
+            break;
+        }
         const int r1 = (search_distance == 1 || depth < search_depth_threshold) ? 1 : 0;
         u32* ticket = &g.p->ticket;
         switch (search_distance) {
