@@ -202,19 +202,22 @@ __global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_k
     }
 }
 
-// ---- single-block sort for small inputs: every pass of the same stable LSD scheme inside one CTA, data in shared memory
-constexpr int BS_THREADS = 1024, BS_WARPS = BS_THREADS / 32;
-template <typename K>
+// ---- single-block sort for small inputs: every pass of the same stable LSD scheme inside one CTA, data in shared memory.
+// THREADS is chosen by the input size (256 / 512 / 1024): the per-pass fixed costs (histogram zeroing, the scan over the warps'
+// counters, the barriers) grow with the number of warps, and most reinsertion rounds of a small scene sort < 2048 pairs.
+template <typename K, int THREADS>
 struct BlockSortCfg {
     static constexpr int ITEMS = sizeof(K) == 8 ? 4 : 8;
-    static constexpr int MAX_N = BS_THREADS * ITEMS;
-    static constexpr size_t SMEM = (size_t)MAX_N * (sizeof(K) + 4) * 2 + (size_t)(BS_WARPS * 256 + 256) * 4;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int MAX_N = THREADS * ITEMS;
+    static constexpr size_t SMEM = (size_t)MAX_N * (sizeof(K) + 4) * 2 + (size_t)(WARPS * 256 + 256) * 4;
 };
 
-template <typename K>
-__global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
-                                                               u32* __restrict__ vout, u32 n, int passes) {
-    constexpr int ITEMS = BlockSortCfg<K>::ITEMS, MAX_N = BlockSortCfg<K>::MAX_N;
+template <typename K, int THREADS>
+__global__ void __launch_bounds__(THREADS) block_sort_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
+                                                            u32* __restrict__ vout, u32 n, int passes) {
+    using Cfg = BlockSortCfg<K, THREADS>;
+    constexpr int ITEMS = Cfg::ITEMS, MAX_N = Cfg::MAX_N, BS_WARPS = Cfg::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* kbuf[2] = {reinterpret_cast<K*>(smem_raw), reinterpret_cast<K*>(smem_raw) + MAX_N};
     u32* vbuf[2] = {reinterpret_cast<u32*>(kbuf[1] + MAX_N), reinterpret_cast<u32*>(kbuf[1] + MAX_N) + MAX_N};
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
     u32* dstart = whist + BS_WARPS * 256;    // [256]
     __shared__ u32 s_wsum[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int j = tid; j < MAX_N; j += BS_THREADS) {
+    for (int j = tid; j < MAX_N; j += THREADS) {
         bool ok = (u32)j < n;
         kbuf[0][j] = ok ? kin[j] : (K)~(K)0;  // padding sorts behind every valid key and stays there (stable)
         vbuf[0][j] = ok ? vin[j] : 0u;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
     u32* mywh = whist + warp * 256;
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
-        for (int j = tid; j < BS_WARPS * 256; j += BS_THREADS) whist[j] = 0;
+        for (int j = tid; j < BS_WARPS * 256; j += THREADS) whist[j] = 0;
         __syncthreads();
         K key[ITEMS];
         u32 val[ITEMS], rank[ITEMS];
@@ -250,26 +253,30 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
             __syncwarp();
         }
         __syncthreads();
-        u32 run = 0, x = 0;
-        if (tid < 256) {
-            for (int k = 0; k < BS_WARPS; k++) {
-                u32 c = whist[k * 256 + tid];
-                whist[k * 256 + tid] = run;
-                run += c;
-            }
-            x = run;
+        // digit d = tid (256 digits; with 256 threads every thread owns one): exclusive scan across warps, then across digits
+        for (int d0 = 0; d0 < 256; d0 += THREADS) {
+            const int d = d0 + tid;
+            u32 run = 0, x = 0;
+            if (d < 256) {
+                for (int k = 0; k < BS_WARPS; k++) {
+                    u32 c = whist[k * 256 + d];
+                    whist[k * 256 + d] = run;
+                    run += c;
+                }
+                x = run;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                if (lane == 31) s_wsum[d >> 5] = x;
             }
-            if (lane == 31) s_wsum[warp] = x;
-        }
-        __syncthreads();
-        if (tid < 256) {
-            u32 wbase = 0;
-            for (int k = 0; k < warp; k++) wbase += s_wsum[k];
-            dstart[tid] = wbase + x - run;
+            __syncthreads();
+            if (d < 256) {
+                u32 wbase = 0;
+                for (int k = 0; k < (d >> 5); k++) wbase += s_wsum[k];
+                dstart[d] = wbase + x - run;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -282,10 +289,23 @@ __global__ void __launch_bounds__(BS_THREADS) block_sort_kernel(const K* __restr
         __syncthreads();
         src ^= 1;
     }
-    for (u32 j = tid; j < n; j += BS_THREADS) {
+    for (u32 j = tid; j < n; j += THREADS) {
         kout[j] = kbuf[src][j];
         vout[j] = vbuf[src][j];
     }
+}
+
+template <typename K, int THREADS>
+static int launch_block_sort(ObvhsContext* ctx, const K* keys, const u32* vals, K* keys_alt, u32* vals_alt, u32 n, int passes) {
+    using Cfg = BlockSortCfg<K, THREADS>;
+    static bool attr = false;
+    if (!attr) {
+        CU_TRY(ctx, cudaFuncSetAttribute(block_sort_kernel<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr = true;
+    }
+    block_sort_kernel<K, THREADS><<<1, THREADS, Cfg::SMEM, ctx->stream>>>(keys, vals, keys_alt, vals_alt, n, passes);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
 }
 
 template <typename K>
@@ -303,15 +323,10 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
         OBVHS_SET_ERR(ctx, "radix sort: unsupported size n=%zu passes=%d", n, passes);
         return OBVHS_ERR_UNSUPPORTED;
     }
-    if (n <= (size_t)BlockSortCfg<K>::MAX_N) {  // one launch, no scratch
-        static bool bs_attr[2] = {false, false};
-        const int w = sizeof(K) == 8 ? 1 : 0;
-        if (!bs_attr[w]) {
-            CU_TRY(ctx, cudaFuncSetAttribute(block_sort_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BlockSortCfg<K>::SMEM));
-            bs_attr[w] = true;
-        }
-        block_sort_kernel<K><<<1, BS_THREADS, BlockSortCfg<K>::SMEM, ctx->stream>>>(keys, vals, keys_alt, vals_alt, (u32)n, passes);
-        KERNEL_CHECK(ctx);
+    if (n <= (size_t)BlockSortCfg<K, 1024>::MAX_N) {  // one launch, no scratch
+        if (n <= (size_t)BlockSortCfg<K, 256>::MAX_N) ST_TRY((launch_block_sort<K, 256>(ctx, keys, vals, keys_alt, vals_alt, (u32)n, passes)));
+        else if (n <= (size_t)BlockSortCfg<K, 512>::MAX_N) ST_TRY((launch_block_sort<K, 512>(ctx, keys, vals, keys_alt, vals_alt, (u32)n, passes)));
+        else ST_TRY((launch_block_sort<K, 1024>(ctx, keys, vals, keys_alt, vals_alt, (u32)n, passes)));
         *sorted_keys = keys_alt;
         *sorted_vals = vals_alt;
         return OBVHS_OK;
