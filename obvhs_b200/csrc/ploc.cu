@@ -492,30 +492,32 @@ __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* _
                                                                  int parity, u32 depth, u32 search_depth_threshold,
                                                                  const u32* __restrict__ free_slots, u32 insert_start) {
     extern __shared__ __align__(128) unsigned char tail_smem[];
-    Node32* buf[2] = {reinterpret_cast<Node32*>(tail_smem), reinterpret_cast<Node32*>(tail_smem) + PLOC_TAIL};
+    // (both buffers are addressed off the shared array itself, not through a pointer table, so the accesses compile to LDS/STS)
+    Node32* const base = reinterpret_cast<Node32*>(tail_smem);
     __shared__ signed char sm[PLOC_TAIL];
     __shared__ u32 s_wsum[TAIL_THREADS / 32];
     u32 count = g->state[parity].count;
     u32 insert = g->state[parity].insert_index;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (u32 j = tid; j < count * 2; j += TAIL_THREADS) reinterpret_cast<float4*>(buf[0])[j] = __ldg(reinterpret_cast<const float4*>(cur_g) + j);
+    for (u32 j = tid; j < count * 2; j += TAIL_THREADS) reinterpret_cast<float4*>(base)[j] = __ldg(reinterpret_cast<const float4*>(cur_g) + j);
     int src = 0;
     __syncthreads();
-    while (count > 1) {
-        const Node32* cur = buf[src];
-        Node32* next = buf[src ^ 1];
+    while (count > 32) {  // (the last iterations, a few dozen of them with a handful of clusters each, run in one warp below)
+        const Node32* cur = base + (src ? PLOC_TAIL : 0);
+        Node32* next = base + (src ? 0 : PLOC_TAIL);
         const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
+        const int ipt = count > (u32)TAIL_THREADS ? TAIL_ITEMS : 1;  // one cluster per thread as soon as they fit
 #pragma unroll
         for (int k = 0; k < TAIL_ITEMS; k++) {
-            u32 i = tid * TAIL_ITEMS + k;
-            if (i < count) sm[i] = (signed char)search_offset<R>(cur, (int)i, i, count, r1);
+            u32 i = tid * ipt + k;
+            if (k < ipt && i < count) sm[i] = (signed char)search_offset<R>(cur, (int)i, i, count, r1);
         }
         __syncthreads();
         u32 flags = 0, local = 0;  // packed: outputs in the low 16 bits, merges in the high 16
 #pragma unroll
         for (int k = 0; k < TAIL_ITEMS; k++) {
-            u32 i = tid * TAIL_ITEMS + k;
-            if (i < count) {
+            u32 i = tid * ipt + k;
+            if (k < ipt && i < count) {
                 int m = sm[i];
                 int mb = sm[(int)i + m];
                 bool mutual = (m + mb) == 0;
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* _
         for (int k = 0; k < TAIL_ITEMS; k++) {
             u32 f = (flags >> (2 * k)) & 3u;
             if (f & 1u) {
-                u32 i = tid * TAIL_ITEMS + k;
+                u32 i = tid * ipt + k;
                 u32 pos = run & 0xffffu;
                 Node32 left = cur[i];
                 if (f & 2u) {
@@ -569,7 +571,49 @@ __global__ void __launch_bounds__(TAIL_THREADS) ploc_tail_kernel(const Node32* _
         src ^= 1;
         depth++;
     }
-    if (tid < 2) reinterpret_cast<float4*>(bvh_nodes)[tid] = reinterpret_cast<const float4*>(buf[src])[tid];  // ploc/mod.rs:499
+    // At most 32 clusters: one warp, one cluster per lane, warp barriers and ballots instead of block barriers and scans.
+    if (w == 0) {
+        const u32 lt = (1u << lane) - 1u;
+        while (count > 1 && count <= 32) {
+            const Node32* cur = base + (src ? PLOC_TAIL : 0);
+            Node32* next = base + (src ? 0 : PLOC_TAIL);
+            const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
+            const bool have = (u32)lane < count;
+            if (have) sm[lane] = (signed char)search_offset<R>(cur, lane, (u32)lane, count, r1);
+            __syncwarp();
+            bool outp = false, emits = false;
+            int m = 0;
+            if (have) {
+                m = sm[lane];
+                const int mb = sm[lane + m];
+                const bool mutual = (m + mb) == 0;
+                emits = mutual && m < 0;
+                outp = !mutual || emits;
+            }
+            const u32 out_mask = __ballot_sync(0xffffffffu, outp), emit_mask = __ballot_sync(0xffffffffu, emits);
+            if (outp) {
+                const u32 pos = __popc(out_mask & lt);
+                const Node32 left = cur[lane];
+                if (emits) {
+                    const Node32 right = cur[lane + m];
+                    const u32 slot = child_slot(free_slots, insert_start, insert, (u32)__popc(emit_mask & lt));
+                    store_node(bvh_nodes + slot, left);
+                    store_node(bvh_nodes + slot + 1, right);
+                    next[pos] = make_node32(box_union(node_box(left), node_box(right)), 0u, slot);
+                } else {
+                    next[pos] = left;
+                }
+            }
+            __syncwarp();
+            const u32 outs = (u32)__popc(out_mask);
+            if (outs >= count) break;  // no progress
+            count = outs;
+            insert -= 2 * (u32)__popc(emit_mask);
+            src ^= 1;
+            depth++;
+        }
+    }
+    if (tid < 2) reinterpret_cast<float4*>(bvh_nodes)[tid] = reinterpret_cast<const float4*>(base + (src ? PLOC_TAIL : 0))[tid];  // ploc/mod.rs:499
     if (tid == 0) {
         g->state[0].count = count;
         g->state[0].insert_index = insert;
