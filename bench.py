@@ -587,13 +587,204 @@ def run_dynamic(args):
         dist.destroy_process_group()
 
 
+def run_demoscene(args):
+    """--workload demoscene: BASELINE.json configs[2] (examples/demoscene.rs): demoscene(1280, 570) = 3,276,800 triangles,
+    medium_build, through BOTH tree types: build_bvh2_from_tris + Bvh2 traversal (what the example renders with) and
+    build_cwbvh_from_tris + CwBvh traversal. Rays: the jittered / depth-of-field primary set of AA sample 0 (closest hit) and the
+    sun shadow ray leaving every primary hit (`ray_traverse_miss`, demoscene.rs:185-193). `value` = CwBvh closest-hit Mrays/s."""
+    import torch
+
+    from obvhs_b200 import api, camera, test_util as tu
+    from obvhs_b200.types import make_rays
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    width = 1280 if args.tris == 10_000_000 else int(round((args.tris / 2) ** 0.5))
+    tris = tu.demoscene(width, 570)
+    n_tris = tris.shape[0]
+    cam = camera.demoscene_camera(1280)
+    rays_all = camera.demoscene_primary(cam, 0)
+    from obvhs_b200.sharding import shard_range
+
+    lo, hi = shard_range(rays_all.shape[0], rank, world)
+    rays = np.ascontiguousarray(rays_all[lo:hi])
+    desc = f"demoscene({width},570) {n_tris} tris, medium_build, {cam.width}x{cam.height} primary rays + sun shadow rays, Bvh2 and CwBvh"
+    sun = np.array([0.35, -0.1, 0.19], np.float32)
+    sun = sun / np.float32(np.sqrt(np.float32((sun * sun).sum())))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_bind as ob
+
+        threads = len(os.sched_getaffinity(0))
+        t0 = time.perf_counter()
+        c = ob.build_cwbvh_from_tris(tris, "medium_build", threads=threads)
+        build_s = time.perf_counter() - t0
+        bt = c.bvh_tris(tris)
+        sample = rays_all[:: max(1, rays_all.shape[0] // args.ref_rays)][: args.ref_rays]
+        ts = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            c.ray_traverse(bt, sample, threads=threads)
+            if it >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        v = sample.shape[0] / float(np.mean(ts)) / 1e6
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": float(np.mean(ts)) * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "preset": "medium_build"},
+                          "build": {"value": n_tris / build_s / 1e6, "unit": "Mtris/s", "ms": build_s * 1e3},
+                          "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                           "sample": f"{sample.shape[0]} of {rays_all.shape[0]} primary rays (strided), full CwBvh build"},
+                          "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local_rank, stream=stream.cuda_stream)
+    params = api.BvhBuildParams.medium_build()
+    n_rays = rays.shape[0]
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(tris).to(dev)
+        d_rays = torch.from_numpy(rays).to(dev)
+        d_hits = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
+        d_miss = torch.empty(n_rays, dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        d_counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        # shadow rays from the CwBvh primary hits (replicated build on every rank: no collective on this path)
+        cw = api.build_cwbvh_from_tris(d_tris, params, ctx=ctx)
+        cw.ray_traverse(d_rays, out=d_hits)
+    stream.synchronize()
+    t = d_hits[:, 3].view(torch.float32).cpu().numpy()
+    hit = t < np.float32(3.0e38)
+    o, d = rays[hit, 0:3], rays[hit, 4:7]
+    hit_p = o + d * t[hit, None] - d * np.float32(0.01)
+    shadow = make_rays(hit_p.astype(np.float32), np.tile(-sun, (hit_p.shape[0], 1)).astype(np.float32), 0.0, np.inf)
+    n_shadow = shadow.shape[0]
+    with torch.cuda.stream(stream):
+        d_shadow = torch.from_numpy(shadow).to(dev)
+    stream.synchronize()
+
+    def timed(fn):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r = fn()
+            e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1), r
+
+    res = {}
+    launches0 = None
+    sampler = ClockSampler(local_rank)
+    for tree in ("cwbvh", "bvh2"):
+        build = (lambda: api.build_cwbvh_from_tris(d_tris, params, ctx=ctx)) if tree == "cwbvh" else (lambda: api.build_bvh2_from_tris(d_tris, params, ctx=ctx))
+        b_ms, p_ms, s_ms = [], [], []
+        keep = None
+        for it in range(args.warmup + args.steps):
+            if it == args.warmup and tree == "cwbvh":
+                if dist:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                if rank == 0:
+                    sampler.start()
+                launches0 = ctx.launch_count
+            tb, bvh = timed(build)
+            tp, _ = timed(lambda: bvh.ray_traverse(d_rays, out=d_hits))
+            tsd, _ = timed(lambda: bvh.ray_traverse_miss(d_shadow, out=d_miss[:n_shadow]))
+            keep = bvh  # the previous tree stays alive while the next one is built (result cache holds both sets)
+            if it >= args.warmup:
+                b_ms.append(tb)
+                p_ms.append(tp)
+                s_ms.append(tsd)
+        tot = torch.tensor([sum(b_ms), sum(p_ms), sum(s_ms)], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        bm, pm, sm_ = (tot / args.steps).tolist()
+        cnt = torch.tensor([n_rays, n_shadow], dtype=torch.int64, device=dev)
+        if dist:
+            dist.all_reduce(cnt)
+        nr, ns = cnt.tolist()
+        res[tree] = {"build_ms": bm, "build_mtris_per_s": n_tris / (bm * 1e-3) / 1e6, "primary_ms": pm, "primary_mrays_per_s": nr / (pm * 1e-3) / 1e6,
+                     "shadow_ms": sm_, "shadow_mrays_per_s": ns / (sm_ * 1e-3) / 1e6, "unoccluded": int(d_miss[:n_shadow].sum().item())}
+        if tree == "cwbvh":
+            with torch.cuda.stream(stream):
+                d_counters.zero_()
+                keep.ray_traverse(d_rays, out=d_hits, counters=d_counters)
+            stream.synchronize()
+            nodes_visited, tris_tested = [int(x) for x in d_counters.tolist()]
+            cw_keep = keep
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: CwBvh primary rays from pinned host memory, hits back to the host
+    from obvhs_b200.types import RAY_HIT
+
+    h_rays = torch.from_numpy(rays).pin_memory()
+    h_hits = torch.empty((n_rays, 4), dtype=torch.int32).pin_memory()
+    hits_np = h_hits.numpy().view(RAY_HIT).reshape(-1)
+    e_t = []
+    for it in range(5):
+        t0 = time.perf_counter()
+        cw_keep.ray_traverse(h_rays.numpy(), out=hits_np)
+        if it >= 2:
+            e_t.append(time.perf_counter() - t0)
+    e2e = torch.tensor([float(np.mean(e_t))], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        alg_bytes = n_rays * 48 + 80 * nodes_visited + 48 * tris_tested
+        achieved = alg_bytes / (res["cwbvh"]["primary_ms"] * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle_bind as ob
+
+            threads = len(os.sched_getaffinity(0))
+            sample = rays[:: max(1, n_rays // 200_000)][:200_000]
+            c = ob.build_cwbvh_from_tris(tris, "medium_build", threads=threads)
+            bt = c.bvh_tris(tris)
+            c.ray_traverse(bt, sample[:1000], threads=threads)
+            t0 = time.perf_counter()
+            c.ray_traverse(bt, sample, threads=threads)
+            dt = time.perf_counter() - t0
+            cpu = {"value": sample.shape[0] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                   "sample": f"{sample.shape[0]} of {n_rays} primary rays (strided), CwBvh; C++ restatement of the obvhs CPU path (OpenMP)",
+                   "build_mtris_per_s": n_tris / c.core_build_seconds / 1e6}
+        nr_all = res["cwbvh"]["primary_mrays_per_s"] * res["cwbvh"]["primary_ms"] * 1e3
+        print(json.dumps({
+            "metric": METRIC, "value": res["cwbvh"]["primary_mrays_per_s"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sum(res[t][k] for t in res for k in ("build_ms", "primary_ms", "shadow_ms")), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "preset": "medium_build", "rays_per_gpu": n_rays, "shadow_rays_per_gpu": n_shadow, "tris": n_tris,
+                       "l2": "flushed between timed calls (256 MB write)", "multi_gpu": "replicated build, rays sharded" if world > 1 else "single GPU"},
+            "build": {"value": res["cwbvh"]["build_mtris_per_s"], "unit": "Mtris/s", "ms": res["cwbvh"]["build_ms"]},
+            "cwbvh": res["cwbvh"], "bvh2": res["bvh2"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "traverse_persistent_kernel<CwTree, closest>", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "nodes_visited": nodes_visited, "tris_tested": tris_tested},
+            "cpu_baseline": cpu,
+            "e2e": {"value": nr_all / e2e.item() / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 64 * n_rays, "d2h_bytes_per_step": 16 * n_rays,
+                    "how": "obvhs_cuda_cwbvh_ray_traverse_batch with pinned HOST rays / hits"},
+            "gpu_launches": launches, "clocks": clocks}))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain", "bounce", "dynamic"])
+    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
     ap.add_argument("--samples", type=int, default=24, help="AA samples of the bounce workload (165 = the 100M-ray set of SURVEY.md 8d)")
     ap.add_argument("--tris", type=int, default=10_000_000)
     ap.add_argument("--ref-rays", type=int, default=2_073_600, help="ray sample bound for the CPU legs")
@@ -602,6 +793,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "dynamic":
         run_dynamic(args)
+    elif args.workload == "demoscene":
+        run_demoscene(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
