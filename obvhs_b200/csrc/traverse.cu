@@ -305,11 +305,22 @@ struct Bvh2Tree {
         u32 cur;  // left child of the pair to test next, or AT_ROOT before the root test
         u32 sp;
         RayResult o;
+        // one-triangle-per-step form only: the leaf being drained and what is still owed to the current pair
+        u32 phase;        // 0 = test the next pair, 1 / 2 = draining the nearer / farther leaf of the pair, 3 = draining a leaf root
+        u32 pend_first, pend_count;
+        float right_t;    // entry distance of the farther child, compared with tmax AFTER the nearer leaf was drained (:310)
+        u32 r_count, r_first, l_first;
+        bool go_left;
     };
     __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rp) const {
         ray_load(st.r, rp);
         st.cur = AT_ROOT;
         st.sp = 0;
+        st.phase = 0;
+        st.pend_first = st.pend_count = 0;
+        st.right_t = 0.f;
+        st.r_count = st.r_first = st.l_first = 0;
+        st.go_left = false;
         result_reset(st.o);
     }
     // aabb.rs:186-206; glam sse2 min/max (a<b?a:b) and max_element/min_element pairing (x,z),(y,z)
@@ -348,9 +359,115 @@ struct Bvh2Tree {
         }
         return go_on;
     }
+    // The same loop with at most ONE triangle per call (persistent kernel): a leaf is drained over several calls while the rest of
+    // the pair's work (the farther child's `right_t < tmax` test with the tmax the nearer leaf left behind, then descend / push /
+    // pop) waits in the state. The sequence of box and triangle tests of a ray is exactly the reference's.
+    template <int MODE, bool COUNT>
+    __device__ __forceinline__ bool step_one_tri(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
+        bool done = false;
+        u32 stage = 0;  // after this call's test: 0 = nothing more, 1 = decide the farther child, 2 = descend / push / pop
+        if (st.phase != 0) {
+            const u32 pid = st.pend_first;
+            const float t = tri_intersect(tris, pid, st.r);
+            if (COUNT) tris_tested++;
+            st.pend_first++;
+            st.pend_count--;
+            bool halt = false;
+            if (MODE == 0) {
+                if (t < st.r.tmax) {
+                    st.o.hit_id = pid;
+                    st.o.hit_t = t;
+                    st.r.tmax = t;
+                }
+            } else if (MODE == 1) {
+                if (t < st.r.tmax) {
+                    st.o.is_miss = false;
+                    halt = true;
+                }
+            } else {
+                if (t < __int_as_float(0x7f800000)) st.o.count++;
+            }
+            if (halt) done = true;
+            else if (st.pend_count == 0) {  // the leaf is finished
+                if (st.phase == 3) done = true;
+                else stage = st.phase;  // 1 -> the farther child is next, 2 -> finish the pair
+                st.phase = 0;
+            }
+        } else if (st.cur == AT_ROOT) {
+            if (node_count == 0) done = true;
+            else {
+                const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
+                if (COUNT) nodes_tested++;
+                const u32 prim_count = __float_as_uint(lo.w), first_index = __float_as_uint(hi.w);
+                if (!(box_t(lo, hi, st.r) < st.r.tmax)) done = true;
+                else if (prim_count != 0) {
+                    st.phase = 3;
+                    st.pend_first = first_index;
+                    st.pend_count = prim_count;
+                } else st.cur = first_index;
+            }
+        } else {
+            const float4* np = nodes + (size_t)st.cur * 2;
+            const float4 llo = __ldg(np), lhi = __ldg(np + 1), rlo = __ldg(np + 2), rhi = __ldg(np + 3);
+            if (COUNT) nodes_tested += 2;
+            float left_t = box_t(llo, lhi, st.r), right_t = box_t(rlo, rhi, st.r);
+            u32 l_count = __float_as_uint(llo.w), l_first = __float_as_uint(lhi.w);
+            u32 r_count = __float_as_uint(rlo.w), r_first = __float_as_uint(rhi.w);
+            if (left_t > right_t) {  // :294-297
+                float tf = left_t; left_t = right_t; right_t = tf;
+                u32 tu = l_count; l_count = r_count; r_count = tu;
+                tu = l_first; l_first = r_first; r_first = tu;
+            }
+            st.right_t = right_t;
+            st.r_count = r_count;
+            st.r_first = r_first;
+            st.l_first = l_first;
+            const bool hit_left = left_t < st.r.tmax;
+            if (hit_left && l_count != 0) {
+                st.go_left = false;
+                st.phase = 1;
+                st.pend_first = l_first;
+                st.pend_count = l_count;
+            } else {
+                st.go_left = hit_left;
+                stage = 1;
+            }
+        }
+        bool go_right = false;
+        if (stage == 1) {
+            const bool hit_right = st.right_t < st.r.tmax;  // ray.tmax may have shrunk in the nearer leaf (:310)
+            if (hit_right && st.r_count != 0) {
+                st.phase = 2;
+                st.pend_first = st.r_first;
+                st.pend_count = st.r_count;
+            } else {
+                go_right = hit_right;
+                stage = 2;
+            }
+        }
+        if (stage == 2) {
+            if (st.go_left) {
+                st.cur = st.l_first;
+                if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
+                    stack[st.sp] = st.r_first;
+                    st.sp = min(st.sp + 1u, (u32)(CAP - 1));
+                }
+            } else if (go_right) {
+                st.cur = st.r_first;
+            } else if (st.sp == 0) {
+                st.o.hit_t = st.r.tmax;  // :326 `hit.t = ray.tmax`
+                done = true;
+            } else {
+                st.sp--;
+                st.cur = stack[st.sp];
+            }
+        }
+        return done;
+    }
     // one iteration of ray_traverse_dynamic's loop (:284-331); the first call performs the root test (:273-282)
     template <int MODE, bool COUNT, bool ONE_TRI = false>
     __device__ __forceinline__ bool step(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
+        if (ONE_TRI) return step_one_tri<MODE, COUNT>(st, stack, nodes_tested, tris_tested);
         bool done = false;
         if (st.cur == AT_ROOT) {
             if (node_count == 0) return true;
