@@ -30,7 +30,7 @@ typedef enum {
     OBVHS_OK = 0,
     OBVHS_ERR_INVALID_ARG = -1,
     OBVHS_ERR_CUDA = -2,
-    OBVHS_ERR_UNSUPPORTED = -3, /* include_exact_node_aabbs, depth beyond the fixed stacks, >= 2^30 primitives */
+    OBVHS_ERR_UNSUPPORTED = -3, /* depth beyond the fixed stacks, >= 2^30 primitives */
     OBVHS_ERR_NAN_INPUT = -4,   /* the reference panics / goes out of bounds on NaN AABBs (ploc/mod.rs:451) */
     OBVHS_ERR_STACK_OVERFLOW = -5,
     OBVHS_ERR_CAPACITY = -6     /* a growing output (Vec::push in the reference) does not fit the caller's arrays */
@@ -215,6 +215,10 @@ int obvhs_cuda_bvh2_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsBvh
  * include_exact_node_aabbs must be 0. */
 int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t max_prims_per_leaf, int order_children,
                              int include_exact_node_aabbs, ObvhsCwBvh** out);
+/* CwBvh::exact_node_aabbs (src/cwbvh/mod.rs:47; filled when bvh2_to_cwbvh was called with include_exact_node_aabbs,
+ * bvh2_to_cwbvh.rs:60-80): one Aabb per Bvh2 node slot, entry i < node_count = the unquantised box of wide node i, the rest
+ * Aabb::empty(). *count receives the number of entries (0 when absent); out may be NULL to query it. */
+int obvhs_cuda_cwbvh_exact_node_aabbs(ObvhsContext* ctx, const ObvhsCwBvh* bvh, ObvhsAabb* out, size_t capacity, size_t* count);
 /* build_cwbvh_from_tris(triangles, config, core_build_time) (cwbvh/builder.rs:20-85). core_build_seconds (optional)
  * is INCREMENTED by the device time of PLOC -> reinsertion -> collapse, as the reference's `+=` does. The permuted
  * triangle array (examples/obj_cwbvh.rs:63-67) is attached to the result so it can be traversed directly. */

@@ -103,6 +103,7 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_free": (None, [_vp]),
     "obvhs_cuda_cwbvh_node_count": (_sz, [_vp]),
     "obvhs_cuda_cwbvh_prim_count": (_sz, [_vp]),
+    "obvhs_cuda_cwbvh_exact_node_aabbs": (_i32, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_cwbvh_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_cwbvh_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _PP]),
     "obvhs_cuda_cwbvh_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
@@ -590,6 +591,16 @@ class CwBvh:
         total = np.zeros(8, dtype=np.float32)
         self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_download(self.ctx.h, self.h, _ptr(nodes), _ptr(prims), _ptr(total)))
         return nodes, prims, total
+
+    def exact_node_aabbs(self):
+        """CwBvh::exact_node_aabbs (src/cwbvh/mod.rs:47) as an (n, 8) float32 array, or None when absent."""
+        count = _sz(0)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_exact_node_aabbs(self.ctx.h, self.h, None, 0, C.byref(count)))
+        if count.value == 0:
+            return None
+        out = np.zeros((count.value, 8), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_exact_node_aabbs(self.ctx.h, self.h, _ptr(out), count.value, C.byref(count)))
+        return out
 
     def set_triangles(self, tris):
         t = _as_f32(tris, 12)

@@ -659,11 +659,7 @@ int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t m
                              int include_exact_node_aabbs, ObvhsCwBvh** out) {
     API_ENTER(ctx);
     ARG_CHECK(ctx, bvh && out, "null argument");
-    if (include_exact_node_aabbs) {
-        OBVHS_SET_ERR(ctx, "include_exact_node_aabbs is not supported");
-        return OBVHS_ERR_UNSUPPORTED;
-    }
-    return bvh2_to_cwbvh_device(ctx, bvh, max_prims_per_leaf, order_children != 0, out);
+    return bvh2_to_cwbvh_device(ctx, bvh, max_prims_per_leaf, order_children != 0, out, include_exact_node_aabbs != 0);
 }
 
 int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris, size_t n, const ObvhsBuildParams* params,
@@ -752,8 +748,23 @@ void obvhs_cuda_cwbvh_free(ObvhsCwBvh* bvh) {
     obvhs_result_free(ctx, bvh->nodes);
     obvhs_result_free(ctx, bvh->primitive_indices);
     obvhs_result_free(ctx, bvh->bvh_tris);
+    obvhs_result_free(ctx, bvh->exact_node_aabbs);
     delete bvh;
     obvhs_context_release(ctx);
+}
+// CwBvh::exact_node_aabbs (cwbvh/mod.rs:47): *count = number of entries (0 when the tree was converted without them)
+int obvhs_cuda_cwbvh_exact_node_aabbs(ObvhsContext* ctx, const ObvhsCwBvh* bvh, ObvhsAabb* out, size_t capacity, size_t* count) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && count, "null argument");
+    *count = bvh->exact_node_aabbs ? bvh->exact_count : 0;
+    if (!out || *count == 0) return OBVHS_OK;
+    if (capacity < *count) {
+        OBVHS_SET_ERR(ctx, "exact_node_aabbs: %zu entries, capacity %zu", *count, capacity);
+        return OBVHS_ERR_CAPACITY;
+    }
+    ST_TRY(copy_out(ctx, out, (const ObvhsAabb*)bvh->exact_node_aabbs, *count));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
 }
 int obvhs_cuda_cwbvh_uses_spatial_splits(const ObvhsCwBvh* bvh) { return bvh && bvh->uses_spatial_splits; }
 void obvhs_cuda_cwbvh_set_uses_spatial_splits(ObvhsCwBvh* bvh, int v) { if (bvh) bvh->uses_spatial_splits = v != 0; }

@@ -185,6 +185,8 @@ struct ObvhsCwBvh {
     ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices, or null
     size_t node_count = 0, prim_count = 0;
     ObvhsAabb total_aabb = {};
+    ObvhsAabb* exact_node_aabbs = nullptr;  // cwbvh/mod.rs:47, exact_count entries (the Bvh2's node count), or null
+    size_t exact_count = 0;
     bool uses_spatial_splits = false;  // cwbvh/mod.rs:54
 };
 
@@ -319,7 +321,8 @@ int bvh2_collapse_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 max_prims, float
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);
 int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, size_t n, u32 iterations, u64* applied_out);
 // cwbvh_build.cu
-int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out);
+int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out,
+                         bool include_exact_node_aabbs = false);
 // traverse.cu
 int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
                           u64* d_counters);

@@ -645,6 +645,7 @@ struct EmitArgs {
     int order_children;
     u32 expected;  // M = 1 + S(root, 0)
     CwGlobals* g;
+    float4* exact;  // CwBvh::exact_node_aabbs (bvh2_to_cwbvh.rs:78-80), or null
 };
 
 constexpr int EMIT_THREADS = 512;
@@ -683,7 +684,13 @@ __global__ void __launch_bounds__(EMIT_THREADS) cwbvh_emit_all_kernel(EmitArgs a
             const bool have = t < qlen;
             uint4 item = make_uint4(0, 0, 0, 0);
             if (have) item = __ldcg(&cur[t]);
-            emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, have, item, nullptr, nxt, &g->queue_count[level % 3], a.out_nodes, a.out_prims,
+if (a.exact && have && gl == 0) {  // exact_node_aabbs[node_index_bvh8] = *aabb (bvh2_to_cwbvh.rs:78-80)
+                const float4* src = reinterpret_cast<const float4*>(a.nodes + item.y);
+                const float4 lo = __ldg(src), hi = __ldg(src + 1);
+                a.exact[2 * (size_t)item.x] = make_float4(lo.x, lo.y, lo.z, 0.f);
+                a.exact[2 * (size_t)item.x + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+            }
+                        emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, have, item, nullptr, nxt, &g->queue_count[level % 3], a.out_nodes, a.out_prims,
                            a.order_children, g, gmask, gl, sbuf);
         }
         grid.sync();
@@ -710,6 +717,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) cwbvh_emit_all_kernel(EmitArgs a
     if (tid == 0) g->emitted = emitted;
 }
 
+// vec![Aabb::empty(); bvh2.nodes.len()] (bvh2_to_cwbvh.rs:60-62; aabb.rs:166-171)
+__global__ void fill_empty_aabbs_kernel(float4* out, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float FMAX = 3.40282347e+38f;
+    out[2 * (size_t)i] = make_float4(FMAX, FMAX, FMAX, 0.f);
+    out[2 * (size_t)i + 1] = make_float4(-FMAX, -FMAX, -FMAX, 0.f);
+}
+
 __global__ void root_aabb_kernel(const Node32* nodes, float* out8) {
     Node32 r = load_node(nodes);
     out8[0] = r.minx; out8[1] = r.miny; out8[2] = r.minz; out8[3] = 0.f;
@@ -718,7 +734,8 @@ __global__ void root_aabb_kernel(const Node32* nodes, float* out8) {
 
 }  // namespace
 
-int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out) {
+int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out,
+                         bool include_exact_node_aabbs) {
     cudaStream_t s = ctx->stream;
     ObvhsCwBvh* cw = new ObvhsCwBvh();
     cw->device = ctx->device;
@@ -795,11 +812,18 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->primitive_indices, std::max<size_t>(1, cw->prim_count) * 4));
     CU_TRY(ctx, queue_a.alloc(M, s));
     CU_TRY(ctx, queue_b.alloc(M, s));
+    if (include_exact_node_aabbs) {
+        cw->exact_count = n_nodes;
+        CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->exact_node_aabbs, (size_t)n_nodes * sizeof(ObvhsAabb)));
+        fill_empty_aabbs_kernel<<<div_up(n_nodes, 256), 256, 0, s>>>(reinterpret_cast<float4*>(cw->exact_node_aabbs), n_nodes);
+        KERNEL_CHECK(ctx);
+    }
     {
         EmitArgs ea;
         ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.dec = dec.p; ea.P = P.p;
         ea.queue_a = queue_a.p; ea.queue_b = queue_b.p; ea.out_nodes = reinterpret_cast<uint4*>(cw->nodes);
         ea.out_prims = cw->primitive_indices; ea.order_children = order_children ? 1 : 0; ea.expected = M; ea.g = g.p;
+        ea.exact = reinterpret_cast<float4*>(cw->exact_node_aabbs);
         int per_sm = 0;
         CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_emit_all_kernel, EMIT_THREADS, 0));
         // few, fat blocks: the cost of a grid-wide barrier grows with the number of participating blocks

@@ -2224,6 +2224,12 @@ void orc_cwbvh_get(const OrcCwBvh* c, OrcCwBvhNode* nodes, u32* primitive_indice
     if (total) *total = c->total_aabb;
 }
 int orc_cwbvh_validate(const OrcCwBvh* c, const OrcAabb* prim_aabbs, size_t n, char* msg) { return cwbvh_validate(*c, prim_aabbs, n, msg); }
+// CwBvh::exact_node_aabbs (cwbvh/mod.rs:47): bvh2.nodes.len() entries, Aabb::empty() beyond the wide nodes; returns the length
+size_t orc_cwbvh_exact_node_aabbs(const OrcCwBvh* c, OrcAabb* out, size_t cap) {
+    size_t m = std::min(cap, c->exact_node_aabbs.size());
+    if (out && m) memcpy(out, c->exact_node_aabbs.data(), m * sizeof(OrcAabb));
+    return c->exact_node_aabbs.size();
+}
 
 OrcCwBvh* orc_build_cwbvh_from_tris(const OrcTriangle* tris, size_t n, u32 search_distance, size_t search_depth_threshold,
                                     float reinsertion_batch_ratio, int precision, u32 max_prims_per_leaf, int pre_split, int threads,

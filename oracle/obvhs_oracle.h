@@ -93,6 +93,7 @@ size_t    orc_cwbvh_node_count(const OrcCwBvh*);
 size_t    orc_cwbvh_prim_count(const OrcCwBvh*);
 void      orc_cwbvh_get(const OrcCwBvh*, OrcCwBvhNode* nodes, uint32_t* primitive_indices, OrcAabb* total_aabb);
 int       orc_cwbvh_validate(const OrcCwBvh*, const OrcAabb* prim_aabbs, size_t n, char* msg); /* cwbvh/mod.rs:747-908 */
+size_t    orc_cwbvh_exact_node_aabbs(const OrcCwBvh*, OrcAabb* out, size_t cap);            /* cwbvh/mod.rs:47 (0 when absent) */
 
 /* one-call builder (cwbvh/builder.rs:20-85). core_seconds mirrors core_build_time. */
 OrcCwBvh* orc_build_cwbvh_from_tris(const OrcTriangle* tris, size_t n, uint32_t search_distance,

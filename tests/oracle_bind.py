@@ -76,6 +76,7 @@ def lib():
             "orc_cwbvh_prim_count": (sz, [vp]),
             "orc_cwbvh_get": (None, [vp, vp, vp, vp]),
             "orc_cwbvh_validate": (i32, [vp, vp, sz, C.c_char_p]),
+            "orc_cwbvh_exact_node_aabbs": (sz, [vp, vp, sz]),
             "orc_build_cwbvh_from_tris": (vp, [vp, sz, u32, sz, f32, i32, u32, i32, i32, vp]),
             "orc_cwbvh_ray_traverse": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
             "orc_cwbvh_ray_traverse_miss": (None, [vp, vp, vp, sz, vp, i32, i32, vp]),
@@ -318,6 +319,15 @@ class CwBvh:
         """examples/obj_cwbvh.rs:63-67: triangles permuted by primitive_indices."""
         _, prims, _ = self.get()
         return np.ascontiguousarray(np.asarray(tris, dtype=np.float32)[prims])
+
+    def exact_node_aabbs(self):
+        """CwBvh::exact_node_aabbs (None when the tree was converted without them)"""
+        n = lib().orc_cwbvh_exact_node_aabbs(self.h, None, 0)
+        if n == 0:
+            return None
+        out = np.zeros((n, 8), np.float32)
+        lib().orc_cwbvh_exact_node_aabbs(self.h, _p(out), n)
+        return out
 
     def aabb_traverse(self, queries, direction=(0.0, 0.0, 0.0)):
         """traverse!(.., node.intersect_aabb(&aabb, state.oct_inv4), ..) per query: (counts, primitive slots in call order)"""

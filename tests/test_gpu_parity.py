@@ -398,8 +398,19 @@ def test_unsupported_paths_fail_loudly(api):
         api.PlocBuilder().build(7, ob.tri_aabbs(tris))  # not a PlocSearchDistance
     with pytest.raises(api.ObvhsError):
         api.PlocBuilder().build(6, ob.tri_aabbs(tris), None, 96)  # not a SortPrecision
-    with pytest.raises(api.ObvhsError):
-        api.bvh2_to_cwbvh(api.PlocBuilder().build(6, ob.tri_aabbs(tris)), 3, True, True)  # include_exact_node_aabbs
+
+
+@pytest.mark.parametrize("scene", ["cornell", "terrain32", "kitchen"])
+def test_cwbvh_exact_node_aabbs(api, scenes, scene):
+    # bvh2_to_cwbvh(.., include_exact_node_aabbs = true) (bvh2_to_cwbvh.rs:60-80): the unquantised box of every wide node
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, 6, 64, 2).to_cwbvh(3, True, True)
+    got = api.bvh2_to_cwbvh(api.PlocBuilder().build(6, aabbs, None, api.SortPrecision.U64, 2), 3, True, True)
+    assert got.download()[0].tobytes() == want.get()[0].tobytes()
+    w, g = want.exact_node_aabbs(), got.exact_node_aabbs()
+    assert g.shape == w.shape and g.shape[0] == 2 * aabbs.shape[0] - 1
+    assert np.array_equal(g[:, [0, 1, 2, 4, 5, 6]].view(np.uint32), w[:, [0, 1, 2, 4, 5, 6]].view(np.uint32))
+    assert api.bvh2_to_cwbvh(api.PlocBuilder().build(6, aabbs), 3, True, False).exact_node_aabbs() is None
 
 
 def test_large_scene_full_parity_and_properties(api):

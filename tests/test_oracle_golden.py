@@ -146,3 +146,21 @@ def test_refit_fast_vs_full_differ_only_in_zero_sign(scenes):
             assert np.array_equal(res[0]["aabb"], res[1]["aabb"]), name  # value compare: -0.0 == +0.0
             bits_differ = res[0]["aabb"].view(np.uint32) != res[1]["aabb"].view(np.uint32)
             assert np.all(res[0]["aabb"][bits_differ] == 0.0)
+
+
+def test_exact_node_aabbs_bound_by_quantised_boxes(scenes):
+    # bvh2_to_cwbvh(.., include_exact_node_aabbs = true) (bvh2_to_cwbvh.rs:60-80): entry i is the unquantised box of wide node i;
+    # the node's quantisation frame (p .. p + extent * 255, cwbvh/node.rs:261-265) must contain it, the root's is the scene box
+    aabbs = ob.tri_aabbs(scenes["kitchen"])
+    b = ob.ploc_build(aabbs, None, 6, 64, 2)
+    c = b.to_cwbvh(3, True, True)
+    nodes, _, total = c.get()
+    ex = c.exact_node_aabbs()
+    assert ex.shape[0] == b.node_count
+    m = nodes.shape[0]
+    assert np.array_equal(ex[0, [0, 1, 2, 4, 5, 6]], total[[0, 1, 2, 4, 5, 6]])
+    extent = (nodes["e"].astype(np.uint32) << 23).view(np.float32)
+    lo, hi = nodes["p"], nodes["p"] + extent * np.float32(255.0)
+    assert np.all(ex[:m, 0:3] >= lo) and np.all(ex[:m, 4:7] <= hi + np.abs(hi) * 1e-6 + 1e-6)
+    assert np.all(ex[m:, 0] == np.float32(3.4028235e38)) and np.all(ex[m:, 4] == np.float32(-3.4028235e38))  # Aabb::empty()
+    assert ob.ploc_build(aabbs, None, 6, 64, 2).to_cwbvh(3, True, False).exact_node_aabbs() is None
