@@ -9,6 +9,8 @@
 // "ties keep ascending original order", i.e. a STABLE sort. Stability here comes from: tiles are taken in ticket
 // order and chained by look-back; inside a tile warps own consecutive chunks; inside a warp items are ranked item by
 // item with lanes ordered by lane id (warp-striped layout == memory order).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -78,25 +80,22 @@ __device__ __forceinline__ u32 digit_peers(u32 d) {
     return peers;
 }
 
-template <typename K, bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
-                                                                const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
-                                                                int shift, const u32* __restrict__ goffs, u32* status, u32* ticket) {
+// One tile of one pass. goff: exclusive digit offsets of the pass (global, or the CTA's shared copy). CG: the inputs were
+// written earlier in the SAME launch by other CTAs (sort_mid_kernel), so they are read through L2.
+template <typename K, bool WRITE_KEYS, bool CG>
+__device__ __forceinline__ void onesweep_tile(const K* kin, K* kout, const u32* vin, u32* vout, size_t n, int shift, const u32* goffs, u32* status,
+                                              u32 tile, unsigned char* smem_raw) {
     constexpr int SORT_ITEMS = SortCfg<K>::ITEMS, SORT_TILE = SortCfg<K>::TILE;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     K* skeys = reinterpret_cast<K*>(smem_raw);
     u32* svals = reinterpret_cast<u32*>(skeys + SORT_TILE);
     u32* whist = svals + SORT_TILE;          // [SORT_WARPS][256] per-warp digit counts -> exclusive offsets across warps
     u32* dstart = whist + SORT_WARPS * 256;  // [256] start of each digit inside the tile
     u32* gbase = dstart + 256;               // [256] global position of local position 0 of each digit
-    __shared__ u32 s_tile;
     __shared__ u32 s_wsum[SORT_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int k = 0; k < SORT_WARPS; k++) whist[k * 256 + tid] = 0;
     __syncthreads();
-    const u32 tile = s_tile;
     const size_t base = (size_t)tile * SORT_TILE;
     const u32 valid = (u32)min((size_t)SORT_TILE, n - base);
     const size_t wstart = base + (size_t)warp * (SORT_ITEMS * 32);
@@ -108,8 +107,8 @@ __global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_k
     for (int i = 0; i < SORT_ITEMS; i++) {
         size_t idx = wstart + i * 32 + lane;
         bool ok = idx < n;
-        key[i] = ok ? kin[idx] : (K)~(K)0;  // padding sorts behind every valid key of the tile
-        val[i] = ok ? vin[idx] : 0u;
+        key[i] = ok ? (CG ? __ldcg(kin + idx) : kin[idx]) : (K)~(K)0;  // padding sorts behind every valid key of the tile
+        val[i] = ok ? (CG ? __ldcg(vin + idx) : vin[idx]) : 0u;
     }
     u32* mywh = whist + warp * 256;
     const u32 lt = (1u << lane) - 1u;
@@ -199,6 +198,71 @@ __global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_k
         u32 o = gbase[d] + j;
         if (WRITE_KEYS) kout[o] = k;
         vout[o] = svals[j];
+    }
+    __syncthreads();  // the shared arrays are reused by the caller's next tile
+}
+
+template <typename K, bool WRITE_KEYS>
+__global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout,
+                                                                const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
+                                                                int shift, const u32* __restrict__ goffs, u32* status, u32* ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    onesweep_tile<K, WRITE_KEYS, false>(kin, kout, vin, vout, n, shift, goffs, status, s_tile, smem_raw);
+}
+
+// Mid-size sorts (a few thousand to a million pairs: the reinsertion rounds of a large scene, the Morton sort of a small one)
+// in ONE cooperative launch: digit histograms -> grid barrier -> per pass { every CTA scans the pass's histogram into shared
+// memory, tiles dealt round-robin } with a grid barrier between passes. Replaces 2 + passes launches that are each shorter than
+// their own launch latency.
+template <typename K>
+__global__ void __launch_bounds__(SORT_THREADS, SortCfg<K>::MIN_CTAS) sort_mid_kernel(K* keys, K* keys_alt, u32* vals, u32* vals_alt, u32 n, int passes,
+                                                                                    u32* ghist, u32* status, u32 tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_goffs[256];
+    __shared__ u32 s_ws[SORT_WARPS];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {  // all digit histograms in one read of the keys
+        u32* sh = reinterpret_cast<u32*>(smem_raw);
+        for (int t = tid; t < passes * 256; t += SORT_THREADS) sh[t] = 0;
+        __syncthreads();
+        for (u32 i = blockIdx.x * SORT_THREADS + tid; i < n; i += gridDim.x * SORT_THREADS) {
+            const K k = keys[i];
+            for (int p = 0; p < passes; p++) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
+        }
+        __syncthreads();
+        for (int t = tid; t < passes * 256; t += SORT_THREADS) {
+            const u32 c = sh[t];
+            if (c) atomicAdd(&ghist[t], c);
+        }
+    }
+    grid.sync();
+    K *kin = keys, *kout = keys_alt;
+    u32 *vin = vals, *vout = vals_alt;
+    for (int p = 0; p < passes; p++) {
+        {  // exclusive scan of this pass's 256 bins (every CTA its own copy)
+            const u32 c = __ldcg(&ghist[p * 256 + tid]);
+            u32 x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_ws[warp] = x;
+            __syncthreads();
+            u32 wbase = 0;
+            for (int k = 0; k < warp; k++) wbase += s_ws[k];
+            s_goffs[tid] = wbase + x - c;
+            __syncthreads();
+        }
+        for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+            onesweep_tile<K, true, true>(kin, kout, vin, vout, n, 8 * p, s_goffs, status + (size_t)p * tiles * 256, tile, smem_raw);
+        grid.sync();
+        K* tk = kin; kin = kout; kout = tk;
+        u32* tv = vin; vin = vout; vout = tv;
     }
 }
 
@@ -308,6 +372,8 @@ static int launch_block_sort(ObvhsContext* ctx, const K* keys, const u32* vals, 
     return OBVHS_OK;
 }
 
+constexpr size_t SORT_MID_MAX = (size_t)1 << 20;  // pairs up to which one cooperative launch does the whole sort
+
 template <typename K>
 constexpr size_t onesweep_smem() {
     return (size_t)SortCfg<K>::TILE * (sizeof(K) + 4) + (SORT_WARPS * 256 + 512) * 4;
@@ -341,21 +407,38 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
     u32* goffs = ghist + (size_t)passes * 256;
     u32* ticket = goffs + (size_t)passes * 256;
     u32* status = ticket + 8;
-    int hist_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
-    sort_hist_kernel<K><<<hist_blocks, 256, 0, ctx->stream>>>(keys, n, passes, ghist);
-    KERNEL_CHECK(ctx);
-    sort_scan_kernel<<<passes, 256, 0, ctx->stream>>>(ghist, goffs);
-    KERNEL_CHECK(ctx);
     static bool attr_set[2] = {false, false};
     const int which = sizeof(K) == 8 ? 1 : 0;
     if (!attr_set[which]) {
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
-        // four CTAs per SM need ~140 KB of shared memory: ask for the largest carve-out
+        CU_TRY(ctx, cudaFuncSetAttribute(sort_mid_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
+        // three / four CTAs per SM need 140-180 KB of shared memory: ask for the largest carve-out
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CU_TRY(ctx, cudaFuncSetAttribute(sort_mid_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[which] = true;
     }
+    if (n <= SORT_MID_MAX) {
+        static int per_sm[2] = {0, 0};
+        if (per_sm[which] == 0) {
+            CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[which], sort_mid_kernel<K>, SORT_THREADS, onesweep_smem<K>()));
+            if (per_sm[which] < 1) per_sm[which] = 1;
+        }
+        const int blocks = (int)std::min<size_t>((size_t)per_sm[which] * ctx->sm_count, tiles);
+        u32 un = (u32)n, utiles = (u32)tiles;
+        void* args[] = {&keys, &keys_alt, &vals, &vals_alt, &un, &passes, &ghist, &status, &utiles};
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)sort_mid_kernel<K>, dim3(blocks), dim3(SORT_THREADS), args, onesweep_smem<K>(), ctx->stream));
+        KERNEL_CHECK(ctx);
+        *sorted_keys = (passes & 1) ? keys_alt : keys;
+        *sorted_vals = (passes & 1) ? vals_alt : vals;
+        return OBVHS_OK;
+    }
+    int hist_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    sort_hist_kernel<K><<<hist_blocks, 256, 0, ctx->stream>>>(keys, n, passes, ghist);
+    KERNEL_CHECK(ctx);
+    sort_scan_kernel<<<passes, 256, 0, ctx->stream>>>(ghist, goffs);
+    KERNEL_CHECK(ctx);
     K *kin = keys, *kout = keys_alt;
     u32 *vin = vals, *vout = vals_alt;
     for (int p = 0; p < passes; p++) {
