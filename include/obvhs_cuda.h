@@ -238,6 +238,10 @@ int obvhs_cuda_cwbvh_upload(ObvhsContext* ctx, const ObvhsCwBvhNode* nodes, size
                             ObvhsCwBvh** out);
 /* bvh_tris[i] = tris[primitive_indices[i]] (examples/obj_cwbvh.rs:63-67), kept on the device inside the handle. */
 int obvhs_cuda_cwbvh_set_triangles(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* tris, size_t n);
+/* Bytes per primitive of the handle's internal triangle buffer (the third pointer of obvhs_cuda_cwbvh_device_ptrs): the
+ * triangles permuted by primitive_indices are kept as the reference's RtTriangle {v0, e1, e2, ng} (src/rt_triangle.rs:160-183,
+ * 64 bytes), whose intersect() returns exactly what Triangle::intersect() does. */
+size_t obvhs_cuda_cwbvh_triangle_bytes(void);
 /* device addresses of the buffers (for NCCL broadcast of a finished tree); bvh_tris is NULL until set. */
 int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** primitive_indices, void** bvh_tris);
 /* empty device-resident CwBvh with the given sizes, to receive a broadcast */

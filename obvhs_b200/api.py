@@ -107,6 +107,7 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_cwbvh_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _PP]),
     "obvhs_cuda_cwbvh_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
+    "obvhs_cuda_cwbvh_triangle_bytes": (_sz, []),
     "obvhs_cuda_cwbvh_device_ptrs": (_i32, [_vp, _PP, _PP, _PP]),
     "obvhs_cuda_cwbvh_alloc": (_i32, [_vp, _sz, _sz, _i32, _vp, _PP]),
     "obvhs_cuda_cwbvh_ray_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),

@@ -804,7 +804,7 @@ int obvhs_cuda_cwbvh_alloc(ObvhsContext* ctx, size_t node_count, size_t prim_cou
     } guard{cw};
     if (node_count) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->nodes, node_count * sizeof(ObvhsCwBvhNode)));
     if (prim_count) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->primitive_indices, prim_count * 4));
-    if (prim_count && with_triangles) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->bvh_tris, prim_count * sizeof(ObvhsTriangle)));
+    if (prim_count && with_triangles) CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&cw->bvh_tris, prim_count * OBVHS_RT_TRIANGLE_BYTES));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     guard.b = nullptr;
     *out = cw;
@@ -848,6 +848,7 @@ int obvhs_cuda_cwbvh_set_triangles(ObvhsContext* ctx, ObvhsCwBvh* bvh, const Obv
     return OBVHS_OK;
 }
 
+size_t obvhs_cuda_cwbvh_triangle_bytes(void) { return OBVHS_RT_TRIANGLE_BYTES; }
 int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** primitive_indices, void** bvh_tris) {
     if (!bvh) return OBVHS_ERR_INVALID_ARG;
     if (nodes) *nodes = bvh->nodes;

@@ -29,6 +29,7 @@ static_assert(sizeof(ObvhsCwBvhNode) == 80, "CwBvhNode");
 static_assert(sizeof(ObvhsRay) == 64, "Ray");
 static_assert(sizeof(ObvhsRayHit) == 16, "RayHit");
 
+#define OBVHS_RT_TRIANGLE_BYTES 64  // rt_triangle.rs:160-168 RtTriangle {v0, e1, e2, ng}: the handles' internal triangle layout
 #define OBVHS_SM_COUNT 148  // B200: grids are sized in multiples of this
 
 // ----------------------------------------------------------------------------------------------------------
@@ -169,7 +170,7 @@ struct ObvhsBvh2 {
     Node32* nodes = nullptr;          // node_count
     u32* primitive_indices = nullptr;  // prim_count
     u32* parents = nullptr;            // node_count, or null when not computed (Bvh2::parents: Option)
-    ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices (for ray traversal), or null
+    void* bvh_tris = nullptr;  // triangles permuted by primitive_indices as 64-byte RtTriangles (see traverse.cu), or null
     size_t node_count = 0, prim_count = 0;
     size_t max_depth = 96;  // bvh2/mod.rs:87 DEFAULT_MAX_STACK_DEPTH
     size_t ploc_iterations = 0;
@@ -182,7 +183,7 @@ struct ObvhsCwBvh {
     int device = 0;
     ObvhsCwBvhNode* nodes = nullptr;
     u32* primitive_indices = nullptr;
-    ObvhsTriangle* bvh_tris = nullptr;  // triangles permuted by primitive_indices, or null
+    void* bvh_tris = nullptr;  // triangles permuted by primitive_indices as 64-byte RtTriangles (see traverse.cu), or null
     size_t node_count = 0, prim_count = 0;
     ObvhsAabb total_aabb = {};
     ObvhsAabb* exact_node_aabbs = nullptr;  // cwbvh/mod.rs:47, exact_count entries (the Bvh2's node count), or null

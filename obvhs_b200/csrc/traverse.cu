@@ -29,23 +29,33 @@ struct RayRegs {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin, tmax;
 };
 
-// triangle.rs:35-76; glam sse2 cross/dot operand order, no FMA.
+// triangle.rs:35-76; glam sse2 cross/dot operand order, no FMA. The handle keeps its triangles in the
+// reference's OWN precomputed form, RtTriangle {v0, e1 = v0 - v1, e2 = v2 - v0, ng = e1 x e2} (rt_triangle.rs:171-183, 64 bytes):
+// e1, e2 and ng are the first values Triangle::intersect computes, rounded identically when the handle is filled
+// (rt_triangle_of), so RtTriangle::intersect (rt_triangle.rs:199-239) returns bit for bit what Triangle::intersect does while
+// the per-test work drops by the 15 operations of the edge / normal set-up.
+constexpr int RT_TRI_VEC4 = 4;  // float4 per stored triangle
+__device__ __forceinline__ void rt_triangle_of(const float4 a, const float4 b, const float4 c4, float4 (&out)[4]) {
+    const float e1x = a.x - b.x, e1y = a.y - b.y, e1z = a.z - b.z;        // v0 - v1
+    const float e2x = c4.x - a.x, e2y = c4.y - a.y, e2z = c4.z - a.z;     // v2 - v0
+    out[0] = make_float4(a.x, a.y, a.z, 0.f);
+    out[1] = make_float4(e1x, e1y, e1z, 0.f);
+    out[2] = make_float4(e2x, e2y, e2z, 0.f);
+    out[3] = make_float4(e1y * e2z - e2y * e1z, e1z * e2x - e2z * e1x, e1x * e2y - e2x * e1y, 0.f);  // e1 x e2
+}
 __device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, u32 id, const RayRegs& r) {
-    const float4* t = tris + (size_t)id * 3;
-    float4 a = __ldg(t), b = __ldg(t + 1), c4 = __ldg(t + 2);
-    float e1x = a.x - b.x, e1y = a.y - b.y, e1z = a.z - b.z;        // v0 - v1
-    float e2x = c4.x - a.x, e2y = c4.y - a.y, e2z = c4.z - a.z;     // v2 - v0
-    float nx = e1y * e2z - e2y * e1z, ny = e1z * e2x - e2z * e1x, nz = e1x * e2y - e2x * e1y;  // e1 x e2
+    const float4* t = tris + (size_t)id * RT_TRI_VEC4;
+    const float4 a = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2), n = __ldg(t + 3);
     float cx = a.x - r.ox, cy = a.y - r.oy, cz = a.z - r.oz;        // v0 - origin
     float rx = r.dy * cz - cy * r.dz, ry = r.dz * cx - cz * r.dx, rz = r.dx * cy - cx * r.dy;  // d x c
-    float inv_det = 1.0f / ((nx * r.dx + ny * r.dy) + nz * r.dz);
-    float u = ((rx * e2x + ry * e2y) + rz * e2z) * inv_det;
-    float v = ((rx * e1x + ry * e1y) + rz * e1z) * inv_det;
+    float inv_det = 1.0f / ((n.x * r.dx + n.y * r.dy) + n.z * r.dz);
+    float u = ((rx * e2.x + ry * e2.y) + rz * e2.z) * inv_det;
+    float v = ((rx * e1.x + ry * e1.y) + rz * e1.z) * inv_det;
     float w = 1.0f - u - v;
     u32 sign = __float_as_uint(u) | __float_as_uint(v) | __float_as_uint(w);
     bool valid = (inv_det != 0.0f) && ((sign & 0x80000000u) == 0);
     if (valid) {
-        float tt = ((nx * cx + ny * cy) + nz * cz) * inv_det;
+        float tt = ((n.x * cx + n.y * cy) + n.z * cz) * inv_det;
         if (tt >= r.tmin && tt <= r.tmax) return tt;
     }
     return __int_as_float(0x7f800000);
@@ -612,13 +622,16 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
     trav_flush_counters<COUNT>(counters, nodes_visited, tris_tested);
 }
 
-// examples/obj_cwbvh.rs:63-67: bvh_tris[i] = tris[primitive_indices[i]]
-__global__ void permute_tris_kernel(const float4* __restrict__ tris, const u32* __restrict__ prim_idx, float4* __restrict__ out,
-                                    size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread, 3 per triangle
-    if (i >= n * 3) return;
-    size_t t = i / 3, k = i - t * 3;
-    out[i] = __ldg(tris + (size_t)prim_idx[t] * 3 + k);
+// examples/obj_cwbvh.rs:63-67: bvh_tris[i] = tris[primitive_indices[i]], stored as RtTriangle::new(v0, v1, v2) (rt_triangle.rs:171-183)
+__global__ void __launch_bounds__(256) permute_tris_kernel(const float4* __restrict__ tris, const u32* __restrict__ prim_idx,
+                                                           float4* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* src = tris + (size_t)prim_idx[i] * 3;
+    float4 rt[4];
+    rt_triangle_of(__ldg(src), __ldg(src + 1), __ldg(src + 2), rt);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[i * RT_TRI_VEC4 + k] = rt[k];
 }
 
 // ray.rs:6-12, 34-52
@@ -782,9 +795,9 @@ int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTrian
     const size_t n = bvh->prim_count;
     if (n == 0) return OBVHS_OK;
     (void)n_tris;  // indices are < n_tris by construction of the builders; uploaded trees are the caller's responsibility
-    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * sizeof(ObvhsTriangle)));
-    permute_tris_kernel<<<div_up(n * 3, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
-                                                                    reinterpret_cast<float4*>(bvh->bvh_tris), n);
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * OBVHS_RT_TRIANGLE_BYTES));
+    permute_tris_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
+                                                                reinterpret_cast<float4*>(bvh->bvh_tris), n);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
@@ -801,9 +814,9 @@ int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTri
     }
     n = bvh->prim_count;
     if (n == 0) return OBVHS_OK;
-    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * sizeof(ObvhsTriangle)));
-    permute_tris_kernel<<<div_up(n * 3, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
-                                                                    reinterpret_cast<float4*>(bvh->bvh_tris), n);
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&bvh->bvh_tris, n * OBVHS_RT_TRIANGLE_BYTES));
+    permute_tris_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_tris), bvh->primitive_indices,
+                                                                reinterpret_cast<float4*>(bvh->bvh_tris), n);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }

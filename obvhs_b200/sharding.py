@@ -45,7 +45,7 @@ def broadcast_cwbvh(bvh, ctx, src: int = 0):
     """Replicate a finished CwBvh (built on rank `src`; pass None elsewhere) to every rank's GPU.
 
     Three NCCL broadcasts straight out of / into the library's device buffers: nodes (80*M B), primitive_indices (4*N B),
-    permuted triangles (48*N B). Returns this rank's CwBvh handle."""
+    permuted triangles (64*N B, RtTriangle form). Returns this rank's CwBvh handle."""
     import torch.distributed as dist
 
     from . import api
@@ -62,11 +62,12 @@ def broadcast_cwbvh(bvh, ctx, src: int = 0):
     dist.broadcast(meta, src=src)
     m = meta.tolist()
     node_count, prim_count, has_tris, total = int(m[0]), int(m[1]), bool(m[2]), m[3:]
+    tri_bytes = int(ctx.lib.obvhs_cuda_cwbvh_triangle_bytes())  # the handle keeps 64-byte RtTriangles
     if rank != src:
         bvh = api.CwBvh.alloc(node_count, prim_count, has_tris, np.asarray(total, np.float32), ctx=ctx)
         nodes_p, prims_p, tris_p = bvh.device_ptrs()
     ctx.synchronize()
-    for ptr, nbytes in ((nodes_p, node_count * 80), (prims_p, prim_count * 4), (tris_p if has_tris else 0, prim_count * 48)):
+    for ptr, nbytes in ((nodes_p, node_count * 80), (prims_p, prim_count * 4), (tris_p if has_tris else 0, prim_count * tri_bytes)):
         if ptr and nbytes:
             dist.broadcast(device_bytes_tensor(ptr, nbytes, ctx.device), src=src)
     return bvh
