@@ -220,6 +220,14 @@ struct ObvhsCwBvh {
         CU_TRY(ctx, cudaGetLastError());       \
     } while (0)
 
+// One-time per-kernel set-up (cudaFuncSetAttribute, occupancy queries) is PER DEVICE: the flags are indexed by device ordinal so a
+// process that drives several GPUs through several contexts configures every one of them.
+template <class T>
+struct PerDevice {
+    T v[64] = {};
+    T& operator[](int device) { return v[device & 63]; }
+};
+
 static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 // Scratch from the context's arena (see ObvhsContext). Released in bulk when the API call that allocated it returns.

@@ -635,7 +635,8 @@ void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGl
 template <int R>
 cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, Node32* bvh_nodes, signed char* merge, PlocGlobals* g, int parity,
                        u32 depth, u32 thr, u64* scan_status, const u32* free_slots, u32 insert_start) {
-    static int per_sm = 0;
+    static PerDevice<int> per_sm_dev;
+    int& per_sm = per_sm_dev[ctx->device];
     if (per_sm == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_mid_kernel<R>, SEARCH_TILE, 0);
         if (e != cudaSuccess) return e;
@@ -651,7 +652,8 @@ template <int R>
 cudaError_t launch_tail(ObvhsContext* ctx, const Node32* cur, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth, u32 thr,
                         const u32* free_slots, u32 insert_start) {
     constexpr int smem = 2 * PLOC_TAIL * (int)sizeof(Node32);
-    static bool attr = false;
+    static PerDevice<bool> attr_dev;
+    bool& attr = attr_dev[ctx->device];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(ploc_tail_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

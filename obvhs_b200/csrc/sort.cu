@@ -362,7 +362,8 @@ __global__ void __launch_bounds__(THREADS) block_sort_kernel(const K* __restrict
 template <typename K, int THREADS>
 static int launch_block_sort(ObvhsContext* ctx, const K* keys, const u32* vals, K* keys_alt, u32* vals_alt, u32 n, int passes) {
     using Cfg = BlockSortCfg<K, THREADS>;
-    static bool attr = false;
+    static PerDevice<bool> attr_dev;
+    bool& attr = attr_dev[ctx->device];
     if (!attr) {
         CU_TRY(ctx, cudaFuncSetAttribute(block_sort_kernel<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr = true;
@@ -407,9 +408,9 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
     u32* goffs = ghist + (size_t)passes * 256;
     u32* ticket = goffs + (size_t)passes * 256;
     u32* status = ticket + 8;
-    static bool attr_set[2] = {false, false};
-    const int which = sizeof(K) == 8 ? 1 : 0;
-    if (!attr_set[which]) {
+    static PerDevice<bool> attr_dev;  // (one instance per key type: this is a template)
+    bool& attr_ok = attr_dev[ctx->device];
+    if (!attr_ok) {
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
         CU_TRY(ctx, cudaFuncSetAttribute(sort_mid_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<K>()));
@@ -417,15 +418,16 @@ int radix_sort_pairs(ObvhsContext* ctx, K* keys, K* keys_alt, u32* vals, u32* va
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU_TRY(ctx, cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU_TRY(ctx, cudaFuncSetAttribute(sort_mid_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set[which] = true;
+        attr_ok = true;
     }
     if (n <= SORT_MID_MAX) {
-        static int per_sm[2] = {0, 0};
-        if (per_sm[which] == 0) {
-            CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[which], sort_mid_kernel<K>, SORT_THREADS, onesweep_smem<K>()));
-            if (per_sm[which] < 1) per_sm[which] = 1;
+        static PerDevice<int> per_sm_dev;
+        int& per_sm = per_sm_dev[ctx->device];
+        if (per_sm == 0) {
+            CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_mid_kernel<K>, SORT_THREADS, onesweep_smem<K>()));
+            if (per_sm < 1) per_sm = 1;
         }
-        const int blocks = (int)std::min<size_t>((size_t)per_sm[which] * ctx->sm_count, tiles);
+        const int blocks = (int)std::min<size_t>((size_t)per_sm * ctx->sm_count, tiles);
         u32 un = (u32)n, utiles = (u32)tiles;
         void* args[] = {&keys, &keys_alt, &vals, &vals_alt, &un, &passes, &ghist, &status, &utiles};
         CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)sort_mid_kernel<K>, dim3(blocks), dim3(SORT_THREADS), args, onesweep_smem<K>(), ctx->stream));
