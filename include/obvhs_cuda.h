@@ -85,8 +85,8 @@ const char* obvhs_cuda_last_error(const ObvhsContext* ctx);
 int obvhs_cuda_synchronize(ObvhsContext* ctx);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx);
-/* Tuning knobs that do not change any result. key "traverse": "auto" (default: a device-side probe of the batch picks the
- * kernel), "static" (one ray per thread) or "persistent[:refill[:chunk]]" (persistent warps refilled from a ray cursor when
+/* Tuning knobs that do not change any result. key "traverse": "auto" (default: every 128-ray block of the batch is
+ * judged on the device and goes to the kernel that suits it), "static" (one ray per thread) or "persistent[:refill[:chunk]]" (persistent warps refilled from a ray cursor when
  * `refill` of 32 lanes have finished, `chunk` consecutive rays per fetch). key "trace": "1"/"0" stage timing on stderr
  * (the reference's scope!/timeit! macros, lib.rs:158-205). Environment: OBVHS_TRAVERSE, OBVHS_TRACE set the defaults. */
 int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value);

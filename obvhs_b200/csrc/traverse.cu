@@ -151,31 +151,26 @@ __device__ __forceinline__ u32 node_intersect(const uint4 q0, const uint4 q1, co
     return node_children<true>(q1, q2, q3, q4, rdx, rdy, rdz, adx, ady, adz, cx, cy, cz, aox, aoy, aoz, r.tmax, oct_inv4, magic);
 }
 
-// ---- batch coherence probe (auto mode) ------------------------------------------------------------------------
+// ---- coherence vote (auto mode) --------------------------------------------------------------------------------
 // Which kernel is faster depends on whether the 32 rays of a warp do similar work. Measured on B200: primary camera rays
-// (kitchen) run 8-25 % faster one-ray-per-thread; bounce / random rays run 2.3x faster on the persistent refill kernel.
-// The probe looks at up to 1024 evenly spaced groups of 32 consecutive rays: a group is coherent when every direction is
-// within ~25 degrees of lane 0's and every origin within 2 % of the scene diagonal of lane 0's. probe[0] = coherent
-// groups, probe[1] = groups sampled; both kernels are launched and the one not selected exits at once.
-__device__ __forceinline__ bool probe_says_coherent(const u32* __restrict__ probe) {
-    return __ldg(probe) * 10u >= __ldg(probe + 1) * 6u;
-}
-__global__ void __launch_bounds__(128) ray_coherence_kernel(const float4* __restrict__ rays, size_t n_groups, size_t stride, float max_dist2,
-                                                            u32* __restrict__ probe) {
-    const size_t g = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5));
-    if (g * stride >= n_groups) return;  // warp-uniform
-    const size_t i = g * stride * 32 + (threadIdx.x & 31u);
-    const float4 o = __ldg(rays + i * 4), d = __ldg(rays + i * 4 + 1);
-    const float ox = __shfl_sync(0xffffffffu, o.x, 0), oy = __shfl_sync(0xffffffffu, o.y, 0), oz = __shfl_sync(0xffffffffu, o.z, 0);
-    const float dx = __shfl_sync(0xffffffffu, d.x, 0), dy = __shfl_sync(0xffffffffu, d.y, 0), dz = __shfl_sync(0xffffffffu, d.z, 0);
-    const float dot = d.x * dx + d.y * dy + d.z * dz, l2 = d.x * d.x + d.y * d.y + d.z * d.z, l02 = dx * dx + dy * dy + dz * dz;
-    const float ex = o.x - ox, ey = o.y - oy, ez = o.z - oz;
-    const bool ok = dot > 0.0f && dot * dot >= 0.82f * l2 * l02 && (ex * ex + ey * ey + ez * ez) <= max_dist2;
-    const bool all = __all_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31u) == 0) {
-        if (all) atomicAdd(probe, 1u);
-        atomicAdd(probe + 1, 1u);
-    }
+// (kitchen) run 25-40 % faster one-ray-per-thread; bounce / random rays run 2-3x faster on the persistent refill kernel.
+// The one-ray-per-thread kernel is launched over the whole batch and every CTA votes on its own 128 rays: a warp is coherent
+// when every direction is within ~25 degrees of lane 0's and every origin within 2 % of the scene diagonal of lane 0's.
+// A CTA with an incoherent warp appends its index to the deferred list and exits; the persistent kernel, launched right
+// behind, takes the rays of the deferred CTAs (and exits at once when there are none). No separate probe pass, and a batch
+// that mixes camera and bounce rays gets each part on the kernel that suits it.
+struct DeferList {
+    u32* count;   // number of deferred 128-ray blocks
+    u32* blocks;  // their indices, in arrival order
+    float max_dist2;
+};
+__device__ __forceinline__ bool warp_is_coherent(const RayRegs& r, bool valid, float max_dist2) {
+    const float ox = __shfl_sync(0xffffffffu, r.ox, 0), oy = __shfl_sync(0xffffffffu, r.oy, 0), oz = __shfl_sync(0xffffffffu, r.oz, 0);
+    const float dx = __shfl_sync(0xffffffffu, r.dx, 0), dy = __shfl_sync(0xffffffffu, r.dy, 0), dz = __shfl_sync(0xffffffffu, r.dz, 0);
+    const float dot = r.dx * dx + r.dy * dy + r.dz * dz, l2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz, l02 = dx * dx + dy * dy + dz * dz;
+    const float ex = r.ox - ox, ey = r.oy - oy, ez = r.oz - oz;
+    const bool ok = !valid || (dot > 0.0f && dot * dot >= 0.82f * l2 * l02 && (ex * ex + ey * ey + ez * ez) <= max_dist2);
+    return __all_sync(0xffffffffu, ok);
 }
 
 // ---- per-ray state machines ---------------------------------------------------------------------------------------
@@ -553,14 +548,22 @@ __device__ __forceinline__ void trav_flush_counters(unsigned long long* __restri
 // One ray per thread: the fastest form for coherent batches (primary / shadow rays of neighbouring pixels).
 template <class Tree, int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                       unsigned long long* __restrict__ counters, const u32* __restrict__ probe) {
-    if (probe && !probe_says_coherent(probe)) return;  // auto mode: the persistent kernel handles this batch
+                                                       unsigned long long* __restrict__ counters, const DeferList defer) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 nodes_visited = 0, tris_tested = 0;
-    if (i < n) {
-        typename Tree::State st;
-        typename Tree::StackT stack[Tree::STACK];
-        tree.begin(st, rays + i * 4);
+    typename Tree::State st;
+    typename Tree::StackT stack[Tree::STACK];
+    const bool valid = i < n;
+    if (valid) tree.begin(st, rays + i * 4);
+    bool mine = valid;
+    if (defer.count) {  // auto mode: vote, hand the block over to the persistent kernel when one of its warps is incoherent
+        const bool coherent = warp_is_coherent(st.r, valid, defer.max_dist2);
+        if (!__syncthreads_and(coherent)) {
+            if (threadIdx.x == 0) defer.blocks[atomicAdd(defer.count, 1u)] = blockIdx.x;
+            mine = false;
+        }
+    }
+    if (mine) {
         while (!tree.template step<MODE, COUNT, OBVHS_STATIC_ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
         }
         result_store<MODE>(st.o, out, i);
@@ -573,11 +576,17 @@ __global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const fl
 // instead of idling until its longest ray ends (measured on the 10M-triangle soup with the one-ray-per-thread kernel:
 // 5.8 of 32 lanes active per issued instruction, issue slots 75 % busy -- divergence-bound, not memory-bound). Every ray
 // still runs the reference's exact per-ray state machine, so results and counters are identical to traverse_kernel's.
-template <class Tree, int MODE, bool COUNT, int REFILL>
+template <class Tree, int MODE, bool COUNT, int REFILL, bool DEFER>
 __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n, void* __restrict__ out,
                                                                   unsigned long long* __restrict__ counters, u32* __restrict__ next_ray, u32 chunk,
-                                                                  const u32* __restrict__ probe) {
-    if (probe && probe_says_coherent(probe)) return;  // auto mode: the one-ray-per-thread kernel handles this batch
+                                                                  const DeferList defer) {
+    // auto mode: only the rays of the 128-ray blocks the one-ray-per-thread kernel deferred (slot k of the list covers the
+    // virtual indices [128 k, 128 k + 128)); otherwise the whole batch
+    const u32 n_rays = n;
+    if (DEFER) {  // (a separate instantiation: the extra live values cost the plain kernel a CTA per SM)
+        n = __ldcg(defer.count) * 128u;
+        if (n == 0) return;
+    }
     constexpr bool ONE_TRI = OBVHS_PERSISTENT_ONE_TRI;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -604,8 +613,11 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
                 const u32 rank = __popc(idle & lt_mask);
                 if (rank < take) {
                     my = chunk_pos + rank;
-                    tree.begin(st, rays + (size_t)my * 4);
-                    active = true;
+                    if (DEFER) my = __ldcg(defer.blocks + (my >> 7)) * 128u + (my & 127u);
+                    if (!DEFER || my < n_rays) {  // (the last block of a batch may be partial)
+                        tree.begin(st, rays + (size_t)my * 4);
+                        active = true;
+                    }
                 }
             }
             chunk_pos += take;
@@ -655,60 +667,68 @@ __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float t
 
 template <class Tree, int MODE, bool COUNT, int REFILL>
 static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, void* d_out, unsigned long long* c, u32* next,
-                               const u32* probe) {
+                               const DeferList& defer) {
     int per_sm = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL>, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-    size_t blocks = (size_t)ctx->sm_count * per_sm, need = (n + 127) / 128;
-    if (blocks > need) blocks = need;
-    traverse_persistent_kernel<Tree, MODE, COUNT, REFILL><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
-                                                                                                      (u32)ctx->traverse_chunk, probe);
+    size_t need = (n + 127) / 128;
+    if (defer.count) {
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, true>, 128, 0));
+        size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (blocks > need) blocks = need;
+        traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
+                                                                                                                (u32)ctx->traverse_chunk, defer);
+    } else {
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, false>, 128, 0));
+        size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (blocks > need) blocks = need;
+        traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
+                                                                                                                 (u32)ctx->traverse_chunk, defer);
+    }
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
 template <class Tree, int REFILL>
 static int launch_persistent_r(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
-                               u32* next, const u32* probe) {
+                               u32* next, const DeferList& defer) {
     if (c) {
-        if (mode == 0) return launch_persistent_t<Tree, 0, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
-        if (mode == 1) return launch_persistent_t<Tree, 1, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
-        return launch_persistent_t<Tree, 2, true, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+        if (mode == 0) return launch_persistent_t<Tree, 0, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+        if (mode == 1) return launch_persistent_t<Tree, 1, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+        return launch_persistent_t<Tree, 2, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
     }
-    if (mode == 0) return launch_persistent_t<Tree, 0, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
-    if (mode == 1) return launch_persistent_t<Tree, 1, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
-    return launch_persistent_t<Tree, 2, false, REFILL>(ctx, tree, rays, n, d_out, c, next, probe);
+    if (mode == 0) return launch_persistent_t<Tree, 0, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+    if (mode == 1) return launch_persistent_t<Tree, 1, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+    return launch_persistent_t<Tree, 2, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
 }
 template <class Tree>
 static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
-                             u32* next, const u32* probe) {
+                             u32* next, const DeferList& defer) {
     switch (ctx->traverse_refill) {
-        case 1: return launch_persistent_r<Tree, 1>(ctx, tree, rays, n, mode, d_out, c, next, probe);
-        case 4: return launch_persistent_r<Tree, 4>(ctx, tree, rays, n, mode, d_out, c, next, probe);
-        case 16: return launch_persistent_r<Tree, 16>(ctx, tree, rays, n, mode, d_out, c, next, probe);
-        case 32: return launch_persistent_r<Tree, 32>(ctx, tree, rays, n, mode, d_out, c, next, probe);
-        default: return launch_persistent_r<Tree, 8>(ctx, tree, rays, n, mode, d_out, c, next, probe);
+        case 1: return launch_persistent_r<Tree, 1>(ctx, tree, rays, n, mode, d_out, c, next, defer);
+        case 4: return launch_persistent_r<Tree, 4>(ctx, tree, rays, n, mode, d_out, c, next, defer);
+        case 16: return launch_persistent_r<Tree, 16>(ctx, tree, rays, n, mode, d_out, c, next, defer);
+        case 32: return launch_persistent_r<Tree, 32>(ctx, tree, rays, n, mode, d_out, c, next, defer);
+        default: return launch_persistent_r<Tree, 8>(ctx, tree, rays, n, mode, d_out, c, next, defer);
     }
 }
 template <class Tree>
 static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
-                         const u32* probe) {
+                         const DeferList& defer) {
     dim3 block(128), grid(div_up(n, 128));
     cudaStream_t s = ctx->stream;
     if (c) {
-        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
-        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
-        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
     } else {
-        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
-        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
-        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, probe);
+        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
     }
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
 
 // Kernel choice shared by both tree types. ctx->traverse_mode: 0 static (one ray per thread), 1 persistent refill, 2 auto
-// (a probe of the batch decides on the device; small batches are static).
+// (every 128-ray block votes on the device, see DeferList; small batches are static).
 constexpr size_t AUTO_STATIC_MAX_PRIMS = 262144;
 template <class Tree>
 static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, size_t prim_count, const float4* rays, size_t n,
@@ -719,36 +739,34 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     if (tm == 2 && n < 16384) tm = 0;
     // Large scenes: even camera rays vary a lot in work per ray (depth complexity, cache misses), and the refill kernel wins
     // regardless of coherence (terrain, jittered primary rays: +3 % at 0.3 M triangles, +16 % at 1 M, +41 % at 3 M, +36 % at
-    // 10 M; the 57 k-triangle kitchen is 41 % faster one-ray-per-thread). The probe only decides for small scenes.
+    // 10 M; the 57 k-triangle kitchen is 41 % faster one-ray-per-thread). The vote only decides for small scenes.
     if (tm == 2 && prim_count > AUTO_STATIC_MAX_PRIMS) tm = 1;
     // 32-bit ray indices inside the persistent kernel: batches beyond 2^31 rays are split into several launches
     const size_t MAX_LAUNCH = (size_t)1 << 31;
     const size_t out_elem = mode == 0 ? sizeof(ObvhsRayHit) : (mode == 1 ? 1 : 4);
     const size_t n_launches = (n + MAX_LAUNCH - 1) / MAX_LAUNCH;
-    DevBuf<u32> scratch;  // [0..1] probe votes, [2..] one ray cursor per persistent launch
-    u32* probe = nullptr;
-    if (tm != 0) {
-        CU_TRY(ctx, scratch.alloc(2 + n_launches, s));
-        CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, (2 + n_launches) * sizeof(u32), s));
-    }
-    if (tm == 2) {
-        probe = scratch.p;
-        const size_t n_groups = n / 32, stride = n_groups > 1024 ? n_groups / 1024 : 1, sampled = (n_groups + stride - 1) / stride;
-        const float dx = total_aabb.max[0] - total_aabb.min[0], dy = total_aabb.max[1] - total_aabb.min[1],
-                    dz = total_aabb.max[2] - total_aabb.min[2];
-        float diag2 = dx * dx + dy * dy + dz * dz;
-        if (!(diag2 > 0.0f) || !(diag2 < 3.0e38f)) diag2 = 3.0e38f;  // unknown scene extent (uploaded tree): directions decide
-        ray_coherence_kernel<<<div_up(sampled, 4), 128, 0, s>>>(rays, n_groups, stride, diag2 * 0.0004f, probe);
-        KERNEL_CHECK(ctx);
-    }
-    if (tm != 0) {
+    if (tm == 2 && n_launches > 1) tm = 1;
+    const DeferList none{nullptr, nullptr, 0.f};
+    if (tm == 0) return launch_static(ctx, tree, rays, n, mode, d_out, c, none);
+    // scratch: [0] deferred block count, [1] unused, [2..] one ray cursor per persistent launch, then the deferred block list
+    const size_t n_blocks = tm == 2 ? (n + 127) / 128 : 0;
+    DevBuf<u32> scratch;
+    CU_TRY(ctx, scratch.alloc(2 + n_launches + n_blocks, s));
+    CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, (2 + n_launches) * sizeof(u32), s));
+    if (tm == 1) {
         for (size_t l = 0; l < n_launches; l++) {
             const size_t off = l * MAX_LAUNCH, cnt = n - off < MAX_LAUNCH ? n - off : MAX_LAUNCH;
-            ST_TRY(launch_persistent(ctx, tree, rays + off * 4, cnt, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, probe));
+            ST_TRY(launch_persistent(ctx, tree, rays + off * 4, cnt, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, none));
         }
-        if (tm == 1) return OBVHS_OK;
+        return OBVHS_OK;
     }
-    return launch_static(ctx, tree, rays, n, mode, d_out, c, probe);
+    const float dx = total_aabb.max[0] - total_aabb.min[0], dy = total_aabb.max[1] - total_aabb.min[1],
+                dz = total_aabb.max[2] - total_aabb.min[2];
+    float diag2 = dx * dx + dy * dy + dz * dz;
+    if (!(diag2 > 0.0f) || !(diag2 < 3.0e38f)) diag2 = 3.0e38f;  // unknown scene extent (uploaded tree): directions decide
+    const DeferList defer{scratch.p, scratch.p + 2 + n_launches, diag2 * 0.0004f};
+    ST_TRY(launch_static(ctx, tree, rays, n, mode, d_out, c, defer));
+    return launch_persistent(ctx, tree, rays, n, mode, d_out, c, scratch.p + 2, defer);
 }
 
 int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,

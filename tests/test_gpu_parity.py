@@ -278,7 +278,7 @@ TRAVERSE_MODES = ["auto", "static", "persistent:8:32", "persistent:1:32", "persi
 @pytest.mark.parametrize("mode", TRAVERSE_MODES)
 @pytest.mark.parametrize("scene", SCENES)
 def test_traversal_hits_bit_exact(api, scenes, scene, mode):
-    # every kernel variant (one ray per thread, persistent warps with ray refill, and the probe-driven choice between
+    # every kernel variant (one ray per thread, persistent warps with ray refill, and the per-block choice between
     # them) runs the reference's per-ray state machine: hits, distances AND the visit counters are identical
     tris = scenes[scene]
     c = ob.build_cwbvh_from_tris(tris, "fast_build")
