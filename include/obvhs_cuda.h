@@ -57,6 +57,10 @@ typedef struct {
     float origin[3]; float _pad0; float direction[3]; float _pad1; float inv_direction[3]; float _pad2;
     float tmin, tmax; float _pad3[2];
 } ObvhsRay;
+/* The arguments of Ray::new(origin, direction, min, max) (src/ray.rs:34-52), 32 bytes: what a caller holds BEFORE the
+ * constructor fills inv_direction. The *_ray_new_* entry points run the constructor on the device (safe_inverse,
+ * ray.rs:6-12, bit for bit), so a host batch crosses PCIe at half the size of the Ray array. */
+typedef struct { float origin[3]; float tmin; float direction[3]; float tmax; } ObvhsRayNew;
 /* src/ray.rs:63-70; RayHit::none() = ids 0xffffffff, t = +inf */
 typedef struct { uint32_t primitive_id, geometry_id, instance_id; float t; } ObvhsRayHit;
 
@@ -264,6 +268,21 @@ int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const Ob
  * counters[0] += nodes visited, counters[1] += triangles tested (host or device pointer to 2 x u64). */
 int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
                                                 ObvhsRayHit* hits, uint64_t* counters);
+/* Ray::new (src/ray.rs:34-52) for n argument records -> n Ray structs (host or device pointers). */
+int obvhs_cuda_ray_new_batch(ObvhsContext* ctx, const ObvhsRayNew* args, size_t n, ObvhsRay* rays);
+/* ray_traverse / ray_traverse_miss / ray_traverse_anyhit of rays[i] = Ray::new(args[i]): identical results to the *_batch
+ * calls above on obvhs_cuda_ray_new_batch's output; the constructor runs on the device chunk by chunk inside the pipelined
+ * H2D -> traversal -> D2H of a host batch. */
+int obvhs_cuda_cwbvh_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n,
+                                            ObvhsRayHit* hits);
+int obvhs_cuda_cwbvh_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n,
+                                                 uint8_t* miss);
+int obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args,
+                                                         size_t n, uint32_t* counts);
+int obvhs_cuda_bvh2_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n,
+                                           ObvhsRayHit* hits);
+int obvhs_cuda_bvh2_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n,
+                                                uint8_t* miss);
 /* ---- broad-phase queries (batched; the per-report closure of the reference becomes a list of reports) ---------------
  * Bvh2::aabb_traverse(aabb, eval) / Bvh2::point_traverse(point, eval)  (src/bvh2/mod.rs:365-456) for n queries with an eval
  * that always continues: counts[i] = number of leaf nodes reported for query i; leaf_ids receives the reported leaf NODE

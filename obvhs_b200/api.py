@@ -114,6 +114,12 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_ray_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "obvhs_cuda_ray_new_batch": (_i32, [_vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_new_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_new_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_ray_new_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_bvh2_ray_new_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_bvh2_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_bvh2_point_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_cwbvh_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
@@ -160,6 +166,14 @@ def _as_f32(x, cols):
         a = a.reshape(0, cols)
     assert a.ndim == 2 and a.shape[1] == cols, a.shape
     return a
+
+
+def _as_rays(x):
+    """(n,16) float32 = Ray structs, (n,8) float32 = Ray::new arguments (types.make_ray_args) -> (array, is_args)."""
+    cols = int(x.shape[1]) if getattr(x, "ndim", 0) == 2 or (_is_torch(x) and x.dim() == 2) else 16
+    if cols == 8:
+        return _as_f32(x, 8), True
+    return _as_f32(x, 16), False
 
 
 class Context:
@@ -368,10 +382,13 @@ class Bvh2:
 
     def ray_traverse(self, rays, out=None, counters=None):
         """Batched Bvh2::ray_traverse (src/bvh2/mod.rs:148-172); returns / fills a RAY_HIT array (or an (n,4) int32 device tensor)."""
-        r = _as_f32(rays, 16)
+        r, is_args = _as_rays(rays)
         n = r.shape[0]
         hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
-        if counters is None:
+        if is_args:
+            assert counters is None
+            self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_new_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
+        elif counters is None:
             self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
         else:
             self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
@@ -379,10 +396,11 @@ class Bvh2:
 
     def ray_traverse_miss(self, rays, out=None):
         """src/bvh2/mod.rs:185-213"""
-        r = _as_f32(rays, 16)
+        r, is_args = _as_rays(rays)
         n = r.shape[0]
         miss = out if out is not None else np.zeros(n, dtype=np.uint8)
-        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_miss_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
+        fn = self.ctx.lib.obvhs_cuda_bvh2_ray_new_traverse_miss_batch if is_args else self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_miss_batch
+        self.ctx.check(fn(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
         return miss
 
     def ray_traverse_anyhit_count(self, rays, out=None):
@@ -635,27 +653,32 @@ class CwBvh:
 
         `out` may be a torch CUDA tensor of shape (n, 4) int32/float32-viewable (16 bytes per ray) to keep hits on device.
         counters: optional np.uint64[2] (or device tensor) accumulating nodes visited / triangles tested."""
-        r = _as_f32(rays, 16)
+        r, is_args = _as_rays(rays)
         n = r.shape[0]
         hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
-        if counters is None:
+        if is_args:  # (n,8) Ray::new arguments: the constructor runs on the device
+            assert counters is None
+            self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_new_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
+        elif counters is None:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
         else:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
         return hits
 
     def ray_traverse_miss(self, rays, out=None):
-        r = _as_f32(rays, 16)
+        r, is_args = _as_rays(rays)
         n = r.shape[0]
         miss = out if out is not None else np.zeros(n, dtype=np.uint8)
-        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_miss_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
+        fn = self.ctx.lib.obvhs_cuda_cwbvh_ray_new_traverse_miss_batch if is_args else self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_miss_batch
+        self.ctx.check(fn(self.ctx.h, self.h, _ptr(r), n, _ptr(miss)))
         return miss
 
     def ray_traverse_anyhit_count(self, rays, out=None):
-        r = _as_f32(rays, 16)
+        r, is_args = _as_rays(rays)
         n = r.shape[0]
         counts = out if out is not None else np.zeros(n, dtype=np.uint32)
-        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(counts)))
+        fn = self.ctx.lib.obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch if is_args else self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch
+        self.ctx.check(fn(self.ctx.h, self.h, _ptr(r), n, _ptr(counts)))
         return counts
 
 
@@ -729,4 +752,14 @@ def make_rays(origin_dir, tmin=0.0, tmax=3.4028234663852886e38, out=None, ctx: C
     n = od.shape[0]
     rays = out if out is not None else np.zeros((n, 16), dtype=np.float32)
     ctx.check(ctx.lib.obvhs_cuda_make_rays(ctx.h, _ptr(od), n, float(tmin), float(tmax), _ptr(rays)))
+    return rays
+
+
+def ray_new(args, out=None, ctx: Context | None = None):
+    """Ray::new (src/ray.rs:34-52) for n argument records ((n,8) float32, types.make_ray_args) -> (n,16) Ray array."""
+    ctx = ctx or default_context()
+    a = _as_f32(args, 8)
+    n = a.shape[0]
+    rays = out if out is not None else np.zeros((n, 16), dtype=np.float32)
+    ctx.check(ctx.lib.obvhs_cuda_ray_new_batch(ctx.h, _ptr(a), n, _ptr(rays)))
     return rays

@@ -11,6 +11,7 @@ int bvh2_pack_nodes_device(ObvhsContext* ctx, const ObvhsBvh2Node* d_in, size_t 
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <type_traits>
 cudaError_t obvhs_result_alloc(ObvhsContext* ctx, void** p, size_t bytes) {
     const size_t GRAIN = (size_t)2 << 20;
     size_t cap = (bytes + GRAIN - 1) / GRAIN * GRAIN;
@@ -859,6 +860,29 @@ int obvhs_cuda_cwbvh_device_ptrs(const ObvhsCwBvh* bvh, void** nodes, void** pri
 
 }  // extern "C"
 
+// Ray::new(origin, direction, min, max) (ray.rs:34-52) for a batch: the 32-byte constructor arguments become the 64-byte Ray the
+// traversal kernels read. A host batch then crosses PCIe at 32 B per ray instead of 64 (the link, not the kernel, bounds a
+// host-to-host traversal call), and the inverse direction is computed where it is consumed.
+__device__ __forceinline__ float safe_inverse_dev(float x) {  // ray.rs:6-12; signum(+-0) = +-1, NaN stays NaN
+    return fabsf(x) <= 1.1920929e-07f ? copysignf(1.0f, x) / 1.1920929e-07f : 1.0f / x;
+}
+__global__ void __launch_bounds__(256) ray_new_kernel(const float4* __restrict__ args, size_t n, float4* __restrict__ rays) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = __ldg(args + 2 * i), d = __ldg(args + 2 * i + 1);
+    float4* r = rays + 4 * i;
+    r[0] = make_float4(o.x, o.y, o.z, 0.0f);
+    r[1] = make_float4(d.x, d.y, d.z, 0.0f);
+    r[2] = make_float4(safe_inverse_dev(d.x), safe_inverse_dev(d.y), safe_inverse_dev(d.z), 0.0f);
+    r[3] = make_float4(o.w, d.w, 0.0f, 0.0f);
+}
+static int ray_new_device(ObvhsContext* ctx, const ObvhsRayNew* d_args, size_t n, ObvhsRay* d_rays) {
+    if (n == 0) return OBVHS_OK;
+    ray_new_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_args), n, reinterpret_cast<float4*>(d_rays));
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
 // Host-resident ray batches are pipelined in chunks over three streams: H2D of chunk k+1 (copy_in), traversal of chunk k
 // (the context's stream) and D2H of chunk k-1 (copy_out) run concurrently, so a batch costs about max(H2D, kernel, D2H)
 // instead of their sum (PCIe is full duplex). Letting the kernel read pinned host memory directly (zero-copy) measured
@@ -875,13 +899,16 @@ static int ensure_pipeline(ObvhsContext* ctx, size_t n_events) {
 }
 
 // `launch(d_rays, count, d_out, d_counters)` enqueues the traversal of a device-resident slice on ctx->stream
-template <class Launch>
-static int traverse_common(ObvhsContext* ctx, const void* bvh, const ObvhsRay* rays, size_t n, void* out, size_t out_elem, uint64_t* counters,
-                           Launch launch) {
+// RayIn = ObvhsRay (used as it is) or ObvhsRayNew (constructor arguments, expanded on the device chunk by chunk)
+template <class RayIn, class Launch>
+static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count, const RayIn* rays, size_t n, void* out, size_t out_elem,
+                           uint64_t* counters, Launch launch) {
+    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
     ARG_CHECK(ctx, bvh, "bvh is null");
     ARG_CHECK(ctx, n == 0 || (rays && out), "null rays/out");
     if (n == 0) return OBVHS_OK;
     DevBuf<ObvhsRay> st_rays;
+    DevBuf<RayIn> st_in;  // PACKED only: the staged constructor arguments
     DevBuf<unsigned char> st_out;
     DevBuf<u64> st_cnt;
     const bool rays_dev = obvhs_is_device_ptr(rays);
@@ -902,22 +929,29 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, const ObvhsRay* r
             d_cnt = st_cnt.p;
         }
     }
-    const size_t MIN_CHUNK = 32768;
-    if (rays_dev) {
-        ST_TRY(launch(rays, n, d_out, d_cnt));
-        if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
-    } else if (n < 2 * MIN_CHUNK) {
-        const ObvhsRay* d_rays = nullptr;
-        ST_TRY(stage_in(ctx, rays, n, st_rays, &d_rays));
+    const size_t MIN_CHUNK = traverse_host_chunk_min(ctx, prim_count);
+    if (rays_dev || n < 65536 || n < MIN_CHUNK + MIN_CHUNK / 2) {
+        const RayIn* d_in = nullptr;
+        ST_TRY(stage_in(ctx, rays, n, st_in, &d_in));  // (a device pointer passes through)
+        const ObvhsRay* d_rays = reinterpret_cast<const ObvhsRay*>(d_in);
+        if (PACKED) {
+            CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
+            ST_TRY(ray_new_device(ctx, reinterpret_cast<const ObvhsRayNew*>(d_in), n, st_rays.p));
+            d_rays = st_rays.p;
+        }
         ST_TRY(launch(d_rays, n, d_out, d_cnt));
         if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
         CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
+        if (PACKED) CU_TRY(ctx, st_in.alloc(n, ctx->stream));
+        unsigned char* d_stage = PACKED ? reinterpret_cast<unsigned char*>(st_in.p) : reinterpret_cast<unsigned char*>(st_rays.p);
         size_t chunk = (n + 15) / 16;  // ~16 stages: the un-overlapped head and tail are 1/16 of the copy time each
         if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
-        if (chunk > ((size_t)1 << 21)) chunk = (size_t)1 << 21;
-        chunk = (chunk + 127) & ~(size_t)127;
-        const size_t n_chunks = (n + chunk - 1) / chunk;
+        if (chunk > ((size_t)1 << 21) && MIN_CHUNK <= ((size_t)1 << 21)) chunk = (size_t)1 << 21;
+        size_t n_chunks = (n + chunk - 1) / chunk;
+        if (n - (n_chunks - 1) * chunk < chunk / 2 && n_chunks > 1) n_chunks--;  // no runt slice at the end: spread it over the others
+        chunk = ((n + n_chunks - 1) / n_chunks + 127) & ~(size_t)127;
+        n_chunks = (n + chunk - 1) / chunk;
         ST_TRY(ensure_pipeline(ctx, 2 * n_chunks + 2));
         cudaEvent_t* ev = ctx->event_pool.data();
         // the staging areas come from the arena, whose reuse is ordered on ctx->stream: the copy streams start after it
@@ -925,12 +959,18 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, const ObvhsRay* r
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ev[0], 0));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev[0], 0));
         const unsigned char* h_rays = reinterpret_cast<const unsigned char*>(rays);
+        // every H2D slice is queued before the first launch: the copy engine never waits for the host to get through the
+        // launches of the previous slice
+        for (size_t c = 0; c < n_chunks; c++) {
+            const size_t off = c * chunk, cnt = (off + chunk <= n) ? chunk : n - off;
+            CU_TRY(ctx, cudaMemcpyAsync(d_stage + off * sizeof(RayIn), h_rays + off * sizeof(RayIn), cnt * sizeof(RayIn), cudaMemcpyHostToDevice, ctx->copy_in));
+            CU_TRY(ctx, cudaEventRecord(ev[2 + 2 * c], ctx->copy_in));
+        }
         for (size_t c = 0; c < n_chunks; c++) {
             const size_t off = c * chunk, cnt = (off + chunk <= n) ? chunk : n - off;
             cudaEvent_t e_in = ev[2 + 2 * c], e_k = ev[3 + 2 * c];
-            CU_TRY(ctx, cudaMemcpyAsync(st_rays.p + off, h_rays + off * sizeof(ObvhsRay), cnt * sizeof(ObvhsRay), cudaMemcpyHostToDevice, ctx->copy_in));
-            CU_TRY(ctx, cudaEventRecord(e_in, ctx->copy_in));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
+            if (PACKED) ST_TRY(ray_new_device(ctx, reinterpret_cast<const ObvhsRayNew*>(st_in.p) + off, cnt, st_rays.p + off));
             ST_TRY(launch(st_rays.p + off, cnt, (unsigned char*)d_out + off * out_elem, d_cnt));
             if (!out_dev) {
                 CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
@@ -950,10 +990,18 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, const ObvhsRay* r
     return OBVHS_OK;
 }
 
-static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
+template <class RayIn>
+static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
                        uint64_t* counters) {
-    return traverse_common(ctx, bvh, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
         return cwbvh_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
+    });
+}
+template <class RayIn>
+static int b2_traverse(ObvhsContext* ctx, const ObvhsBvh2* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
+                       uint64_t* counters) {
+    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+        return bvh2_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
     });
 }
 extern "C" {
@@ -978,13 +1026,40 @@ int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCw
     return cw_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
 }
 
-// ---- Bvh2 ray traversal, collapse, builder (SURVEY.md 8f rank 1) -----------------------------------------------
-static int b2_traverse(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, int mode, void* out, size_t out_elem,
-                       uint64_t* counters) {
-    return traverse_common(ctx, bvh, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
-        return bvh2_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
-    });
+// ---- the same traversals over Ray::new arguments (32 B per ray) -------------------------------------------------------
+int obvhs_cuda_ray_new_batch(ObvhsContext* ctx, const ObvhsRayNew* args, size_t n, ObvhsRay* rays) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, n == 0 || (args && rays), "null args/rays");
+    if (n == 0) return OBVHS_OK;
+    DevBuf<ObvhsRayNew> st_in;
+    DevBuf<ObvhsRay> st_out;
+    const ObvhsRayNew* d_args = nullptr;
+    ST_TRY(stage_in(ctx, args, n, st_in, &d_args));
+    ObvhsRay* d_rays = rays;
+    if (!obvhs_is_device_ptr(rays)) {
+        CU_TRY(ctx, st_out.alloc(n, ctx->stream));
+        d_rays = st_out.p;
+    }
+    ST_TRY(ray_new_device(ctx, d_args, n, d_rays));
+    if (d_rays != rays) ST_TRY(copy_out(ctx, rays, (const ObvhsRay*)d_rays, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
 }
+int obvhs_cuda_cwbvh_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n, ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, args, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
+}
+int obvhs_cuda_cwbvh_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n, uint8_t* miss) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, args, n, 1, miss, 1, nullptr);
+}
+int obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n,
+                                                         uint32_t* counts) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, args, n, 2, counts, 4, nullptr);
+}
+
+// ---- Bvh2 ray traversal, collapse, builder (SURVEY.md 8f rank 1) -----------------------------------------------
 int obvhs_cuda_bvh2_ray_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits) {
     API_ENTER(ctx);
     return b2_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
@@ -1002,6 +1077,14 @@ int obvhs_cuda_bvh2_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsBvh
     API_ENTER(ctx);
     ARG_CHECK(ctx, counters, "counters is null");
     return b2_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+int obvhs_cuda_bvh2_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n, ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, args, n, 0, hits, sizeof(ObvhsRayHit), nullptr);
+}
+int obvhs_cuda_bvh2_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n, uint8_t* miss) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, args, n, 1, miss, 1, nullptr);
 }
 int obvhs_cuda_bvh2_set_triangles(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* tris, size_t n) {
     API_ENTER(ctx);

@@ -27,6 +27,7 @@ static_assert(sizeof(ObvhsTriangle) == 48, "Triangle");
 static_assert(sizeof(ObvhsBvh2Node) == 48, "Bvh2Node");
 static_assert(sizeof(ObvhsCwBvhNode) == 80, "CwBvhNode");
 static_assert(sizeof(ObvhsRay) == 64, "Ray");
+static_assert(sizeof(ObvhsRayNew) == 32, "RayNew");
 static_assert(sizeof(ObvhsRayHit) == 16, "RayHit");
 
 #define OBVHS_RT_TRIANGLE_BYTES 64  // rt_triangle.rs:160-168 RtTriangle {v0, e1, e2, ng}: the handles' internal triangle layout
@@ -338,4 +339,5 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
 int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters);
 int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris);
+size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count);
 int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays);

@@ -89,3 +89,31 @@ def make_rays(origin, direction, tmin=0.0, tmax=np.float32(3.4028235e38)) -> np.
     rays[:, 12] = np.asarray(tmin, dtype=np.float32)
     rays[:, 13] = np.asarray(tmax, dtype=np.float32)
     return rays
+
+
+RAY_NEW_F32 = 8
+
+
+def make_ray_args(origin, direction, tmin=0.0, tmax=np.float32(3.4028235e38)) -> np.ndarray:
+    """The arguments of `Ray::new(origin, direction, min, max)` (reference src/ray.rs:34-52) for n rays -> (n,8) float32
+    [ox oy oz tmin | dx dy dz tmax] (ObvhsRayNew, 32 bytes). The traversal calls accept it in place of the (n,16) Ray array
+    and run the constructor (safe_inverse) on the device; `ray_new` returns exactly what `make_rays` builds on the host."""
+    direction = np.asarray(direction, dtype=np.float32)
+    n = direction.shape[0]
+    a = np.zeros((n, RAY_NEW_F32), dtype=np.float32)
+    a[:, 0:3] = np.asarray(origin, dtype=np.float32)
+    a[:, 3] = np.asarray(tmin, dtype=np.float32)
+    a[:, 4:7] = direction
+    a[:, 7] = np.asarray(tmax, dtype=np.float32)
+    return a
+
+
+def ray_args_of(rays: np.ndarray) -> np.ndarray:
+    """(n,16) Ray structs -> their (n,8) constructor arguments (drops inv_direction)."""
+    rays = np.asarray(rays, dtype=np.float32)
+    a = np.empty((rays.shape[0], RAY_NEW_F32), dtype=np.float32)
+    a[:, 0:3] = rays[:, 0:3]
+    a[:, 3] = rays[:, 12]
+    a[:, 4:7] = rays[:, 4:7]
+    a[:, 7] = rays[:, 13]
+    return a

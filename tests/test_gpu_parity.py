@@ -489,6 +489,69 @@ def test_traversal_host_batches_are_pipelined_in_chunks(api, scenes, n_side):
     assert np.array_equal(miss.astype(bool), want[:, 3].view(np.float32) >= F32_MAX)
 
 
+def test_ray_new_on_device_is_ray_new_of_the_reference(api):
+    # ray.rs:6-12,34-52: safe_inverse bit for bit, including +-0, denormals, |x| == EPSILON and its neighbours, inf and NaN
+    from obvhs_b200.types import make_ray_args, make_rays as host_ray_new
+
+    eps = np.float32(1.1920929e-07)
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, eps, -eps, np.nextafter(eps, np.float32(1)), np.nextafter(eps, np.float32(0)),
+                        -np.nextafter(eps, np.float32(1)), 1.0, -1.0, 3.0, 1e-7, -1e-7, 1e30, -1e30, 3.4028235e38, np.inf, -np.inf, np.nan], np.float32)
+    rng = np.random.default_rng(11)
+    d = np.concatenate([np.stack([special, np.roll(special, 1), np.roll(special, 7)], axis=1),
+                        rng.standard_normal((5000, 3)).astype(np.float32) * np.float32(1e-6),
+                        rng.standard_normal((5000, 3)).astype(np.float32)], axis=0)
+    o = rng.standard_normal(d.shape).astype(np.float32)
+    tmin = rng.random(d.shape[0], dtype=np.float32)
+    tmax = tmin + rng.random(d.shape[0], dtype=np.float32) * np.float32(100)
+    with np.errstate(all="ignore"):
+        want = host_ray_new(o, d, tmin, tmax)
+    def same(got):  # bit for bit, except that a NaN is any NaN (its payload differs between x86 and the GPU's 1/x)
+        nan = np.isnan(want)
+        return np.array_equal(np.isnan(got), nan) and np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+
+    assert same(api.ray_new(make_ray_args(o, d, tmin, tmax)))
+    import torch
+
+    d_args = torch.from_numpy(make_ray_args(o, d, tmin, tmax)).cuda()
+    d_rays = torch.empty((d.shape[0], 16), dtype=torch.float32, device="cuda")
+    api.ray_new(d_args, out=d_rays)
+    assert same(d_rays.cpu().numpy())
+    assert api.ray_new(np.zeros((0, 8), np.float32)).shape == (0, 16)
+
+
+@pytest.mark.parametrize("n_side", [96, 190])
+def test_traversal_over_ray_new_arguments(api, scenes, n_side):
+    # the *_ray_new_* entry points (32-byte constructor arguments, constructor on the device) give the results of the Ray-struct
+    # calls for every flavour, tree type and buffer placement: small staged batch (n_side 96) and chunked pipeline (190)
+    import torch
+    from obvhs_b200.types import RAY_HIT, ray_args_of
+
+    tris = scenes["kitchen"]
+    rays = rays_for(tris, n_side=n_side)
+    rays[::5, 12] = np.float32(0.25)  # per-ray tmin / tmax survive the packing
+    rays[::7, 13] = np.float32(2.5)
+    args = ray_args_of(rays)
+    assert args.shape[1] == 8
+    c = ob.build_cwbvh_from_tris(tris, "fast_build")
+    bt = c.bvh_tris(tris)
+    want = c.ray_traverse(bt, rays)
+    cw = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build())
+    for a in (args, torch.from_numpy(args).pin_memory().numpy()):
+        got = cw.ray_traverse(a)
+        assert np.array_equal(got["primitive_id"], want["primitive_id"])
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    d_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32, device="cuda")
+    cw.ray_traverse(torch.from_numpy(args).cuda(), out=d_hits)
+    cw.ctx.synchronize()
+    assert np.array_equal(d_hits.cpu().numpy().view(RAY_HIT).reshape(-1)["primitive_id"], want["primitive_id"])
+    assert np.array_equal(cw.ray_traverse_miss(args), c.ray_traverse_miss(bt, rays))
+    assert np.array_equal(cw.ray_traverse_anyhit_count(args), c.ray_traverse_anyhit_count(bt, rays))
+    b2 = api.build_bvh2_from_tris(tris, api.BvhBuildParams.fast_build())
+    assert np.array_equal(b2.ray_traverse(args).view(np.uint32), b2.ray_traverse(rays).view(np.uint32))
+    assert np.array_equal(b2.ray_traverse_miss(args), b2.ray_traverse_miss(rays))
+    assert cw.ray_traverse(np.zeros((0, 8), np.float32)).shape[0] == 0
+
+
 def displaced_aabbs(tris, frame):
     """BASELINE config 5 / SURVEY.md 8(d) S4: every vertex moved by 0.01*(hash_noise-0.5) seeded by the frame."""
     t = tris.reshape(-1, 3, 4).copy()
