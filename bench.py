@@ -255,6 +255,8 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
     stream = torch.cuda.Stream(device=dev)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
+    if os.environ.get("OBVHS_BENCH_HOST_SLICE"):  # tuning sweeps only
+        ctx.set_option("host_slice", os.environ["OBVHS_BENCH_HOST_SLICE"])
 
     tris, rays, desc, preset = make_workload(args.workload, args.tris)
     params = api.BvhBuildParams.preset(preset)

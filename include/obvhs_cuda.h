@@ -91,7 +91,8 @@ int obvhs_cuda_synchronize(ObvhsContext* ctx);
 uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx);
 /* Tuning knobs that do not change any result. key "traverse": "auto" (default: every 128-ray block of the batch is
  * judged on the device and goes to the kernel that suits it), "static" (one ray per thread) or "persistent[:refill[:chunk]]" (persistent warps refilled from a ray cursor when
- * `refill` of 32 lanes have finished, `chunk` consecutive rays per fetch). key "trace": "1"/"0" stage timing on stderr
+ * `refill` of 32 lanes have finished, `chunk` consecutive rays per fetch). key "host_slice": rays per pipelined slice of a host-resident ray batch ("0" = sized for the kernel
+ * in use). key "trace": "1"/"0" stage timing on stderr
  * (the reference's scope!/timeit! macros, lib.rs:158-205). Environment: OBVHS_TRAVERSE, OBVHS_TRACE set the defaults. */
 int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value);
 /* 6 built-in presets of src/lib.rs:233-305 by name: fastest_build, very_fast_build, fast_build, medium_build,

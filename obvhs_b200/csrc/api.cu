@@ -189,6 +189,7 @@ static void context_teardown(ObvhsContext* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->compute_alt) cudaStreamDestroy(ctx->compute_alt);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (auto& b : ctx->arena_blocks) cudaFree(b.p);
     for (auto& b : ctx->result_cache) cudaFree(b.p);
@@ -325,6 +326,15 @@ int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value)
             OBVHS_SET_ERR(ctx, "traverse must be auto, static or persistent[:refill[:chunk]]");
             return OBVHS_ERR_INVALID_ARG;
         }
+        return OBVHS_OK;
+    }
+    if (strcmp(key, "host_slice") == 0) {  // rays per pipelined slice of a host batch; 0 = sized for the kernel in use
+        long v = atol(value);
+        if (v < 0) {
+            OBVHS_SET_ERR(ctx, "host_slice must be >= 0");
+            return OBVHS_ERR_INVALID_ARG;
+        }
+        ctx->host_slice = (size_t)v;
         return OBVHS_OK;
     }
     if (strcmp(key, "trace") == 0) {
@@ -890,6 +900,7 @@ static int ray_new_device(ObvhsContext* ctx, const ObvhsRayNew* d_args, size_t n
 static int ensure_pipeline(ObvhsContext* ctx, size_t n_events) {
     if (!ctx->copy_in) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     if (!ctx->copy_out) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    if (!ctx->compute_alt) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->compute_alt, cudaStreamNonBlocking));
     while (ctx->event_pool.size() < n_events) {
         cudaEvent_t e;
         CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -899,6 +910,13 @@ static int ensure_pipeline(ObvhsContext* ctx, size_t n_events) {
 }
 
 // `launch(d_rays, count, d_out, d_counters)` enqueues the traversal of a device-resident slice on ctx->stream
+struct StreamSwap {  // launches go to ctx->stream: point it at another stream for a while, whatever the exit path
+    ObvhsContext* ctx;
+    cudaStream_t saved;
+    explicit StreamSwap(ObvhsContext* c) : ctx(c), saved(c->stream) {}
+    ~StreamSwap() { ctx->stream = saved; }
+};
+
 // RayIn = ObvhsRay (used as it is) or ObvhsRayNew (constructor arguments, expanded on the device chunk by chunk)
 template <class RayIn, class Launch>
 static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count, const RayIn* rays, size_t n, void* out, size_t out_elem,
@@ -929,8 +947,9 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
             d_cnt = st_cnt.p;
         }
     }
-    const size_t MIN_CHUNK = traverse_host_chunk_min(ctx, prim_count);
-    if (rays_dev || n < 65536 || n < MIN_CHUNK + MIN_CHUNK / 2) {
+    bool persistent = false;
+    const size_t MIN_CHUNK = traverse_host_chunk_min(ctx, prim_count, &persistent);
+    if (rays_dev || n < MIN_CHUNK + MIN_CHUNK / 2) {
         const RayIn* d_in = nullptr;
         ST_TRY(stage_in(ctx, rays, n, st_in, &d_in));  // (a device pointer passes through)
         const ObvhsRay* d_rays = reinterpret_cast<const ObvhsRay*>(d_in);
@@ -945,40 +964,57 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
         CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
         if (PACKED) CU_TRY(ctx, st_in.alloc(n, ctx->stream));
         unsigned char* d_stage = PACKED ? reinterpret_cast<unsigned char*>(st_in.p) : reinterpret_cast<unsigned char*>(st_rays.p);
-        size_t chunk = (n + 15) / 16;  // ~16 stages: the un-overlapped head and tail are 1/16 of the copy time each
-        if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
-        if (chunk > ((size_t)1 << 21) && MIN_CHUNK <= ((size_t)1 << 21)) chunk = (size_t)1 << 21;
-        size_t n_chunks = (n + chunk - 1) / chunk;
-        if (n - (n_chunks - 1) * chunk < chunk / 2 && n_chunks > 1) n_chunks--;  // no runt slice at the end: spread it over the others
-        chunk = ((n + n_chunks - 1) / n_chunks + 127) & ~(size_t)127;
-        n_chunks = (n + chunk - 1) / chunk;
+        // Slice boundaries: ~16 equal slices (the un-overlapped head and tail are 1/16 of the copy time each), but never below
+        // what the kernel in use needs to run efficiently (traverse_host_chunk_min).
+        std::vector<size_t> cut(1, 0);
+        {
+            size_t chunk = (n + 15) / 16;
+            if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+            if (chunk > ((size_t)1 << 21) && MIN_CHUNK <= ((size_t)1 << 21)) chunk = (size_t)1 << 21;
+            size_t k = (n + chunk - 1) / chunk;
+            if (n - (k - 1) * chunk < chunk / 2 && k > 1) k--;  // no runt slice at the end: spread it over the others
+            chunk = ((n + k - 1) / k + 127) & ~(size_t)127;
+            while (cut.back() + chunk < n) cut.push_back(cut.back() + chunk);
+        }
+        cut.push_back(n);
+        const size_t n_chunks = cut.size() - 1;
         ST_TRY(ensure_pipeline(ctx, 2 * n_chunks + 2));
         cudaEvent_t* ev = ctx->event_pool.data();
         // the staging areas come from the arena, whose reuse is ordered on ctx->stream: the copy streams start after it
         CU_TRY(ctx, cudaEventRecord(ev[0], ctx->stream));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ev[0], 0));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev[0], 0));
+        // Persistent-kernel slices alternate between two compute streams: the CTAs of slice k+1 move in as those of slice k
+        // run out of rays, so the tail of a slice (a few long rays on an otherwise idle GPU) is hidden behind the next one.
+        const bool two_streams = persistent && n_chunks > 1;
+        if (two_streams) CU_TRY(ctx, cudaStreamWaitEvent(ctx->compute_alt, ev[0], 0));
+        StreamSwap swap(ctx);
+        cudaEvent_t last_alt = nullptr;
         const unsigned char* h_rays = reinterpret_cast<const unsigned char*>(rays);
         // every H2D slice is queued before the first launch: the copy engine never waits for the host to get through the
         // launches of the previous slice
         for (size_t c = 0; c < n_chunks; c++) {
-            const size_t off = c * chunk, cnt = (off + chunk <= n) ? chunk : n - off;
+            const size_t off = cut[c], cnt = cut[c + 1] - off;
             CU_TRY(ctx, cudaMemcpyAsync(d_stage + off * sizeof(RayIn), h_rays + off * sizeof(RayIn), cnt * sizeof(RayIn), cudaMemcpyHostToDevice, ctx->copy_in));
             CU_TRY(ctx, cudaEventRecord(ev[2 + 2 * c], ctx->copy_in));
         }
         for (size_t c = 0; c < n_chunks; c++) {
-            const size_t off = c * chunk, cnt = (off + chunk <= n) ? chunk : n - off;
+            const size_t off = cut[c], cnt = cut[c + 1] - off;
             cudaEvent_t e_in = ev[2 + 2 * c], e_k = ev[3 + 2 * c];
+            ctx->stream = (two_streams && (c & 1)) ? ctx->compute_alt : swap.saved;
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
             if (PACKED) ST_TRY(ray_new_device(ctx, reinterpret_cast<const ObvhsRayNew*>(st_in.p) + off, cnt, st_rays.p + off));
             ST_TRY(launch(st_rays.p + off, cnt, (unsigned char*)d_out + off * out_elem, d_cnt));
+            if (!out_dev || ctx->stream != swap.saved) CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
+            if (ctx->stream != swap.saved) last_alt = e_k;
             if (!out_dev) {
-                CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
                 CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
                 CU_TRY(ctx, cudaMemcpyAsync((unsigned char*)out + off * out_elem, (unsigned char*)d_out + off * out_elem, cnt * out_elem,
                                             cudaMemcpyDeviceToHost, ctx->copy_out));
             }
         }
+        ctx->stream = swap.saved;
+        if (last_alt) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, last_alt, 0));  // join the second compute stream
         if (!out_dev) {  // join the copy-out stream back into the context's stream
             CU_TRY(ctx, cudaEventRecord(ev[1], ctx->copy_out));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev[1], 0));

@@ -137,7 +137,8 @@ struct ObvhsContext {
     std::vector<ResultBlock> result_cache;
     std::unordered_map<void*, size_t> result_live;
     // host-batch pipeline (traverse_common): copy-in / copy-out streams beside `stream`, and a pool of timing-free events
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr, compute_alt = nullptr;
+    size_t host_slice = 0;  // obvhs_cuda_set_option("host_slice", "<rays>"), 0 = automatic
     std::vector<cudaEvent_t> event_pool;
     int traverse_mode = 2, traverse_refill = 4, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
@@ -339,5 +340,5 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
 int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters);
 int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris);
-size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count);
+size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool* persistent);
 int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays);

@@ -769,13 +769,15 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     return launch_persistent(ctx, tree, rays, n, mode, d_out, c, scratch.p + 2, defer);
 }
 
-// Smallest slice of a host batch worth its own launch (traverse_common pipelines H2D | traversal | D2H slice by slice). The
-// one-ray-per-thread kernel is happy with 32 Ki rays; the persistent kernel keeps sm_count * 9 CTAs of 128 lanes resident and
-// only pays off when every lane is refilled several times: 130 k-ray slices ran the 10 M-triangle soup at 29 % of the
-// device-resident rate (251 vs 866 Mrays/s), so a slice there is at least four times the resident lanes.
-size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count) {
-    const bool persistent = ctx->traverse_mode == 1 || (ctx->traverse_mode == 2 && prim_count > AUTO_STATIC_MAX_PRIMS);
-    return persistent ? (size_t)ctx->sm_count * 9 * 128 * 4 : (size_t)32768;
+// Smallest slice of a host batch worth its own launch (traverse_common pipelines H2D | traversal | D2H slice by slice): 32 Ki
+// rays for the one-ray-per-thread kernel. The persistent kernel keeps sm_count * 9 CTAs of 128 lanes resident and pays off
+// when lanes are refilled, while a large slice leaves the GPU idle behind its H2D copy. Measured on 2 M-ray host batches over
+// 10 M triangles (Mrays/s at 1x / 2x / 4x the resident lanes per slice, slices alternating between two compute streams): the
+// kernel-bound soup 445 / 557 / 599, the copy-bound terrain 1081 / 997 / 843, diffuse bounces 1329 / 1321 / 1340 -> 2x.
+size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool* persistent) {
+    *persistent = ctx->traverse_mode == 1 || (ctx->traverse_mode == 2 && prim_count > AUTO_STATIC_MAX_PRIMS);
+    if (ctx->host_slice) return ctx->host_slice < 1024 ? 1024 : ctx->host_slice;  // obvhs_cuda_set_option("host_slice", ...)
+    return *persistent ? (size_t)ctx->sm_count * 9 * 128 * 2 : (size_t)32768;
 }
 
 int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,

@@ -552,6 +552,39 @@ def test_traversal_over_ray_new_arguments(api, scenes, n_side):
     assert cw.ray_traverse(np.zeros((0, 8), np.float32)).shape[0] == 0
 
 
+@pytest.mark.parametrize("mode", ["persistent", "auto", "static"])
+def test_host_slices_on_two_compute_streams(api, scenes, mode):
+    # persistent-kernel slices of a host batch alternate between two compute streams (the tail of one hides behind the next);
+    # forced here with a small host_slice: same hits, and the counters of all slices add up
+    tris = scenes["kitchen"]
+    rays = rays_for(tris, n_side=190)
+    c = ob.build_cwbvh_from_tris(tris, "fast_build")
+    nodes, prims, total = c.get()
+    wc = np.zeros(2, np.uint64)
+    want = c.ray_traverse(c.bvh_tris(tris), rays, counters=wc)
+    ctx = api.Context(0, traverse=mode)
+    ctx.set_option("host_slice", "9000")
+    g = api.CwBvh.upload(nodes, prims, total, ctx=ctx)
+    g.set_triangles(tris)
+    from obvhs_b200.types import ray_args_of
+
+    for r in (rays, ray_args_of(rays)):
+        got = g.ray_traverse(r)
+        assert np.array_equal(got["primitive_id"], want["primitive_id"])
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    gc = np.zeros(2, np.uint64)
+    g.ray_traverse(rays, counters=gc)
+    assert np.array_equal(gc, wc)
+    import torch
+
+    d_hits = torch.empty((rays.shape[0], 4), dtype=torch.int32, device="cuda")  # host rays, device hits: joined on the context's stream
+    g.ray_traverse(rays, out=d_hits)
+    ctx.synchronize()
+    assert np.array_equal(d_hits.cpu().numpy()[:, 0].view(np.uint32), want["primitive_id"])
+    with pytest.raises(api.ObvhsError):
+        ctx.set_option("host_slice", "-1")
+
+
 def displaced_aabbs(tris, frame):
     """BASELINE config 5 / SURVEY.md 8(d) S4: every vertex moved by 0.01*(hash_noise-0.5) seeded by the frame."""
     t = tris.reshape(-1, 3, 4).copy()
