@@ -964,11 +964,14 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
         CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
         if (PACKED) CU_TRY(ctx, st_in.alloc(n, ctx->stream));
         unsigned char* d_stage = PACKED ? reinterpret_cast<unsigned char*>(st_in.p) : reinterpret_cast<unsigned char*>(st_rays.p);
-        // Slice boundaries: ~16 equal slices (the un-overlapped head and tail are 1/16 of the copy time each), but never below
-        // what the kernel in use needs to run efficiently (traverse_host_chunk_min).
+        // Slice boundaries: ~6 equal slices, but never below what the kernel in use needs to run efficiently
+        // (traverse_host_chunk_min). The un-overlapped head (first H2D slice) and tail (last kernel + D2H slice) shrink with the
+        // slice, but many small copies in both directions at once cost more on the link than they save: 2 M kitchen rays
+        // (66 MB up, 33 MB down; plain cudaMemcpyAsync of both concurrently 1.35-1.45 ms) took 1.75 ms in 16 slices, 1.61 in
+        // 4-6, 1.69 in 3 and 1.84 in 2.
         std::vector<size_t> cut(1, 0);
         {
-            size_t chunk = (n + 15) / 16;
+            size_t chunk = (n + 5) / 6;
             if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
             if (chunk > ((size_t)1 << 21) && MIN_CHUNK <= ((size_t)1 << 21)) chunk = (size_t)1 << 21;
             size_t k = (n + chunk - 1) / chunk;

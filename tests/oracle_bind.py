@@ -116,6 +116,14 @@ def tri_aabbs(tris) -> np.ndarray:
     return out
 
 
+def make_rays(origin, direction, tmin=0.0, tmax=np.inf) -> np.ndarray:
+    """Ray::new (ray.rs:34-52) through the oracle's restatement: (n,16) float32 Ray array, one tmin / tmax for all."""
+    od = np.ascontiguousarray(np.concatenate([np.asarray(origin, np.float32), np.asarray(direction, np.float32)], axis=1))
+    out = np.zeros((od.shape[0], 16), dtype=np.float32)
+    lib().orc_make_rays(_p(od), od.shape[0], float(tmin), float(tmax), _p(out))
+    return out
+
+
 def morton_sort(aabbs, precision=64):
     aabbs = _f32c(aabbs, 8)
     n = aabbs.shape[0]

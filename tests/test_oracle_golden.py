@@ -164,3 +164,33 @@ def test_exact_node_aabbs_bound_by_quantised_boxes(scenes):
     assert np.all(ex[:m, 0:3] >= lo) and np.all(ex[:m, 4:7] <= hi + np.abs(hi) * 1e-6 + 1e-6)
     assert np.all(ex[m:, 0] == np.float32(3.4028235e38)) and np.all(ex[m:, 4] == np.float32(-3.4028235e38))  # Aabb::empty()
     assert ob.ploc_build(aabbs, None, 6, 64, 2).to_cwbvh(3, True, False).exact_node_aabbs() is None
+
+
+def ray_new_cases():
+    """Directions around every branch of safe_inverse (ray.rs:6-12): +-0, denormals, |x| == EPSILON and its neighbours, huge, inf."""
+    eps = np.float32(1.1920929e-07)
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, eps, -eps, np.nextafter(eps, np.float32(1)), np.nextafter(eps, np.float32(0)),
+                        -np.nextafter(eps, np.float32(1)), 1.0, -1.0, 3.0, 1e-7, -1e-7, 1e30, -1e30, 3.4028235e38, np.inf, -np.inf], np.float32)
+    rng = np.random.default_rng(11)
+    d = np.concatenate([np.stack([special, np.roll(special, 1), np.roll(special, 7)], axis=1),
+                        rng.standard_normal((5000, 3)).astype(np.float32) * np.float32(1e-6),
+                        rng.standard_normal((5000, 3)).astype(np.float32)], axis=0)
+    o = rng.standard_normal(d.shape).astype(np.float32)
+    return o, d
+
+
+def test_host_ray_helpers_match_the_oracle_ray_new():
+    # obvhs_b200.types.make_rays (numpy) is what the tests and bench.py build rays with: pin it to the oracle's Ray::new, and
+    # make_ray_args / ray_args_of to the 32-byte argument record of include/obvhs_cuda.h (ObvhsRayNew)
+    from obvhs_b200.types import make_ray_args, make_rays, ray_args_of
+
+    o, d = ray_new_cases()
+    want = ob.make_rays(o, d, 0.25, 7.5)
+    with np.errstate(all="ignore"):
+        got = make_rays(o, d, 0.25, 7.5)
+    assert got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes()
+    a = make_ray_args(o, d, 0.25, 7.5)
+    assert a.shape == (o.shape[0], 8) and a.dtype == np.float32
+    assert np.array_equal(a[:, 0:3], o) and np.array_equal(a[:, 4:7].view(np.uint32), d.view(np.uint32))
+    assert np.all(a[:, 3] == np.float32(0.25)) and np.all(a[:, 7] == np.float32(7.5))
+    assert ray_args_of(want).view(np.uint32).tobytes() == a.view(np.uint32).tobytes()
