@@ -969,8 +969,14 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
         // slice, but many small copies in both directions at once cost more on the link than they save: 2 M kitchen rays
         // (66 MB up, 33 MB down; plain cudaMemcpyAsync of both concurrently 1.35-1.45 ms) took 1.75 ms in 16 slices, 1.61 in
         // 4-6, 1.69 in 3 and 1.84 in 2.
+        // A batch bound by the link (always the case for the one-ray-per-thread kernel: 8 G rays/s against 1.7 G rays/s of PCIe)
+        // ends one kernel + one D2H slice after its last H2D slice, so the slices SHRINK towards the end: 5,5,3,2,1 sixteenths.
         std::vector<size_t> cut(1, 0);
-        {
+        if (!persistent && !ctx->host_slice && n >= 16 * MIN_CHUNK) {
+            const size_t unit = ((n + 15) / 16 + 127) & ~(size_t)127;
+            for (size_t parts : {5, 5, 3, 2})
+                if (cut.back() + parts * unit < n) cut.push_back(cut.back() + parts * unit);
+        } else {
             size_t chunk = (n + 5) / 6;
             if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
             if (chunk > ((size_t)1 << 21) && MIN_CHUNK <= ((size_t)1 << 21)) chunk = (size_t)1 << 21;
