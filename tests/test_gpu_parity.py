@@ -579,6 +579,31 @@ def test_host_slices_on_two_compute_streams(api, scenes, mode):
         ctx.set_option("host_slice", "-1")
 
 
+def test_ray_new_entry_points_edge_cases(api, scenes):
+    # error behaviour of the Ray::new entry points matches the Ray-struct ones; extreme slice sizes are clamped, not rejected
+    from obvhs_b200.types import ray_args_of
+
+    tris = scenes["cornell"]
+    rays = rays_for(tris, n_side=64)
+    args = ray_args_of(rays)
+    ctx = api.Context(0, traverse="persistent")
+    bvh = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.medium_build(), ctx=ctx)
+    want = bvh.ray_traverse(rays)
+    for sl in ("1", "1000000000", "0"):  # 1 -> 1024-ray slices (one launch each, event pool grows), huge -> a single shot
+        ctx.set_option("host_slice", sl)
+        got = bvh.ray_traverse(args)
+        assert got.tobytes() == want.tobytes(), sl
+    lib, h = ctx.lib, ctx.h
+    hits = np.zeros(4, dtype=np.uint8)
+    assert lib.obvhs_cuda_cwbvh_ray_new_traverse_batch(h, bvh.h, None, 4, hits.ctypes.data) < 0  # null args
+    assert lib.obvhs_cuda_cwbvh_ray_new_traverse_batch(h, None, args.ctypes.data, 4, hits.ctypes.data) < 0  # null bvh
+    assert lib.obvhs_cuda_cwbvh_ray_new_traverse_batch(h, bvh.h, None, 0, None) == 0  # empty batch
+    assert lib.obvhs_cuda_ray_new_batch(h, None, 3, hits.ctypes.data) < 0
+    bare = api.CwBvh.upload(*bvh.download(), ctx=ctx)  # no triangles attached
+    with pytest.raises(api.ObvhsError):
+        bare.ray_traverse(args)
+
+
 def displaced_aabbs(tris, frame):
     """BASELINE config 5 / SURVEY.md 8(d) S4: every vertex moved by 0.01*(hash_noise-0.5) seeded by the frame."""
     t = tris.reshape(-1, 3, 4).copy()
