@@ -985,6 +985,12 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
             chunk = ((n + k - 1) / k + 127) & ~(size_t)127;
             while (cut.back() + chunk < n) cut.push_back(cut.back() + chunk);
         }
+        if (persistent && !ctx->host_slice && cut.size() >= 2) {
+            // the batch ends one kernel + one D2H slice after the last H2D slice: halve that one (the two compute streams hide
+            // what the smaller launch loses in efficiency)
+            const size_t mid = (cut.back() + (n - cut.back()) / 2 + 127) & ~(size_t)127;
+            if (mid > cut.back() && mid < n) cut.push_back(mid);
+        }
         cut.push_back(n);
         const size_t n_chunks = cut.size() - 1;
         ST_TRY(ensure_pipeline(ctx, 2 * n_chunks + 2));
