@@ -162,6 +162,29 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.mode}
 
 
+def bind_to_gpu_numa_node(local_rank: int, world: int):
+    """N > 1 only: run this rank (and so allocate its pinned staging buffers, first touch) on the CPUs NVML reports as local to its
+    GPU. Eight ranks that float across both sockets pull half of their host batches over the inter-socket link. Returns a note for
+    the JSON line. (At N = 1 the process keeps every core: the cpu_baseline leg runs there.)"""
+    if world <= 1 or os.environ.get("OBVHS_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return "no GPU-local CPUs reported"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} GPU-local CPUs"
+    except Exception as e:  # noqa: BLE001  (a box without NVML affinity data just keeps the default placement)
+        return f"unbound ({type(e).__name__})"
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -245,6 +268,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    numa_note = bind_to_gpu_numa_node(local_rank, world)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -413,7 +437,8 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic" if args.workload != "kitchen" else "kitchen.obj fixture (reference asset), generated rays",
             "config": {"workload": desc, "preset": preset, "rays_per_gpu": n_rays, "rays_total": n_rays_all, "tris": n_tris, "l2": "flushed between steps (256 MB write)",
-                       "multi_gpu": "build on rank 0, NCCL broadcast, rays sharded (one batch per GPU)" if world > 1 else "single GPU"},
+                       "multi_gpu": "build on rank 0, NCCL broadcast, rays sharded (one batch per GPU)" if world > 1 else "single GPU",
+                       "host_numa": numa_note},
             "build": {"value": build_mtris, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count},
             "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
