@@ -11,18 +11,11 @@ import oracle_bind as ob
 from obvhs_b200 import test_util as tu
 from obvhs_b200.types import make_rays
 
-from test_gpu_parity import assert_nodes_equal
+from test_gpu_parity import api, assert_nodes_equal, oracle_refit_semantics  # noqa: F401  (fixtures)
 
 pytestmark = pytest.mark.gpu
 
 PRESET_NAMES = list(ob.PRESETS)
-
-
-@pytest.fixture(scope="module")
-def api():
-    from obvhs_b200 import api as a
-
-    return a
 
 
 def random_scene(seed):
@@ -93,3 +86,61 @@ def test_random_scene_cwbvh_and_bvh2_end_to_end(api, seed):
     gh2 = got2.ray_traverse(rays)
     assert np.array_equal(gh2["primitive_id"], wh2["primitive_id"])
     assert np.array_equal(gh2["t"].view(np.uint32), wh2["t"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS))
+def test_random_scene_rebuilds_queries_and_dynamic_updates(api, seed):
+    # the remaining stages on the same scenes: PLOC with a random search distance / precision / depth threshold, reinsertion
+    # at a random ratio, a partial rebuild of a random leaf set and a full rebuild (ploc/rebuild.rs), box and point queries on
+    # both tree types, then two frames of moved leaves (refit_all + reinsertion, examples/physics.rs)
+    from test_gpu_parity import displaced_aabbs
+    from test_gpu_queries import query_boxes
+    from test_oracle_rebuild import leaf_ids
+
+    rng = np.random.default_rng(5000 + seed)
+    tris = random_scene(seed)
+    aabbs = ob.tri_aabbs(tris)
+    sd = int(rng.choice([1, 2, 6, 14, 24, 32]))
+    prec = int(rng.choice([64, 128]))
+    thr = int(rng.integers(0, 4))
+    ratio = float(rng.choice([0.01, 0.1, 0.5, 1.0]))
+    what = f"seed {seed} n {tris.shape[0]} sd {sd} prec {prec} thr {thr} ratio {ratio}"
+    want = ob.ploc_build(aabbs, None, sd, prec, thr)
+    got = api.PlocBuilder().build(sd, aabbs, None, api.SortPrecision(prec), thr)
+    assert_nodes_equal(got.download()[0], want.get()[0], what + " ploc")
+    assert api.ReinsertionOptimizer().run(got, ratio) == want.reinsertion_run(ratio), what
+    assert_nodes_equal(got.download()[0], want.get()[0], what + " reinsertion")
+    # queries on the Bvh2 and on the CwBvh made from it
+    q = query_boxes(tris, 300, seed, 0.1)
+    pts = (q[:, 0:3] + q[:, 4:7]) * np.float32(0.5)
+    wc = want.to_cwbvh(int(rng.integers(1, 4)), bool(rng.integers(0, 2)))
+    gc = api.CwBvh.upload(*wc.get())
+    for w, g in ((want, got), (wc, gc)):
+        for fn, arg in (("aabb_traverse", q), ("point_traverse", pts)):
+            wcounts, wids = getattr(w, fn)(arg)
+            gcounts, gids = getattr(g, fn)(arg)
+            assert np.array_equal(gcounts, wcounts) and np.array_equal(gids, wids), what + " " + fn
+    # partial rebuild of a random set of leaves, then a full rebuild
+    want.compute_parents()
+    got.compute_parents()
+    ids = leaf_ids(want)
+    ids = ids[rng.random(len(ids)) < rng.choice([0.02, 0.3, 1.0])]
+    if len(ids):
+        wflags = want.rebuild_path_flags(ids)
+        assert np.array_equal(api.compute_rebuild_path_flags(got, ids), wflags), what
+        want.partial_rebuild(wflags, sd, prec, thr)
+        api.PlocBuilder().partial_rebuild(got, wflags, sd, api.SortPrecision(prec), thr)
+        assert_nodes_equal(got.download()[0], want.get()[0], what + " partial_rebuild")
+        assert np.array_equal(got.download()[1], want.get()[1]), what
+    want.full_rebuild(sd, prec, thr)
+    api.PlocBuilder().full_rebuild(got, sd, api.SortPrecision(prec), thr)
+    assert_nodes_equal(got.download()[0], want.get()[0], what + " full_rebuild")
+    # moved leaves
+    for frame in range(2):
+        moved = displaced_aabbs(tris, frame + seed)
+        want.set_leaf_aabbs(moved)
+        want.refit_all()
+        got.set_leaf_aabbs(moved)
+        assert_nodes_equal(got.download()[0], want.get()[0], what + f" frame {frame} refit")
+        assert api.ReinsertionOptimizer().run(got, 0.05) == want.reinsertion_run(0.05), what
+        assert_nodes_equal(got.download()[0], want.get()[0], what + f" frame {frame} reinsertion")
