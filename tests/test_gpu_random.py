@@ -144,3 +144,41 @@ def test_random_scene_rebuilds_queries_and_dynamic_updates(api, seed):
         assert_nodes_equal(got.download()[0], want.get()[0], what + f" frame {frame} refit")
         assert api.ReinsertionOptimizer().run(got, 0.05) == want.reinsertion_run(0.05), what
         assert_nodes_equal(got.download()[0], want.get()[0], what + f" frame {frame} reinsertion")
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS))
+def test_random_scene_traversal_flavours_and_kernel_variants(api, seed):
+    # closest hit / miss / all-hit counts and the visit counters, through a random kernel variant (one ray per thread, persistent
+    # warps at a random refill threshold and fetch size, or the per-block choice), for rays with random tmin / tmax windows,
+    # axis-parallel directions and origins inside the scene; CwBvh and Bvh2
+    rng = np.random.default_rng(9000 + seed)
+    tris = random_scene(seed)
+    rays = random_rays(tris, seed, m=3000)
+    v = tris.reshape(-1, 4)[:, :3]
+    ext = max(float(np.max(v.max(axis=0) - v.min(axis=0))), 1e-3)
+    k = rng.random(rays.shape[0])
+    rays[k < 0.3, 12] = (rng.random(int((k < 0.3).sum())) * ext).astype(np.float32)           # tmin > 0
+    rays[k > 0.6, 13] = (rng.random(int((k > 0.6).sum())) * 2.0 * ext).astype(np.float32)     # finite tmax (some below tmin)
+    ax = rng.integers(0, rays.shape[0], 200)
+    d = np.zeros((200, 3), np.float32)
+    d[np.arange(200), rng.integers(0, 3, 200)] = rng.choice(np.array([-1.0, 1.0], np.float32), 200)
+    rays[ax] = make_rays(rays[ax, 0:3], d, 0.0, np.inf)
+    mode = ["static", "auto", f"persistent:{rng.choice([1, 4, 8, 16, 32])}:{rng.choice([32, 64, 128])}"][seed % 3]
+    ctx = api.Context(0, traverse=mode)
+    preset = PRESET_NAMES[seed % 4]
+    wc = ob.build_cwbvh_from_tris(tris, preset)
+    gc = api.CwBvh.upload(*wc.get(), ctx=ctx)
+    gc.set_triangles(tris)
+    wb = ob.build_bvh2_from_tris(tris, preset)
+    gb = api.Bvh2.upload(*wb.get(), max_depth=wb.max_depth, ctx=ctx)
+    gb.set_triangles(tris)
+    for w, g in ((wc, gc), (wb, gb)):
+        bt = w.bvh_tris(tris)
+        cw, cg = np.zeros(2, np.uint64), np.zeros(2, np.uint64)
+        want = w.ray_traverse(bt, rays, counters=cw)
+        got = g.ray_traverse(rays, counters=cg)
+        assert np.array_equal(got["primitive_id"], want["primitive_id"]), (seed, mode)
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (seed, mode)
+        assert np.array_equal(cg, cw), (seed, mode)
+        assert np.array_equal(g.ray_traverse_miss(rays), w.ray_traverse_miss(bt, rays)), (seed, mode)
+        assert np.array_equal(g.ray_traverse_anyhit_count(rays), w.ray_traverse_anyhit_count(bt, rays)), (seed, mode)
