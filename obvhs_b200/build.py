@@ -78,5 +78,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_TEST_SRC = os.path.join(_HERE, "..", "tests", "cpp", "host_api.cpp")
+HOST_TEST_BIN = os.path.join(LIB_DIR, "host_api_test.bin")
+
+
+def build_host_test(force: bool = False) -> str:
+    """The C++ host side (include/obvhs.hpp) compiled with plain g++ against the shared library: tests/cpp/host_api.cpp ->
+    obvhs_b200/lib/host_api_test.bin (run by tests/test_gpu_cpp_host.py on the GPU box; it travels with the snapshot)."""
+    build()
+    deps = [HOST_TEST_SRC, os.path.join(_HERE, "..", "include", "obvhs.hpp"), os.path.join(_HERE, "..", "include", "obvhs_cuda.h"), LIB_PATH]
+    if not force and os.path.exists(HOST_TEST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_TEST_BIN) for d in deps):
+        return HOST_TEST_BIN
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", HOST_TEST_SRC, "-o", HOST_TEST_BIN, "-L", LIB_DIR, "-lobvhs_cuda",
+                           "-Wl,-rpath,$ORIGIN"])
+    return HOST_TEST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_host_test(force="--force" in sys.argv))
