@@ -2275,6 +2275,12 @@ void orc_cwbvh_ray_traverse_anyhit_count(const OrcCwBvh* c, const OrcTriangle* b
     traverse_batch<2>(*c, bvh_tris, rays, n, nullptr, nullptr, counts, threads, 1, nullptr);
 }
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray) { return tri_intersect(*tri, *ray); }
+// the Aabb primitives the path is built on, exported so that the reference's own unit tests (aabb.rs:222-360) pin them
+float orc_aabb_half_area(const OrcAabb* a) { return half_area(*a); }
+void orc_aabb_union(const OrcAabb* a, const OrcAabb* b, OrcAabb* out) { *out = aabb_union(*a, *b); }
+float orc_aabb_intersect_ray(const OrcAabb* a, const OrcRay* ray) { return aabb_intersect_ray(*a, *ray); }
+int orc_aabb_intersect_aabb(const OrcAabb* a, const OrcAabb* b) { return aabb_intersect_aabb(a->min, a->max, b->min, b->max); }
+int orc_aabb_contains_point(const OrcAabb* a, const float* p3) { return aabb_contains_point(a->min, a->max, p3); }
 void orc_triangle_normal(const OrcTriangle* tri, float* out3) {
     V3 nrm = tri_normal(*tri);
     out3[0] = nrm.x;

@@ -150,6 +150,11 @@ size_t orc_cwbvh_point_traverse(const OrcCwBvh*, const float* points4, size_t n,
                                 uint32_t* prim_ids, size_t cap);
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray);               /* triangle.rs:35-76 */
 void  orc_triangle_normal(const OrcTriangle* tri, float* out3);                         /* triangle.rs:20-24 */
+float orc_aabb_half_area(const OrcAabb* a);                                              /* aabb.rs:151-154 */
+void  orc_aabb_union(const OrcAabb* a, const OrcAabb* b, OrcAabb* out);                 /* aabb.rs:84-89 */
+float orc_aabb_intersect_ray(const OrcAabb* a, const OrcRay* ray);                      /* aabb.rs:186-206 */
+int   orc_aabb_intersect_aabb(const OrcAabb* a, const OrcAabb* b);                      /* aabb.rs:181-183 */
+int   orc_aabb_contains_point(const OrcAabb* a, const float* p3);                       /* aabb.rs:70-72 */
 int   orc_max_threads(void);
 
 #ifdef __cplusplus

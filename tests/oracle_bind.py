@@ -87,6 +87,11 @@ def lib():
             "orc_cwbvh_point_traverse": (sz, [vp, vp, sz, vp, vp, vp, sz]),
             "orc_triangle_intersect": (f32, [vp, vp]),
             "orc_triangle_normal": (None, [vp, vp]),
+            "orc_aabb_half_area": (f32, [vp]),
+            "orc_aabb_union": (None, [vp, vp, vp]),
+            "orc_aabb_intersect_ray": (f32, [vp, vp]),
+            "orc_aabb_intersect_aabb": (i32, [vp, vp]),
+            "orc_aabb_contains_point": (i32, [vp, vp]),
             "orc_max_threads": (i32, []),
             "orc_test_split3_64": (C.c_uint64, [u32]),
             "orc_test_split3_128": (None, [C.c_uint64, vp, vp]),

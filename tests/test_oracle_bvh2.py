@@ -125,3 +125,44 @@ def test_bvh2_and_cwbvh_agree_on_incoherent_rays():
     srays[:, 13] = np.where(hit, hc["t"] * np.float32(1.001), np.float32(5.0))
     assert np.array_equal(b.ray_traverse_miss(b.bvh_tris(tris), srays).astype(bool), ~hit)
     assert np.array_equal(b.ray_traverse_anyhit_count(b.bvh_tris(tris), srays) > 0, hit)
+
+
+def test_reference_test_reinsertion():
+    # bvh2/reinsertion.rs:394-436: VeryLow PLOC over demoscene(32), validate, run(0.25), validate, run(0.5), validate -- with
+    # and without parents computed up front. (The reference also calls reorder_in_stack_traversal_order between the two runs: a
+    # pure re-indexing of the nodes that this path does not carry; the invariants checked are the same.)
+    tris = tu.demoscene(32, 0)
+    aabbs = ob.tri_aabbs(tris)
+    for with_parents in (False, True):
+        bvh = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 2, 64, 1)
+        assert bvh.validate(aabbs, tight_fit=False)[0] == 0
+        if with_parents:
+            bvh.compute_parents()
+            assert bvh.validate(aabbs, tight_fit=False)[0] == 0
+        n0 = bvh.get()[0].tobytes()
+        for ratio in (0.25, 0.5):
+            bvh.reinsertion_run(ratio)
+            rc, msg = bvh.validate(aabbs, tight_fit=False)
+            assert rc == 0, msg
+        assert bvh.get()[0].tobytes() != n0  # the optimizer did move nodes
+        assert np.array_equal(np.sort(bvh.get()[1]), np.arange(tris.shape[0], dtype=np.uint32))
+
+
+def test_reference_test_refit_all():
+    # bvh2/mod.rs:1110-1142: move every triangle (scale 1.3, rotate 0.1 rad about y, translate), rewrite the leaf boxes through
+    # primitives_to_nodes, refit_all, validate with tight_fit = true
+    tris = tu.demoscene(32, 0)
+    aabbs = ob.tri_aabbs(tris)
+    bvh = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 2, 64, 1)
+    c, s = np.float32(np.cos(0.1)), np.float32(np.sin(0.1))
+    rot = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)  # Quat::from_rotation_y
+    v = tris.reshape(-1, 3, 4)[:, :, :3] * np.float32(1.3)
+    v = (v @ rot.T + np.array([0.33, 0.3, 0.37], np.float32)).astype(np.float32)
+    moved = np.zeros_like(tris).reshape(-1, 3, 4)
+    moved[:, :, :3] = v
+    moved_aabbs = ob.tri_aabbs(np.ascontiguousarray(moved.reshape(-1, 12)))
+    assert bvh.validate(moved_aabbs, tight_fit=True)[0] != 0  # stale boxes no longer fit
+    bvh.set_leaf_aabbs(moved_aabbs)
+    bvh.refit_all()
+    rc, msg = bvh.validate(moved_aabbs, tight_fit=True)
+    assert rc == 0, msg

@@ -194,3 +194,30 @@ def test_host_ray_helpers_match_the_oracle_ray_new():
     assert np.array_equal(a[:, 0:3], o) and np.array_equal(a[:, 4:7].view(np.uint32), d.view(np.uint32))
     assert np.all(a[:, 3] == np.float32(0.25)) and np.all(a[:, 7] == np.float32(7.5))
     assert ray_args_of(want).view(np.uint32).tobytes() == a.view(np.uint32).tobytes()
+
+
+def _aabb(mn, mx):
+    a = np.zeros(8, np.float32)
+    a[0:3], a[4:7] = mn, mx
+    return a
+
+
+def test_reference_aabb_unit_tests():
+    # src/aabb.rs:222-360: the known answers of the reference's own Aabb tests, through the primitives the oracle builds on
+    L = ob.lib()
+    p = lambda a: a.ctypes.data_as(ob.C.c_void_p)  # noqa: E731
+    unit = _aabb([0, 0, 0], [1, 1, 1])
+    assert L.orc_aabb_half_area(p(unit)) == 3.0                                   # test_half_area (:313-317)
+    out = np.zeros(8, np.float32)
+    L.orc_aabb_union(p(unit), p(_aabb([0.5, 0.5, 0.5], [1.5, 1.5, 1.5])), p(out))    # test_union (:252-259)
+    assert np.array_equal(out[[0, 1, 2, 4, 5, 6]], np.array([0, 0, 0, 1.5, 1.5, 1.5], np.float32))
+    assert L.orc_aabb_intersect_aabb(p(unit), p(_aabb([0.5] * 3, [1.5] * 3))) == 1  # test_intersect_aabb (:341-348)
+    assert L.orc_aabb_intersect_aabb(p(unit), p(_aabb([1.5] * 3, [2.5] * 3))) == 0
+    pt = lambda x: np.array(x, np.float32)  # noqa: E731
+    assert L.orc_aabb_contains_point(p(unit), p(pt([0.5, 0.5, 0.5]))) == 1         # test_contains_point (:237-242)
+    assert L.orc_aabb_contains_point(p(unit), p(pt([1.5, 1.5, 1.5]))) == 0
+    assert L.orc_aabb_contains_point(p(unit), p(pt([1.0, 0.0, 1.0]))) == 1         # closed interval (cmpge / cmple)
+    ray = ob.make_rays(np.array([[-1, -1, -1]], np.float32), np.array([[1, 1, 1]], np.float32), 0.0, 3.4028235e38)
+    assert L.orc_aabb_intersect_ray(p(unit), p(ray)) == 1.0                         # test_intersect_ray (:350-357)
+    ray2 = ob.make_rays(np.array([[2, 2, 2]], np.float32), np.array([[1, 1, 1]], np.float32), 0.0, 3.4028235e38)
+    assert L.orc_aabb_intersect_ray(p(unit), p(ray2)) == np.inf
