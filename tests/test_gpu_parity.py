@@ -245,6 +245,23 @@ def test_reinsertion_run_with_candidates(api, scenes, scene):
         opt.run_with_candidates(got, np.array([wn.shape[0]], np.uint32), 1)
 
 
+def test_reference_test_reinsert_node_on_gpu(api):
+    # bvh2/mod.rs:1144-1163: Bvh2::reinsert_node for every node id in turn (one candidate, one iteration per call), the tree
+    # compared with the oracle's after the whole sequence and validated
+    tris = tu.demoscene(16, 0)
+    aabbs = ob.tri_aabbs(tris)
+    want = ob.build_bvh2_from_tris(tris, "fastest_build")
+    wn, wp = want.get()
+    got = api.Bvh2.upload(wn, wp, want.max_depth, True)
+    opt = api.ReinsertionOptimizer()
+    for node_id in range(1, wn.shape[0]):
+        ids = np.array([node_id], np.uint32)
+        assert opt.run_with_candidates(got, ids, 1) == want.reinsertion_run_with_candidates(ids, 1), node_id
+    assert_nodes_equal(got.download()[0], want.get()[0], "reinsert_node sequence")
+    rc, msg = ob.bvh2_from(got.download()[0], wp, want.max_depth).validate(aabbs, tight_fit=False)
+    assert rc == 0, msg
+
+
 @pytest.mark.parametrize("scene", SCENES)
 @pytest.mark.parametrize("max_prims,order", [(1, True), (3, True), (2, False)])
 def test_cwbvh_collapse_bytes(api, scenes, scene, max_prims, order):

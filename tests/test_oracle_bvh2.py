@@ -166,3 +166,19 @@ def test_reference_test_refit_all():
     bvh.refit_all()
     rc, msg = bvh.validate(moved_aabbs, tight_fit=True)
     assert rc == 0, msg
+
+
+def test_reference_test_reinsert_node():
+    # bvh2/mod.rs:1144-1163: build_bvh2_from_tris(demoscene(32), fastest_build), then Bvh2::reinsert_node(node_id) for every node
+    # id 1..len, validate. reinsert_node (bvh2/mod.rs:763-773) = find_reinsertion + apply when area_diff > 0, which is
+    # run_with_candidates over one candidate for one iteration.
+    tris = tu.demoscene(32, 0)
+    aabbs = ob.tri_aabbs(tris)
+    bvh = ob.build_bvh2_from_tris(tris, "fastest_build")
+    n0 = bvh.get()[0].tobytes()
+    applied = 0
+    for node_id in range(1, bvh.node_count):
+        applied += bvh.reinsertion_run_with_candidates(np.array([node_id], np.uint32), 1)
+    rc, msg = bvh.validate(aabbs, tight_fit=False)
+    assert rc == 0, msg
+    assert applied > 0 and bvh.get()[0].tobytes() != n0
