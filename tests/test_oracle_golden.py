@@ -221,3 +221,48 @@ def test_reference_aabb_unit_tests():
     assert L.orc_aabb_intersect_ray(p(unit), p(ray)) == 1.0                         # test_intersect_ray (:350-357)
     ray2 = ob.make_rays(np.array([[2, 2, 2]], np.float32), np.array([[1, 1, 1]], np.float32), 0.0, 3.4028235e38)
     assert L.orc_aabb_intersect_ray(p(unit), p(ray2)) == np.inf
+
+
+def test_reference_exact_aabbs_cwbvh_and_compute_parents():
+    # tests/mod.rs:387-446 (exact_aabbs_cwbvh): every inner child's exact box lies inside the parent's quantised child box AND inside
+    # the child node's own quantised frame; tests/mod.rs:325-349 (compute_parents_cwbvh): every node but the root is an inner child of
+    # exactly the node that references it. Accessors restated from cwbvh/node.rs:251-304 (child_aabb, aabb, is_leaf, child_node_index).
+    tris = tu.demoscene(100, 0)
+    aabbs = ob.tri_aabbs(tris)
+    bvh2 = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 1, 64, 0)  # very_fast_build (lib.rs:246-256)
+    cw = bvh2.to_cwbvh(3, True, True)
+    assert cw.validate(aabbs)[0] == 0
+    nodes, _, _ = cw.get()
+    exact = cw.exact_node_aabbs()
+    assert exact is not None and exact.shape[0] >= nodes.shape[0]
+    e = (nodes["e"].astype(np.uint32) << 23).view(np.float32)                      # compute_extent
+    p = nodes["p"]
+    own_min, own_max = p, p + e * np.float32(255.0)                                 # CwBvhNode::aabb, NQ_SCALE = 255
+    parent_of = np.full(nodes.shape[0], -1, np.int64)
+    checked = 0
+    for ch in range(8):
+        inner = (nodes["imask"] & (1 << ch)) != 0                                   # !is_leaf(ch)
+        idx = np.nonzero(inner)[0]
+        slot = (nodes["child_meta"][idx, ch] & 0b11111).astype(np.int64) - 24
+        rel = np.array([bin(int(m) & ~(0xFFFFFFFF << int(s)) & 0xFFFFFFFF).count("1") for m, s in zip(nodes["imask"][idx], slot)], np.int64)
+        child = nodes["child_base_idx"][idx].astype(np.int64) + rel                 # child_node_index
+        cmin = np.stack([nodes[f"child_min_{a}"][idx, ch] for a in "xyz"], axis=1).astype(np.float32) * e[idx] + p[idx]   # child_aabb
+        cmax = np.stack([nodes[f"child_max_{a}"][idx, ch] for a in "xyz"], axis=1).astype(np.float32) * e[idx] + p[idx]
+        ex_min, ex_max = exact[child][:, 0:3], exact[child][:, 4:7]
+        assert np.all(ex_min >= cmin) and np.all(ex_max <= cmax)
+        assert np.all(ex_min >= own_min[child]) and np.all(ex_max <= own_max[child])
+        assert np.all(parent_of[child] == -1)                                       # referenced once
+        parent_of[child] = idx
+        checked += idx.size
+    assert checked == nodes.shape[0] - 1 and parent_of[0] == -1 and np.all(parent_of[1:] >= 0)
+
+
+def test_reference_reuse_allocs():
+    # tests/mod.rs:448-500: a builder reused for a second, smaller scene (build_with_bvh) gives a tree that validates tightly.
+    # (On the GPU path the reuse is the context's result cache and arena: tests/test_gpu_parity.py builds many scenes per context.)
+    for side in (99, 98):
+        tris = tu.demoscene(side, 0)
+        aabbs = ob.tri_aabbs(tris)
+        bvh = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 14, 64, 0)  # PlocSearchDistance::default() = Medium
+        rc, msg = bvh.validate(aabbs, tight_fit=True)
+        assert rc == 0, msg
