@@ -211,6 +211,12 @@ public:
         ctx_.check(obvhs_cuda_cwbvh_download(ctx_.get(), h_.get(), nodes ? nodes->data() : nullptr,
                                              primitive_indices ? primitive_indices->data() : nullptr, total_aabb));
     }
+    // CwBvh::compute_parents, src/cwbvh/mod.rs:494-509
+    std::vector<uint32_t> compute_parents() const {
+        std::vector<uint32_t> parents(node_count());
+        ctx_.check(obvhs_cuda_cwbvh_compute_parents(ctx_.get(), h_.get(), parents.data()));
+        return parents;
+    }
     // CwBvh::exact_node_aabbs, src/cwbvh/mod.rs:47 (empty when the tree was converted without them)
     std::vector<Aabb> exact_node_aabbs() const {
         size_t count = 0;

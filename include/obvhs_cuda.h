@@ -224,6 +224,9 @@ int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t m
  * bvh2_to_cwbvh.rs:60-80): one Aabb per Bvh2 node slot, entry i < node_count = the unquantised box of wide node i, the rest
  * Aabb::empty(). *count receives the number of entries (0 when absent); out may be NULL to query it. */
 int obvhs_cuda_cwbvh_exact_node_aabbs(ObvhsContext* ctx, const ObvhsCwBvh* bvh, ObvhsAabb* out, size_t capacity, size_t* count);
+/* CwBvh::compute_parents (src/cwbvh/mod.rs:494-509): parents[node_index] = the node whose inner child slot references it,
+ * parents[0] = 0. `parents` holds node_count entries (host or device). */
+int obvhs_cuda_cwbvh_compute_parents(ObvhsContext* ctx, const ObvhsCwBvh* bvh, uint32_t* parents);
 /* build_cwbvh_from_tris(triangles, config, core_build_time) (cwbvh/builder.rs:20-85). core_build_seconds (optional)
  * is INCREMENTED by the device time of PLOC -> reinsertion -> collapse, as the reference's `+=` does. The permuted
  * triangle array (examples/obj_cwbvh.rs:63-67) is attached to the result so it can be traversed directly. */

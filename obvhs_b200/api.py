@@ -104,6 +104,7 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_node_count": (_sz, [_vp]),
     "obvhs_cuda_cwbvh_prim_count": (_sz, [_vp]),
     "obvhs_cuda_cwbvh_exact_node_aabbs": (_i32, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "obvhs_cuda_cwbvh_compute_parents": (_i32, [_vp, _vp, _vp]),
     "obvhs_cuda_cwbvh_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_cwbvh_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _PP]),
     "obvhs_cuda_cwbvh_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
@@ -610,6 +611,12 @@ class CwBvh:
         total = np.zeros(8, dtype=np.float32)
         self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_download(self.ctx.h, self.h, _ptr(nodes), _ptr(prims), _ptr(total)))
         return nodes, prims, total
+
+    def compute_parents(self, out=None):
+        """CwBvh::compute_parents (src/cwbvh/mod.rs:494-509): parent node index per node (parents[0] = 0)."""
+        parents = out if out is not None else np.zeros(self.node_count, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_compute_parents(self.ctx.h, self.h, _ptr(parents)))
+        return parents
 
     def exact_node_aabbs(self):
         """CwBvh::exact_node_aabbs (src/cwbvh/mod.rs:47) as an (n, 8) float32 array, or None when absent."""

@@ -777,6 +777,21 @@ int obvhs_cuda_cwbvh_exact_node_aabbs(ObvhsContext* ctx, const ObvhsCwBvh* bvh, 
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return OBVHS_OK;
 }
+int obvhs_cuda_cwbvh_compute_parents(ObvhsContext* ctx, const ObvhsCwBvh* bvh, uint32_t* parents) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (parents || bvh->node_count == 0), "null argument");
+    if (bvh->node_count == 0) return OBVHS_OK;
+    DevBuf<u32> st;
+    u32* d = parents;
+    if (!obvhs_is_device_ptr(parents)) {
+        CU_TRY(ctx, st.alloc(bvh->node_count, ctx->stream));
+        d = st.p;
+    }
+    ST_TRY(cwbvh_compute_parents_device(ctx, bvh, d));
+    if (d != parents) ST_TRY(copy_out(ctx, parents, (const u32*)d, bvh->node_count));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OBVHS_OK;
+}
 int obvhs_cuda_cwbvh_uses_spatial_splits(const ObvhsCwBvh* bvh) { return bvh && bvh->uses_spatial_splits; }
 void obvhs_cuda_cwbvh_set_uses_spatial_splits(ObvhsCwBvh* bvh, int v) { if (bvh) bvh->uses_spatial_splits = v != 0; }
 int obvhs_cuda_bvh2_uses_spatial_splits(const ObvhsBvh2* bvh) { return bvh && bvh->uses_spatial_splits; }

@@ -304,6 +304,7 @@ int ploc_compute_rebuild_path_flags_device(ObvhsContext* ctx, const ObvhsBvh2* b
 // query_kind 0 = boxes (2 float4 per query), 1 = points (1 float4). counts / ids may be host or device.
 int bvh2_query_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, int query_kind, const float4* d_queries, size_t n, u32* counts, u32* ids,
                       size_t capacity, size_t* total_out);
+int cwbvh_compute_parents_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, u32* d_parents);
 int cwbvh_query_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, int query_kind, const float4* d_queries, size_t n, const float* host_dir3,
                        u32* counts, u32* ids, size_t capacity, size_t* total_out);
 // splits.cu : spatial pre-splits (src/splits.rs). Arrays live in the arena of the API call in flight and grow like the Vecs.

@@ -246,6 +246,32 @@ int bvh2_query_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, int query_kind, c
                 : run_query<0, 1>(ctx, bvh->nodes, nc, 0, 0, d_queries, n, counts, ids, capacity, total_out);
 }
 
+namespace {
+// CwBvh::compute_parents (cwbvh/mod.rs:494-509): one thread per (node, child slot); an occupied inner slot writes the node's index
+// into its child's entry. Every node but the root is referenced by exactly one slot, so the writes never collide; parents[0] = 0.
+__global__ void __launch_bounds__(256) cwbvh_parents_kernel(const uint4* __restrict__ nodes, u32 node_count, u32* __restrict__ parents) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 node = t >> 3, ch = t & 7u;
+    if (node >= node_count) return;
+    if (t == 0) parents[0] = 0;
+    const uint4 q0 = __ldg(nodes + (size_t)node * 5), q1 = __ldg(nodes + (size_t)node * 5 + 1);
+    const u32 imask = q0.w >> 24;
+    const u32 meta = ((ch < 4 ? q1.z : q1.w) >> ((ch & 3u) * 8u)) & 0xffu;  // child_meta[ch]
+    if (meta == 0 || !(imask & (1u << ch))) return;                         // is_child_empty / is_leaf (node.rs:279-286)
+    const u32 slot = (meta & 31u) - 24u;                                    // child_node_index (node.rs:299-304)
+    parents[q1.x + __popc(imask & ~(0xffffffffu << slot))] = node;
+}
+}  // namespace
+
+int cwbvh_compute_parents_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, u32* d_parents) {
+    if (bvh->node_count == 0) return OBVHS_OK;
+    CU_TRY(ctx, cudaMemsetAsync(d_parents, 0, bvh->node_count * sizeof(u32), ctx->stream));  // vec![0; nodes.len()]
+    cwbvh_parents_kernel<<<div_up(bvh->node_count * 8, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(bvh->nodes), (u32)bvh->node_count,
+                                                                                    d_parents);
+    KERNEL_CHECK(ctx);
+    return OBVHS_OK;
+}
+
 int cwbvh_query_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, int query_kind, const float4* d_queries, size_t n, const float* host_dir3,
                        u32* counts, u32* ids, size_t capacity, size_t* total_out) {
     const u32 root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:149-153

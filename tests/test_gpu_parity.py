@@ -430,6 +430,29 @@ def test_cwbvh_exact_node_aabbs(api, scenes, scene):
     assert api.bvh2_to_cwbvh(api.PlocBuilder().build(6, aabbs), 3, True, False).exact_node_aabbs() is None
 
 
+@pytest.mark.parametrize("scene", ["cornell", "terrain32", "kitchen"])
+def test_cwbvh_compute_parents(api, scenes, scene):
+    # CwBvh::compute_parents (cwbvh/mod.rs:494-509) and the property the reference's test checks (tests/mod.rs:325-349): the
+    # parent's inner child slots contain the child
+    import torch
+    from test_oracle_golden import cwbvh_parents_numpy
+
+    tris = scenes[scene]
+    bvh = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build())
+    nodes, _, _ = bvh.download()
+    want = cwbvh_parents_numpy(nodes)
+    got = bvh.compute_parents()
+    assert got[0] == 0 and np.array_equal(got, want)
+    d = torch.empty(nodes.shape[0], dtype=torch.int32, device="cuda")
+    bvh.compute_parents(out=d)
+    bvh.ctx.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), want)
+    if nodes.shape[0] > 1:
+        assert np.all(got[1:] < np.arange(1, nodes.shape[0]))  # parents come first in the converter's layout
+    empty = api.build_cwbvh_from_tris(np.zeros((0, 12), np.float32), api.BvhBuildParams.fast_build())
+    assert empty.compute_parents().shape[0] == empty.node_count
+
+
 def test_large_scene_full_parity_and_properties(api):
     # 1M-triangle soup + 0.5M terrain: full byte parity against the oracle (seconds on the CPU) plus size-independent
     # properties: sorted keys, stable ties, valid trees, closest hit <= any brute-force sample

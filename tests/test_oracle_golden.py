@@ -223,6 +223,19 @@ def test_reference_aabb_unit_tests():
     assert L.orc_aabb_intersect_ray(p(unit), p(ray2)) == np.inf
 
 
+def cwbvh_parents_numpy(nodes):
+    """CwBvh::compute_parents (cwbvh/mod.rs:494-509) restated with numpy over CWBVH_NODE records."""
+    parents = np.zeros(nodes.shape[0], np.uint32)
+    for ch in range(8):
+        inner = ((nodes["imask"] & (1 << ch)) != 0) & (nodes["child_meta"][:, ch] != 0)
+        idx = np.nonzero(inner)[0]
+        slot = (nodes["child_meta"][idx, ch] & 0b11111).astype(np.int64) - 24
+        below = nodes["imask"][idx].astype(np.int64) & ((1 << slot) - 1)
+        rel = np.array([bin(int(b)).count("1") for b in below], np.int64)
+        parents[nodes["child_base_idx"][idx].astype(np.int64) + rel] = idx
+    return parents
+
+
 def test_reference_exact_aabbs_cwbvh_and_compute_parents():
     # tests/mod.rs:387-446 (exact_aabbs_cwbvh): every inner child's exact box lies inside the parent's quantised child box AND inside
     # the child node's own quantised frame; tests/mod.rs:325-349 (compute_parents_cwbvh): every node but the root is an inner child of
@@ -255,6 +268,7 @@ def test_reference_exact_aabbs_cwbvh_and_compute_parents():
         parent_of[child] = idx
         checked += idx.size
     assert checked == nodes.shape[0] - 1 and parent_of[0] == -1 and np.all(parent_of[1:] >= 0)
+    assert np.array_equal(cwbvh_parents_numpy(nodes)[1:], parent_of[1:].astype(np.uint32))
 
 
 def test_reference_reuse_allocs():
