@@ -2224,6 +2224,133 @@ void orc_cwbvh_get(const OrcCwBvh* c, OrcCwBvhNode* nodes, u32* primitive_indice
     if (total) *total = c->total_aabb;
 }
 int orc_cwbvh_validate(const OrcCwBvh* c, const OrcAabb* prim_aabbs, size_t n, char* msg) { return cwbvh_validate(*c, prim_aabbs, n, msg); }
+
+// ---- CwBvh::order_children / order_node_children as a separate pass (cwbvh/mod.rs:520-735) -------------------------------
+// Not on the GPU path yet; restated here so that the next widening step has a pinned checker
+// (tests/mod.rs:351-385 order_children_cwbvh, :431-445).
+namespace {
+inline bool cw_is_child_empty(const OrcCwBvhNode& n, int ch) { return n.child_meta[ch] == 0; }          // node.rs:284-286
+inline bool cw_is_leaf(const OrcCwBvhNode& n, int ch) { return (n.imask & (1u << ch)) == 0; }           // node.rs:279-281
+inline u32 cw_child_node_index(const OrcCwBvhNode& n, int ch) {                                        // node.rs:299-304
+    const u32 slot_index = (u32)(n.child_meta[ch] & 0b11111) - 24u;
+    return n.child_base_idx + (u32)__builtin_popcount((u32)n.imask & ~(0xffffffffu << slot_index));
+}
+inline OrcAabb cw_node_aabb_compressed(const OrcCwBvhNode& n) {                                        // node.rs:261-275
+    OrcAabb a = aabb_empty();
+    for (int k = 0; k < 3; k++) {
+        u32 bits = (u32)n.e[k] << 23;
+        float e;
+        memcpy(&e, &bits, 4);
+        a.min[k] = n.p[k];
+        a.max[k] = n.p[k] + e * 255.0f;  // p + e * NQ_SCALE
+    }
+    return a;
+}
+inline V3 aabb_center(const OrcAabb& a) { return (v3(a.max) + v3(a.min)) * 0.5f; }                      // aabb.rs:113-115
+
+void cwbvh_order_node_children(OrcCwBvh& bvh, const OrcAabb* prim_aabbs, size_t node_index, bool direct_layout) {
+    const OrcCwBvhNode old_node = bvh.nodes[node_index];
+    const bool have_exact = !bvh.exact_node_aabbs.empty();
+    auto node_aabb = [&](size_t i) { return have_exact ? bvh.exact_node_aabbs[i] : cw_node_aabb_compressed(bvh.nodes[i]); };  // :737-745
+    const V3 center = aabb_center(cw_node_aabb_compressed(old_node));
+    float cost[8][8];
+    for (auto& row : cost)
+        for (float& c : row) c = 3.40282347e+38f;
+    size_t child_inner_count = 0;
+    for (int ch = 0; ch < 8; ch++)
+        if (!cw_is_child_empty(old_node, ch) && !cw_is_leaf(old_node, ch)) child_inner_count++;
+    V3 old_child_centers[8] = {};
+    for (int ch = 0; ch < 8; ch++) {
+        if (cw_is_child_empty(old_node, ch)) continue;
+        if (cw_is_leaf(old_node, ch)) {
+            const u32 meta = old_node.child_meta[ch];  // child_primitives, node.rs:290-295
+            const u32 start = old_node.primitive_base_idx + (meta & 0b11111u), count = (u32)__builtin_popcount(meta & 0b11100000u);
+            OrcAabb a = aabb_empty();
+            for (u32 i = 0; i < count; i++) {
+                size_t prim_index = start + i;
+                if (!direct_layout) prim_index = bvh.primitive_indices[prim_index];
+                a = aabb_union(a, prim_aabbs[prim_index]);
+            }
+            old_child_centers[ch] = aabb_center(a);
+        } else {
+            old_child_centers[ch] = aabb_center(node_aabb(cw_child_node_index(old_node, ch)));
+        }
+    }
+    for (int s = 0; s < 8; s++) {
+        const V3 d = V3{(s & 0b100) ? -1.0f : 1.0f, (s & 0b010) ? -1.0f : 1.0f, (s & 0b001) ? -1.0f : 1.0f};
+        for (int ch = 0; ch < 8; ch++) {
+            if (cw_is_child_empty(old_node, ch)) continue;
+            cost[ch][s] = dot(d, old_child_centers[ch] - center);
+        }
+    }
+    size_t assignment[8];
+    bool slot_filled[8] = {};
+    for (size_t& a : assignment) a = (size_t)INVALID32;
+    for (;;) {  // greedy: cheapest unfilled slot of any unassigned child
+        float min_cost = 3.40282347e+38f;
+        size_t min_slot = (size_t)INVALID32, min_index = (size_t)INVALID32;
+        for (int ch = 0; ch < 8; ch++) {
+            if (cw_is_child_empty(old_node, ch) || assignment[ch] != (size_t)INVALID32) continue;
+            for (int sl = 0; sl < 8; sl++)
+                if (!slot_filled[sl] && cost[ch][sl] < min_cost) {
+                    min_cost = cost[ch][sl];
+                    min_slot = (size_t)sl;
+                    min_index = (size_t)ch;
+                }
+        }
+        if (min_slot == (size_t)INVALID32) break;
+        slot_filled[min_slot] = true;
+        assignment[min_index] = min_slot;
+    }
+    OrcCwBvhNode new_node = old_node;
+    new_node.imask = 0;
+    for (int ch = 0; ch < 8; ch++) new_node.child_meta[ch] = 0;
+    for (int ch = 0; ch < 8; ch++) {
+        if (cw_is_child_empty(old_node, ch)) continue;
+        const size_t new_ch = assignment[ch];
+        if (new_ch >= 8) {
+            fprintf(stderr, "oracle: order_node_children left a child unassigned -- the reference asserts\n");
+            abort();
+        }
+        if (cw_is_leaf(old_node, ch)) new_node.child_meta[new_ch] = old_node.child_meta[ch];
+        else {
+            new_node.imask |= (uint8_t)(1u << new_ch);
+            new_node.child_meta[new_ch] = (uint8_t)((24 + new_ch) | 0b00100000);
+        }
+        new_node.child_min_x[new_ch] = old_node.child_min_x[ch];
+        new_node.child_max_x[new_ch] = old_node.child_max_x[ch];
+        new_node.child_min_y[new_ch] = old_node.child_min_y[ch];
+        new_node.child_max_y[new_ch] = old_node.child_max_y[ch];
+        new_node.child_min_z[new_ch] = old_node.child_min_z[ch];
+        new_node.child_max_z[new_ch] = old_node.child_max_z[ch];
+    }
+    if (child_inner_count == 0) {
+        bvh.nodes[node_index] = new_node;
+        return;
+    }
+    OrcCwBvhNode old_child_nodes[8];
+    OrcAabb old_child_exact[8];
+    for (int ch = 0; ch < 8; ch++) {
+        if (cw_is_child_empty(old_node, ch) || cw_is_leaf(old_node, ch)) continue;
+        const u32 ci = cw_child_node_index(old_node, ch);
+        old_child_nodes[ch] = bvh.nodes[ci];
+        if (have_exact) old_child_exact[ch] = bvh.exact_node_aabbs[ci];
+    }
+    for (int ch = 0; ch < 8; ch++) {
+        if (cw_is_child_empty(old_node, ch) || assignment[ch] == (size_t)INVALID32 || cw_is_leaf(old_node, ch)) continue;
+        const size_t new_idx = cw_child_node_index(new_node, (int)assignment[ch]);
+        bvh.nodes[new_idx] = old_child_nodes[ch];
+        if (have_exact) bvh.exact_node_aabbs[new_idx] = old_child_exact[ch];
+    }
+    bvh.nodes[node_index] = new_node;
+}
+}  // namespace
+void orc_cwbvh_order_node_children(OrcCwBvh* c, const OrcAabb* prim_aabbs, size_t node_index, int direct_layout) {
+    cwbvh_order_node_children(*c, prim_aabbs, node_index, direct_layout != 0);
+}
+void orc_cwbvh_order_children(OrcCwBvh* c, const OrcAabb* prim_aabbs, int direct_layout) {  // cwbvh/mod.rs:520-524
+    for (size_t i = 0; i < c->nodes.size(); i++) cwbvh_order_node_children(*c, prim_aabbs, i, direct_layout != 0);
+}
 // CwBvh::exact_node_aabbs (cwbvh/mod.rs:47): bvh2.nodes.len() entries, Aabb::empty() beyond the wide nodes; returns the length
 size_t orc_cwbvh_exact_node_aabbs(const OrcCwBvh* c, OrcAabb* out, size_t cap) {
     size_t m = std::min(cap, c->exact_node_aabbs.size());

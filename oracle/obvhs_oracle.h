@@ -150,6 +150,8 @@ size_t orc_cwbvh_point_traverse(const OrcCwBvh*, const float* points4, size_t n,
                                 uint32_t* prim_ids, size_t cap);
 float orc_triangle_intersect(const OrcTriangle* tri, const OrcRay* ray);               /* triangle.rs:35-76 */
 void  orc_triangle_normal(const OrcTriangle* tri, float* out3);                         /* triangle.rs:20-24 */
+void  orc_cwbvh_order_node_children(OrcCwBvh*, const OrcAabb* prim_aabbs, size_t node_index, int direct_layout); /* cwbvh/mod.rs:538-735 */
+void  orc_cwbvh_order_children(OrcCwBvh*, const OrcAabb* prim_aabbs, int direct_layout);                          /* cwbvh/mod.rs:520-524 */
 float orc_aabb_half_area(const OrcAabb* a);                                              /* aabb.rs:151-154 */
 void  orc_aabb_union(const OrcAabb* a, const OrcAabb* b, OrcAabb* out);                 /* aabb.rs:84-89 */
 float orc_aabb_intersect_ray(const OrcAabb* a, const OrcRay* ray);                      /* aabb.rs:186-206 */

@@ -87,6 +87,8 @@ def lib():
             "orc_cwbvh_point_traverse": (sz, [vp, vp, sz, vp, vp, vp, sz]),
             "orc_triangle_intersect": (f32, [vp, vp]),
             "orc_triangle_normal": (None, [vp, vp]),
+            "orc_cwbvh_order_node_children": (None, [vp, vp, sz, i32]),
+            "orc_cwbvh_order_children": (None, [vp, vp, i32]),
             "orc_aabb_half_area": (f32, [vp]),
             "orc_aabb_union": (None, [vp, vp, vp]),
             "orc_aabb_intersect_ray": (f32, [vp, vp]),
@@ -332,6 +334,14 @@ class CwBvh:
         """examples/obj_cwbvh.rs:63-67: triangles permuted by primitive_indices."""
         _, prims, _ = self.get()
         return np.ascontiguousarray(np.asarray(tris, dtype=np.float32)[prims])
+
+    def order_children(self, prim_aabbs, direct_layout=False):
+        """CwBvh::order_children (cwbvh/mod.rs:520-524)"""
+        lib().orc_cwbvh_order_children(self.h, _p(_f32c(prim_aabbs, 8)), int(direct_layout))
+
+    def order_node_children(self, prim_aabbs, node_index, direct_layout=False):
+        """CwBvh::order_node_children (cwbvh/mod.rs:538-735)"""
+        lib().orc_cwbvh_order_node_children(self.h, _p(_f32c(prim_aabbs, 8)), int(node_index), int(direct_layout))
 
     def exact_node_aabbs(self):
         """CwBvh::exact_node_aabbs (None when the tree was converted without them)"""

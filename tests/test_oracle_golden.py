@@ -280,3 +280,38 @@ def test_reference_reuse_allocs():
         bvh = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 14, 64, 0)  # PlocSearchDistance::default() = Medium
         rc, msg = bvh.validate(aabbs, tight_fit=True)
         assert rc == 0, msg
+
+
+def test_reference_order_children_cwbvh():
+    # tests/mod.rs:351-385 (order_children_cwbvh) and :431-445 (the tail of exact_aabbs_cwbvh): CwBvh::order_node_children on every
+    # node, then CwBvh::order_children, validating after each; with exact_node_aabbs present they move with their nodes.
+    tris = tu.demoscene(100, 0)
+    aabbs = ob.tri_aabbs(tris)
+    rays = camera.primary_rays(camera.Camera(64, 64, 60.0, np.array([0.5, 0.9, 1.7], np.float32), np.array([0.5, 0.0, 0.5], np.float32)))
+    for with_exact in (False, True):
+        bvh2 = ob.ploc_build(aabbs, np.arange(tris.shape[0], dtype=np.uint32), 1, 64, 0)  # very_fast_build
+        cw = bvh2.to_cwbvh(3, True, with_exact)
+        assert cw.validate(aabbs)[0] == 0
+        before = cw.ray_traverse(cw.bvh_tris(tris), rays)
+        n0 = cw.get()[0].tobytes()
+        if not with_exact:
+            for node in range(cw.node_count):
+                cw.order_node_children(aabbs, node, False)
+            rc, msg = cw.validate(aabbs)
+            assert rc == 0, msg
+        cw.order_children(aabbs, False)
+        rc, msg = cw.validate(aabbs)
+        assert rc == 0, msg
+        cw.order_children(aabbs, False)
+        rc, msg = cw.validate(aabbs)
+        assert rc == 0, msg
+        nodes, prims, _ = cw.get()
+        assert nodes.tobytes() != n0  # "a slightly different order" than the converter's (cwbvh/mod.rs:510-513)
+        # the same tree in another child order: identical closest hits (distances bit for bit)
+        after = cw.ray_traverse(cw.bvh_tris(tris), rays)
+        assert np.array_equal(after["t"].view(np.uint32), before["t"].view(np.uint32)) and (before["t"] < 3e38).sum() > 1000
+        assert np.array_equal(cwbvh_parents_numpy(nodes)[1:] < np.arange(1, nodes.shape[0]), np.ones(nodes.shape[0] - 1, bool))
+        if with_exact:  # exact boxes still inside their (moved) nodes' frames
+            exact = cw.exact_node_aabbs()
+            e = (nodes["e"].astype(np.uint32) << 23).view(np.float32)
+            assert np.all(exact[: nodes.shape[0], 0:3] >= nodes["p"]) and np.all(exact[: nodes.shape[0], 4:7] <= nodes["p"] + e * np.float32(255.0))
