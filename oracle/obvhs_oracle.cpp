@@ -2073,6 +2073,36 @@ int orc_bvh2_validate(const OrcBvh2* b, const OrcAabb* prim_aabbs, size_t n, int
     return bvh2_validate(*b, prim_aabbs, n, tight_fit != 0, msg);
 }
 void orc_bvh2_compute_parents(OrcBvh2* b) { compute_parents(*b); }
+// Bvh2::reorder_in_stack_traversal_order (bvh2/mod.rs:462-500): a pure re-indexing (parents before children, sibling pairs in the
+// pop order of a stack that receives the first child's pair before the second's). Not on the GPU path yet;
+// restated so that the reference's test_reinsertion (bvh2/reinsertion.rs:394-436) runs here exactly as written.
+void orc_bvh2_reorder_in_stack_traversal_order(OrcBvh2* b) {
+    OrcBvh2& bvh = *b;
+    if (bvh.nodes.size() < 2) return;
+    std::vector<OrcBvh2Node> new_nodes;
+    new_nodes.reserve(bvh.nodes.size());
+    std::vector<u32> mapping(bvh.nodes.size(), 0);
+    std::vector<u32> stack;
+    stack.push_back(bvh.nodes[0].first_index);
+    new_nodes.push_back(bvh.nodes[0]);
+    while (!stack.empty()) {
+        const u32 cur = stack.back();
+        stack.pop_back();
+        const OrcBvh2Node node_a = bvh.nodes[cur], node_b = bvh.nodes[(size_t)cur + 1];
+        if (!is_leaf(node_a)) stack.push_back(node_a.first_index);
+        if (!is_leaf(node_b)) stack.push_back(node_b.first_index);
+        const u32 new_idx = (u32)new_nodes.size();
+        mapping[cur] = new_idx;
+        mapping[(size_t)cur + 1] = new_idx + 1;
+        new_nodes.push_back(node_a);
+        new_nodes.push_back(node_b);
+    }
+    for (OrcBvh2Node& n : new_nodes)
+        if (!is_leaf(n)) n.first_index = mapping[n.first_index];
+    bvh.nodes = std::move(new_nodes);
+    if (!bvh.parents.empty()) compute_parents(bvh);  // update_parents
+    bvh.children_are_ordered_after_parents = true;
+}
 void orc_bvh2_collapse(OrcBvh2* b, u32 max_prims, float traversal_cost) { collapse(*b, max_prims, traversal_cost); }
 int orc_bvh2_has_parents(const OrcBvh2* b) { return b->parents.empty() ? 0 : 1; }
 void orc_bvh2_ray_traverse(const OrcBvh2* b, const OrcTriangle* bvh_tris, const OrcRay* rays, size_t n, OrcRayHit* hits, int threads,

@@ -66,6 +66,7 @@ OrcBvh2* orc_bvh2_from(const OrcBvh2Node* nodes, size_t n_nodes, const uint32_t*
 /* returns 0 when valid, else a negative code; msg (>=256 B) receives a description (bvh2/mod.rs:786-981) */
 int      orc_bvh2_validate(const OrcBvh2*, const OrcAabb* prim_aabbs, size_t n, int tight_fit, char* msg);
 void     orc_bvh2_compute_parents(OrcBvh2*);                                            /* bvh2/mod.rs:586-619 */
+void  orc_bvh2_reorder_in_stack_traversal_order(OrcBvh2*);                              /* bvh2/mod.rs:462-500 */
 void     orc_bvh2_collapse(OrcBvh2*, uint32_t max_prims, float traversal_cost);             /* bvh2/leaf_collapser.rs:21-192 */
 int      orc_bvh2_has_parents(const OrcBvh2*);
 void     orc_bvh2_refit_all(OrcBvh2*);                                                  /* bvh2/mod.rs:527-569 */

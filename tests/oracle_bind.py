@@ -50,6 +50,7 @@ def lib():
             "orc_bvh2_validate": (i32, [vp, vp, sz, i32, C.c_char_p]),
             "orc_bvh2_compute_parents": (None, [vp]),
             "orc_bvh2_refit_all": (None, [vp]),
+            "orc_bvh2_reorder_in_stack_traversal_order": (None, [vp]),
             "orc_ploc_full_rebuild": (None, [vp, u32, i32, sz, i32]),
             "orc_ploc_partial_rebuild": (None, [vp, vp, u32, i32, sz, i32]),
             "orc_compute_rebuild_path_flags": (None, [vp, vp, sz, vp]),
@@ -185,6 +186,10 @@ class Bvh2:
 
     def refit_all(self):
         lib().orc_bvh2_refit_all(self.h)
+
+    def reorder_in_stack_traversal_order(self):
+        """Bvh2::reorder_in_stack_traversal_order (bvh2/mod.rs:462-500)"""
+        lib().orc_bvh2_reorder_in_stack_traversal_order(self.h)
 
     def set_leaf_aabbs(self, prim_aabbs):
         prim_aabbs = _f32c(prim_aabbs, 8)

@@ -128,9 +128,8 @@ def test_bvh2_and_cwbvh_agree_on_incoherent_rays():
 
 
 def test_reference_test_reinsertion():
-    # bvh2/reinsertion.rs:394-436: VeryLow PLOC over demoscene(32), validate, run(0.25), validate, run(0.5), validate -- with
-    # and without parents computed up front. (The reference also calls reorder_in_stack_traversal_order between the two runs: a
-    # pure re-indexing of the nodes that this path does not carry; the invariants checked are the same.)
+    # bvh2/reinsertion.rs:394-436 as written: VeryLow PLOC over demoscene(32), validate, run(0.25), validate,
+    # reorder_in_stack_traversal_order, run(0.5), validate -- with and without parents computed up front
     tris = tu.demoscene(32, 0)
     aabbs = ob.tri_aabbs(tris)
     for with_parents in (False, True):
@@ -144,6 +143,16 @@ def test_reference_test_reinsertion():
             bvh.reinsertion_run(ratio)
             rc, msg = bvh.validate(aabbs, tight_fit=False)
             assert rc == 0, msg
+            if ratio == 0.25:
+                nodes_before = bvh.get()[0]
+                bvh.reorder_in_stack_traversal_order()
+                nodes_after = bvh.get()[0]
+                # a re-indexing: same multiset of boxes, parents now precede their children
+                assert sorted(nodes_before["aabb"].tobytes()[i:i + 32] for i in range(0, nodes_before.shape[0] * 32, 32)) == \
+                    sorted(nodes_after["aabb"].tobytes()[i:i + 32] for i in range(0, nodes_after.shape[0] * 32, 32))
+                inner = nodes_after["prim_count"] == 0
+                assert np.all(nodes_after["first_index"][inner] > np.nonzero(inner)[0])
+                assert bvh.validate(aabbs, tight_fit=False)[0] == 0
         assert bvh.get()[0].tobytes() != n0  # the optimizer did move nodes
         assert np.array_equal(np.sort(bvh.get()[1]), np.arange(tris.shape[0], dtype=np.uint32))
 
