@@ -298,6 +298,16 @@ private:
     Context ctx_;
 };
 
+// Bvh2::compute_primitives_to_nodes(nodes, primitive_indices, &mut primitives_to_nodes), src/bvh2/mod.rs:647-665, over downloaded
+// arrays (host-side bookkeeping): the leaf node holding each primitive id, INVALID_ID when none
+inline std::vector<uint32_t> compute_primitives_to_nodes(const std::vector<Bvh2Node>& nodes, const std::vector<uint32_t>& primitive_indices) {
+    std::vector<uint32_t> out(primitive_indices.size(), INVALID_ID);
+    for (size_t node_id = 0; node_id < nodes.size(); node_id++)
+        for (uint32_t k = nodes[node_id].first_index, end = k + nodes[node_id].prim_count; nodes[node_id].prim_count != 0 && k < end; k++)
+            out[primitive_indices[k]] = (uint32_t)node_id;
+    return out;
+}
+
 // compute_rebuild_path_flags(bvh, leaves, flags), src/ploc/rebuild.rs:12-43
 inline std::vector<uint8_t> compute_rebuild_path_flags(const Bvh2& bvh, const uint32_t* leaves, size_t n_leaves) {
     std::vector<uint8_t> flags(bvh.node_count());

@@ -350,6 +350,13 @@ class Bvh2:
     def compute_parents(self):
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_compute_parents(self.ctx.h, self.h))
 
+    def compute_primitives_to_nodes(self):
+        """Bvh2::compute_primitives_to_nodes (src/bvh2/mod.rs:647-665) from the downloaded tree (host-side bookkeeping)."""
+        from .types import compute_primitives_to_nodes
+
+        nodes, prims = self.download()
+        return compute_primitives_to_nodes(nodes, prims)
+
     def refit_all(self):
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_refit_all(self.ctx.h, self.h))
 

@@ -117,3 +117,19 @@ def ray_args_of(rays: np.ndarray) -> np.ndarray:
     a[:, 4:7] = rays[:, 4:7]
     a[:, 7] = rays[:, 13]
     return a
+
+
+def compute_primitives_to_nodes(nodes: np.ndarray, primitive_indices: np.ndarray) -> np.ndarray:
+    """`Bvh2::compute_primitives_to_nodes` (reference src/bvh2/mod.rs:647-665) over downloaded arrays: for every primitive id the
+    leaf NODE that holds it (0xFFFFFFFF when none; with spatial splits the last leaf in node order wins, as in the reference's
+    loop). What examples/physics.rs indexes before `resize_node` / `reinsert_node`; host-side bookkeeping, not a kernel."""
+    prims = np.asarray(primitive_indices, dtype=np.uint32)
+    out = np.full(prims.shape[0], 0xFFFFFFFF, dtype=np.uint32)
+    leaf = np.nonzero(nodes["prim_count"] != 0)[0]
+    counts = nodes["prim_count"][leaf].astype(np.int64)
+    if leaf.size == 0 or counts.sum() == 0:
+        return out
+    first = np.repeat(nodes["first_index"][leaf].astype(np.int64), counts)
+    within = np.arange(counts.sum(), dtype=np.int64) - np.repeat(np.cumsum(counts) - counts, counts)
+    out[prims[first + within]] = np.repeat(leaf.astype(np.uint32), counts)  # repeated ids: the last assignment wins
+    return out

@@ -104,6 +104,18 @@ int main() {
     }
     const size_t m = rays.size();
 
+    {  // host-only pieces of the header (these run without a GPU too)
+        CHECK(safe_inverse(0.0f) == 8388608.0f && safe_inverse(-0.0f) == -8388608.0f && safe_inverse(4.0f) == 0.25f, "safe_inverse");
+        std::vector<Bvh2Node> tree(3);
+        std::memset(tree.data(), 0, tree.size() * sizeof(Bvh2Node));
+        tree[0].first_index = 1;                             // root: inner, children 1 and 2
+        tree[1].prim_count = 2, tree[1].first_index = 0;     // leaf over slots 0..1
+        tree[2].prim_count = 1, tree[2].first_index = 2;     // leaf over slot 2
+        const std::vector<uint32_t> p2n = compute_primitives_to_nodes(tree, {2u, 0u, 1u});
+        CHECK(p2n.size() == 3 && p2n[2] == 1 && p2n[0] == 1 && p2n[1] == 2, "compute_primitives_to_nodes");
+        if (failures) return 1;
+    }
+
     try {
         Context ctx(0);
         const BvhBuildParams params = BvhBuildParams::fast_build();

@@ -191,3 +191,24 @@ def test_reference_test_reinsert_node():
     rc, msg = bvh.validate(aabbs, tight_fit=False)
     assert rc == 0, msg
     assert applied > 0 and bvh.get()[0].tobytes() != n0
+
+
+def test_compute_primitives_to_nodes_host_helper():
+    # bvh2/mod.rs:647-665 against the reference's loop written out, on plain, collapsed and pre-split trees
+    from obvhs_b200.types import compute_primitives_to_nodes
+
+    tris = tu.soup_with_large_triangles(2000, 30, 4)
+    for preset in ("fastest_build", "medium_build", "slow_build"):
+        b = ob.build_bvh2_from_tris(tris, preset)
+        nodes, prims = b.get()
+        want = np.full(prims.shape[0], 0xFFFFFFFF, np.uint32)
+        for node_id in range(nodes.shape[0]):
+            if nodes["prim_count"][node_id] != 0:
+                s = int(nodes["first_index"][node_id])
+                for k in range(s, s + int(nodes["prim_count"][node_id])):
+                    want[prims[k]] = node_id
+        got = compute_primitives_to_nodes(nodes, prims)
+        assert np.array_equal(got, want), preset
+        held = got[got != 0xFFFFFFFF]
+        assert np.all(nodes["prim_count"][held] != 0)
+    assert compute_primitives_to_nodes(np.zeros(0, ob.BVH2_NODE), np.zeros(0, np.uint32)).shape == (0,)
