@@ -143,6 +143,12 @@ struct DeviceScope {  // makes the context's device current for the duration of 
     }
     ~DeviceScope() {
         ctx->api_depth--;
+        if (ctx->api_depth == 0 && ctx->staged_host) {
+            // a host buffer was copied with cudaMemcpyAsync (truly asynchronous when it is pinned): every entry point behaves
+            // synchronously towards host inputs, so the caller may overwrite them right after the call
+            cudaStreamSynchronize(ctx->stream);
+            ctx->staged_host = false;
+        }
         ctx->arena_block = mark_block;
         ctx->arena_off = mark_off;
         ctx->arena_used = mark_used;
@@ -266,6 +272,7 @@ int obvhs_cuda_create(int device, void* stream, ObvhsContext** out) {
     const char* tr = getenv("OBVHS_TRACE");
     ctx->trace = tr && tr[0] == '1';
     if (const char* tm = getenv("OBVHS_TRAVERSE")) obvhs_cuda_set_option(ctx, "traverse", tm);
+    if (const char* tv = getenv("OBVHS_TRAVERSE_VARIANT")) obvhs_cuda_set_option(ctx, "traverse_variant", tv);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -315,8 +322,8 @@ int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value)
             ctx->traverse_mode = 1;
             if (value[10] == ':') {
                 int refill = atoi(value + 11);
-                if (refill != 1 && refill != 4 && refill != 8 && refill != 16 && refill != 32) {
-                    OBVHS_SET_ERR(ctx, "traverse refill threshold must be 1, 4, 8, 16 or 32");
+                if (refill < 1 || refill > 32) {
+                    OBVHS_SET_ERR(ctx, "traverse refill threshold must be in 1..32");
                     return OBVHS_ERR_INVALID_ARG;
                 }
                 ctx->traverse_refill = refill;
@@ -325,6 +332,19 @@ int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value)
         } else {
             OBVHS_SET_ERR(ctx, "traverse must be auto, static or persistent[:refill[:chunk]]");
             return OBVHS_ERR_INVALID_ARG;
+        }
+        return OBVHS_OK;
+    }
+    if (strcmp(key, "traverse_variant") == 0) {  // persistent-kernel variant "<id>[:<node_thr>]" (traverse.cu: launch_persistent_t)
+        const int id = atoi(value);
+        if (id < 0 || id > 8) {
+            OBVHS_SET_ERR(ctx, "traverse_variant id must be in 0..8");
+            return OBVHS_ERR_INVALID_ARG;
+        }
+        ctx->traverse_variant = id;
+        if (const char* c2 = strchr(value, ':')) {
+            const int thr = atoi(c2 + 1);
+            ctx->traverse_node_thr = thr < 1 ? 1 : (thr > 33 ? 33 : thr);
         }
         return OBVHS_OK;
     }
@@ -931,17 +951,28 @@ struct StreamSwap {  // launches go to ctx->stream: point it at another stream f
     explicit StreamSwap(ObvhsContext* c) : ctx(c), saved(c->stream) {}
     ~StreamSwap() { ctx->stream = saved; }
 };
+// a failed call must not return while the side streams still use arena staging the DeviceScope is about to release
+struct PipelineGuard {
+    ObvhsContext* ctx;
+    bool armed = false;
+    ~PipelineGuard() {
+        if (!armed) return;
+        if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in);
+        if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
+        if (ctx->compute_alt) cudaStreamSynchronize(ctx->compute_alt);
+        cudaStreamSynchronize(ctx->stream);
+    }
+};
 
-// RayIn = ObvhsRay (used as it is) or ObvhsRayNew (constructor arguments, expanded on the device chunk by chunk)
+// RayIn = ObvhsRay (the reference's 64-byte struct) or ObvhsRayNew (the 32-byte arguments of Ray::new; the kernels run the
+// constructor themselves when they fetch a ray, traverse.cu: ray_load)
 template <class RayIn, class Launch>
 static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count, const RayIn* rays, size_t n, void* out, size_t out_elem,
                            uint64_t* counters, Launch launch) {
-    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
     ARG_CHECK(ctx, bvh, "bvh is null");
     ARG_CHECK(ctx, n == 0 || (rays && out), "null rays/out");
     if (n == 0) return OBVHS_OK;
-    DevBuf<ObvhsRay> st_rays;
-    DevBuf<RayIn> st_in;  // PACKED only: the staged constructor arguments
+    DevBuf<RayIn> st_in;
     DevBuf<unsigned char> st_out;
     DevBuf<u64> st_cnt;
     const bool rays_dev = obvhs_is_device_ptr(rays);
@@ -964,21 +995,15 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
     }
     bool persistent = false;
     const size_t MIN_CHUNK = traverse_host_chunk_min(ctx, prim_count, &persistent);
+    PipelineGuard guard{ctx};
     if (rays_dev || n < MIN_CHUNK + MIN_CHUNK / 2) {
         const RayIn* d_in = nullptr;
         ST_TRY(stage_in(ctx, rays, n, st_in, &d_in));  // (a device pointer passes through)
-        const ObvhsRay* d_rays = reinterpret_cast<const ObvhsRay*>(d_in);
-        if (PACKED) {
-            CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
-            ST_TRY(ray_new_device(ctx, reinterpret_cast<const ObvhsRayNew*>(d_in), n, st_rays.p));
-            d_rays = st_rays.p;
-        }
-        ST_TRY(launch(d_rays, n, d_out, d_cnt));
+        ST_TRY(launch(d_in, n, d_out, d_cnt));
         if (!out_dev) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * out_elem, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
-        CU_TRY(ctx, st_rays.alloc(n, ctx->stream));
-        if (PACKED) CU_TRY(ctx, st_in.alloc(n, ctx->stream));
-        unsigned char* d_stage = PACKED ? reinterpret_cast<unsigned char*>(st_in.p) : reinterpret_cast<unsigned char*>(st_rays.p);
+        CU_TRY(ctx, st_in.alloc(n, ctx->stream));
+        unsigned char* d_stage = reinterpret_cast<unsigned char*>(st_in.p);
         // Slice boundaries: ~6 equal slices, but never below what the kernel in use needs to run efficiently
         // (traverse_host_chunk_min). The un-overlapped head (first H2D slice) and tail (last kernel + D2H slice) shrink with the
         // slice, but many small copies in both directions at once cost more on the link than they save: 2 M kitchen rays
@@ -1012,6 +1037,7 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
         cudaEvent_t* ev = ctx->event_pool.data();
         // the staging areas come from the arena, whose reuse is ordered on ctx->stream: the copy streams start after it
         CU_TRY(ctx, cudaEventRecord(ev[0], ctx->stream));
+        guard.armed = true;
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ev[0], 0));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev[0], 0));
         // Persistent-kernel slices alternate between two compute streams: the CTAs of slice k+1 move in as those of slice k
@@ -1033,8 +1059,7 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
             cudaEvent_t e_in = ev[2 + 2 * c], e_k = ev[3 + 2 * c];
             ctx->stream = (two_streams && (c & 1)) ? ctx->compute_alt : swap.saved;
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
-            if (PACKED) ST_TRY(ray_new_device(ctx, reinterpret_cast<const ObvhsRayNew*>(st_in.p) + off, cnt, st_rays.p + off));
-            ST_TRY(launch(st_rays.p + off, cnt, (unsigned char*)d_out + off * out_elem, d_cnt));
+            ST_TRY(launch(st_in.p + off, cnt, (unsigned char*)d_out + off * out_elem, d_cnt));
             if (!out_dev || ctx->stream != swap.saved) CU_TRY(ctx, cudaEventRecord(e_k, ctx->stream));
             if (ctx->stream != swap.saved) last_alt = e_k;
             if (!out_dev) {
@@ -1053,21 +1078,24 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
     if (counters && !cnt_dev) CU_TRY(ctx, cudaMemcpyAsync(counters, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     // host-visible results (or host-staged inputs whose arena slot is released on return): synchronous like the reference
     if (!out_dev || !rays_dev || (counters && !cnt_dev)) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    guard.armed = false;
     return OBVHS_OK;
 }
 
 template <class RayIn>
 static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
                        uint64_t* counters) {
-    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
-        return cwbvh_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
+    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
+    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const RayIn* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+        return cwbvh_traverse_device(ctx, bvh, d_rays, PACKED, cnt, mode, d_out, d_cnt);
     });
 }
 template <class RayIn>
 static int b2_traverse(ObvhsContext* ctx, const ObvhsBvh2* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
                        uint64_t* counters) {
-    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const ObvhsRay* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
-        return bvh2_traverse_device(ctx, bvh, d_rays, cnt, mode, d_out, d_cnt);
+    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
+    return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const RayIn* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
+        return bvh2_traverse_device(ctx, bvh, d_rays, PACKED, cnt, mode, d_out, d_cnt);
     });
 }
 extern "C" {

@@ -141,6 +141,9 @@ struct ObvhsContext {
     size_t host_slice = 0;  // obvhs_cuda_set_option("host_slice", "<rays>"), 0 = automatic
     std::vector<cudaEvent_t> event_pool;
     int traverse_mode = 2, traverse_refill = 4, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
+    int traverse_variant = 0, traverse_node_thr = 16;                  // obvhs_cuda_set_option("traverse_variant", "<id>[:<node_thr>]"), traverse.cu
+    size_t traverse_resident_lanes = 0;                                 // lanes the persistent kernel keeps resident (set by its launcher)
+    bool staged_host = false;  // a stage_in() of this API call copied from HOST memory: the call synchronises before it returns
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
 };
 
@@ -268,6 +271,7 @@ static inline int stage_in(ObvhsContext* ctx, const T* src, size_t count, DevBuf
     }
     CU_TRY(ctx, stage.alloc(count, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(stage.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->staged_host = true;  // the caller may reuse `src` as soon as the API call returns (DeviceScope synchronises)
     *out = stage.p;
     return OBVHS_OK;
 }
@@ -336,10 +340,12 @@ int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u
 int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out,
                          bool include_exact_node_aabbs = false);
 // traverse.cu
-int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
+// d_rays: ObvhsRay[n] (packed = false) or ObvhsRayNew[n] (packed = true: Ray::new runs inside the kernel)
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
                           u64* d_counters);
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
-int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters);
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+                         u64* d_counters);
 int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris);
 size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool* persistent);
 int make_rays_device(ObvhsContext* ctx, const float* d_od, size_t n, float tmin, float tmax, ObvhsRay* d_rays);

@@ -182,10 +182,52 @@ struct RayResult {
     u32 count;
     bool is_miss;
 };
-__device__ __forceinline__ void ray_load(RayRegs& r, const float4* __restrict__ rp) {
-    float4 ro = __ldg(rp), rd = __ldg(rp + 1), ri = __ldg(rp + 2), rt = __ldg(rp + 3);
-    r = RayRegs{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ri.x, ri.y, ri.z, rt.x, rt.y};
+// ray.rs:6-12, 34-52
+__device__ __forceinline__ float safe_inverse(float x) {
+    const float EPS = 1.1920929e-07f;
+    if (fabsf(x) <= EPS) return copysignf(1.0f, x) / EPS;
+    return 1.0f / x;
 }
+// Ray `i` of the batch. packed = false: the reference's 64-byte Ray {origin, direction, inv_direction, tmin, tmax} (ray.rs:15-30).
+// packed = true: the 32-byte arguments of Ray::new {origin, tmin, direction, tmax}; the constructor (ray.rs:34-52: inv_direction =
+// safe_inverse(direction), IEEE division) runs here, where its result is consumed -- no separate pass, half the bytes per ray.
+__device__ __forceinline__ void ray_load(RayRegs& r, const float4* __restrict__ rays, size_t i, bool packed) {
+    if (packed) {
+        const float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+        r = RayRegs{o.x, o.y, o.z, d.x, d.y, d.z, safe_inverse(d.x), safe_inverse(d.y), safe_inverse(d.z), o.w, d.w};
+    } else {
+        const float4* rp = rays + 4 * i;
+        float4 ro = __ldg(rp), rd = __ldg(rp + 1), ri = __ldg(rp + 2), rt = __ldg(rp + 3);
+        r = RayRegs{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ri.x, ri.y, ri.z, rt.x, rt.y};
+    }
+}
+// Per-lane traversal stack. The lowest SS entries of every lane live in shared memory as [entry][thread]: one 8-byte column per
+// lane, so a warp whose lanes sit at 32 different depths still pushes or pops in two conflict-free wavefronts. The same access
+// to a local-memory array touches up to 32 different 128-byte lines (local memory interleaves the lanes' words per index).
+// Entries beyond SS spill to local memory. SS = 0: plain local array.
+constexpr int TRAV_BLOCK = 128;
+template <class T, int CAP, int SS>
+struct LaneStack {
+    T local[CAP - SS > 0 ? CAP - SS : 1];
+    static __device__ __forceinline__ T* column() {
+        __shared__ T sh[SS * TRAV_BLOCK];
+        return sh + threadIdx.x;
+    }
+    __device__ __forceinline__ void put(u32 i, const T& v) {
+        if (i < (u32)SS) column()[i * TRAV_BLOCK] = v;
+        else local[i - SS] = v;
+    }
+    __device__ __forceinline__ T get(u32 i) const {
+        if (i < (u32)SS) return column()[i * TRAV_BLOCK];
+        return local[i - SS];
+    }
+};
+template <class T, int CAP>
+struct LaneStack<T, CAP, 0> {
+    T local[CAP];
+    __device__ __forceinline__ void put(u32 i, const T& v) { local[i] = v; }
+    __device__ __forceinline__ T get(u32 i) const { return local[i]; }
+};
 __device__ __forceinline__ void result_reset(RayResult& o) {
     o.hit_id = 0xffffffffu;  // RayHit::none(), ray.rs:74-83
     o.hit_t = __int_as_float(0x7f800000);
@@ -214,8 +256,8 @@ struct CwTree {
         uint2 cur, prim;  // cwbvh/mod.rs:84-120 current_group / primitive_group
         RayResult o;
     };
-    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rp) const {
-        ray_load(st.r, rp);
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, bool packed) const {
+        ray_load(st.r, rays, i, packed);
         // cwbvh/mod.rs:1001-1010
         st.oct_inv4 = (st.r.dx < 0.0f ? 0u : 0x04040404u) | (st.r.dy < 0.0f ? 0u : 0x02020202u) | (st.r.dz < 0.0f ? 0u : 0x01010101u);
         st.sp = 0;
@@ -223,42 +265,42 @@ struct CwTree {
         st.prim = make_uint2(0u, 0u);
         result_reset(st.o);
     }
-    // One turn of the traverse! loop (traverse_macro.rs:59-126): drain the primitive group, test one node, pop when both
-    // groups are empty. Returns true when the ray is done. The loop has ONE exit: in miss mode the first hit clears all
+    // One turn of the traverse! loop (traverse_macro.rs:59-126) is tri_step() for every primitive of the current group, then
+    // node_step(): test one node, pop when both groups are empty. The loop has ONE exit: in miss mode the first hit clears all
     // pending work (cwbvh/mod.rs:216-220 returns there) and the state machine runs out on its own. An early `break`/`goto`
     // out of the primitive loop made ptxas (12.9, sm_100a) share convergence-barrier registers between the primitive loop
     // and the node test, and the persistent kernel then dead-locked on scenes where lanes of one warp sat in both at once.
-    // ONE_TRI: at most one triangle per call, and no node test while triangles of the current group are pending. The per-ray
-    // sequence of tests is unchanged (a ray still drains its group before its next node), only the interleaving with the other
-    // lanes of the warp differs: in an incoherent warp the `while` form makes all lanes wait for the lane with the most
-    // triangles before every node test.
-    template <int MODE, bool COUNT, bool ONE_TRI = false>
-    __device__ __forceinline__ bool step(State& st, uint2* __restrict__ stack, u32& nodes_visited, u32& tris_tested) const {
-        for (bool first = true; st.prim.y != 0 && (!ONE_TRI || first); first = false) {  // traverse_macro.rs:64-72
-            u32 local = 31u - __clz(st.prim.y);
-            st.prim.y &= ~(1u << local);
-            u32 pid = st.prim.x + local;
-            float t = tri_intersect(tris, pid, st.r);
-            if (COUNT) tris_tested++;
-            if (MODE == 0) {
-                if (t < st.r.tmax) {  // cwbvh/mod.rs:184-189
-                    st.o.hit_id = pid;
-                    st.o.hit_t = t;
-                    st.r.tmax = t;
-                }
-            } else if (MODE == 1) {
-                if (t < st.r.tmax) {
-                    st.o.is_miss = false;
-                    st.prim.y = 0;
-                    st.cur.y = 0;
-                    st.sp = 0;
-                }
-            } else {
-                if (t < __int_as_float(0x7f800000)) st.o.count++;
+    __device__ __forceinline__ bool tris_pending(const State& st) const { return st.prim.y != 0; }
+    // traverse_macro.rs:64-72, one primitive of the current group (highest set bit first)
+    template <int MODE, bool COUNT>
+    __device__ __forceinline__ void tri_step(State& st, u32& tris_tested) const {
+        u32 local = 31u - __clz(st.prim.y);
+        st.prim.y &= ~(1u << local);
+        u32 pid = st.prim.x + local;
+        float t = tri_intersect(tris, pid, st.r);
+        if (COUNT) tris_tested++;
+        if (MODE == 0) {
+            if (t < st.r.tmax) {  // cwbvh/mod.rs:184-189
+                st.o.hit_id = pid;
+                st.o.hit_t = t;
+                st.r.tmax = t;
             }
+        } else if (MODE == 1) {
+            if (t < st.r.tmax) {
+                st.o.is_miss = false;
+                st.prim.y = 0;
+                st.cur.y = 0;
+                st.sp = 0;
+            }
+        } else {
+            if (t < __int_as_float(0x7f800000)) st.o.count++;
         }
+    }
+    // traverse_macro.rs:76-123 with an empty primitive group: next node of the current group (or nothing), then pop / finish.
+    // Returns true when the ray is done.
+    template <bool COUNT, class Stack>
+    __device__ __forceinline__ bool node_step(State& st, Stack& stack, u32& nodes_visited) const {
         bool done = false;
-        if (!ONE_TRI || st.prim.y == 0) {  // (ONE_TRI: triangles of this group still pending -> next call)
         st.prim = make_uint2(0u, 0u);
         if (st.cur.y & 0xff000000u) {  // traverse_macro.rs:76-103
             u32 hits_imask = st.cur.y;
@@ -266,7 +308,7 @@ struct CwTree {
             u32 child_index_base = st.cur.x;
             st.cur.y &= ~(1u << child_index_offset);
             if (st.cur.y & 0xff000000u) {  // faststack.rs:299-303 saturating push
-                stack[st.sp] = st.cur;
+                stack.put(st.sp, st.cur);
                 st.sp = min(st.sp + 1u, 31u);
             }
             u32 slot_index = (child_index_offset - 24u) ^ (st.oct_inv4 & 0xffu);
@@ -286,11 +328,20 @@ struct CwTree {
             if (st.sp == 0) done = true;
             else {
                 st.sp--;
-                st.cur = stack[st.sp];
+                st.cur = stack.get(st.sp);
             }
         }
-        }
         return done;
+    }
+    // ONE_TRI: at most one triangle per call, and no node test while triangles of the current group are pending. The per-ray
+    // sequence of tests is unchanged (a ray still drains its group before its next node), only the interleaving with the other
+    // lanes of the warp differs: in an incoherent warp the `while` form makes all lanes wait for the lane with the most
+    // triangles before every node test.
+    template <int MODE, bool COUNT, bool ONE_TRI, class Stack>
+    __device__ __forceinline__ bool step(State& st, Stack& stack, u32& nodes_visited, u32& tris_tested) const {
+        for (bool first = true; st.prim.y != 0 && (!ONE_TRI || first); first = false) tri_step<MODE, COUNT>(st, tris_tested);
+        if (ONE_TRI && st.prim.y != 0) return false;  // triangles of this group still pending -> next call
+        return node_step<COUNT>(st, stack, nodes_visited);
     }
 };
 
@@ -317,8 +368,8 @@ struct Bvh2Tree {
         u32 r_count, r_first, l_first;
         bool go_left;
     };
-    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rp) const {
-        ray_load(st.r, rp);
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, bool packed) const {
+        ray_load(st.r, rays, i, packed);
         st.cur = AT_ROOT;
         st.sp = 0;
         st.phase = 0;
@@ -367,8 +418,8 @@ struct Bvh2Tree {
     // The same loop with at most ONE triangle per call (persistent kernel): a leaf is drained over several calls while the rest of
     // the pair's work (the farther child's `right_t < tmax` test with the tmax the nearer leaf left behind, then descend / push /
     // pop) waits in the state. The sequence of box and triangle tests of a ray is exactly the reference's.
-    template <int MODE, bool COUNT>
-    __device__ __forceinline__ bool step_one_tri(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
+    template <int MODE, bool COUNT, class Stack>
+    __device__ __forceinline__ bool step_one_tri(State& st, Stack& stack, u32& nodes_tested, u32& tris_tested) const {
         bool done = false;
         u32 stage = 0;  // after this call's test: 0 = nothing more, 1 = decide the farther child, 2 = descend / push / pop
         if (st.phase != 0) {
@@ -454,7 +505,7 @@ struct Bvh2Tree {
             if (st.go_left) {
                 st.cur = st.l_first;
                 if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
-                    stack[st.sp] = st.r_first;
+                    stack.put(st.sp, st.r_first);
                     st.sp = min(st.sp + 1u, (u32)(CAP - 1));
                 }
             } else if (go_right) {
@@ -464,14 +515,14 @@ struct Bvh2Tree {
                 done = true;
             } else {
                 st.sp--;
-                st.cur = stack[st.sp];
+                st.cur = stack.get(st.sp);
             }
         }
         return done;
     }
     // one iteration of ray_traverse_dynamic's loop (:284-331); the first call performs the root test (:273-282)
-    template <int MODE, bool COUNT, bool ONE_TRI = false>
-    __device__ __forceinline__ bool step(State& st, u32* __restrict__ stack, u32& nodes_tested, u32& tris_tested) const {
+    template <int MODE, bool COUNT, bool ONE_TRI, class Stack>
+    __device__ __forceinline__ bool step(State& st, Stack& stack, u32& nodes_tested, u32& tris_tested) const {
         if (ONE_TRI) return step_one_tri<MODE, COUNT>(st, stack, nodes_tested, tris_tested);
         bool done = false;
         if (st.cur == AT_ROOT) {
@@ -513,7 +564,7 @@ struct Bvh2Tree {
         if (go_left) {
             st.cur = l_first;
             if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
-                stack[st.sp] = r_first;
+                stack.put(st.sp, r_first);
                 st.sp = min(st.sp + 1u, (u32)(CAP - 1));
             }
         } else if (go_right) {
@@ -524,7 +575,7 @@ struct Bvh2Tree {
                 return true;
             }
             st.sp--;
-            st.cur = stack[st.sp];
+            st.cur = stack.get(st.sp);
         }
         return false;
     }
@@ -547,14 +598,15 @@ __device__ __forceinline__ void trav_flush_counters(unsigned long long* __restri
 
 // One ray per thread: the fastest form for coherent batches (primary / shadow rays of neighbouring pixels).
 template <class Tree, int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                       unsigned long long* __restrict__ counters, const DeferList defer) {
+__global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, bool packed,
+                                                              void* __restrict__ out, unsigned long long* __restrict__ counters,
+                                                              const DeferList defer) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 nodes_visited = 0, tris_tested = 0;
     typename Tree::State st;
-    typename Tree::StackT stack[Tree::STACK];
+    LaneStack<typename Tree::StackT, Tree::STACK, 0> stack;
     const bool valid = i < n;
-    if (valid) tree.begin(st, rays + i * 4);
+    if (valid) tree.begin(st, rays, i, packed);
     bool mine = valid;
     if (defer.count) {  // auto mode: vote, hand the block over to the persistent kernel when one of its warps is incoherent
         const bool coherent = warp_is_coherent(st.r, valid, defer.max_dist2);
@@ -572,14 +624,27 @@ __global__ void __launch_bounds__(128) traverse_kernel(const Tree tree, const fl
 }
 
 // Persistent-warp variant for incoherent batches: a warp keeps its 32 lanes busy by pulling new rays from a global
-// cursor (warp-private chunks of consecutive rays, one atomicAdd per chunk) whenever at least REFILL lanes have finished,
+// cursor (warp-private chunks of consecutive rays, one atomicAdd per chunk) whenever at least `refill` lanes have finished,
 // instead of idling until its longest ray ends (measured on the 10M-triangle soup with the one-ray-per-thread kernel:
 // 5.8 of 32 lanes active per issued instruction, issue slots 75 % busy -- divergence-bound, not memory-bound). Every ray
 // still runs the reference's exact per-ray state machine, so results and counters are identical to traverse_kernel's.
-template <class Tree, int MODE, bool COUNT, int REFILL, bool DEFER>
-__global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n, void* __restrict__ out,
-                                                                  unsigned long long* __restrict__ counters, u32* __restrict__ next_ray, u32 chunk,
-                                                                  const DeferList defer) {
+//
+// POLICY 0: every turn of the inner loop runs both halves of the state machine, the lanes with a pending triangle the triangle
+//           test and the others the node test (two divergent paths per turn, each with part of the warp).
+// POLICY 1: every turn runs ONE of them for the whole warp. The node test (the expensive half: ~250 instructions, five 16-byte
+//           loads) runs when at least `node_thr` lanes are waiting for it or no lane has a triangle pending; otherwise the
+//           triangle lanes take a turn and the node lanes wait, so node tests are issued with fuller warps. The per-ray order
+//           of tests is untouched (only which lanes move in a given turn changes).
+// SS      : stack entries per lane kept in shared memory (LaneStack).
+// MINB    : __launch_bounds__ minimum CTAs per SM (register cap).
+struct PersistArgs {
+    u32 chunk, refill, node_thr, packed;
+};
+template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
+__global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n,
+                                                                               void* __restrict__ out, unsigned long long* __restrict__ counters,
+                                                                               u32* __restrict__ next_ray, const PersistArgs pa,
+                                                                               const DeferList defer) {
     // auto mode: only the rays of the 128-ray blocks the one-ray-per-thread kernel deferred (slot k of the list covers the
     // virtual indices [128 k, 128 k + 128)); otherwise the whole batch
     const u32 n_rays = n;
@@ -594,7 +659,8 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
     bool active = false, exhausted = false;
     u32 my = 0;
     typename Tree::State st = {};
-    typename Tree::StackT stack[Tree::STACK];
+    LaneStack<typename Tree::StackT, Tree::STACK, SS> stack;
+    const u32 chunk = pa.chunk;
     // the warp owns [chunk_pos, chunk_end): consecutive rays, so refills stay close to the rays still in flight
     u32 chunk_pos = 0, chunk_end = 0;  // (n + warps * chunk < 2^32: the host splits larger batches)
     for (;;) {
@@ -615,7 +681,7 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
                     my = chunk_pos + rank;
                     if (DEFER) my = __ldcg(defer.blocks + (my >> 7)) * 128u + (my & 127u);
                     if (!DEFER || my < n_rays) {  // (the last block of a batch may be partial)
-                        tree.begin(st, rays + (size_t)my * 4);
+                        tree.begin(st, rays, my, pa.packed != 0);
                         active = true;
                     }
                 }
@@ -623,13 +689,32 @@ __global__ void __launch_bounds__(128) traverse_persistent_kernel(const Tree tre
             chunk_pos += take;
         }
         if (!__any_sync(0xffffffffu, active)) break;
-        const u32 min_active = (exhausted && chunk_pos == chunk_end) ? 1u : (u32)(33 - REFILL);
-        do {
-            if (active && tree.template step<MODE, COUNT, ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
-                result_store<MODE>(st.o, out, my);
-                active = false;
-            }
-        } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
+        const u32 min_active = (exhausted && chunk_pos == chunk_end) ? 1u : 33u - pa.refill;
+        if constexpr (POLICY == 0) {
+            do {
+                if (active && tree.template step<MODE, COUNT, ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
+                    result_store<MODE>(st.o, out, my);
+                    active = false;
+                }
+            } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
+        } else {
+            u32 n_active;
+            do {
+                const bool want_tri = active && tree.tris_pending(st);
+                const u32 tri_mask = __ballot_sync(0xffffffffu, want_tri);
+                const u32 node_mask = __ballot_sync(0xffffffffu, active && !want_tri);
+                if (tri_mask != 0 && (u32)__popc(node_mask) < pa.node_thr) {
+                    if (want_tri) tree.template tri_step<MODE, COUNT>(st, tris_tested);
+                    n_active = __popc(tri_mask | node_mask);
+                } else {
+                    if (active && !want_tri && tree.template node_step<COUNT>(st, stack, nodes_visited)) {
+                        result_store<MODE>(st.o, out, my);
+                        active = false;
+                    }
+                    n_active = __popc(__ballot_sync(0xffffffffu, active));
+                }
+            } while (n_active >= min_active);
+        }
     }
     trav_flush_counters<COUNT>(counters, nodes_visited, tris_tested);
 }
@@ -646,12 +731,6 @@ __global__ void __launch_bounds__(256) permute_tris_kernel(const float4* __restr
     for (int k = 0; k < 4; k++) out[i * RT_TRI_VEC4 + k] = rt[k];
 }
 
-// ray.rs:6-12, 34-52
-__device__ __forceinline__ float safe_inverse(float x) {
-    const float EPS = 1.1920929e-07f;
-    if (fabsf(x) <= EPS) return copysignf(1.0f, x) / EPS;
-    return 1.0f / x;
-}
 __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float tmin, float tmax, float4* __restrict__ rays) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -665,63 +744,75 @@ __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float t
 
 }  // namespace
 
-template <class Tree, int MODE, bool COUNT, int REFILL>
-static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, void* d_out, unsigned long long* c, u32* next,
-                               const DeferList& defer) {
+// Persistent-kernel variants (POLICY, SS, MINB) selectable per context: obvhs_cuda_set_option("traverse_variant", "<id>[:<node_thr>]").
+// Variant 0 is the round-1 kernel. Only CwTree has the split tri_step / node_step POLICY 1 needs; Bvh2 trees always run variant 0.
+template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
+static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, void* d_out, unsigned long long* c,
+                               u32* next, const DeferList& defer) {
+    auto kernel = traverse_persistent_kernel<Tree, MODE, COUNT, DEFER, POLICY, SS, MINB>;
     int per_sm = 0;
-    size_t need = (n + 127) / 128;
-    if (defer.count) {
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, true>, 128, 0));
-        size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
-        if (blocks > need) blocks = need;
-        traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
-                                                                                                                (u32)ctx->traverse_chunk, defer);
-    } else {
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, false>, 128, 0));
-        size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
-        if (blocks > need) blocks = need;
-        traverse_persistent_kernel<Tree, MODE, COUNT, REFILL, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next,
-                                                                                                                 (u32)ctx->traverse_chunk, defer);
-    }
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRAV_BLOCK, 0));
+    const size_t need = (n + TRAV_BLOCK - 1) / TRAV_BLOCK;
+    size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+    if (blocks > need) blocks = need;
+    ctx->traverse_resident_lanes = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm) * TRAV_BLOCK;
+    const PersistArgs pa{(u32)ctx->traverse_chunk, (u32)ctx->traverse_refill, (u32)ctx->traverse_node_thr, packed ? 1u : 0u};
+    kernel<<<(unsigned)blocks, TRAV_BLOCK, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next, pa, defer);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
 }
-template <class Tree, int REFILL>
-static int launch_persistent_r(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
+template <class Tree>
+struct HasSplitSteps { static constexpr bool value = false; };
+template <>
+struct HasSplitSteps<CwTree> { static constexpr bool value = true; };
+
+template <class Tree, int MODE, bool COUNT>
+static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, void* d_out, unsigned long long* c,
                                u32* next, const DeferList& defer) {
+    if (defer.count) return launch_persistent_v<Tree, MODE, COUNT, true, 0, 0, 8>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    if constexpr (HasSplitSteps<Tree>::value) {
+        switch (ctx->traverse_variant) {
+#define OBVHS_V(ID, POLICY, SS, MINB) \
+    case ID: return launch_persistent_v<Tree, MODE, COUNT, false, POLICY, SS, MINB>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+            OBVHS_V(1, 1, 0, 9)
+            OBVHS_V(2, 0, 8, 9)
+            OBVHS_V(3, 1, 8, 9)
+            OBVHS_V(4, 1, 12, 9)
+            OBVHS_V(5, 1, 8, 10)
+            OBVHS_V(6, 1, 8, 12)
+            OBVHS_V(7, 0, 0, 10)
+            OBVHS_V(8, 1, 0, 10)
+#undef OBVHS_V
+            default: break;
+        }
+    }
+    return launch_persistent_v<Tree, MODE, COUNT, false, 0, 0, 9>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+}
+template <class Tree>
+static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, int mode, void* d_out,
+                             unsigned long long* c, u32* next, const DeferList& defer) {
     if (c) {
-        if (mode == 0) return launch_persistent_t<Tree, 0, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
-        if (mode == 1) return launch_persistent_t<Tree, 1, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
-        return launch_persistent_t<Tree, 2, true, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+        if (mode == 0) return launch_persistent_t<Tree, 0, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+        if (mode == 1) return launch_persistent_t<Tree, 1, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+        return launch_persistent_t<Tree, 2, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
     }
-    if (mode == 0) return launch_persistent_t<Tree, 0, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
-    if (mode == 1) return launch_persistent_t<Tree, 1, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
-    return launch_persistent_t<Tree, 2, false, REFILL>(ctx, tree, rays, n, d_out, c, next, defer);
+    if (mode == 0) return launch_persistent_t<Tree, 0, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    if (mode == 1) return launch_persistent_t<Tree, 1, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    return launch_persistent_t<Tree, 2, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
 }
 template <class Tree>
-static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
-                             u32* next, const DeferList& defer) {
-    switch (ctx->traverse_refill) {
-        case 1: return launch_persistent_r<Tree, 1>(ctx, tree, rays, n, mode, d_out, c, next, defer);
-        case 4: return launch_persistent_r<Tree, 4>(ctx, tree, rays, n, mode, d_out, c, next, defer);
-        case 16: return launch_persistent_r<Tree, 16>(ctx, tree, rays, n, mode, d_out, c, next, defer);
-        case 32: return launch_persistent_r<Tree, 32>(ctx, tree, rays, n, mode, d_out, c, next, defer);
-        default: return launch_persistent_r<Tree, 8>(ctx, tree, rays, n, mode, d_out, c, next, defer);
-    }
-}
-template <class Tree>
-static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, int mode, void* d_out, unsigned long long* c,
-                         const DeferList& defer) {
-    dim3 block(128), grid(div_up(n, 128));
+static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, int mode, void* d_out,
+                         unsigned long long* c, const DeferList& defer) {
+    dim3 block(TRAV_BLOCK), grid(div_up(n, TRAV_BLOCK));
     cudaStream_t s = ctx->stream;
     if (c) {
-        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
-        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
-        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
     } else {
-        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
-        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
-        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, d_out, c, defer);
+        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
     }
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
@@ -732,7 +823,8 @@ static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays
 constexpr size_t AUTO_STATIC_MAX_PRIMS = 262144;
 template <class Tree>
 static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, size_t prim_count, const float4* rays, size_t n,
-                             int mode, void* d_out, u64* d_counters) {
+                             bool packed, int mode, void* d_out, u64* d_counters) {
+    const size_t ray_vec4 = packed ? 2 : 4;  // float4 per ray
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
     int tm = ctx->traverse_mode;
@@ -747,7 +839,7 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     const size_t n_launches = (n + MAX_LAUNCH - 1) / MAX_LAUNCH;
     if (tm == 2 && n_launches > 1) tm = 1;
     const DeferList none{nullptr, nullptr, 0.f};
-    if (tm == 0) return launch_static(ctx, tree, rays, n, mode, d_out, c, none);
+    if (tm == 0) return launch_static(ctx, tree, rays, n, packed, mode, d_out, c, none);
     // scratch: [0] deferred block count, [1] unused, [2..] one ray cursor per persistent launch, then the deferred block list
     const size_t n_blocks = tm == 2 ? (n + 127) / 128 : 0;
     DevBuf<u32> scratch;
@@ -756,7 +848,7 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     if (tm == 1) {
         for (size_t l = 0; l < n_launches; l++) {
             const size_t off = l * MAX_LAUNCH, cnt = n - off < MAX_LAUNCH ? n - off : MAX_LAUNCH;
-            ST_TRY(launch_persistent(ctx, tree, rays + off * 4, cnt, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, none));
+            ST_TRY(launch_persistent(ctx, tree, rays + off * ray_vec4, cnt, packed, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, none));
         }
         return OBVHS_OK;
     }
@@ -765,8 +857,8 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     float diag2 = dx * dx + dy * dy + dz * dz;
     if (!(diag2 > 0.0f) || !(diag2 < 3.0e38f)) diag2 = 3.0e38f;  // unknown scene extent (uploaded tree): directions decide
     const DeferList defer{scratch.p, scratch.p + 2 + n_launches, diag2 * 0.0004f};
-    ST_TRY(launch_static(ctx, tree, rays, n, mode, d_out, c, defer));
-    return launch_persistent(ctx, tree, rays, n, mode, d_out, c, scratch.p + 2, defer);
+    ST_TRY(launch_static(ctx, tree, rays, n, packed, mode, d_out, c, defer));
+    return launch_persistent(ctx, tree, rays, n, packed, mode, d_out, c, scratch.p + 2, defer);
 }
 
 // Smallest slice of a host batch worth its own launch (traverse_common pipelines H2D | traversal | D2H slice by slice): 32 Ki
@@ -777,10 +869,11 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
 size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool* persistent) {
     *persistent = ctx->traverse_mode == 1 || (ctx->traverse_mode == 2 && prim_count > AUTO_STATIC_MAX_PRIMS);
     if (ctx->host_slice) return ctx->host_slice < 1024 ? 1024 : ctx->host_slice;  // obvhs_cuda_set_option("host_slice", ...)
-    return *persistent ? (size_t)ctx->sm_count * 9 * 128 * 2 : (size_t)32768;
+    const size_t lanes = ctx->traverse_resident_lanes ? ctx->traverse_resident_lanes : (size_t)ctx->sm_count * 9 * TRAV_BLOCK;
+    return *persistent ? lanes * 2 : (size_t)32768;
 }
 
-int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out,
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
                           u64* d_counters) {
     if (n == 0) return OBVHS_OK;
     if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
@@ -792,10 +885,11 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsR
     tree.tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
     tree.root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
     tree.magic = 0x4B000000u;
-    return traverse_dispatch(ctx, tree, bvh->total_aabb, bvh->prim_count, reinterpret_cast<const float4*>(d_rays), n, mode, d_out, d_counters);
+    return traverse_dispatch(ctx, tree, bvh->total_aabb, bvh->prim_count, reinterpret_cast<const float4*>(d_rays), n, packed, mode, d_out, d_counters);
 }
 
-int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* d_rays, size_t n, int mode, void* d_out, u64* d_counters) {
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+                         u64* d_counters) {
     if (n == 0) return OBVHS_OK;
     if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
         OBVHS_SET_ERR(ctx, "Bvh2 has no triangles attached (call obvhs_cuda_bvh2_set_triangles)");
@@ -805,11 +899,11 @@ int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     if (bvh->max_depth <= 96) {  // fast_stack!(u32, (96, 192), self.max_depth, ...) bvh2/mod.rs:166
         Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
-        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
     }
     if (bvh->max_depth <= 192) {
         Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
-        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
     }
     OBVHS_SET_ERR(ctx, "Bvh2 traversal: max_depth %zu > 192 needs the reference's heap stack -- not supported", bvh->max_depth);
     return OBVHS_ERR_UNSUPPORTED;

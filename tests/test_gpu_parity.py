@@ -322,6 +322,38 @@ def test_traversal_hits_bit_exact(api, scenes, scene, mode):
     assert np.array_equal(g.ray_traverse_anyhit_count(srays), c.ray_traverse_anyhit_count(bt, srays))
 
 
+@pytest.mark.parametrize("variant", ["1:1", "1:16", "1:33", "2:16", "3:8", "3:24", "4:16", "5:16", "6:12", "7:16", "8:20"])
+@pytest.mark.parametrize("scene", ["soup4k", "kitchen"])
+def test_persistent_kernel_variants_bit_exact(api, scenes, scene, variant):
+    # the persistent kernel's scheduling policy (which lanes move in a turn), shared-memory short stack and register cap are
+    # tuning knobs: every variant must return the oracle's hits AND visit counters, for Ray structs and Ray::new records alike
+    from obvhs_b200.types import ray_args_of
+
+    tris = scenes[scene]
+    c = ob.build_cwbvh_from_tris(tris, "fast_build")
+    nodes, prims, total = c.get()
+    bt = c.bvh_tris(tris)
+    rays = rays_for(tris)
+    wc = np.zeros(2, np.uint64)
+    want = c.ray_traverse(bt, rays, counters=wc)
+    ctx = api.Context(0, traverse="persistent:4:32")
+    ctx.set_option("traverse_variant", variant)
+    g = api.CwBvh.upload(nodes, prims, total, ctx=ctx)
+    g.set_triangles(tris)
+    gc = np.zeros(2, np.uint64)
+    got = g.ray_traverse(rays, counters=gc)
+    assert got.tobytes() == want.tobytes()
+    assert np.array_equal(gc, wc)
+    assert g.ray_traverse(ray_args_of(rays)).tobytes() == want.tobytes()  # Ray::new inside the kernel
+    srays = rays.copy()
+    finite = np.isfinite(want["t"])
+    srays[:, 13] = np.where(finite, want["t"] * np.float32(0.999), np.float32(5.0))
+    srays[::3, 13] = np.float32(1e30)
+    assert np.array_equal(g.ray_traverse_miss(srays), c.ray_traverse_miss(bt, srays))
+    assert np.array_equal(g.ray_traverse_miss(ray_args_of(srays)), c.ray_traverse_miss(bt, srays))
+    assert np.array_equal(g.ray_traverse_anyhit_count(srays), c.ray_traverse_anyhit_count(bt, srays))
+
+
 @pytest.mark.parametrize("preset", ["fastest_build", "very_fast_build", "fast_build", "medium_build"])
 @pytest.mark.parametrize("scene", ["cornell", "terrain32", "kitchen"])
 def test_build_cwbvh_from_tris_end_to_end(api, scenes, scene, preset):
