@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- device-timed PLOC+CWBVH build (Mtris/s) and CWBVH closest-hit traversal (Mrays/s) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitchen|soup|terrain]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload s3|kitchen|soup|terrain|bounce|demoscene|dynamic]
 
-One "step" = one pass of the hot path over one batch: build_cwbvh_from_tris (PLOC -> reinsertion -> CWBVH collapse) on
-the scene, then closest-hit traversal of the ray batch, both through the C ABI with inputs resident in HBM. The headline
-`value` is traversal Mrays/s (BASELINE.json metric, first half), `build` carries the Mtris/s half. N > 1: rank 0 builds,
-the tree is broadcast with NCCL, every rank traverses its own ray batch against its replica (weak scaling, no collective
-on the traversal path). `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP on all host cores;
-the rustc/rayon binary cannot be produced in this image) on the same workload.
+Default workload `s3` = BASELINE.json configs[3] with configs[1] beside it in the same JSON line:
+  * top level: the synthetic 10 M-triangle scene demoscene(2237, 0), `fast_build` on ONE GPU, the finished CWBVH broadcast with NCCL
+    (obvhs_cuda_cwbvh_broadcast), 100 320 000 incoherent diffuse-bounce rays (examples/demoscene.rs:126-178, generated on the
+    device) sharded over the N GPUs in contiguous ranges -- STRONG scaling: the ray set is fixed, per-GPU work shrinks with N;
+  * "kitchen": kitchen.obj, `fast_build`, 1920x1080 primary rays (examples/obj_cwbvh.rs), sharded the same way.
+One "step" = one pass of the hot path over one batch: build_cwbvh_from_tris (PLOC -> reinsertion -> CWBVH collapse) on rank 0,
+broadcast, closest-hit traversal of this rank's rays, all through the C ABI with inputs resident in HBM. `value` is traversal
+Mrays/s (all ranks' rays / max-over-ranks device time), `build` carries the Mtris/s half of the metric, `e2e` the same call with
+pinned HOST buffers. `parity` compares the run's own results with the CPU oracle on a sample and across ranks.
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP on all host cores; the rustc/rayon binary cannot
+be produced in this image) on a bounded sample of the same workloads.
 """
 from __future__ import annotations
 
@@ -258,6 +263,471 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# =====================================================================================================================
+# Headline: S3 (10 M triangles, 100 M sharded bounce rays) + kitchen
+# =====================================================================================================================
+S3_RES = 2237             # demoscene(2237, 0) -> 10 008 338 triangles
+S3_RAYS = 100_320_000     # 1280 x 475 px x 165 samples; here: the first 100 320 000 BOUNCE rays of the recipe
+
+
+def cached_demoscene(res: int):
+    """tu.demoscene(res, 0) costs ~25 s of numpy at 10 M triangles and the driver runs bench.py eight times on one box
+    (N = 1, 2, 4, 8, both arms): keep the generated INPUT triangles in /tmp for the following runs."""
+    from obvhs_b200 import test_util as tu
+
+    path = os.path.join(os.environ.get("OBVHS_CACHE_DIR", "/tmp/obvhs_bench_cache"), f"demoscene_{res}_0.npy")
+    try:
+        a = np.load(path)
+        if a.shape == (2 * res * res, 12) and a.dtype == np.float32:
+            return a
+    except Exception:  # noqa: BLE001
+        pass
+    a = tu.demoscene(res, 0)
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = f"{path}.{os.getpid()}.tmp.npy"
+        np.save(tmp, a)
+        os.replace(tmp, path)
+    except Exception:  # noqa: BLE001
+        pass
+    return a
+
+
+def headline_config(args):
+    """The `config` object: identical for both arms (the driver compares them)."""
+    res = S3_RES if args.tris == 10_000_000 else int(round((args.tris / 2) ** 0.5))
+    return {"workload": f"S3: demoscene({res},0) {2 * res * res} tris, fast_build on one GPU, {args.rays} incoherent diffuse-bounce rays "
+                        f"(examples/demoscene.rs:126-178) sharded over the GPUs; kitchen.obj 56939 tris, fast_build, 1920x1080 primary rays in `kitchen`",
+            "preset": "fast_build", "tris": 2 * res * res, "rays_total": args.rays,
+            "l2": "S3 inputs (3.2 GB of rays) exceed L2; L2 also flushed between steps (256 MB write)",
+            "multi_gpu": "build on rank 0, NCCL broadcast below the C ABI, rays sharded in contiguous ranges (strong scaling)"}, res
+
+
+def hits_hash_np(hits) -> int:
+    """Order-independent 64-bit checksum of a RayHit array: sum over rays of (t_bits << 32 | primitive_id) mod 2^64."""
+    h = np.asarray(hits).view(np.uint32).reshape(-1, 4)
+    with np.errstate(over="ignore"):
+        return int(((h[:, 3].astype(np.uint64) << np.uint64(32)) | h[:, 0].astype(np.uint64)).sum(dtype=np.uint64))
+
+
+def hits_hash_dev(d_hits) -> int:
+    import torch
+
+    v = (d_hits[:, 3].to(torch.int64) & 0xFFFFFFFF) << 32 | (d_hits[:, 0].to(torch.int64) & 0xFFFFFFFF)
+    return int(v.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def bytes_hash_dev(ptr: int, nbytes: int, device: int) -> int:
+    """64-bit word sum of a device buffer (nbytes rounded down to 8)."""
+    import torch
+
+    from obvhs_b200.sharding import device_bytes_tensor
+
+    if not ptr or nbytes < 8:
+        return 0
+    t = device_bytes_tensor(ptr, nbytes - nbytes % 8, device).view(torch.int64)
+    return int(t.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+class Env:
+    pass
+
+
+def setup_env(args):
+    import torch
+
+    from obvhs_b200 import api
+
+    e = Env()
+    e.world = int(os.environ.get("WORLD_SIZE", "1"))
+    e.rank = int(os.environ.get("RANK", "0"))
+    e.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    e.numa_note = bind_to_gpu_numa_node(e.local_rank, e.world)
+    torch.cuda.set_device(e.local_rank)
+    e.dist = None
+    if e.world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{e.local_rank}"))
+        e.dist = dist
+    e.dev = torch.device(f"cuda:{e.local_rank}")
+    e.stream = torch.cuda.Stream(device=e.dev)
+    e.ctx = api.Context(e.local_rank, stream=e.stream.cuda_stream)
+    if os.environ.get("OBVHS_BENCH_HOST_SLICE"):  # tuning sweeps only
+        e.ctx.set_option("host_slice", os.environ["OBVHS_BENCH_HOST_SLICE"])
+    if e.dist:  # the library's own communicator (NCCL below the C ABI); torch.distributed only ships the 128-byte id
+        box = [api.nccl_unique_id() if e.rank == 0 else None]
+        e.dist.broadcast_object_list(box, src=0)
+        e.ctx.comm_init(box[0], e.rank, e.world)
+    with torch.cuda.stream(e.stream):
+        e.flush = torch.empty(256 << 20, dtype=torch.uint8, device=e.dev)  # > 126 MB L2
+    return e
+
+
+def all_max(e, values):
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device=e.dev)
+    if e.dist:
+        e.dist.all_reduce(t, op=e.dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def all_same_u64(e, value: int) -> bool:
+    """True when every rank holds the same 64-bit value."""
+    import torch
+
+    v = value - (1 << 64) if value >= (1 << 63) else value
+    lo = torch.tensor([v], dtype=torch.int64, device=e.dev)
+    hi = lo.clone()
+    if e.dist:
+        e.dist.all_reduce(lo, op=e.dist.ReduceOp.MIN)
+        e.dist.all_reduce(hi, op=e.dist.ReduceOp.MAX)
+    return int(lo.item()) == int(hi.item())
+
+
+def host_link_probe(e, h_in, d_in, d_out, h_out):
+    """Plain pinned copies of this rank's e2e buffers, both directions at once: the link's share of the e2e time."""
+    import torch
+
+    s_in, s_out = torch.cuda.Stream(device=e.dev), torch.cuda.Stream(device=e.dev)
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"concurrent_ms": best * 1e3, "h2d_gbs": h_in.numel() * h_in.element_size() / best / 1e9,
+            "d2h_gbs": h_out.numel() * h_out.element_size() / best / 1e9}
+
+
+def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound, oracle_tree=None):
+    """One workload through the timed loop. tris: host triangles on rank 0 (None elsewhere); d_args: this rank's (n, 8) device ray
+    records. Returns the result object (rank 0) -- every rank must call it (collectives inside)."""
+    import torch
+
+    from obvhs_b200 import api
+    from obvhs_b200.types import RAY_HIT, make_rays
+
+    ctx, stream, dev, rank, world, dist = e.ctx, e.stream, e.dev, e.rank, e.world, e.dist
+    params = api.BvhBuildParams.preset(preset)
+    n_rays = int(d_args.shape[0])
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(tris).to(dev) if rank == 0 else None
+        d_hits = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
+        d_counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    stream.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    state = {"bvh": None}
+
+    def one_step():
+        with torch.cuda.stream(stream):
+            e.flush.zero_()  # L2 flush between iterations, outside the timed events
+            e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+            e0.record(stream)
+            bvh = api.build_cwbvh_from_tris(d_tris, params, ctx=ctx) if rank == 0 else state["bvh"]
+            e1.record(stream)
+            if world > 1:
+                bvh = api.CwBvh.broadcast(bvh, ctx, 0)
+            e2.record(stream)
+            bvh.ray_traverse(d_args, out=d_hits)
+            e3.record(stream)
+        stream.synchronize()
+        # the previous tree stays alive while the next one is built (the context's result cache then holds both buffer sets)
+        state["prev"], state["bvh"] = state["bvh"], bvh
+        # the broadcast is timed on the building rank: elsewhere e0..e2 mostly waits for rank 0's build
+        return e0.elapsed_time(e1) if rank == 0 else 0.0, e1.elapsed_time(e2) if rank == 0 else 0.0, e2.elapsed_time(e3), e0.elapsed_time(e3)
+
+    for _ in range(args.warmup):
+        one_step()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(e.local_rank, period_s=0.02)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    sums = [0.0, 0.0, 0.0, 0.0]
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        for k, v in enumerate(one_step()):
+            sums[k] += v
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    build_ms, bcast_ms, trav_ms, step_ms = [v / args.steps for v in all_max(e, sums)]
+    my_trav_ms = sums[2] / args.steps
+    value = n_total / (trav_ms * 1e-3) / 1e6  # all ranks' rays / max-over-ranks time
+    bvh = state["bvh"]
+
+    # ---- roofline of the traversal kernel on THIS GPU: algorithmic bytes from the per-launch counters -------------------
+    with torch.cuda.stream(stream):
+        d_counters.zero_()
+        bvh.ray_traverse(d_args, out=d_hits, counters=d_counters)
+    stream.synchronize()
+    nodes_visited, tris_tested = [int(x) for x in d_counters.tolist()]
+    alg_bytes = n_rays * (32 + 16) + 80 * nodes_visited + 48 * tris_tested  # SURVEY.md section 8(d) B_trav
+    peak, peak_src = measured_peak_hbm()
+    achieved = alg_bytes / (my_trav_ms * 1e-3) / 1e9
+    traffic = ncu_traffic(name, n_rays)
+    hit_count = int((d_hits[:, 3].view(torch.float32) < 3.0e38).sum().item())
+
+    # ---- parity: replicas identical across ranks, this run's hits equal to the CPU oracle's on a sample -----------------
+    nodes_p, prims_p, tris_p = bvh.device_ptrs()
+    tree_hash = (bytes_hash_dev(nodes_p, bvh.node_count * 80, e.local_rank) ^ bytes_hash_dev(prims_p, bvh.prim_count * 4, e.local_rank)
+                 ^ bytes_hash_dev(tris_p, bvh.prim_count * 64, e.local_rank))
+    n_probe = min(1 << 20, n_rays)
+    probe_n = torch.tensor([n_probe], dtype=torch.int64, device=dev)
+    if dist:
+        dist.broadcast(probe_n, src=0)
+    n_probe = int(probe_n.item())
+    probe = d_args[:n_probe].clone() if rank == 0 else torch.empty((n_probe, 8), dtype=torch.float32, device=dev)
+    if dist:
+        dist.broadcast(probe, src=0)
+    with torch.cuda.stream(stream):
+        p_hits = torch.empty((n_probe, 4), dtype=torch.int32, device=dev)
+        bvh.ray_traverse(probe, out=p_hits)
+    stream.synchronize()
+    probe_hash = hits_hash_dev(p_hits)
+    parity = {"replicas_identical_across_ranks": all_same_u64(e, tree_hash), "probe_hits_identical_across_ranks": all_same_u64(e, probe_hash),
+              "probe_rays": n_probe, "tree_hash": f"{tree_hash:016x}", "probe_hits_hash": f"{probe_hash:016x}"}
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle_bind as ob
+
+        threads = len(os.sched_getaffinity(0))
+        t0 = time.perf_counter()
+        c = oracle_tree if oracle_tree is not None else ob.build_cwbvh_from_tris(tris, preset, threads=threads)
+        cpu_build_wall = time.perf_counter() - t0
+        bt = c.bvh_tris(tris)
+        gn, gp, _ = bvh.download()
+        wn, wp, _ = c.get()
+        n_cmp = min(args.parity_rays, n_rays)
+        idx = torch.arange(0, n_rays, max(1, n_rays // n_cmp), device=dev)[:n_cmp]
+        a = d_args[idx].cpu().numpy()
+        sample = make_rays(a[:, 0:3], a[:, 4:7], a[:, 3], a[:, 7])
+        got = d_hits[idx].cpu().numpy().view(RAY_HIT).reshape(-1)
+        want = c.ray_traverse(bt, sample, threads=threads, use_simd=True)
+        parity.update({"oracle_sample_rays": int(sample.shape[0]),
+                       "cwbvh_nodes_bit_exact": bool(gn.shape == wn.shape and gn.tobytes() == wn.tobytes()),
+                       "primitive_indices_equal": bool(np.array_equal(gp, wp)),
+                       "hit_ids_mismatch": int((got["primitive_id"] != want["primitive_id"]).sum()),
+                       "hit_t_bits_mismatch": int((got["t"].view(np.uint32) != want["t"].view(np.uint32)).sum()),
+                       "hits_hash_gpu": f"{hits_hash_np(got):016x}", "hits_hash_oracle": f"{hits_hash_np(want):016x}"})
+        parity["ok"] = bool(parity["cwbvh_nodes_bit_exact"] and parity["primitive_indices_equal"] and parity["hit_ids_mismatch"] == 0
+                            and parity["hit_t_bits_mismatch"] == 0)
+        if world == 1:  # the CPU baseline proper: rank 0, N = 1 only
+            m = min(args.ref_rays, n_rays)
+            idx = torch.arange(0, n_rays, max(1, n_rays // m), device=dev)[:m]
+            a = d_args[idx].cpu().numpy()
+            sample = make_rays(a[:, 0:3], a[:, 4:7], a[:, 3], a[:, 7])
+            c.ray_traverse(bt, sample[:4096], threads=threads, use_simd=True)
+            t0 = time.perf_counter()
+            c.ray_traverse(bt, sample, threads=threads, use_simd=True)
+            dt = time.perf_counter() - t0
+            cpu = {"value": sample.shape[0] / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                   "sample": f"{sample.shape[0]} of {n_rays} rays (strided), one full build; C++ restatement of the obvhs CPU path (OpenMP), "
+                             "not the rustc/rayon binary",
+                   "build_mtris_per_s": n_tris / c.core_build_seconds / 1e6, "build_wall_s": cpu_build_wall}
+        del c, bt
+    ok_flag = torch.tensor([1 if parity.get("ok", True) and parity["replicas_identical_across_ranks"] and parity["probe_hits_identical_across_ranks"] else 0],
+                           dtype=torch.int64, device=dev)
+    if dist:
+        dist.broadcast(ok_flag, src=0)
+
+    # ---- e2e: the same calls with pinned HOST buffers, copies inside the timed region; every rank its own slice -----------
+    h_args = torch.empty((n_rays, 8), dtype=torch.float32).pin_memory()
+    h_args.copy_(d_args)
+    h_hits = torch.empty((n_rays, 4), dtype=torch.int32).pin_memory()
+    hits_np = h_hits.numpy().view(RAY_HIT).reshape(-1)
+    e_t, e_b, e_s = [], [], []
+    if dist:
+        dist.barrier()
+    for it in range(2 + max(2, min(args.steps, 5))):
+        t1 = time.perf_counter()
+        bvh.ray_traverse(h_args.numpy(), out=hits_np)
+        t2 = time.perf_counter()
+        if it >= 2:
+            e_t.append(t2 - t1)
+    e2e_hit_count = int((hits_np["t"] < 3.0e38).sum())
+    assert e2e_hit_count == hit_count, (e2e_hit_count, hit_count)
+    link = host_link_probe(e, h_args, d_args, d_hits, h_hits)
+    # the drop-in call over the reference's own 64-byte Ray structs, on a bounded prefix of the slice
+    n_struct = min(n_rays, 1 << 25)
+    h_rays = torch.empty((n_struct, 16), dtype=torch.float32).pin_memory()
+    with torch.cuda.stream(stream):
+        d_rays = torch.empty((n_struct, 16), dtype=torch.float32, device=dev)
+        api.ray_new(d_args[:n_struct], out=d_rays, ctx=ctx)
+        h_rays.copy_(d_rays)
+    stream.synchronize()
+    del d_rays
+    for it in range(2 + max(2, min(args.steps, 5))):
+        t1 = time.perf_counter()
+        bvh.ray_traverse(h_rays.numpy(), out=hits_np[:n_struct])
+        t2 = time.perf_counter()
+        if it >= 2:
+            e_s.append(t2 - t1)
+    if rank == 0:  # host-to-host build
+        h_tris = torch.from_numpy(tris).pin_memory()
+        for it in range(4):
+            t0 = time.perf_counter()
+            eb = api.build_cwbvh_from_tris(h_tris.numpy(), params, ctx=ctx)
+            if it >= 1:
+                e_b.append(time.perf_counter() - t0)
+        del eb, h_tris
+    e2e_trav_s, e2e_struct_s, e2e_build_s = all_max(e, [float(np.mean(e_t)), float(np.mean(e_s)) / n_struct * n_rays, float(np.mean(e_b)) if e_b else 0.0])
+    link_all = all_max(e, [link["concurrent_ms"], -link["h2d_gbs"], -link["d2h_gbs"]])
+    res = None
+    if rank == 0:
+        res = {
+            "value": value, "unit": "Mrays/s", "ms_per_step": step_ms, "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
+            "rays_total": n_total, "rays_this_gpu": n_rays, "tris": n_tris, "hits_this_gpu": hit_count,
+            "build": {"value": n_tris / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count,
+                      "floor_bytes": 48 * n_tris + 4 * n_tris + 80 * bvh.node_count,
+                      "frac_of_hbm_at_floor": (48 * n_tris + 4 * n_tris + 80 * bvh.node_count) / (build_ms * 1e-3) / 1e9 / peak if build_ms > 0 else None},
+            "broadcast": {"ms": bcast_ms, "bytes": 80 * bvh.node_count + 68 * bvh.prim_count,
+                          "gbs": (80 * bvh.node_count + 68 * bvh.prim_count) / (bcast_ms * 1e-3) / 1e9 if bcast_ms > 0 else None},
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_algorithmic": achieved / peak,
+                         "frac_dram": (traffic / (my_trav_ms * 1e-3) / 1e9 / peak) if traffic else None, "traffic": traffic,
+                         "kernel": kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": my_trav_ms,
+                         "nodes_visited": nodes_visited, "tris_tested": tris_tested,
+                         "note": "per GPU (rank 0's launch). B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); traffic = DRAM bytes "
+                                 "of the same launch from the committed ncu capture (profiles/traffic.json), null when the launch size differs from it"},
+            "cpu_baseline": cpu, "parity": parity,
+            "e2e": {"value": n_total / e2e_trav_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays, "d2h_bytes_per_step": 16 * n_rays,
+                    "how": "obvhs_cuda_cwbvh_ray_new_traverse_batch: pinned HOST Ray::new records (32 B/ray) in, pinned HOST RayHits out, every rank its "
+                           "own slice, max over ranks; the kernels run Ray::new as they fetch a ray",
+                    "ray_struct": {"value": n_total / e2e_struct_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 64 * n_rays, "measured_on_rays": n_struct,
+                                   "how": "obvhs_cuda_cwbvh_ray_traverse_batch over the reference's 64-byte Ray structs (the drop-in call)"},
+                    "build": {"mtris_per_s": n_tris / e2e_build_s / 1e6 if e2e_build_s > 0 else None, "h2d_bytes": 48 * n_tris,
+                              "how": "obvhs_cuda_build_cwbvh_from_tris from pinned HOST triangles, tree left on the device (rank 0)"},
+                    "host_link": {"slowest_rank_concurrent_copy_ms": link_all[0], "slowest_rank_h2d_gbs": -link_all[1], "slowest_rank_d2h_gbs": -link_all[2],
+                                  "how": "plain pinned cudaMemcpyAsync of this rank's ray records up and hits down at the same time (what bounds e2e)"}},
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+        }
+    state.clear()
+    return res, bool(ok_flag.item())
+
+
+def run_headline(args):
+    import torch
+
+    from obvhs_b200 import api, camera, device_rays, test_util as tu
+    from obvhs_b200.sharding import device_bytes_tensor, shard_range
+    from obvhs_b200.types import ray_args_of
+
+    e = setup_env(args)
+    config, res_terrain = headline_config(args)
+    # ---- S3 ----------------------------------------------------------------------------------------------------------
+    n_tris = 2 * res_terrain * res_terrain
+    tris = cached_demoscene(res_terrain) if e.rank == 0 else None
+    params = api.BvhBuildParams.fast_build()
+    with torch.cuda.stream(e.stream):
+        bvh0 = api.build_cwbvh_from_tris(torch.from_numpy(tris).to(e.dev), params, ctx=e.ctx) if e.rank == 0 else None
+        if e.world > 1:
+            bvh0 = api.CwBvh.broadcast(bvh0, e.ctx, 0)
+        _, _, tris_p = bvh0.device_ptrs()
+        rt_tris = device_bytes_tensor(tris_p, bvh0.prim_count * 64, e.local_rank).view(torch.float32).view(-1, 16)
+        lo, hi = shard_range(args.rays, e.rank, e.world)
+        cam = device_rays.DeviceCamera(camera.demoscene_camera(1280), e.dev)
+        d_args, aa_samples, n_primary = device_rays.bounce_set(cam, bvh0, rt_tris, lo, hi, args.rays)
+    e.stream.synchronize()
+    del rt_tris, bvh0
+    s3, ok_s3 = measure(e, args, "s3", tris, n_tris, "fast_build", d_args, args.rays, "traverse_persistent_kernel<CwTree, closest>", "hbm")
+    del d_args, tris
+    torch.cuda.empty_cache()
+    # ---- kitchen -------------------------------------------------------------------------------------------------------
+    ktris = tu.kitchen()
+    krays = ray_args_of(camera.primary_rays(camera.kitchen_camera(1920)))
+    klo, khi = shard_range(krays.shape[0], e.rank, e.world)
+    with torch.cuda.stream(e.stream):
+        d_kargs = torch.from_numpy(np.ascontiguousarray(krays[klo:khi])).to(e.dev)
+    kitchen, ok_k = measure(e, args, "kitchen", ktris if e.rank == 0 else None, ktris.shape[0], "fast_build", d_kargs, krays.shape[0],
+                            "traverse_kernel<CwTree, closest>", "issue/L2")
+    if e.rank == 0:
+        kitchen["roofline"]["note"] += ("; the kitchen's tree (0.5 MB) and triangles (3.6 MB) live in L1/L2: frac_algorithmic measures cache-served reuse, "
+                                       "the kernel is issue-bound (ncu: profiles/), frac_dram is the share of HBM bandwidth it actually uses")
+        line = {"metric": METRIC, "value": s3["value"], "unit": "Mrays/s", "n_gpus": e.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": s3["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (demoscene terrain, device-generated rays); kitchen.obj fixture (reference asset) in `kitchen`", "config": config,
+                "detail": {"aa_samples_walked": aa_samples, "primary_rays_traced_for_the_bounce_set": n_primary, "host_numa": e.numa_note,
+                           "rays_per_gpu": hi - lo}}
+        for k in ("build", "traverse_ms", "broadcast_ms", "broadcast", "roofline", "cpu_baseline", "parity", "e2e", "gpu_launches", "clocks",
+                  "wall_s_timed_region"):
+            line[k] = s3[k]
+        line["gpu_launches"] = s3["gpu_launches"] + kitchen["gpu_launches"]
+        line["kitchen"] = kitchen
+        line["parity_ok"] = bool(ok_s3 and ok_k)
+        print(json.dumps(line))
+    if e.dist:
+        e.dist.barrier()
+        e.dist.destroy_process_group()
+    if not (ok_s3 and ok_k):
+        raise SystemExit("bench.py: parity check failed (see `parity` in the JSON line)")
+
+
+def run_headline_reference(args):
+    """--impl reference for the headline: the CPU restatement on a bounded sample of both workloads, same `config`."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle_bind as ob
+    from obvhs_b200 import camera, test_util as tu
+
+    config, res_terrain = headline_config(args)
+    threads = len(os.sched_getaffinity(0))
+    tris = cached_demoscene(res_terrain)
+    n_builds = max(1, min(args.steps, 2))
+    build_s = []
+    c = None
+    for _ in range(n_builds):
+        c = ob.build_cwbvh_from_tris(tris, "fast_build", threads=threads)
+        build_s.append(c.core_build_seconds)
+    bt = c.bvh_tris(tris)
+    n_samples = max(1, int(round(args.ref_rays / (1280 * 475 * 0.6))))
+    rays, _ = camera.demoscene_bounce_set(camera.demoscene_camera(1280), range(n_samples), bt,
+                                          lambda r: c.ray_traverse(bt, r, threads=threads, use_simd=True))
+    rays = rays[: args.ref_rays]
+    ts = []
+    for it in range(min(args.warmup, 1) + args.steps):
+        t0 = time.perf_counter()
+        c.ray_traverse(bt, rays, threads=threads, use_simd=True)
+        if it >= min(args.warmup, 1):
+            ts.append(time.perf_counter() - t0)
+    trav_s, b_s = float(np.mean(ts)), float(np.mean(build_s))
+    mrays = rays.shape[0] / trav_s / 1e6
+    ktris = tu.kitchen()
+    krays = camera.primary_rays(camera.kitchen_camera(1920))
+    kr = cpu_reference_leg(ktris, krays, "fast_build", max(1, min(args.steps, 5)), 1)
+    kmrays = krays.shape[0] / kr["trav_s"] / 1e6
+    sample = (f"S3: {rays.shape[0]} bounce rays of AA samples 0..{n_samples - 1} (CPU-generated with the same recipe) per step, {n_builds} full builds of "
+              f"{tris.shape[0]} tris; kitchen: all {krays.shape[0]} rays and a full build per step; C++ restatement of the obvhs CPU path (OpenMP), not the "
+              "rustc/rayon binary")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": (trav_s + b_s) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (demoscene terrain); kitchen.obj fixture (reference asset) in `kitchen`", "config": config,
+        "build": {"value": tris.shape[0] / b_s / 1e6, "unit": "Mtris/s", "ms": b_s * 1e3},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample, "build_mtris_per_s": tris.shape[0] / b_s / 1e6},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kitchen": {"value": kmrays, "unit": "Mrays/s", "build": {"value": ktris.shape[0] / kr["build_s"] / 1e6, "unit": "Mtris/s", "ms": kr["build_s"] * 1e3},
+                    "e2e": {"value": kmrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "gpu_launches": 0}))
+
+
 def run_ours(args):
     import torch
 
@@ -462,11 +932,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+def ncu_traffic(workload, n_rays=None):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None. With n_rays:
+    only when the capture was taken on a launch of that many rays (the headline's N = 1 configuration)."""
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload, {}).get("bytes")
+            ent = json.load(f).get(workload, {})
+        if n_rays is not None and ent.get("rays") not in (None, n_rays):
+            return None
+        return ent.get("bytes")
     except (OSError, ValueError):
         return None
 
@@ -835,14 +1309,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="kitchen", choices=["kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
+    ap.add_argument("--workload", default="s3", choices=["s3", "kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
+    ap.add_argument("--rays", type=int, default=S3_RAYS, help="size of the headline's global bounce-ray set")
+    ap.add_argument("--parity-rays", type=int, default=262_144, help="rays of the in-run oracle comparison")
     ap.add_argument("--samples", type=int, default=24, help="AA samples of the bounce workload (165 = the 100M-ray set of SURVEY.md 8d)")
     ap.add_argument("--tris", type=int, default=10_000_000)
     ap.add_argument("--ref-rays", type=int, default=2_073_600, help="ray sample bound for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "dynamic":
+    if args.workload == "s3":
+        run_headline_reference(args) if args.impl == "reference" else run_headline(args)
+    elif args.workload == "dynamic":
         run_dynamic(args)
     elif args.workload == "demoscene":
         run_demoscene(args)

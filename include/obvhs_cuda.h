@@ -33,7 +33,8 @@ typedef enum {
     OBVHS_ERR_UNSUPPORTED = -3, /* depth beyond the fixed stacks, >= 2^30 primitives */
     OBVHS_ERR_NAN_INPUT = -4,   /* the reference panics / goes out of bounds on NaN AABBs (ploc/mod.rs:451) */
     OBVHS_ERR_STACK_OVERFLOW = -5,
-    OBVHS_ERR_CAPACITY = -6     /* a growing output (Vec::push in the reference) does not fit the caller's arrays */
+    OBVHS_ERR_CAPACITY = -6,    /* a growing output (Vec::push in the reference) does not fit the caller's arrays */
+    OBVHS_ERR_NCCL = -7         /* NCCL missing at run time, or a collective failed */
 } ObvhsStatus;
 
 /* src/aabb.rs:11-16 -- two Vec3A lanes; the 4th float of each lane is padding (never read, never compared). */
@@ -93,7 +94,8 @@ uint64_t obvhs_cuda_launch_count(const ObvhsContext* ctx);
  * judged on the device and goes to the kernel that suits it), "static" (one ray per thread) or "persistent[:refill[:chunk]]" (persistent warps refilled from a ray cursor when
  * `refill` of 32 lanes have finished, `chunk` consecutive rays per fetch). key "host_slice": rays per pipelined slice of a host-resident ray batch ("0" = sized for the kernel
  * in use). key "trace": "1"/"0" stage timing on stderr
- * (the reference's scope!/timeit! macros, lib.rs:158-205). Environment: OBVHS_TRAVERSE, OBVHS_TRACE set the defaults. */
+ * (the reference's scope!/timeit! macros, lib.rs:158-205). key "traverse_variant": "<id>" picks the persistent kernel's
+ * scheduling / stack / register-cap variant (traverse.cu; 0 = default). Environment: OBVHS_TRAVERSE, OBVHS_TRAVERSE_VARIANT, OBVHS_TRACE set the defaults. */
 int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value);
 /* 6 built-in presets of src/lib.rs:233-305 by name: fastest_build, very_fast_build, fast_build, medium_build,
  * slow_build, very_slow_build. */
@@ -217,7 +219,7 @@ int obvhs_cuda_bvh2_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsBvh
 
 /* ---- CwBvh (src/cwbvh) ------------------------------------------------------------------------------------ */
 /* bvh2_to_cwbvh(&bvh2, max_prims_per_leaf, order_children, include_exact_node_aabbs) (bvh2_to_cwbvh.rs:490-510).
- * include_exact_node_aabbs must be 0. */
+ * include_exact_node_aabbs != 0 also fills CwBvh::exact_node_aabbs (see obvhs_cuda_cwbvh_exact_node_aabbs). */
 int obvhs_cuda_bvh2_to_cwbvh(ObvhsContext* ctx, const ObvhsBvh2* bvh, uint32_t max_prims_per_leaf, int order_children,
                              int include_exact_node_aabbs, ObvhsCwBvh** out);
 /* CwBvh::exact_node_aabbs (src/cwbvh/mod.rs:47; filled when bvh2_to_cwbvh was called with include_exact_node_aabbs,
@@ -272,6 +274,8 @@ int obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch(ObvhsContext* ctx, const Ob
  * counters[0] += nodes visited, counters[1] += triangles tested (host or device pointer to 2 x u64). */
 int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRay* rays, size_t n,
                                                 ObvhsRayHit* hits, uint64_t* counters);
+int obvhs_cuda_cwbvh_ray_new_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n,
+                                                    ObvhsRayHit* hits, uint64_t* counters);
 /* Ray::new (src/ray.rs:34-52) for n argument records -> n Ray structs (host or device pointers). */
 int obvhs_cuda_ray_new_batch(ObvhsContext* ctx, const ObvhsRayNew* args, size_t n, ObvhsRay* rays);
 /* ray_traverse / ray_traverse_miss / ray_traverse_anyhit of rays[i] = Ray::new(args[i]): identical results to the *_batch
@@ -287,6 +291,23 @@ int obvhs_cuda_bvh2_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* b
                                            ObvhsRayHit* hits);
 int obvhs_cuda_bvh2_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n,
                                                 uint8_t* miss);
+/* ---- multi-GPU: replicate a finished tree -------------------------------------------------------------------
+ * The reference's CwBvh is a plain Clone of three Vecs and an Aabb (src/cwbvh/mod.rs:43-55) and ray_traverse only reads &self
+ * (:169): the build runs on ONE GPU, the finished tree is broadcast over NVLink / NVSwitch with NCCL, and every rank traverses
+ * its own range of rays against its replica (no collective on the traversal path). One process (or thread) per GPU, one
+ * context per rank. NCCL is bound at run time (dlopen libnccl.so.2, override with OBVHS_NCCL_LIB); OBVHS_ERR_NCCL without it.
+ *   obvhs_cuda_nccl_unique_id : on ONE rank; the caller ships the 128 bytes to the others (file, socket, MPI, torch.distributed)
+ *   obvhs_cuda_comm_init      : collective over `world` ranks; binds an ncclComm_t to the context (freed with it)
+ *   obvhs_cuda_cwbvh_broadcast: collective; *bvh is the finished tree on `root`; elsewhere NULL or a handle from an earlier
+ *                               broadcast (its buffers are reused when the sizes match) and receives the replica: nodes,
+ *                               primitive_indices, total_aabb, flags and the permuted triangles when the root has them.
+ *                               A 64-byte header broadcast, then ONE grouped NCCL launch, all on the context's stream; the
+ *                               receivers make one host round trip (the header), the root none. */
+#define OBVHS_NCCL_UNIQUE_ID_BYTES 128
+int obvhs_cuda_nccl_unique_id(uint8_t id[OBVHS_NCCL_UNIQUE_ID_BYTES]);
+int obvhs_cuda_comm_init(ObvhsContext* ctx, const uint8_t id[OBVHS_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+int obvhs_cuda_cwbvh_broadcast(ObvhsContext* ctx, ObvhsCwBvh** bvh, int root);
+
 /* ---- broad-phase queries (batched; the per-report closure of the reference becomes a list of reports) ---------------
  * Bvh2::aabb_traverse(aabb, eval) / Bvh2::point_traverse(point, eval)  (src/bvh2/mod.rs:365-456) for n queries with an eval
  * that always continues: counts[i] = number of leaf nodes reported for query i; leaf_ids receives the reported leaf NODE

@@ -115,6 +115,10 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_ray_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "obvhs_cuda_cwbvh_ray_new_traverse_batch_counted": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "obvhs_cuda_nccl_unique_id": (_i32, [_vp]),
+    "obvhs_cuda_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "obvhs_cuda_cwbvh_broadcast": (_i32, [_vp, _PP, _i32]),
     "obvhs_cuda_ray_new_batch": (_i32, [_vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_new_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_new_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
@@ -202,6 +206,13 @@ class Context:
     def synchronize(self):
         self.check(self.lib.obvhs_cuda_synchronize(self.h))
 
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """obvhs_cuda_comm_init: bind an NCCL communicator over `world` ranks to this context (collective). `unique_id` is the
+        128-byte id `nccl_unique_id()` returned on one rank, shipped to the others by the caller."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self.check(self.lib.obvhs_cuda_comm_init(self.h, buf, int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.obvhs_cuda_launch_count(self.h))
@@ -216,6 +227,15 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    """obvhs_cuda_nccl_unique_id (call on ONE rank, then ship the bytes to the others)."""
+    buf = (C.c_uint8 * 128)()
+    rc = load_library().obvhs_cuda_nccl_unique_id(buf)
+    if rc != 0:
+        raise ObvhsError(rc, "NCCL is not available (libnccl.so.2 not found)")
+    return bytes(buf)
 
 
 _default_ctx = {}
@@ -612,6 +632,19 @@ class CwBvh:
         ctx.check(ctx.lib.obvhs_cuda_cwbvh_alloc(ctx.h, node_count, prim_count, int(with_triangles), _ptr(total), C.byref(h)))
         return cls(ctx, h)
 
+    @staticmethod
+    def broadcast(bvh: "CwBvh | None", ctx: Context, root: int = 0) -> "CwBvh":
+        """obvhs_cuda_cwbvh_broadcast (collective over ctx's communicator): `bvh` is the finished tree on `root`; elsewhere None or a
+        replica from an earlier broadcast (reused when the sizes match). Returns this rank's handle; the transfer is ordered on
+        the context's stream."""
+        h = C.c_void_p(bvh.h.value if bvh is not None else None)
+        ctx.check(ctx.lib.obvhs_cuda_cwbvh_broadcast(ctx.h, C.byref(h), int(root)))
+        if bvh is not None:
+            if bvh.h.value == h.value:
+                return bvh
+            bvh.h = None  # the library freed (replaced) the old handle
+        return CwBvh(ctx, h)
+
     def download(self):
         nodes = np.zeros(self.node_count, dtype=CWBVH_NODE)
         prims = np.zeros(self.prim_count, dtype=np.uint32)
@@ -670,8 +703,9 @@ class CwBvh:
         r, is_args = _as_rays(rays)
         n = r.shape[0]
         hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
-        if is_args:  # (n,8) Ray::new arguments: the constructor runs on the device
-            assert counters is None
+        if is_args and counters is not None:  # (n,8) Ray::new arguments: the constructor runs on the device
+            self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_new_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
+        elif is_args:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_new_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))
         elif counters is None:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch(self.ctx.h, self.h, _ptr(r), n, _ptr(hits)))

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libobvhs_cuda.so")
-SOURCES = ["api.cu", "ploc.cu", "sort.cu", "bvh2.cu", "collapse.cu", "splits.cu", "reinsertion.cu", "cwbvh_build.cu", "traverse.cu", "query.cu"]
+SOURCES = ["api.cu", "ploc.cu", "sort.cu", "bvh2.cu", "collapse.cu", "splits.cu", "reinsertion.cu", "cwbvh_build.cu", "traverse.cu", "query.cu", "comm.cu"]
 HEADERS = ["common.cuh", "compact.cuh", "cwbvh_exponent.h", os.path.join("..", "..", "include", "obvhs_cuda.h")]
 
 NVCC_FLAGS = [
@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB_PATH, *objs,
-            "-Xlinker", "--exclude-libs,ALL"]
+            "-Xlinker", "--exclude-libs,ALL", "-ldl"]
     subprocess.check_call(link)
     # a static archive of the same objects: what a Rust build.rs would link (north_star)
     ar = os.path.join(LIB_DIR, "libobvhs_cuda.a")

@@ -190,6 +190,7 @@ static void context_teardown(ObvhsContext* ctx) {
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_destroy(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -335,17 +336,13 @@ int obvhs_cuda_set_option(ObvhsContext* ctx, const char* key, const char* value)
         }
         return OBVHS_OK;
     }
-    if (strcmp(key, "traverse_variant") == 0) {  // persistent-kernel variant "<id>[:<node_thr>]" (traverse.cu: launch_persistent_t)
+    if (strcmp(key, "traverse_variant") == 0) {  // persistent-kernel variant (traverse.cu: launch_persistent_t)
         const int id = atoi(value);
-        if (id < 0 || id > 8) {
-            OBVHS_SET_ERR(ctx, "traverse_variant id must be in 0..8");
+        if (id < 0 || id > 4) {
+            OBVHS_SET_ERR(ctx, "traverse_variant id must be in 0..4");
             return OBVHS_ERR_INVALID_ARG;
         }
         ctx->traverse_variant = id;
-        if (const char* c2 = strchr(value, ':')) {
-            const int thr = atoi(c2 + 1);
-            ctx->traverse_node_thr = thr < 1 ? 1 : (thr > 33 ? 33 : thr);
-        }
         return OBVHS_OK;
     }
     if (strcmp(key, "host_slice") == 0) {  // rays per pipelined slice of a host batch; 0 = sized for the kernel in use
@@ -1118,6 +1115,29 @@ int obvhs_cuda_cwbvh_ray_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCw
     API_ENTER(ctx);
     ARG_CHECK(ctx, counters, "counters is null");
     return cw_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+
+int obvhs_cuda_cwbvh_ray_new_traverse_batch_counted(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayNew* args, size_t n, ObvhsRayHit* hits,
+                                                    uint64_t* counters) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, counters, "counters is null");
+    return cw_traverse(ctx, bvh, args, n, 0, hits, sizeof(ObvhsRayHit), counters);
+}
+
+// ---- multi-GPU (comm.cu) -----------------------------------------------------------------------------------------
+int obvhs_cuda_nccl_unique_id(uint8_t id[OBVHS_NCCL_UNIQUE_ID_BYTES]) {
+    if (!id) return OBVHS_ERR_INVALID_ARG;
+    return comm_unique_id(id);
+}
+int obvhs_cuda_comm_init(ObvhsContext* ctx, const uint8_t id[OBVHS_NCCL_UNIQUE_ID_BYTES], int rank, int world) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, id && world >= 1 && rank >= 0 && rank < world, "bad id / rank / world");
+    return comm_init(ctx, id, rank, world);
+}
+int obvhs_cuda_cwbvh_broadcast(ObvhsContext* ctx, ObvhsCwBvh** bvh, int root) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && root >= 0 && root < ctx->comm_world, "bad handle pointer / root");
+    return comm_broadcast_cwbvh(ctx, bvh, root);
 }
 
 // ---- the same traversals over Ray::new arguments (32 B per ray) -------------------------------------------------------

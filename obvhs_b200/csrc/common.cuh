@@ -141,8 +141,12 @@ struct ObvhsContext {
     size_t host_slice = 0;  // obvhs_cuda_set_option("host_slice", "<rays>"), 0 = automatic
     std::vector<cudaEvent_t> event_pool;
     int traverse_mode = 2, traverse_refill = 4, traverse_chunk = 32;  // obvhs_cuda_set_option("traverse", "auto|static|persistent[:refill[:chunk]]")
-    int traverse_variant = 0, traverse_node_thr = 16;                  // obvhs_cuda_set_option("traverse_variant", "<id>[:<node_thr>]"), traverse.cu
+    int traverse_variant = 0;                                           // obvhs_cuda_set_option("traverse_variant", "<id>"), traverse.cu
     size_t traverse_resident_lanes = 0;                                 // lanes the persistent kernel keeps resident (set by its launcher)
+    // multi-GPU (comm.cu): an NCCL communicator bound to this context's device, and the 64-byte device header of a broadcast
+    void* comm = nullptr;  // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    void* comm_header = nullptr;
     bool staged_host = false;  // a stage_in() of this API call copied from HOST memory: the call synchronises before it returns
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
 };
@@ -287,6 +291,12 @@ static inline int copy_out(ObvhsContext* ctx, T* dst, const T* src_dev, size_t c
     }
     return OBVHS_OK;
 }
+
+// comm.cu
+int comm_unique_id(uint8_t* id);
+int comm_init(ObvhsContext* ctx, const uint8_t* id, int rank, int world);
+void comm_destroy(ObvhsContext* ctx);
+int comm_broadcast_cwbvh(ObvhsContext* ctx, ObvhsCwBvh** bvh, int root);
 
 // ---- stage entry points implemented across the .cu files ---------------------------------------------------
 // ploc.cu

@@ -43,9 +43,7 @@ __device__ __forceinline__ void rt_triangle_of(const float4 a, const float4 b, c
     out[2] = make_float4(e2x, e2y, e2z, 0.f);
     out[3] = make_float4(e1y * e2z - e2y * e1z, e1z * e2x - e2z * e1x, e1x * e2y - e2x * e1y, 0.f);  // e1 x e2
 }
-__device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, u32 id, const RayRegs& r) {
-    const float4* t = tris + (size_t)id * RT_TRI_VEC4;
-    const float4 a = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2), n = __ldg(t + 3);
+__device__ __forceinline__ float tri_intersect_vals(const float4 a, const float4 e1, const float4 e2, const float4 n, const RayRegs& r) {
     float cx = a.x - r.ox, cy = a.y - r.oy, cz = a.z - r.oz;        // v0 - origin
     float rx = r.dy * cz - cy * r.dz, ry = r.dz * cx - cz * r.dx, rz = r.dx * cy - cx * r.dy;  // d x c
     float inv_det = 1.0f / ((n.x * r.dx + n.y * r.dy) + n.z * r.dz);
@@ -59,6 +57,16 @@ __device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, 
         if (tt >= r.tmin && tt <= r.tmax) return tt;
     }
     return __int_as_float(0x7f800000);
+}
+__device__ __forceinline__ float tri_intersect(const float4* __restrict__ tris, u32 id, const RayRegs& r) {
+    const float4* t = tris + (size_t)id * RT_TRI_VEC4;
+    return tri_intersect_vals(__ldg(t), __ldg(t + 1), __ldg(t + 2), __ldg(t + 3), r);
+}
+__device__ __forceinline__ float4 as_f4(const uint4 q) {
+    return make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+}
+__device__ __forceinline__ float tri_intersect_regs(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const RayRegs& r) {
+    return tri_intersect_vals(as_f4(q0), as_f4(q1), as_f4(q2), as_f4(q3), r);
 }
 
 // u8 -> f32 without the (quarter-rate) I2F pipe: 0x4B000000 | byte is the float 8388608 + byte, and subtracting 8388608
@@ -270,7 +278,6 @@ struct CwTree {
     // pending work (cwbvh/mod.rs:216-220 returns there) and the state machine runs out on its own. An early `break`/`goto`
     // out of the primitive loop made ptxas (12.9, sm_100a) share convergence-barrier registers between the primitive loop
     // and the node test, and the persistent kernel then dead-locked on scenes where lanes of one warp sat in both at once.
-    __device__ __forceinline__ bool tris_pending(const State& st) const { return st.prim.y != 0; }
     // traverse_macro.rs:64-72, one primitive of the current group (highest set bit first)
     template <int MODE, bool COUNT>
     __device__ __forceinline__ void tri_step(State& st, u32& tris_tested) const {
@@ -330,6 +337,86 @@ struct CwTree {
                 st.sp--;
                 st.cur = stack.get(st.sp);
             }
+        }
+        return done;
+    }
+    // One turn with a SINGLE memory round trip for the whole warp (persistent kernel, POLICY 1). step<ONE_TRI> runs the triangle
+    // lanes and the node lanes of a warp as two divergent paths, each with its own load -> use dependency, so a turn costs two
+    // serialized memory latencies. Here every lane first works out what it needs next -- the next triangle of its group (64 bytes)
+    // or the next node (80 bytes; a lane whose group ran dry pops its stack first, in the same turn) -- then the warp issues all
+    // the 16-byte loads together, and only then splits into the triangle test and the node test. The per-ray sequence of tests is
+    // exactly traverse_macro.rs:59-126 (a ray still drains its primitive group before its next node). Returns true when the ray
+    // is done. Measured on B200 (10 M triangles): long-scoreboard stalls per issue 6.2 -> 3.3, issue-slot utilisation 67 -> 77 %,
+    // but 12 % more instructions (every lane advances one test per turn instead of up to two): +2 % on the soup, -4 % on the
+    // bounce set. Kept as a selectable variant, not the default.
+    template <int MODE, bool COUNT, class Stack>
+    __device__ __forceinline__ bool fused_turn(State& st, Stack& stack, u32& nodes_visited, u32& tris_tested) const {
+        const bool tri = st.prim.y != 0;
+        const uint4* addr = nullptr;
+        u32 pid = 0;
+        bool done = false;
+        if (tri) {  // traverse_macro.rs:64-72: highest set bit first
+            const u32 local = 31u - __clz(st.prim.y);
+            st.prim.y &= ~(1u << local);
+            pid = st.prim.x + local;
+            addr = reinterpret_cast<const uint4*>(tris) + (size_t)pid * RT_TRI_VEC4;
+        } else {
+            if ((st.cur.y & 0xff000000u) == 0) {  // traverse_macro.rs:112-123: both groups empty -> pop or finish
+                if (st.sp == 0) done = true;
+                else {
+                    st.sp--;
+                    st.cur = stack.get(st.sp);
+                }
+            }
+            if (!done) {  // traverse_macro.rs:76-103
+                const u32 hits_imask = st.cur.y;
+                const u32 child_index_offset = 31u - __clz(hits_imask);
+                const u32 child_index_base = st.cur.x;
+                st.cur.y &= ~(1u << child_index_offset);
+                if (st.cur.y & 0xff000000u) {  // faststack.rs:299-303 saturating push
+                    stack.put(st.sp, st.cur);
+                    st.sp = min(st.sp + 1u, 31u);
+                }
+                const u32 slot_index = (child_index_offset - 24u) ^ (st.oct_inv4 & 0xffu);
+                const u32 relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+                addr = nodes + (size_t)(child_index_base + relative_index) * 5;
+            }
+        }
+        // the warp's loads, issued together (asm volatile: the compiler must not sink them into the two branches below)
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0, q4 = q0;
+        if (addr) {
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(addr));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(addr));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "l"(addr));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+48];" : "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(addr));
+            if (!tri) asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+64];" : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w) : "l"(addr));
+        }
+        if (tri) {
+            const float t = tri_intersect_regs(q0, q1, q2, q3, st.r);
+            if (COUNT) tris_tested++;
+            if (MODE == 0) {
+                if (t < st.r.tmax) {  // cwbvh/mod.rs:184-189
+                    st.o.hit_id = pid;
+                    st.o.hit_t = t;
+                    st.r.tmax = t;
+                }
+            } else if (MODE == 1) {
+                if (t < st.r.tmax) {  // cwbvh/mod.rs:216-220: the first hit ends the ray
+                    st.o.is_miss = false;
+                    done = true;
+                }
+            } else {
+                if (t < __int_as_float(0x7f800000)) st.o.count++;
+            }
+        } else if (!done) {
+            if (COUNT) nodes_visited++;
+            const u32 hitmask = node_intersect(q0, q1, q2, q3, q4, st.r, st.oct_inv4, magic);
+            st.cur.x = q1.x;                                   // child_base_idx
+            st.prim.x = q1.y;                                  // primitive_base_idx
+            st.cur.y = (hitmask & 0xff000000u) | (q0.w >> 24);  // | imask
+            st.prim.y = hitmask & 0x00ffffffu;
+            // nothing hit and nothing stacked: finished (otherwise the next turn pops)
+            if (st.prim.y == 0 && (st.cur.y & 0xff000000u) == 0 && st.sp == 0) done = true;
         }
         return done;
     }
@@ -631,14 +718,17 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, c
 //
 // POLICY 0: every turn of the inner loop runs both halves of the state machine, the lanes with a pending triangle the triangle
 //           test and the others the node test (two divergent paths per turn, each with part of the warp).
-// POLICY 1: every turn runs ONE of them for the whole warp. The node test (the expensive half: ~250 instructions, five 16-byte
-//           loads) runs when at least `node_thr` lanes are waiting for it or no lane has a triangle pending; otherwise the
-//           triangle lanes take a turn and the node lanes wait, so node tests are issued with fuller warps. The per-ray order
-//           of tests is untouched (only which lanes move in a given turn changes).
-// SS      : stack entries per lane kept in shared memory (LaneStack).
+// POLICY 1: CwTree::fused_turn -- the loads of the whole warp are issued before the warp splits (one memory round trip per turn).
+// SS      : stack entries per lane kept in shared memory (LaneStack); the rest spills to local memory.
 // MINB    : __launch_bounds__ minimum CTAs per SM (register cap).
+// Dead ends measured in round 2 on the 10 M-triangle scenes (soup / bounce / terrain Mrays/s against 856 / 5865 / 2230 for the
+// default): running ONE of the two halves per turn for the whole warp, the node test only when >= 8 / 16 / 24 lanes wait for it
+// (555 / 732 / 800 on the soup: the waiting lanes cost more turns than the fuller node tests save); holding fetched nodes in
+// registers until >= 16 lanes hold one (692: no gain in lanes per instruction, 24 % more instructions); 48 registers for ten
+// CTAs per SM (785: spills); the shared-memory short stack alone (857 / 5771 / 2171: removes 2.1 GB of local-memory write-through
+// per 2 M rays, no time change).
 struct PersistArgs {
-    u32 chunk, refill, node_thr, packed;
+    u32 chunk, refill, packed;
 };
 template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
 __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n,
@@ -698,22 +788,12 @@ __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(c
                 }
             } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
         } else {
-            u32 n_active;
             do {
-                const bool want_tri = active && tree.tris_pending(st);
-                const u32 tri_mask = __ballot_sync(0xffffffffu, want_tri);
-                const u32 node_mask = __ballot_sync(0xffffffffu, active && !want_tri);
-                if (tri_mask != 0 && (u32)__popc(node_mask) < pa.node_thr) {
-                    if (want_tri) tree.template tri_step<MODE, COUNT>(st, tris_tested);
-                    n_active = __popc(tri_mask | node_mask);
-                } else {
-                    if (active && !want_tri && tree.template node_step<COUNT>(st, stack, nodes_visited)) {
-                        result_store<MODE>(st.o, out, my);
-                        active = false;
-                    }
-                    n_active = __popc(__ballot_sync(0xffffffffu, active));
+                if (active && tree.template fused_turn<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
+                    result_store<MODE>(st.o, out, my);
+                    active = false;
                 }
-            } while (n_active >= min_active);
+            } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
         }
     }
     trav_flush_counters<COUNT>(counters, nodes_visited, tris_tested);
@@ -744,8 +824,8 @@ __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float t
 
 }  // namespace
 
-// Persistent-kernel variants (POLICY, SS, MINB) selectable per context: obvhs_cuda_set_option("traverse_variant", "<id>[:<node_thr>]").
-// Variant 0 is the round-1 kernel. Only CwTree has the split tri_step / node_step POLICY 1 needs; Bvh2 trees always run variant 0.
+// Persistent-kernel variants (POLICY, SS, MINB) selectable per context: obvhs_cuda_set_option("traverse_variant", "<id>").
+// Variant 0 is the default. Only CwTree has fused_turn (POLICY 1); Bvh2 trees always run variant 0.
 template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
 static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, void* d_out, unsigned long long* c,
                                u32* next, const DeferList& defer) {
@@ -756,7 +836,7 @@ static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4
     size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
     if (blocks > need) blocks = need;
     ctx->traverse_resident_lanes = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm) * TRAV_BLOCK;
-    const PersistArgs pa{(u32)ctx->traverse_chunk, (u32)ctx->traverse_refill, (u32)ctx->traverse_node_thr, packed ? 1u : 0u};
+    const PersistArgs pa{(u32)ctx->traverse_chunk, (u32)ctx->traverse_refill, packed ? 1u : 0u};
     kernel<<<(unsigned)blocks, TRAV_BLOCK, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next, pa, defer);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
@@ -774,14 +854,10 @@ static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4
         switch (ctx->traverse_variant) {
 #define OBVHS_V(ID, POLICY, SS, MINB) \
     case ID: return launch_persistent_v<Tree, MODE, COUNT, false, POLICY, SS, MINB>(ctx, tree, rays, n, packed, d_out, c, next, defer);
-            OBVHS_V(1, 1, 0, 9)
-            OBVHS_V(2, 0, 8, 9)
+            OBVHS_V(1, 0, 8, 9)
+            OBVHS_V(2, 1, 0, 9)
             OBVHS_V(3, 1, 8, 9)
-            OBVHS_V(4, 1, 12, 9)
-            OBVHS_V(5, 1, 8, 10)
-            OBVHS_V(6, 1, 8, 12)
-            OBVHS_V(7, 0, 0, 10)
-            OBVHS_V(8, 1, 0, 10)
+            OBVHS_V(4, 0, 0, 10)
 #undef OBVHS_V
             default: break;
         }

@@ -6,7 +6,8 @@ ordered), the finished tree (80-byte nodes, primitive_indices, permuted triangle
 NVLink/NVSwitch, and every rank traverses its own contiguous range of rays against its replica. There is no exchange step
 during traversal, hence no collective on the traversal path.
 
-`torch.distributed` is the plumbing (backend "nccl" on GPUs, "gloo" in the CPU tests).
+`torch.distributed` launches the ranks and ships the communicator id (backend "nccl" on GPUs, "gloo" in the CPU tests); the tree
+itself travels through the library's own NCCL communicator (include/obvhs_cuda.h: obvhs_cuda_comm_init / _cwbvh_broadcast).
 """
 from __future__ import annotations
 
@@ -41,36 +42,29 @@ def broadcast_meta(meta, src: int = 0):
     return box[0]
 
 
-def broadcast_cwbvh(bvh, ctx, src: int = 0):
-    """Replicate a finished CwBvh (built on rank `src`; pass None elsewhere) to every rank's GPU.
-
-    Three NCCL broadcasts straight out of / into the library's device buffers: nodes (80*M B), primitive_indices (4*N B),
-    permuted triangles (64*N B, RtTriangle form). Returns this rank's CwBvh handle."""
+def init_comm(ctx):
+    """Bind the library's own NCCL communicator to `ctx` (obvhs_cuda_comm_init). torch.distributed only ships the 128-byte id from
+    rank 0; every later transfer runs below the C ABI, on the context's stream. Idempotent."""
     import torch.distributed as dist
 
     from . import api
 
-    import torch
+    if getattr(ctx, "comm_world", None) is not None:
+        return
+    box = [api.nccl_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], dist.get_rank(), dist.get_world_size())
 
-    rank = dist.get_rank()
-    # sizes + scene AABB travel as one small NCCL broadcast (11 float64: exact for counts < 2^53 and for f32 bounds)
-    meta = torch.zeros(11, dtype=torch.float64, device=f"cuda:{ctx.device}")
-    if rank == src:
-        nodes_p, prims_p, tris_p = bvh.device_ptrs()
-        meta[:3] = torch.tensor([bvh.node_count, bvh.prim_count, 1.0 if tris_p else 0.0], dtype=torch.float64)
-        meta[3:] = torch.from_numpy(bvh.total_aabb().astype(np.float64))
-    dist.broadcast(meta, src=src)
-    m = meta.tolist()
-    node_count, prim_count, has_tris, total = int(m[0]), int(m[1]), bool(m[2]), m[3:]
-    tri_bytes = int(ctx.lib.obvhs_cuda_cwbvh_triangle_bytes())  # the handle keeps 64-byte RtTriangles
-    if rank != src:
-        bvh = api.CwBvh.alloc(node_count, prim_count, has_tris, np.asarray(total, np.float32), ctx=ctx)
-        nodes_p, prims_p, tris_p = bvh.device_ptrs()
-    ctx.synchronize()
-    for ptr, nbytes in ((nodes_p, node_count * 80), (prims_p, prim_count * 4), (tris_p if has_tris else 0, prim_count * tri_bytes)):
-        if ptr and nbytes:
-            dist.broadcast(device_bytes_tensor(ptr, nbytes, ctx.device), src=src)
-    return bvh
+
+def broadcast_cwbvh(bvh, ctx, src: int = 0):
+    """Replicate a finished CwBvh (built on rank `src`; pass None -- or an earlier replica to refill -- elsewhere) to every rank's
+    GPU: obvhs_cuda_cwbvh_broadcast, i.e. a 64-byte header plus ONE grouped NCCL launch for nodes (80*M B), primitive_indices
+    (4*N B) and the permuted triangles (64*N B, RtTriangle form), straight out of / into the library's device buffers and ordered
+    on the context's stream (whatever follows on that stream sees the replica). Returns this rank's CwBvh handle."""
+    from . import api
+
+    init_comm(ctx)
+    return api.CwBvh.broadcast(bvh, ctx, src)
 
 
 def broadcast_arrays_cpu(arrays, src: int = 0):

@@ -1,5 +1,5 @@
 """python scripts/trav_sweep.py <workload> [tris] [samples] -- device time of the persistent traversal kernel variants on one workload.
-VARIANTS = comma list of "<variant>:<node_thr>[/<refill>]" (obvhs_cuda_set_option traverse_variant / traverse); all must return
+VARIANTS = comma list of "<variant>[/<refill>]" (obvhs_cuda_set_option traverse_variant / traverse); all must return
 identical hits. PACKED=1 feeds the 32-byte Ray::new records instead of the 64-byte Ray structs."""
 import os
 import sys
@@ -16,7 +16,7 @@ from obvhs_b200.types import ray_args_of  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "soup"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
 samples = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-variants = os.environ.get("VARIANTS", "0:16,1:8,1:16,1:24,2:16,3:16,4:16,5:16,6:16,7:16,8:16").split(",")
+variants = os.environ.get("VARIANTS", "0,1,2,3,4").split(",")
 tris, rays, desc, preset = bench.make_workload(wl, n)
 ctx0 = api.Context(0)
 d_tris = torch.from_numpy(tris).cuda()

@@ -322,7 +322,7 @@ def test_traversal_hits_bit_exact(api, scenes, scene, mode):
     assert np.array_equal(g.ray_traverse_anyhit_count(srays), c.ray_traverse_anyhit_count(bt, srays))
 
 
-@pytest.mark.parametrize("variant", ["1:1", "1:16", "1:33", "2:16", "3:8", "3:24", "4:16", "5:16", "6:12", "7:16", "8:20"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("scene", ["soup4k", "kitchen"])
 def test_persistent_kernel_variants_bit_exact(api, scenes, scene, variant):
     # the persistent kernel's scheduling policy (which lanes move in a turn), shared-memory short stack and register cap are
