@@ -491,14 +491,14 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
     tree_hash = (bytes_hash_dev(nodes_p, bvh.node_count * 80, e.local_rank) ^ bytes_hash_dev(prims_p, bvh.prim_count * 4, e.local_rank)
                  ^ bytes_hash_dev(tris_p, bvh.prim_count * 64, e.local_rank))
     n_probe = min(1 << 20, n_rays)
-    probe_n = torch.tensor([n_probe], dtype=torch.int64, device=dev)
-    if dist:
-        dist.broadcast(probe_n, src=0)
-    n_probe = int(probe_n.item())
-    probe = d_args[:n_probe].clone() if rank == 0 else torch.empty((n_probe, 8), dtype=torch.float32, device=dev)
-    if dist:
-        dist.broadcast(probe, src=0)
-    with torch.cuda.stream(stream):
+    with torch.cuda.stream(stream):  # (torch's collectives order themselves against the CURRENT stream: keep everything on ours)
+        probe_n = torch.tensor([n_probe], dtype=torch.int64, device=dev)
+        if dist:
+            dist.broadcast(probe_n, src=0)
+        n_probe = int(probe_n.item())
+        probe = d_args[:n_probe].clone() if rank == 0 else torch.empty((n_probe, 8), dtype=torch.float32, device=dev)
+        if dist:
+            dist.broadcast(probe, src=0)
         p_hits = torch.empty((n_probe, 4), dtype=torch.int32, device=dev)
         bvh.ray_traverse(probe, out=p_hits)
     stream.synchronize()
@@ -594,13 +594,15 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
     res = None
     if rank == 0:
         res = {
-            "value": value, "unit": "Mrays/s", "ms_per_step": step_ms, "traverse_ms": trav_ms, "broadcast_ms": bcast_ms,
+            "value": value, "unit": "Mrays/s", "ms_per_step": step_ms, "traverse_ms": trav_ms, "broadcast_ms": bcast_ms if world > 1 else 0.0,
             "rays_total": n_total, "rays_this_gpu": n_rays, "tris": n_tris, "hits_this_gpu": hit_count,
             "build": {"value": n_tris / (build_ms * 1e-3) / 1e6 if build_ms > 0 else None, "unit": "Mtris/s", "ms": build_ms, "cwbvh_nodes": bvh.node_count,
                       "floor_bytes": 48 * n_tris + 4 * n_tris + 80 * bvh.node_count,
                       "frac_of_hbm_at_floor": (48 * n_tris + 4 * n_tris + 80 * bvh.node_count) / (build_ms * 1e-3) / 1e9 / peak if build_ms > 0 else None},
-            "broadcast": {"ms": bcast_ms, "bytes": 80 * bvh.node_count + 68 * bvh.prim_count,
-                          "gbs": (80 * bvh.node_count + 68 * bvh.prim_count) / (bcast_ms * 1e-3) / 1e9 if bcast_ms > 0 else None},
+            "broadcast": ({"ms": bcast_ms, "bytes": 80 * bvh.node_count + 68 * bvh.prim_count,
+                           "gbs": (80 * bvh.node_count + 68 * bvh.prim_count) / (bcast_ms * 1e-3) / 1e9 if bcast_ms > 0 else None,
+                           "how": "obvhs_cuda_cwbvh_broadcast on the building rank's stream: 64-byte header + one grouped NCCL launch (nodes, indices, RtTriangles)"}
+                          if world > 1 else None),
             "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_algorithmic": achieved / peak,
                          "frac_dram": (traffic / (my_trav_ms * 1e-3) / 1e9 / peak) if traffic else None, "traffic": traffic,
                          "kernel": kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": my_trav_ms,
