@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libobvhs_cuda.so")
 SOURCES = ["api.cu", "ploc.cu", "sort.cu", "bvh2.cu", "collapse.cu", "splits.cu", "reinsertion.cu", "cwbvh_build.cu", "traverse.cu", "query.cu", "comm.cu"]
-HEADERS = ["common.cuh", "compact.cuh", "cwbvh_exponent.h", os.path.join("..", "..", "include", "obvhs_cuda.h")]
+HEADERS = ["common.cuh", "compact.cuh", "sort_tile.cuh", "cwbvh_exponent.h", os.path.join("..", "..", "include", "obvhs_cuda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,9 +17,19 @@
 //                           dirty ancestor paths are then refit bottom-up (pending-child counters), which produces the
 //                           same tight boxes as the reference's per-entry refit_from_fast walks.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "sort_tile.cuh"
 
+// A whole ReinsertionOptimizer::run is ONE cooperative launch (reinsertion_run_kernel): every round's candidate keys, candidate
+// sort, find_reinsertion, gain sort, conflict resolution, apply and refit are phases of the same kernel, separated by a
+// barrier over the CTAs that take part in the round. The rounds of a run are a chain of small dependent steps (16 rounds x
+// ~15 barriers): as 80 separate launches they cost ~190 us per round whatever their size (3.7 ms of a 10.9 ms build at 10 M
+// triangles, 1.45 ms of 2.3 ms on the kitchen); as one launch 3.0 ms and 1.2 ms (per-phase times: OBVHS_TRACE=1).
+//   * per-round participation: round r runs on K_r CTAs, sized for its candidate count; a barrier over 50 CTAs is much cheaper
+//     than one over 592, and the later rounds are small (batch ~ 1/(2k-1)). CTAs beyond K_r wait for the round's done flag.
+//   * the conflict-resolution loop finishes in ONE CTA (block barriers) once few entries are undecided.
 namespace cg = cooperative_groups;
 
 namespace {
@@ -31,63 +41,87 @@ __device__ __forceinline__ u32 f32_radix_key(float f) {
     return u ^ mask;
 }
 
-__device__ __forceinline__ float node_half_area(const Node32* __restrict__ nodes, u32 id) {
-    const float4* q = reinterpret_cast<const float4*>(nodes + id);
-    float4 a = __ldg(q), b = __ldg(q + 1);
-    return box_half_area(Box{a.x, a.y, a.z, b.x, b.y, b.z});
+// Node reads of the read-only phases (candidate keys, find_reinsertion): ordinary L1-cached loads. The tree is rewritten by the
+// apply / refit phases of the previous round of the SAME launch, but every phase boundary is a RoundBarrier whose
+// __threadfence() is MEMBAR.SC.GPU + CCTL.IVALL on sm_100a: the SM's L1 is invalidated before the phase starts, exactly what
+// cooperative_groups' grid.sync() relies on. (Reading through L2 only, ld.global.cg, made the branch-and-bound search 4-6x
+// slower: it re-reads the upper levels of the tree constantly. ld.global.nc is not an option: not covered by the fence.)
+template <bool NC>
+__device__ __forceinline__ Node32 find_load_node(const Node32* nodes, u32 id) {
+    if (NC) {
+        const float4* q = reinterpret_cast<const float4*>(nodes + id);
+        float4 a = __ldg(q), b = __ldg(q + 1);
+        Node32 n;
+        n.minx = a.x; n.miny = a.y; n.minz = a.z; n.prim_count = __float_as_uint(a.w);
+        n.maxx = b.x; n.maxy = b.y; n.maxz = b.z; n.first_index = __float_as_uint(b.w);
+        return n;
+    }
+    return load_node(nodes + id);
 }
-__device__ __forceinline__ Node32 ldg_node(const Node32* __restrict__ nodes, u32 id) {
-    const float4* q = reinterpret_cast<const float4*>(nodes + id);
-    float4 a = __ldg(q), b = __ldg(q + 1);
-    Node32 n;
-    n.minx = a.x; n.miny = a.y; n.minz = a.z; n.prim_count = __float_as_uint(a.w);
-    n.maxx = b.x; n.maxy = b.y; n.maxz = b.z; n.first_index = __float_as_uint(b.w);
-    return n;
-}
+__device__ __forceinline__ float node_half_area_cg(const Node32* nodes, u32 id) { return box_half_area(node_box(load_node(nodes + id))); }
 
-// K8: reinsertion.rs:121-139
-__global__ void __launch_bounds__(256) cand_init_kernel(const Node32* __restrict__ nodes, u32 m, u32* __restrict__ keys, u32* __restrict__ vals) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    u32 id = j + 1;
-    keys[j] = f32_radix_key(-node_half_area(nodes, id));
-    vals[j] = id;
-}
+constexpr int RSTACK = 192;  // fast_stack!((f32,u32), (96,192), max_depth*2, ...) reinsertion.rs:287 with max_depth <= 96
 
-constexpr int RSTACK = 192;  // fast_stack!((f32,u32), (96,192), max_depth*2, ...) reinsertion.rs:147 with max_depth <= 96
-
-// K9: reinsertion.rs:233-334. Stack pushes saturate at the last slot and pop_fast saturates at 0 (faststack.rs:299-310).
-__global__ void __launch_bounds__(128) find_reinsertion_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ parents,
-                                                               const u32* __restrict__ cand_ids, u32 count, u32* __restrict__ r_from,
-                                                               u32* __restrict__ r_to, float* __restrict__ r_diff, u32* __restrict__ gain_keys,
-                                                               u32* __restrict__ gain_vals) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const u32 node_id = cand_ids[j];
+// The (f32, u32) stack of find_reinsertion: 192 entries of local memory (StackStack), or -- for max_depth > 96, where the
+// reference switches to HeapStack::new_with_capacity(max_depth * 2) (faststack.rs:44-47) -- a slice of a global arena,
+// interleaved over the threads of the grid so that a warp's accesses at equal depth coalesce. Two types, so that the common
+// case carries no pointers and no run-time choice.
+struct LocalFindStack {
     float s_area[RSTACK];
     u32 s_id[RSTACK];
+    __device__ __forceinline__ u32 cap() const { return RSTACK; }
+    __device__ __forceinline__ void put(u32 i, float a, u32 id) {
+        s_area[i] = a;
+        s_id[i] = id;
+    }
+    __device__ __forceinline__ void get(u32 i, float& a, u32& id) const {
+        a = s_area[i];
+        id = s_id[i];
+    }
+};
+struct HeapFindStack {
+    float* h_area;
+    u32* h_id;
+    u32 stride, capacity;
+    __device__ __forceinline__ u32 cap() const { return capacity; }
+    __device__ __forceinline__ void put(u32 i, float a, u32 id) {
+        h_area[(size_t)i * stride] = a;
+        h_id[(size_t)i * stride] = id;
+    }
+    __device__ __forceinline__ void get(u32 i, float& a, u32& id) const {
+        a = h_area[(size_t)i * stride];
+        id = h_id[(size_t)i * stride];
+    }
+};
+
+// K9: reinsertion.rs:233-334. Stack pushes saturate at the last slot and pop_fast saturates at 0 (faststack.rs:299-310).
+// Nodes are read through L2 (ld.global.cg): they are rewritten by the apply phase of the previous round of the same launch.
+template <bool NC, class Stack>
+__device__ __forceinline__ void find_reinsertion(const Node32* nodes, const u32* parents, u32 node_id, Stack& stk, u32& out_from, u32& out_to,
+                                                 float& out_diff) {
+    const u32 cap1 = stk.cap() - 1u;
     u32 sp = 0;
     u32 best_to = 0;
     float best_diff = 0.0f;
-    const Node32 self = ldg_node(nodes, node_id);
+    const Node32 self = find_load_node<NC>(nodes, node_id);
     const Box aabb = node_box(self);
     const float node_area = box_half_area(aabb);
-    const u32 parent_id = parents[node_id];
-    const float parent_area = node_half_area(nodes, parent_id);
+    const u32 parent_id = NC ? __ldg(parents + node_id) : parents[node_id];
+    const float parent_area = box_half_area(node_box(find_load_node<NC>(nodes, parent_id)));
     float area_diff = parent_area;
     u32 sib = sibling_id(node_id);
-    Box pivot_bbox = node_box(ldg_node(nodes, sib));
+    Box pivot_bbox = node_box(find_load_node<NC>(nodes, sib));
     u32 pivot_id = parent_id;
     for (;;) {
-        s_area[sp] = area_diff;
-        s_id[sp] = sib;
-        sp = min(sp + 1u, (u32)RSTACK - 1u);
+        stk.put(sp, area_diff, sib);
+        sp = min(sp + 1u, cap1);
         while (sp != 0) {
             sp = sp - 1;
-            float top_area_diff = s_area[sp];
-            u32 top_sibling_id = s_id[sp];
+            float top_area_diff;
+            u32 top_sibling_id;
+            stk.get(sp, top_area_diff, top_sibling_id);
             if (top_area_diff - node_area <= best_diff) continue;
-            const Node32 dst = ldg_node(nodes, top_sibling_id);
+            const Node32 dst = find_load_node<NC>(nodes, top_sibling_id);
             const Box dbox = node_box(dst);
             float merged_area = box_half_area(box_union(dbox, aabb));
             float reinsert_area = top_area_diff - merged_area;
@@ -97,21 +131,19 @@ __global__ void __launch_bounds__(128) find_reinsertion_kernel(const Node32* __r
             }
             if (dst.prim_count == 0) {
                 float child_area = reinsert_area + box_half_area(dbox);
-                s_area[sp] = child_area;
-                s_id[sp] = dst.first_index;
-                sp = min(sp + 1u, (u32)RSTACK - 1u);
-                s_area[sp] = child_area;
-                s_id[sp] = dst.first_index + 1;
-                sp = min(sp + 1u, (u32)RSTACK - 1u);
+                stk.put(sp, child_area, dst.first_index);
+                sp = min(sp + 1u, cap1);
+                stk.put(sp, child_area, dst.first_index + 1);
+                sp = min(sp + 1u, cap1);
             }
         }
         if (pivot_id != parent_id) {
-            pivot_bbox = box_union(pivot_bbox, node_box(ldg_node(nodes, sib)));
-            area_diff += node_half_area(nodes, pivot_id) - box_half_area(pivot_bbox);
+            pivot_bbox = box_union(pivot_bbox, node_box(find_load_node<NC>(nodes, sib)));
+            area_diff += box_half_area(node_box(find_load_node<NC>(nodes, pivot_id))) - box_half_area(pivot_bbox);
         }
         if (pivot_id == 0) break;
         sib = sibling_id(pivot_id);
-        pivot_id = parents[pivot_id];
+        pivot_id = NC ? __ldg(parents + pivot_id) : parents[pivot_id];
     }
     u32 from = node_id;
     if (best_to == sibling_id(from) || best_to == parent_id) {  // reinsertion.rs:328-333 -> Reinsertion::default()
@@ -119,11 +151,9 @@ __global__ void __launch_bounds__(128) find_reinsertion_kernel(const Node32* __r
         best_to = 0;
         best_diff = 0.0f;
     }
-    r_from[j] = from;
-    r_to[j] = best_to;
-    r_diff[j] = best_diff;
-    gain_keys[j] = f32_radix_key(-best_diff);  // descending area_diff, ties by candidate rank (stable)
-    gain_vals[j] = j;
+    out_from = from;
+    out_to = best_to;
+    out_diff = best_diff;
 }
 
 struct ReinsertState {
@@ -131,81 +161,213 @@ struct ReinsertState {
     u32 undecided[3];  // entries still undecided after resolution iteration i, in slot i % 3
     u32 applied;       // running total of applied reinsertions
     u32 error;         // 1: resolution iteration counter overflow
-    u32 pad[2];
+    u32 iterations;    // resolution iterations of the whole run (tracing)
+    u32 barriers;      // barriers block 0 went through (tracing)
 };
 
-struct ResolveArgs {
-    const u32* order;      // gain-sorted rank -> candidate rank
-    const u32* r_from;
-    const u32* r_to;
-    const float* r_diff;
-    u32 count;
+// One round of the run. m = number of candidate-sort entries (nodes 1..m), 0 when the candidates are given; count = candidates
+// searched; blocks = CTAs taking part; *_off = this round's zeroed sort scratch (ghist[4*256] then status[4*tiles*256]).
+struct RoundPlan {
+    u32 m, count, blocks, cand_off, gain_off;
+};
+
+struct RunArgs {
+    Node32* nodes;
+    u32* parents;
+    const RoundPlan* plan;
+    u32 n_rounds;
+    const u32* fixed_candidates;  // run_with_candidates: the same ids every round (no candidate sort)
+    u32 *ckeys, *ckeys_alt, *cvals, *cvals_alt;
+    u32 *gkeys, *gkeys_alt, *gvals, *gvals_alt;
+    u32* sort_scratch;
+    u32* round_barrier;  // one counter per round (zeroed), + done flags behind them
+    u32* round_done;
+    u32 *r_from, *r_to;
+    float* r_diff;
     u32* cells;            // 5 per entry
     u32* status;           // 0 undecided, 1 accepted, 2 rejected / inactive
+    u32* und_list[2];      // ranks still undecided, ping-pong between resolution iterations
     ReinsertState* st;
     u32* touched;          // per node, == round_stamp when touched this round
     unsigned long long* reserve;  // per node, min over ((~stamp) << 32 | rank)
     u32* mark;             // per node, == round_stamp when on a dirty path
     u32* pending;          // per node, arrivals still due before the node can be refit
-    Node32* nodes;
-    u32* parents;
-    u32 round_stamp;       // 1-based round index
+    unsigned long long* trace_ns;  // OBVHS_TRACE: globaltimer of block 0 at the end of each phase, 10 per round (or null)
+    float* heap_area;      // find_reinsertion stacks for max_depth > 96 (null: local memory)
+    u32* heap_id;
+    u32 heap_cap;
 };
 
-// K10, one cooperative launch per round: conflict cells -> greedy-MIS resolution by deterministic reservations ->
-// apply -> dirty-path marking -> bottom-up refit. Phases are separated by grid-wide barriers; no host round trips.
-constexpr int RESOLVE_THREADS = 1024;  // few, fat blocks: a grid-wide barrier costs more the more blocks take part
-// SINGLE: the whole round fits one CTA (a few thousand entries): the phases are separated by __syncthreads instead of
-// grid-wide barriers (about 2 us each; a round has ~20 of them, which was the entire 40 us of a kitchen-sized round).
-struct PhaseBarrier {
-    cg::grid_group grid;
-    bool single;
+__device__ __forceinline__ void phase_stamp(const RunArgs& a, u32 round, u32 phase) {
+    if (a.trace_ns && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace_ns[round * 10 + phase] = t;
+    }
+}
+
+// atomicSub(p, 1) with release semantics: the stores before it (a refitted box) are visible to whoever observes the new count.
+// MEMBAR.ALL.GPU + ATOMG; unlike __threadfence() (MEMBAR.SC.GPU + CCTL.IVALL) it leaves the SM's L1 alone.
+__device__ __forceinline__ u32 atomic_dec_release(u32* p) {
+    u32 old;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(0xffffffffu) : "memory");
+    return old;
+}
+
+// Barrier over the first `k` CTAs of the grid on a monotonic counter (one counter per round, zeroed by the host). All CTAs of
+// a cooperative launch are co-resident, so spinning is safe.
+struct RoundBarrier {
+    u32* counter;
+    u32 k, gen;
     __device__ __forceinline__ void sync() {
-        if (single) __syncthreads();
-        else grid.sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            gen++;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            const u32 target = gen * k;
+            while (*reinterpret_cast<volatile u32*>(counter) < target) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
     }
 };
-template <bool SINGLE>
-__global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel(ResolveArgs a) {
-    PhaseBarrier grid{cg::this_grid(), SINGLE};
-    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+
+// Stable LSD radix sort of n (key, value) pairs by the k CTAs of the round; the four digit histograms are already in ghist.
+// Returns (through the references) the buffers that hold the result.
+__device__ __forceinline__ void round_sort(u32*& keys, u32*& keys_alt, u32*& vals, u32*& vals_alt, u32 n, u32* ghist, u32* status, RoundBarrier& bar,
+                                           unsigned char* smem_raw, u32* s_goffs, u32* s_ws) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tiles = (n + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE;
+    for (int p = 0; p < 4; p++) {
+        {  // exclusive scan of this pass's 256 bins (every CTA its own copy)
+            const u32 c = __ldcg(&ghist[p * 256 + tid]);
+            u32 x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_ws[warp] = x;
+            __syncthreads();
+            u32 wbase = 0;
+            for (int k = 0; k < warp; k++) wbase += s_ws[k];
+            s_goffs[tid] = wbase + x - c;
+            __syncthreads();
+        }
+        for (u32 tile = blockIdx.x; tile < tiles; tile += bar.k)
+            onesweep_tile<u32, true, true>(keys, keys_alt, vals, vals_alt, n, 8 * p, s_goffs, status + (size_t)p * tiles * 256, tile, smem_raw);
+        bar.sync();
+        u32* t = keys; keys = keys_alt; keys_alt = t;
+        t = vals; vals = vals_alt; vals_alt = t;
+    }
+}
+
+// Small inputs (a few thousand pairs: every round of a kitchen-sized scene, the late rounds of a large one): stable sort by
+// COUNTING. Every CTA of the round stages all n keys in shared memory and ranks its own slice of them -- rank(i) = #{j : k_j <
+// k_i} + #{j < i : k_j == k_i} -- then scatters straight to the sorted position: one phase, no passes, no histograms. The O(n^2)
+// compares are spread over the round's CTAs (n = 4556 on 18 CTAs: 4.5 k compares per thread).
+constexpr u32 RANK_SORT_MAX = 2048;  // beyond this the four radix passes are cheaper (measured: 4555 keys 46 us by counting, 20 us by radix)
+__device__ __forceinline__ void rank_sort(const u32* keys, const u32* vals, u32* vals_out, u32 n, RoundBarrier& bar, unsigned char* smem_raw) {
+    u32* sk = reinterpret_cast<u32*>(smem_raw);
+    const u32 n4 = (n + 3u) & ~3u;
+    for (u32 j = threadIdx.x; j < n4; j += blockDim.x) sk[j] = j < n ? __ldcg(keys + j) : 0xffffffffu;  // padding ranks behind every key
+    __syncthreads();
+    const u32 nthreads = bar.k * blockDim.x;
+    const uint4* sk4 = reinterpret_cast<const uint4*>(sk);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const u32 ki = sk[i];
+        u32 rank = 0;
+        // keys before i count when <=, keys after i when < (a stable rank); four keys per shared-memory load
+        for (u32 j4 = 0; j4 < n4 / 4; j4++) {
+            const uint4 k = sk4[j4];
+            const u32 j = j4 * 4;
+            rank += (k.x < ki || (k.x == ki && j < i)) ? 1u : 0u;
+            rank += (k.y < ki || (k.y == ki && j + 1 < i)) ? 1u : 0u;
+            rank += (k.z < ki || (k.z == ki && j + 2 < i)) ? 1u : 0u;
+            rank += (k.w < ki || (k.w == ki && j + 3 < i)) ? 1u : 0u;
+        }
+        vals_out[rank] = __ldcg(vals + i);
+    }
+    bar.sync();
+}
+
+// the four 8-bit digit histograms of the keys a CTA produces, accumulated in shared memory and flushed to ghist
+__device__ __forceinline__ void hist_clear(u32* sh) {
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+}
+__device__ __forceinline__ void hist_add(u32* sh, u32 key) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) atomicAdd(&sh[p * 256 + ((key >> (8 * p)) & 0xffu)], 1u);
+}
+__device__ __forceinline__ void hist_flush(u32* sh, u32* ghist) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) {
+        const u32 c = sh[t];
+        if (c) atomicAdd(&ghist[t], c);
+    }
+    __syncthreads();
+}
+
+constexpr int RUN_THREADS = SORT_THREADS;   // 256: the sort tile routine is written for it
+constexpr int RUN_MIN_CTAS = 2;             // two CTAs per SM: barriers over 296 CTAs cost less than the extra search lanes of 592 bring
+constexpr u32 RESOLVE_SINGLE_BELOW = 256;   // undecided entries from which ONE CTA finishes the resolution loop (one entry per thread)
+
+// K10 conflict resolution + apply + refit of one round: the reference applies the gain-sorted list SEQUENTIALLY, skipping
+// entries that touch a node already touched (see the file header of the previous revision / DESIGN.md K10): the accepted set is
+// the greedy maximal independent set in rank order over static cells, computed with deterministic reservations.
+__device__ __forceinline__ void resolve_round(const RunArgs& a, const u32* order, u32 count, u32 round_stamp, RoundBarrier& bar) {
+    const u32 round = round_stamp - 1;
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = bar.k * blockDim.x;
     ReinsertState* st = a.st;
     if (tid == 0) st->undecided[0] = st->undecided[1] = st->undecided[2] = 0;
     // ---- cells of entry r (gain order): {to, from, sibling(from), parent(to), parent(from)} (reinsertion.rs:198-208)
-    for (u32 r = tid; r < a.count; r += nthreads) {
-        u32 j = a.order[r];
-        float d = a.r_diff[j];
+    for (u32 r = tid; r < count; r += nthreads) {
+        u32 j = __ldcg(order + r);
+        float d = __ldcg(a.r_diff + j);
         if (!(d > 0.0f)) {  // reinsertion.rs:178-180
             a.status[r] = 2;
             continue;
         }
-        u32 from = a.r_from[j], to = a.r_to[j];
+        u32 from = __ldcg(a.r_from + j), to = __ldcg(a.r_to + j);
         u32* c = a.cells + (size_t)r * 5;
         c[0] = to;
         c[1] = from;
         c[2] = sibling_id(from);
-        c[3] = a.parents[to];
-        c[4] = a.parents[from];
+        c[3] = __ldcg(a.parents + to);
+        c[4] = __ldcg(a.parents + from);
         a.status[r] = 0;
         atomicMax(&st->active, r + 1);
     }
-    grid.sync();
+    bar.sync();
+    phase_stamp(a, round, 5);
     const u32 active = __ldcg(&st->active);
-    // ---- resolution: the accepted set of the reference's sequential sweep (see the file header)
-    for (u32 iter = 1;; iter++) {
+    // ---- resolution. Every iteration works on the list of ranks still undecided (iteration 1: all active ranks) and appends
+    // the ones it leaves undecided to the other list. Grid-wide while the list is long, then block 0 alone (block barriers only).
+    bool single = active <= RESOLVE_SINGLE_BELOW;
+    u32 iter = 1, n_in = active;
+    for (;; iter++) {
         if (iter > 0xffffu) {
             if (tid == 0) st->error = 1;
             break;
         }
-        const u32 stamp = (a.round_stamp << 16) | iter;  // strictly increasing over the whole run
-        if (tid == 0) st->undecided[(iter + 1) % 3] = 0;  // slot of the NEXT iteration; the previous one may still be read
-        for (u32 r = tid; r < active; r += nthreads) {
+        if (single && blockIdx.x != 0) break;  // block 0 finishes; everybody meets at the barrier below the loop
+        const u32 stride = single ? blockDim.x : nthreads;
+        const u32 first = single ? threadIdx.x : tid;
+        const u32 stamp = (round_stamp << 16) | iter;  // strictly increasing over the whole run
+        const u32* lin = a.und_list[iter & 1];
+        u32* lout = a.und_list[(iter + 1) & 1];
+        if (first == 0) st->undecided[(iter + 1) % 3] = 0;  // slot of the NEXT iteration; the previous one may still be read
+        for (u32 q = first; q < n_in; q += stride) {
+            const u32 r = iter == 1 ? q : __ldcg(lin + q);
             if (__ldcg(&a.status[r]) != 0) continue;
             const u32* c = a.cells + (size_t)r * 5;
-            u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
-            if (__ldcg(&a.touched[c0]) == a.round_stamp || __ldcg(&a.touched[c1]) == a.round_stamp || __ldcg(&a.touched[c2]) == a.round_stamp ||
-                __ldcg(&a.touched[c3]) == a.round_stamp || __ldcg(&a.touched[c4]) == a.round_stamp) {
-                a.status[r] = 2;
+            u32 c0 = __ldcg(c), c1 = __ldcg(c + 1), c2 = __ldcg(c + 2), c3 = __ldcg(c + 3), c4 = __ldcg(c + 4);
+            if (__ldcg(&a.touched[c0]) == round_stamp || __ldcg(&a.touched[c1]) == round_stamp || __ldcg(&a.touched[c2]) == round_stamp ||
+                __ldcg(&a.touched[c3]) == round_stamp || __ldcg(&a.touched[c4]) == round_stamp) {
+                __stcg(&a.status[r], 2u);
                 continue;
             }
             // newer stamps carry a smaller high word, so stale reservations always lose against current ones
@@ -216,35 +378,59 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel
             atomicMin(a.reserve + c3, v);
             atomicMin(a.reserve + c4, v);
         }
-        grid.sync();
-        u32 und = 0;
-        for (u32 r = tid; r < active; r += nthreads) {
-            if (__ldcg(&a.status[r]) != 0) continue;
-            const u32* c = a.cells + (size_t)r * 5;
-            unsigned long long v = ((unsigned long long)(~stamp) << 32) | r;
-            u32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
-            if (__ldcg(a.reserve + c0) == v && __ldcg(a.reserve + c1) == v && __ldcg(a.reserve + c2) == v && __ldcg(a.reserve + c3) == v &&
-                __ldcg(a.reserve + c4) == v) {
-                a.status[r] = 1;
-                a.touched[c0] = a.round_stamp;
-                a.touched[c1] = a.round_stamp;
-                a.touched[c2] = a.round_stamp;
-                a.touched[c3] = a.round_stamp;
-                a.touched[c4] = a.round_stamp;
-            } else {
-                und++;
+        if (single) {
+            __threadfence();
+            __syncthreads();
+        } else bar.sync();
+        for (u32 q0 = first - (first & 31u); q0 < n_in; q0 += stride) {  // warp-uniform trip count: one list reservation per warp
+            const u32 q = q0 + (threadIdx.x & 31u);
+            bool und = false;
+            u32 r = 0;
+            if (q < n_in) {
+                r = iter == 1 ? q : __ldcg(lin + q);
+                if (__ldcg(&a.status[r]) == 0) {
+                    const u32* c = a.cells + (size_t)r * 5;
+                    unsigned long long v = ((unsigned long long)(~stamp) << 32) | r;
+                    u32 c0 = __ldcg(c), c1 = __ldcg(c + 1), c2 = __ldcg(c + 2), c3 = __ldcg(c + 3), c4 = __ldcg(c + 4);
+                    if (__ldcg(a.reserve + c0) == v && __ldcg(a.reserve + c1) == v && __ldcg(a.reserve + c2) == v && __ldcg(a.reserve + c3) == v &&
+                        __ldcg(a.reserve + c4) == v) {
+                        __stcg(&a.status[r], 1u);
+                        __stcg(&a.touched[c0], round_stamp);
+                        __stcg(&a.touched[c1], round_stamp);
+                        __stcg(&a.touched[c2], round_stamp);
+                        __stcg(&a.touched[c3], round_stamp);
+                        __stcg(&a.touched[c4], round_stamp);
+                    } else {
+                        und = true;
+                    }
+                }
+            }
+            const u32 bal = __ballot_sync(0xffffffffu, und);
+            if (bal) {
+                u32 base = 0;
+                if ((threadIdx.x & 31u) == 0) base = atomicAdd(&st->undecided[iter % 3], (u32)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (und) lout[base + __popc(bal & ((1u << (threadIdx.x & 31u)) - 1u))] = r;
             }
         }
-        if (und) atomicAdd(&st->undecided[iter % 3], und);
-        grid.sync();
-        if (__ldcg(&st->undecided[iter % 3]) == 0) break;
+        if (single) {
+            __threadfence();
+            __syncthreads();
+        } else bar.sync();
+        const u32 left = __ldcg(&st->undecided[iter % 3]);
+        if (left == 0) break;
+        n_in = left;
+        if (!single && left <= RESOLVE_SINGLE_BELOW) single = true;  // (every CTA reads the same count: a uniform decision)
     }
+    if (tid == 0) atomicAdd(&st->iterations, iter);
+    bar.sync();
+    phase_stamp(a, round, 6);
     // ---- apply: reinsert_node without its two refits (reinsertion.rs:336-382); accepted entries are disjoint
     u32 applied = 0;
     for (u32 r = tid; r < active; r += nthreads) {
         if (__ldcg(&a.status[r]) != 1) continue;
         const u32* c = a.cells + (size_t)r * 5;
-        u32 to = c[0], from = c[1], sib = c[2], parent_id = c[4];
+        u32 to = __ldcg(c), from = __ldcg(c + 1), sib = __ldcg(c + 2), parent_id = __ldcg(c + 4);
         Node32 sibling_node = load_node_cg(a.nodes + sib);
         Node32 dst_node = load_node_cg(a.nodes + to);
         Node32 new_to = dst_node;
@@ -266,136 +452,288 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) reinsert_resolve_apply_kernel
         applied++;
     }
     if (applied) atomicAdd(&st->applied, applied);
-    grid.sync();
+    bar.sync();
+    phase_stamp(a, round, 7);
     // ---- dirty paths: every accepted entry dirties `to` and the old parent of `from`, and all their ancestors.
     // pending[x] = arrivals node x waits for: one per dirty child plus one self token when x is a start node.
+    // (Both walks below are chains of dependent L2 round trips, one tree level after the other: the next level's parent index is
+    // requested together with the current level's atomic, and the refit carries the box it just computed upwards.)
     for (u32 r = tid; r < active; r += nthreads) {
         if (__ldcg(&a.status[r]) != 1) continue;
         const u32* c = a.cells + (size_t)r * 5;
-        u32 starts[2] = {c[0], c[4]};
+        u32 starts[2] = {__ldcg(c), __ldcg(c + 4)};
         for (int k = 0; k < 2; k++) {
             u32 node = starts[k];
             atomicAdd(&a.pending[node], 1u);  // self token, released by this entry in the refit phase
-            if (atomicExch(&a.mark[node], a.round_stamp) == a.round_stamp) continue;
+            u32 p = node != 0 ? __ldcg(&a.parents[node]) : 0u;
+            if (atomicExch(&a.mark[node], round_stamp) == round_stamp) continue;
             while (node != 0) {
-                u32 p = __ldcg(&a.parents[node]);
                 atomicAdd(&a.pending[p], 1u);
-                if (atomicExch(&a.mark[p], a.round_stamp) == a.round_stamp) break;
+                const u32 pp = p != 0 ? __ldcg(&a.parents[p]) : 0u;
+                if (atomicExch(&a.mark[p], round_stamp) == round_stamp) break;
+                node = p;
+                p = pp;
+            }
+        }
+    }
+    bar.sync();
+    phase_stamp(a, round, 8);
+    // ---- refit: whoever brings pending[x] to zero refits x (first.union(second)) and carries on to its parent. Above the
+    // start node the children of x are the node we come from (its box is in registers) and its sibling, and x's first_index is
+    // the left one of the two (bvh2/node.rs:154-180), so a level costs: atomic, sibling load, store + fence.
+    for (u32 r = tid; r < active; r += nthreads) {
+        if (__ldcg(&a.status[r]) != 1) continue;
+        const u32* c = a.cells + (size_t)r * 5;
+        u32 starts[2] = {__ldcg(c), __ldcg(c + 4)};
+        for (int k = 0; k < 2; k++) {
+            u32 node = starts[k];
+            if (atomicSub(&a.pending[node], 1u) != 1u) continue;  // somebody below is still due
+            const Node32 me = load_node_cg(a.nodes + node);
+            u32 par = node != 0 ? __ldcg(&a.parents[node]) : 0u;
+            Box cur = node_box(me);
+            if (me.prim_count == 0) {
+                const Node32 c0 = load_node_cg(a.nodes + me.first_index), c1 = load_node_cg(a.nodes + me.first_index + 1);
+                cur = box_union(node_box(c0), node_box(c1));
+                store_node(a.nodes + node, make_node32(cur, 0u, me.first_index));
+            }
+            while (node != 0) {
+                const u32 p = par;
+                if (atomic_dec_release(&a.pending[p]) != 1u) break;
+                const Node32 sn = load_node_cg(a.nodes + sibling_id(node));
+                par = p != 0 ? __ldcg(&a.parents[p]) : 0u;
+                const bool node_is_left = (node & 1u) != 0;
+                cur = node_is_left ? box_union(cur, node_box(sn)) : box_union(node_box(sn), cur);
+                store_node(a.nodes + p, make_node32(cur, 0u, left_sibling_id(node)));
                 node = p;
             }
         }
     }
-    grid.sync();
-    // ---- refit: whoever brings pending[x] to zero refits x (first.union(second)) and carries on to its parent
-    for (u32 r = tid; r < active; r += nthreads) {
-        if (__ldcg(&a.status[r]) != 1) continue;
-        const u32* c = a.cells + (size_t)r * 5;
-        u32 starts[2] = {c[0], c[4]};
-        for (int k = 0; k < 2; k++) {
-            u32 node = starts[k];
-            for (;;) {
-                if (atomicSub(&a.pending[node], 1u) != 1u) break;  // somebody below is still due
-                Node32 me = load_node_cg(a.nodes + node);
-                if (me.prim_count == 0) {
-                    Node32 c0 = load_node_cg(a.nodes + me.first_index), c1 = load_node_cg(a.nodes + me.first_index + 1);
-                    store_node(a.nodes + node, make_node32(box_union(node_box(c0), node_box(c1)), 0u, me.first_index));
+    if (tid == 0) st->active = 0;  // the next round starts from zero (nobody reads `active` after the last barrier)
+}
+
+template <int MIN_CTAS, bool NC>
+__global__ void __launch_bounds__(RUN_THREADS, MIN_CTAS) reinsertion_run_kernel(RunArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_goffs[256];
+    __shared__ u32 s_ws[SORT_WARPS];
+    u32* s_hist = reinterpret_cast<u32*>(smem_raw);  // 4 x 256 counters; the sort tiles reuse the same bytes afterwards
+    for (u32 round = 0; round < a.n_rounds; round++) {
+        const RoundPlan pl = a.plan[round];
+        if (round > 0) {  // the tree of the previous round must be complete (its participants may have been other CTAs)
+            if (threadIdx.x == 0) {
+                while (*reinterpret_cast<volatile u32*>(a.round_done + round - 1) == 0) {
                 }
-                if (node == 0) break;
                 __threadfence();
-                node = __ldcg(&a.parents[node]);
             }
+            __syncthreads();
+        }
+        if (pl.count == 0 || pl.blocks == 0) {  // an empty round (the host does not plan any; kept for safety)
+            if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile u32*>(a.round_done + round) = 1u;
+            continue;
+        }
+        if (blockIdx.x >= pl.blocks) continue;
+        RoundBarrier bar{a.round_barrier + round, pl.blocks, 0};
+        const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = pl.blocks * blockDim.x;
+        const u32 round_stamp = round + 1;
+        const u32* cand_ids = a.fixed_candidates;
+        phase_stamp(a, round, 0);
+        if (!cand_ids) {
+            // ---- K8 candidates (reinsertion.rs:121-139): half areas of nodes [1, m], stable radix sort on the f32 key of -cost
+            u32* ghist = a.sort_scratch + pl.cand_off;
+            hist_clear(s_hist);
+            for (u32 j = tid; j < pl.m; j += nthreads) {
+                const u32 key = f32_radix_key(-node_half_area_cg(a.nodes, j + 1));
+                a.ckeys[j] = key;
+                a.cvals[j] = j + 1;
+                hist_add(s_hist, key);
+            }
+            hist_flush(s_hist, ghist);
+            bar.sync();
+            phase_stamp(a, round, 1);
+            u32 *k0 = a.ckeys, *k1 = a.ckeys_alt, *v0 = a.cvals, *v1 = a.cvals_alt;
+            if (pl.m <= RANK_SORT_MAX) {
+                rank_sort(k0, v0, v1, pl.m, bar, smem_raw);
+                v0 = v1;
+            } else round_sort(k0, k1, v0, v1, pl.m, ghist, ghist + 4 * 256, bar, smem_raw, s_goffs, s_ws);
+            cand_ids = v0;
+        }
+        phase_stamp(a, round, 2);
+        // ---- K9 find_reinsertion for the first `count` candidates; gain keys: descending area_diff, ties by candidate rank
+        u32* ghist = a.sort_scratch + pl.gain_off;
+        hist_clear(s_hist);
+        for (u32 j = tid; j < pl.count; j += nthreads) {
+            u32 from, to;
+            float diff;
+            if (a.heap_area) {
+                HeapFindStack stk{a.heap_area + (size_t)blockIdx.x * blockDim.x + threadIdx.x, a.heap_id + (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+                                  gridDim.x * blockDim.x, a.heap_cap};
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+            } else {
+                LocalFindStack stk;
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+            }
+            a.r_from[j] = from;
+            a.r_to[j] = to;
+            a.r_diff[j] = diff;
+            const u32 key = f32_radix_key(-diff);
+            a.gkeys[j] = key;
+            a.gvals[j] = j;
+            hist_add(s_hist, key);
+        }
+        hist_flush(s_hist, ghist);
+        bar.sync();
+        phase_stamp(a, round, 3);
+        u32 *k0 = a.gkeys, *k1 = a.gkeys_alt, *v0 = a.gvals, *v1 = a.gvals_alt;
+        if (pl.count <= RANK_SORT_MAX) {
+            rank_sort(k0, v0, v1, pl.count, bar, smem_raw);
+            v0 = v1;
+        } else round_sort(k0, k1, v0, v1, pl.count, ghist, ghist + 4 * 256, bar, smem_raw, s_goffs, s_ws);
+        phase_stamp(a, round, 4);
+        resolve_round(a, v0, pl.count, round_stamp, bar);
+        bar.sync();
+        phase_stamp(a, round, 9);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.st->barriers += bar.gen;
+            __threadfence();
+            *reinterpret_cast<volatile u32*>(a.round_done + round) = 1u;
         }
     }
-    if (tid == 0) st->active = 0;  // next round starts from zero (nobody reads `active` after the last barrier)
 }
 
 }  // namespace
 
-// Scratch of one optimisation run + one round of optimize_candidates (reinsertion.rs:141-208): find_reinsertion for the
-// first `count` candidates, stable sort by descending gain, conflict-checked apply (greedy in gain order) + refit.
-struct ReinsertRun {
-    ObvhsContext* ctx;
-    ObvhsBvh2* bvh;
-    DevBuf<u32> r_from, r_to, gkeys, gkeys_alt, gvals, gvals_alt, cells, status, touched, mark, pending;
-    DevBuf<float> r_diff;
-    DevBuf<unsigned long long> reserve;
-    DevBuf<ReinsertState> st;
-    int coop_blocks = 0;
-
-    int init(ObvhsContext* c, ObvhsBvh2* b, size_t max_count) {
-        ctx = c;
-        bvh = b;
-        cudaStream_t s = ctx->stream;
-        const size_t len = bvh->node_count;
-        CU_TRY(ctx, r_from.alloc(max_count, s));
-        CU_TRY(ctx, r_to.alloc(max_count, s));
-        CU_TRY(ctx, r_diff.alloc(max_count, s));
-        CU_TRY(ctx, gkeys.alloc(max_count, s));
-        CU_TRY(ctx, gkeys_alt.alloc(max_count, s));
-        CU_TRY(ctx, gvals.alloc(max_count, s));
-        CU_TRY(ctx, gvals_alt.alloc(max_count, s));
-        CU_TRY(ctx, cells.alloc(max_count * 5, s));
-        CU_TRY(ctx, status.alloc(max_count, s));
-        CU_TRY(ctx, touched.alloc(len, s));
-        CU_TRY(ctx, mark.alloc(len, s));
-        CU_TRY(ctx, pending.alloc(len, s));
-        CU_TRY(ctx, reserve.alloc(len, s));
-        CU_TRY(ctx, st.alloc(1, s));
-        CU_TRY(ctx, cudaMemsetAsync(touched.p, 0, len * 4, s));
-        CU_TRY(ctx, cudaMemsetAsync(mark.p, 0, len * 4, s));
-        CU_TRY(ctx, cudaMemsetAsync(pending.p, 0, len * 4, s));
-        CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
-        CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks, reinsert_resolve_apply_kernel<false>, RESOLVE_THREADS, 0));
-        coop_blocks = std::max(1, coop_blocks) * ctx->sm_count;
-        return OBVHS_OK;
-    }
-
-    int round(const u32* cand_ids, u32 count, u32 round_stamp) {
-        cudaStream_t s = ctx->stream;
-        TraceScope* tsp = new TraceScope(ctx, "  reins_find");
-        find_reinsertion_kernel<<<div_up(count, 128), 128, 0, s>>>(bvh->nodes, bvh->parents, cand_ids, count, r_from.p, r_to.p, r_diff.p,
-                                                                  gkeys.p, gvals.p);
-        KERNEL_CHECK(ctx);
-        delete tsp;
-        TraceScope ts(ctx, "  reins_gain_sort_resolve");
-        u32 *gk, *order;
-        ST_TRY(radix_sort_pairs_u32(ctx, gkeys.p, gkeys_alt.p, gvals.p, gvals_alt.p, count, 4, &gk, &order));
-        ResolveArgs ra;
-        ra.order = order; ra.r_from = r_from.p; ra.r_to = r_to.p; ra.r_diff = r_diff.p; ra.count = count;
-        ra.cells = cells.p; ra.status = status.p; ra.st = st.p; ra.touched = touched.p; ra.reserve = reserve.p;
-        ra.mark = mark.p; ra.pending = pending.p; ra.nodes = bvh->nodes; ra.parents = bvh->parents; ra.round_stamp = round_stamp;
-        void* args[] = {&ra};
-        if (count <= 4 * RESOLVE_THREADS) {  // one CTA, block-level barriers, a plain launch
-            reinsert_resolve_apply_kernel<true><<<1, RESOLVE_THREADS, 0, s>>>(ra);
-        } else {
-            int blocks = std::min(coop_blocks, std::max(1, div_up(count, RESOLVE_THREADS)));
-            CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)reinsert_resolve_apply_kernel<false>, dim3(blocks), dim3(RESOLVE_THREADS), args, 0, s));
-        }
-        KERNEL_CHECK(ctx);
-        return OBVHS_OK;
-    }
-
-    int finish(u64* applied_out) {
-        u32* h = reinterpret_cast<u32*>(ctx->pinned);
-        CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h[5]) {
-            OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
-            return OBVHS_ERR_CUDA;
-        }
-        if (applied_out) *applied_out = h[4];
-        return OBVHS_OK;
-    }
-};
-
 static int reinsertion_prologue(ObvhsContext* ctx, ObvhsBvh2* bvh) {
-    if (bvh->max_depth > 96) {
-        OBVHS_SET_ERR(ctx, "reinsertion: max_depth %zu > 96 needs a heap stack (faststack.rs) -- not supported", bvh->max_depth);
-        return OBVHS_ERR_UNSUPPORTED;
-    }
     if (!bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));  // init_parents_if_uninit
     bvh->children_are_ordered_after_parents = false;                    // reinsertion.rs:93,113
+    return OBVHS_OK;
+}
+
+// rounds: (m, count) per round; candidates given (fixed != nullptr) or selected by area every round
+static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<RoundPlan>& plan, const u32* fixed, u64* applied_out) {
+    cudaStream_t s = ctx->stream;
+    const size_t len = bvh->node_count;
+    size_t max_m = 0, max_count = 0;
+    for (const RoundPlan& p : plan) {
+        max_m = std::max<size_t>(max_m, p.m);
+        max_count = std::max<size_t>(max_count, p.count);
+    }
+    if (max_count == 0) return OBVHS_OK;
+    const size_t smem = onesweep_smem<u32>();
+    void* kernel = (void*)reinsertion_run_kernel<RUN_MIN_CTAS, false>;
+    static PerDevice<int> per_sm_dev;
+    int& per_sm = per_sm_dev[ctx->device];
+    if (per_sm == 0) {
+        CU_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RUN_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    // max_depth > 96: the reference's HeapStack of max_depth * 2 entries per search (faststack.rs:44-47); here a global arena,
+    // with fewer resident CTAs so that it stays small
+    const bool heap = bvh->max_depth > 96;
+    const size_t heap_cap = heap ? bvh->max_depth * 2 : 0;
+    int resident = per_sm * ctx->sm_count;
+    if (heap) resident = std::min(resident, std::max(ctx->sm_count / 2, (int)(((size_t)1 << 30) / (heap_cap * 8 * RUN_THREADS))));
+    if (resident < 1) resident = 1;
+    // CTAs per round: one search per thread where possible, one sort tile per CTA, never more than are resident
+    size_t scratch_words = 0;
+    int grid = 1;
+    for (RoundPlan& p : plan) {
+        if (p.count == 0) continue;
+        const size_t want = std::max<size_t>((p.count + 127) / 128, (std::max<size_t>(p.m, p.count) + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE);
+        p.blocks = (u32)std::max<size_t>(1, std::min<size_t>(want, (size_t)resident));
+        grid = std::max(grid, (int)p.blocks);
+        const size_t tiles_c = (p.m + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE, tiles_g = (p.count + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE;
+        p.cand_off = (u32)scratch_words;
+        scratch_words += p.m ? 4 * 256 + 4 * tiles_c * 256 : 0;
+        p.gain_off = (u32)scratch_words;
+        scratch_words += 4 * 256 + 4 * tiles_g * 256;
+        if (scratch_words >= ((size_t)1 << 31)) {
+            OBVHS_SET_ERR(ctx, "reinsertion: ratio sequence too long for one run (%zu rounds)", plan.size());
+            return OBVHS_ERR_UNSUPPORTED;
+        }
+    }
+    RunArgs a = {};
+    DevBuf<RoundPlan> d_plan;
+    DevBuf<u32> ckeys, ckeys_alt, cvals, cvals_alt, gkeys, gkeys_alt, gvals, gvals_alt, scratch, rbar, r_from, r_to, cells, status, und0, und1, touched, mark, pending, heap_id;
+    DevBuf<float> r_diff, heap_area;
+    DevBuf<unsigned long long> reserve, trace_ns;
+    DevBuf<ReinsertState> st;
+    const size_t n_rounds = plan.size();
+    if (ctx->trace) {
+        CU_TRY(ctx, trace_ns.alloc(n_rounds * 10, s));
+        CU_TRY(ctx, cudaMemsetAsync(trace_ns.p, 0, n_rounds * 80, s));
+    }
+    CU_TRY(ctx, d_plan.alloc(n_rounds, s));
+    if (!fixed) {
+        CU_TRY(ctx, ckeys.alloc(max_m, s));
+        CU_TRY(ctx, ckeys_alt.alloc(max_m, s));
+        CU_TRY(ctx, cvals.alloc(max_m, s));
+        CU_TRY(ctx, cvals_alt.alloc(max_m, s));
+    }
+    CU_TRY(ctx, gkeys.alloc(max_count, s));
+    CU_TRY(ctx, gkeys_alt.alloc(max_count, s));
+    CU_TRY(ctx, gvals.alloc(max_count, s));
+    CU_TRY(ctx, gvals_alt.alloc(max_count, s));
+    CU_TRY(ctx, scratch.alloc(scratch_words, s));
+    CU_TRY(ctx, rbar.alloc(2 * n_rounds, s));
+    CU_TRY(ctx, r_from.alloc(max_count, s));
+    CU_TRY(ctx, r_to.alloc(max_count, s));
+    CU_TRY(ctx, r_diff.alloc(max_count, s));
+    CU_TRY(ctx, cells.alloc(max_count * 5, s));
+    CU_TRY(ctx, status.alloc(max_count, s));
+    CU_TRY(ctx, und0.alloc(max_count, s));
+    CU_TRY(ctx, und1.alloc(max_count, s));
+    CU_TRY(ctx, touched.alloc(len, s));
+    CU_TRY(ctx, mark.alloc(len, s));
+    CU_TRY(ctx, pending.alloc(len, s));
+    CU_TRY(ctx, reserve.alloc(len, s));
+    CU_TRY(ctx, st.alloc(1, s));
+    if (heap) {
+        CU_TRY(ctx, heap_area.alloc(heap_cap * (size_t)grid * RUN_THREADS, s));
+        CU_TRY(ctx, heap_id.alloc(heap_cap * (size_t)grid * RUN_THREADS, s));
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(d_plan.p, plan.data(), n_rounds * sizeof(RoundPlan), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemsetAsync(scratch.p, 0, scratch_words * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(rbar.p, 0, 2 * n_rounds * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(touched.p, 0, len * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(mark.p, 0, len * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(pending.p, 0, len * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(reserve.p, 0xff, len * 8, s));
+    CU_TRY(ctx, cudaMemsetAsync(st.p, 0, sizeof(ReinsertState), s));
+    a.nodes = bvh->nodes; a.parents = bvh->parents; a.plan = d_plan.p; a.n_rounds = (u32)n_rounds; a.fixed_candidates = fixed;
+    a.ckeys = ckeys.p; a.ckeys_alt = ckeys_alt.p; a.cvals = cvals.p; a.cvals_alt = cvals_alt.p;
+    a.gkeys = gkeys.p; a.gkeys_alt = gkeys_alt.p; a.gvals = gvals.p; a.gvals_alt = gvals_alt.p;
+    a.sort_scratch = scratch.p; a.round_barrier = rbar.p; a.round_done = rbar.p + n_rounds;
+    a.r_from = r_from.p; a.r_to = r_to.p; a.r_diff = r_diff.p; a.cells = cells.p; a.status = status.p; a.und_list[0] = und0.p; a.und_list[1] = und1.p; a.st = st.p;
+    a.touched = touched.p; a.reserve = reserve.p; a.mark = mark.p; a.pending = pending.p;
+    a.trace_ns = ctx->trace ? trace_ns.p : nullptr;
+    a.heap_area = heap ? heap_area.p : nullptr; a.heap_id = heap ? heap_id.p : nullptr; a.heap_cap = (u32)heap_cap;
+    void* args[] = {&a};
+    CU_TRY(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(RUN_THREADS), args, smem, s));
+    KERNEL_CHECK(ctx);
+    ReinsertState* h = reinterpret_cast<ReinsertState*>(ctx->pinned);
+    CU_TRY(ctx, cudaMemcpyAsync(h, st.p, sizeof(ReinsertState), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (ctx->trace) {
+        fprintf(stderr, "[obvhs trace]   reinsertion run: %zu rounds, grid %d x %d, %u resolution iterations, %u barriers, %u applied\n", n_rounds, grid,
+                RUN_THREADS, h->iterations, h->barriers, h->applied);
+        std::vector<unsigned long long> t(n_rounds * 10);
+        CU_TRY(ctx, cudaMemcpy(t.data(), trace_ns.p, n_rounds * 80, cudaMemcpyDeviceToHost));
+        static const char* names[9] = {"cand keys", "cand sort", "find", "gain sort", "cells", "resolve", "apply", "dirty", "refit"};
+        for (size_t r = 0; r < n_rounds; r++) {
+            fprintf(stderr, "[obvhs trace]     round %2zu (m %7u, count %7u, %3u CTAs):", r, plan[r].m, plan[r].count, plan[r].blocks);
+            for (int k = 0; k < 9; k++) {
+                const unsigned long long t0 = t[r * 10 + k], t1 = t[r * 10 + k + 1];
+                fprintf(stderr, " %s %.1f", names[k], t1 >= t0 && t0 ? (t1 - t0) * 1e-3 : 0.0);
+            }
+            fprintf(stderr, " us\n");
+        }
+    }
+    if (h->error) {
+        OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
+        return OBVHS_ERR_CUDA;
+    }
+    if (applied_out) *applied_out = h->applied;
     return OBVHS_OK;
 }
 
@@ -409,15 +747,12 @@ int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u
         return OBVHS_ERR_UNSUPPORTED;
     }
     ST_TRY(reinsertion_prologue(ctx, bvh));
-    ReinsertRun run;
-    ST_TRY(run.init(ctx, bvh, n));
-    for (u32 k = 0; k < iterations; k++) ST_TRY(run.round(d_node_ids, (u32)n, k + 1));
-    return run.finish(applied_out);
+    std::vector<RoundPlan> plan(iterations, RoundPlan{0u, (u32)n, 0u, 0u, 0u});
+    return reinsertion_launch(ctx, bvh, plan, d_node_ids, applied_out);
 }
 
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out) {
     if (applied_out) *applied_out = 0;
-    cudaStream_t s = ctx->stream;
     const size_t len = bvh->node_count;
     if (len == 0 || !(ratio > 0.0f)) return OBVHS_OK;  // reinsertion.rs:43-45 (NaN ratio: `<=` is false in Rust; treated as no-op here)
     if (len == 1) return OBVHS_OK;                      // root is a leaf
@@ -433,40 +768,18 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
         return OBVHS_ERR_UNSUPPORTED;
     }
     // reinsertion.rs:104-107 per round sizes
-    std::vector<size_t> node_counts(n_seq);
-    size_t max_nc = 0;
+    std::vector<RoundPlan> plan;
     for (size_t k = 0; k < n_seq; k++) {
         volatile float f0 = (float)len * ratio;
         volatile float f = f0 * seq[k];
         double fd = (double)f;
         size_t batch = !(fd > 0.0) ? 0 : (fd >= 18446744073709551616.0 ? ~(size_t)0 : (size_t)fd);  // `as usize` saturates
         if (batch < 1) batch = 1;
-        size_t nc = batch >= len ? len : std::min(len, batch + 1);
-        node_counts[k] = nc;
-        max_nc = std::max(max_nc, nc);
-    }
-    const size_t max_take = std::min(len, max_nc * 2), max_count = max_nc - 1;
-    if (max_count == 0) return OBVHS_OK;
-    DevBuf<u32> ckeys, ckeys_alt, cvals, cvals_alt;
-    CU_TRY(ctx, ckeys.alloc(max_take, s));
-    CU_TRY(ctx, ckeys_alt.alloc(max_take, s));
-    CU_TRY(ctx, cvals.alloc(max_take, s));
-    CU_TRY(ctx, cvals_alt.alloc(max_take, s));
-    ReinsertRun run;
-    ST_TRY(run.init(ctx, bvh, max_count));
-    for (size_t k = 0; k < n_seq; k++) {
-        const size_t nc = node_counts[k];
+        const size_t nc = batch >= len ? len : std::min(len, batch + 1);
         const u32 take = (u32)std::min(len, nc * 2), count = (u32)(nc - 1);
         if (count == 0 || take < 2) continue;
-        const u32 m = take - 1;
-        u32 *sk, *cand_ids;
-        {
-            TraceScope ts(ctx, "  reins_candidates_sort");
-            cand_init_kernel<<<div_up(m, 256), 256, 0, s>>>(bvh->nodes, m, ckeys.p, cvals.p);
-            KERNEL_CHECK(ctx);
-            ST_TRY(radix_sort_pairs_u32(ctx, ckeys.p, ckeys_alt.p, cvals.p, cvals_alt.p, m, 4, &sk, &cand_ids));
-        }
-        ST_TRY(run.round(cand_ids, count, (u32)k + 1));
+        plan.push_back(RoundPlan{take - 1, count, 0u, 0u, 0u});
     }
-    return run.finish(applied_out);
+    if (plan.empty()) return OBVHS_OK;
+    return reinsertion_launch(ctx, bvh, plan, nullptr, applied_out);
 }
