@@ -6,9 +6,10 @@
 //   K2  morton_kernel         f64 normalise, 21 bits/axis, bit interleave                         ploc/mod.rs:287-288,782-785
 //   K3  onesweep radix sort   (sort.cu), stable: ties by ascending original index                  ploc/mod.rs:811-827
 //   K4  gather_nodes_kernel   nodes into sorted order                                             ploc/mod.rs:829-846
-//   K5  ploc_search_kernel    radius-r nearest neighbour; window staged in smem by a TMA bulk copy ploc/mod.rs:329-419,575-651
-//   K6  ploc_merge_kernel     the reference's SEQUENTIAL merge sweep restated as flags + a decoupled-look-back scan
-//                             (kept/parent outputs, merges) + scatter                             ploc/mod.rs:420-487
+//   K5+K6 ploc_fused_kernel   one pass per iteration: the tile's window of sorted cluster AABBs staged in smem by a TMA bulk
+//                             copy, radius-r nearest neighbour (ploc/mod.rs:329-419,575-651), then the reference's SEQUENTIAL
+//                             merge sweep restated as flags + a decoupled-look-back scan (kept/parent outputs, merges) +
+//                             scatter (ploc/mod.rs:420-487); ploc_mid_kernel / ploc_tail_kernel for the small iterations
 // Node order, child slots (allocated from the END of bvh.nodes in sweep order) and AABB bits equal the sequential
 // reference sweep exactly.
 #include <cooperative_groups.h>
@@ -41,6 +42,10 @@ struct PlocGlobals {
     u32 ticket;
     u32 pad2;
     u32 mid_depth, mid_parity;  // written by ploc_mid_kernel: iterations done so far / parity of the live state
+    // large iterations (ploc_fused_kernel), launched several at a time without a host round trip in between:
+    u32 fused_depth;     // iterations completed so far
+    u32 fused_stop;      // 1: the cluster count reached the hand-over size, the remaining launches do nothing; 2: no progress
+    u32 fused_ticket[2]; // tile tickets, by iteration parity
 };
 
 __global__ void ploc_globals_init_kernel(PlocGlobals* g, u32 n) {
@@ -55,6 +60,9 @@ __global__ void ploc_globals_init_kernel(PlocGlobals* g, u32 n) {
         g->state[1].count = 0;
         g->state[1].insert_index = 0;
         g->ticket = 0;
+        g->fused_depth = 0;
+        g->fused_stop = 0;
+        g->fused_ticket[0] = g->fused_ticket[1] = 0;
     }
 }
 
@@ -210,7 +218,7 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
         : "memory");
 }
 
-constexpr int SEARCH_TILE = 256;
+constexpr int SEARCH_TILE = 256;  // (granularity of the scan-status allocation)
 
 __device__ __forceinline__ Box smem_box(const Node32* w, int j) {
     const float4* q = reinterpret_cast<const float4*>(w + j);
@@ -251,42 +259,6 @@ __device__ __forceinline__ int search_offset(const Node32* win, int li, u32 i, u
     return best;
 }
 
-// K5. One thread per node. The tile's window [tile-R, tile+TILE+R) of sorted cluster AABBs is brought into shared
-// memory by one TMA bulk copy. r1: the reference's r=1 fast path (ploc/mod.rs:329-382): -1 iff cost(i-1,i) < cost(i,i+1),
-// first element +1, last element -1. Otherwise find_best_node (ploc/mod.rs:624-650): scan i-R..i-1 then i+1..i+R with
-// `cost <= best` so the LAST minimum wins; cost(lo,hi) = half_area(union(nodes[lo], nodes[hi])) with the lower index first.
-template <int R>
-__global__ void __launch_bounds__(SEARCH_TILE) ploc_search_kernel(const Node32* __restrict__ cur, const PlocGlobals* __restrict__ g,
-                                                                  int parity, int r1, signed char* __restrict__ merge, u64* scan_status,
-                                                                  u32* ticket) {
-    __shared__ __align__(128) Node32 win[SEARCH_TILE + 2 * R];
-    __shared__ __align__(8) u64 bar;
-    const u32 count = g->state[parity].count;
-    // reset the chained-scan state the merge kernel of this iteration uses
-    if (threadIdx.x == 0) {
-        scan_status[blockIdx.x] = 0;
-        if (blockIdx.x == 0) *ticket = 0;
-    }
-    const u32 tile0 = blockIdx.x * SEARCH_TILE;
-    if (tile0 >= count) return;
-    const u32 lo = tile0 >= (u32)R ? tile0 - R : 0u;
-    const u32 hi = min(count, tile0 + SEARCH_TILE + R);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        u32 bytes = (hi - lo) * (u32)sizeof(Node32);
-        mbar_expect_tx(&bar, bytes);
-        tma_bulk_g2s(win, cur + lo, bytes, &bar);
-    }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-    const u32 i = tile0 + threadIdx.x;
-    if (i >= count) return;
-    const int off = search_offset<R>(win, (int)(i - lo), i, count, r1);
-    merge[i] = (signed char)off;
-}
-
-constexpr int MERGE_THREADS = 256, MERGE_ITEMS = 4, MERGE_TILE = MERGE_THREADS * MERGE_ITEMS;
-constexpr int MERGE_HALO = 32;  // >= largest search distance
 constexpr u64 SCAN_AGG = 1ull << 62, SCAN_INCL = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
 
 // K6. The sequential sweep of ploc/mod.rs:423-487 visits index = 0..count: a node whose choice is not mutual is
@@ -301,39 +273,70 @@ __device__ __forceinline__ u32 child_slot(const u32* __restrict__ free_slots, u3
     return free_slots ? free_slots[(insert_start - insert_base) / 2 + mi] : insert_base - 2 * (mi + 1);
 }
 
-// One tile of the merge sweep. CG: the inputs were written earlier in the SAME launch by other CTAs (ploc_mid_kernel), so
-// they are read through L2 (ld.global.cg) instead of the non-coherent L1.
-template <bool CG>
-__device__ __forceinline__ void ploc_merge_tile(const Node32* cur, Node32* next, Node32* bvh_nodes, const signed char* merge, PlocGlobals* g,
-                                                int parity, u32 count, u32 insert_base, u32 tile, u64* scan_status,
-                                                const u32* __restrict__ free_slots, u32 insert_start) {
-    __shared__ signed char sm[MERGE_TILE + 2 * MERGE_HALO];
-    __shared__ u64 s_wsum[MERGE_THREADS / 32];
-    __shared__ u64 s_excl;
-    const u32 tiles = (count + MERGE_TILE - 1) / MERGE_TILE;
-    const u32 tile0 = tile * MERGE_TILE;
-    for (int j = threadIdx.x; j < MERGE_TILE + 2 * MERGE_HALO; j += MERGE_THREADS) {
-        long long gi = (long long)tile0 - MERGE_HALO + j;
-        sm[j] = (gi >= 0 && gi < (long long)count) ? (CG ? __ldcg(merge + gi) : merge[gi]) : (signed char)0;
+// K5 + K6 of one iteration in ONE pass over the clusters (iterations above PLOC_MID_MAX clusters). A tile of 1024 clusters
+// and a halo of 2R on each side is brought into shared memory by one TMA bulk copy; the CTA computes the neighbour choice of its
+// own clusters AND of the R clusters on each side (what the mutual-pair test of its own clusters needs), then runs the merge
+// sweep -- flags, packed decoupled-look-back scan, scatter -- reading the cluster boxes from shared memory. Against separate
+// search and merge launches this reads every cluster once instead of twice, needs no merge[] array, and halves the launches.
+// All loop state lives on the device (g->state[parity], g->fused_*): the host enqueues several iterations back to back, sized
+// for the last count it knows (CTAs beyond the live tiles exit), and reads the state back once per batch instead of once per
+// iteration. `depth` is the iteration this launch would be; a launch does nothing once g->fused_stop is set.
+constexpr int FUSED_THREADS = 256, FUSED_ITEMS = 4, FUSED_TILE = FUSED_THREADS * FUSED_ITEMS;
+
+// One tile of one fused iteration. TMA: the window arrives by a bulk copy (separate launches: `cur` was written by the previous
+// kernel); otherwise by ld.global.cg (ploc_mid_kernel: `cur` was written by other CTAs of the same launch). `bar_phase`: parity
+// of the mbarrier phase to wait for (a CTA of the mid kernel reuses its barrier tile after tile).
+template <int R, bool TMA>
+__device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next, Node32* __restrict__ bvh_nodes, PlocGlobals* g, int parity, u32 depth,
+                                                u32 count, u32 insert_base, int r1, u32 tile, u64* st, const u32* __restrict__ free_slots,
+                                                u32 insert_start, Node32* win, signed char* sm, u64* bar, u32 bar_phase, u64* s_wsum, u64* s_excl) {
+    const u32 tiles = (count + FUSED_TILE - 1) / FUSED_TILE;
+    const u32 tile0 = tile * FUSED_TILE;
+    const u32 lo = tile0 >= 2u * R ? tile0 - 2u * R : 0u;
+    const u32 hi = min(count, tile0 + FUSED_TILE + 2u * R);
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            const u32 bytes = (hi - lo) * (u32)sizeof(Node32);
+            mbar_expect_tx(bar, bytes);
+            tma_bulk_g2s(win, cur + lo, bytes, bar);
+        }
+        mbar_wait(bar, bar_phase);
+    } else {
+        for (u32 j = threadIdx.x; j < (hi - lo) * 2; j += FUSED_THREADS)
+            reinterpret_cast<float4*>(win)[j] = __ldcg(reinterpret_cast<const float4*>(cur + lo) + j);
+        __syncthreads();
+    }
+    // ---- search: own clusters, then the halo of R on each side. sm[j] <-> cluster tile0 - R + j (0 outside the array)
+    // (striped over the threads: consecutive lanes read consecutive 32-byte boxes; the blocked mapping the scan below uses would
+    // put a warp's 128-bit shared-memory loads on the same banks -- measured 2.5x slower at R = 6)
+#pragma unroll
+    for (int k = 0; k < FUSED_ITEMS; k++) {
+        const u32 j = k * FUSED_THREADS + threadIdx.x, i = tile0 + j;
+        if (i < count) sm[j + R] = (signed char)search_offset<R>(win, (int)(i - lo), i, count, r1);
+    }
+    if (threadIdx.x < 2 * R) {
+        const int j = threadIdx.x < R ? (int)threadIdx.x : FUSED_TILE + (int)threadIdx.x;  // left halo 0..R-1, right halo TILE+R..TILE+2R-1
+        const long long i = (long long)tile0 - R + j;
+        sm[j] = (i >= 0 && i < (long long)count) ? (signed char)search_offset<R>(win, (int)(i - lo), (u32)i, count, r1) : (signed char)0;
     }
     __syncthreads();
-    u32 flags = 0;  // per item: bit0 = writes an output, bit1 = emits a parent
+    // ---- merge sweep (K6 above): flags, packed (outputs, merges) scan, scatter
+    u32 flags = 0;
     u64 local = 0;
 #pragma unroll
-    for (int k = 0; k < MERGE_ITEMS; k++) {
-        u32 i = tile0 + threadIdx.x * MERGE_ITEMS + k;
+    for (int k = 0; k < FUSED_ITEMS; k++) {
+        const u32 i = tile0 + threadIdx.x * FUSED_ITEMS + k;
         if (i < count) {
-            int li = threadIdx.x * MERGE_ITEMS + k + MERGE_HALO;
-            int m = sm[li];
-            int mb = sm[li + m];
-            bool mutual = (m + mb) == 0;
-            bool emits = mutual && m < 0;
-            bool outp = !mutual || emits;
+            const int li = threadIdx.x * FUSED_ITEMS + k + R;
+            const int m = sm[li];
+            const int mb = sm[li + m];
+            const bool mutual = (m + mb) == 0;
+            const bool emits = mutual && m < 0;
+            const bool outp = !mutual || emits;
             flags |= (outp ? 1u : 0u) << (2 * k) | (emits ? 2u : 0u) << (2 * k);
             local += (outp ? 1ull : 0ull) + (emits ? (1ull << 31) : 0ull);
         }
     }
-    // block exclusive scan of the packed pair
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u64 x = local;
 #pragma unroll
@@ -345,33 +348,30 @@ __device__ __forceinline__ void ploc_merge_tile(const Node32* cur, Node32* next,
     __syncthreads();
     u64 wbase = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < MERGE_THREADS / 32; k++) {
-        u64 s = s_wsum[k];
-        if (k < w) wbase += s;
-        total += s;
+    for (int k = 0; k < FUSED_THREADS / 32; k++) {
+        const u64 sv = s_wsum[k];
+        if (k < w) wbase += sv;
+        total += sv;
     }
-    u64 thread_excl = wbase + x - local;
-    // decoupled look-back over tiles by warp 0: 32 predecessors per L2 round trip (a one-thread walk pays the full latency per
-    // predecessor, and the first wave of a 10M-cluster iteration has > 1000 tiles with aggregates only)
-    if (threadIdx.x < 32) {
-        volatile u64* st = scan_status;
+    const u64 thread_excl = wbase + x - local;
+    if (threadIdx.x < 32) {  // decoupled look-back by warp 0, 32 predecessors per L2 round trip
+        volatile u64* vst = st;
         u64 excl = 0;
         if (tile == 0) {
-            if (lane == 0) st[0] = SCAN_INCL | total;
+            if (lane == 0) vst[0] = SCAN_INCL | total;
         } else {
-            if (lane == 0) st[tile] = SCAN_AGG | total;
-            long long t = (long long)tile - 1;  // lane k looks at tile t - k
+            if (lane == 0) vst[tile] = SCAN_AGG | total;
+            long long t = (long long)tile - 1;
             for (;;) {
                 const long long mine = t - lane;
-                u64 sv = 2ull << 62;  // SCAN_INCL | 0: tiles before the first one
-                if (mine >= 0) sv = st[mine];
+                u64 sv = 2ull << 62;
+                if (mine >= 0) sv = vst[mine];
                 const u32 incl = __ballot_sync(0xffffffffu, (sv & SCAN_INCL) != 0);
                 const u32 ready = __ballot_sync(0xffffffffu, (sv & (SCAN_INCL | SCAN_AGG)) != 0);
-                // consume lanes 0..first-1 while they are ready; stop at the first inclusive value (tiles < 0 count as one)
                 const u32 not_ready = ~ready;
                 const int first_gap = not_ready ? __ffs(not_ready) - 1 : 32;
                 const int first_incl = incl ? __ffs(incl) - 1 : 32;
-                const int upto = min(first_gap, first_incl + 1);  // number of lanes whose value is consumed
+                const int upto = min(first_gap, first_incl + 1);
                 u64 v = lane < upto ? (sv & SCAN_MASK) : 0ull;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -379,30 +379,32 @@ __device__ __forceinline__ void ploc_merge_tile(const Node32* cur, Node32* next,
                 if (first_incl < first_gap) break;
                 t -= upto;
             }
-            if (lane == 0) st[tile] = SCAN_INCL | (excl + total);
+            if (lane == 0) vst[tile] = SCAN_INCL | (excl + total);
         }
-        if (lane == 0) s_excl = excl;
+        if (lane == 0) *s_excl = excl;
         if (lane == 0 && tile == tiles - 1) {  // loop state of the next iteration
-            u64 all = excl + total;
-            u32 outs = (u32)(all & 0x7fffffffull), merges = (u32)(all >> 31);
+            const u64 all = excl + total;
+            const u32 outs = (u32)(all & 0x7fffffffull), merges = (u32)(all >> 31);
             g->state[parity ^ 1].count = outs;
             g->state[parity ^ 1].insert_index = insert_base - 2 * merges;
+            g->fused_depth = depth + 1;
+            if (outs >= count || outs == 0) g->fused_stop = 2;  // no progress (non-finite boxes): the host reports it
         }
     }
     __syncthreads();
-    u64 run = s_excl + thread_excl;
+    u64 run = *s_excl + thread_excl;
 #pragma unroll
-    for (int k = 0; k < MERGE_ITEMS; k++) {
-        u32 f = (flags >> (2 * k)) & 3u;
+    for (int k = 0; k < FUSED_ITEMS; k++) {
+        const u32 f = (flags >> (2 * k)) & 3u;
         if (f & 1u) {
-            u32 i = tile0 + threadIdx.x * MERGE_ITEMS + k;
-            u32 pos = (u32)(run & 0x7fffffffull);
-            Node32 left = CG ? load_node_cg(cur + i) : load_node(cur + i);
+            const u32 i = tile0 + threadIdx.x * FUSED_ITEMS + k;
+            const u32 pos = (u32)(run & 0x7fffffffull);
+            const Node32 left = load_node(win + (i - lo));
             if (f & 2u) {
-                u32 mi = (u32)(run >> 31);
-                int m = sm[threadIdx.x * MERGE_ITEMS + k + MERGE_HALO];
-                Node32 right = CG ? load_node_cg(cur + (i + m)) : load_node(cur + (i + m));
-                u32 slot = child_slot(free_slots, insert_start, insert_base, mi);
+                const u32 mi = (u32)(run >> 31);
+                const int m = sm[threadIdx.x * FUSED_ITEMS + k + R];
+                const Node32 right = load_node(win + (i - lo) + m);
+                const u32 slot = child_slot(free_slots, insert_start, insert_base, mi);
                 store_node(bvh_nodes + slot, left);
                 store_node(bvh_nodes + slot + 1, right);
                 store_node(next + pos, make_node32(box_union(node_box(left), node_box(right)), 0u, slot));
@@ -416,59 +418,77 @@ __device__ __forceinline__ void ploc_merge_tile(const Node32* cur, Node32* next,
     __syncthreads();  // the shared arrays are reused by the caller's next tile
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS) ploc_merge_kernel(const Node32* __restrict__ cur, Node32* __restrict__ next,
-                                                                   Node32* __restrict__ bvh_nodes, const signed char* __restrict__ merge,
-                                                                   PlocGlobals* g, int parity, u64* scan_status, u32* ticket,
-                                                                   const u32* __restrict__ free_slots, u32 insert_start) {
+template <int R>
+__global__ void __launch_bounds__(FUSED_THREADS) ploc_fused_kernel(Node32* buf0, Node32* buf1, Node32* __restrict__ bvh_nodes, PlocGlobals* g,
+                                                                   u32 depth, u32 search_depth_threshold, u64* scan_status, u32 status_stride,
+                                                                   const u32* __restrict__ free_slots, u32 insert_start, u32 stop_at) {
+    __shared__ __align__(128) Node32 win[FUSED_TILE + 4 * R];
+    __shared__ signed char sm[FUSED_TILE + 2 * R];
+    __shared__ __align__(8) u64 bar;
+    __shared__ u64 s_wsum[FUSED_THREADS / 32];
+    __shared__ u64 s_excl;
     __shared__ u32 s_tile;
-    const u32 count = g->state[parity].count;
-    const u32 insert_base = g->state[parity].insert_index;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    const int parity = (int)(depth & 1u);
+    // reset the chained-scan state and the ticket of the NEXT iteration (its tiles are a subset of this grid)
+    if (threadIdx.x == 0) {
+        scan_status[(size_t)(parity ^ 1) * status_stride + blockIdx.x] = 0;
+        if (blockIdx.x == 0) g->fused_ticket[parity ^ 1] = 0;
+        mbar_init(&bar, 1);
+    }
+    // one thread reads the loop state for the whole CTA (fused_stop may be set by another CTA of this very launch: every
+    // thread of a CTA must take the same exit)
+    __shared__ u32 s_state[2];
+    if (threadIdx.x == 0) {
+        const u32 stop = *reinterpret_cast<volatile u32*>(&g->fused_stop);
+        const u32 c = g->state[parity].count;
+        u32 t = 0xffffffffu;
+        if (stop == 0) {
+            if (c <= stop_at) g->fused_stop = 1;  // small enough for the cooperative mid kernel: this and every later launch do nothing
+            else t = atomicAdd(&g->fused_ticket[parity], 1u);  // tiles in ticket order: the look-back only waits for running CTAs
+        }
+        s_state[0] = c;
+        s_state[1] = g->state[parity].insert_index;
+        s_tile = t;
+    }
     __syncthreads();
+    const u32 count = s_state[0], insert_base = s_state[1];
     const u32 tile = s_tile;
-    if (tile >= (count + MERGE_TILE - 1) / MERGE_TILE) return;
-    ploc_merge_tile<false>(cur, next, bvh_nodes, merge, g, parity, count, insert_base, tile, scan_status, free_slots, insert_start);
+    if (tile >= (count + FUSED_TILE - 1) / FUSED_TILE) return;
+    const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
+    ploc_fused_tile<R, true>(parity ? buf1 : buf0, parity ? buf0 : buf1, bvh_nodes, g, parity, depth, count, insert_base, r1, tile,
+                             scan_status + (size_t)parity * status_stride, free_slots, insert_start, win, sm, &bar, 0u, s_wsum, &s_excl);
 }
 
 // Iterations between "too small to be worth a launch + a host round trip each" and the single-CTA tail: ONE cooperative
-// launch loops search -> grid barrier -> merge -> grid barrier until at most PLOC_TAIL clusters are left. Tiles are dealt
+// launch loops { fused search + merge tiles -> grid barrier } until at most PLOC_TAIL clusters are left. Tiles are dealt
 // round-robin (tile t to CTA t % gridDim.x), so the merge scan's look-back only ever waits for CTAs that are running.
 // The window is loaded with plain L2 loads (the clusters were written by other CTAs of this launch).
 // g->state[2] receives {count, insert_index} bookkeeping as usual; g->mid_depth / mid_parity report where the loop stopped.
 constexpr int PLOC_TAIL = 2048;  // clusters the single-CTA tail kernel takes over at
-constexpr u32 PLOC_MID_MAX = 262144;
+constexpr u32 PLOC_MID_MAX = 1u << 20;
 template <int R>
-__global__ void __launch_bounds__(SEARCH_TILE) ploc_mid_kernel(Node32* bufA, Node32* bufB, Node32* bvh_nodes, signed char* merge, PlocGlobals* g,
-                                                              int parity, u32 depth, u32 search_depth_threshold, u64* scan_status,
-                                                              const u32* __restrict__ free_slots, u32 insert_start) {
-    static_assert(SEARCH_TILE == MERGE_THREADS, "one block size for both phases");
+__global__ void __launch_bounds__(FUSED_THREADS) ploc_mid_kernel(Node32* bufA, Node32* bufB, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth,
+                                                                u32 search_depth_threshold, u64* scan_status, u32 status_stride,
+                                                                const u32* __restrict__ free_slots, u32 insert_start) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    __shared__ __align__(16) Node32 win[SEARCH_TILE + 2 * R];
+    __shared__ __align__(128) Node32 win[FUSED_TILE + 4 * R];
+    __shared__ signed char sm[FUSED_TILE + 2 * R];
+    __shared__ u64 s_wsum[FUSED_THREADS / 32];
+    __shared__ u64 s_excl;
     Node32 *cur = bufA, *next = bufB;  // the caller passes them in the order of `parity`
     for (;;) {
         const u32 count = __ldcg(&g->state[parity].count);
         const u32 insert_base = __ldcg(&g->state[parity].insert_index);
         if (count <= PLOC_TAIL) break;
         const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
-        // ---- search
-        const u32 stiles = (count + SEARCH_TILE - 1) / SEARCH_TILE;
-        for (u32 tile = blockIdx.x; tile < stiles; tile += gridDim.x) {
-            const u32 tile0 = tile * SEARCH_TILE;
-            const u32 lo = tile0 >= (u32)R ? tile0 - R : 0u;
-            const u32 hi = min(count, tile0 + SEARCH_TILE + R);
-            for (u32 j = threadIdx.x; j < (hi - lo) * 2; j += SEARCH_TILE)
-                reinterpret_cast<float4*>(win)[j] = __ldcg(reinterpret_cast<const float4*>(cur + lo) + j);
-            __syncthreads();
-            const u32 i = tile0 + threadIdx.x;
-            if (i < count) merge[i] = (signed char)search_offset<R>(win, (int)(i - lo), i, count, r1);
-            __syncthreads();
-        }
-        const u32 mtiles = (count + MERGE_TILE - 1) / MERGE_TILE;
-        for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < mtiles; t += gridDim.x * blockDim.x) scan_status[t] = 0;
-        grid.sync();
-        // ---- merge
-        for (u32 tile = blockIdx.x; tile < mtiles; tile += gridDim.x)
-            ploc_merge_tile<true>(cur, next, bvh_nodes, merge, g, parity, count, insert_base, tile, scan_status, free_slots, insert_start);
+        const u32 tiles = (count + FUSED_TILE - 1) / FUSED_TILE;
+        u64* st = scan_status + (size_t)(depth & 1u) * status_stride;
+        u64* st_next = scan_status + (size_t)((depth + 1) & 1u) * status_stride;
+        for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < tiles; t += gridDim.x * blockDim.x) st_next[t] = 0;  // next iteration's scan state
+        // fused search + merge, tiles dealt round-robin (tile t to CTA t % gridDim.x): the look-back only waits for running CTAs
+        for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+            ploc_fused_tile<R, false>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm, nullptr,
+                                      0u, s_wsum, &s_excl);
         grid.sync();
         Node32* tmp = cur;
         cur = next;
@@ -627,25 +647,26 @@ __global__ void iota_kernel(u32* p, u32 n) {
 }
 
 template <int R>
-void launch_search(ObvhsContext* ctx, u32 count, const Node32* cur, const PlocGlobals* g, int parity, int r1, signed char* merge,
-                   u64* scan_status, u32* ticket) {
-    ploc_search_kernel<R><<<div_up(count, SEARCH_TILE), SEARCH_TILE, 0, ctx->stream>>>(cur, g, parity, r1, merge, scan_status, ticket);
+void launch_fused(ObvhsContext* ctx, u32 count, Node32* buf0, Node32* buf1, Node32* bvh_nodes, PlocGlobals* g, u32 depth, u32 thr, u64* scan_status,
+                  u32 status_stride, const u32* free_slots, u32 insert_start, u32 stop_at) {
+    ploc_fused_kernel<R><<<div_up(count, FUSED_TILE), FUSED_THREADS, 0, ctx->stream>>>(buf0, buf1, bvh_nodes, g, depth, thr, scan_status, status_stride,
+                                                                                       free_slots, insert_start, stop_at);
 }
 
 template <int R>
-cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, Node32* bvh_nodes, signed char* merge, PlocGlobals* g, int parity,
-                       u32 depth, u32 thr, u64* scan_status, const u32* free_slots, u32 insert_start) {
+cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, Node32* bvh_nodes, PlocGlobals* g, int parity, u32 depth, u32 thr,
+                       u64* scan_status, u32 status_stride, const u32* free_slots, u32 insert_start) {
     static PerDevice<int> per_sm_dev;
     int& per_sm = per_sm_dev[ctx->device];
     if (per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_mid_kernel<R>, SEARCH_TILE, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_mid_kernel<R>, FUSED_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
     // as few CTAs as the work needs: the cost of a grid-wide barrier grows with the number of participants
-    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, SEARCH_TILE)));
-    void* args[] = {&cur, &next, &bvh_nodes, &merge, &g, &parity, &depth, &thr, &scan_status, &free_slots, &insert_start};
-    return cudaLaunchCooperativeKernel((void*)ploc_mid_kernel<R>, dim3(blocks), dim3(SEARCH_TILE), args, 0, ctx->stream);
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, FUSED_TILE)));
+    void* args[] = {&cur, &next, &bvh_nodes, &g, &parity, &depth, &thr, &scan_status, &status_stride, &free_slots, &insert_start};
+    return cudaLaunchCooperativeKernel((void*)ploc_mid_kernel<R>, dim3(blocks), dim3(FUSED_THREADS), args, 0, ctx->stream);
 }
 
 template <int R>
@@ -753,14 +774,14 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
     } bufA{bufA_p}, bufB{bufB_p};
     DevBuf<u64> keys, keys_alt;
     DevBuf<u32> vals, vals_alt;
-    DevBuf<signed char> merge;
     DevBuf<u64> scan_status;
     CU_TRY(ctx, keys.alloc(n, s));
     CU_TRY(ctx, keys_alt.alloc(n, s));
     CU_TRY(ctx, vals.alloc(n, s));
     CU_TRY(ctx, vals_alt.alloc(n, s));
-    CU_TRY(ctx, merge.alloc(n, s));
-    CU_TRY(ctx, scan_status.alloc(div_up(n, SEARCH_TILE) + 1, s));
+    const u32 status_stride = (u32)div_up(n, SEARCH_TILE) + 1;  // (one region per iteration parity for the fused kernel)
+    CU_TRY(ctx, scan_status.alloc(2 * (size_t)status_stride, s));
+    CU_TRY(ctx, cudaMemsetAsync(scan_status.p, 0, 2 * (size_t)status_stride * sizeof(u64), s));
 
     TraceScope* tsp = new TraceScope(ctx, "  ploc_morton");
     morton_params_kernel<<<1, 32, 0, s>>>(g.p);
@@ -814,12 +835,12 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
             const u32 thr32 = (u32)std::min<size_t>(search_depth_threshold, 0xffffffffu);
             cudaError_t e;
             switch (search_distance) {
-                case 1: e = launch_mid<1>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
-                case 2: e = launch_mid<2>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
-                case 6: e = launch_mid<6>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
-                case 14: e = launch_mid<14>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
-                case 24: e = launch_mid<24>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
-                default: e = launch_mid<32>(ctx, count, cur, next, bvh->nodes, merge.p, g.p, parity, (u32)depth, thr32, scan_status.p, free_slots, insert_start); break;
+                case 1: e = launch_mid<1>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
+                case 2: e = launch_mid<2>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
+                case 6: e = launch_mid<6>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
+                case 14: e = launch_mid<14>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
+                case 24: e = launch_mid<24>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
+                default: e = launch_mid<32>(ctx, count, cur, next, bvh->nodes, g.p, parity, (u32)depth, thr32, scan_status.p, status_stride, free_slots, insert_start); break;
             }
             ctx->launches++;
             CU_TRY(ctx, e);
@@ -842,21 +863,24 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
             count = new_count;
             break;
         }
-        const int r1 = (search_distance == 1 || depth < search_depth_threshold) ? 1 : 0;
-        u32* ticket = &g.p->ticket;
-        switch (search_distance) {
-            case 1: launch_search<1>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
-            case 2: launch_search<2>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
-            case 6: launch_search<6>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
-            case 14: launch_search<14>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
-            case 24: launch_search<24>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
-            default: launch_search<32>(ctx, count, cur, g.p, parity, r1, merge.p, scan_status.p, ticket); break;
+        // large iterations: FUSED_BATCH fused search+merge launches back to back, then ONE read-back of the loop state
+        constexpr int FUSED_BATCH = 4;
+        const u32 thr32 = (u32)std::min<size_t>(search_depth_threshold, 0xffffffffu);
+        Node32 *buf0 = (depth & 1) ? next : cur, *buf1 = (depth & 1) ? cur : next;  // buffer of the even / odd iterations
+        for (int k = 0; k < FUSED_BATCH; k++) {
+            const u32 d = (u32)depth + (u32)k;
+            switch (search_distance) {
+                case 1: launch_fused<1>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+                case 2: launch_fused<2>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+                case 6: launch_fused<6>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+                case 14: launch_fused<14>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+                case 24: launch_fused<24>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+                default: launch_fused<32>(ctx, count, buf0, buf1, bvh->nodes, g.p, d, thr32, scan_status.p, status_stride, free_slots, insert_start, PLOC_MID_MAX); break;
+            }
+            KERNEL_CHECK(ctx);
         }
-        KERNEL_CHECK(ctx);
-        ploc_merge_kernel<<<div_up(count, MERGE_TILE), MERGE_THREADS, 0, s>>>(cur, next, bvh->nodes, merge.p, g.p, parity, scan_status.p,
-                                                                            ticket, free_slots, insert_start);
-        KERNEL_CHECK(ctx);
-        CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[parity ^ 1], sizeof(PlocState), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(h_state, &g.p->state[0], 2 * sizeof(PlocState), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(h_state + 6, &g.p->fused_depth, 8, cudaMemcpyDeviceToHost, s));
         const bool read_nan = !nan_checked;
         if (read_nan) CU_TRY(ctx, cudaMemcpyAsync(h_state + 4, &g.p->nan_flag, 4, cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
@@ -865,14 +889,15 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
             OBVHS_SET_ERR(ctx, "NaN in input AABBs (the reference goes out of bounds here, ploc/mod.rs:451)");
             return OBVHS_ERR_NAN_INPUT;
         }
-        u32 new_count = h_state[0];
-        if (new_count >= count || new_count == 0) {
+        const u32 new_depth = h_state[6], stop = h_state[7];
+        const u32 new_count = h_state[2 * (new_depth & 1u)];
+        if (stop == 2 || new_depth <= depth || new_count >= count || new_count == 0) {
             OBVHS_SET_ERR(ctx, "PLOC made no progress (count %u -> %u); non-finite AABBs?", count, new_count);
             return OBVHS_ERR_NAN_INPUT;
         }
+        if (((new_depth - (u32)depth) & 1u) != 0) std::swap(cur, next);
+        depth = new_depth;
         count = new_count;
-        std::swap(cur, next);
-        depth++;
     }
     {
         // tail: everything that is left (count <= PLOC_TAIL, possibly the whole build) in one single-CTA launch
@@ -924,6 +949,9 @@ __global__ void rebuild_globals_kernel(PlocGlobals* g, const Node32* __restrict_
         g->state[1].count = 0;
         g->state[1].insert_index = 0;
         g->ticket = 0;
+        g->fused_depth = 0;
+        g->fused_stop = 0;
+        g->fused_ticket[0] = g->fused_ticket[1] = 0;
     }
 }
 

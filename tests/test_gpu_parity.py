@@ -707,3 +707,43 @@ def test_dynamic_frames_refit_and_reinsertion(api, scenes, scene):
         assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} frame {frame} reinsertion")
         rc, msg = ob.bvh2_from(got.download()[0], wp, want.max_depth).validate(moved)
         assert rc == 0, msg
+
+
+def graded_boxes(n, g):
+    """n boxes on a line whose spacing grows by the factor (1 + g): PLOC merges about one pair per iteration, so the tree is a
+    chain of depth ~n/2 (300 boxes at 5 %: max_depth 156; 2000 at 0.5 %: ~1000) -- beyond the reference's fixed 96 / 192-entry
+    stacks, where it switches to HeapStack (faststack.rs:44-47)."""
+    c = np.cumprod(np.full(n, 1.0 + g))
+    a = np.zeros((n, 8), np.float32)
+    h = (c * g * 0.25).astype(np.float32)
+    a[:, 0], a[:, 4] = c - h, c + h
+    a[:, 1], a[:, 5], a[:, 2], a[:, 6] = -0.01, 0.01, -0.01, 0.01
+    return a
+
+
+@pytest.mark.parametrize("n,g", [(300, 0.05), (2000, 0.005)])
+def test_deep_trees_reinsertion_and_builders(api, n, g):
+    # max_depth > 96: find_reinsertion runs on a heap stack of 2 * max_depth entries, like the reference; every preset builds
+    aabbs = graded_boxes(n, g)
+    want = ob.ploc_build(aabbs, None, 6, 64, 2)
+    assert want.max_depth > 96
+    got = api.PlocBuilder().build(6, aabbs, None, 64, 2)
+    assert got.max_depth == want.max_depth
+    for ratio in (0.25, 1.0):
+        wa = want.reinsertion_run(ratio)
+        ga = api.ReinsertionOptimizer().run(got, ratio)
+        assert ga == wa
+        gn, _, gpar = got.download(with_parents=True)
+        wn, _, wpar = want.get(with_parents=True)
+        assert_nodes_equal(gn, wn, f"graded {n} boxes, ratio {ratio}")
+        assert np.array_equal(gpar[1:], wpar[1:])
+    # build_cwbvh<T: Boundable> (cwbvh/builder.rs:98-123) for all six presets: (search distance, threshold, ratio, precision)
+    presets = {"fastest_build": (1, 0, 0.0, 64, 1), "very_fast_build": (1, 0, 0.01, 64, 8), "fast_build": (6, 2, 0.02, 64, 8),
+               "medium_build": (14, 3, 0.05, 64, 8), "slow_build": (24, 2, 0.2, 128, 8), "very_slow_build": (14, 1, 1.0, 128, 8)}
+    for preset, (sd, thr, ratio, prec, mp) in presets.items():
+        b = ob.ploc_build(aabbs, None, sd, prec, thr)
+        b.reinsertion_run(ratio)
+        w = b.to_cwbvh(min(max(mp, 1), 3), True).get()
+        c = api.build_cwbvh(aabbs, api.BvhBuildParams.preset(preset)).download()
+        assert c[0].tobytes() == w[0].tobytes(), preset
+        assert np.array_equal(c[1], w[1])
