@@ -80,6 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 HOST_TEST_SRC = os.path.join(_HERE, "..", "tests", "cpp", "host_api.cpp")
 HOST_TEST_BIN = os.path.join(LIB_DIR, "host_api_test.bin")
+HOST_TEST_BIN_STATIC = os.path.join(LIB_DIR, "host_api_test_static.bin")  # linked against libobvhs_cuda.a, as a Rust build.rs links it
 
 
 def build_host_test(force: bool = False) -> str:
@@ -91,6 +92,11 @@ def build_host_test(force: bool = False) -> str:
         return HOST_TEST_BIN
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", HOST_TEST_SRC, "-o", HOST_TEST_BIN, "-L", LIB_DIR, "-lobvhs_cuda",
                            "-Wl,-rpath,$ORIGIN"])
+    # the same program linked STATICALLY against libobvhs_cuda.a + libcudart_static, exactly the link line of
+    # rust/obvhs-cuda-sys/build.rs (static=obvhs_cuda, static=cudart_static, stdc++, dl, rt, pthread)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", HOST_TEST_SRC, "-o", HOST_TEST_BIN_STATIC, os.path.join(LIB_DIR, "libobvhs_cuda.a"),
+                           "-L", cuda_lib, "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
     return HOST_TEST_BIN
 
 

@@ -705,28 +705,26 @@ int obvhs_cuda_build_cwbvh_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tri
         ObvhsBvh2* b;
         ~Guard() { obvhs_cuda_bvh2_free(b); }
     } guard{bvh2};
-    {
-        TraceScope ts(ctx, "reinsertion_optimize");
-        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
-    }
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
     u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 3 ? 3 : params->max_prims_per_leaf);  // builder.rs:74
     ObvhsCwBvh* cw = nullptr;
     {
         TraceScope ts(ctx, "bvh2_to_cwbvh");
         ST_TRY(bvh2_to_cwbvh_device(ctx, bvh2, mp, true, &cw));
     }
+    struct CwGuard {  // every early return below frees the tree
+        ObvhsCwBvh* b;
+        ~CwGuard() { if (b) obvhs_cuda_cwbvh_free(b); }
+    } cw_guard{cw};
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    int rc = cwbvh_permute_tris_device(ctx, cw, d_tris, n);
-    if (rc == OBVHS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = OBVHS_ERR_CUDA;
-    if (rc != OBVHS_OK) {
-        obvhs_cuda_cwbvh_free(cw);
-        return rc;
-    }
+    ST_TRY(cwbvh_permute_tris_device(ctx, cw, d_tris, n));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (core_build_seconds) {
         float ms = 0.f;
         CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         *core_build_seconds += (double)ms * 1e-3;
     }
+    cw_guard.b = nullptr;
     *out = cw;
     return OBVHS_OK;
 }
@@ -1267,17 +1265,11 @@ int obvhs_cuda_build_bvh2_from_tris(ObvhsContext* ctx, const ObvhsTriangle* tris
         ObvhsBvh2* b;
         ~Guard() { if (b) obvhs_cuda_bvh2_free(b); }
     } guard{bvh2};
-    {
-        TraceScope ts(ctx, "reinsertion_optimize");
-        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
-    }
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio, nullptr, 0, nullptr));
     u32 mp = params->max_prims_per_leaf < 1 ? 1 : (params->max_prims_per_leaf > 255 ? 255 : params->max_prims_per_leaf);  // builder.rs:75
     ST_TRY(bvh2_collapse_device(ctx, bvh2, mp, params->collapse_traversal_cost));
-    {
-        TraceScope ts(ctx, "reinsertion_optimize (post collapse)");
-        ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio * params->post_collapse_reinsertion_batch_ratio_multiplier,
-                                      nullptr, 0, nullptr));
-    }
+    ST_TRY(reinsertion_run_device(ctx, bvh2, params->reinsertion_batch_ratio * params->post_collapse_reinsertion_batch_ratio_multiplier, nullptr, 0,
+                                  nullptr));
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ST_TRY(bvh2_permute_tris_device(ctx, bvh2, d_tris, n));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -6,11 +6,13 @@
 //     fminf/fmaxf order -0 < +0 and drop NaNs, so they are NOT used for tree AABBs.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include <atomic>
 #include <mutex>
+#include <optional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -151,7 +153,11 @@ struct ObvhsContext {
     bool trace = false;  // OBVHS_TRACE=1: per-stage wall times on stderr (the reference's scope!/timeit! macros, lib.rs:158-205)
 };
 
-// Stage scope: when tracing, synchronises the stream at exit and prints the elapsed wall time of the stage.
+// Stage scope. Always an NVTX range named like the reference's profiling scope of the same stage (`crate::scope!`: build_ploc,
+// build_ploc_from_leaves, preallocate_builder, sort_nodes -- ploc/mod.rs:56,70,177,265,779; reinsertion_optimize,
+// reinsertion_optimize_candidates -- reinsertion.rs:41,66; calculate_cost, convert_to_cwbvh -- bvh2_to_cwbvh.rs:70,215; collapse;
+// split_aabbs_precise), visible in Nsight Systems / ncu --nvtx; NVTX3 is header-only and a no-op without a tool attached. With
+// OBVHS_TRACE=1 it also synchronises the stream at entry / exit and prints the elapsed wall time of the stage.
 struct TraceScope {
     ObvhsContext* ctx;
     const char* name;
@@ -159,17 +165,23 @@ struct TraceScope {
     u64 l0 = 0;
     static double now();
     TraceScope(ObvhsContext* c, const char* n) : ctx(c), name(n) {
+        const char* label = n;
+        while (*label == ' ') label++;  // (the indentation only structures the OBVHS_TRACE print-out)
+        nvtxRangePushA(label);
         if (ctx->trace) {
             cudaStreamSynchronize(ctx->stream);
             t0 = now();
             l0 = ctx->launches;
         }
     }
+    TraceScope(const TraceScope&) = delete;
+    TraceScope& operator=(const TraceScope&) = delete;
     ~TraceScope() {
         if (ctx->trace) {
             cudaStreamSynchronize(ctx->stream);
             fprintf(stderr, "[obvhs trace] %-28s %9.3f ms  %5llu launches\n", name, (now() - t0) * 1e3, (unsigned long long)(ctx->launches - l0));
         }
+        nvtxRangePop();
     }
 };
 

@@ -763,7 +763,8 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
         ST_TRY(bvh2_compute_parents_into(ctx, bvh, parents_tmp.p));
         parents = parents_tmp.p;
     }
-    TraceScope* tsp = new TraceScope(ctx, "  cwbvh_cost");
+    std::optional<TraceScope> tsp;
+    tsp.emplace(ctx, "  calculate_cost");
     CU_TRY(ctx, P.alloc(n_nodes, s));
     CU_TRY(ctx, arrivals.alloc(n_nodes, s));
     CU_TRY(ctx, dec.alloc(n_nodes, s));
@@ -798,8 +799,8 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     CU_TRY(ctx, cudaMemcpyAsync(h, &dec.p->S[0], 4, cudaMemcpyDeviceToHost, s));  // M = 1 + S(root, 0)
     CU_TRY(ctx, cudaMemcpyAsync(h + 8, root_box.p, 32, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
-    delete tsp;
-    TraceScope ts_emit(ctx, "  cwbvh_emit");
+    tsp.reset();
+    TraceScope ts_emit(ctx, "  convert_to_cwbvh");
     const u32 M = h[0] + 1;
     memcpy(&cw->total_aabb, h + 8, 32);  // bvh2_to_cwbvh.rs:506 total_aabb = bvh2.nodes[0].aabb
     if (M == 0 || M > n_nodes) {

@@ -772,9 +772,12 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
     struct B {
         Node32* p;
     } bufA{bufA_p}, bufB{bufB_p};
+    TraceScope ts_all(ctx, " build_ploc_from_leaves");
     DevBuf<u64> keys, keys_alt;
     DevBuf<u32> vals, vals_alt;
     DevBuf<u64> scan_status;
+    std::optional<TraceScope> ts_alloc;
+    ts_alloc.emplace(ctx, "  preallocate_builder");
     CU_TRY(ctx, keys.alloc(n, s));
     CU_TRY(ctx, keys_alt.alloc(n, s));
     CU_TRY(ctx, vals.alloc(n, s));
@@ -782,8 +785,10 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
     const u32 status_stride = (u32)div_up(n, SEARCH_TILE) + 1;  // (one region per iteration parity for the fused kernel)
     CU_TRY(ctx, scan_status.alloc(2 * (size_t)status_stride, s));
     CU_TRY(ctx, cudaMemsetAsync(scan_status.p, 0, 2 * (size_t)status_stride * sizeof(u64), s));
+    ts_alloc.reset();
 
-    TraceScope* tsp = new TraceScope(ctx, "  ploc_morton");
+    std::optional<TraceScope> tsp;  // (staged scopes: every early return closes the open one)
+    tsp.emplace(ctx, "  ploc_morton");
     morton_params_kernel<<<1, 32, 0, s>>>(g.p);
     KERNEL_CHECK(ctx);
     const bool wide = sort_precision == 128;
@@ -803,8 +808,8 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
         }
         if (probe->total) CU_TRY(ctx, cudaMemcpyAsync(probe->total, g.p->total, sizeof(ObvhsAabb), cudaMemcpyDeviceToDevice, s));
     }
-    delete tsp;
-    tsp = new TraceScope(ctx, "  ploc_sort_gather");
+    tsp.reset();
+    tsp.emplace(ctx, "  sort_nodes");
     u64* skeys;
     u32* order;
     ST_TRY(radix_sort_pairs_u64(ctx, keys.p, keys_alt.p, vals.p, vals_alt.p, n, 8, &skeys, &order));
@@ -821,7 +826,7 @@ static int ploc_from_leaves(ObvhsContext* ctx, ObvhsBvh2* bvh, PlocGlobals* gp, 
     gather_nodes_kernel<<<div_up(2 * n, 256), 256, 0, s>>>(bufA.p, order, un, bufB.p);
     KERNEL_CHECK(ctx);
 
-    delete tsp;
+    tsp.reset();
     TraceScope ts_iter(ctx, "  ploc_iterations");
     Node32 *cur = bufB.p, *next = bufA.p;
     u32* h_state = reinterpret_cast<u32*>(ctx->pinned);

@@ -181,6 +181,15 @@ struct StoreOffset {
     __device__ void operator()(u32 i, u32 exclusive, u32) const { offsets[i] = exclusive; }
 };
 
+// 64-bit total of the per-query counts: the offsets are a u32 prefix scan, which silently wraps from 2^32 reports on
+__global__ void __launch_bounds__(256) sum_counts_u64_kernel(const u32* __restrict__ counts, u32 n, unsigned long long* total) {
+    unsigned long long v = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += counts[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
+}
+
 template <int TREE, int QUERY>
 int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_group, u32 oct_inv4, const float4* d_queries, size_t n, u32* counts,
               u32* ids, size_t capacity, size_t* total_out) {
@@ -193,6 +202,9 @@ int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_gro
     }
     const u32 un = (u32)n;
     DevBuf<u32> d_counts, d_offsets, tiles, d_total, d_ids;
+    DevBuf<unsigned long long> d_total64;
+    CU_TRY(ctx, d_total64.alloc(1, s));
+    CU_TRY(ctx, cudaMemsetAsync(d_total64.p, 0, 8, s));
     CU_TRY(ctx, d_counts.alloc(n, s));
     CU_TRY(ctx, d_offsets.alloc(n, s));
     CU_TRY(ctx, tiles.alloc((size_t)div_up(n, CP_TILE) + 1, s));
@@ -200,10 +212,20 @@ int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_gro
     query_kernel<TREE, QUERY, false><<<div_up(n, 128), 128, 0, s>>>(nodes, node_count, root_group, oct_inv4, d_queries, un, d_counts.p, nullptr, nullptr);
     KERNEL_CHECK(ctx);
     ST_TRY(scan_values(ctx, CountOf{d_counts.p}, StoreOffset{d_offsets.p}, un, tiles.p, d_total.p));
+    sum_counts_u64_kernel<<<std::min(div_up(n, 256), ctx->sm_count * 8), 256, 0, s>>>(d_counts.p, un, d_total64.p);
+    KERNEL_CHECK(ctx);
     u32* h = reinterpret_cast<u32*>(ctx->pinned);
     CU_TRY(ctx, cudaMemcpyAsync(h, d_total.p, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h + 2, d_total64.p, 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
-    const size_t total = h[0];  // (a u32 sum: more than 2^32 reports in one batch is not supported)
+    unsigned long long total64 = 0;
+    memcpy(&total64, h + 2, 8);
+    if (total64 >= (1ull << 32)) {  // the u32 offsets would have wrapped: refuse instead of writing ids at wrapped positions
+        if (total_out) *total_out = (size_t)total64;
+        OBVHS_SET_ERR(ctx, "query batch reports %llu ids: 2^32 or more per batch is not supported (split the batch)", total64);
+        return OBVHS_ERR_UNSUPPORTED;
+    }
+    const size_t total = h[0];
     if (total_out) *total_out = total;
     ST_TRY(copy_out(ctx, counts, (const u32*)d_counts.p, n));
     if (!ids) return OBVHS_OK;

@@ -746,6 +746,7 @@ int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u
         OBVHS_SET_ERR(ctx, "reinsertion: too many iterations (%u)", iterations);
         return OBVHS_ERR_UNSUPPORTED;
     }
+    TraceScope ts(ctx, "reinsertion_optimize_candidates");
     ST_TRY(reinsertion_prologue(ctx, bvh));
     std::vector<RoundPlan> plan(iterations, RoundPlan{0u, (u32)n, 0u, 0u, 0u});
     return reinsertion_launch(ctx, bvh, plan, d_node_ids, applied_out);
@@ -756,6 +757,7 @@ int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const
     const size_t len = bvh->node_count;
     if (len == 0 || !(ratio > 0.0f)) return OBVHS_OK;  // reinsertion.rs:43-45 (NaN ratio: `<=` is false in Rust; treated as no-op here)
     if (len == 1) return OBVHS_OK;                      // root is a leaf
+    TraceScope ts(ctx, "reinsertion_optimize");
     ST_TRY(reinsertion_prologue(ctx, bvh));
     std::vector<float> default_seq;
     if (!seq) {

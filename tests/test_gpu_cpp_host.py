@@ -12,6 +12,10 @@ from obvhs_b200 import build as b
 def test_cpp_host_side_compiles_and_links():
     path = b.build_host_test()
     assert os.path.exists(path) and os.access(path, os.X_OK)
+    # and statically, against libobvhs_cuda.a + libcudart_static: the link line of rust/obvhs-cuda-sys/build.rs
+    assert os.path.exists(b.HOST_TEST_BIN_STATIC) and os.access(b.HOST_TEST_BIN_STATIC, os.X_OK)
+    ldd = subprocess.run(["ldd", b.HOST_TEST_BIN_STATIC], capture_output=True, text=True).stdout
+    assert "libobvhs_cuda" not in ldd and "libcudart" not in ldd
 
 
 def test_cpp_host_side_has_no_cpu_fallback():
@@ -25,9 +29,13 @@ def test_cpp_host_side_has_no_cpu_fallback():
 
 
 @pytest.mark.gpu
-def test_cpp_host_program_on_gpu():
-    # the binary built by __graft_entry__.build() travels with the snapshot; only a missing one is built here
-    path = b.HOST_TEST_BIN if os.path.exists(b.HOST_TEST_BIN) else b.build_host_test()
-    p = subprocess.run([path], capture_output=True, text=True, timeout=300)
+@pytest.mark.parametrize("linkage", ["shared", "static"])
+def test_cpp_host_program_on_gpu(linkage):
+    # the binaries built by __graft_entry__.build() travel with the snapshot; only missing ones are built here.
+    # static: the same program linked against libobvhs_cuda.a + libcudart_static, as a Rust build.rs links the library
+    want = b.HOST_TEST_BIN if linkage == "shared" else b.HOST_TEST_BIN_STATIC
+    if not os.path.exists(want):
+        b.build_host_test(force=True)
+    p = subprocess.run([want], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, (p.returncode, p.stdout[-3000:], p.stderr[-2000:])
     assert "-> ok" in p.stdout
