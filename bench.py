@@ -46,7 +46,7 @@ def make_workload(name: str, n_tris: int, seed: int = 0):
         return tris, rays, "kitchen.obj 56939 tris, fast_build, 1920x1080 primary rays (examples/obj_cwbvh.rs camera)", "fast_build"
     if name == "terrain":
         res = int(round((n_tris / 2) ** 0.5))
-        tris = tu.demoscene(res, 0)
+        tris = cached_demoscene(res)
         cam = camera.demoscene_camera(1920)
         rays = camera.demoscene_primary(cam, 0)
         return tris, rays, f"demoscene({res},0) {tris.shape[0]} tris, fast_build, {cam.width}x{cam.height} jittered primary rays", "fast_build"
@@ -67,7 +67,7 @@ def make_workload(name: str, n_tris: int, seed: int = 0):
         # the timed set is the cosine-hemisphere bounce ray leaving every primary hit (examples/demoscene.rs:126-178).
         # rays=None: they are generated after the build, by tracing the primary rays with the implementation under test.
         res = int(round((n_tris / 2) ** 0.5))
-        tris = tu.demoscene(res, 0)
+        tris = cached_demoscene(res)
         return tris, None, f"demoscene({res},0) {tris.shape[0]} tris, fast_build, diffuse bounce rays of 1280x475 px", "fast_build"
     raise SystemExit(f"unknown workload {name}")
 

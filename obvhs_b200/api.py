@@ -134,9 +134,11 @@ SIGNATURES = {
 
 
 def load_library(path: str = LIB_PATH):
-    """dlopen the C-ABI library and bind every declared symbol. Raises if it is missing: there is no fallback."""
+    """dlopen the C-ABI library and bind every declared symbol. Raises if it is missing: there is no fallback.
+    OBVHS_LIB_PATH selects another build of the same library (tuning variants, obvhs_b200/build.py: build_variant)."""
     global _lib
     if _lib is None:
+        path = os.environ.get("OBVHS_LIB_PATH", path)
         if not os.path.exists(path):
             raise ObvhsError(-2, f"{path} not built (run `python -m obvhs_b200.build`); there is no CPU fallback")
         lib = C.CDLL(path)

@@ -43,6 +43,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Tuning only: the library compiled with extra -D flags into obvhs_b200/lib_variants/<name>/libobvhs_cuda.so (git-ignored;
+    travels to the GPU box). Select it with OBVHS_LIB_PATH (read by api.load_library)."""
+    out_dir = os.path.join(_HERE, "lib_variants", name)
+    obj_dir = os.path.join(out_dir, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed")
+    lib = os.path.join(out_dir, "libobvhs_cuda.so")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", lib, *objs, "-Xlinker",
+                           "--exclude-libs,ALL", "-ldl"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH

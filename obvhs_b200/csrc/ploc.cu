@@ -354,30 +354,43 @@ __device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next,
         total += sv;
     }
     const u64 thread_excl = wbase + x - local;
-    if (threadIdx.x < 32) {  // decoupled look-back by warp 0, 32 predecessors per L2 round trip
+    if (threadIdx.x < 32) {
+        // Decoupled look-back by warp 0. Every iteration is a cold start (all tiles begin together, only tile 0 holds an
+        // inclusive value), so the chain of inclusive values advances one look-back window per L2 round trip: the window is
+        // 4 x 32 predecessors, all requested before any is consumed (32 per trip cost a 1024-tile iteration ~22 us).
         volatile u64* vst = st;
         u64 excl = 0;
         if (tile == 0) {
             if (lane == 0) vst[0] = SCAN_INCL | total;
         } else {
             if (lane == 0) vst[tile] = SCAN_AGG | total;
-            long long t = (long long)tile - 1;
-            for (;;) {
-                const long long mine = t - lane;
-                u64 sv = 2ull << 62;
-                if (mine >= 0) sv = vst[mine];
-                const u32 incl = __ballot_sync(0xffffffffu, (sv & SCAN_INCL) != 0);
-                const u32 ready = __ballot_sync(0xffffffffu, (sv & (SCAN_INCL | SCAN_AGG)) != 0);
-                const u32 not_ready = ~ready;
-                const int first_gap = not_ready ? __ffs(not_ready) - 1 : 32;
-                const int first_incl = incl ? __ffs(incl) - 1 : 32;
-                const int upto = min(first_gap, first_incl + 1);
-                u64 v = lane < upto ? (sv & SCAN_MASK) : 0ull;
+            long long t = (long long)tile - 1;  // lane k of sub-window j looks at tile t - 32 j - k
+            bool done = false;
+            while (!done) {
+                u64 sv[4];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                if (first_incl < first_gap) break;
-                t -= upto;
+                for (int j = 0; j < 4; j++) {
+                    const long long mine = t - 32 * j - lane;
+                    sv[j] = mine >= 0 ? vst[mine] : (2ull << 62);  // SCAN_INCL | 0: tiles before the first one
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (done) break;
+                    const u32 incl = __ballot_sync(0xffffffffu, (sv[j] & SCAN_INCL) != 0);
+                    const u32 ready = __ballot_sync(0xffffffffu, (sv[j] & (SCAN_INCL | SCAN_AGG)) != 0);
+                    // consume lanes 0..first-1 while they are ready; stop at the first inclusive value
+                    const u32 not_ready = ~ready;
+                    const int first_gap = not_ready ? __ffs(not_ready) - 1 : 32;
+                    const int first_incl = incl ? __ffs(incl) - 1 : 32;
+                    const int upto = min(first_gap, first_incl + 1);  // number of lanes whose value is consumed
+                    u64 v = lane < upto ? (sv[j] & SCAN_MASK) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    excl += v;
+                    t -= upto;
+                    if (first_incl < first_gap) done = true;
+                    else if (upto < 32) break;  // a gap: re-read from there
+                }
             }
             if (lane == 0) vst[tile] = SCAN_INCL | (excl + total);
         }

@@ -10,11 +10,19 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 // pairs per thread / per tile: the 10M-key Morton sort (u64 keys) streams best with 4096-pair tiles at 3 CTAs per SM; the
 // reinsertion sorts (u32 keys, at most a few hundred thousand pairs) want more, smaller tiles to fill the 148 SMs
+// (tuning hooks: obvhs_b200/build.py build_variant compiles the library with other values. Measured on the 10 M-key Morton sort,
+// 8 passes: 16 items x 3 CTAs 900 us, 12 x 4 1150, 8 x 4 1378, 8 x 5 1642, 20 x 2 888 -- larger tiles win, the 20 x 2 gain is noise-level)
+#ifndef OBVHS_SORT_ITEMS64
+#define OBVHS_SORT_ITEMS64 16
+#endif
+#ifndef OBVHS_SORT_CTAS64
+#define OBVHS_SORT_CTAS64 3
+#endif
 template <typename K>
 struct SortCfg {
-    static constexpr int ITEMS = sizeof(K) == 8 ? 16 : 8;
+    static constexpr int ITEMS = sizeof(K) == 8 ? OBVHS_SORT_ITEMS64 : 8;
     static constexpr int TILE = SORT_THREADS * ITEMS;
-    static constexpr int MIN_CTAS = sizeof(K) == 8 ? 3 : 4;
+    static constexpr int MIN_CTAS = sizeof(K) == 8 ? OBVHS_SORT_CTAS64 : 4;
 };
 constexpr u32 FLAG_AGG = 1u << 30, FLAG_INCL = 2u << 30, STATUS_MASK = (1u << 30) - 1;
 
@@ -111,7 +119,8 @@ __device__ __forceinline__ void onesweep_tile(const K* kin, K* kout, const u32* 
         st_status(st, FLAG_AGG | agg);
         // Windowed look-back: LOOKBACK predecessor words are requested at once (independent L2 round trips in flight) and
         // then consumed in order. A one-word-at-a-time walk made the first wave of CTAs (hundreds of tiles that only have
-        // aggregates yet) pay one full L2 latency per predecessor: 160 of the 164 us of a 10M-key pass.
+        // aggregates yet) pay one full L2 latency per predecessor: 160 of the 164 us of a 10M-key pass. (A window of 32 after the
+        // local scatter, when the key registers are free, measured slower: 966 vs 900 us for the eight passes.)
         constexpr int LOOKBACK = 8;
         long long t = (long long)tile - 1;
         bool done = false;
