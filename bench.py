@@ -461,8 +461,10 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
     sums = [0.0, 0.0, 0.0, 0.0]
     wall0 = time.perf_counter()
     for _ in range(args.steps):
+        torch.cuda.nvtx.range_push("obvhs_timed_step")  # (ncu --nvtx --nvtx-include "obvhs_timed_step/" lists exactly one step's launches)
         for k, v in enumerate(one_step()):
             sums[k] += v
+        torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -649,7 +651,7 @@ def run_headline(args):
         d_args, aa_samples, n_primary = device_rays.bounce_set(cam, bvh0, rt_tris, lo, hi, args.rays)
     e.stream.synchronize()
     del rt_tris, bvh0
-    s3, ok_s3 = measure(e, args, "s3", tris, n_tris, "fast_build", d_args, args.rays, "traverse_persistent_kernel<CwTree, closest>", "hbm")
+    s3, ok_s3 = measure(e, args, "s3", tris, n_tris, "fast_build", d_args, args.rays, "traverse_persistent_kernel<CwTree, closest>", "issue/L1-L2")
     del d_args, tris
     torch.cuda.empty_cache()
     # ---- kitchen -------------------------------------------------------------------------------------------------------
@@ -661,6 +663,9 @@ def run_headline(args):
     kitchen, ok_k = measure(e, args, "kitchen", ktris if e.rank == 0 else None, ktris.shape[0], "fast_build", d_kargs, krays.shape[0],
                             "traverse_kernel<CwTree, closest>", "issue/L2")
     if e.rank == 0:
+        s3["roofline"]["note"] += ("; on this ray set (7.6 nodes and 0.3 triangles per ray) the upper tree levels are served by L1 (76 % hits) and L2 (57 %): "
+                                   "the kernel is issue-bound (ncu, profiles/r2a_traverse_kernel_s3_full.md: issue slots 77 % busy, ALU pipe 68 %, 23.4 of 32 "
+                                   "lanes per instruction); frac_algorithmic is cache-served reuse, frac_dram the share of HBM bandwidth actually used")
         kitchen["roofline"]["note"] += ("; the kitchen's tree (0.5 MB) and triangles (3.6 MB) live in L1/L2: frac_algorithmic measures cache-served reuse, "
                                        "the kernel is issue-bound (ncu: profiles/), frac_dram is the share of HBM bandwidth it actually uses")
         line = {"metric": METRIC, "value": s3["value"], "unit": "Mrays/s", "n_gpus": e.world, "steps": args.steps, "warmup": args.warmup,
@@ -679,6 +684,51 @@ def run_headline(args):
         e.dist.barrier()
         e.dist.destroy_process_group()
     if not (ok_s3 and ok_k):
+        raise SystemExit("bench.py: parity check failed (see `parity` in the JSON line)")
+
+
+def run_cornell(args):
+    """--workload cornell: BASELINE.json configs[0] / SURVEY.md 8(d) S0 (examples/cornell_box_cwbvh.rs:22-126): 34 triangles,
+    medium_build, 1280x720 primary rays, eye (0,1,2.1) -> (0,1,0), fov 90. Sharded over the GPUs like the headline."""
+    import torch
+
+    from obvhs_b200 import camera, test_util as tu
+    from obvhs_b200.sharding import shard_range
+    from obvhs_b200.types import ray_args_of
+
+    tris = tu.cornell_box()
+    rays = camera.primary_rays(camera.cornell_camera(1280, 720))
+    config = {"workload": f"S0: cornell box {tris.shape[0]} tris (examples/cornell_box_cwbvh.rs), medium_build, 1280x720 primary rays", "preset": "medium_build",
+              "tris": int(tris.shape[0]), "rays_total": int(rays.shape[0]), "l2": "flushed between steps (256 MB write)"}
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = cpu_reference_leg(tris, rays, "medium_build", max(1, min(args.steps, 5)), 1)
+        v = rays.shape[0] / r["trav_s"] / 1e6
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": (r["trav_s"] + r["build_s"]) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "cornell box (the example's own 34 triangles)", "config": config,
+                          "build": {"value": tris.shape[0] / r["build_s"] / 1e6, "unit": "Mtris/s", "ms": r["build_s"] * 1e3},
+                          "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": "all rays, full build per step"},
+                          "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    e = setup_env(args)
+    args_all = ray_args_of(rays)
+    lo, hi = shard_range(args_all.shape[0], e.rank, e.world)
+    with torch.cuda.stream(e.stream):
+        d_args = torch.from_numpy(np.ascontiguousarray(args_all[lo:hi])).to(e.dev)
+    res, ok = measure(e, args, "cornell", tris if e.rank == 0 else None, tris.shape[0], "medium_build", d_args, args_all.shape[0],
+                      "traverse_kernel<CwTree, closest>", "issue/L1")
+    if e.rank == 0:
+        line = {"metric": METRIC, "n_gpus": e.world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "cornell box (the example's own 34 triangles), generated rays", "config": config}
+        line.update(res)
+        line["parity_ok"] = ok
+        print(json.dumps(line))
+    if e.dist:
+        e.dist.barrier()
+        e.dist.destroy_process_group()
+    if not ok:
         raise SystemExit("bench.py: parity check failed (see `parity` in the JSON line)")
 
 
@@ -963,6 +1013,24 @@ def dynamic_frames(tris, n_frames):
     return out
 
 
+def dynamic_frames_device(d_tris, n_frames):
+    """The same frames generated on the device (torch), for the 100-frame run: (n_frames, n, 8) f32 on d_tris' device."""
+    import torch
+
+    from obvhs_b200 import device_rays
+
+    n = d_tris.shape[0]
+    t0 = d_tris.view(n, 3, 4)[:, :, 0:3]
+    k = torch.arange(n * 9, dtype=torch.int64, device=d_tris.device)
+    out = torch.zeros((n_frames, n, 8), dtype=torch.float32, device=d_tris.device)
+    for f in range(n_frames):
+        noise = device_rays.hash_noise(k, torch.full_like(k, f), 17).view(n, 3, 3)
+        v = t0 + (noise - 0.5) * 0.01
+        out[f, :, 0:3] = v.amin(dim=1)
+        out[f, :, 4:7] = v.amax(dim=1)
+    return out
+
+
 def run_dynamic(args):
     """--workload dynamic: dynamic Bvh2 maintenance (examples/physics.rs update loop): a step = one frame = rewrite the leaf
     AABBs of 1M moving triangles, refit_all (bvh2/mod.rs:527-569), ReinsertionOptimizer::run(0.01) (reinsertion.rs:40-57)."""
@@ -972,9 +1040,10 @@ def run_dynamic(args):
     res = int(round((args.tris / 2) ** 0.5)) if args.tris != 10_000_000 else 708
     tris = tu.demoscene(res, 0)
     n = tris.shape[0]
-    n_frames = 8
-    frames = dynamic_frames(tris, n_frames)
-    desc = f"demoscene({res},0) {n} moving tris: per frame set leaf AABBs + refit_all + reinsertion(0.01); {n_frames} distinct frames cycled"
+    n_frames = max(1, args.frames)  # the GPU arm runs this many DISTINCT frames (100), generated on the device
+    n_cpu_frames = min(n_frames, 8)  # the CPU legs use the first few of the same sequence (numpy generator, bounded)
+    frames = dynamic_frames(tris, n_cpu_frames)
+    desc = f"demoscene({res},0) {n} moving tris: per frame set leaf AABBs + refit_all + reinsertion(0.01); {n_frames} distinct frames"
     if args.impl == "reference":
         if rank != 0:
             return
@@ -986,7 +1055,7 @@ def run_dynamic(args):
         ts = []
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            b.set_leaf_aabbs(frames[it % n_frames])
+            b.set_leaf_aabbs(frames[it % n_cpu_frames])
             b.refit_all()
             b.reinsertion_run(0.01, threads=threads)
             if it >= args.warmup:
@@ -1016,7 +1085,7 @@ def run_dynamic(args):
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     with torch.cuda.stream(stream):
         d_tris = torch.from_numpy(tris).to(dev)
-        d_frames = torch.from_numpy(frames).to(dev)
+        d_frames = dynamic_frames_device(d_tris, n_frames)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         bvh = api.PlocBuilder(ctx).build_tris(api.PlocSearchDistance.Low, d_tris, api.SortPrecision.U64, 2)
         opt = api.ReinsertionOptimizer()
@@ -1045,7 +1114,8 @@ def run_dynamic(args):
         sampler.start()
     l0 = ctx.launch_count
     refit_ms, reins_ms = [], []
-    for it in range(args.steps):
+    n_timed = max(args.steps, n_frames)  # every distinct frame at least once
+    for it in range(n_timed):
         a, b = frame(args.warmup + it, d_frames)
         refit_ms.append(a)
         reins_ms.append(b)
@@ -1055,15 +1125,17 @@ def run_dynamic(args):
     tot = torch.tensor([sum(refit_ms), sum(reins_ms)], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    refit, reins = (tot / args.steps).tolist()
+    refit, reins = (tot / n_timed).tolist()
     value = world * n / ((refit + reins) * 1e-3) / 1e6
     # e2e: per-frame AABBs come from pinned HOST memory
-    h_frames = torch.from_numpy(frames).pin_memory()
-    hs = [h_frames[f].numpy() for f in range(n_frames)]
+    n_e2e = min(n_frames, 8)
+    h_frames = torch.empty((n_e2e, n, 8), dtype=torch.float32).pin_memory()
+    h_frames.copy_(d_frames[:n_e2e])
+    hs = [h_frames[f].numpy() for f in range(n_e2e)]
     e_t = []
     for it in range(2 + max(2, min(args.steps, 5))):
         t0 = time.perf_counter()
-        bvh.set_leaf_aabbs(hs[it % n_frames])
+        bvh.set_leaf_aabbs(hs[it % n_e2e])
         opt.run(bvh, 0.01)
         ctx.synchronize()
         if it >= 2:
@@ -1084,13 +1156,13 @@ def run_dynamic(args):
             ts = []
             for it in range(4):
                 t0 = time.perf_counter()
-                b.set_leaf_aabbs(frames[it % n_frames])
+                b.set_leaf_aabbs(frames[it % n_cpu_frames])
                 b.refit_all()
                 b.reinsertion_run(0.01, threads=threads)
                 ts.append(time.perf_counter() - t0)
             cpu = {"value": n / float(np.mean(ts[1:])) / 1e6, "unit": "Mtris/s", "cores": threads, "kind": "port", "sample": "3 full frames"}
         print(json.dumps({
-            "metric": "dynamic Bvh2 refit + reinsertion Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
+            "metric": "dynamic Bvh2 refit + reinsertion Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": n_timed,
             "warmup": args.warmup, "ms_per_step": refit + reins, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": desc, "tris": n, "l2": "flushed between steps (256 MB write)",
                                             "multi_gpu": "replicas only" if world > 1 else "single GPU"},
@@ -1311,7 +1383,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s3", choices=["s3", "kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
+    ap.add_argument("--workload", default="s3", choices=["s3", "cornell", "kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
+    ap.add_argument("--frames", type=int, default=100, help="distinct frames of the dynamic workload (SURVEY.md 8d S4: 100)")
     ap.add_argument("--rays", type=int, default=S3_RAYS, help="size of the headline's global bounce-ray set")
     ap.add_argument("--parity-rays", type=int, default=262_144, help="rays of the in-run oracle comparison")
     ap.add_argument("--samples", type=int, default=24, help="AA samples of the bounce workload (165 = the 100M-ray set of SURVEY.md 8d)")
@@ -1322,6 +1395,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "s3":
         run_headline_reference(args) if args.impl == "reference" else run_headline(args)
+    elif args.workload == "cornell":
+        run_cornell(args)
     elif args.workload == "dynamic":
         run_dynamic(args)
     elif args.workload == "demoscene":

@@ -10,7 +10,7 @@ timeout -s KILL 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TA
 timeout -s KILL 900 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_$TAG.log 2>&1
 tail -3 gpurun_out/pytest_$TAG.log; tail -2 gpurun_out/smoke_$TAG.log; tail -c 600 gpurun_out/bench_$TAG.log
 # launch list: one timed step of the headline (S3 step = build + traversal; kitchen likewise); ray generation launches come first
-timeout -s KILL 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout -s KILL 1200 ncu --nvtx --nvtx-include "obvhs_timed_step/" --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 # full capture of the S3 traversal launch: skip the 272 primary-ray launches of the ray generation and the 3 warm-up steps
 timeout -s KILL 1200 ncu --set full --clock-control none --import-source on -k regex:traverse_persistent_kernel -s 275 -c 1 -f -o gpurun_out/prof_s3_traverse_$TAG \
