@@ -45,9 +45,25 @@ struct Emitter {  // FILL = false: count only
     }
 };
 
-// bvh2/mod.rs:365-456. CAP = the reference's fixed stack (fast_stack!(u32, (96, 192), max_depth)), saturating push.
-template <int QUERY, bool FILL, int CAP>
-__device__ __forceinline__ void bvh2_query(const float4* __restrict__ nodes, u32 node_count, const QueryBox& q, Emitter& e) {
+// The u32 stack of the Bvh2 queries: the reference's fixed StackStack<u32, 96 | 192> (saturating push), or -- beyond max_depth
+// 192, where fast_stack! switches to HeapStack::new_with_capacity(max_depth) (faststack.rs:44-47) -- a slice of a global arena,
+// interleaved over the threads of the grid.
+template <int CAP>
+struct QueryStack {
+    u32 data[CAP];
+    __device__ __forceinline__ u32 cap() const { return CAP; }
+    __device__ __forceinline__ u32& at(u32 i) { return data[i]; }
+};
+struct QueryHeapStack {
+    u32* base;
+    u32 stride, capacity;
+    __device__ __forceinline__ u32 cap() const { return capacity; }
+    __device__ __forceinline__ u32& at(u32 i) { return base[(size_t)i * stride]; }
+};
+
+// bvh2/mod.rs:365-456
+template <int QUERY, bool FILL, class Stack>
+__device__ __forceinline__ void bvh2_query(const float4* __restrict__ nodes, u32 node_count, const QueryBox& q, Emitter& e, Stack& stack) {
     if (node_count == 0) return;
     {
         const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
@@ -55,25 +71,25 @@ __device__ __forceinline__ void bvh2_query(const float4* __restrict__ nodes, u32
             if (box_test<QUERY>(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, q)) e.emit<FILL>(0u);
             return;
         }
-        u32 stack[CAP];
+        const u32 cap1 = stack.cap() - 1u;
         u32 sp = 0;
-        stack[sp++] = __float_as_uint(hi.w);
+        stack.at(sp++) = __float_as_uint(hi.w);
         while (sp > 0) {
-            const u32 node_index = stack[--sp];
+            const u32 node_index = stack.at(--sp);
             const float4* np = nodes + (size_t)node_index * 2;
             const float4 llo = __ldg(np), lhi = __ldg(np + 1), rlo = __ldg(np + 2), rhi = __ldg(np + 3);
             if (box_test<QUERY>(llo.x, llo.y, llo.z, lhi.x, lhi.y, lhi.z, q)) {
                 if (__float_as_uint(llo.w) != 0) e.emit<FILL>(node_index);
                 else {
-                    stack[sp] = __float_as_uint(lhi.w);
-                    sp = min(sp + 1u, (u32)(CAP - 1));
+                    stack.at(sp) = __float_as_uint(lhi.w);
+                    sp = min(sp + 1u, cap1);
                 }
             }
             if (box_test<QUERY>(rlo.x, rlo.y, rlo.z, rhi.x, rhi.y, rhi.z, q)) {
                 if (__float_as_uint(rlo.w) != 0) e.emit<FILL>(node_index + 1);
                 else {
-                    stack[sp] = __float_as_uint(rhi.w);
-                    sp = min(sp + 1u, (u32)(CAP - 1));
+                    stack.at(sp) = __float_as_uint(rhi.w);
+                    sp = min(sp + 1u, cap1);
                 }
             }
         }
@@ -157,19 +173,30 @@ __device__ __forceinline__ void cwbvh_query(const uint4* __restrict__ nodes, u32
     }
 }
 
-// TREE 0 = Bvh2 (CAP 96), 1 = Bvh2 (CAP 192), 2 = CwBvh
+// TREE 0 = Bvh2 (CAP 96), 1 = Bvh2 (CAP 192), 2 = CwBvh, 3 = Bvh2 with a heap stack of heap_cap entries per thread (grid-stride:
+// the launch has a bounded number of threads so that the arena stays small)
 template <int TREE, int QUERY, bool FILL>
 __global__ void __launch_bounds__(128) query_kernel(const void* __restrict__ nodes, u32 node_count, u32 root_group, u32 oct_inv4,
                                                     const float4* __restrict__ queries, u32 n, u32* __restrict__ counts,
-                                                    const u32* __restrict__ offsets, u32* __restrict__ ids) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const QueryBox q = load_query<QUERY>(queries, i);
-    Emitter e{FILL ? ids + offsets[i] : nullptr, 0u};
-    if (TREE == 0) bvh2_query<QUERY, FILL, 96>(reinterpret_cast<const float4*>(nodes), node_count, q, e);
-    else if (TREE == 1) bvh2_query<QUERY, FILL, 192>(reinterpret_cast<const float4*>(nodes), node_count, q, e);
-    else cwbvh_query<QUERY, FILL>(reinterpret_cast<const uint4*>(nodes), root_group, oct_inv4, q, e);
-    if (!FILL) counts[i] = e.count;
+                                                    const u32* __restrict__ offsets, u32* __restrict__ ids, u32* heap, u32 heap_cap) {
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (u32 i = tid; i < n; i += nthreads) {
+        const QueryBox q = load_query<QUERY>(queries, i);
+        Emitter e{FILL ? ids + offsets[i] : nullptr, 0u};
+        if (TREE == 0) {
+            QueryStack<96> st;
+            bvh2_query<QUERY, FILL>(reinterpret_cast<const float4*>(nodes), node_count, q, e, st);
+        } else if (TREE == 1) {
+            QueryStack<192> st;
+            bvh2_query<QUERY, FILL>(reinterpret_cast<const float4*>(nodes), node_count, q, e, st);
+        } else if (TREE == 3) {
+            QueryHeapStack st{heap + tid, nthreads, heap_cap};
+            bvh2_query<QUERY, FILL>(reinterpret_cast<const float4*>(nodes), node_count, q, e, st);
+        } else {
+            cwbvh_query<QUERY, FILL>(reinterpret_cast<const uint4*>(nodes), root_group, oct_inv4, q, e);
+        }
+        if (!FILL) counts[i] = e.count;
+    }
 }
 
 struct CountOf {
@@ -192,7 +219,7 @@ __global__ void __launch_bounds__(256) sum_counts_u64_kernel(const u32* __restri
 
 template <int TREE, int QUERY>
 int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_group, u32 oct_inv4, const float4* d_queries, size_t n, u32* counts,
-              u32* ids, size_t capacity, size_t* total_out) {
+              u32* ids, size_t capacity, size_t* total_out, u32 heap_cap = 0) {
     cudaStream_t s = ctx->stream;
     if (total_out) *total_out = 0;
     if (n == 0) return OBVHS_OK;
@@ -209,7 +236,15 @@ int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_gro
     CU_TRY(ctx, d_offsets.alloc(n, s));
     CU_TRY(ctx, tiles.alloc((size_t)div_up(n, CP_TILE) + 1, s));
     CU_TRY(ctx, d_total.alloc(1, s));
-    query_kernel<TREE, QUERY, false><<<div_up(n, 128), 128, 0, s>>>(nodes, node_count, root_group, oct_inv4, d_queries, un, d_counts.p, nullptr, nullptr);
+    // heap stacks (TREE 3): at most 256 Ki threads, each with heap_cap entries of the arena
+    DevBuf<u32> heap;
+    int blocks = div_up(n, 128);
+    if (TREE == 3) {
+        blocks = std::min(blocks, 2048);
+        CU_TRY(ctx, heap.alloc((size_t)blocks * 128 * heap_cap, s));
+    }
+    query_kernel<TREE, QUERY, false><<<blocks, 128, 0, s>>>(nodes, node_count, root_group, oct_inv4, d_queries, un, d_counts.p, nullptr, nullptr,
+                                                             heap.p, heap_cap);
     KERNEL_CHECK(ctx);
     ST_TRY(scan_values(ctx, CountOf{d_counts.p}, StoreOffset{d_offsets.p}, un, tiles.p, d_total.p));
     sum_counts_u64_kernel<<<std::min(div_up(n, 256), ctx->sm_count * 8), 256, 0, s>>>(d_counts.p, un, d_total64.p);
@@ -240,7 +275,8 @@ int run_query(ObvhsContext* ctx, const void* nodes, u32 node_count, u32 root_gro
         CU_TRY(ctx, d_ids.alloc(total, s));
         d_out = d_ids.p;
     }
-    query_kernel<TREE, QUERY, true><<<div_up(n, 128), 128, 0, s>>>(nodes, node_count, root_group, oct_inv4, d_queries, un, nullptr, d_offsets.p, d_out);
+    query_kernel<TREE, QUERY, true><<<blocks, 128, 0, s>>>(nodes, node_count, root_group, oct_inv4, d_queries, un, nullptr, d_offsets.p, d_out, heap.p,
+                                                            heap_cap);
     KERNEL_CHECK(ctx);
     if (!out_dev) ST_TRY(copy_out(ctx, ids, (const u32*)d_out, total));
     return OBVHS_OK;
@@ -255,9 +291,11 @@ u32 octant_inv4(const float* dir) {  // cwbvh/mod.rs:1001-1010; NULL = Vec3A::ZE
 
 int bvh2_query_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, int query_kind, const float4* d_queries, size_t n, u32* counts, u32* ids,
                       size_t capacity, size_t* total_out) {
-    if (bvh->max_depth > 192) {  // the reference switches to a heap stack there (fast_stack!)
-        OBVHS_SET_ERR(ctx, "max_depth %zu > 192 is not supported by the fixed traversal stack", bvh->max_depth);
-        return OBVHS_ERR_UNSUPPORTED;
+    const u32 nc0 = (u32)bvh->node_count;
+    if (bvh->max_depth > 192) {  // the reference switches to HeapStack::new_with_capacity(max_depth) there (fast_stack!)
+        const u32 cap = (u32)bvh->max_depth;
+        if (query_kind == 0) return run_query<3, 0>(ctx, bvh->nodes, nc0, 0, 0, d_queries, n, counts, ids, capacity, total_out, cap);
+        return run_query<3, 1>(ctx, bvh->nodes, nc0, 0, 0, d_queries, n, counts, ids, capacity, total_out, cap);
     }
     const bool deep = bvh->max_depth > 96;
     const u32 nc = (u32)bvh->node_count;

@@ -236,6 +236,15 @@ struct LaneStack<T, CAP, 0> {
     __device__ __forceinline__ void put(u32 i, const T& v) { local[i] = v; }
     __device__ __forceinline__ T get(u32 i) const { return local[i]; }
 };
+// CAP = 0: a heap stack (the reference's HeapStack for max_depth beyond the fixed sizes, faststack.rs:44-47): this lane's slice
+// of a global arena, interleaved over the threads of the grid
+template <class T>
+struct LaneStack<T, 0, 0> {
+    T* base;
+    u32 stride;
+    __device__ __forceinline__ void put(u32 i, const T& v) { base[(size_t)i * stride] = v; }
+    __device__ __forceinline__ T get(u32 i) const { return base[(size_t)i * stride]; }
+};
 __device__ __forceinline__ void result_reset(RayResult& o) {
     o.hit_id = 0xffffffffu;  // RayHit::none(), ray.rs:74-83
     o.hit_t = __int_as_float(0x7f800000);
@@ -264,6 +273,8 @@ struct CwTree {
         uint2 cur, prim;  // cwbvh/mod.rs:84-120 current_group / primitive_group
         RayResult o;
     };
+    template <class Stack>
+    __device__ __forceinline__ void bind_stack(Stack&) const {}
     __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, bool packed) const {
         ray_load(st.r, rays, i, packed);
         // cwbvh/mod.rs:1001-1010
@@ -440,8 +451,18 @@ struct Bvh2Tree {
     const float4* nodes;
     const float4* tris;
     u32 node_count;
+    u32* heap;      // CAP == 0 only: arena of heap_cap entries per thread of the launch
+    u32 heap_cap;
     typedef u32 StackT;
     static constexpr int STACK = CAP;
+    __device__ __forceinline__ u32 cap_m1() const { return CAP ? (u32)(CAP - 1) : heap_cap - 1u; }
+    template <class Stack>
+    __device__ __forceinline__ void bind_stack(Stack& stack) const {
+        if constexpr (CAP == 0) {
+            stack.base = heap + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+            stack.stride = gridDim.x * blockDim.x;
+        }
+    }
     static constexpr u32 AT_ROOT = 0xffffffffu;
     struct State {
         RayRegs r;
@@ -593,7 +614,7 @@ struct Bvh2Tree {
                 st.cur = st.l_first;
                 if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
                     stack.put(st.sp, st.r_first);
-                    st.sp = min(st.sp + 1u, (u32)(CAP - 1));
+                    st.sp = min(st.sp + 1u, cap_m1());
                 }
             } else if (go_right) {
                 st.cur = st.r_first;
@@ -652,7 +673,7 @@ struct Bvh2Tree {
             st.cur = l_first;
             if (go_right) {  // :321-324, saturating push (faststack.rs:299-303)
                 stack.put(st.sp, r_first);
-                st.sp = min(st.sp + 1u, (u32)(CAP - 1));
+                st.sp = min(st.sp + 1u, cap_m1());
             }
         } else if (go_right) {
             st.cur = r_first;
@@ -692,6 +713,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, c
     u32 nodes_visited = 0, tris_tested = 0;
     typename Tree::State st;
     LaneStack<typename Tree::StackT, Tree::STACK, 0> stack;
+    tree.bind_stack(stack);
     const bool valid = i < n;
     if (valid) tree.begin(st, rays, i, packed);
     bool mine = valid;
@@ -750,6 +772,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(c
     u32 my = 0;
     typename Tree::State st = {};
     LaneStack<typename Tree::StackT, Tree::STACK, SS> stack;
+    tree.bind_stack(stack);
     const u32 chunk = pa.chunk;
     // the warp owns [chunk_pos, chunk_end): consecutive rays, so refills stay close to the rays still in flight
     u32 chunk_pos = 0, chunk_end = 0;  // (n + warps * chunk < 2^32: the host splits larger batches)
@@ -899,11 +922,12 @@ static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays
 constexpr size_t AUTO_STATIC_MAX_PRIMS = 262144;
 template <class Tree>
 static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, size_t prim_count, const float4* rays, size_t n,
-                             bool packed, int mode, void* d_out, u64* d_counters) {
+                             bool packed, int mode, void* d_out, u64* d_counters, bool force_persistent = false) {
     const size_t ray_vec4 = packed ? 2 : 4;  // float4 per ray
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
     int tm = ctx->traverse_mode;
+    if (force_persistent) tm = 1;  // (heap stacks: the arena is sized for the resident lanes of the persistent kernel)
     if (tm == 2 && n < 16384) tm = 0;
     // Large scenes: even camera rays vary a lot in work per ray (depth complexity, cache misses), and the refill kernel wins
     // regardless of coherence (terrain, jittered primary rays: +3 % at 0.3 M triangles, +16 % at 1 M, +41 % at 3 M, +36 % at
@@ -974,15 +998,20 @@ int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_
     ObvhsAabb unknown = {};  // the Bvh2 handle does not keep the scene box: the probe then judges directions only
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     if (bvh->max_depth <= 96) {  // fast_stack!(u32, (96, 192), self.max_depth, ...) bvh2/mod.rs:166
-        Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
+        Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, nullptr, 0u};
         return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
     }
     if (bvh->max_depth <= 192) {
-        Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count};
+        Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, nullptr, 0u};
         return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
     }
-    OBVHS_SET_ERR(ctx, "Bvh2 traversal: max_depth %zu > 192 needs the reference's heap stack -- not supported", bvh->max_depth);
-    return OBVHS_ERR_UNSUPPORTED;
+    // beyond 192 the reference allocates HeapStack::new_with_capacity(max_depth) per call: here one arena for the launch, max_depth
+    // entries for each of the (at most sm_count * 16 * 128) lanes the persistent kernel keeps resident
+    DevBuf<u32> heap;
+    CU_TRY(ctx, heap.alloc((size_t)ctx->sm_count * 16 * TRAV_BLOCK * bvh->max_depth, ctx->stream));
+    Bvh2Tree<0> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, heap.p,
+                     (u32)bvh->max_depth};
+    return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters, true);
 }
 
 // bvh_tris[i] = tris[primitive_indices[i]] for a Bvh2 (examples/demoscene.rs:66-70)

@@ -154,3 +154,52 @@ def test_collision_broad_phase_like_the_physics_example(api):
     for s1 in range(0, len(aabbs), 997):
         ref = brute_aabb(aabbs, aabbs[s1])
         assert {(s1, int(s2)) for s2 in ref if s2 != s1} == {p for p in got if p[0] == s1}
+
+
+@pytest.mark.parametrize("n,g", [(300, 0.05), (2000, 0.005)])
+def test_deep_bvh2_traversal_and_queries(api, n, g):
+    # max_depth 156 (the 192-entry fixed stack) and ~1000 (beyond every fixed stack: the reference's HeapStack, here a global arena):
+    # Bvh2 ray traversal (closest / miss / all-hit count, both kernels) and the box / point queries against the oracle
+    from test_gpu_parity import graded_boxes
+    from obvhs_b200.types import make_rays
+
+    a = graded_boxes(n, g)
+    tris = np.zeros((n, 12), np.float32)  # one thin triangle per box, same AABB
+    tris[:, 0:3] = a[:, 0:3]
+    tris[:, 4:7] = np.stack([a[:, 4], a[:, 1], a[:, 2]], axis=1)
+    tris[:, 8:11] = np.stack([a[:, 0], a[:, 5], a[:, 6]], axis=1)
+    aabbs = ob.tri_aabbs(tris)
+    w = ob.ploc_build(aabbs, None, 6, 64, 2)
+    assert w.max_depth > (192 if n == 2000 else 96)
+    wn, wp = w.get()
+    gb = api.Bvh2.upload(wn, wp, max_depth=w.max_depth)
+    gb.set_triangles(tris)
+    bt = w.bvh_tris(tris)
+    rng = np.random.default_rng(5)
+    m = 40000
+    x = (aabbs[rng.integers(0, n, m), 0] + aabbs[rng.integers(0, n, m), 4]) * np.float32(0.5)
+    o = np.stack([x, np.full(m, 0.5, np.float32), rng.random(m, dtype=np.float32) * np.float32(0.02) - np.float32(0.01)], axis=1).astype(np.float32)
+    d = np.stack([rng.random(m, dtype=np.float32) * np.float32(0.4) - np.float32(0.2), np.full(m, -1.0, np.float32),
+                  rng.random(m, dtype=np.float32) * np.float32(0.02) - np.float32(0.01)], axis=1).astype(np.float32)
+    rays = make_rays(o, d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32), 0.0, np.inf)
+    rays[m // 2:, 0:3] = np.stack([np.full(m - m // 2, -1.0, np.float32), np.zeros(m - m // 2, np.float32), np.zeros(m - m // 2, np.float32)], axis=1)
+    rays[m // 2:, 4:7] = np.array([1.0, 0.0, 0.0], np.float32)  # along the whole chain: deep stacks
+    rays[m // 2:, 8:11] = np.array([1.0, 8388608.0, 8388608.0], np.float32)
+    want = w.ray_traverse(bt, rays)
+    assert (want["t"] < np.inf).sum() > 100
+    for mode in ("static", "persistent"):
+        ctx = api.Context(0, traverse=mode)
+        g2 = api.Bvh2.upload(wn, wp, max_depth=w.max_depth, ctx=ctx)
+        g2.set_triangles(tris)
+        got = g2.ray_traverse(rays)
+        assert np.array_equal(got["primitive_id"], want["primitive_id"]) and np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+        assert np.array_equal(g2.ray_traverse_miss(rays), w.ray_traverse_miss(bt, rays))
+        assert np.array_equal(g2.ray_traverse_anyhit_count(rays), w.ray_traverse_anyhit_count(bt, rays))
+    q = query_boxes(tris, 2000, 2, 0.2)
+    wc, wi = w.aabb_traverse(q)
+    gc, gi = gb.aabb_traverse(q)
+    assert np.array_equal(gc, wc) and np.array_equal(gi, wi) and wc[0] == n
+    pts = (q[:, 0:3] + q[:, 4:7]) * np.float32(0.5)
+    wc, wi = w.point_traverse(pts)
+    gc, gi = gb.point_traverse(pts)
+    assert np.array_equal(gc, wc) and np.array_equal(gi, wi)
