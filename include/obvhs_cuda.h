@@ -177,7 +177,11 @@ int obvhs_cuda_bvh2_upload(ObvhsContext* ctx, const ObvhsBvh2Node* nodes, size_t
                            const uint32_t* primitive_indices, size_t prim_count, size_t max_depth,
                            int children_ordered_after_parents, ObvhsBvh2** out);
 int obvhs_cuda_bvh2_compute_parents(ObvhsContext* ctx, ObvhsBvh2* bvh);                 /* bvh2/mod.rs:586-619 */
-int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh);                       /* bvh2/mod.rs:527-569 */
+int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh);
+/* Bvh2::reorder_in_stack_traversal_order (src/bvh2/mod.rs:462-500): nodes re-indexed in the pop order of the reference's stack
+ * (parents before children, each sibling pair followed by the subtree of its second node, then of its first); parents are
+ * recomputed when present; children_are_ordered_after_parents becomes true. */
+int obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ObvhsContext* ctx, ObvhsBvh2* bvh);                       /* bvh2/mod.rs:527-569 */
 /* rewrite every leaf's AABB from per-primitive AABBs (dynamic scenes, examples/physics.rs:500-539), then refit_all */
 int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* prim_aabbs, size_t n);
 
@@ -229,6 +233,13 @@ int obvhs_cuda_cwbvh_exact_node_aabbs(ObvhsContext* ctx, const ObvhsCwBvh* bvh, 
 /* CwBvh::compute_parents (src/cwbvh/mod.rs:494-509): parents[node_index] = the node whose inner child slot references it,
  * parents[0] = 0. `parents` holds node_count entries (host or device). */
 int obvhs_cuda_cwbvh_compute_parents(ObvhsContext* ctx, const ObvhsCwBvh* bvh, uint32_t* parents);
+/* CwBvh::order_children(&mut self, primitives, direct_layout) (src/cwbvh/mod.rs:520-735): every node's children re-assigned to
+ * the octant slots by the greedy cost table over child centres (leaf children: union of their primitives' boxes; inner children:
+ * the child's own box, exact when the tree carries exact_node_aabbs), inner children's records moved inside their range.
+ * prim_aabbs: the primitives as Boundable::aabb(), indexed by primitive id (direct_layout = 0) or already in
+ * primitive_indices order (direct_layout != 0). Note: permuted triangles attached to the handle stay valid (primitive order
+ * does not change). */
+int obvhs_cuda_cwbvh_order_children(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsAabb* prim_aabbs, size_t n, int direct_layout);
 /* build_cwbvh_from_tris(triangles, config, core_build_time) (cwbvh/builder.rs:20-85). core_build_seconds (optional)
  * is INCREMENTED by the device time of PLOC -> reinsertion -> collapse, as the reference's `+=` does. The permuted
  * triangle array (examples/obj_cwbvh.rs:63-67) is attached to the result so it can be traversed directly. */

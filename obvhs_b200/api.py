@@ -86,6 +86,7 @@ SIGNATURES = {
     "obvhs_cuda_bvh2_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _sz, _i32, _PP]),
     "obvhs_cuda_bvh2_compute_parents": (_i32, [_vp, _vp]),
     "obvhs_cuda_bvh2_refit_all": (_i32, [_vp, _vp]),
+    "obvhs_cuda_bvh2_reorder_in_stack_traversal_order": (_i32, [_vp, _vp]),
     "obvhs_cuda_bvh2_set_leaf_aabbs": (_i32, [_vp, _vp, _vp, _sz]),
     "obvhs_cuda_reinsertion_run": (_i32, [_vp, _vp, _f32, _vp, _sz, C.POINTER(_u64)]),
     "obvhs_cuda_reinsertion_run_with_candidates": (_i32, [_vp, _vp, _vp, _sz, _u32, C.POINTER(_u64)]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_prim_count": (_sz, [_vp]),
     "obvhs_cuda_cwbvh_exact_node_aabbs": (_i32, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_cwbvh_compute_parents": (_i32, [_vp, _vp, _vp]),
+    "obvhs_cuda_cwbvh_order_children": (_i32, [_vp, _vp, _vp, _sz, _i32]),
     "obvhs_cuda_cwbvh_download": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "obvhs_cuda_cwbvh_upload": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _PP]),
     "obvhs_cuda_cwbvh_set_triangles": (_i32, [_vp, _vp, _vp, _sz]),
@@ -371,6 +373,10 @@ class Bvh2:
 
     def compute_parents(self):
         self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_compute_parents(self.ctx.h, self.h))
+
+    def reorder_in_stack_traversal_order(self):
+        """Bvh2::reorder_in_stack_traversal_order (src/bvh2/mod.rs:462-500)."""
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_reorder_in_stack_traversal_order(self.ctx.h, self.h))
 
     def compute_primitives_to_nodes(self):
         """Bvh2::compute_primitives_to_nodes (src/bvh2/mod.rs:647-665) from the downloaded tree (host-side bookkeeping)."""
@@ -659,6 +665,11 @@ class CwBvh:
         parents = out if out is not None else np.zeros(self.node_count, dtype=np.uint32)
         self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_compute_parents(self.ctx.h, self.h, _ptr(parents)))
         return parents
+
+    def order_children(self, prim_aabbs, direct_layout: bool = False):
+        """CwBvh::order_children(primitives, direct_layout) (src/cwbvh/mod.rs:520-524); the primitives as (n, 8) AABBs."""
+        a = _as_f32(prim_aabbs, 8)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_order_children(self.ctx.h, self.h, _ptr(a), a.shape[0], int(direct_layout)))
 
     def exact_node_aabbs(self):
         """CwBvh::exact_node_aabbs (src/cwbvh/mod.rs:47) as an (n, 8) float32 array, or None when absent."""

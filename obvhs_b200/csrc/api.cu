@@ -523,6 +523,12 @@ int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     ARG_CHECK(ctx, bvh, "bvh is null");
     return bvh2_refit_all_device(ctx, bvh);
 }
+int obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ObvhsContext* ctx, ObvhsBvh2* bvh) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh, "bvh is null");
+    // (primitive_indices is untouched, so permuted triangles attached to the handle stay valid)
+    return bvh2_reorder_in_stack_traversal_order_device(ctx, bvh);
+}
 // PlocBuilder::full_rebuild / partial_rebuild / compute_rebuild_path_flags (src/ploc/rebuild.rs)
 int obvhs_cuda_ploc_full_rebuild(ObvhsContext* ctx, ObvhsBvh2* bvh, uint32_t search_distance, uint32_t sort_precision,
                                  size_t search_depth_threshold) {
@@ -806,6 +812,16 @@ int obvhs_cuda_cwbvh_compute_parents(ObvhsContext* ctx, const ObvhsCwBvh* bvh, u
     if (d != parents) ST_TRY(copy_out(ctx, parents, (const u32*)d, bvh->node_count));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return OBVHS_OK;
+}
+// CwBvh::order_children (src/cwbvh/mod.rs:520-524); the primitives arrive as their AABBs (Boundable::aabb)
+int obvhs_cuda_cwbvh_order_children(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsAabb* prim_aabbs, size_t n, int direct_layout) {
+    API_ENTER(ctx);
+    ARG_CHECK(ctx, bvh && (n == 0 || prim_aabbs), "null argument");
+    if (bvh->node_count == 0) return OBVHS_OK;
+    DevBuf<ObvhsAabb> st;
+    const ObvhsAabb* d = nullptr;
+    ST_TRY(stage_in(ctx, prim_aabbs, n, st, &d));
+    return cwbvh_order_children_device(ctx, bvh, d, n, direct_layout != 0);
 }
 int obvhs_cuda_cwbvh_uses_spatial_splits(const ObvhsCwBvh* bvh) { return bvh && bvh->uses_spatial_splits; }
 void obvhs_cuda_cwbvh_set_uses_spatial_splits(ObvhsCwBvh* bvh, int v) { if (bvh) bvh->uses_spatial_splits = v != 0; }

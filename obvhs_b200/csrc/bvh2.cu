@@ -5,6 +5,10 @@
 //                     The reference sweeps indices in reverse (or a stack order); any bottom-up order gives the same
 //                     bits because min/max are exact and the operand order (first, second) is fixed. Here: one thread
 //                     per leaf climbs with an arrival counter per inner node; the second arriver refits the node.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -85,7 +89,143 @@ __global__ void __launch_bounds__(256) set_node_aabbs_kernel(Node32* nodes, u32 
     store_node(nodes + id, nd);
 }
 
+// ---- Bvh2::reorder_in_stack_traversal_order (src/bvh2/mod.rs:462-500) --------------------------------------------------------
+// The reference pops sibling pairs off a stack that receives the FIRST child's pair before the SECOND's, so a pair is followed
+// by the whole subtree under its second node, then by the subtree under its first node; the k-th popped pair lands at new
+// indices 2k+1, 2k+2 (the root keeps index 0). With pairs(x) = number of sibling pairs below node x (= inner nodes of its
+// subtree), the pair below the second node of pair k is pair k + 1 and the pair below its first node is pair
+// k + 1 + pairs(second). Two passes: pairs() bottom-up with arrival counters (as refit_all), then a top-down breadth-first
+// sweep that carries every pair's rank and writes both nodes -- with their first_index already remapped -- to their final
+// slots. One cooperative launch, a grid barrier per tree level.
+__global__ void __launch_bounds__(256) subtree_pairs_kernel(const Node32* __restrict__ nodes, u32 n, const u32* __restrict__ parents, u32* arrivals,
+                                                            u32* pairs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || i == 0) return;
+    if (__float_as_uint(__ldg(reinterpret_cast<const float4*>(nodes + i)).w) == 0) return;  // start at leaves (pairs = 0, pre-zeroed)
+    u32 p = parents[i];
+    for (;;) {
+        __threadfence();
+        if (atomicAdd(&arrivals[p], 1u) == 0) return;  // first arriver: the sibling subtree is not finished yet
+        const u32 first = __float_as_uint(__ldg(reinterpret_cast<const float4*>(nodes + p) + 1).w);
+        pairs[p] = 1u + __ldcg(&pairs[first]) + __ldcg(&pairs[first + 1]);
+        if (p == 0) return;
+        p = parents[p];
+    }
+}
+
+struct ReorderArgs {
+    const Node32* in;
+    Node32* out;
+    const u32* pairs;
+    uint2* queue[2];  // (old index of the pair's first node, rank of the pair)
+    u32* qcount;      // [3], slot = level % 3
+};
+__global__ void __launch_bounds__(256) reorder_bfs_kernel(ReorderArgs a) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const u32 lane = threadIdx.x & 31u;
+    if (tid == 0) {
+        Node32 root = load_node(a.in);
+        u32 n0 = 0;
+        if (root.prim_count == 0) {
+            a.queue[0][0] = make_uint2(root.first_index, 0u);
+            root.first_index = 1;  // mapping[first_index] of the first popped pair
+            n0 = 1;
+        }
+        store_node(a.out, root);
+        a.qcount[0] = n0;
+        a.qcount[1] = 0;
+        a.qcount[2] = 0;
+    }
+    grid.sync();
+    for (u32 level = 0;; level++) {
+        const u32 n = __ldcg(&a.qcount[level % 3]);
+        if (n == 0) break;
+        const uint2* q = a.queue[level & 1];
+        uint2* qn = a.queue[(level + 1) & 1];
+        u32* qn_count = &a.qcount[(level + 1) % 3];
+        for (u32 base = blockIdx.x * blockDim.x; base < n; base += nthreads) {  // CTA-uniform trip count (warp-aggregated pushes)
+            const u32 idx = base + threadIdx.x;
+            uint2 push_a = make_uint2(0, 0), push_b = make_uint2(0, 0);
+            bool has_a = false, has_b = false;
+            if (idx < n) {
+                const uint2 e = __ldcg(q + idx);
+                const u32 cur = e.x, r = e.y;
+                Node32 na = load_node(a.in + cur), nb = load_node(a.in + cur + 1);
+                const u32 pb = nb.prim_count == 0 ? __ldg(a.pairs + cur + 1) : 0u;
+                if (na.prim_count == 0) {
+                    has_a = true;
+                    push_a = make_uint2(na.first_index, r + 1u + pb);
+                    na.first_index = 2u * push_a.y + 1u;
+                }
+                if (nb.prim_count == 0) {
+                    has_b = true;
+                    push_b = make_uint2(nb.first_index, r + 1u);
+                    nb.first_index = 2u * push_b.y + 1u;
+                }
+                store_node(a.out + 2u * r + 1u, na);
+                store_node(a.out + 2u * r + 2u, nb);
+            }
+            const u32 ba = __ballot_sync(0xffffffffu, has_a), bb = __ballot_sync(0xffffffffu, has_b);
+            const u32 total = __popc(ba) + __popc(bb);
+            u32 wbase = 0;
+            if (lane == 0 && total) wbase = atomicAdd(qn_count, total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            const u32 lt = (1u << lane) - 1u;
+            if (has_a) qn[wbase + __popc(ba & lt)] = push_a;
+            if (has_b) qn[wbase + __popc(ba) + __popc(bb & lt)] = push_b;
+        }
+        if (tid == 0) a.qcount[(level + 2) % 3] = 0;  // the slot of level + 2: nobody reads or writes it now
+        grid.sync();
+    }
+}
+
 }  // namespace
+
+int bvh2_reorder_in_stack_traversal_order_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
+    if (bvh->node_count < 2) return OBVHS_OK;  // bvh2/mod.rs:463-465
+    cudaStream_t s = ctx->stream;
+    const u32 n = (u32)bvh->node_count;
+    DevBuf<u32> parents_tmp, arrivals, pairs, qcount;
+    DevBuf<uint2> q0, q1;
+    const u32* parents = bvh->parents;
+    if (!parents) {
+        CU_TRY(ctx, parents_tmp.alloc(n, s));
+        ST_TRY(bvh2_compute_parents_into(ctx, bvh, parents_tmp.p));
+        parents = parents_tmp.p;
+    }
+    CU_TRY(ctx, arrivals.alloc(n, s));
+    CU_TRY(ctx, pairs.alloc(n, s));
+    CU_TRY(ctx, q0.alloc((size_t)n / 2 + 1, s));
+    CU_TRY(ctx, q1.alloc((size_t)n / 2 + 1, s));
+    CU_TRY(ctx, qcount.alloc(4, s));
+    CU_TRY(ctx, cudaMemsetAsync(arrivals.p, 0, (size_t)n * 4, s));
+    CU_TRY(ctx, cudaMemsetAsync(pairs.p, 0, (size_t)n * 4, s));
+    subtree_pairs_kernel<<<div_up(n, 256), 256, 0, s>>>(bvh->nodes, n, parents, arrivals.p, pairs.p);
+    KERNEL_CHECK(ctx);
+    Node32* out = nullptr;
+    CU_TRY(ctx, obvhs_result_alloc(ctx, (void**)&out, (size_t)n * sizeof(Node32)));
+    ReorderArgs ra{bvh->nodes, out, pairs.p, {q0.p, q1.p}, qcount.p};
+    static PerDevice<int> per_sm_dev;
+    int& per_sm = per_sm_dev[ctx->device];
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reorder_bfs_kernel, 256, 0);
+        if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(n / 2, 256)));
+    void* args[] = {&ra};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)reorder_bfs_kernel, dim3(blocks), dim3(256), args, 0, s);
+    if (e != cudaSuccess) {
+        obvhs_result_free(ctx, out);
+        CU_TRY(ctx, e);
+    }
+    KERNEL_CHECK(ctx);
+    obvhs_result_free(bvh->owner, bvh->nodes);  // (stream order: the kernel above is the last reader)
+    bvh->nodes = out;
+    if (bvh->parents) ST_TRY(bvh2_compute_parents_device(ctx, bvh));  // update_parents (bvh2/mod.rs:492-494)
+    bvh->children_are_ordered_after_parents = true;                   // :498
+    return OBVHS_OK;
+}
 
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh) {
     if (bvh->node_count == 0) return OBVHS_OK;

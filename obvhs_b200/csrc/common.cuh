@@ -352,6 +352,7 @@ int radix_sort_pairs_u32(ObvhsContext* ctx, u32* keys, u32* keys_alt, u32* vals,
 int bvh2_compute_parents_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 int bvh2_compute_parents_into(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32* d_parents);
 int bvh2_refit_all_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
+int bvh2_reorder_in_stack_traversal_order_device(ObvhsContext* ctx, ObvhsBvh2* bvh);
 int bvh2_set_node_aabbs_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, const ObvhsAabb* d_aabbs, size_t n);
 // collapse.cu
 int bvh2_collapse_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 max_prims, float traversal_cost);
@@ -359,6 +360,7 @@ int bvh2_collapse_device(ObvhsContext* ctx, ObvhsBvh2* bvh, u32 max_prims, float
 int reinsertion_run_device(ObvhsContext* ctx, ObvhsBvh2* bvh, float ratio, const float* seq, size_t n_seq, u64* applied_out);
 int reinsertion_run_candidates_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const u32* d_node_ids, size_t n, u32 iterations, u64* applied_out);
 // cwbvh_build.cu
+int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsAabb* d_prim_aabbs, size_t n_prims, bool direct_layout);
 int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out,
                          bool include_exact_node_aabbs = false);
 // traverse.cu

@@ -717,6 +717,205 @@ if (a.exact && have && gl == 0) {  // exact_node_aabbs[node_index_bvh8] = *aabb 
     if (tid == 0) g->emitted = emitted;
 }
 
+// ---- CwBvh::order_children as a separate pass (src/cwbvh/mod.rs:520-735) -----------------------------------------------------
+// The reference loops `for i in 0..nodes.len() { order_node_children(i) }`. Node i only permutes its own eight slots and moves the
+// 80-byte records (and exact boxes) of its inner children inside its own range [child_base_idx, child_base_idx + inner_count); what
+// it reads of a child (p, e -- or the exact box -- for the centre) does not change when that child is reordered later, and a
+// parent always has a lower index than its children. So the sequential loop equals a top-down sweep level by level: one
+// cooperative launch, an 8-lane group per node (lane = old slot), a grid barrier per CWBVH level.
+struct OrderArgs {
+    uint4* nodes;
+    float4* exact;                // CwBvh::exact_node_aabbs or null
+    const float4* prim_aabbs;     // the primitives' boxes (Boundable::aabb), two float4 each
+    const u32* primitive_indices;
+    int direct_layout;
+    u32* queue[2];
+    u32* qcount;                  // [3]
+    u32* error;                   // 1: a child could not be assigned (non-finite centres): the reference asserts
+};
+constexpr int ORDER_THREADS = 256;
+__global__ void __launch_bounds__(ORDER_THREADS) cwbvh_order_children_kernel(OrderArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const u32 ngroups = nthreads >> 3, group = tid >> 3;
+    const int gl = threadIdx.x & 7, lane = threadIdx.x & 31, gbase = lane & ~7;
+    const u32 gmask = 0xffu << gbase;
+    __shared__ __align__(16) u32 s_img[(ORDER_THREADS / 8) * 20];
+    u32* img = s_img + (threadIdx.x >> 3) * 20;
+    if (tid == 0) {
+        a.queue[0][0] = 0;
+        a.qcount[0] = 1;
+        a.qcount[1] = a.qcount[2] = 0;
+    }
+    grid.sync();
+    for (u32 level = 0;; level++) {
+        const u32 n = __ldcg(&a.qcount[level % 3]);
+        if (n == 0) break;
+        const u32* q = a.queue[level & 1];
+        u32* qn = a.queue[(level + 1) & 1];
+        u32* qn_count = &a.qcount[(level + 1) % 3];
+        for (u32 t0 = (group & ~3u); t0 < n; t0 += ngroups) {  // warp-uniform trip count: the four groups of a warp stay in step
+            const u32 t = t0 + (group & 3u);
+            const bool have = t < n;
+            const u32 x = have ? __ldcg(q + t) : 0u;
+            const uint4 q0 = __ldcg(a.nodes + (size_t)x * 5), q1 = __ldcg(a.nodes + (size_t)x * 5 + 1);
+            const uint4 q2 = __ldcg(a.nodes + (size_t)x * 5 + 2), q3 = __ldcg(a.nodes + (size_t)x * 5 + 3), q4 = __ldcg(a.nodes + (size_t)x * 5 + 4);
+            const u32 imask = q0.w >> 24, child_base = q1.x, prim_base = q1.y;
+            const u32 meta = ((gl < 4 ? q1.z : q1.w) >> ((gl & 3) * 8)) & 0xffu;
+            const bool empty = !have || meta == 0;
+            const bool leaf = (imask & (1u << gl)) == 0;  // node.rs:279-281 (true for empty slots too)
+            const bool inner = !empty && !leaf;
+            // the node's own centre always comes from the compressed box (cwbvh/mod.rs:549), max = p + e * 255 (node.rs:261-265)
+            const float px = __uint_as_float(q0.x), py = __uint_as_float(q0.y), pz = __uint_as_float(q0.z);
+            const float ex = __uint_as_float((q0.w & 0xffu) << 23), ey = __uint_as_float(((q0.w >> 8) & 0xffu) << 23),
+                        ez = __uint_as_float(((q0.w >> 16) & 0xffu) << 23);
+            const float cx = ((px + ex * 255.0f) + px) * 0.5f, cy = ((py + ey * 255.0f) + py) * 0.5f, cz = ((pz + ez * 255.0f) + pz) * 0.5f;
+            // centre of this lane's child
+            u32 old_child_idx = 0;
+            float ccx = 0.f, ccy = 0.f, ccz = 0.f;
+            if (inner) {
+                const u32 slot_index = (meta & 31u) - 24u;  // node.rs:299-304
+                old_child_idx = child_base + __popc(imask & ~(0xffffffffu << slot_index));
+                float mnx, mny, mnz, mxx, mxy, mxz;
+                if (a.exact) {  // node_aabb(): the exact box when the tree carries them (cwbvh/mod.rs:737-745)
+                    const float4 lo = __ldcg(a.exact + 2 * (size_t)old_child_idx), hi = __ldcg(a.exact + 2 * (size_t)old_child_idx + 1);
+                    mnx = lo.x; mny = lo.y; mnz = lo.z; mxx = hi.x; mxy = hi.y; mxz = hi.z;
+                } else {
+                    const uint4 c0 = __ldcg(a.nodes + (size_t)old_child_idx * 5);
+                    mnx = __uint_as_float(c0.x); mny = __uint_as_float(c0.y); mnz = __uint_as_float(c0.z);
+                    mxx = mnx + __uint_as_float((c0.w & 0xffu) << 23) * 255.0f;
+                    mxy = mny + __uint_as_float(((c0.w >> 8) & 0xffu) << 23) * 255.0f;
+                    mxz = mnz + __uint_as_float(((c0.w >> 16) & 0xffu) << 23) * 255.0f;
+                }
+                ccx = (mxx + mnx) * 0.5f; ccy = (mxy + mny) * 0.5f; ccz = (mxz + mnz) * 0.5f;
+            } else if (!empty) {  // child_primitives (node.rs:290-295): union of the primitives' boxes, starting from Aabb::empty()
+                const u32 start = prim_base + (meta & 31u), count = __popc(meta & 0xe0u);
+                const float FMAX = 3.40282347e+38f;
+                Box b{FMAX, FMAX, FMAX, -FMAX, -FMAX, -FMAX};
+                for (u32 i = 0; i < count; i++) {
+                    u32 pi = start + i;
+                    if (!a.direct_layout) pi = __ldg(a.primitive_indices + pi);
+                    const float4 lo = __ldg(a.prim_aabbs + 2 * (size_t)pi), hi = __ldg(a.prim_aabbs + 2 * (size_t)pi + 1);
+                    b = box_union(b, Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
+                }
+                ccx = (b.maxx + b.minx) * 0.5f; ccy = (b.maxy + b.miny) * 0.5f; ccz = (b.maxz + b.minz) * 0.5f;
+            }
+            // cost table of this child (cwbvh/mod.rs:584-600) and the greedy assignment (:605-636): globally cheapest (child, slot)
+            // first, ties to the first in (child, slot) scan order, costs that are not < f32::MAX never assigned
+            float cost[8];
+            {
+                const float vx = ccx - cx, vy = ccy - cy, vz = ccz - cz;
+#pragma unroll
+                for (int sl = 0; sl < 8; sl++) {
+                    const float dx = (sl & 4) ? -1.0f : 1.0f, dy = (sl & 2) ? -1.0f : 1.0f, dz = (sl & 1) ? -1.0f : 1.0f;
+                    cost[sl] = (dx * vx + dy * vy) + dz * vz;
+                }
+            }
+            int my_slot = -1;
+            u32 filled = 0;
+#pragma unroll 1
+            for (int round = 0; round < 8; round++) {
+                float best_cost = 3.40282347e+38f;
+                int best_s = -1;
+                if (!empty && my_slot < 0) {
+#pragma unroll
+                    for (int sl = 0; sl < 8; sl++) {
+                        if (!(filled & (1u << sl)) && cost[sl] < best_cost) {
+                            best_cost = cost[sl];
+                            best_s = sl;
+                        }
+                    }
+                }
+                float wc = best_cost;
+                int wl = best_s >= 0 ? gl : 99, ws = best_s;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const float oc = __shfl_xor_sync(0xffffffffu, wc, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, wl, o), os = __shfl_xor_sync(0xffffffffu, ws, o);
+                    const bool take = (ol != 99) && (wl == 99 || oc < wc || (oc == wc && ol < wl));
+                    if (take) {
+                        wc = oc;
+                        wl = ol;
+                        ws = os;
+                    }
+                }
+                if (!__ballot_sync(0xffffffffu, wl != 99)) break;  // warp-uniform exit
+                if (wl != 99) {
+                    filled |= 1u << ws;
+                    if (wl == gl) my_slot = ws;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, !empty && my_slot < 0) & gmask) {
+                if (gl == 0) *a.error = 1;
+            }
+            const bool ok = !empty && my_slot >= 0;
+            const u32 new_imask = (__ballot_sync(0xffffffffu, ok && inner ? true : false) >> gbase) & 0xffu;  // by OLD lane; rebuilt by slot below
+            // imask by NEW slot: OR of (1 << my_slot) over the inner lanes of the group
+            u32 im = (ok && inner) ? (1u << my_slot) : 0u;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) im |= __shfl_xor_sync(0xffffffffu, im, o);
+            (void)new_imask;
+            // ---- the node's new 80-byte image (cwbvh/mod.rs:638-663)
+            // `let mut new_node = old_node` (:643): only imask and child_meta are cleared, so a slot left empty keeps the quantised
+            // bytes the OLD node had in that slot -- dead data to a traversal, but part of the bit-exact image
+            __syncwarp();
+            u8* ib = reinterpret_cast<u8*>(img);
+            if (have && gl == 0) {
+                uint4* iq = reinterpret_cast<uint4*>(img);
+                iq[0] = make_uint4(q0.x, q0.y, q0.z, (q0.w & 0x00ffffffu) | (im << 24));
+                iq[1] = make_uint4(child_base, prim_base, 0u, 0u);
+                iq[2] = q2;
+                iq[3] = q3;
+                iq[4] = q4;
+            }
+            __syncwarp();
+            if (ok) {
+                const int sh = (gl & 3) * 8;
+                ib[24 + my_slot] = inner ? (u8)((24u + (u32)my_slot) | 0x20u) : (u8)meta;
+                ib[32 + my_slot] = (u8)(((gl < 4 ? q2.x : q2.y) >> sh) & 0xffu);
+                ib[40 + my_slot] = (u8)(((gl < 4 ? q2.z : q2.w) >> sh) & 0xffu);
+                ib[48 + my_slot] = (u8)(((gl < 4 ? q3.x : q3.y) >> sh) & 0xffu);
+                ib[56 + my_slot] = (u8)(((gl < 4 ? q3.z : q3.w) >> sh) & 0xffu);
+                ib[64 + my_slot] = (u8)(((gl < 4 ? q4.x : q4.y) >> sh) & 0xffu);
+                ib[72 + my_slot] = (u8)(((gl < 4 ? q4.z : q4.w) >> sh) & 0xffu);
+            }
+            // ---- move the inner children's records (and exact boxes) to the index their new slot implies (:665-733)
+            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, c2 = c0, c3 = c0, c4 = c0;
+            float4 e0 = make_float4(0, 0, 0, 0), e1 = e0;
+            const bool mover = ok && inner;
+            if (mover) {
+                const uint4* src = a.nodes + (size_t)old_child_idx * 5;
+                c0 = __ldcg(src); c1 = __ldcg(src + 1); c2 = __ldcg(src + 2); c3 = __ldcg(src + 3); c4 = __ldcg(src + 4);
+                if (a.exact) {
+                    e0 = __ldcg(a.exact + 2 * (size_t)old_child_idx);
+                    e1 = __ldcg(a.exact + 2 * (size_t)old_child_idx + 1);
+                }
+            }
+            __syncwarp();  // every record of the range is in registers before any is overwritten
+            u32 new_child_idx = 0;
+            if (mover) {
+                new_child_idx = child_base + __popc(im & ~(0xffffffffu << my_slot));
+                uint4* dst = a.nodes + (size_t)new_child_idx * 5;
+                dst[0] = c0; dst[1] = c1; dst[2] = c2; dst[3] = c3; dst[4] = c4;
+                if (a.exact) {
+                    a.exact[2 * (size_t)new_child_idx] = e0;
+                    a.exact[2 * (size_t)new_child_idx + 1] = e1;
+                }
+            }
+            if (have && gl < 5) a.nodes[(size_t)x * 5 + gl] = reinterpret_cast<const uint4*>(img)[gl];
+            // ---- next level: this node's inner children (one queue reservation per warp)
+            const u32 movers = __ballot_sync(0xffffffffu, mover);
+            u32 wbase = 0;
+            if (lane == 0 && movers) wbase = atomicAdd(qn_count, (u32)__popc(movers));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (mover) qn[wbase + __popc(movers & ((1u << lane) - 1u))] = new_child_idx;
+            __syncwarp();
+        }
+        if (tid == 0) a.qcount[(level + 2) % 3] = 0;
+        grid.sync();
+    }
+}
+
 // vec![Aabb::empty(); bvh2.nodes.len()] (bvh2_to_cwbvh.rs:60-62; aabb.rs:166-171)
 __global__ void fill_empty_aabbs_kernel(float4* out, u32 n) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -848,5 +1047,45 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     guard.b = nullptr;
     *out = cw;
+    return OBVHS_OK;
+}
+
+// CwBvh::order_children(&mut self, primitives, direct_layout) (src/cwbvh/mod.rs:520-524) with the primitives given as their AABBs
+int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsAabb* d_prim_aabbs, size_t n_prims, bool direct_layout) {
+    if (bvh->node_count == 0) return OBVHS_OK;
+    (void)n_prims;
+    cudaStream_t s = ctx->stream;
+    DevBuf<u32> q0, q1, qcount;
+    CU_TRY(ctx, q0.alloc(bvh->node_count, s));
+    CU_TRY(ctx, q1.alloc(bvh->node_count, s));
+    CU_TRY(ctx, qcount.alloc(4, s));
+    CU_TRY(ctx, cudaMemsetAsync(qcount.p, 0, 16, s));
+    OrderArgs a;
+    a.nodes = reinterpret_cast<uint4*>(bvh->nodes);
+    a.exact = reinterpret_cast<float4*>(bvh->exact_node_aabbs);
+    a.prim_aabbs = reinterpret_cast<const float4*>(d_prim_aabbs);
+    a.primitive_indices = bvh->primitive_indices;
+    a.direct_layout = direct_layout ? 1 : 0;
+    a.queue[0] = q0.p;
+    a.queue[1] = q1.p;
+    a.qcount = qcount.p;
+    a.error = qcount.p + 3;
+    static PerDevice<int> per_sm_dev;
+    int& per_sm = per_sm_dev[ctx->device];
+    if (per_sm == 0) {
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_order_children_kernel, ORDER_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(bvh->node_count * 8, ORDER_THREADS)));
+    void* args[] = {&a};
+    CU_TRY(ctx, cudaLaunchCooperativeKernel((void*)cwbvh_order_children_kernel, dim3(blocks), dim3(ORDER_THREADS), args, 0, s));
+    KERNEL_CHECK(ctx);
+    u32* h = reinterpret_cast<u32*>(ctx->pinned);
+    CU_TRY(ctx, cudaMemcpyAsync(h, qcount.p + 3, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (h[0] != 0) {
+        OBVHS_SET_ERR(ctx, "order_children: a child could not be assigned to a slot (non-finite boxes? the reference asserts here)");
+        return OBVHS_ERR_NAN_INPUT;
+    }
     return OBVHS_OK;
 }

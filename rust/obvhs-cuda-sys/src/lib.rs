@@ -1,7 +1,7 @@
 //! Raw bindings to `libobvhs_cuda` (`include/obvhs_cuda.h`): the B200 (sm_100a) implementation of obvhs' data-parallel hot path
 //! -- PLOC BVH2 build, parallel reinsertion, BVH2 -> CWBVH collapse, CWBVH / BVH2 ray traversal, broad-phase queries -- plus the
-//! NCCL broadcast of a finished tree. **Written but NOT compiled in the build image (no rustc/cargo)**; generated from the header by
-//! the script in `tests/test_rust_shim.py`'s docstring, which also checks that every C symbol is declared here with the same arity.
+//! NCCL broadcast of a finished tree. **Written but NOT compiled in the build image (no rustc/cargo)**; the `extern "C"` block is generated from the header by
+//! `scripts/gen_rust_sys.py`, and `tests/test_rust_shim.py` checks that every C symbol is declared here with the same arity.
 //!
 //! POD layouts are byte-identical to the `#[repr(C)]` types of obvhs 0.3.1 they mirror (sizes asserted below and, on the C side, in
 //! `obvhs_b200/csrc/common.cuh`): inside the obvhs crate these structs are replaced by `crate::{aabb::Aabb, triangle::Triangle,
@@ -215,6 +215,7 @@ extern "C" {
     ) -> c_int;
     pub fn obvhs_cuda_bvh2_compute_parents(ctx: *mut Context, bvh: *mut Bvh2) -> c_int;
     pub fn obvhs_cuda_bvh2_refit_all(ctx: *mut Context, bvh: *mut Bvh2) -> c_int;
+    pub fn obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ctx: *mut Context, bvh: *mut Bvh2) -> c_int;
     pub fn obvhs_cuda_bvh2_set_leaf_aabbs(ctx: *mut Context, bvh: *mut Bvh2, prim_aabbs: *const Aabb, n: usize) -> c_int;
     pub fn obvhs_cuda_reinsertion_run(
         ctx: *mut Context,
@@ -295,6 +296,13 @@ extern "C" {
         count: *mut usize,
     ) -> c_int;
     pub fn obvhs_cuda_cwbvh_compute_parents(ctx: *mut Context, bvh: *const CwBvh, parents: *mut u32) -> c_int;
+    pub fn obvhs_cuda_cwbvh_order_children(
+        ctx: *mut Context,
+        bvh: *mut CwBvh,
+        prim_aabbs: *const Aabb,
+        n: usize,
+        direct_layout: c_int,
+    ) -> c_int;
     pub fn obvhs_cuda_build_cwbvh_from_tris(
         ctx: *mut Context,
         tris: *const Triangle,

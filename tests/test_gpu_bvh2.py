@@ -215,3 +215,53 @@ def test_build_over_aabbs_equals_component_calls(api, scenes):
         a = api.build_bvh2(aabbs, p).download()
         b = api.build_bvh2_from_tris(tris, p).download()
         assert_nodes_equal(a[0], b[0], preset)
+
+
+@pytest.mark.parametrize("scene", ["terrain32", "soup4k", "kitchen"])
+@pytest.mark.parametrize("with_parents", [False, True])
+def test_reorder_in_stack_traversal_order_bit_exact(api, scenes, scene, with_parents):
+    # the reference's test_reinsertion sequence (bvh2/reinsertion.rs:394-436): VeryLow PLOC, run(0.25),
+    # reorder_in_stack_traversal_order (bvh2/mod.rs:462-500), run(0.5) -- every step bit-exact against the oracle, and the
+    # reordered tree validates with parents before children
+    aabbs = ob.tri_aabbs(scenes[scene])
+    want = ob.ploc_build(aabbs, None, 2, 64, 0)
+    got = api.PlocBuilder().build(2, aabbs, None, 64, 0)
+    if with_parents:
+        want.compute_parents()
+        got.compute_parents()
+    want.reinsertion_run(0.25)
+    api.ReinsertionOptimizer().run(got, 0.25)
+    want.reorder_in_stack_traversal_order()
+    got.reorder_in_stack_traversal_order()
+    assert got.children_are_ordered_after_parents
+    gn, gp, gpar = got.download(with_parents=True)
+    wn, wp, wpar = want.get(with_parents=True)
+    assert_nodes_equal(gn, wn, f"{scene} after reorder")
+    assert np.array_equal(gp, wp) and np.array_equal(gpar[1:], wpar[1:])
+    inner = gn["prim_count"] == 0
+    assert np.all(gn["first_index"][inner] > np.nonzero(inner)[0])  # children after parents
+    rc, msg = ob.bvh2_from(gn, gp, want.max_depth).validate(aabbs)
+    assert rc == 0, msg
+    want.reinsertion_run(0.5)
+    api.ReinsertionOptimizer().run(got, 0.5)
+    assert_nodes_equal(got.download()[0], want.get()[0], f"{scene} reinsertion after reorder")
+
+
+def test_reorder_degenerate_and_deep(api):
+    from test_gpu_parity import graded_boxes
+
+    for n in (1, 2, 3):
+        aabbs = graded_boxes(n, 0.05)
+        got = api.PlocBuilder().build(6, aabbs, None, 64, 2)
+        want = ob.ploc_build(aabbs, None, 6, 64, 2)
+        got.reorder_in_stack_traversal_order()
+        want.reorder_in_stack_traversal_order()
+        assert_nodes_equal(got.download()[0], want.get()[0], f"{n} leaves")
+    aabbs = graded_boxes(2000, 0.005)  # a chain ~1000 levels deep: one grid barrier per level
+    got = api.PlocBuilder().build(6, aabbs, None, 64, 2)
+    want = ob.ploc_build(aabbs, None, 6, 64, 2)
+    api.ReinsertionOptimizer().run(got, 0.3)
+    want.reinsertion_run(0.3)
+    got.reorder_in_stack_traversal_order()
+    want.reorder_in_stack_traversal_order()
+    assert_nodes_equal(got.download()[0], want.get()[0], "deep chain")

@@ -747,3 +747,41 @@ def test_deep_trees_reinsertion_and_builders(api, n, g):
         c = api.build_cwbvh(aabbs, api.BvhBuildParams.preset(preset)).download()
         assert c[0].tobytes() == w[0].tobytes(), preset
         assert np.array_equal(c[1], w[1])
+
+
+@pytest.mark.parametrize("scene", ["cornell", "ico_plane", "terrain32", "soup4k", "kitchen"])
+@pytest.mark.parametrize("exact", [False, True])
+def test_cwbvh_order_children_bit_exact(api, scenes, scene, exact):
+    # CwBvh::order_children as a separate pass (cwbvh/mod.rs:520-735; the reference's order_children_cwbvh test, tests/mod.rs:351-385):
+    # node bytes (and exact boxes) equal to the oracle's sequential loop, for both primitive layouts; hits unchanged
+    tris = scenes[scene]
+    aabbs = ob.tri_aabbs(tris)
+    for direct in (False, True):
+        wb = ob.ploc_build(aabbs, None, 6, 64, 2)
+        wb.reinsertion_run(0.02)
+        w = wb.to_cwbvh(3, False, exact)  # built WITHOUT the converter's ordering, so that the pass has work to do
+        gb = api.PlocBuilder().build(6, aabbs, None, 64, 2)
+        api.ReinsertionOptimizer().run(gb, 0.02)
+        g = api.bvh2_to_cwbvh(gb, 3, False, exact)
+        assert g.download()[0].tobytes() == w.get()[0].tobytes()
+        prims = w.get()[1]
+        pa = aabbs[prims] if direct else aabbs
+        g.set_triangles(tris)
+        rays = rays_for(tris)
+        before = g.ray_traverse(rays)
+        w.order_children(pa, direct)
+        g.order_children(pa, direct)
+        gn, gp, _ = g.download()
+        wn, wp, _ = w.get()
+        assert gn.tobytes() == wn.tobytes(), f"{scene} direct={direct} exact={exact}"
+        assert np.array_equal(gp, wp)
+        if exact:
+            assert np.array_equal(g.exact_node_aabbs()[:, [0, 1, 2, 4, 5, 6]], w.exact_node_aabbs()[:, [0, 1, 2, 4, 5, 6]])
+        after = g.ray_traverse(rays)
+        assert np.array_equal(after["primitive_id"], before["primitive_id"]) and np.array_equal(after["t"].view(np.uint32), before["t"].view(np.uint32))
+        rc, msg = ob.cwbvh_from(gn, gp, g.total_aabb()).validate(aabbs)
+        assert rc == 0, msg
+        # a second pass over an already ordered tree is deterministic as well
+        w.order_children(pa, direct)
+        g.order_children(pa, direct)
+        assert g.download()[0].tobytes() == w.get()[0].tobytes()
