@@ -18,6 +18,7 @@ be produced in this image) on a bounded sample of the same workloads.
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -732,6 +733,120 @@ def run_cornell(args):
         raise SystemExit("bench.py: parity check failed (see `parity` in the JSON line)")
 
 
+def run_passes(args):
+    """--workload passes: the two layout passes next to the hot path, each timed on the device with the oracle's
+    sequential loop timed beside it and byte-compared: `Bvh2::reorder_in_stack_traversal_order` (src/bvh2/mod.rs:462-500) and
+    `CwBvh::order_children` as a separate pass (src/cwbvh/mod.rs:520-735) on a tree converted WITHOUT ordering. One GPU."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+
+    import oracle_bind as ob  # the checker and the CPU leg only
+    from obvhs_b200 import api, camera, test_util as tu
+    from obvhs_b200.types import ray_args_of
+
+    e = setup_env(args) if int(os.environ.get("WORLD_SIZE", "1")) == 1 else None
+    if e is None:
+        raise SystemExit("--workload passes is a one-GPU measurement (run it without torchrun)")
+    res = S3_RES if args.tris == 10_000_000 else int(round((args.tris / 2) ** 0.5))
+    scenes = [("kitchen", tu.kitchen(), camera.kitchen_camera(1920)), (f"demoscene({res},0)", cached_demoscene(res), camera.demoscene_camera(1280))]
+    params = api.BvhBuildParams.fast_build()
+    single = dataclasses.replace(params, max_prims_per_leaf=1)
+    out = {}
+
+    def timed_ms(fn):
+        with torch.cuda.stream(e.stream):
+            e.flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(e.stream)
+            r = fn()
+            b.record(e.stream)
+        e.stream.synchronize()
+        return a.elapsed_time(b), r
+
+    for name, tris, cam in scenes:
+        n = tris.shape[0]
+        with torch.cuda.stream(e.stream):
+            d_tris = torch.from_numpy(tris).to(e.dev)
+            v = d_tris.view(n, 3, 4)[:, :, :3]
+            d_aabbs = torch.zeros((n, 8), dtype=torch.float32, device=e.dev)
+            d_aabbs[:, 0:3] = v.amin(1)
+            d_aabbs[:, 4:7] = v.amax(1)
+            d_rays = torch.from_numpy(ray_args_of(camera.primary_rays(cam))).to(e.dev)
+            n_rays = d_rays.shape[0]
+            d_hits = torch.empty((n_rays, 4), dtype=torch.int32, device=e.dev)
+        e.stream.synchronize()
+        aabbs = d_aabbs.cpu().numpy()
+        steps = max(1, min(args.steps, 5))
+
+        def t_hash():
+            return int((d_hits[:, 3].to(torch.int64) & 0xFFFFFFFF).sum().item())
+
+        # ---- Bvh2::reorder_in_stack_traversal_order
+        ms, trav_before, trav_after = [], [], []
+        for it in range(steps):
+            with torch.cuda.stream(e.stream):
+                b2 = api.build_bvh2_from_tris(d_tris, params, ctx=e.ctx)
+            if it == 0:
+                before_nodes, before_prims = b2.download()
+                depth = b2.max_depth
+            trav_before.append(timed_ms(lambda: b2.ray_traverse(d_rays, out=d_hits))[0])
+            h0 = t_hash()
+            ms.append(timed_ms(b2.reorder_in_stack_traversal_order)[0])
+            trav_after.append(timed_ms(lambda: b2.ray_traverse(d_rays, out=d_hits))[0])
+            h1 = t_hash()
+        got_nodes, got_prims = b2.download()
+        w = ob.bvh2_from(before_nodes, before_prims, depth)
+        t0 = time.perf_counter()
+        w.reorder_in_stack_traversal_order()
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        wn, wp = w.get()
+        nodes2 = int(got_nodes.shape[0])
+        reorder = {"ms": float(np.mean(ms)), "nodes": nodes2, "Mnodes_per_s": nodes2 / float(np.mean(ms)) / 1e3,
+                   "algorithmic_bytes": nodes2 * (48 + 48 + 4 + 4 + 4), "gbs": nodes2 * 108 / float(np.mean(ms)) / 1e6,
+                   "cpu_oracle_ms": cpu_ms, "bit_exact_vs_oracle": bool(got_nodes.tobytes() == wn.tobytes() and np.array_equal(got_prims, wp)),
+                   "bvh2_traverse_ms_before": float(np.mean(trav_before)), "bvh2_traverse_ms_after": float(np.mean(trav_after)),
+                   "closest_t_unchanged": bool(h0 == h1), "rays": n_rays}
+        del b2, w, wn, wp, got_nodes, before_nodes
+        # ---- CwBvh::order_children on a tree converted without the converter's ordering
+        ms, trav_unordered, trav_ordered = [], [], []
+        for it in range(steps):
+            with torch.cuda.stream(e.stream):
+                b2 = api.build_bvh2_from_tris(d_tris, single, ctx=e.ctx)  # the converter wants one primitive per Bvh2 leaf (bvh2_to_cwbvh.rs:201)
+                cw = api.bvh2_to_cwbvh(b2, 3, False, False)
+                cw.set_triangles(d_tris)
+            if it == 0:
+                u_nodes, u_prims, _ = cw.download()
+                total = cw.total_aabb()
+            trav_unordered.append(timed_ms(lambda: cw.ray_traverse(d_rays, out=d_hits))[0])
+            h0 = t_hash()
+            ms.append(timed_ms(lambda: cw.order_children(d_aabbs, False))[0])
+            trav_ordered.append(timed_ms(lambda: cw.ray_traverse(d_rays, out=d_hits))[0])
+            h1 = t_hash()
+        g_nodes, g_prims, _ = cw.download()
+        w = ob.cwbvh_from(u_nodes, u_prims, total)
+        t0 = time.perf_counter()
+        w.order_children(aabbs, False)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        wn, wp, _ = w.get()
+        nn = int(g_nodes.shape[0])
+        order = {"ms": float(np.mean(ms)), "nodes": nn, "Mnodes_per_s": nn / float(np.mean(ms)) / 1e3,
+                 "cpu_oracle_ms": cpu_ms, "bit_exact_vs_oracle": bool(g_nodes.tobytes() == wn.tobytes() and np.array_equal(g_prims, wp)),
+                 "cwbvh_traverse_ms_unordered": float(np.mean(trav_unordered)), "cwbvh_traverse_ms_ordered": float(np.mean(trav_ordered)),
+                 "closest_t_unchanged": bool(h0 == h1), "rays": n_rays}
+        out[name] = {"tris": int(n), "reorder_in_stack_traversal_order": reorder, "order_children": order}
+        del b2, cw, w, d_tris, d_aabbs, d_rays, d_hits
+        torch.cuda.empty_cache()
+    ok = all(s[k]["bit_exact_vs_oracle"] and s[k]["closest_t_unchanged"] for s in out.values() for k in ("reorder_in_stack_traversal_order", "order_children"))
+    print(json.dumps({"metric": "layout_pass_ms", "unit": "ms", "higher_is_better": False, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "dtype": "u8/f32", "data": "kitchen.obj fixture; synthetic demoscene terrain", "preset": "fast_build",
+                      "timing": "CUDA events on the context's stream, L2 flushed before every timed call, mean of the steps; the CPU figure is the "
+                                "oracle's single-threaded sequential loop on this box (the reference's passes are single-threaded)",
+                      "scenes": out, "parity_ok": ok}))
+    if not ok:
+        raise SystemExit("bench.py: layout pass parity failed")
+
+
 def run_headline_reference(args):
     """--impl reference for the headline: the CPU restatement on a bounded sample of both workloads, same `config`."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -1383,7 +1498,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s3", choices=["s3", "cornell", "kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene"])
+    ap.add_argument("--workload", default="s3", choices=["s3", "cornell", "kitchen", "soup", "terrain", "bounce", "dynamic", "demoscene", "passes"])
     ap.add_argument("--frames", type=int, default=100, help="distinct frames of the dynamic workload (SURVEY.md 8d S4: 100)")
     ap.add_argument("--rays", type=int, default=S3_RAYS, help="size of the headline's global bounce-ray set")
     ap.add_argument("--parity-rays", type=int, default=262_144, help="rays of the in-run oracle comparison")
@@ -1401,6 +1516,8 @@ def main():
         run_dynamic(args)
     elif args.workload == "demoscene":
         run_demoscene(args)
+    elif args.workload == "passes":
+        run_passes(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

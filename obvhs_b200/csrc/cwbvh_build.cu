@@ -1040,7 +1040,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
             fprintf(stderr, "[obvhs trace]     emit level %2u: %8u nodes %9.1f us\n", l, hg->level_len[l], (hg->level_ns[l + 1] - hg->level_ns[l]) * 1e-3);
     }
     if (h[0] != 0 || h[4] != M) {
-        OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: %s (emitted %u of %u nodes; non-finite AABBs? the reference panics here)",
+        OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: %s (emitted %u of %u nodes; non-finite AABBs, or Bvh2 leaves holding more than one primitive -- bvh2_to_cwbvh.rs:201 wants the uncollapsed tree? the reference panics here)",
                       h[0] == 2 ? "order_children left a child unassigned" : h[0] == 3 ? "node count mismatch" : "invalid decision on the emit path",
                       h[4], M);
         return OBVHS_ERR_NAN_INPUT;
