@@ -95,55 +95,97 @@ struct HeapFindStack {
 };
 
 // K9: reinsertion.rs:233-334. Stack pushes saturate at the last slot and pop_fast saturates at 0 (faststack.rs:299-310).
-// Nodes are read through L2 (ld.global.cg): they are rewritten by the apply phase of the previous round of the same launch.
+// The reads of pivot level k+1 (sibling node, pivot node, the pivot's parent index) are issued at the start of level k: their
+// addresses are known one level ahead, the tree is read-only in this phase, and the values are consumed only where the reference
+// reads them. The first stack entry of a level (always the sibling) skips the push/pop round trip through the stack.
+// -DOBVHS_FIND_DEBUG (build.build_variant) adds per-round search statistics to the OBVHS_TRACE print-out.
+#ifdef OBVHS_FIND_DEBUG
+#define FIND_DBG(...) __VA_ARGS__
+#else
+#define FIND_DBG(...)
+#endif
 template <bool NC, class Stack>
 __device__ __forceinline__ void find_reinsertion(const Node32* nodes, const u32* parents, u32 node_id, Stack& stk, u32& out_from, u32& out_to,
-                                                 float& out_diff) {
+                                                 float& out_diff FIND_DBG(, u32& dbg_visits, u32& dbg_pops, u32& dbg_load_cycles, u32& dbg_get_cycles)) {
     const u32 cap1 = stk.cap() - 1u;
     u32 sp = 0;
     u32 best_to = 0;
     float best_diff = 0.0f;
+    const u32 parent_id = NC ? __ldg(parents + node_id) : parents[node_id];
     const Node32 self = find_load_node<NC>(nodes, node_id);
+    u32 sib = sibling_id(node_id);
+    Node32 sib_node = find_load_node<NC>(nodes, sib);
+    Node32 piv_node = find_load_node<NC>(nodes, parent_id);
+    u32 next_pivot = NC ? __ldg(parents + parent_id) : parents[parent_id];
     const Box aabb = node_box(self);
     const float node_area = box_half_area(aabb);
-    const u32 parent_id = NC ? __ldg(parents + node_id) : parents[node_id];
-    const float parent_area = box_half_area(node_box(find_load_node<NC>(nodes, parent_id)));
-    float area_diff = parent_area;
-    u32 sib = sibling_id(node_id);
-    Box pivot_bbox = node_box(find_load_node<NC>(nodes, sib));
+    float area_diff = box_half_area(node_box(piv_node));  // parent_area
+    Box pivot_bbox = node_box(sib_node);
     u32 pivot_id = parent_id;
+    // ONE flat loop: an iteration either pops an entry (skipping pruned ones) or moves to the next pivot and takes that level's
+    // first entry. The reference's two nested loops, run by 32 lanes with 32 different searches, cost the warp the SUM over the
+    // levels of the longest subtree search at that level (lanes wait at the end of every inner loop); flat, it costs the longest
+    // lane's own total: find of round 0 383 -> 282 us at 10 M triangles, 111 -> 82 us on the kitchen. The late rounds (a few dozen
+    // searches of <= 17 visits / 32 pops / 9 levels) stay at ~15 us = ~45 iterations x ~650 cycles of dependent instructions of a
+    // lone warp; node loads are ~105 cycles of that (OBVHS_FIND_DEBUG). Requesting the child popped next (first_index + 1) at push
+    // time changed nothing there and cost round 0 at 10 M a third (282 -> 377 us: half of those reads are pruned at the pop).
+    Node32 n_sib = sib_node, n_piv = piv_node;
+    u32 n_next = 0;
+    bool started = false;
     for (;;) {
-        stk.put(sp, area_diff, sib);
-        sp = min(sp + 1u, cap1);
-        while (sp != 0) {
-            sp = sp - 1;
-            float top_area_diff;
-            u32 top_sibling_id;
-            stk.get(sp, top_area_diff, top_sibling_id);
-            if (top_area_diff - node_area <= best_diff) continue;
-            const Node32 dst = find_load_node<NC>(nodes, top_sibling_id);
-            const Box dbox = node_box(dst);
-            float merged_area = box_half_area(box_union(dbox, aabb));
-            float reinsert_area = top_area_diff - merged_area;
-            if (reinsert_area > best_diff) {
-                best_to = top_sibling_id;
-                best_diff = reinsert_area;
+        float top_area_diff;
+        u32 top_sibling_id;
+        bool first = false, have;
+        if (sp == 0) {
+            if (started) {  // the level's stack ran empty: reinsertion.rs:315-326
+                if (pivot_id != parent_id) {
+                    pivot_bbox = box_union(pivot_bbox, node_box(sib_node));
+                    area_diff += box_half_area(node_box(piv_node)) - box_half_area(pivot_bbox);
+                }
+                if (pivot_id == 0) break;
+                sib = sibling_id(pivot_id);
+                pivot_id = next_pivot;
+                sib_node = n_sib;
+                piv_node = n_piv;
+                next_pivot = n_next;
             }
-            if (dst.prim_count == 0) {
-                float child_area = reinsert_area + box_half_area(dbox);
-                stk.put(sp, child_area, dst.first_index);
-                sp = min(sp + 1u, cap1);
-                stk.put(sp, child_area, dst.first_index + 1);
-                sp = min(sp + 1u, cap1);
+            started = true;
+            if (pivot_id != 0) {  // the reads of the level after this one
+                n_sib = find_load_node<NC>(nodes, sibling_id(pivot_id));
+                n_piv = find_load_node<NC>(nodes, next_pivot);
+                n_next = NC ? __ldg(parents + next_pivot) : parents[next_pivot];
             }
+            top_area_diff = area_diff;  // stack.push((area_diff, sibling_id)) + the pop that follows it
+            top_sibling_id = sib;
+            first = true;
+            have = !(top_area_diff - node_area <= best_diff);
+        } else {
+            do {
+                sp = sp - 1;
+                stk.get(sp, top_area_diff, top_sibling_id);
+                FIND_DBG(dbg_pops++;)
+                have = !(top_area_diff - node_area <= best_diff);
+            } while (!have && sp != 0);
         }
-        if (pivot_id != parent_id) {
-            pivot_bbox = box_union(pivot_bbox, node_box(find_load_node<NC>(nodes, sib)));
-            area_diff += box_half_area(node_box(find_load_node<NC>(nodes, pivot_id))) - box_half_area(pivot_bbox);
+        if (!have) continue;
+        FIND_DBG(dbg_visits++;)
+        FIND_DBG(long long l0; asm volatile("mov.u64 %0, %%clock64;" : "=l"(l0));)
+        const Node32 dst = first ? sib_node : find_load_node<NC>(nodes, top_sibling_id);
+        FIND_DBG(long long l1; asm volatile("mov.u64 %0, %%clock64;" : "=l"(l1) : "f"(dst.minx), "f"(dst.maxx)); dbg_load_cycles += (u32)(l1 - l0);)
+        const Box dbox = node_box(dst);
+        float merged_area = box_half_area(box_union(dbox, aabb));
+        float reinsert_area = top_area_diff - merged_area;
+        if (reinsert_area > best_diff) {
+            best_to = top_sibling_id;
+            best_diff = reinsert_area;
         }
-        if (pivot_id == 0) break;
-        sib = sibling_id(pivot_id);
-        pivot_id = NC ? __ldg(parents + pivot_id) : parents[pivot_id];
+        if (dst.prim_count == 0) {
+            float child_area = reinsert_area + box_half_area(dbox);
+            stk.put(sp, child_area, dst.first_index);
+            sp = min(sp + 1u, cap1);
+            stk.put(sp, child_area, dst.first_index + 1);
+            sp = min(sp + 1u, cap1);
+        }
     }
     u32 from = node_id;
     if (best_to == sibling_id(from) || best_to == parent_id) {  // reinsertion.rs:328-333 -> Reinsertion::default()
@@ -193,6 +235,7 @@ struct RunArgs {
     u32* mark;             // per node, == round_stamp when on a dirty path
     u32* pending;          // per node, arrivals still due before the node can be refit
     unsigned long long* trace_ns;  // OBVHS_TRACE: globaltimer of block 0 at the end of each phase, 10 per round (or null)
+    unsigned long long* find_dbg;  // -DOBVHS_FIND_DEBUG builds: per round {max cycles, sum cycles, max visits, max pops} of one search
     float* heap_area;      // find_reinsertion stacks for max_depth > 96 (null: local memory)
     u32* heap_id;
     u32 heap_cap;
@@ -567,10 +610,32 @@ __global__ void __launch_bounds__(RUN_THREADS, MIN_CTAS) reinsertion_run_kernel(
             if (a.heap_area) {
                 HeapFindStack stk{a.heap_area + (size_t)blockIdx.x * blockDim.x + threadIdx.x, a.heap_id + (size_t)blockIdx.x * blockDim.x + threadIdx.x,
                                   gridDim.x * blockDim.x, a.heap_cap};
+#ifdef OBVHS_FIND_DEBUG
+                u32 dv = 0, dp = 0, dl = 0, dg = 0;
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, dv, dp, dl, dg);
+#else
                 find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+#endif
             } else {
                 LocalFindStack stk;
+#ifdef OBVHS_FIND_DEBUG
+                u32 dv = 0, dp = 0, dl = 0, dg = 0;
+                const long long c0 = clock64();
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, dv, dp, dl, dg);
+                const unsigned long long dc = (unsigned long long)(clock64() - c0);
+                if (a.find_dbg) {
+                    atomicMax(a.find_dbg + round * 8, dc);
+                    atomicAdd(a.find_dbg + round * 8 + 1, dc);
+                    atomicMax(a.find_dbg + round * 8 + 2, (unsigned long long)dv);
+                    atomicMax(a.find_dbg + round * 8 + 3, (unsigned long long)dp);
+                    atomicAdd(a.find_dbg + round * 8 + 4, (unsigned long long)dv);
+                    atomicAdd(a.find_dbg + round * 8 + 5, (unsigned long long)dp);
+                    atomicAdd(a.find_dbg + round * 8 + 6, (unsigned long long)dl);
+                    atomicAdd(a.find_dbg + round * 8 + 7, (unsigned long long)dg);
+                }
+#else
                 find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+#endif
             }
             a.r_from[j] = from;
             a.r_to[j] = to;
@@ -656,12 +721,16 @@ static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<Rou
     DevBuf<RoundPlan> d_plan;
     DevBuf<u32> ckeys, ckeys_alt, cvals, cvals_alt, gkeys, gkeys_alt, gvals, gvals_alt, scratch, rbar, r_from, r_to, cells, status, und0, und1, touched, mark, pending, heap_id;
     DevBuf<float> r_diff, heap_area;
-    DevBuf<unsigned long long> reserve, trace_ns;
+    DevBuf<unsigned long long> reserve, trace_ns, find_dbg;
     DevBuf<ReinsertState> st;
     const size_t n_rounds = plan.size();
     if (ctx->trace) {
         CU_TRY(ctx, trace_ns.alloc(n_rounds * 10, s));
         CU_TRY(ctx, cudaMemsetAsync(trace_ns.p, 0, n_rounds * 80, s));
+#ifdef OBVHS_FIND_DEBUG
+        CU_TRY(ctx, find_dbg.alloc(n_rounds * 8, s));
+        CU_TRY(ctx, cudaMemsetAsync(find_dbg.p, 0, n_rounds * 64, s));
+#endif
     }
     CU_TRY(ctx, d_plan.alloc(n_rounds, s));
     if (!fixed) {
@@ -707,6 +776,7 @@ static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<Rou
     a.r_from = r_from.p; a.r_to = r_to.p; a.r_diff = r_diff.p; a.cells = cells.p; a.status = status.p; a.und_list[0] = und0.p; a.und_list[1] = und1.p; a.st = st.p;
     a.touched = touched.p; a.reserve = reserve.p; a.mark = mark.p; a.pending = pending.p;
     a.trace_ns = ctx->trace ? trace_ns.p : nullptr;
+    a.find_dbg = find_dbg.p;
     a.heap_area = heap ? heap_area.p : nullptr; a.heap_id = heap ? heap_id.p : nullptr; a.heap_cap = (u32)heap_cap;
     void* args[] = {&a};
     CU_TRY(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(RUN_THREADS), args, smem, s));
@@ -728,6 +798,16 @@ static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<Rou
             }
             fprintf(stderr, " us\n");
         }
+#ifdef OBVHS_FIND_DEBUG
+        std::vector<unsigned long long> fd(n_rounds * 8);
+        CU_TRY(ctx, cudaMemcpy(fd.data(), find_dbg.p, n_rounds * 64, cudaMemcpyDeviceToHost));
+        for (size_t r = 0; r < n_rounds; r++) {
+            const unsigned long long* f = &fd[r * 8];
+            const double c = plan[r].count;
+            fprintf(stderr, "[obvhs trace]     find %2zu: longest search %llu cycles, mean %.0f; visits max %llu mean %.1f; pops max %llu mean %.1f; per visit: node load %.0f cycles; per pop: stack get %.0f cycles\n",
+                    r, f[0], f[1] / c, f[2], f[4] / c, f[3], f[5] / c, (double)f[6] / (double)(f[4] ? f[4] : 1), (double)f[7] / (double)(f[5] ? f[5] : 1));
+        }
+#endif
     }
     if (h->error) {
         OBVHS_SET_ERR(ctx, "reinsertion: conflict resolution did not converge");
