@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <array>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -91,6 +92,17 @@ public:
         if (rc != OBVHS_OK) throw Error(rc, obvhs_cuda_last_error(h_.get()));
     }
     void synchronize() const { check(obvhs_cuda_synchronize(h_.get())); }
+    // Multi-GPU (one process per GPU; no equivalent in the reference, whose CwBvh is cloned freely): `nccl_unique_id` on one rank,
+    // the 128 bytes shipped to the others by the caller, then `comm_init` on every rank (collective). See CwBvh::broadcast.
+    static std::array<uint8_t, OBVHS_NCCL_UNIQUE_ID_BYTES> nccl_unique_id() {
+        std::array<uint8_t, OBVHS_NCCL_UNIQUE_ID_BYTES> id{};
+        int rc = obvhs_cuda_nccl_unique_id(id.data());
+        if (rc != OBVHS_OK) throw Error(rc, "obvhs_cuda_nccl_unique_id failed (libnccl.so.2 not loadable?)");
+        return id;
+    }
+    void comm_init(const std::array<uint8_t, OBVHS_NCCL_UNIQUE_ID_BYTES>& id, int rank, int world) const {
+        check(obvhs_cuda_comm_init(h_.get(), id.data(), rank, world));
+    }
     uint64_t launch_count() const { return obvhs_cuda_launch_count(h_.get()); }
     // "traverse": auto | static | persistent[:refill[:chunk]]; "host_slice": rays per pipelined slice; "trace": 0 | 1
     void set_option(const char* key, const char* value) const {
@@ -148,6 +160,8 @@ public:
                                             primitive_indices ? primitive_indices->data() : nullptr, parents ? parents->data() : nullptr));
     }
     void compute_parents() { ctx_.check(obvhs_cuda_bvh2_compute_parents(ctx_.get(), h_.get())); }  // src/bvh2/mod.rs:586-619
+    // Bvh2::reorder_in_stack_traversal_order, src/bvh2/mod.rs:462-500
+    void reorder_in_stack_traversal_order() { ctx_.check(obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ctx_.get(), h_.get())); }
     void refit_all() { ctx_.check(obvhs_cuda_bvh2_refit_all(ctx_.get(), h_.get())); }              // src/bvh2/mod.rs:527-569
     // rewrites every leaf box from per-primitive boxes and refits (the update loop of examples/physics.rs)
     void set_leaf_aabbs(const Aabb* prim_aabbs, size_t n) { ctx_.check(obvhs_cuda_bvh2_set_leaf_aabbs(ctx_.get(), h_.get(), prim_aabbs, n)); }
@@ -226,6 +240,20 @@ public:
         return out;
     }
     void set_triangles(const Triangle* tris, size_t n) { ctx_.check(obvhs_cuda_cwbvh_set_triangles(ctx_.get(), h_.get(), tris, n)); }
+    // CwBvh::order_children(&mut self, primitives, direct_layout), src/cwbvh/mod.rs:520-524, the primitives given as their AABBs
+    void order_children(const Aabb* prim_aabbs, size_t n, bool direct_layout) {
+        ctx_.check(obvhs_cuda_cwbvh_order_children(ctx_.get(), h_.get(), prim_aabbs, n, direct_layout));
+    }
+    // Collective over the ranks of ctx.comm_init: `root_tree` is the finished tree on rank `root` (returned as is) and null
+    // elsewhere, where a replica is returned (nodes, primitive_indices, total_aabb, flags, permuted triangles). One 64-byte header
+    // broadcast + one grouped NCCL launch on the context's stream. (Re-filling an earlier replica in place is offered by the C
+    // entry point only: it may free the handle it is given, which a shared handle cannot express.)
+    static CwBvh broadcast(const Context& ctx, const CwBvh* root_tree, int root) {
+        ObvhsCwBvh* h = root_tree ? root_tree->get() : nullptr;
+        ctx.check(obvhs_cuda_cwbvh_broadcast(ctx.get(), &h, root));
+        if (root_tree && h == root_tree->get()) return *root_tree;
+        return CwBvh(ctx, h);
+    }
     // CwBvh::ray_traverse / ray_traverse_miss / ray_traverse_anyhit over a batch with the triangle closure,
     // src/cwbvh/mod.rs:169-245; hit.primitive_id indexes primitive_indices order, as in the reference
     void ray_traverse(const Ray* rays, size_t n, RayHit* hits) const { ctx_.check(obvhs_cuda_cwbvh_ray_traverse_batch(ctx_.get(), h_.get(), rays, n, hits)); }

@@ -181,7 +181,7 @@ int obvhs_cuda_bvh2_refit_all(ObvhsContext* ctx, ObvhsBvh2* bvh);
 /* Bvh2::reorder_in_stack_traversal_order (src/bvh2/mod.rs:462-500): nodes re-indexed in the pop order of the reference's stack
  * (parents before children, each sibling pair followed by the subtree of its second node, then of its first); parents are
  * recomputed when present; children_are_ordered_after_parents becomes true. */
-int obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ObvhsContext* ctx, ObvhsBvh2* bvh);                       /* bvh2/mod.rs:527-569 */
+int obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ObvhsContext* ctx, ObvhsBvh2* bvh);                       /* bvh2/mod.rs:462-500 */
 /* rewrite every leaf's AABB from per-primitive AABBs (dynamic scenes, examples/physics.rs:500-539), then refit_all */
 int obvhs_cuda_bvh2_set_leaf_aabbs(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsAabb* prim_aabbs, size_t n);
 

@@ -50,6 +50,12 @@ pub fn nccl_unique_id() -> Result<[u8; sys::OBVHS_NCCL_UNIQUE_ID_BYTES]> {
 /// Device-resident `Bvh2` (bvh2/mod.rs:31-85).
 pub struct Bvh2 { h: *mut sys::Bvh2 }
 impl Drop for Bvh2 { fn drop(&mut self) { unsafe { sys::obvhs_cuda_bvh2_free(self.h) } } }
+impl Bvh2 {
+    /// `Bvh2::reorder_in_stack_traversal_order(&mut self)` (bvh2/mod.rs:462-500)
+    pub fn reorder_in_stack_traversal_order(&mut self, ctx: &Context) -> Result<()> {
+        ctx.check(unsafe { sys::obvhs_cuda_bvh2_reorder_in_stack_traversal_order(ctx.h, self.h) })
+    }
+}
 
 /// `PlocBuilder::build(&mut self, search_distance, aabbs, indices, sort_precision, search_depth_threshold) -> Bvh2` (ploc/mod.rs:95-102)
 pub struct PlocBuilder<'c> { pub ctx: &'c Context }
@@ -117,6 +123,11 @@ impl CwBvh {
     pub fn ray_traverse_miss_batch(&self, ctx: &Context, rays: &[Ray], miss: &mut [u8]) -> Result<()> {
         assert_eq!(rays.len(), miss.len());
         ctx.check(unsafe { sys::obvhs_cuda_cwbvh_ray_traverse_miss_batch(ctx.h, self.h, rays.as_ptr(), rays.len(), miss.as_mut_ptr()) })
+    }
+    /// `CwBvh::order_children(&mut self, primitives: &[T], direct_layout)` (cwbvh/mod.rs:520-524) with `T::aabb()` collected by the
+    /// caller (`primitives.iter().map(Boundable::aabb)`).
+    pub fn order_children(&mut self, ctx: &Context, prim_aabbs: &[Aabb], direct_layout: bool) -> Result<()> {
+        ctx.check(unsafe { sys::obvhs_cuda_cwbvh_order_children(ctx.h, self.h, prim_aabbs.as_ptr(), prim_aabbs.len(), direct_layout as i32) })
     }
     /// Replicate the tree built on `root` to every rank of the context's communicator (`Clone` across GPUs): pass the tree on
     /// `root`, `None` (or an earlier replica to refill) elsewhere.

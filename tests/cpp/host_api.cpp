@@ -221,6 +221,44 @@ int main() {
         std::sort(bp.begin(), bp.end());
         CHECK(bp.size() == n && bp.front() == 0 && bp.back() == n - 1, "rebuilt tree lost primitives");
 
+        // layout passes: Bvh2::reorder_in_stack_traversal_order keeps the hits and puts every child pair behind its parent;
+        // CwBvh::order_children on a tree converted WITHOUT ordering keeps the hits and is idempotent
+        {
+            Bvh2 b3 = build_bvh2_from_tris(ctx, tris.data(), n, BvhBuildParams::fast_build());
+            std::vector<RayHit> h0(m), h1(m);
+            b3.ray_traverse(rays.data(), m, h0.data());
+            b3.reorder_in_stack_traversal_order();
+            CHECK(b3.children_are_ordered_after_parents(), "reorder did not set children_are_ordered_after_parents");
+            b3.ray_traverse(rays.data(), m, h1.data());
+            size_t diff_t = 0;
+            for (size_t i = 0; i < m; i++) diff_t += std::memcmp(&h0[i].t, &h1[i].t, 4) != 0;
+            CHECK(diff_t == 0, "reorder changed %zu hit distances", diff_t);
+            std::vector<Bvh2Node> rn;
+            b3.download(&rn, nullptr);
+            size_t out_of_order = 0;
+            for (size_t i = 0; i < rn.size(); i++) out_of_order += rn[i].prim_count == 0 && rn[i].first_index <= i;
+            CHECK(out_of_order == 0, "%zu inner nodes point backwards after the reorder", out_of_order);
+
+            std::vector<Aabb> boxes(n);
+            for (size_t i = 0; i < n; i++)
+                for (int k = 0; k < 3; k++) {
+                    boxes[i].min[k] = std::min(tris[i].v0[k], std::min(tris[i].v1[k], tris[i].v2[k]));
+                    boxes[i].max[k] = std::max(tris[i].v0[k], std::max(tris[i].v1[k], tris[i].v2[k]));
+                }
+            CwBvh cu = bvh2_to_cwbvh(b, 3, false, true);
+            cu.set_triangles(tris.data(), n);
+            cu.ray_traverse(rays.data(), m, h0.data());
+            cu.order_children(boxes.data(), n, false);
+            cu.ray_traverse(rays.data(), m, h1.data());
+            CHECK(std::memcmp(h0.data(), h1.data(), m * sizeof(RayHit)) == 0, "order_children changed the hits");
+            std::vector<CwBvhNode> o1, o2;
+            cu.download(&o1, nullptr);
+            cu.order_children(boxes.data(), n, false);
+            cu.download(&o2, nullptr);
+            CHECK(std::memcmp(o1.data(), o2.data(), o1.size() * sizeof(CwBvhNode)) == 0, "order_children is not idempotent");
+            CHECK(cu.exact_node_aabbs().size() >= o1.size(), "exact boxes lost");  // vec![Aabb::empty(); bvh2.nodes.len()], bvh2_to_cwbvh.rs:60-62
+        }
+
         // errors surface as exceptions with the library's message
         bool threw = false;
         try {
