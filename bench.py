@@ -557,7 +557,7 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
     h_args.copy_(d_args)
     h_hits = torch.empty((n_rays, 4), dtype=torch.int32).pin_memory()
     hits_np = h_hits.numpy().view(RAY_HIT).reshape(-1)
-    e_t, e_b, e_s = [], [], []
+    e_t, e_b, e_s, e_n = [], [], [], []
     if dist:
         dist.barrier()
     for it in range(2 + max(2, min(args.steps, 5))):
@@ -565,10 +565,34 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
         bvh.ray_traverse(h_args.numpy(), out=hits_np)
         t2 = time.perf_counter()
         if it >= 2:
-            e_t.append(t2 - t1)
+            e_n.append(t2 - t1)
     e2e_hit_count = int((hits_np["t"] < 3.0e38).sum())
     assert e2e_hit_count == hit_count, (e2e_hit_count, hit_count)
-    link = host_link_probe(e, h_args, d_args, d_hits, h_hits)
+    # Every ray of these workloads is Ray::new_inf(origin, direction) / Ray::new(o, d, 0.0, f32::MAX) (examples/demoscene.rs:152,178;
+    # obj_cwbvh.rs:104): one (tmin, tmax) for the batch, so the call a user makes ships origin and direction only (24 B per ray)
+    with torch.cuda.stream(stream):
+        t_lo, t_hi = d_args[:, 3].min().item(), d_args[:, 3].max().item()
+        m_lo, m_hi = d_args[:, 7].min().item(), d_args[:, 7].max().item()
+    uniform = bool(t_lo == t_hi and m_lo == m_hi)
+    if uniform:
+        h_od = torch.empty((n_rays, 6), dtype=torch.float32).pin_memory()
+        with torch.cuda.stream(stream):
+            d_od = d_args[:, [0, 1, 2, 4, 5, 6]].contiguous()
+            h_od.copy_(d_od)
+            ref_hash = hits_hash_np(hits_np)
+        stream.synchronize()
+        for it in range(2 + max(2, min(args.steps, 5))):
+            t1 = time.perf_counter()
+            bvh.ray_od_traverse(h_od.numpy(), t_lo, m_lo, out=hits_np)
+            t2 = time.perf_counter()
+            if it >= 2:
+                e_t.append(t2 - t1)
+        assert hits_hash_np(hits_np) == ref_hash, "24-byte ray records gave different hits than the Ray::new records"
+        link = host_link_probe(e, h_od, d_od, d_hits, h_hits)
+        del d_od, h_od
+    else:
+        e_t = list(e_n)
+        link = host_link_probe(e, h_args, d_args, d_hits, h_hits)
     # the drop-in call over the reference's own 64-byte Ray structs, on a bounded prefix of the slice
     n_struct = min(n_rays, 1 << 25)
     h_rays = torch.empty((n_struct, 16), dtype=torch.float32).pin_memory()
@@ -592,7 +616,8 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
             if it >= 1:
                 e_b.append(time.perf_counter() - t0)
         del eb, h_tris
-    e2e_trav_s, e2e_struct_s, e2e_build_s = all_max(e, [float(np.mean(e_t)), float(np.mean(e_s)) / n_struct * n_rays, float(np.mean(e_b)) if e_b else 0.0])
+    e2e_trav_s, e2e_struct_s, e2e_build_s, e2e_new_s = all_max(e, [float(np.mean(e_t)), float(np.mean(e_s)) / n_struct * n_rays,
+                                                                    float(np.mean(e_b)) if e_b else 0.0, float(np.mean(e_n))])
     link_all = all_max(e, [link["concurrent_ms"], -link["h2d_gbs"], -link["d2h_gbs"]])
     res = None
     if rank == 0:
@@ -613,9 +638,12 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
                          "note": "per GPU (rank 0's launch). B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); traffic = DRAM bytes "
                                  "of the same launch from the committed ncu capture (profiles/traffic.json), null when the launch size differs from it"},
             "cpu_baseline": cpu, "parity": parity,
-            "e2e": {"value": n_total / e2e_trav_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays, "d2h_bytes_per_step": 16 * n_rays,
-                    "how": "obvhs_cuda_cwbvh_ray_new_traverse_batch: pinned HOST Ray::new records (32 B/ray) in, pinned HOST RayHits out, every rank its "
-                           "own slice, max over ranks; the kernels run Ray::new as they fetch a ray",
+            "e2e": {"value": n_total / e2e_trav_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": (24 if uniform else 32) * n_rays, "d2h_bytes_per_step": 16 * n_rays,
+                    "how": ("obvhs_cuda_cwbvh_ray_od_traverse_batch: pinned HOST (origin, direction) records (24 B/ray, one tmin/tmax per batch = Ray::new_inf) in, "
+                            if uniform else "obvhs_cuda_cwbvh_ray_new_traverse_batch: pinned HOST Ray::new records (32 B/ray) in, ") +
+                           "pinned HOST RayHits out, every rank its own slice, max over ranks; the kernels run Ray::new as they fetch a ray",
+                    "ray_new": {"value": n_total / e2e_new_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays,
+                                "how": "obvhs_cuda_cwbvh_ray_new_traverse_batch over 32-byte Ray::new records (per-ray tmin / tmax)"},
                     "ray_struct": {"value": n_total / e2e_struct_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 64 * n_rays, "measured_on_rays": n_struct,
                                    "how": "obvhs_cuda_cwbvh_ray_traverse_batch over the reference's 64-byte Ray structs (the drop-in call)"},
                     "build": {"mtris_per_s": n_tris / e2e_build_s / 1e6 if e2e_build_s > 0 else None, "h2d_bytes": 48 * n_tris,

@@ -28,6 +28,7 @@ using Bvh2Node = ObvhsBvh2Node;      // src/bvh2/node.rs:40-66
 using CwBvhNode = ObvhsCwBvhNode;    // src/cwbvh/node.rs:14-54
 using Ray = ObvhsRay;                // src/ray.rs:15-30
 using RayNew = ObvhsRayNew;          // the arguments of Ray::new, src/ray.rs:34
+using RayOd = ObvhsRayOd;            // origin + direction of Ray::new_inf, src/ray.rs:55-57 (one tmin/tmax per batch)
 using RayHit = ObvhsRayHit;          // src/ray.rs:63-70
 constexpr uint32_t INVALID_ID = 0xffffffffu;  // src/ray.rs:72
 
@@ -178,6 +179,9 @@ public:
     void ray_traverse(const RayNew* args, size_t n, RayHit* hits) const {
         ctx_.check(obvhs_cuda_bvh2_ray_new_traverse_batch(ctx_.get(), h_.get(), args, n, hits));
     }
+    void ray_traverse(const RayOd* od, size_t n, RayHit* hits, float tmin = 0.0f, float tmax = INFINITY) const {
+        ctx_.check(obvhs_cuda_bvh2_ray_od_traverse_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, hits));
+    }
     void ray_traverse_miss(const Ray* rays, size_t n, uint8_t* miss) const {
         ctx_.check(obvhs_cuda_bvh2_ray_traverse_miss_batch(ctx_.get(), h_.get(), rays, n, miss));
     }
@@ -259,6 +263,13 @@ public:
     void ray_traverse(const Ray* rays, size_t n, RayHit* hits) const { ctx_.check(obvhs_cuda_cwbvh_ray_traverse_batch(ctx_.get(), h_.get(), rays, n, hits)); }
     void ray_traverse(const RayNew* args, size_t n, RayHit* hits) const {
         ctx_.check(obvhs_cuda_cwbvh_ray_new_traverse_batch(ctx_.get(), h_.get(), args, n, hits));
+    }
+    // rays[i] = Ray::new(od[i].origin, od[i].direction, tmin, tmax); defaults = Ray::new_inf (src/ray.rs:55-57)
+    void ray_traverse(const RayOd* od, size_t n, RayHit* hits, float tmin = 0.0f, float tmax = INFINITY) const {
+        ctx_.check(obvhs_cuda_cwbvh_ray_od_traverse_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, hits));
+    }
+    void ray_traverse_miss(const RayOd* od, size_t n, uint8_t* miss, float tmin = 0.0f, float tmax = INFINITY) const {
+        ctx_.check(obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, miss));
     }
     void ray_traverse_miss(const Ray* rays, size_t n, uint8_t* miss) const {
         ctx_.check(obvhs_cuda_cwbvh_ray_traverse_miss_batch(ctx_.get(), h_.get(), rays, n, miss));

@@ -62,6 +62,11 @@ typedef struct {
  * constructor fills inv_direction. The *_ray_new_* entry points run the constructor on the device (safe_inverse,
  * ray.rs:6-12, bit for bit), so a host batch crosses PCIe at half the size of the Ray array. */
 typedef struct { float origin[3]; float tmin; float direction[3]; float tmax; } ObvhsRayNew;
+/* Origin and direction alone, 24 bytes: the per-ray part of Ray::new_inf(origin, direction) (src/ray.rs:55-57), which is how the
+ * camera, bounce and shadow loops of the reference's examples construct every ray (examples/demoscene.rs:152,178,189,213), and of
+ * Ray::new(eye, direction, 0.0, f32::MAX) (examples/cornell_box_cwbvh.rs:116, obj_cwbvh.rs:104). The *_ray_od_* entry points take
+ * ONE (tmin, tmax) for the batch and run the constructor on the device: 24 instead of 64 bytes per ray cross PCIe. */
+typedef struct { float origin[3]; float direction[3]; } ObvhsRayOd;
 /* src/ray.rs:63-70; RayHit::none() = ids 0xffffffff, t = +inf */
 typedef struct { uint32_t primitive_id, geometry_id, instance_id; float t; } ObvhsRayHit;
 
@@ -302,6 +307,14 @@ int obvhs_cuda_bvh2_ray_new_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* b
                                            ObvhsRayHit* hits);
 int obvhs_cuda_bvh2_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayNew* args, size_t n,
                                                 uint8_t* miss);
+/* The same for rays[i] = Ray::new(od[i].origin, od[i].direction, tmin, tmax) -- tmin = 0, tmax = INFINITY is Ray::new_inf
+ * (src/ray.rs:55-57). Bit-identical results to the calls above on the expanded rays. */
+int obvhs_cuda_cwbvh_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                           ObvhsRayHit* hits);
+int obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin,
+                                                float tmax, uint8_t* miss);
+int obvhs_cuda_bvh2_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                          ObvhsRayHit* hits);
 /* ---- multi-GPU: replicate a finished tree -------------------------------------------------------------------
  * The reference's CwBvh is a plain Clone of three Vecs and an Aabb (src/cwbvh/mod.rs:43-55) and ray_traverse only reads &self
  * (:169): the build runs on ONE GPU, the finished tree is broadcast over NVLink / NVSwitch with NCCL, and every rank traverses

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import math
 import os
 from dataclasses import dataclass
 
@@ -127,6 +128,9 @@ SIGNATURES = {
     "obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_bvh2_ray_new_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_bvh2_ray_new_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "obvhs_cuda_cwbvh_ray_od_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
+    "obvhs_cuda_cwbvh_ray_od_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
+    "obvhs_cuda_bvh2_ray_od_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
     "obvhs_cuda_bvh2_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_bvh2_point_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_cwbvh_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
@@ -430,6 +434,15 @@ class Bvh2:
             self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
         return hits
 
+    def ray_od_traverse(self, origin_dir, tmin=0.0, tmax=math.inf, out=None):
+        """ray_traverse of Ray::new(o, d, tmin, tmax) for (n,6) float32 [origin | direction] records: 24 bytes per ray cross PCIe,
+        one pair of bounds per batch (defaults = Ray::new_inf, src/ray.rs:55-57)."""
+        od = _as_f32(origin_dir, 6)
+        n = od.shape[0]
+        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_bvh2_ray_od_traverse_batch(self.ctx.h, self.h, _ptr(od), n, float(tmin), float(tmax), _ptr(hits)))
+        return hits
+
     def ray_traverse_miss(self, rays, out=None):
         """src/bvh2/mod.rs:185-213"""
         r, is_args = _as_rays(rays)
@@ -725,6 +738,22 @@ class CwBvh:
         else:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
         return hits
+
+    def ray_od_traverse(self, origin_dir, tmin=0.0, tmax=math.inf, out=None):
+        """ray_traverse of Ray::new(o, d, tmin, tmax) for (n,6) float32 [origin | direction] records (ObvhsRayOd): 24 bytes per ray
+        cross PCIe, one pair of bounds per batch (defaults = Ray::new_inf, src/ray.rs:55-57, as examples/demoscene.rs builds its rays)."""
+        od = _as_f32(origin_dir, 6)
+        n = od.shape[0]
+        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_od_traverse_batch(self.ctx.h, self.h, _ptr(od), n, float(tmin), float(tmax), _ptr(hits)))
+        return hits
+
+    def ray_od_traverse_miss(self, origin_dir, tmin=0.0, tmax=math.inf, out=None):
+        od = _as_f32(origin_dir, 6)
+        n = od.shape[0]
+        miss = out if out is not None else np.zeros(n, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(self.ctx.h, self.h, _ptr(od), n, float(tmin), float(tmax), _ptr(miss)))
+        return miss
 
     def ray_traverse_miss(self, rays, out=None):
         r, is_args = _as_rays(rays)

@@ -1094,19 +1094,23 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
 }
 
 template <class RayIn>
+static RayFormat ray_format_of(float tmin = 0.f, float tmax = 0.f) {
+    return RayFormat{std::is_same<RayIn, ObvhsRayOd>::value ? 2u : std::is_same<RayIn, ObvhsRayNew>::value ? 1u : 0u, tmin, tmax};
+}
+template <class RayIn>
 static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
-                       uint64_t* counters) {
-    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
+                       uint64_t* counters, float tmin = 0.f, float tmax = 0.f) {
+    const RayFormat fmt = ray_format_of<RayIn>(tmin, tmax);
     return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const RayIn* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
-        return cwbvh_traverse_device(ctx, bvh, d_rays, PACKED, cnt, mode, d_out, d_cnt);
+        return cwbvh_traverse_device(ctx, bvh, d_rays, fmt, cnt, mode, d_out, d_cnt);
     });
 }
 template <class RayIn>
 static int b2_traverse(ObvhsContext* ctx, const ObvhsBvh2* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
-                       uint64_t* counters) {
-    constexpr bool PACKED = std::is_same<RayIn, ObvhsRayNew>::value;
+                       uint64_t* counters, float tmin = 0.f, float tmax = 0.f) {
+    const RayFormat fmt = ray_format_of<RayIn>(tmin, tmax);
     return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const RayIn* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
-        return bvh2_traverse_device(ctx, bvh, d_rays, PACKED, cnt, mode, d_out, d_cnt);
+        return bvh2_traverse_device(ctx, bvh, d_rays, fmt, cnt, mode, d_out, d_cnt);
     });
 }
 extern "C" {
@@ -1188,6 +1192,22 @@ int obvhs_cuda_cwbvh_ray_new_traverse_anyhit_count_batch(ObvhsContext* ctx, cons
 }
 
 // ---- Bvh2 ray traversal, collapse, builder -----------------------------------------------
+// rays[i] = Ray::new(od[i].origin, od[i].direction, tmin, tmax): 24 bytes per ray, one pair of bounds per batch
+int obvhs_cuda_cwbvh_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                           ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, od, n, 0, hits, sizeof(ObvhsRayHit), nullptr, tmin, tmax);
+}
+int obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin,
+                                                float tmax, uint8_t* miss) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, od, n, 1, miss, 1, nullptr, tmin, tmax);
+}
+int obvhs_cuda_bvh2_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                          ObvhsRayHit* hits) {
+    API_ENTER(ctx);
+    return b2_traverse(ctx, bvh, od, n, 0, hits, sizeof(ObvhsRayHit), nullptr, tmin, tmax);
+}
 int obvhs_cuda_bvh2_ray_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRay* rays, size_t n, ObvhsRayHit* hits) {
     API_ENTER(ctx);
     return b2_traverse(ctx, bvh, rays, n, 0, hits, sizeof(ObvhsRayHit), nullptr);

@@ -364,11 +364,17 @@ int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsA
 int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_per_leaf, bool order_children, ObvhsCwBvh** out,
                          bool include_exact_node_aabbs = false);
 // traverse.cu
-// d_rays: ObvhsRay[n] (packed = false) or ObvhsRayNew[n] (packed = true: Ray::new runs inside the kernel)
-int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+// How the rays of a batch lie in memory. kind 0: ObvhsRay[n] (64 B). kind 1: ObvhsRayNew[n] (32 B, Ray::new runs inside the kernel).
+// kind 2: ObvhsRayOd[n] (24 B: origin, direction) with ONE (tmin, tmax) for the batch.
+struct RayFormat {
+    u32 kind;
+    float tmin, tmax;
+    __host__ __device__ size_t bytes() const { return kind == 0 ? 64 : kind == 1 ? 32 : 24; }
+};
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, const RayFormat& fmt, size_t n, int mode, void* d_out,
                           u64* d_counters);
 int cwbvh_permute_tris_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsTriangle* d_tris, size_t n);
-int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, const RayFormat& fmt, size_t n, int mode, void* d_out,
                          u64* d_counters);
 int bvh2_permute_tris_device(ObvhsContext* ctx, ObvhsBvh2* bvh, const ObvhsTriangle* d_tris, size_t n_tris);
 size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool* persistent);

@@ -196,11 +196,17 @@ __device__ __forceinline__ float safe_inverse(float x) {
     if (fabsf(x) <= EPS) return copysignf(1.0f, x) / EPS;
     return 1.0f / x;
 }
-// Ray `i` of the batch. packed = false: the reference's 64-byte Ray {origin, direction, inv_direction, tmin, tmax} (ray.rs:15-30).
-// packed = true: the 32-byte arguments of Ray::new {origin, tmin, direction, tmax}; the constructor (ray.rs:34-52: inv_direction =
-// safe_inverse(direction), IEEE division) runs here, where its result is consumed -- no separate pass, half the bytes per ray.
-__device__ __forceinline__ void ray_load(RayRegs& r, const float4* __restrict__ rays, size_t i, bool packed) {
-    if (packed) {
+// Ray `i` of the batch (RayFormat, common.cuh). kind 0: the reference's 64-byte Ray {origin, direction, inv_direction, tmin, tmax}
+// (ray.rs:15-30). kind 1: the 32-byte arguments of Ray::new {origin, tmin, direction, tmax}; the constructor (ray.rs:34-52:
+// inv_direction = safe_inverse(direction), IEEE division) runs here, where its result is consumed -- no separate pass, half the
+// bytes per ray. kind 2: 24 bytes {origin, direction} with one (tmin, tmax) for the whole batch, as every camera / bounce loop of the
+// reference's examples constructs its rays (Ray::new(o, d, 0.0, f32::MAX), Ray::new_inf): the bounds come from the constant bank.
+__device__ __forceinline__ void ray_load(RayRegs& r, const float4* __restrict__ rays, size_t i, const RayFormat fmt) {
+    if (fmt.kind == 2) {
+        const float2* p = reinterpret_cast<const float2*>(rays) + 3 * i;
+        const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        r = RayRegs{a.x, a.y, b.x, b.y, c.x, c.y, safe_inverse(b.y), safe_inverse(c.x), safe_inverse(c.y), fmt.tmin, fmt.tmax};
+    } else if (fmt.kind == 1) {
         const float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
         r = RayRegs{o.x, o.y, o.z, d.x, d.y, d.z, safe_inverse(d.x), safe_inverse(d.y), safe_inverse(d.z), o.w, d.w};
     } else {
@@ -275,8 +281,8 @@ struct CwTree {
     };
     template <class Stack>
     __device__ __forceinline__ void bind_stack(Stack&) const {}
-    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, bool packed) const {
-        ray_load(st.r, rays, i, packed);
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, const RayFormat fmt) const {
+        ray_load(st.r, rays, i, fmt);
         // cwbvh/mod.rs:1001-1010
         st.oct_inv4 = (st.r.dx < 0.0f ? 0u : 0x04040404u) | (st.r.dy < 0.0f ? 0u : 0x02020202u) | (st.r.dz < 0.0f ? 0u : 0x01010101u);
         st.sp = 0;
@@ -476,8 +482,8 @@ struct Bvh2Tree {
         u32 r_count, r_first, l_first;
         bool go_left;
     };
-    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, bool packed) const {
-        ray_load(st.r, rays, i, packed);
+    __device__ __forceinline__ void begin(State& st, const float4* __restrict__ rays, size_t i, const RayFormat fmt) const {
+        ray_load(st.r, rays, i, fmt);
         st.cur = AT_ROOT;
         st.sp = 0;
         st.phase = 0;
@@ -706,7 +712,7 @@ __device__ __forceinline__ void trav_flush_counters(unsigned long long* __restri
 
 // One ray per thread: the fastest form for coherent batches (primary / shadow rays of neighbouring pixels).
 template <class Tree, int MODE, bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, bool packed,
+__global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, const float4* __restrict__ rays, size_t n, const RayFormat fmt,
                                                               void* __restrict__ out, unsigned long long* __restrict__ counters,
                                                               const DeferList defer) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, c
     LaneStack<typename Tree::StackT, Tree::STACK, 0> stack;
     tree.bind_stack(stack);
     const bool valid = i < n;
-    if (valid) tree.begin(st, rays, i, packed);
+    if (valid) tree.begin(st, rays, i, fmt);
     bool mine = valid;
     if (defer.count) {  // auto mode: vote, hand the block over to the persistent kernel when one of its warps is incoherent
         const bool coherent = warp_is_coherent(st.r, valid, defer.max_dist2);
@@ -750,7 +756,8 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, c
 // CTAs per SM (785: spills); the shared-memory short stack alone (857 / 5771 / 2171: removes 2.1 GB of local-memory write-through
 // per 2 M rays, no time change).
 struct PersistArgs {
-    u32 chunk, refill, packed;
+    u32 chunk, refill;
+    RayFormat fmt;
 };
 template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
 __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(const Tree tree, const float4* __restrict__ rays, u32 n,
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(c
                     my = chunk_pos + rank;
                     if (DEFER) my = __ldcg(defer.blocks + (my >> 7)) * 128u + (my & 127u);
                     if (!DEFER || my < n_rays) {  // (the last block of a batch may be partial)
-                        tree.begin(st, rays, my, pa.packed != 0);
+                        tree.begin(st, rays, my, pa.fmt);
                         active = true;
                     }
                 }
@@ -850,7 +857,7 @@ __global__ void make_rays_kernel(const float* __restrict__ od, size_t n, float t
 // Persistent-kernel variants (POLICY, SS, MINB) selectable per context: obvhs_cuda_set_option("traverse_variant", "<id>").
 // Variant 0 is the default. Only CwTree has fused_turn (POLICY 1); Bvh2 trees always run variant 0.
 template <class Tree, int MODE, bool COUNT, bool DEFER, int POLICY, int SS, int MINB>
-static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, void* d_out, unsigned long long* c,
+static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, const RayFormat& fmt, void* d_out, unsigned long long* c,
                                u32* next, const DeferList& defer) {
     auto kernel = traverse_persistent_kernel<Tree, MODE, COUNT, DEFER, POLICY, SS, MINB>;
     int per_sm = 0;
@@ -859,7 +866,7 @@ static int launch_persistent_v(ObvhsContext* ctx, const Tree& tree, const float4
     size_t blocks = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
     if (blocks > need) blocks = need;
     ctx->traverse_resident_lanes = (size_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm) * TRAV_BLOCK;
-    const PersistArgs pa{(u32)ctx->traverse_chunk, (u32)ctx->traverse_refill, packed ? 1u : 0u};
+    const PersistArgs pa{(u32)ctx->traverse_chunk, (u32)ctx->traverse_refill, fmt};
     kernel<<<(unsigned)blocks, TRAV_BLOCK, 0, ctx->stream>>>(tree, rays, (u32)n, d_out, c, next, pa, defer);
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
@@ -870,13 +877,13 @@ template <>
 struct HasSplitSteps<CwTree> { static constexpr bool value = true; };
 
 template <class Tree, int MODE, bool COUNT>
-static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, void* d_out, unsigned long long* c,
+static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, const RayFormat& fmt, void* d_out, unsigned long long* c,
                                u32* next, const DeferList& defer) {
-    if (defer.count) return launch_persistent_v<Tree, MODE, COUNT, true, 0, 0, 8>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    if (defer.count) return launch_persistent_v<Tree, MODE, COUNT, true, 0, 0, 8>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
     if constexpr (HasSplitSteps<Tree>::value) {
         switch (ctx->traverse_variant) {
 #define OBVHS_V(ID, POLICY, SS, MINB) \
-    case ID: return launch_persistent_v<Tree, MODE, COUNT, false, POLICY, SS, MINB>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    case ID: return launch_persistent_v<Tree, MODE, COUNT, false, POLICY, SS, MINB>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
             OBVHS_V(1, 0, 8, 9)
             OBVHS_V(2, 1, 0, 9)
             OBVHS_V(3, 1, 8, 9)
@@ -885,33 +892,33 @@ static int launch_persistent_t(ObvhsContext* ctx, const Tree& tree, const float4
             default: break;
         }
     }
-    return launch_persistent_v<Tree, MODE, COUNT, false, 0, 0, 9>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    return launch_persistent_v<Tree, MODE, COUNT, false, 0, 0, 9>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
 }
 template <class Tree>
-static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, int mode, void* d_out,
+static int launch_persistent(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, const RayFormat& fmt, int mode, void* d_out,
                              unsigned long long* c, u32* next, const DeferList& defer) {
     if (c) {
-        if (mode == 0) return launch_persistent_t<Tree, 0, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
-        if (mode == 1) return launch_persistent_t<Tree, 1, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
-        return launch_persistent_t<Tree, 2, true>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+        if (mode == 0) return launch_persistent_t<Tree, 0, true>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
+        if (mode == 1) return launch_persistent_t<Tree, 1, true>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
+        return launch_persistent_t<Tree, 2, true>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
     }
-    if (mode == 0) return launch_persistent_t<Tree, 0, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
-    if (mode == 1) return launch_persistent_t<Tree, 1, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
-    return launch_persistent_t<Tree, 2, false>(ctx, tree, rays, n, packed, d_out, c, next, defer);
+    if (mode == 0) return launch_persistent_t<Tree, 0, false>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
+    if (mode == 1) return launch_persistent_t<Tree, 1, false>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
+    return launch_persistent_t<Tree, 2, false>(ctx, tree, rays, n, fmt, d_out, c, next, defer);
 }
 template <class Tree>
-static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, bool packed, int mode, void* d_out,
+static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays, size_t n, const RayFormat& fmt, int mode, void* d_out,
                          unsigned long long* c, const DeferList& defer) {
     dim3 block(TRAV_BLOCK), grid(div_up(n, TRAV_BLOCK));
     cudaStream_t s = ctx->stream;
     if (c) {
-        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
-        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
-        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        if (mode == 0) traverse_kernel<Tree, 0, true><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, true><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
+        else traverse_kernel<Tree, 2, true><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
     } else {
-        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
-        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
-        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, packed, d_out, c, defer);
+        if (mode == 0) traverse_kernel<Tree, 0, false><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
+        else if (mode == 1) traverse_kernel<Tree, 1, false><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
+        else traverse_kernel<Tree, 2, false><<<grid, block, 0, s>>>(tree, rays, n, fmt, d_out, c, defer);
     }
     KERNEL_CHECK(ctx);
     return OBVHS_OK;
@@ -922,8 +929,8 @@ static int launch_static(ObvhsContext* ctx, const Tree& tree, const float4* rays
 constexpr size_t AUTO_STATIC_MAX_PRIMS = 262144;
 template <class Tree>
 static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAabb& total_aabb, size_t prim_count, const float4* rays, size_t n,
-                             bool packed, int mode, void* d_out, u64* d_counters, bool force_persistent = false) {
-    const size_t ray_vec4 = packed ? 2 : 4;  // float4 per ray
+                             const RayFormat& fmt, int mode, void* d_out, u64* d_counters, bool force_persistent = false) {
+    const size_t ray_bytes = fmt.bytes();
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_counters);
     cudaStream_t s = ctx->stream;
     int tm = ctx->traverse_mode;
@@ -939,7 +946,7 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     const size_t n_launches = (n + MAX_LAUNCH - 1) / MAX_LAUNCH;
     if (tm == 2 && n_launches > 1) tm = 1;
     const DeferList none{nullptr, nullptr, 0.f};
-    if (tm == 0) return launch_static(ctx, tree, rays, n, packed, mode, d_out, c, none);
+    if (tm == 0) return launch_static(ctx, tree, rays, n, fmt, mode, d_out, c, none);
     // scratch: [0] deferred block count, [1] unused, [2..] one ray cursor per persistent launch, then the deferred block list
     const size_t n_blocks = tm == 2 ? (n + 127) / 128 : 0;
     DevBuf<u32> scratch;
@@ -948,7 +955,7 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     if (tm == 1) {
         for (size_t l = 0; l < n_launches; l++) {
             const size_t off = l * MAX_LAUNCH, cnt = n - off < MAX_LAUNCH ? n - off : MAX_LAUNCH;
-            ST_TRY(launch_persistent(ctx, tree, rays + off * ray_vec4, cnt, packed, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, none));
+            ST_TRY(launch_persistent(ctx, tree, reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rays) + off * ray_bytes), cnt, fmt, mode, (char*)d_out + off * out_elem, c, scratch.p + 2 + l, none));
         }
         return OBVHS_OK;
     }
@@ -957,8 +964,8 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     float diag2 = dx * dx + dy * dy + dz * dz;
     if (!(diag2 > 0.0f) || !(diag2 < 3.0e38f)) diag2 = 3.0e38f;  // unknown scene extent (uploaded tree): directions decide
     const DeferList defer{scratch.p, scratch.p + 2 + n_launches, diag2 * 0.0004f};
-    ST_TRY(launch_static(ctx, tree, rays, n, packed, mode, d_out, c, defer));
-    return launch_persistent(ctx, tree, rays, n, packed, mode, d_out, c, scratch.p + 2, defer);
+    ST_TRY(launch_static(ctx, tree, rays, n, fmt, mode, d_out, c, defer));
+    return launch_persistent(ctx, tree, rays, n, fmt, mode, d_out, c, scratch.p + 2, defer);
 }
 
 // Smallest slice of a host batch worth its own launch (traverse_common pipelines H2D | traversal | D2H slice by slice): 32 Ki
@@ -973,7 +980,7 @@ size_t traverse_host_chunk_min(const ObvhsContext* ctx, size_t prim_count, bool*
     return *persistent ? lanes * 2 : (size_t)32768;
 }
 
-int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, const RayFormat& fmt, size_t n, int mode, void* d_out,
                           u64* d_counters) {
     if (n == 0) return OBVHS_OK;
     if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
@@ -985,10 +992,10 @@ int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* 
     tree.tris = reinterpret_cast<const float4*>(bvh->bvh_tris);
     tree.root_group = bvh->node_count ? 0x80000000u : 0u;  // cwbvh/mod.rs:147-151: empty bvh => nothing to visit
     tree.magic = 0x4B000000u;
-    return traverse_dispatch(ctx, tree, bvh->total_aabb, bvh->prim_count, reinterpret_cast<const float4*>(d_rays), n, packed, mode, d_out, d_counters);
+    return traverse_dispatch(ctx, tree, bvh->total_aabb, bvh->prim_count, reinterpret_cast<const float4*>(d_rays), n, fmt, mode, d_out, d_counters);
 }
 
-int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, bool packed, size_t n, int mode, void* d_out,
+int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_rays, const RayFormat& fmt, size_t n, int mode, void* d_out,
                          u64* d_counters) {
     if (n == 0) return OBVHS_OK;
     if (bvh->node_count > 0 && bvh->prim_count > 0 && !bvh->bvh_tris) {
@@ -999,11 +1006,11 @@ int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     if (bvh->max_depth <= 96) {  // fast_stack!(u32, (96, 192), self.max_depth, ...) bvh2/mod.rs:166
         Bvh2Tree<96> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, nullptr, 0u};
-        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, fmt, mode, d_out, d_counters);
     }
     if (bvh->max_depth <= 192) {
         Bvh2Tree<192> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, nullptr, 0u};
-        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters);
+        return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, fmt, mode, d_out, d_counters);
     }
     // beyond 192 the reference allocates HeapStack::new_with_capacity(max_depth) per call: here one arena for the launch, max_depth
     // entries for each of the (at most sm_count * 16 * 128) lanes the persistent kernel keeps resident
@@ -1011,7 +1018,7 @@ int bvh2_traverse_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, const void* d_
     CU_TRY(ctx, heap.alloc((size_t)ctx->sm_count * 16 * TRAV_BLOCK * bvh->max_depth, ctx->stream));
     Bvh2Tree<0> tree{reinterpret_cast<const float4*>(bvh->nodes), reinterpret_cast<const float4*>(bvh->bvh_tris), (u32)bvh->node_count, heap.p,
                      (u32)bvh->max_depth};
-    return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, packed, mode, d_out, d_counters, true);
+    return traverse_dispatch(ctx, tree, unknown, bvh->prim_count, rays, n, fmt, mode, d_out, d_counters, true);
 }
 
 // bvh_tris[i] = tris[primitive_indices[i]] for a Bvh2 (examples/demoscene.rs:66-70)

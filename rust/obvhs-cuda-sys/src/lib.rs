@@ -50,6 +50,10 @@ pub struct Ray {
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct RayNew { pub origin: [f32; 3], pub tmin: f32, pub direction: [f32; 3], pub tmax: f32 }
+/// origin and direction of `Ray::new_inf(origin, direction)` (src/ray.rs:55-57); one (tmin, tmax) per batch
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct RayOd { pub origin: [f32; 3], pub direction: [f32; 3] }
 /// src/ray.rs:63-70
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -74,6 +78,7 @@ const _: () = {
     assert!(core::mem::size_of::<CwBvhNode>() == 80);
     assert!(core::mem::size_of::<Ray>() == 64);
     assert!(core::mem::size_of::<RayNew>() == 32);
+    assert!(core::mem::size_of::<RayOd>() == 24);
     assert!(core::mem::size_of::<RayHit>() == 16);
 };
 
@@ -426,6 +431,33 @@ extern "C" {
         args: *const RayNew,
         n: usize,
         miss: *mut u8,
+    ) -> c_int;
+    pub fn obvhs_cuda_cwbvh_ray_od_traverse_batch(
+        ctx: *mut Context,
+        bvh: *const CwBvh,
+        od: *const RayOd,
+        n: usize,
+        tmin: f32,
+        tmax: f32,
+        hits: *mut RayHit,
+    ) -> c_int;
+    pub fn obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(
+        ctx: *mut Context,
+        bvh: *const CwBvh,
+        od: *const RayOd,
+        n: usize,
+        tmin: f32,
+        tmax: f32,
+        miss: *mut u8,
+    ) -> c_int;
+    pub fn obvhs_cuda_bvh2_ray_od_traverse_batch(
+        ctx: *mut Context,
+        bvh: *const Bvh2,
+        od: *const RayOd,
+        n: usize,
+        tmin: f32,
+        tmax: f32,
+        hits: *mut RayHit,
     ) -> c_int;
     pub fn obvhs_cuda_nccl_unique_id(id: *mut u8) -> c_int;
     pub fn obvhs_cuda_comm_init(ctx: *mut Context, id: *const u8, rank: c_int, world: c_int) -> c_int;

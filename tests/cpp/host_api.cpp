@@ -153,6 +153,19 @@ int main() {
         std::vector<RayHit> hits2(m);
         cw.ray_traverse(args.data(), m, hits2.data());
         CHECK(std::memcmp(hits.data(), hits2.data(), m * sizeof(RayHit)) == 0, "Ray::new path differs from the Ray-struct path");
+        // ... and as (origin, direction) records with one pair of bounds for the batch (all rays here are Ray::new_inf)
+        std::vector<RayOd> od(m);
+        bool uniform = true;
+        for (size_t i = 0; i < m; i++) {
+            std::memcpy(od[i].origin, args[i].origin, 12);
+            std::memcpy(od[i].direction, args[i].direction, 12);
+            uniform = uniform && args[i].tmin == args[0].tmin && args[i].tmax == args[0].tmax;
+        }
+        if (uniform) {
+            std::vector<RayHit> hits3(m);
+            cw.ray_traverse(od.data(), m, hits3.data(), args[0].tmin, args[0].tmax);
+            CHECK(std::memcmp(hits.data(), hits3.data(), m * sizeof(RayHit)) == 0, "24-byte ray path differs from the Ray-struct path");
+        }
         std::vector<Ray> built(m);
         ray_new_batch(ctx, args.data(), m, built.data());
         CHECK(std::memcmp(built.data(), rays.data(), m * sizeof(Ray)) == 0, "device Ray::new differs from the host constructor");

@@ -618,6 +618,51 @@ def test_traversal_over_ray_new_arguments(api, scenes, n_side):
     assert cw.ray_traverse(np.zeros((0, 8), np.float32)).shape[0] == 0
 
 
+@pytest.mark.parametrize("n_side", [96, 190])
+@pytest.mark.parametrize("bounds", [(0.0, np.inf), (0.0, 3.4028234663852886e38), (0.3, 2.5)])
+def test_traversal_over_origin_direction_records(api, scenes, n_side, bounds):
+    # the *_ray_od_* entry points (24 bytes per ray, ONE tmin / tmax per batch: Ray::new_inf, ray.rs:55-57, and the
+    # Ray::new(o, d, 0.0, f32::MAX) of the examples) equal the oracle on the expanded rays: host, pinned and device buffers,
+    # the staged (96) and the pipelined (190) host path, closest hit / miss, both tree types, every kernel choice
+    import torch
+    from obvhs_b200.types import RAY_HIT
+
+    tris = scenes["kitchen"]
+    base = rays_for(tris, n_side=n_side)
+    od = np.ascontiguousarray(base[:, [0, 1, 2, 4, 5, 6]])
+    tmin, tmax = np.float32(bounds[0]), np.float32(bounds[1])
+    rays = ob.make_rays(od[:, 0:3], od[:, 3:6], tmin, tmax)
+    c = ob.build_cwbvh_from_tris(tris, "fast_build")
+    bt = c.bvh_tris(tris)
+    want = c.ray_traverse(bt, rays)
+    want_miss = c.ray_traverse_miss(bt, rays)
+    for mode in ("auto", "persistent", "static"):
+        ctx = api.Context(0, traverse=mode)
+        cw = api.build_cwbvh_from_tris(tris, api.BvhBuildParams.fast_build(), ctx=ctx)
+        for a in (od, torch.from_numpy(od).pin_memory().numpy()):
+            got = cw.ray_od_traverse(a, tmin, tmax)
+            assert np.array_equal(got["primitive_id"], want["primitive_id"]), mode
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), mode
+        d_hits = torch.empty((od.shape[0], 4), dtype=torch.int32, device="cuda")
+        cw.ray_od_traverse(torch.from_numpy(od).cuda(), tmin, tmax, out=d_hits)
+        ctx.synchronize()
+        assert d_hits.cpu().numpy().view(RAY_HIT).reshape(-1).tobytes() == want.tobytes(), mode
+        assert np.array_equal(cw.ray_od_traverse_miss(od, tmin, tmax), want_miss), mode
+        assert cw.ray_od_traverse(np.zeros((0, 6), np.float32)).shape[0] == 0
+    b2 = api.build_bvh2_from_tris(tris, api.BvhBuildParams.fast_build())
+    assert np.array_equal(b2.ray_od_traverse(od, tmin, tmax).view(np.uint32), b2.ray_traverse(rays).view(np.uint32))
+    # an odd-sized slice of a device buffer that is only 8-byte aligned
+    d_od = torch.from_numpy(od).cuda()
+    part = d_od[3:1003]
+    got = cw.ray_od_traverse(part, tmin, tmax)
+    assert got.tobytes() == want[3:1003].tobytes()
+    lib, h = cw.ctx.lib, cw.ctx.h
+    hits = np.zeros(64, dtype=np.uint8)
+    assert lib.obvhs_cuda_cwbvh_ray_od_traverse_batch(h, cw.h, None, 4, 0.0, 1.0, hits.ctypes.data) < 0
+    assert lib.obvhs_cuda_cwbvh_ray_od_traverse_batch(h, None, od.ctypes.data, 4, 0.0, 1.0, hits.ctypes.data) < 0
+    assert lib.obvhs_cuda_cwbvh_ray_od_traverse_batch(h, cw.h, None, 0, 0.0, 1.0, None) == 0
+
+
 @pytest.mark.parametrize("mode", ["persistent", "auto", "static"])
 def test_host_slices_on_two_compute_streams(api, scenes, mode):
     # persistent-kernel slices of a host batch alternate between two compute streams (the tail of one hides behind the next);
