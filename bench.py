@@ -581,15 +581,20 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
             h_od.copy_(d_od)
             ref_hash = hits_hash_np(hits_np)
         stream.synchronize()
+        h_hits8 = torch.empty((n_rays, 2), dtype=torch.int32).pin_memory()  # ObvhsRayHit8 {primitive_id, t}: all this path writes into a RayHit
+        hits8_np = h_hits8.numpy()
         for it in range(2 + max(2, min(args.steps, 5))):
             t1 = time.perf_counter()
-            bvh.ray_od_traverse(h_od.numpy(), t_lo, m_lo, out=hits_np)
+            bvh.ray_od_traverse(h_od.numpy(), t_lo, m_lo, out=hits8_np, hit8=True)
             t2 = time.perf_counter()
             if it >= 2:
                 e_t.append(t2 - t1)
-        assert hits_hash_np(hits_np) == ref_hash, "24-byte ray records gave different hits than the Ray::new records"
-        link = host_link_probe(e, h_od, d_od, d_hits, h_hits)
-        del d_od, h_od
+        h8 = hits8_np.view(np.uint32)
+        with np.errstate(over="ignore"):
+            hash8 = int(((h8[:, 1].astype(np.uint64) << np.uint64(32)) | h8[:, 0].astype(np.uint64)).sum(dtype=np.uint64))
+        assert hash8 == ref_hash, "24-byte ray records / 8-byte hit records gave different hits than the Ray::new records"
+        link = host_link_probe(e, h_od, d_od, d_hits.view(-1)[: 2 * n_rays].view(n_rays, 2), h_hits8)
+        del d_od, h_od, h_hits8, hits8_np, h8
     else:
         e_t = list(e_n)
         link = host_link_probe(e, h_args, d_args, d_hits, h_hits)
@@ -638,12 +643,14 @@ def measure(e, args, name, tris, n_tris, preset, d_args, n_total, kernel, bound,
                          "note": "per GPU (rank 0's launch). B_trav = rays*(32+16) + 80*nodes_visited + 48*tris_tested (SURVEY.md 8d); traffic = DRAM bytes "
                                  "of the same launch from the committed ncu capture (profiles/traffic.json), null when the launch size differs from it"},
             "cpu_baseline": cpu, "parity": parity,
-            "e2e": {"value": n_total / e2e_trav_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": (24 if uniform else 32) * n_rays, "d2h_bytes_per_step": 16 * n_rays,
-                    "how": ("obvhs_cuda_cwbvh_ray_od_traverse_batch: pinned HOST (origin, direction) records (24 B/ray, one tmin/tmax per batch = Ray::new_inf) in, "
-                            if uniform else "obvhs_cuda_cwbvh_ray_new_traverse_batch: pinned HOST Ray::new records (32 B/ray) in, ") +
-                           "pinned HOST RayHits out, every rank its own slice, max over ranks; the kernels run Ray::new as they fetch a ray",
+            "e2e": {"value": n_total / e2e_trav_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": (24 if uniform else 32) * n_rays, "d2h_bytes_per_step": (8 if uniform else 16) * n_rays,
+                    "how": ("obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch: pinned HOST (origin, direction) records (24 B/ray, one tmin/tmax per batch = Ray::new_inf) in, "
+                            "pinned HOST {primitive_id, t} records (8 B/ray) out, "
+                            if uniform else "obvhs_cuda_cwbvh_ray_new_traverse_batch: pinned HOST Ray::new records (32 B/ray) in, pinned HOST RayHits out, ") +
+                           "every rank its own slice, max over ranks; the kernels run Ray::new as they fetch a ray",
                     "ray_new": {"value": n_total / e2e_new_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays,
-                                "how": "obvhs_cuda_cwbvh_ray_new_traverse_batch over 32-byte Ray::new records (per-ray tmin / tmax)"},
+                                "d2h_bytes_per_step": 16 * n_rays,
+                                "how": "obvhs_cuda_cwbvh_ray_new_traverse_batch over 32-byte Ray::new records (per-ray tmin / tmax), 16-byte RayHits out"},
                     "ray_struct": {"value": n_total / e2e_struct_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 64 * n_rays, "measured_on_rays": n_struct,
                                    "how": "obvhs_cuda_cwbvh_ray_traverse_batch over the reference's 64-byte Ray structs (the drop-in call)"},
                     "build": {"mtris_per_s": n_tris / e2e_build_s / 1e6 if e2e_build_s > 0 else None, "h2d_bytes": 48 * n_tris,

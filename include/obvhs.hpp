@@ -30,6 +30,7 @@ using Ray = ObvhsRay;                // src/ray.rs:15-30
 using RayNew = ObvhsRayNew;          // the arguments of Ray::new, src/ray.rs:34
 using RayOd = ObvhsRayOd;            // origin + direction of Ray::new_inf, src/ray.rs:55-57 (one tmin/tmax per batch)
 using RayHit = ObvhsRayHit;          // src/ray.rs:63-70
+using RayHit8 = ObvhsRayHit8;        // {primitive_id, t}: what the triangle closure writes into a RayHit
 constexpr uint32_t INVALID_ID = 0xffffffffu;  // src/ray.rs:72
 
 // the reference panics; the C ABI returns a status; this layer throws
@@ -267,6 +268,9 @@ public:
     // rays[i] = Ray::new(od[i].origin, od[i].direction, tmin, tmax); defaults = Ray::new_inf (src/ray.rs:55-57)
     void ray_traverse(const RayOd* od, size_t n, RayHit* hits, float tmin = 0.0f, float tmax = INFINITY) const {
         ctx_.check(obvhs_cuda_cwbvh_ray_od_traverse_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, hits));
+    }
+    void ray_traverse(const RayOd* od, size_t n, RayHit8* hits, float tmin = 0.0f, float tmax = INFINITY) const {
+        ctx_.check(obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, hits));
     }
     void ray_traverse_miss(const RayOd* od, size_t n, uint8_t* miss, float tmin = 0.0f, float tmax = INFINITY) const {
         ctx_.check(obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ctx_.get(), h_.get(), od, n, tmin, tmax, miss));

@@ -70,6 +70,10 @@ typedef struct { float origin[3]; float direction[3]; } ObvhsRayOd;
 /* src/ray.rs:63-70; RayHit::none() = ids 0xffffffff, t = +inf */
 typedef struct { uint32_t primitive_id, geometry_id, instance_id; float t; } ObvhsRayHit;
 
+/* What CwBvh::ray_traverse with the triangle closure writes into a RayHit (cwbvh/mod.rs:184-189): primitive_id and t. geometry_id and
+ * instance_id stay RayHit::none()'s INVALID on this path, so a host batch can bring back 8 instead of 16 bytes per ray. */
+typedef struct { uint32_t primitive_id; float t; } ObvhsRayHit8;
+
 /* src/lib.rs:208-231 BvhBuildParams, field for field. ploc_search_distance is the u32 form of PlocSearchDistance
  * (ploc/mod.rs:534-562: 1,2,6,14,24,32); sort_precision is 64 or 128 (ploc/mod.rs:658-661). */
 typedef struct {
@@ -311,6 +315,9 @@ int obvhs_cuda_bvh2_ray_new_traverse_miss_batch(ObvhsContext* ctx, const ObvhsBv
  * (src/ray.rs:55-57). Bit-identical results to the calls above on the expanded rays. */
 int obvhs_cuda_cwbvh_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
                                            ObvhsRayHit* hits);
+/* the same closest hits as {primitive_id, t} records: hits[i] == {h.primitive_id, h.t} of obvhs_cuda_cwbvh_ray_od_traverse_batch's h */
+int obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                                ObvhsRayHit8* hits);
 int obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin,
                                                 float tmax, uint8_t* miss);
 int obvhs_cuda_bvh2_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsBvh2* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,

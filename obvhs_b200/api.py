@@ -25,7 +25,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .types import BVH2_NODE, CWBVH_NODE, RAY_HIT
+from .types import BVH2_NODE, CWBVH_NODE, RAY_HIT, RAY_HIT8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libobvhs_cuda.so")
@@ -130,6 +130,7 @@ SIGNATURES = {
     "obvhs_cuda_bvh2_ray_new_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "obvhs_cuda_cwbvh_ray_od_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
     "obvhs_cuda_cwbvh_ray_od_traverse_miss_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
+    "obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
     "obvhs_cuda_bvh2_ray_od_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _f32, _f32, _vp]),
     "obvhs_cuda_bvh2_aabb_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "obvhs_cuda_bvh2_point_traverse_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
@@ -739,13 +740,15 @@ class CwBvh:
             self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_traverse_batch_counted(self.ctx.h, self.h, _ptr(r), n, _ptr(hits), _ptr(counters)))
         return hits
 
-    def ray_od_traverse(self, origin_dir, tmin=0.0, tmax=math.inf, out=None):
+    def ray_od_traverse(self, origin_dir, tmin=0.0, tmax=math.inf, out=None, hit8=False):
         """ray_traverse of Ray::new(o, d, tmin, tmax) for (n,6) float32 [origin | direction] records (ObvhsRayOd): 24 bytes per ray
-        cross PCIe, one pair of bounds per batch (defaults = Ray::new_inf, src/ray.rs:55-57, as examples/demoscene.rs builds its rays)."""
+        cross PCIe, one pair of bounds per batch (defaults = Ray::new_inf, src/ray.rs:55-57, as examples/demoscene.rs builds its rays).
+        hit8: results as 8-byte RAY_HIT8 {primitive_id, t} records (all this path writes into a RayHit) instead of RAY_HIT."""
         od = _as_f32(origin_dir, 6)
         n = od.shape[0]
-        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT)
-        self.ctx.check(self.ctx.lib.obvhs_cuda_cwbvh_ray_od_traverse_batch(self.ctx.h, self.h, _ptr(od), n, float(tmin), float(tmax), _ptr(hits)))
+        hits = out if out is not None else np.zeros(n, dtype=RAY_HIT8 if hit8 else RAY_HIT)
+        fn = self.ctx.lib.obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch if hit8 else self.ctx.lib.obvhs_cuda_cwbvh_ray_od_traverse_batch
+        self.ctx.check(fn(self.ctx.h, self.h, _ptr(od), n, float(tmin), float(tmax), _ptr(hits)))
         return hits
 
     def ray_od_traverse_miss(self, origin_dir, tmin=0.0, tmax=math.inf, out=None):

@@ -1094,13 +1094,13 @@ static int traverse_common(ObvhsContext* ctx, const void* bvh, size_t prim_count
 }
 
 template <class RayIn>
-static RayFormat ray_format_of(float tmin = 0.f, float tmax = 0.f) {
-    return RayFormat{std::is_same<RayIn, ObvhsRayOd>::value ? 2u : std::is_same<RayIn, ObvhsRayNew>::value ? 1u : 0u, tmin, tmax};
+static RayFormat ray_format_of(float tmin = 0.f, float tmax = 0.f, bool hit8 = false) {
+    return RayFormat{std::is_same<RayIn, ObvhsRayOd>::value ? 2u : std::is_same<RayIn, ObvhsRayNew>::value ? 1u : 0u, tmin, tmax, hit8 ? 1u : 0u};
 }
 template <class RayIn>
 static int cw_traverse(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const RayIn* rays, size_t n, int mode, void* out, size_t out_elem,
                        uint64_t* counters, float tmin = 0.f, float tmax = 0.f) {
-    const RayFormat fmt = ray_format_of<RayIn>(tmin, tmax);
+    const RayFormat fmt = ray_format_of<RayIn>(tmin, tmax, mode == 0 && out_elem == sizeof(ObvhsRayHit8));
     return traverse_common(ctx, bvh, bvh ? bvh->prim_count : 0, rays, n, out, out_elem, counters, [=](const RayIn* d_rays, size_t cnt, void* d_out, u64* d_cnt) {
         return cwbvh_traverse_device(ctx, bvh, d_rays, fmt, cnt, mode, d_out, d_cnt);
     });
@@ -1197,6 +1197,11 @@ int obvhs_cuda_cwbvh_ray_od_traverse_batch(ObvhsContext* ctx, const ObvhsCwBvh* 
                                            ObvhsRayHit* hits) {
     API_ENTER(ctx);
     return cw_traverse(ctx, bvh, od, n, 0, hits, sizeof(ObvhsRayHit), nullptr, tmin, tmax);
+}
+int obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin, float tmax,
+                                                ObvhsRayHit8* hits) {
+    API_ENTER(ctx);
+    return cw_traverse(ctx, bvh, od, n, 0, hits, sizeof(ObvhsRayHit8), nullptr, tmin, tmax);
 }
 int obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const ObvhsRayOd* od, size_t n, float tmin,
                                                 float tmax, uint8_t* miss) {

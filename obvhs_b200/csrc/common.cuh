@@ -369,6 +369,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
 struct RayFormat {
     u32 kind;
     float tmin, tmax;
+    u32 hit8;  // closest-hit results as ObvhsRayHit8 {primitive_id, t} (8 B) instead of ObvhsRayHit (16 B)
     __host__ __device__ size_t bytes() const { return kind == 0 ? 64 : kind == 1 ? 32 : 24; }
 };
 int cwbvh_traverse_device(ObvhsContext* ctx, const ObvhsCwBvh* bvh, const void* d_rays, const RayFormat& fmt, size_t n, int mode, void* d_out,

@@ -257,10 +257,14 @@ __device__ __forceinline__ void result_reset(RayResult& o) {
     o.count = 0;
     o.is_miss = true;
 }
+// hit8: closest hits as 8-byte {primitive_id, t} records (ObvhsRayHit8) instead of the 16-byte RayHit whose geometry_id / instance_id
+// this path never sets (they stay RayHit::none()'s INVALID)
 template <int MODE>
-__device__ __forceinline__ void result_store(const RayResult& o, void* __restrict__ out, size_t i) {
-    if (MODE == 0) reinterpret_cast<uint4*>(out)[i] = make_uint4(o.hit_id, 0xffffffffu, 0xffffffffu, __float_as_uint(o.hit_t));
-    else if (MODE == 1) reinterpret_cast<u8*>(out)[i] = o.is_miss ? 1 : 0;
+__device__ __forceinline__ void result_store(const RayResult& o, void* __restrict__ out, size_t i, u32 hit8) {
+    if (MODE == 0) {
+        if (hit8) reinterpret_cast<uint2*>(out)[i] = make_uint2(o.hit_id, __float_as_uint(o.hit_t));
+        else reinterpret_cast<uint4*>(out)[i] = make_uint4(o.hit_id, 0xffffffffu, 0xffffffffu, __float_as_uint(o.hit_t));
+    } else if (MODE == 1) reinterpret_cast<u8*>(out)[i] = o.is_miss ? 1 : 0;
     else reinterpret_cast<u32*>(out)[i] = o.count;
 }
 
@@ -733,7 +737,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const Tree tree, c
     if (mine) {
         while (!tree.template step<MODE, COUNT, OBVHS_STATIC_ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
         }
-        result_store<MODE>(st.o, out, i);
+        result_store<MODE>(st.o, out, i, fmt.hit8);
     }
     trav_flush_counters<COUNT>(counters, nodes_visited, tris_tested);
 }
@@ -813,14 +817,14 @@ __global__ void __launch_bounds__(TRAV_BLOCK, MINB) traverse_persistent_kernel(c
         if constexpr (POLICY == 0) {
             do {
                 if (active && tree.template step<MODE, COUNT, ONE_TRI>(st, stack, nodes_visited, tris_tested)) {
-                    result_store<MODE>(st.o, out, my);
+                    result_store<MODE>(st.o, out, my, pa.fmt.hit8);
                     active = false;
                 }
             } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
         } else {
             do {
                 if (active && tree.template fused_turn<MODE, COUNT>(st, stack, nodes_visited, tris_tested)) {
-                    result_store<MODE>(st.o, out, my);
+                    result_store<MODE>(st.o, out, my, pa.fmt.hit8);
                     active = false;
                 }
             } while ((u32)__popc(__ballot_sync(0xffffffffu, active)) >= min_active);
@@ -942,7 +946,7 @@ static int traverse_dispatch(ObvhsContext* ctx, const Tree& tree, const ObvhsAab
     if (tm == 2 && prim_count > AUTO_STATIC_MAX_PRIMS) tm = 1;
     // 32-bit ray indices inside the persistent kernel: batches beyond 2^31 rays are split into several launches
     const size_t MAX_LAUNCH = (size_t)1 << 31;
-    const size_t out_elem = mode == 0 ? sizeof(ObvhsRayHit) : (mode == 1 ? 1 : 4);
+    const size_t out_elem = mode == 0 ? (fmt.hit8 ? 8 : sizeof(ObvhsRayHit)) : (mode == 1 ? 1 : 4);
     const size_t n_launches = (n + MAX_LAUNCH - 1) / MAX_LAUNCH;
     if (tm == 2 && n_launches > 1) tm = 1;
     const DeferList none{nullptr, nullptr, 0.f};

@@ -43,7 +43,8 @@ RAY_HIT = np.dtype([("primitive_id", "<u4"), ("geometry_id", "<u4"), ("instance_
 
 assert BVH2_NODE.itemsize == 48
 assert CWBVH_NODE.itemsize == 80
-assert RAY_HIT.itemsize == 16
+RAY_HIT8 = np.dtype([("primitive_id", "<u4"), ("t", "<f4")])  # ObvhsRayHit8
+assert RAY_HIT.itemsize == 16 and RAY_HIT8.itemsize == 8
 
 INVALID_ID = 0xFFFFFFFF
 F32_EPSILON = np.float32(1.1920929e-07)

@@ -54,6 +54,10 @@ pub struct RayNew { pub origin: [f32; 3], pub tmin: f32, pub direction: [f32; 3]
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct RayOd { pub origin: [f32; 3], pub direction: [f32; 3] }
+/// what the triangle closure writes into a `RayHit` (cwbvh/mod.rs:184-189)
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct RayHit8 { pub primitive_id: u32, pub t: f32 }
 /// src/ray.rs:63-70
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -79,6 +83,7 @@ const _: () = {
     assert!(core::mem::size_of::<Ray>() == 64);
     assert!(core::mem::size_of::<RayNew>() == 32);
     assert!(core::mem::size_of::<RayOd>() == 24);
+    assert!(core::mem::size_of::<RayHit8>() == 8);
     assert!(core::mem::size_of::<RayHit>() == 16);
 };
 
@@ -440,6 +445,15 @@ extern "C" {
         tmin: f32,
         tmax: f32,
         hits: *mut RayHit,
+    ) -> c_int;
+    pub fn obvhs_cuda_cwbvh_ray_od_traverse_hit8_batch(
+        ctx: *mut Context,
+        bvh: *const CwBvh,
+        od: *const RayOd,
+        n: usize,
+        tmin: f32,
+        tmax: f32,
+        hits: *mut RayHit8,
     ) -> c_int;
     pub fn obvhs_cuda_cwbvh_ray_od_traverse_miss_batch(
         ctx: *mut Context,

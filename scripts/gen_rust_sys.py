@@ -9,7 +9,7 @@ body = re.sub(r"/\*.*?\*/", "", h[h.index("typedef struct ObvhsContext ObvhsCont
 decls = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(obvhs_cuda_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", body, flags=re.S)
 TY = {"int": "c_int", "void": "c_void", "size_t": "usize", "uint32_t": "u32", "uint64_t": "u64", "uint8_t": "u8", "float": "f32", "double": "f64",
       "char": "c_char", "ObvhsAabb": "Aabb", "ObvhsTriangle": "Triangle", "ObvhsBvh2Node": "Bvh2Node", "ObvhsCwBvhNode": "CwBvhNode", "ObvhsRay": "Ray",
-      "ObvhsRayNew": "RayNew", "ObvhsRayOd": "RayOd", "ObvhsRayHit": "RayHit", "ObvhsBuildParams": "BuildParams", "ObvhsContext": "Context", "ObvhsBvh2": "Bvh2",
+      "ObvhsRayNew": "RayNew", "ObvhsRayOd": "RayOd", "ObvhsRayHit": "RayHit", "ObvhsRayHit8": "RayHit8", "ObvhsBuildParams": "BuildParams", "ObvhsContext": "Context", "ObvhsBvh2": "Bvh2",
       "ObvhsCwBvh": "CwBvh"}
 
 

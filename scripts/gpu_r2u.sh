@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cpp_host.py -m gpu -q --tb=short -x -p no:cacheprovider --timeout 300 -k "origin_direction or ray_new or cpp_host or two_compute" > gpurun_out/pytest_r2u.log 2>&1
+timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cpp_host.py -m gpu -q --tb=short -x -p no:cacheprovider --timeout 300 -k "origin_direction or ray_new or cpp_host or two_compute or persistent_kernel_variants" > gpurun_out/pytest_r2u.log 2>&1
 tail -5 gpurun_out/pytest_r2u.log
 timeout 900 python bench.py --steps 5 > gpurun_out/bench_r2u.json 2> gpurun_out/bench_r2u.err
 tail -3 gpurun_out/bench_r2u.err

@@ -648,6 +648,13 @@ def test_traversal_over_origin_direction_records(api, scenes, n_side, bounds):
         ctx.synchronize()
         assert d_hits.cpu().numpy().view(RAY_HIT).reshape(-1).tobytes() == want.tobytes(), mode
         assert np.array_equal(cw.ray_od_traverse_miss(od, tmin, tmax), want_miss), mode
+        h8 = cw.ray_od_traverse(od, tmin, tmax, hit8=True)  # {primitive_id, t} records: 8 bytes per ray back
+        assert h8.dtype.itemsize == 8 and np.array_equal(h8["primitive_id"], want["primitive_id"]), mode
+        assert np.array_equal(h8["t"].view(np.uint32), want["t"].view(np.uint32)), mode
+        d8 = torch.empty((od.shape[0], 2), dtype=torch.int32, device="cuda")
+        cw.ray_od_traverse(torch.from_numpy(od).cuda(), tmin, tmax, out=d8, hit8=True)
+        ctx.synchronize()
+        assert d8.cpu().numpy().tobytes() == h8.tobytes(), mode
         assert cw.ray_od_traverse(np.zeros((0, 6), np.float32)).shape[0] == 0
     b2 = api.build_bvh2_from_tris(tris, api.BvhBuildParams.fast_build())
     assert np.array_equal(b2.ray_od_traverse(od, tmin, tmax).view(np.uint32), b2.ray_traverse(rays).view(np.uint32))
