@@ -59,6 +59,12 @@ __device__ __forceinline__ void store_dec(Dec* p, const Dec& r) {
     q[2] = make_uint4(r.meta_hi, r.S[0], r.S[1], r.S[2]);
     q[3] = make_uint4(r.S[3], r.S[4], r.S[5], r.S[6]);
 }
+// What the emit pass needs of a record, as ONE 16-byte vector per node: {meta_lo, meta_hi, S[0], P} (P = primitives in the subtree).
+// The cost pass writes it next to the 64-byte record and never reads it (the frontier form carries the primitive counts through
+// the arrival words and the work items; the climbing form for small trees keeps a 4-byte P array that stays in L2); the emit pass
+// then touches one sector per BVH2 node instead of two of the record plus one of P (emit 1.03 -> 0.92 ms at 10 M triangles,
+// 1.32 -> 1.12 on the soup).
+__device__ __forceinline__ void store_hot(uint4* p, const Dec& d, u32 prims) { *p = make_uint4(d.meta_lo, d.meta_hi, d.S[0], prims); }
 __device__ __forceinline__ u32 dec_meta_of(const Dec& d, u32 i) { return ((i < 4 ? d.meta_lo >> (8 * i) : d.meta_hi >> (8 * (i - 4)))) & 0xffu; }
 
 struct CwGlobals {
@@ -154,7 +160,7 @@ __device__ __forceinline__ Dec inner_dec(const Dec& L, const Dec& R, float ha, u
 // recomputed by whoever needs them, here and in the emit pass), which halves the pass's DRAM writes.
 constexpr int COST_THREADS = 64;  // small CTAs: a CTA lives as long as its longest climber, and most threads stop after one or two levels
 __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* __restrict__ nodes, const u32* __restrict__ parents, u32 n_nodes,
-                                                         u32 max_prims_per_leaf, Dec* dec, u32* P, u32* arrivals) {
+                                                         u32 max_prims_per_leaf, Dec* dec, uint4* hot, u32* P, u32* arrivals) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     Node32 nd = load_node(nodes + i);
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* 
     bool mine_is_leaf = true;
     if (i == 0) {  // a single-leaf tree: the host reads S[0] of the root record
         store_dec(dec, mine);
+        store_hot(hot, mine, my_prims);
         P[0] = my_prims;
         return;
     }
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* 
         const u32 node = parents[me];
         if (!mine_is_leaf) {  // publish before signalling: the sibling's thread (or the emit pass) reads it
             store_dec(dec + me, mine);
+            store_hot(hot + me, mine, my_prims);
             P[me] = my_prims;
             __threadfence();
         }
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(COST_THREADS) cwbvh_cost_kernel(const Node32* 
         const Dec d = inner_dec(L, R, ha, num_primitives, max_prims_per_leaf);
         if (node == 0) {
             store_dec(dec, d);
+            store_hot(hot, d, num_primitives);
             P[0] = num_primitives;
             return;
         }
@@ -210,15 +219,19 @@ struct CostArgs {
     const u32* parents;
     u32 n_nodes, max_prims_per_leaf;
     Dec* dec;
-    u32* P;
-    u32* arrivals;
-    u32* queue[2];   // frontier lists, (n_nodes + 1) / 2 entries each
+    uint4* hot;
+    u32* arrivals;   // per inner node: arrivals in bits 0-1, "left / right child is a leaf" in bits 2 / 3, primitives of the children that arrived in bits 4-31
+    uint4* queue[2];  // frontier lists, (n_nodes + 1) / 2 entries each: {node, first_child | left_is_leaf << 30 | right_is_leaf << 31, primitives in the subtree, -}
     u32* qcount;     // [3], slot = round % 3
 };
 constexpr int FRONT_THREADS = 256;
+#ifndef OBVHS_FRONT_MIN_CTAS
+#define OBVHS_FRONT_MIN_CTAS 4  // 64 registers (73 unconstrained = 3 CTAs): the pass waits on memory, 1.42 -> 1.35 ms at 10 M triangles
+#endif
+constexpr int FRONT_MIN_CTAS = OBVHS_FRONT_MIN_CTAS;
 
 // appends `item` of every thread with `flag` to q (count in *qn): block scan + one atomic per call. Whole CTA must call.
-__device__ __forceinline__ void frontier_push(bool flag, u32 item, u32* q, u32* qn) {
+__device__ __forceinline__ void frontier_push(bool flag, uint4 item, uint4* q, u32* qn) {
     __shared__ u32 s_w[FRONT_THREADS / 32];
     __shared__ u32 s_base;
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -237,30 +250,64 @@ __device__ __forceinline__ void frontier_push(bool flag, u32 item, u32* q, u32* 
     if (flag) q[s_base + before + __popc(bal & ((1u << lane) - 1u))] = item;
 }
 
-// record of inner node `node` from its two finished children (leaf children are recomputed from their nodes)
-__device__ __forceinline__ void frontier_node(const CostArgs& a, u32 node) {
-    const Node32 me = load_node(a.nodes + node);
-    const u32 first = me.first_index;
-    const Node32 ln = load_node(a.nodes + first), rn = load_node(a.nodes + first + 1);
+// Child `child` (with `prims` primitives below it) is finished: count it at its parent and leave a note whether it is a leaf and
+// how many primitives it brings. The second arriver knows both children (siblings are adjacent, the left one odd:
+// bvh2/node.rs:154-180), what kind each is and the parent's primitive count, so whoever computes the parent can request
+// everything it needs -- its own box, and per child either the leaf node or the decision record -- in ONE round trip instead of
+// three dependent ones (node -> child nodes -> child records), and no per-node primitive count is read back at all.
+// (28 bits of primitives per word: the host refuses trees beyond 2^28 primitives.)
+__device__ __forceinline__ bool frontier_arrive(const CostArgs& a, u32 child, bool child_is_leaf, u32 prims, uint4& entry) {
+    const u32 parent = a.parents[child];
+    const bool left = (child & 1u) != 0;
+    const u32 mine = 1u | (child_is_leaf ? (left ? 4u : 8u) : 0u) | prims << 4;
+    const u32 old = atomicAdd(&a.arrivals[parent], mine);
+    if ((old & 3u) != 1u) return false;
+    entry = make_uint4(parent, left_sibling_id(child) | (((old | mine) >> 2) & 3u) << 30, (old >> 4) + prims, 0u);
+    return true;
+}
+
+// record of inner node e.x from its two finished children (leaf children are recomputed from their nodes)
+__device__ __forceinline__ void frontier_node(const CostArgs& a, const uint4 e) {
+    const u32 node = e.x, first = e.y & 0x3fffffffu;
+    const bool lleaf = (e.y >> 30) & 1u, rleaf = (e.y >> 31) & 1u;
+    // all reads first: 2 vectors for a leaf (its node), 4 + the primitive count for an inner child (its record)
+    const uint4* lsrc = lleaf ? reinterpret_cast<const uint4*>(a.nodes + first) : reinterpret_cast<const uint4*>(a.dec + first);
+    const uint4* rsrc = rleaf ? reinterpret_cast<const uint4*>(a.nodes + first + 1) : reinterpret_cast<const uint4*>(a.dec + first + 1);
+    const uint4* msrc = reinterpret_cast<const uint4*>(a.nodes + node);
+    const uint4 m0 = __ldcg(msrc), m1 = __ldcg(msrc + 1);
+    const uint4 l0 = __ldcg(lsrc), l1 = __ldcg(lsrc + 1), r0 = __ldcg(rsrc), r1 = __ldcg(rsrc + 1);
+    uint4 l2 = make_uint4(0, 0, 0, 0), l3 = l2, r2 = l2, r3 = l2;
+    if (!lleaf) {
+        l2 = __ldcg(lsrc + 2);
+        l3 = __ldcg(lsrc + 3);
+    }
+    if (!rleaf) {
+        r2 = __ldcg(rsrc + 2);
+        r3 = __ldcg(rsrc + 3);
+    }
+    auto as_node = [](const uint4 q0, const uint4 q1) {
+        Node32 n;
+        n.minx = __uint_as_float(q0.x); n.miny = __uint_as_float(q0.y); n.minz = __uint_as_float(q0.z); n.prim_count = q0.w;
+        n.maxx = __uint_as_float(q1.x); n.maxy = __uint_as_float(q1.y); n.maxz = __uint_as_float(q1.z); n.first_index = q1.w;
+        return n;
+    };
+    auto as_dec = [](const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3) {
+        Dec r;
+        r.cost[0] = __uint_as_float(q0.x); r.cost[1] = __uint_as_float(q0.y); r.cost[2] = __uint_as_float(q0.z); r.cost[3] = __uint_as_float(q0.w);
+        r.cost[4] = __uint_as_float(q1.x); r.cost[5] = __uint_as_float(q1.y); r.cost[6] = __uint_as_float(q1.z); r.meta_lo = q1.w;
+        r.meta_hi = q2.x; r.S[0] = q2.y; r.S[1] = q2.z; r.S[2] = q2.w;
+        r.S[3] = q3.x; r.S[4] = q3.y; r.S[5] = q3.z; r.S[6] = q3.w;
+        return r;
+    };
     Dec L, R;
-    u32 lp, rp;
-    if (ln.prim_count != 0) {
-        L = leaf_dec(ln);
-        lp = ln.prim_count;
-    } else {
-        L = load_dec_cg(a.dec + first);
-        lp = __ldcg(&a.P[first]);
-    }
-    if (rn.prim_count != 0) {
-        R = leaf_dec(rn);
-        rp = rn.prim_count;
-    } else {
-        R = load_dec_cg(a.dec + first + 1);
-        rp = __ldcg(&a.P[first + 1]);
-    }
-    const u32 num_primitives = lp + rp;
-    store_dec(a.dec + node, inner_dec(L, R, box_half_area(node_box(me)), num_primitives, a.max_prims_per_leaf));
-    a.P[node] = num_primitives;
+    if (lleaf) L = leaf_dec(as_node(l0, l1));
+    else L = as_dec(l0, l1, l2, l3);
+    if (rleaf) R = leaf_dec(as_node(r0, r1));
+    else R = as_dec(r0, r1, r2, r3);
+    const u32 num_primitives = e.z;
+    const Dec d = inner_dec(L, R, box_half_area(node_box(as_node(m0, m1))), num_primitives, a.max_prims_per_leaf);
+    store_dec(a.dec + node, d);
+    store_hot(a.hot + node, d, num_primitives);
 }
 
 // Below this many ready nodes a round is cheaper as plain climbing (the rest of the tree is a few thousand nodes, and every
@@ -268,44 +315,43 @@ __device__ __forceinline__ void frontier_node(const CostArgs& a, u32 node) {
 // second arriver, publishing with a fence as in cwbvh_cost_kernel.
 constexpr u32 FRONT_CLIMB_BELOW = 32768;
 
-__global__ void __launch_bounds__(FRONT_THREADS) cwbvh_cost_frontier_kernel(CostArgs a) {
+__global__ void __launch_bounds__(FRONT_THREADS, FRONT_MIN_CTAS) cwbvh_cost_frontier_kernel(CostArgs a) {
     cg::grid_group grid = cg::this_grid();
     const u32 nthreads = gridDim.x * blockDim.x;
     // round 0: every leaf arrives at its parent
     for (u32 base = blockIdx.x * blockDim.x; base < a.n_nodes; base += nthreads) {
         const u32 i = base + threadIdx.x;
         bool push = false;
-        u32 p = 0;
+        uint4 e = make_uint4(0, 0, 0, 0);
         if (i < a.n_nodes) {
             const u32 prim_count = __float_as_uint(__ldg(reinterpret_cast<const float4*>(a.nodes + i)).w);
             if (prim_count != 0) {
                 if (i == 0) {  // a single-leaf tree: the host reads S[0] of the root record
-                    store_dec(a.dec, leaf_dec(load_node(a.nodes)));
-                    a.P[0] = prim_count;
+                    const Dec d = leaf_dec(load_node(a.nodes));
+                    store_dec(a.dec, d);
+                    store_hot(a.hot, d, prim_count);
                 } else {
-                    p = a.parents[i];
-                    push = atomicAdd(&a.arrivals[p], 1u) == 1u;
+                    push = frontier_arrive(a, i, true, prim_count, e);
                 }
             }
         }
-        frontier_push(push, p, a.queue[0], &a.qcount[1]);
+        frontier_push(push, e, a.queue[0], &a.qcount[1]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[2] = 0;
     grid.sync();
     for (u32 round = 1;; round++) {
-        const u32* q = a.queue[(round - 1) & 1];
-        u32* qnext = a.queue[round & 1];
+        const uint4* q = a.queue[(round - 1) & 1];
+        uint4* qnext = a.queue[round & 1];
         const u32 n = __ldcg(&a.qcount[round % 3]);
         if (n == 0) break;
         if (n < FRONT_CLIMB_BELOW) {
             for (u32 idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += nthreads) {
-                u32 node = __ldcg(q + idx);
+                uint4 e = __ldcg(q + idx);
                 for (;;) {
-                    frontier_node(a, node);
-                    if (node == 0) break;
+                    frontier_node(a, e);
+                    if (e.x == 0) break;
                     __threadfence();
-                    node = a.parents[node];
-                    if (atomicAdd(&a.arrivals[node], 1u) == 0) break;  // the other child's thread will do this node
+                    if (!frontier_arrive(a, e.x, false, e.z, e)) break;  // the other child's thread will do the parent
                 }
             }
             break;
@@ -314,16 +360,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) cwbvh_cost_frontier_kernel(Cost
         for (u32 base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
             const u32 idx = base + threadIdx.x;
             bool push = false;
-            u32 p = 0;
+            uint4 e = make_uint4(0, 0, 0, 0);
             if (idx < n) {
-                const u32 node = __ldcg(q + idx);
-                frontier_node(a, node);
-                if (node != 0) {
-                    p = a.parents[node];
-                    push = atomicAdd(&a.arrivals[p], 1u) == 1u;
-                }
+                e = __ldcg(q + idx);
+                frontier_node(a, e);
+                if (e.x != 0) push = frontier_arrive(a, e.x, false, e.z, e);
             }
-            frontier_push(push, p, qnext, qn_next);
+            frontier_push(push, e, qnext, qn_next);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[(round + 2) % 3] = 0;  // the slot of round + 2; nobody reads or writes it now
         grid.sync();
@@ -340,14 +383,13 @@ struct Entry {
     Node32 n;
 };
 __device__ __forceinline__ u32 entry_meta(const Entry& e, u32 i) { return ((i < 4 ? e.meta_lo >> (8 * i) : e.meta_hi >> (8 * (i - 4)))) & 0xffu; }
-__device__ __forceinline__ void entry_load(Entry& e, const Node32* __restrict__ nodes, const Dec* __restrict__ dec, const u32* __restrict__ P) {
-    const uint4* dq = reinterpret_cast<const uint4*>(dec + e.node);
+__device__ __forceinline__ void entry_load(Entry& e, const Node32* __restrict__ nodes, const uint4* __restrict__ hot) {
     e.n = load_node(nodes + e.node);
-    uint4 q1 = __ldcg(dq + 1), q2 = __ldcg(dq + 2);
-    e.meta_lo = q1.w;
-    e.meta_hi = q2.x;
-    e.S0 = q2.y;
-    e.P = __ldcg(P + e.node);
+    const uint4 h = __ldcg(hot + e.node);
+    e.meta_lo = h.x;
+    e.meta_hi = h.y;
+    e.S0 = h.z;
+    e.P = h.w;
     if (e.n.prim_count != 0) {  // leaves have no stored record (see cwbvh_cost_kernel): all LEAF decisions, nothing below
         e.meta_lo = 0;
         e.meta_hi = 0;
@@ -367,8 +409,8 @@ __device__ __forceinline__ void entry_load(Entry& e, const Node32* __restrict__ 
 struct GroupOut {
     u32 x;  // CWBVH node index being written
 };
-__device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __restrict__ bvh2_prims, const Dec* __restrict__ dec,
-                               const u32* __restrict__ P, bool have, uint4 item, u32* __restrict__ next_queue_idx, uint4* __restrict__ next_queue,
+__device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __restrict__ bvh2_prims, const uint4* __restrict__ hot,
+                               bool have, uint4 item, u32* __restrict__ next_queue_idx, uint4* __restrict__ next_queue,
                                u32* queue_counter, uint4* __restrict__ out_nodes, u32* __restrict__ out_prims, int order_children, CwGlobals* g,
                                u32 gmask, int gl, u32* sbuf) {
     const int lane = threadIdx.x & 31, gbase = lane & ~7;
@@ -382,7 +424,7 @@ __device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __re
     e.n = Node32{0, 0, 0, 0, 0, 0, 0, 0};
     if (have && gl == 0) {
         e.node = item.y;
-        entry_load(e, nodes, dec, P);
+        entry_load(e, nodes, hot);
         e.expand = e.n.prim_count == 0 ? 1u : 0u;  // a leaf root is its own single child
     }
     // the wide node's own box (lane 0 holds the BVH2 node) and exponents: lanes 0..2 take one axis each
@@ -434,7 +476,7 @@ __device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __re
             e.node = d[0];
             e.idx = d[1] & 0xffu;
             if (d[1] & FRESH) {
-                entry_load(e, nodes, dec, P);  // ONE trip: node, decision record, primitive count
+                entry_load(e, nodes, hot);  // ONE trip: node, decision record, primitive count
                 e.expand = (entry_meta(e, e.idx) & 3u) == KIND_DISTRIBUTE ? 1u : 0u;
             } else {
                 e.meta_lo = d[2]; e.meta_hi = d[3]; e.S0 = d[4]; e.P = d[5];
@@ -636,8 +678,7 @@ __device__ void emit_wide_node(const Node32* __restrict__ nodes, const u32* __re
 struct EmitArgs {
     const Node32* nodes;
     const u32* bvh2_prims;
-    const Dec* dec;
-    const u32* P;
+    const uint4* hot;  // {meta_lo, meta_hi, S[0], P} per BVH2 node (store_hot)
     uint4* queue_a;  // work items {cwbvh node index, bvh2 node, child_base, prim_base}
     uint4* queue_b;
     uint4* out_nodes;
@@ -690,7 +731,7 @@ if (a.exact && have && gl == 0) {  // exact_node_aabbs[node_index_bvh8] = *aabb 
                 a.exact[2 * (size_t)item.x] = make_float4(lo.x, lo.y, lo.z, 0.f);
                 a.exact[2 * (size_t)item.x + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
             }
-                        emit_wide_node(a.nodes, a.bvh2_prims, a.dec, a.P, have, item, nullptr, nxt, &g->queue_count[level % 3], a.out_nodes, a.out_prims,
+                        emit_wide_node(a.nodes, a.bvh2_prims, a.hot, have, item, nullptr, nxt, &g->queue_count[level % 3], a.out_nodes, a.out_prims,
                            a.order_children, g, gmask, gl, sbuf);
         }
         grid.sync();
@@ -952,6 +993,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     const u32 n_nodes = (u32)bvh->node_count;
     DevBuf<u32> parents_tmp, P, arrivals;
+    DevBuf<uint4> hot;
     DevBuf<uint4> queue_a, queue_b;
     DevBuf<Dec> dec;
     DevBuf<CwGlobals> g;
@@ -964,7 +1006,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     std::optional<TraceScope> tsp;
     tsp.emplace(ctx, "  calculate_cost");
-    CU_TRY(ctx, P.alloc(n_nodes, s));
+    CU_TRY(ctx, hot.alloc(n_nodes, s));
     CU_TRY(ctx, arrivals.alloc(n_nodes, s));
     CU_TRY(ctx, dec.alloc(n_nodes, s));
     CU_TRY(ctx, g.alloc(1, s));
@@ -974,17 +1016,23 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     // small trees: the frontier kernel would switch to climbing after its first round anyway, and a plain launch is cheaper
     // than a cooperative one (kitchen, 114 k nodes: 0.11 vs 0.14 ms)
     if (n_nodes < 8 * FRONT_CLIMB_BELOW) {
-        cwbvh_cost_kernel<<<div_up(n_nodes, COST_THREADS), COST_THREADS, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, P.p, arrivals.p);
+        CU_TRY(ctx, P.alloc(n_nodes, s));
+        cwbvh_cost_kernel<<<div_up(n_nodes, COST_THREADS), COST_THREADS, 0, s>>>(bvh->nodes, parents, n_nodes, max_prims_per_leaf, dec.p, hot.p, P.p, arrivals.p);
         KERNEL_CHECK(ctx);
     } else {
-        DevBuf<u32> q0, q1, qcount;
+        if (bvh->prim_count >= ((size_t)1 << 28)) {  // frontier_arrive keeps primitive counts in 28 bits of the arrival word
+            OBVHS_SET_ERR(ctx, "bvh2_to_cwbvh: more than 2^28 primitives are not supported");
+            return OBVHS_ERR_UNSUPPORTED;
+        }
+        DevBuf<uint4> q0, q1;
+        DevBuf<u32> qcount;
         CU_TRY(ctx, q0.alloc((size_t)n_nodes / 2 + 1, s));
         CU_TRY(ctx, q1.alloc((size_t)n_nodes / 2 + 1, s));
         CU_TRY(ctx, qcount.alloc(4, s));
         CU_TRY(ctx, cudaMemsetAsync(qcount.p, 0, 16, s));
         CostArgs ca;
         ca.nodes = bvh->nodes; ca.parents = parents; ca.n_nodes = n_nodes; ca.max_prims_per_leaf = max_prims_per_leaf;
-        ca.dec = dec.p; ca.P = P.p; ca.arrivals = arrivals.p; ca.queue[0] = q0.p; ca.queue[1] = q1.p; ca.qcount = qcount.p;
+        ca.dec = dec.p; ca.hot = hot.p; ca.arrivals = arrivals.p; ca.queue[0] = q0.p; ca.queue[1] = q1.p; ca.qcount = qcount.p;
         int per_sm = 0;
         CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cwbvh_cost_frontier_kernel, FRONT_THREADS, 0));
         const int blocks = std::min(std::max(1, per_sm) * ctx->sm_count, std::max(1, div_up(n_nodes, FRONT_THREADS)));
@@ -1020,7 +1068,7 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
     }
     {
         EmitArgs ea;
-        ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.dec = dec.p; ea.P = P.p;
+        ea.nodes = bvh->nodes; ea.bvh2_prims = bvh->primitive_indices; ea.hot = hot.p;
         ea.queue_a = queue_a.p; ea.queue_b = queue_b.p; ea.out_nodes = reinterpret_cast<uint4*>(cw->nodes);
         ea.out_prims = cw->primitive_indices; ea.order_children = order_children ? 1 : 0; ea.expected = M; ea.g = g.p;
         ea.exact = reinterpret_cast<float4*>(cw->exact_node_aabbs);
