@@ -17,6 +17,15 @@ timeout -s KILL 1200 ncu --set full --clock-control none --import-source on -k r
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_s3_$TAG.log 2>&1
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"traverse_kernel" -s 3 -c 1 -f -o gpurun_out/prof_kitchen_traverse_$TAG \
     python bench.py --workload kitchen --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_kitchen_$TAG.log 2>&1
+# the other BASELINE configs and the layout passes (never under a profiler)
+timeout -s KILL 600 python bench.py --workload passes --steps 3 > gpurun_out/bench_passes_$TAG.log 2>&1
+timeout -s KILL 600 python bench.py --workload cornell --steps 10 > gpurun_out/bench_cornell_$TAG.log 2>&1
+timeout -s KILL 900 python bench.py --workload dynamic --steps 10 > gpurun_out/bench_dynamic_$TAG.log 2>&1
+# full captures of the two conversion kernels of the 10 M build (third build of trace_build.py)
+for k in cwbvh_cost_frontier_kernel cwbvh_emit_all_kernel; do
+  timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_${k}_$TAG \
+     python scripts/trace_build.py terrain 10008338 > gpurun_out/ncu_${k}_$TAG.log 2>&1
+done
 for wl in terrain kitchen; do
   timeout -s KILL 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \
      --log-file gpurun_out/build_kernels_${wl}_$TAG.csv python scripts/trace_build.py $wl 10008338 > gpurun_out/build_kernels_${wl}_$TAG.log 2>&1
