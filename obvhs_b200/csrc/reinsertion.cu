@@ -106,7 +106,7 @@ struct HeapFindStack {
 #endif
 template <bool NC, class Stack>
 __device__ __forceinline__ void find_reinsertion(const Node32* nodes, const u32* parents, u32 node_id, Stack& stk, u32& out_from, u32& out_to,
-                                                 float& out_diff FIND_DBG(, u32& dbg_visits, u32& dbg_pops, u32& dbg_load_cycles, u32& dbg_get_cycles)) {
+                                                 float& out_diff, const bool keep_next FIND_DBG(, u32& dbg_visits, u32& dbg_pops, u32& dbg_load_cycles, u32& dbg_get_cycles)) {
     const u32 cap1 = stk.cap() - 1u;
     u32 sp = 0;
     u32 best_to = 0;
@@ -132,11 +132,25 @@ __device__ __forceinline__ void find_reinsertion(const Node32* nodes, const u32*
     Node32 n_sib = sib_node, n_piv = piv_node;
     u32 n_next = 0;
     bool started = false;
+    // keep_next (rounds with at most one search per lane, where the longest search is the cost: -25 % on the kitchen's first
+    // round; with several searches per lane the extra path costs the 10 M scene's first rounds 3-10 %): the entry popped right
+    // after an inner node's two pushes is always its second child, with the best gain unchanged in between, so it stays in
+    // registers (no store / load round trip between learning first_index and requesting that child), and a pair that the pop test
+    // would reject anyway (the best gain only grows) is not pushed at all.
+    bool have_next = false;
+    float next_area = 0.0f;
+    u32 next_id = 0;
     for (;;) {
         float top_area_diff;
         u32 top_sibling_id;
         bool first = false, have;
-        if (sp == 0) {
+        if (have_next) {
+            top_area_diff = next_area;
+            top_sibling_id = next_id;
+            have_next = false;
+            have = true;
+            FIND_DBG(dbg_pops++;)
+        } else if (sp == 0) {
             if (started) {  // the level's stack ran empty: reinsertion.rs:315-326
                 if (pivot_id != parent_id) {
                     pivot_bbox = box_union(pivot_bbox, node_box(sib_node));
@@ -181,10 +195,18 @@ __device__ __forceinline__ void find_reinsertion(const Node32* nodes, const u32*
         }
         if (dst.prim_count == 0) {
             float child_area = reinsert_area + box_half_area(dbox);
-            stk.put(sp, child_area, dst.first_index);
-            sp = min(sp + 1u, cap1);
-            stk.put(sp, child_area, dst.first_index + 1);
-            sp = min(sp + 1u, cap1);
+            if (!keep_next) {
+                stk.put(sp, child_area, dst.first_index);
+                sp = min(sp + 1u, cap1);
+                stk.put(sp, child_area, dst.first_index + 1);
+                sp = min(sp + 1u, cap1);
+            } else if (!(child_area - node_area <= best_diff)) {
+                stk.put(sp, child_area, dst.first_index);
+                sp = min(sp + 1u, cap1);
+                have_next = true;
+                next_area = child_area;
+                next_id = dst.first_index + 1;
+            }
         }
     }
     u32 from = node_id;
@@ -604,6 +626,7 @@ __global__ void __launch_bounds__(RUN_THREADS, MIN_CTAS) reinsertion_run_kernel(
         // ---- K9 find_reinsertion for the first `count` candidates; gain keys: descending area_diff, ties by candidate rank
         u32* ghist = a.sort_scratch + pl.gain_off;
         hist_clear(s_hist);
+        const bool keep_next = pl.count <= nthreads;
         for (u32 j = tid; j < pl.count; j += nthreads) {
             u32 from, to;
             float diff;
@@ -612,16 +635,16 @@ __global__ void __launch_bounds__(RUN_THREADS, MIN_CTAS) reinsertion_run_kernel(
                                   gridDim.x * blockDim.x, a.heap_cap};
 #ifdef OBVHS_FIND_DEBUG
                 u32 dv = 0, dp = 0, dl = 0, dg = 0;
-                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, dv, dp, dl, dg);
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, keep_next, dv, dp, dl, dg);
 #else
-                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, keep_next);
 #endif
             } else {
                 LocalFindStack stk;
 #ifdef OBVHS_FIND_DEBUG
                 u32 dv = 0, dp = 0, dl = 0, dg = 0;
                 const long long c0 = clock64();
-                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, dv, dp, dl, dg);
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, keep_next, dv, dp, dl, dg);
                 const unsigned long long dc = (unsigned long long)(clock64() - c0);
                 if (a.find_dbg) {
                     atomicMax(a.find_dbg + round * 8, dc);
@@ -634,7 +657,7 @@ __global__ void __launch_bounds__(RUN_THREADS, MIN_CTAS) reinsertion_run_kernel(
                     atomicAdd(a.find_dbg + round * 8 + 7, (unsigned long long)dg);
                 }
 #else
-                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff);
+                find_reinsertion<NC>(a.nodes, a.parents, __ldcg(cand_ids + j), stk, from, to, diff, keep_next);
 #endif
             }
             a.r_from[j] = from;
