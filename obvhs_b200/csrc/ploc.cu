@@ -286,14 +286,15 @@ constexpr int FUSED_THREADS = 256, FUSED_ITEMS = 4, FUSED_TILE = FUSED_THREADS *
 // One tile of one fused iteration. TMA: the window arrives by a bulk copy (separate launches: `cur` was written by the previous
 // kernel); otherwise by ld.global.cg (ploc_mid_kernel: `cur` was written by other CTAs of the same launch). `bar_phase`: parity
 // of the mbarrier phase to wait for (a CTA of the mid kernel reuses its barrier tile after tile).
-template <int R, bool TMA>
+template <int R, bool TMA, int ITEMS = FUSED_ITEMS>
 __device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next, Node32* __restrict__ bvh_nodes, PlocGlobals* g, int parity, u32 depth,
                                                 u32 count, u32 insert_base, int r1, u32 tile, u64* st, const u32* __restrict__ free_slots,
                                                 u32 insert_start, Node32* win, signed char* sm, u64* bar, u32 bar_phase, u64* s_wsum, u64* s_excl) {
-    const u32 tiles = (count + FUSED_TILE - 1) / FUSED_TILE;
-    const u32 tile0 = tile * FUSED_TILE;
+    constexpr int TILE = FUSED_THREADS * ITEMS;  // (the mid kernel shrinks its tiles with the cluster count; the arrays are sized for FUSED_TILE)
+    const u32 tiles = (count + TILE - 1) / TILE;
+    const u32 tile0 = tile * TILE;
     const u32 lo = tile0 >= 2u * R ? tile0 - 2u * R : 0u;
-    const u32 hi = min(count, tile0 + FUSED_TILE + 2u * R);
+    const u32 hi = min(count, tile0 + TILE + 2u * R);
     if (TMA) {
         if (threadIdx.x == 0) {
             const u32 bytes = (hi - lo) * (u32)sizeof(Node32);
@@ -310,12 +311,12 @@ __device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next,
     // (striped over the threads: consecutive lanes read consecutive 32-byte boxes; the blocked mapping the scan below uses would
     // put a warp's 128-bit shared-memory loads on the same banks -- measured 2.5x slower at R = 6)
 #pragma unroll
-    for (int k = 0; k < FUSED_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const u32 j = k * FUSED_THREADS + threadIdx.x, i = tile0 + j;
         if (i < count) sm[j + R] = (signed char)search_offset<R>(win, (int)(i - lo), i, count, r1);
     }
     if (threadIdx.x < 2 * R) {
-        const int j = threadIdx.x < R ? (int)threadIdx.x : FUSED_TILE + (int)threadIdx.x;  // left halo 0..R-1, right halo TILE+R..TILE+2R-1
+        const int j = threadIdx.x < R ? (int)threadIdx.x : TILE + (int)threadIdx.x;  // left halo 0..R-1, right halo TILE+R..TILE+2R-1
         const long long i = (long long)tile0 - R + j;
         sm[j] = (i >= 0 && i < (long long)count) ? (signed char)search_offset<R>(win, (int)(i - lo), (u32)i, count, r1) : (signed char)0;
     }
@@ -324,10 +325,10 @@ __device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next,
     u32 flags = 0;
     u64 local = 0;
 #pragma unroll
-    for (int k = 0; k < FUSED_ITEMS; k++) {
-        const u32 i = tile0 + threadIdx.x * FUSED_ITEMS + k;
+    for (int k = 0; k < ITEMS; k++) {
+        const u32 i = tile0 + threadIdx.x * ITEMS + k;
         if (i < count) {
-            const int li = threadIdx.x * FUSED_ITEMS + k + R;
+            const int li = threadIdx.x * ITEMS + k + R;
             const int m = sm[li];
             const int mb = sm[li + m];
             const bool mutual = (m + mb) == 0;
@@ -407,15 +408,15 @@ __device__ __forceinline__ void ploc_fused_tile(const Node32* cur, Node32* next,
     __syncthreads();
     u64 run = *s_excl + thread_excl;
 #pragma unroll
-    for (int k = 0; k < FUSED_ITEMS; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const u32 f = (flags >> (2 * k)) & 3u;
         if (f & 1u) {
-            const u32 i = tile0 + threadIdx.x * FUSED_ITEMS + k;
+            const u32 i = tile0 + threadIdx.x * ITEMS + k;
             const u32 pos = (u32)(run & 0x7fffffffull);
             const Node32 left = load_node(win + (i - lo));
             if (f & 2u) {
                 const u32 mi = (u32)(run >> 31);
-                const int m = sm[threadIdx.x * FUSED_ITEMS + k + R];
+                const int m = sm[threadIdx.x * ITEMS + k + R];
                 const Node32 right = load_node(win + (i - lo) + m);
                 const u32 slot = child_slot(free_slots, insert_start, insert_base, mi);
                 store_node(bvh_nodes + slot, left);
@@ -494,14 +495,28 @@ __global__ void __launch_bounds__(FUSED_THREADS) ploc_mid_kernel(Node32* bufA, N
         const u32 insert_base = __ldcg(&g->state[parity].insert_index);
         if (count <= PLOC_TAIL) break;
         const int r1 = (R == 1 || depth < search_depth_threshold) ? 1 : 0;
-        const u32 tiles = (count + FUSED_TILE - 1) / FUSED_TILE;
         u64* st = scan_status + (size_t)(depth & 1u) * status_stride;
         u64* st_next = scan_status + (size_t)((depth + 1) & 1u) * status_stride;
-        for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < tiles; t += gridDim.x * blockDim.x) st_next[t] = 0;  // next iteration's scan state
-        // fused search + merge, tiles dealt round-robin (tile t to CTA t % gridDim.x): the look-back only waits for running CTAs
-        for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-            ploc_fused_tile<R, false>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm, nullptr,
-                                      0u, s_wsum, &s_excl);
+        for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < (count + FUSED_THREADS - 1) / FUSED_THREADS; t += gridDim.x * blockDim.x)
+            st_next[t] = 0;  // next iteration's scan state (for the smallest tile it may choose)
+        // fused search + merge, tiles dealt round-robin (tile t to CTA t % gridDim.x): the look-back only waits for running CTAs.
+        // An iteration costs a grid barrier plus the time of the tiles one CTA gets, so the tiles shrink with the cluster count:
+        // once every CTA has at most one tile, 256 clusters per tile instead of 1024 cut its serial part by four (PLOC iterations of
+        // the 10 M-triangle build 1.87 -> 1.66 ms; moving the two thresholds by 2-8x changes nothing measurable).
+        const u32 one_item = gridDim.x * FUSED_THREADS;  // clusters the grid covers with one cluster per thread
+        if (count <= one_item) {
+            for (u32 tile = blockIdx.x; tile < (count + FUSED_THREADS - 1) / FUSED_THREADS; tile += gridDim.x)
+                ploc_fused_tile<R, false, 1>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm,
+                                             nullptr, 0u, s_wsum, &s_excl);
+        } else if (count <= 2 * one_item) {
+            for (u32 tile = blockIdx.x; tile < (count + 2 * FUSED_THREADS - 1) / (2 * FUSED_THREADS); tile += gridDim.x)
+                ploc_fused_tile<R, false, 2>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm,
+                                             nullptr, 0u, s_wsum, &s_excl);
+        } else {
+            for (u32 tile = blockIdx.x; tile < (count + FUSED_TILE - 1) / FUSED_TILE; tile += gridDim.x)
+                ploc_fused_tile<R, false>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm,
+                                          nullptr, 0u, s_wsum, &s_excl);
+        }
         grid.sync();
         Node32* tmp = cur;
         cur = next;
@@ -677,7 +692,7 @@ cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, 
         if (per_sm < 1) per_sm = 1;
     }
     // as few CTAs as the work needs: the cost of a grid-wide barrier grows with the number of participants
-    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, FUSED_TILE)));
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, FUSED_THREADS)));
     void* args[] = {&cur, &next, &bvh_nodes, &g, &parity, &depth, &thr, &scan_status, &status_stride, &free_slots, &insert_start};
     return cudaLaunchCooperativeKernel((void*)ploc_mid_kernel<R>, dim3(blocks), dim3(FUSED_THREADS), args, 0, ctx->stream);
 }
