@@ -18,9 +18,12 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 #ifndef OBVHS_SORT_CTAS64
 #define OBVHS_SORT_CTAS64 3
 #endif
+#ifndef OBVHS_SORT_ITEMS32
+#define OBVHS_SORT_ITEMS32 8
+#endif
 template <typename K>
 struct SortCfg {
-    static constexpr int ITEMS = sizeof(K) == 8 ? OBVHS_SORT_ITEMS64 : 8;
+    static constexpr int ITEMS = sizeof(K) == 8 ? OBVHS_SORT_ITEMS64 : OBVHS_SORT_ITEMS32;
     static constexpr int TILE = SORT_THREADS * ITEMS;
     static constexpr int MIN_CTAS = sizeof(K) == 8 ? OBVHS_SORT_CTAS64 : 4;
 };
