@@ -218,7 +218,7 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
         : "memory");
 }
 
-constexpr int SEARCH_TILE = 256;  // (granularity of the scan-status allocation)
+constexpr int SEARCH_TILE = 128;  // (granularity of the scan-status allocation: the smallest tile any kernel variant uses)
 
 __device__ __forceinline__ Box smem_box(const Node32* w, int j) {
     const float4* q = reinterpret_cast<const float4*>(w + j);
@@ -281,7 +281,13 @@ __device__ __forceinline__ u32 child_slot(const u32* __restrict__ free_slots, u3
 // All loop state lives on the device (g->state[parity], g->fused_*): the host enqueues several iterations back to back, sized
 // for the last count it knows (CTAs beyond the live tiles exit), and reads the state back once per batch instead of once per
 // iteration. `depth` is the iteration this launch would be; a launch does nothing once g->fused_stop is set.
-constexpr int FUSED_THREADS = 256, FUSED_ITEMS = 4, FUSED_TILE = FUSED_THREADS * FUSED_ITEMS;
+#ifndef OBVHS_FUSED_THREADS
+#define OBVHS_FUSED_THREADS 256
+#endif
+#ifndef OBVHS_FUSED_ITEMS
+#define OBVHS_FUSED_ITEMS 4
+#endif
+constexpr int FUSED_THREADS = OBVHS_FUSED_THREADS, FUSED_ITEMS = OBVHS_FUSED_ITEMS, FUSED_TILE = FUSED_THREADS * FUSED_ITEMS;
 
 // One tile of one fused iteration. TMA: the window arrives by a bulk copy (separate launches: `cur` was written by the previous
 // kernel); otherwise by ld.global.cg (ploc_mid_kernel: `cur` was written by other CTAs of the same launch). `bar_phase`: parity
