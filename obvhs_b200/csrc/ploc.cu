@@ -484,6 +484,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) ploc_fused_kernel(Node32* buf0,
 // round-robin (tile t to CTA t % gridDim.x), so the merge scan's look-back only ever waits for CTAs that are running.
 // The window is loaded with plain L2 loads (the clusters were written by other CTAs of this launch).
 // g->state[2] receives {count, insert_index} bookkeeping as usual; g->mid_depth / mid_parity report where the loop stopped.
+#ifndef OBVHS_MID_SHRINK
+#define OBVHS_MID_SHRINK 1
+#endif
 constexpr int PLOC_TAIL = 2048;  // clusters the single-CTA tail kernel takes over at
 constexpr u32 PLOC_MID_MAX = 1u << 20;
 template <int R>
@@ -510,11 +513,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) ploc_mid_kernel(Node32* bufA, N
         // once every CTA has at most one tile, 256 clusters per tile instead of 1024 cut its serial part by four (PLOC iterations of
         // the 10 M-triangle build 1.87 -> 1.66 ms; moving the two thresholds by 2-8x changes nothing measurable).
         const u32 one_item = gridDim.x * FUSED_THREADS;  // clusters the grid covers with one cluster per thread
-        if (count <= one_item) {
+        if (OBVHS_MID_SHRINK && count <= one_item) {
             for (u32 tile = blockIdx.x; tile < (count + FUSED_THREADS - 1) / FUSED_THREADS; tile += gridDim.x)
                 ploc_fused_tile<R, false, 1>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm,
                                              nullptr, 0u, s_wsum, &s_excl);
-        } else if (count <= 2 * one_item) {
+        } else if (OBVHS_MID_SHRINK && count <= 2 * one_item) {
             for (u32 tile = blockIdx.x; tile < (count + 2 * FUSED_THREADS - 1) / (2 * FUSED_THREADS); tile += gridDim.x)
                 ploc_fused_tile<R, false, 2>(cur, next, bvh_nodes, g, parity, depth, count, insert_base, r1, tile, st, free_slots, insert_start, win, sm,
                                              nullptr, 0u, s_wsum, &s_excl);
@@ -698,7 +701,7 @@ cudaError_t launch_mid(ObvhsContext* ctx, u32 count, Node32* cur, Node32* next, 
         if (per_sm < 1) per_sm = 1;
     }
     // as few CTAs as the work needs: the cost of a grid-wide barrier grows with the number of participants
-    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, FUSED_THREADS)));
+    const int blocks = std::min(per_sm * ctx->sm_count, std::max(1, div_up(count, OBVHS_MID_SHRINK ? FUSED_THREADS : FUSED_TILE)));
     void* args[] = {&cur, &next, &bvh_nodes, &g, &parity, &depth, &thr, &scan_status, &status_stride, &free_slots, &insert_start};
     return cudaLaunchCooperativeKernel((void*)ploc_mid_kernel<R>, dim3(blocks), dim3(FUSED_THREADS), args, 0, ctx->stream);
 }
