@@ -289,11 +289,13 @@ struct RoundBarrier {
         if (threadIdx.x == 0) {
             gen++;
             __threadfence();
-            atomicAdd(counter, 1u);
-            const u32 target = gen * k;
-            while (*reinterpret_cast<volatile u32*>(counter) < target) {
+            if (k > 1) {  // (a round of ONE CTA only needs the fence: it still invalidates the SM's L1 for the words atomics changed)
+                atomicAdd(counter, 1u);
+                const u32 target = gen * k;
+                while (*reinterpret_cast<volatile u32*>(counter) < target) {
+                }
+                __threadfence();
             }
-            __threadfence();
         }
         __syncthreads();
     }
