@@ -99,6 +99,12 @@ struct HeapFindStack {
 // addresses are known one level ahead, the tree is read-only in this phase, and the values are consumed only where the reference
 // reads them. The first stack entry of a level (always the sibling) skips the push/pop round trip through the stack.
 // -DOBVHS_FIND_DEBUG (build.build_variant) adds per-round search statistics to the OBVHS_TRACE print-out.
+#ifndef OBVHS_RANK_SORT_MAX
+#define OBVHS_RANK_SORT_MAX 6144  // (the keys must fit the sort tile's shared memory: 26 KB)
+#endif
+#ifndef OBVHS_RANK_LANES
+#define OBVHS_RANK_LANES 8
+#endif
 #ifdef OBVHS_FIND_DEBUG
 #define FIND_DBG(...) __VA_ARGS__
 #else
@@ -335,7 +341,7 @@ __device__ __forceinline__ void round_sort(u32*& keys, u32*& keys_alt, u32*& val
 // COUNTING. Every CTA of the round stages all n keys in shared memory and ranks its own slice of them -- rank(i) = #{j : k_j <
 // k_i} + #{j < i : k_j == k_i} -- then scatters straight to the sorted position: one phase, no passes, no histograms. The O(n^2)
 // compares are spread over the round's CTAs (n = 4556 on 18 CTAs: 4.5 k compares per thread).
-constexpr u32 RANK_SORT_MAX = 2048;  // beyond this the four radix passes are cheaper (measured: 4555 keys 46 us by counting, 20 us by radix)
+constexpr u32 RANK_SORT_MAX = OBVHS_RANK_SORT_MAX;  // beyond this the four radix passes are cheaper (one lane per key: 4555 keys 46 us by counting, 20 us by radix)
 __device__ __forceinline__ void rank_sort(const u32* keys, const u32* vals, u32* vals_out, u32 n, RoundBarrier& bar, unsigned char* smem_raw) {
     u32* sk = reinterpret_cast<u32*>(smem_raw);
     const u32 n4 = (n + 3u) & ~3u;
@@ -343,11 +349,20 @@ __device__ __forceinline__ void rank_sort(const u32* keys, const u32* vals, u32*
     __syncthreads();
     const u32 nthreads = bar.k * blockDim.x;
     const uint4* sk4 = reinterpret_cast<const uint4*>(sk);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+    // S = 1, 2, 4 or 8 adjacent lanes share one key when the round has the threads for it: each scans a slice of the keys.
+    // Measured on the 1 M-triangle dynamic frames (16 rounds of 640-20 k candidates): 1.42 -> 1.27 ms per frame against one lane per
+    // key up to 2048 keys and four radix passes beyond (2048 keys x 8 lanes 1.31 ms, 4096 x 4 1.34, 4096 x 8 1.29, 6144 x 8 1.27)
+    u32 S = 1;
+    while (S < OBVHS_RANK_LANES && 2 * S * n <= nthreads) S *= 2;
+    const u32 part = threadIdx.x & (S - 1u);
+    const u32 q4 = n4 / 4, per = (q4 + S - 1) / S, j4_lo = part * per, j4_hi = min(q4, j4_lo + per);
+    for (u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) / S; i0 < ((n + 31u) & ~31u); i0 += nthreads / S) {  // warp-uniform trip count
+        const bool live = i0 < n;
+        const u32 i = live ? i0 : 0u;
         const u32 ki = sk[i];
         u32 rank = 0;
         // keys before i count when <=, keys after i when < (a stable rank); four keys per shared-memory load
-        for (u32 j4 = 0; j4 < n4 / 4; j4++) {
+        for (u32 j4 = j4_lo; j4 < j4_hi; j4++) {
             const uint4 k = sk4[j4];
             const u32 j = j4 * 4;
             rank += (k.x < ki || (k.x == ki && j < i)) ? 1u : 0u;
@@ -355,7 +370,8 @@ __device__ __forceinline__ void rank_sort(const u32* keys, const u32* vals, u32*
             rank += (k.z < ki || (k.z == ki && j + 2 < i)) ? 1u : 0u;
             rank += (k.w < ki || (k.w == ki && j + 3 < i)) ? 1u : 0u;
         }
-        vals_out[rank] = __ldcg(vals + i);
+        for (u32 o = 1; o < S; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (live && part == 0) vals_out[rank] = __ldcg(vals + i);
     }
     bar.sync();
 }
@@ -729,7 +745,10 @@ static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<Rou
     int grid = 1;
     for (RoundPlan& p : plan) {
         if (p.count == 0) continue;
-        const size_t want = std::max<size_t>((p.count + 127) / 128, (std::max<size_t>(p.m, p.count) + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE);
+        size_t want = std::max<size_t>((p.count + 127) / 128, (std::max<size_t>(p.m, p.count) + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE);
+        // the counting sort (up to RANK_SORT_MAX keys) costs n / S comparisons per thread with S lanes per key: give it eight lanes per key
+        // from 512 keys on, where it is the longest phase of the round
+        if (p.m >= 512 && p.m <= RANK_SORT_MAX) want = std::max<size_t>(want, (p.m * OBVHS_RANK_LANES + RUN_THREADS - 1) / RUN_THREADS);
         p.blocks = (u32)std::max<size_t>(1, std::min<size_t>(want, (size_t)resident));
         grid = std::max(grid, (int)p.blocks);
         const size_t tiles_c = (p.m + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE, tiles_g = (p.count + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE;
