@@ -19,9 +19,10 @@ from .api import (  # noqa: F401
     build_cwbvh_from_tris,
     bvh2_to_cwbvh,
     compute_rebuild_path_flags,
+    nccl_unique_id,
     presplit_tris,
     ray_new,
     split_aabbs_precise,
     split_aabbs_preset,
 )
-from .types import make_ray_args, make_rays, ray_args_of, safe_inverse  # noqa: F401
+from .types import RAY_HIT, RAY_HIT8, make_ray_args, make_rays, ray_args_of, safe_inverse  # noqa: F401
