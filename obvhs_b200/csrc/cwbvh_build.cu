@@ -770,9 +770,10 @@ struct OrderArgs {
     const float4* prim_aabbs;     // the primitives' boxes (Boundable::aabb), two float4 each
     const u32* primitive_indices;
     int direct_layout;
+    u32 n_prims;                  // number of boxes in prim_aabbs
     u32* queue[2];
     u32* qcount;                  // [3]
-    u32* error;                   // 1: a child could not be assigned (non-finite centres): the reference asserts
+    u32* error;                   // 1: a child could not be assigned (non-finite centres): the reference asserts; 2: a primitive index beyond prim_aabbs
 };
 constexpr int ORDER_THREADS = 256;
 __global__ void __launch_bounds__(ORDER_THREADS) cwbvh_order_children_kernel(OrderArgs a) {
@@ -836,6 +837,10 @@ __global__ void __launch_bounds__(ORDER_THREADS) cwbvh_order_children_kernel(Ord
                 for (u32 i = 0; i < count; i++) {
                     u32 pi = start + i;
                     if (!a.direct_layout) pi = __ldg(a.primitive_indices + pi);
+                    if (pi >= a.n_prims) {  // the reference would panic on the slice index
+                        *a.error = 2;
+                        break;
+                    }
                     const float4 lo = __ldg(a.prim_aabbs + 2 * (size_t)pi), hi = __ldg(a.prim_aabbs + 2 * (size_t)pi + 1);
                     b = box_union(b, Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
                 }
@@ -1101,7 +1106,6 @@ int bvh2_to_cwbvh_device(ObvhsContext* ctx, const ObvhsBvh2* bvh, u32 max_prims_
 // CwBvh::order_children(&mut self, primitives, direct_layout) (src/cwbvh/mod.rs:520-524) with the primitives given as their AABBs
 int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsAabb* d_prim_aabbs, size_t n_prims, bool direct_layout) {
     if (bvh->node_count == 0) return OBVHS_OK;
-    (void)n_prims;
     cudaStream_t s = ctx->stream;
     DevBuf<u32> q0, q1, qcount;
     CU_TRY(ctx, q0.alloc(bvh->node_count, s));
@@ -1114,6 +1118,7 @@ int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsA
     a.prim_aabbs = reinterpret_cast<const float4*>(d_prim_aabbs);
     a.primitive_indices = bvh->primitive_indices;
     a.direct_layout = direct_layout ? 1 : 0;
+    a.n_prims = (u32)std::min<size_t>(n_prims, 0xffffffffu);
     a.queue[0] = q0.p;
     a.queue[1] = q1.p;
     a.qcount = qcount.p;
@@ -1131,6 +1136,10 @@ int cwbvh_order_children_device(ObvhsContext* ctx, ObvhsCwBvh* bvh, const ObvhsA
     u32* h = reinterpret_cast<u32*>(ctx->pinned);
     CU_TRY(ctx, cudaMemcpyAsync(h, qcount.p + 3, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (h[0] == 2) {
+        OBVHS_SET_ERR(ctx, "order_children: a leaf refers to a primitive beyond the %zu boxes given (wrong direct_layout?); the tree may be partly reordered", n_prims);
+        return OBVHS_ERR_INVALID_ARG;
+    }
     if (h[0] != 0) {
         OBVHS_SET_ERR(ctx, "order_children: a child could not be assigned to a slot (non-finite boxes? the reference asserts here)");
         return OBVHS_ERR_NAN_INPUT;

@@ -837,3 +837,5 @@ def test_cwbvh_order_children_bit_exact(api, scenes, scene, exact):
         w.order_children(pa, direct)
         g.order_children(pa, direct)
         assert g.download()[0].tobytes() == w.get()[0].tobytes()
+    with pytest.raises(api.ObvhsError):  # fewer boxes than the leaves refer to: reported, not read out of bounds
+        g.order_children(aabbs[: max(1, aabbs.shape[0] // 2)], False)
