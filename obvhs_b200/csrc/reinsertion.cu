@@ -105,6 +105,9 @@ struct HeapFindStack {
 #ifndef OBVHS_RANK_LANES
 #define OBVHS_RANK_LANES 8
 #endif
+#ifndef OBVHS_FIND_PER_CTA
+#define OBVHS_FIND_PER_CTA 128  // searches per 256-thread CTA of a round (64: dynamic frames +1 %, kitchen build -2 %; 256: -3 % / 0; 16 rank lanes: +3 % / -2 %)
+#endif
 #ifdef OBVHS_FIND_DEBUG
 #define FIND_DBG(...) __VA_ARGS__
 #else
@@ -745,7 +748,7 @@ static int reinsertion_launch(ObvhsContext* ctx, ObvhsBvh2* bvh, std::vector<Rou
     int grid = 1;
     for (RoundPlan& p : plan) {
         if (p.count == 0) continue;
-        size_t want = std::max<size_t>((p.count + 127) / 128, (std::max<size_t>(p.m, p.count) + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE);
+        size_t want = std::max<size_t>((p.count + OBVHS_FIND_PER_CTA - 1) / OBVHS_FIND_PER_CTA, (std::max<size_t>(p.m, p.count) + SortCfg<u32>::TILE - 1) / SortCfg<u32>::TILE);
         // the counting sort (up to RANK_SORT_MAX keys) costs n / S comparisons per thread with S lanes per key: give it eight lanes per key
         // from 512 keys on, where it is the longest phase of the round
         if (p.m >= 512 && p.m <= RANK_SORT_MAX) want = std::max<size_t>(want, (p.m * OBVHS_RANK_LANES + RUN_THREADS - 1) / RUN_THREADS);
