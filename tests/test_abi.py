@@ -38,6 +38,27 @@ def test_python_bindings_cover_header(lib_path):
     api.load_library()
 
 
+def declared_arity():
+    """name -> number of parameters, from the header's prototypes."""
+    text = open(os.path.join(ROOT, "include", "obvhs_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(obvhs_cuda_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = " ".join(args.split())
+        out[name] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_python_bindings_have_the_header_arity():
+    # a ctypes signature with a missing or extra argument corrupts the call silently: compare every binding with its prototype
+    from obvhs_b200 import api
+
+    arity = declared_arity()
+    assert set(arity) == set(api.SIGNATURES)
+    wrong = {n: (len(sig[1]), arity[n]) for n, sig in api.SIGNATURES.items() if len(sig[1]) != arity[n]}
+    assert wrong == {}
+
+
 def test_presets_match_reference_table(lib_path):
     # src/lib.rs:233-305
     from obvhs_b200.api import BvhBuildParams, PlocSearchDistance, SortPrecision
@@ -56,7 +77,9 @@ def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text('#include "obvhs_cuda.h"\n_Static_assert(sizeof(ObvhsCwBvhNode)==80,"");_Static_assert(sizeof(ObvhsRay)==64,"");\n'
                    '_Static_assert(sizeof(ObvhsBvh2Node)==48,"");_Static_assert(sizeof(ObvhsAabb)==32,"");\n'
-                   '_Static_assert(sizeof(ObvhsTriangle)==48,"");_Static_assert(sizeof(ObvhsRayHit)==16,"");int main(void){return 0;}\n')
+                   '_Static_assert(sizeof(ObvhsTriangle)==48,"");_Static_assert(sizeof(ObvhsRayHit)==16,"");\n'
+                   '_Static_assert(sizeof(ObvhsRayNew)==32,"");_Static_assert(sizeof(ObvhsRayOd)==24,"");_Static_assert(sizeof(ObvhsRayHit8)==8,"");\n'
+                   'int main(void){return 0;}\n')
     subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
 
 
